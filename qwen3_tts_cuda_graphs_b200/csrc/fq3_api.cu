@@ -1,0 +1,663 @@
+// fq3_api.cu — host side of libfq3.so: engine construction, phase-program builders, C ABI (include/fq3.h).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fq3.h"
+#include "fq3_kernel.cuh"
+
+using namespace fq3;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return -code;
+}
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return fail(FQ3_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                                  std::to_string(__LINE__));                                         \
+  } while (0)
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct StackHost {
+  fq3_stack_desc d;
+  std::vector<uint64_t> offs;
+  int qdim() const { return d.n_q_heads * d.head_dim; }
+  int kvdim() const { return d.n_kv_heads * d.head_dim; }
+  int qkvdim() const { return qdim() + 2 * kvdim(); }
+  int kmax() const { return std::max(std::max(d.hidden, d.inter), qdim()); }
+};
+
+}  // namespace
+
+struct fq3_engine {
+  int dev = 0, G = 0;
+  size_t smem_max = 0;
+  fq3_model_desc desc{};
+  StackHost tk, pr;
+  std::vector<uint64_t> lm_head_offs, pred_embed_offs;
+  int max_rows = 8;
+  int ncb = 15;
+  void* bufs[kNumBufs] = {};
+  int ld[kNumBufs] = {};
+  StackRt rt[2]{};
+  StreamState* d_st = nullptr;
+  std::vector<StreamState> h_st;
+  float* attn_part = nullptr;
+  unsigned* attn_cnt = nullptr;
+  unsigned* grid_bar = nullptr;
+  int* err_host = nullptr;
+  int* err_dev = nullptr;
+  float* pred_logits_all = nullptr;
+  uint8_t* seen_scratch = nullptr;
+  Phase *d_frames = nullptr, *d_pred = nullptr, *d_talker = nullptr, *d_prefill = nullptr, *d_linear = nullptr;
+  int n_frames_ph = 0, n_pred_ph = 0, n_talker_ph = 0, n_prefill_ph = 0;
+  int64_t launches = 0;
+  unsigned long long watchdog_ns = 4000000000ull;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+template <class T>
+int dalloc(fq3_engine* e, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 16)));
+  if (zero) CK(cudaMemset(q, 0, std::max<size_t>(n * sizeof(T), 16)));
+  e->owned.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+uint32_t off16(uint64_t byte_off) { return (uint32_t)(byte_off >> 4); }
+
+// One decoder layer = 5 phases.
+void push_layer(std::vector<Phase>& v, const StackHost& s, uint8_t stack, int layer, bool rows2, uint8_t aux,
+                bool keep) {
+  const uint64_t* o = &s.offs[(size_t)layer * 8];
+  const uint16_t r2 = rows2 ? F_ROWS2 : 0, kp = keep ? F_L2_KEEP : 0;
+  const uint8_t X = stack == ST_TALKER ? BUF_TX : BUF_PX, Q = stack == ST_TALKER ? BUF_TQKV : BUF_PQKV,
+                A = stack == ST_TALKER ? BUF_TATT : BUF_PATT, C = stack == ST_TALKER ? BUF_TACT : BUF_PACT;
+  Phase p{};
+  p.stack = stack; p.layer = (uint8_t)layer; p.aux = aux;
+  // 1. RMSNorm + fused QKV projection
+  p.type = PH_GEMV; p.flags = F_PRENORM | r2 | kp; p.in_buf = X; p.out_buf = Q; p.res_buf = 0;
+  p.w_off = off16(o[1]); p.g_off = off16(o[0]); p.b_off = 0; p.N = s.qkvdim(); p.K = s.d.hidden;
+  v.push_back(p);
+  // 2. q/k norm + RoPE + KV append + attention
+  p.type = PH_ATTN; p.flags = r2; p.in_buf = Q; p.out_buf = A; p.w_off = 0; p.g_off = off16(o[2]); p.b_off = off16(o[3]);
+  p.N = 0; p.K = 0;
+  v.push_back(p);
+  // 3. o_proj + residual
+  p.type = PH_GEMV; p.flags = F_RESID | r2 | kp; p.in_buf = A; p.out_buf = X; p.res_buf = X;
+  p.w_off = off16(o[4]); p.g_off = 0; p.b_off = 0; p.N = s.d.hidden; p.K = s.qdim();
+  v.push_back(p);
+  // 4. RMSNorm + gate/up + SiLU*mul
+  p.flags = F_PRENORM | F_SWIGLU | r2 | kp; p.in_buf = X; p.out_buf = C; p.res_buf = 0;
+  p.w_off = off16(o[6]); p.g_off = off16(o[5]); p.N = 2 * s.d.inter; p.K = s.d.hidden;
+  v.push_back(p);
+  // 5. down_proj + residual
+  p.flags = F_RESID | r2 | kp; p.in_buf = C; p.out_buf = X; p.res_buf = X;
+  p.w_off = off16(o[7]); p.g_off = 0; p.N = s.d.hidden; p.K = s.d.inter;
+  v.push_back(p);
+}
+
+void push_predictor(std::vector<Phase>& v, const fq3_engine* e, bool only) {
+  for (int i = 0; i < e->ncb; ++i) {
+    const bool r2 = (i == 0);
+    if (e->desc.has_s2m) {
+      Phase p{};
+      p.type = PH_GEMV; p.stack = ST_PRED; p.aux = (uint8_t)i; p.flags = F_BIAS | F_L2_KEEP | (r2 ? F_ROWS2 : 0);
+      p.in_buf = BUF_PIN; p.out_buf = BUF_PX; p.w_off = off16(e->desc.s2m_w_off); p.b_off = off16(e->desc.s2m_b_off);
+      p.N = e->pr.d.hidden; p.K = e->tk.d.hidden;
+      v.push_back(p);
+    }
+    for (int l = 0; l < e->pr.d.n_layers; ++l) push_layer(v, e->pr, ST_PRED, l, r2, (uint8_t)i, true);
+    Phase h{};
+    h.type = PH_GEMV; h.stack = ST_PRED; h.aux = (uint8_t)i;
+    h.flags = F_PRENORM | F_OUT_F32 | F_L2_KEEP | (r2 ? F_ROWS2 : 0);
+    h.in_buf = BUF_PX; h.out_buf = BUF_LOGITS; h.w_off = off16(e->lm_head_offs[i]);
+    h.g_off = off16(e->pr.d.final_norm_off); h.N = e->pr.d.vocab; h.K = e->pr.d.hidden;
+    v.push_back(h);
+    Phase s{};
+    s.type = PH_SAMPLE; s.stack = ST_PRED; s.aux = (uint8_t)i; s.kind = only ? SMP_PRED_ONLY : SMP_PRED;
+    s.flags = r2 ? F_ROWS2 : 0;
+    v.push_back(s);
+  }
+}
+
+void push_talker(std::vector<Phase>& v, const fq3_engine* e, bool last_row_head) {
+  for (int l = 0; l < e->tk.d.n_layers; ++l) push_layer(v, e->tk, ST_TALKER, l, false, 0, false);
+  Phase h{};
+  h.type = PH_GEMV; h.stack = ST_TALKER;
+  h.flags = F_PRENORM | F_OUT_F32 | F_WRITE_NORMED | (last_row_head ? F_LAST_ROW : 0);
+  h.in_buf = BUF_TX; h.out_buf = BUF_LOGITS; h.w_off = off16(e->desc.codec_head_off);
+  h.g_off = off16(e->tk.d.final_norm_off); h.N = e->tk.d.vocab; h.K = e->tk.d.hidden;
+  v.push_back(h);
+}
+
+int upload(fq3_engine* e, const std::vector<Phase>& v, Phase** d) {
+  if (dalloc(e, d, v.size(), false)) return -1;
+  if (cudaMemcpy(*d, v.data(), v.size() * sizeof(Phase), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  return 0;
+}
+
+void fill_common(fq3_engine* e, LaunchParams& p) {
+  p.arena = reinterpret_cast<const uint8_t*>(e->desc.arena);
+  for (int i = 0; i < kNumBufs; ++i) { p.bufs[i] = e->bufs[i]; p.ld[i] = e->ld[i]; }
+  p.stacks[0] = e->rt[0];
+  p.stacks[1] = e->rt[1];
+  p.st = e->d_st;
+  p.attn_part = e->attn_part;
+  p.attn_cnt = e->attn_cnt;
+  p.grid_bar = e->grid_bar;
+  p.err = e->err_dev;
+  p.n_code_groups = e->desc.n_code_groups;
+  p.eos_id = e->desc.eos_id;
+  p.has_s2m = e->desc.has_s2m;
+  p.max_frames = e->desc.max_frames;
+  p.codec_embed = reinterpret_cast<const bf16*>(p.arena + e->desc.codec_embed_off);
+  for (int i = 0; i < e->ncb; ++i) p.pred_embeds[i] = reinterpret_cast<const bf16*>(p.arena + e->pred_embed_offs[i]);
+  p.pred_logits_all = nullptr;
+  p.pos_override = -1;
+  p.watchdog_ns = e->watchdog_ns;
+  p.n_iters = 1;
+  p.stream0 = 0;
+}
+
+int check_device_fault(fq3_engine* e) {
+  if (e->err_host && e->err_host[0] != 0) {
+    char b[256];
+    snprintf(b, sizeof b, "device watchdog fault: code=%d cta=%d phase=%d detail=%d (1=grid barrier 2=ring full-wait "
+                          "3=ring empty-wait 4=frame handshake 5=bad phase)",
+             e->err_host[0], e->err_host[1], e->err_host[2], e->err_host[3]);
+    return fail(FQ3_E_DEVICE_FAULT, b);
+  }
+  return 0;
+}
+
+// Launch the persistent kernel: one CTA per SM, cooperative (all CTAs co-resident, the grid barrier needs it).
+int launch(fq3_engine* e, LaunchParams& p, int xrows, int kmax, cudaStream_t s) {
+  if (int r = check_device_fault(e)) return r;
+  p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 128);
+  p.xbuf_bytes = (int)round_up((size_t)xrows * kmax * 2, 128);
+  const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - p.prog_bytes - p.xbuf_bytes;
+  p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
+  if (p.n_stages < 2) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
+  const size_t smem = kHeaderBytes + kScratchBytes + p.prog_bytes + p.xbuf_bytes + (size_t)p.n_stages * kStageBytes;
+  CK(cudaMemsetAsync(e->grid_bar, 0, sizeof(unsigned), s));
+  void* args[] = {&p};
+  CK(cudaLaunchCooperativeKernel((void*)fq3_stream_kernel, dim3(e->G), dim3(kThreads), args, smem, s));
+  e->launches += 1;
+  return 0;
+}
+
+Policy to_policy(const fq3_policy* q) {
+  Policy p{};
+  p.do_sample = q->do_sample; p.top_k = q->top_k; p.top_p = q->top_p; p.temperature = q->temperature;
+  p.rep_pen = q->repetition_penalty; p.min_new_tokens = q->min_new_tokens; p.suppress_tail = q->suppress_tail;
+  p.seed = q->seed;
+  return p;
+}
+SubPolicy to_sub(const fq3_subpolicy* q) {
+  SubPolicy p{};
+  p.do_sample = q->do_sample; p.top_k = q->top_k; p.top_p = q->top_p; p.temperature = q->temperature;
+  return p;
+}
+
+int check_stack(const fq3_stack_desc& d, const char* name) {
+  if (d.head_dim != kHeadDim) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": head_dim must be 128");
+  if (d.hidden % 8 || d.inter % 8) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": dims must be multiples of 8");
+  if (d.n_q_heads % d.n_kv_heads) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": nq % nkv != 0");
+  if (d.vocab > kMaxVocab) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": vocab exceeds sampling scratch");
+  const int kmax = std::max(std::max(d.hidden, d.inter), d.n_q_heads * d.head_dim);
+  if (kmax * 2 > kStageBytes) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": a weight row exceeds one ring stage");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fq3_abi_version(void) { return FQ3_ABI_VERSION; }
+const char* fq3_last_error(void) { return g_err.c_str(); }
+
+int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
+  if (!desc || !out) return fail(FQ3_E_INVALID, "null argument");
+  if (desc->abi_version != FQ3_ABI_VERSION) return fail(FQ3_E_INVALID, "ABI version mismatch");
+  if (int r = check_stack(desc->talker, "talker")) return r;
+  if (int r = check_stack(desc->predictor, "predictor")) return r;
+  if (desc->n_code_groups < 2 || desc->n_code_groups > FQ3_MAX_CODE_GROUPS) return fail(FQ3_E_INVALID, "n_code_groups");
+  if (desc->max_streams < 1) return fail(FQ3_E_INVALID, "max_streams");
+  if (!desc->has_s2m && desc->talker.hidden != desc->predictor.hidden)
+    return fail(FQ3_E_INVALID, "talker/predictor widths differ but no small_to_mtp projection given");
+  fq3_engine* e = new fq3_engine();
+  e->desc = *desc;
+  CK(cudaGetDevice(&e->dev));
+  int sms = 0, smem_optin = 0, coop = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->dev));
+  CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->dev));
+  CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->dev));
+  if (!coop) return fail(FQ3_E_UNSUPPORTED, "device lacks cooperative launch");
+  e->G = sms;
+  if (const char* g = getenv("FQ3_GRID")) e->G = std::max(1, std::min(sms, atoi(g)));
+  if (const char* w = getenv("FQ3_WATCHDOG_MS")) e->watchdog_ns = (unsigned long long)atoll(w) * 1000000ull;
+  e->smem_max = (size_t)smem_optin;
+  CK(cudaFuncSetAttribute(fq3_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fq3_stream_kernel, kThreads, smem_optin));
+  if (occ < 1) return fail(FQ3_E_UNSUPPORTED, "stream kernel does not fit on an SM");
+
+  e->ncb = desc->n_code_groups - 1;
+  e->tk.d = desc->talker;
+  e->pr.d = desc->predictor;
+  e->tk.offs.assign(desc->talker.layer_offs, desc->talker.layer_offs + (size_t)desc->talker.n_layers * 8);
+  e->pr.offs.assign(desc->predictor.layer_offs, desc->predictor.layer_offs + (size_t)desc->predictor.n_layers * 8);
+  e->lm_head_offs.assign(desc->lm_head_offs, desc->lm_head_offs + e->ncb);
+  e->pred_embed_offs.assign(desc->pred_embed_offs, desc->pred_embed_offs + e->ncb);
+  e->tk.d.layer_offs = nullptr;
+  e->pr.d.layer_offs = nullptr;
+
+  const int B = desc->max_streams;
+  const int R = std::max(2 * B, kMaxRows);
+  e->max_rows = R;
+  const uint8_t* arena = reinterpret_cast<const uint8_t*>(desc->arena);
+  // --- static KV caches (StaticCache of talker_graph.py:43 / predictor_graph.py:61) ---
+  for (int s = 0; s < 2; ++s) {
+    const StackHost& sh = s == 0 ? e->tk : e->pr;
+    StackRt& r = e->rt[s];
+    r.hidden = sh.d.hidden; r.inter = sh.d.inter; r.n_layers = sh.d.n_layers; r.nq = sh.d.n_q_heads;
+    r.nkv = sh.d.n_kv_heads; r.vocab = sh.d.vocab; r.eps = sh.d.rms_eps; r.max_pos = sh.d.max_pos;
+    r.rope_len = sh.d.rope_len; r.n_slots = B;
+    const size_t n = (size_t)sh.d.n_layers * B * sh.d.n_kv_heads * sh.d.max_pos * kHeadDim;
+    if (dalloc(e, &r.kcache, n)) return -FQ3_E_CUDA;
+    if (dalloc(e, &r.vcache, n)) return -FQ3_E_CUDA;
+    r.rope_cos = reinterpret_cast<const bf16*>(arena + sh.d.rope_cos_off);
+    r.rope_sin = reinterpret_cast<const bf16*>(arena + sh.d.rope_sin_off);
+  }
+  // --- activation buffers ---
+  auto mk = [&](int id, int width, size_t elt) -> int {
+    void* q = nullptr;
+    if (dalloc(e, reinterpret_cast<uint8_t**>(&q), (size_t)R * width * elt)) return -1;
+    e->bufs[id] = q;
+    e->ld[id] = width;
+    return 0;
+  };
+  const int Ht = e->tk.d.hidden, Hp = e->pr.d.hidden;
+  if (mk(BUF_TX, Ht, 2) || mk(BUF_TQKV, e->tk.qkvdim(), 2) || mk(BUF_TATT, e->tk.qdim(), 2) ||
+      mk(BUF_TACT, e->tk.d.inter, 2) || mk(BUF_PX, Hp, 2) || mk(BUF_PQKV, e->pr.qkvdim(), 2) ||
+      mk(BUF_PATT, e->pr.qdim(), 2) || mk(BUF_PACT, e->pr.d.inter, 2) ||
+      mk(BUF_LOGITS, std::max(e->tk.d.vocab, e->pr.d.vocab), 4) || mk(BUF_HID, Ht, 2))
+    return -FQ3_E_CUDA;
+  if (desc->has_s2m) {
+    if (mk(BUF_PIN, Ht, 2)) return -FQ3_E_CUDA;
+  } else {
+    e->bufs[BUF_PIN] = e->bufs[BUF_PX];
+    e->ld[BUF_PIN] = e->ld[BUF_PX];
+  }
+  const int nqmax = std::max(e->tk.d.n_q_heads, e->pr.d.n_q_heads);
+  if (dalloc(e, &e->attn_part, (size_t)R * nqmax * kMaxSplits * kPartStride)) return -FQ3_E_CUDA;
+  if (dalloc(e, &e->attn_cnt, (size_t)std::max(B, 1) * std::max(e->tk.d.n_kv_heads, e->pr.d.n_kv_heads))) return -FQ3_E_CUDA;
+  if (dalloc(e, &e->grid_bar, 4)) return -FQ3_E_CUDA;
+  if (dalloc(e, &e->pred_logits_all, (size_t)e->ncb * e->pr.d.vocab)) return -FQ3_E_CUDA;
+  if (dalloc(e, &e->seen_scratch, (size_t)kMaxVocab * 4)) return -FQ3_E_CUDA;
+  CK(cudaHostAlloc(reinterpret_cast<void**>(&e->err_host), 64, cudaHostAllocMapped));
+  memset(e->err_host, 0, 64);
+  CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->err_dev), e->err_host, 0));
+  // --- per-stream state ---
+  e->h_st.resize(B);
+  if (dalloc(e, &e->d_st, B)) return -FQ3_E_CUDA;
+  for (int b = 0; b < B; ++b) {
+    StreamState& s = e->h_st[b];
+    memset(&s, 0, sizeof s);
+    bf16 *tr = nullptr, *pe = nullptr;
+    if (dalloc(e, &tr, (size_t)e->tk.d.max_pos * Ht)) return -FQ3_E_CUDA;
+    if (dalloc(e, &pe, (size_t)Ht)) return -FQ3_E_CUDA;
+    if (dalloc(e, &s.codes, (size_t)desc->max_frames * desc->n_code_groups)) return -FQ3_E_CUDA;
+    if (dalloc(e, &s.seen, (size_t)round_up(e->tk.d.vocab, 16))) return -FQ3_E_CUDA;
+    s.trailing = tr;
+    s.pad_embed = pe;
+  }
+  CK(cudaMemcpy(e->d_st, e->h_st.data(), sizeof(StreamState) * B, cudaMemcpyHostToDevice));
+  // --- programs ---
+  std::vector<Phase> v;
+  push_predictor(v, e, false);
+  push_talker(v, e, false);
+  {
+    Phase s{};
+    s.type = PH_SAMPLE; s.stack = ST_TALKER; s.kind = SMP_TALKER;
+    v.push_back(s);
+  }
+  e->n_frames_ph = (int)v.size();
+  if (upload(e, v, &e->d_frames)) return fail(FQ3_E_CUDA, "program upload");
+  v.clear();
+  push_predictor(v, e, true);
+  e->n_pred_ph = (int)v.size();
+  if (upload(e, v, &e->d_pred)) return fail(FQ3_E_CUDA, "program upload");
+  v.clear();
+  push_talker(v, e, false);
+  e->n_talker_ph = (int)v.size();
+  if (upload(e, v, &e->d_talker)) return fail(FQ3_E_CUDA, "program upload");
+  v.clear();
+  push_talker(v, e, true);
+  {
+    Phase s{};
+    s.type = PH_SAMPLE; s.stack = ST_TALKER; s.kind = SMP_PREFILL;
+    v.push_back(s);
+  }
+  e->n_prefill_ph = (int)v.size();
+  if (upload(e, v, &e->d_prefill)) return fail(FQ3_E_CUDA, "program upload");
+  if (dalloc(e, &e->d_linear, 1)) return -FQ3_E_CUDA;
+  const size_t frames_need = kHeaderBytes + kScratchBytes + round_up((size_t)e->n_frames_ph * sizeof(Phase), 128) +
+                             2 * (size_t)kStageBytes;
+  if (frames_need > e->smem_max) return fail(FQ3_E_UNSUPPORTED, "frame program does not fit in shared memory");
+  CK(cudaDeviceSynchronize());
+  *out = e;
+  return 0;
+}
+
+int fq3_destroy(fq3_engine* e) {
+  if (!e) return 0;
+  cudaDeviceSynchronize();
+  for (void* p : e->owned) cudaFree(p);
+  if (e->err_host) cudaFreeHost(e->err_host);
+  delete e;
+  return 0;
+}
+
+int fq3_num_sms(const fq3_engine* e) { return e ? e->G : 0; }
+int64_t fq3_launch_count(const fq3_engine* e) { return e ? e->launches : 0; }
+
+static int check_stream(fq3_engine* e, int idx) {
+  if (!e) return fail(FQ3_E_INVALID, "null engine");
+  if (idx < 0 || idx >= e->desc.max_streams) return fail(FQ3_E_INVALID, "stream index out of range");
+  return 0;
+}
+
+int fq3_reset_stream(fq3_engine* e, int idx, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  fq3_reset_stream_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->d_st + idx, e->tk.d.vocab);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int fq3_set_generation_state(fq3_engine* e, int idx, int n_left_pad, int rope_delta, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  fq3_set_state_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e->d_st + idx, 0, 0, 0, 2, n_left_pad, rope_delta, 0);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int fq3_set_text_conditioning(fq3_engine* e, int idx, const void* trailing, int n_trailing, const void* pad_embed,
+                              void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  const int Ht = e->tk.d.hidden;
+  if (n_trailing < 0 || n_trailing > e->tk.d.max_pos) return fail(FQ3_E_TOO_LONG, "trailing text longer than max_seq_len");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_trailing > 0)
+    CK(cudaMemcpyAsync(const_cast<bf16*>(e->h_st[idx].trailing), trailing, (size_t)n_trailing * Ht * 2,
+                       cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(const_cast<bf16*>(e->h_st[idx].pad_embed), pad_embed, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, 0, 0, 4, 0, 0, n_trailing);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int fq3_import_kv(fq3_engine* e, int idx, int layer, const void* k, const void* v, int T, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  const StackRt& S = e->rt[0];
+  if (layer < 0 || layer >= S.n_layers) return fail(FQ3_E_INVALID, "layer out of range");
+  if (T > S.max_pos) {
+    char b[200];
+    snprintf(b, sizeof b, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter "
+                          "reference audio.", T, S.max_pos);
+    return fail(FQ3_E_TOO_LONG, b);
+  }
+  if (T <= 0) return 0;
+  const size_t base = ((size_t)layer * S.n_slots + idx) * S.nkv * (size_t)S.max_pos * kHeadDim;
+  fq3_import_kv_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(S.kcache + base, S.vcache + base,
+                                                             reinterpret_cast<const bf16*>(k),
+                                                             reinterpret_cast<const bf16*>(v), S.nkv, T, S.max_pos);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int fq3_set_loop_state(fq3_engine* e, int idx, int token, const void* past_hidden, int position, int gen_step,
+                       void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  if (token < 0 || token >= e->tk.d.vocab) return fail(FQ3_E_INVALID, "token out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ht = e->tk.d.hidden;
+  fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, token, position, gen_step, 1 | 8 | 16, 0, 0, 0);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  bf16* hid = reinterpret_cast<bf16*>(e->bufs[BUF_HID]) + (size_t)idx * e->ld[BUF_HID];
+  bf16* pin = reinterpret_cast<bf16*>(e->bufs[BUF_PIN]);
+  const int ldp = e->ld[BUF_PIN];
+  const bf16* emb = reinterpret_cast<const bf16*>(reinterpret_cast<const uint8_t*>(e->desc.arena) + e->desc.codec_embed_off) +
+                    (size_t)token * Ht;
+  CK(cudaMemcpyAsync(hid, past_hidden, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(pin + (size_t)(2 * idx) * ldp, past_hidden, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(pin + (size_t)(2 * idx + 1) * ldp, emb, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+static int prefill_rows(const fq3_engine* e) {
+  // rows per pass are bounded by the activation staging buffer: keep >= 4 ring stages
+  const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes -
+                     (long)round_up((size_t)e->n_prefill_ph * sizeof(Phase), 128) - 4L * kStageBytes;
+  long rows = avail / ((long)e->tk.kmax() * 2);
+  const int gq = e->tk.d.n_q_heads / e->tk.d.n_kv_heads;
+  rows = std::min<long>(rows, 16 / gq);
+  return (int)std::max<long>(1, std::min<long>(rows, kMaxRows));
+}
+
+int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pad, const fq3_policy* policy,
+                void* out_logits, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  if (!embeds || !policy || T <= 0) return fail(FQ3_E_INVALID, "bad prefill arguments");
+  if (T > e->tk.d.max_pos) {
+    char b[200];
+    snprintf(b, sizeof b, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter "
+                          "reference audio.", T, e->tk.d.max_pos);
+    return fail(FQ3_E_TOO_LONG, b);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ht = e->tk.d.hidden;
+  const int Mmax = prefill_rows(e);
+  fq3_reset_stream_kernel<<<1, 256, 0, s>>>(e->d_st + idx, e->tk.d.vocab);
+  fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, 0, 0, 2, n_left_pad, -n_left_pad, 0);
+  e->launches += 2;
+  for (int c0 = 0; c0 < T; c0 += Mmax) {
+    const int rows = std::min(Mmax, T - c0);
+    const bool final = (c0 + rows == T);
+    CK(cudaMemcpyAsync(e->bufs[BUF_TX], reinterpret_cast<const bf16*>(embeds) + (size_t)c0 * Ht, (size_t)rows * Ht * 2,
+                       cudaMemcpyDeviceToDevice, s));
+    LaunchParams p{};
+    fill_common(e, p);
+    p.prog = e->d_prefill;
+    p.n_phases = final ? e->n_prefill_ph : e->n_prefill_ph - 2;  // drop head + sample on non-final chunks
+    p.mode = MODE_PREFILL;
+    p.n_rows = rows;
+    p.stream0 = idx;
+    p.pf_pos0 = c0; p.pf_n_pad = n_left_pad; p.pf_rope_delta = -n_left_pad; p.pf_final = final;
+    p.pol = to_policy(policy);
+    if (int r = launch(e, p, rows, e->tk.kmax(), s)) return r;
+  }
+  fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, T, 0, 8, 0, 0, 0);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  if (out_logits)
+    CK(cudaMemcpyAsync(out_logits, e->bufs[BUF_LOGITS], (size_t)e->tk.d.vocab * 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int fq3_talker_step(fq3_engine* e, int idx, const void* embeds, int position, void* out_hidden, void* out_logits,
+                    void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  if (position < 0 || position >= e->tk.d.max_pos) return fail(FQ3_E_TOO_LONG, "position outside the static KV cache");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ht = e->tk.d.hidden;
+  CK(cudaMemcpyAsync(e->bufs[BUF_TX], embeds, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  LaunchParams p{};
+  fill_common(e, p);
+  p.prog = e->d_talker;
+  p.n_phases = e->n_talker_ph;
+  p.mode = MODE_TALKER_STEP;
+  p.n_rows = 1;
+  p.stream0 = idx;
+  p.pos_override = position;
+  if (int r = launch(e, p, 1, e->tk.kmax(), s)) return r;
+  if (out_hidden) CK(cudaMemcpyAsync(out_hidden, e->bufs[BUF_HID], (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  if (out_logits)
+    CK(cudaMemcpyAsync(out_logits, e->bufs[BUF_LOGITS], (size_t)e->tk.d.vocab * 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int fq3_predictor_run(fq3_engine* e, int idx, const void* pred_input, const fq3_subpolicy* sub, uint64_t seed,
+                      void* out_codes_i64, void* out_logits, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  if (!pred_input || !sub || !out_codes_i64) return fail(FQ3_E_INVALID, "bad predictor arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ht = e->tk.d.hidden;
+  CK(cudaMemcpyAsync(e->bufs[BUF_PIN], pred_input, (size_t)2 * Ht * 2, cudaMemcpyDeviceToDevice, s));
+  LaunchParams p{};
+  fill_common(e, p);
+  p.prog = e->d_pred;
+  p.n_phases = e->n_pred_ph;
+  p.mode = MODE_PREDICTOR;
+  p.n_rows = 1;
+  p.stream0 = idx;
+  p.sub = to_sub(sub);
+  p.pol.seed = seed;
+  p.pred_logits_all = out_logits ? e->pred_logits_all : nullptr;
+  const int kmax = std::max(e->pr.kmax(), e->desc.has_s2m ? e->tk.d.hidden : 0);
+  if (int r = launch(e, p, 2, kmax, s)) return r;
+  fq3_codes_to_i64_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(e->d_st + idx) +
+                                                                         offsetof(StreamState, cur_codes)),
+                                           e->ncb, reinterpret_cast<long long*>(out_codes_i64));
+  e->launches += 1;
+  CK(cudaGetLastError());
+  if (out_logits)
+    CK(cudaMemcpyAsync(out_logits, e->pred_logits_all, (size_t)e->ncb * e->pr.d.vocab * 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int fq3_sample(fq3_engine* e, const void* logits_f32, int V, const void* history_i64, int n_history,
+               const fq3_policy* policy, int eos_id, int suppress_eos, int flags, uint64_t draw_index,
+               void* out_token_i64, void* stream) {
+  if (!e || !logits_f32 || !policy || !out_token_i64) return fail(FQ3_E_INVALID, "bad sample arguments");
+  if (V <= 0 || V > kMaxVocab) return fail(FQ3_E_UNSUPPORTED, "vocab exceeds sampling scratch");
+  SampleArgs a{};
+  a.V = V; a.do_sample = policy->do_sample; a.top_k = policy->top_k; a.top_p = policy->top_p;
+  a.temperature = policy->temperature; a.rep_pen = policy->repetition_penalty; a.seen = nullptr;
+  a.suppress_start = policy->suppress_tail > 0 ? std::max(0, V - policy->suppress_tail) : V;
+  a.eos = eos_id; a.suppress_eos = suppress_eos; a.round_bf16 = flags & 1; a.seed = policy->seed; a.draw = draw_index;
+  fq3_sample_kernel<<<1, kConsumerThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float*>(logits_f32), a, reinterpret_cast<const long long*>(history_i64), n_history,
+      e->seen_scratch, reinterpret_cast<long long*>(out_token_i64));
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int fq3_apply_repetition_penalty(fq3_engine* e, void* logits_f32, int V, const void* history_i64, int n_history,
+                                 float penalty, int flags, void* stream) {
+  if (!e || !logits_f32) return fail(FQ3_E_INVALID, "bad arguments");
+  if (V <= 0 || V > kMaxVocab * 4) return fail(FQ3_E_UNSUPPORTED, "vocab exceeds scratch");
+  if (penalty == 1.0f || n_history <= 0 || !history_i64) return 0;  // sampling.py:22-23
+  fq3_rep_penalty_kernel<<<1, kConsumerThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float*>(logits_f32), V, reinterpret_cast<const long long*>(history_i64), n_history, penalty,
+      flags & 1, e->seen_scratch);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_policy* policy, const fq3_subpolicy* sub,
+                      void* stream) {
+  if (!e || !policy || !sub) return fail(FQ3_E_INVALID, "bad decode arguments");
+  if (n_streams < 1 || n_streams > e->desc.max_streams) return fail(FQ3_E_INVALID, "n_streams out of range");
+  if (2 * n_streams > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "batched decode above 4 streams needs the tensor-core path");
+  if (n_frames <= 0) return 0;
+  LaunchParams p{};
+  fill_common(e, p);
+  p.prog = e->d_frames;
+  p.n_phases = e->n_frames_ph;
+  p.mode = MODE_FRAMES;
+  p.n_rows = n_streams;
+  p.n_iters = n_frames;
+  p.pol = to_policy(policy);
+  p.sub = to_sub(sub);
+  const int kmax = std::max(e->pr.kmax(), e->tk.kmax());
+  return launch(e, p, 2 * n_streams, kmax, (cudaStream_t)stream);
+}
+
+int fq3_get_status(fq3_engine* e, int idx, fq3_status* out, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  cudaError_t se = cudaStreamSynchronize((cudaStream_t)stream);
+  if (int r = check_device_fault(e)) return r;
+  if (se != cudaSuccess) return fail(FQ3_E_CUDA, std::string("stream sync: ") + cudaGetErrorString(se));
+  StreamState s;
+  CK(cudaMemcpy(&s, e->d_st + idx, sizeof s, cudaMemcpyDeviceToHost));
+  out->n_frames = s.n_frames; out->done = s.done; out->position = s.position; out->gen_step = s.gen_step;
+  out->token = s.token; out->error = e->err_host[0];
+  return 0;
+}
+
+int fq3_read_codes(fq3_engine* e, int idx, int first, int n, int32_t* codes_out, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  if (first < 0 || n < 0 || first + n > e->desc.max_frames) return fail(FQ3_E_INVALID, "frame range");
+  if (n == 0) return 0;
+  const int g = e->desc.n_code_groups;
+  CK(cudaMemcpyAsync(codes_out, e->h_st[idx].codes + (size_t)first * g, (size_t)n * g * 4, cudaMemcpyDeviceToHost,
+                     (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+void* fq3_codes_device_ptr(fq3_engine* e, int idx) {
+  if (!e || idx < 0 || idx >= e->desc.max_streams) return nullptr;
+  return e->h_st[idx].codes;
+}
+
+int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int N, int K, int flags, const void* gamma,
+               float eps, const void* bias, const void* residual, void* stream) {
+  if (!e || !W || !x || !y) return fail(FQ3_E_INVALID, "null argument");
+  if (M < 1 || M > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "M must be in [1, 8]");
+  if (K % 8 || K * 2 > kStageBytes || N < 1) return fail(FQ3_E_UNSUPPORTED, "K must be a multiple of 8 and fit one stage");
+  if ((flags & 8) && (N % 2)) return fail(FQ3_E_INVALID, "SwiGLU needs an even N");
+  cudaStream_t s = (cudaStream_t)stream;
+  Phase ph{};
+  ph.type = PH_GEMV;
+  ph.flags = F_ABSPTR | ((flags & 1) ? F_PRENORM : 0) | ((flags & 2) ? F_BIAS : 0) | ((flags & 4) ? F_RESID : 0) |
+             ((flags & 8) ? F_SWIGLU : 0) | ((flags & 16) ? F_OUT_F32 : 0);
+  ph.in_buf = BUF_LIN_IN; ph.out_buf = BUF_LIN_OUT; ph.res_buf = BUF_LIN_RES;
+  ph.N = (uint32_t)N; ph.K = (uint32_t)K;
+  CK(cudaMemcpyAsync(e->d_linear, &ph, sizeof ph, cudaMemcpyHostToDevice, s));
+  LaunchParams p{};
+  fill_common(e, p);
+  p.prog = e->d_linear;
+  p.n_phases = 1;
+  p.mode = MODE_LINEAR;
+  p.n_rows = M;
+  p.bufs[BUF_LIN_IN] = const_cast<void*>(x); p.ld[BUF_LIN_IN] = K;
+  p.bufs[BUF_LIN_OUT] = y; p.ld[BUF_LIN_OUT] = (flags & 8) ? N / 2 : N;
+  p.bufs[BUF_LIN_RES] = const_cast<void*>(residual); p.ld[BUF_LIN_RES] = (flags & 8) ? N / 2 : N;
+  p.lin_W = W; p.lin_gamma = gamma; p.lin_bias = bias; p.lin_eps = eps;
+  return launch(e, p, M, K, s);
+}
+
+}  // extern "C"

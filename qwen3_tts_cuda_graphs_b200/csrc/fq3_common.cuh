@@ -1,0 +1,156 @@
+// fq3_common.cuh — shared device/host definitions for the persistent weight-streaming decode kernel.
+//
+// The kernel is a small "phase machine": a program is a flat list of 32-byte phase descriptors (GEMV /
+// attention / sampling).  One CTA per SM runs the whole program; a producer warp streams the weight
+// tiles of every GEMV phase through a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS
+// UBLKCP) while eight consumer warps do the arithmetic.  Because weight addresses never depend on
+// activations or sampled tokens, the producer runs ahead across phase and grid barriers, so HBM stays
+// busy while the consumers wait for each other.  See DESIGN.md §3.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fq3 {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- geometry ---------------------------------------------------------------------------------
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;  // 256
+constexpr int kThreads = kConsumerThreads + 32;        // + one producer warp
+constexpr int kStageBytes = 16 * 1024;                 // one ring stage (weight tile)
+constexpr int kMaxStages = 12;
+constexpr int kRowsPerTileMax = 128;
+constexpr int kScratchBytes = 16 * 1024;  // GEMV partials / attention scratch / sampling scratch
+constexpr int kHeadDim = 128;             // talker and predictor heads (asserted on the host)
+constexpr int kMaxRows = 8;               // activation rows (tokens) per launch, GEMV register tile
+constexpr int kMaxSplits = 32;            // split-KV partitions per (sequence, kv head)
+constexpr int kPartStride = 132;          // floats per attention partial: m, l, pad, pad, o[128]
+constexpr int kNumBufs = 16;
+constexpr int kMaxVocab = 3328;              // sampling scratch holds V fp32 logits in 13 KB
+constexpr int kCtlOffset = 192;            // smem: full[12] | empty[12] | ctl[16] | scratch ...
+constexpr int kHeaderBytes = 256;
+
+// ---- phase descriptors ------------------------------------------------------------------------
+enum PhaseType : uint8_t { PH_END = 0, PH_GEMV = 1, PH_ATTN = 2, PH_SAMPLE = 3 };
+enum StackId : uint8_t { ST_TALKER = 0, ST_PRED = 1 };
+enum SampleKind : uint8_t { SMP_PRED = 0, SMP_TALKER = 1, SMP_PREFILL = 2, SMP_PRED_ONLY = 3 };
+
+enum PhaseFlags : uint16_t {
+  F_PRENORM = 1,        // x <- RMSNorm(x) * gamma before the product
+  F_BIAS = 2,           // + bias
+  F_RESID = 4,          // out = res + y
+  F_SWIGLU = 8,         // rows are (gate_j, up_j) pairs; out[j] = silu(gate) * up
+  F_OUT_F32 = 16,       // store bf16-rounded value as fp32 (logits)
+  F_ROWS2 = 32,         // predictor pass 0: two rows per stream
+  F_LAST_ROW = 64,      // only the last input row is used (prefill head)
+  F_WRITE_NORMED = 128, // CTA 0 also stores the normalised input rows (past_hidden)
+  F_L2_KEEP = 256,      // weights are re-read soon (predictor): L2 evict_last hint
+  F_ABSPTR = 512        // fq3_linear: absolute pointers taken from LaunchParams
+};
+
+struct __align__(16) Phase {
+  uint8_t type;
+  uint8_t stack;
+  uint8_t layer;
+  uint8_t aux;  // predictor pass index / sample kind payload
+  uint16_t flags;
+  uint8_t in_buf, out_buf;
+  uint32_t w_off;  // weight offset in 16-byte units from the arena base (ATTN: unused)
+  uint32_t g_off;  // GEMV: gamma;  ATTN: q_norm gamma
+  uint32_t b_off;  // GEMV: bias;   ATTN: k_norm gamma
+  uint32_t N;
+  uint32_t K;
+  uint8_t res_buf;
+  uint8_t kind;  // SAMPLE: SampleKind
+  uint8_t pad0, pad1;
+};
+static_assert(sizeof(Phase) == 32, "Phase must stay 32 bytes");
+
+enum BufId : uint8_t {
+  BUF_TX = 0, BUF_TQKV, BUF_TATT, BUF_TACT, BUF_PX, BUF_PQKV, BUF_PATT, BUF_PACT, BUF_PIN,
+  BUF_LOGITS, BUF_HID, BUF_LIN_IN, BUF_LIN_OUT, BUF_LIN_RES, BUF_PLOG_ALL, BUF_COUNT
+};
+
+// ---- run-time structures ----------------------------------------------------------------------
+struct StackRt {
+  int hidden, inter, n_layers, nq, nkv, vocab;
+  float eps;
+  int max_pos;    // KV capacity per slot
+  int rope_len;
+  int n_slots;
+  bf16* kcache;   // [layer][slot][kv_head][max_pos][128]
+  bf16* vcache;
+  const bf16* rope_cos;  // [rope_len][128]
+  const bf16* rope_sin;
+};
+
+struct StreamState {  // one per stream, device memory
+  int token;
+  int position;
+  int gen_step;
+  int n_frames;
+  int done;
+  int n_pad;
+  int rope_delta;
+  int n_trailing;
+  unsigned long long draws;
+  const bf16* trailing;   // [n_trailing, H_t]
+  const bf16* pad_embed;  // [H_t]
+  int* codes;             // [max_frames, 16]
+  uint8_t* seen;          // [V_t] first-codebook history bitmap (repetition penalty)
+  int cur_codes[32];
+};
+
+struct Policy {
+  int do_sample, top_k;
+  float top_p, temperature, rep_pen;
+  int min_new_tokens, suppress_tail;
+  unsigned long long seed;
+};
+struct SubPolicy {
+  int do_sample, top_k;
+  float top_p, temperature;
+};
+
+enum Mode : int { MODE_FRAMES = 0, MODE_TALKER_STEP = 1, MODE_PREDICTOR = 2, MODE_PREFILL = 3, MODE_LINEAR = 4 };
+
+struct LaunchParams {
+  const Phase* prog;
+  int n_phases;
+  int n_iters;
+  int mode;
+  int n_rows;    // base row count M (streams for decode, chunk rows for prefill, M for linear)
+  int stream0;   // first stream index (single-stream entry points)
+  int pos_override;  // >=0: talker position for MODE_TALKER_STEP
+  int pf_pos0, pf_n_pad, pf_rope_delta, pf_final;
+  const uint8_t* arena;
+  void* bufs[kNumBufs];
+  int ld[kNumBufs];
+  StackRt stacks[2];
+  StreamState* st;
+  Policy pol;
+  SubPolicy sub;
+  float* attn_part;
+  unsigned* attn_cnt;
+  unsigned* grid_bar;
+  int* err;  // mapped host memory: [0]=code [1]=cta [2]=phase [3]=detail
+  // model constants used by the sampling phases
+  int n_code_groups, eos_id, has_s2m, max_frames;
+  const bf16* codec_embed;            // [V_t, H_t]
+  const bf16* pred_embeds[32];        // [V_p, H_t] each
+  float* pred_logits_all;             // optional [15, V_p] dump (MODE_PREDICTOR)
+  // fq3_linear
+  const void* lin_W;
+  const void* lin_gamma;
+  const void* lin_bias;
+  float lin_eps;
+  // smem carve-up
+  int n_stages, xbuf_bytes, prog_bytes;
+  unsigned long long watchdog_ns;
+};
+
+enum DevErr : int { DE_NONE = 0, DE_GRID_BAR = 1, DE_FULL_WAIT = 2, DE_EMPTY_WAIT = 3, DE_HANDSHAKE = 4, DE_BAD_PHASE = 5 };
+
+}  // namespace fq3

@@ -1,0 +1,1186 @@
+// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a).
+//
+// Replaces the CUDA-graph replays of talker_graph.py:97-107,198-214 and predictor_graph.py:115-167 and
+// the eager per-frame glue of generate.py:149-199 (reference paths under /root/reference/faster_qwen3_tts).
+#pragma once
+#include "fq3_common.cuh"
+
+namespace fq3 {
+
+// =================================================================================================
+// PTX helpers
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+__device__ __forceinline__ void cbar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int ld_volatile_shared_i32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_shared_i32(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
+  acc = fmaf(bf_lo(w.x), bf_lo(x.x), acc);
+  acc = fmaf(bf_hi(w.x), bf_hi(x.x), acc);
+  acc = fmaf(bf_lo(w.y), bf_lo(x.y), acc);
+  acc = fmaf(bf_hi(w.y), bf_hi(x.y), acc);
+  acc = fmaf(bf_lo(w.z), bf_lo(x.z), acc);
+  acc = fmaf(bf_hi(w.z), bf_hi(x.z), acc);
+  acc = fmaf(bf_lo(w.w), bf_lo(x.w), acc);
+  acc = fmaf(bf_hi(w.w), bf_hi(x.w), acc);
+  return acc;
+}
+
+// =================================================================================================
+// Shared-memory layout
+// =================================================================================================
+struct Smem {
+  uint64_t* full;    // [kMaxStages]
+  uint64_t* empty;   // [kMaxStages]
+  int* ctl;          // [0] producer go flag, [1..] broadcast scratch
+  unsigned char* scratch;
+  Phase* prog;
+  unsigned char* xbuf;
+  unsigned char* ring;
+};
+
+__device__ __forceinline__ Smem carve_smem(unsigned char* base, const LaunchParams& p) {
+  Smem s;
+  s.full = reinterpret_cast<uint64_t*>(base);
+  s.empty = s.full + kMaxStages;
+  s.ctl = reinterpret_cast<int*>(base + kCtlOffset);
+  s.scratch = base + kHeaderBytes;
+  s.prog = reinterpret_cast<Phase*>(s.scratch + kScratchBytes);
+  s.xbuf = reinterpret_cast<unsigned char*>(s.prog) + p.prog_bytes;
+  s.ring = s.xbuf + p.xbuf_bytes;
+  return s;
+}
+
+// =================================================================================================
+// Watchdog: a protocol bug must surface as an error, never as a hung GPU.
+// =================================================================================================
+__device__ __noinline__ void device_fault(const LaunchParams& p, int code, int phase, int detail) {
+  volatile int* e = p.err;
+  if (e[0] == 0) {
+    e[1] = blockIdx.x;
+    e[2] = phase;
+    e[3] = detail;
+    e[0] = code;
+  }
+  __threadfence_system();
+  asm volatile("trap;");
+}
+
+struct Spin {
+  unsigned long long t0;
+  unsigned n;
+  __device__ __forceinline__ Spin() : t0(0), n(0) {}
+  __device__ __forceinline__ void tick(const LaunchParams& p, int code, int phase, int detail) {
+    if ((++n & 0x3ff) == 0) {
+      unsigned long long t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > p.watchdog_ns) device_fault(p, code, phase, detail);
+    }
+  }
+};
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const LaunchParams& p, int code, int phase) {
+  if (mbar_try_wait(bar, parity)) return;
+  Spin s;
+  while (!mbar_try_wait(bar, parity)) s.tick(p, code, phase, (int)parity);
+}
+
+// Grid-wide barrier among the consumer threads of all CTAs (monotonic counter, reset by the host).
+__device__ __forceinline__ void grid_sync(const LaunchParams& p, unsigned& epoch, int phase) {
+  cbar_sync();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(p.grid_bar, 1u);
+    const unsigned target = epoch * gridDim.x;
+    Spin s;
+    while (ld_acquire_u32(p.grid_bar) < target) s.tick(p, DE_GRID_BAR, phase, (int)epoch);
+    __threadfence();
+  }
+  cbar_sync();
+}
+
+// =================================================================================================
+// GEMV phase
+// =================================================================================================
+struct GemvPlan {
+  int r0, r1, rt, ntiles;
+};
+__device__ __forceinline__ GemvPlan gemv_plan(const Phase& ph, int cta, int G) {
+  GemvPlan g;
+  const int unit = (ph.flags & F_SWIGLU) ? 2 : 1;
+  const int N = (int)ph.N, K = (int)ph.K;
+  const int nunits = N / unit;
+  const int upc = (nunits + G - 1) / G;
+  g.r0 = min(N, cta * upc * unit);
+  g.r1 = min(N, g.r0 + upc * unit);
+  int rt = min(kRowsPerTileMax, kStageBytes / (K * 2));
+  rt -= rt % unit;
+  g.rt = max(rt, unit);
+  g.ntiles = (g.r1 - g.r0 + g.rt - 1) / g.rt;
+  return g;
+}
+
+__device__ __forceinline__ int phase_rows(const Phase& ph, const LaunchParams& p) {
+  return (ph.flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows;
+}
+
+// Load the activation rows of a GEMV phase into shared memory (bf16), optionally RMS-normalised.
+// HF rounding points (Qwen3RMSNorm): fp32 mean-square, x*rsqrt -> bf16, * weight -> bf16.
+__device__ void load_x(const Phase& ph, const LaunchParams& p, const Smem& sm, int M, int row_off) {
+  const int K = (int)ph.K;
+  const int cpr = K >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* in = reinterpret_cast<const bf16*>(p.bufs[ph.in_buf]);
+  const int ld = p.ld[ph.in_buf];
+  uint4* xs = reinterpret_cast<uint4*>(sm.xbuf);
+  const bool norm = (ph.flags & F_PRENORM) != 0;
+  const bf16* gamma = nullptr;
+  float eps = 0.f;
+  if (norm) {
+    gamma = (ph.flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_gamma)
+                                  : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
+    eps = (ph.flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
+  }
+  for (int m = warp; m < M; m += kConsumerWarps) {
+    const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)(m + row_off) * ld);
+    uint4* dst = xs + (size_t)m * cpr;
+    float ss = 0.f;
+    for (int c = lane; c < cpr; c += 32) {
+      uint4 v = __ldcg(src + c);
+      dst[c] = v;
+      if (norm) {
+        float a;
+        a = bf_lo(v.x); ss = fmaf(a, a, ss); a = bf_hi(v.x); ss = fmaf(a, a, ss);
+        a = bf_lo(v.y); ss = fmaf(a, a, ss); a = bf_hi(v.y); ss = fmaf(a, a, ss);
+        a = bf_lo(v.z); ss = fmaf(a, a, ss); a = bf_hi(v.z); ss = fmaf(a, a, ss);
+        a = bf_lo(v.w); ss = fmaf(a, a, ss); a = bf_hi(v.w); ss = fmaf(a, a, ss);
+      }
+    }
+    if (norm) {
+      ss = warp_sum(ss);
+      const float rs = rsqrtf(ss / (float)K + eps);
+      __syncwarp();
+      const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
+      for (int c = lane; c < cpr; c += 32) {
+        uint4 v = dst[c];
+        uint4 g = __ldg(g4 + c);
+        uint4 o;
+        o.x = pack_bf16x2(bf16r(bf_lo(v.x) * rs) * bf_lo(g.x), bf16r(bf_hi(v.x) * rs) * bf_hi(g.x));
+        o.y = pack_bf16x2(bf16r(bf_lo(v.y) * rs) * bf_lo(g.y), bf16r(bf_hi(v.y) * rs) * bf_hi(g.y));
+        o.z = pack_bf16x2(bf16r(bf_lo(v.z) * rs) * bf_lo(g.z), bf16r(bf_hi(v.z) * rs) * bf_hi(g.z));
+        o.w = pack_bf16x2(bf16r(bf_lo(v.w) * rs) * bf_lo(g.w), bf16r(bf_hi(v.w) * rs) * bf_hi(g.w));
+        dst[c] = o;
+      }
+      if ((ph.flags & F_WRITE_NORMED) && blockIdx.x == 0) {
+        __syncwarp();
+        uint4* hid = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID]);
+        for (int c = lane; c < cpr; c += 32) hid[c] = dst[c];
+      }
+    }
+  }
+}
+
+template <int MT>
+__device__ __forceinline__ void gemv_tile_compute(const uint4* __restrict__ tile, const uint4* __restrict__ xs, int rt,
+                                                  int cpr, int wpr, float* __restrict__ part) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = (cpr + wpr - 1) / wpr;
+  const int nunits = rt * wpr;
+  for (int u = warp; u < nunits; u += kConsumerWarps) {
+    const int row = u / wpr, s = u - row * wpr;
+    const int c0 = s * seg, c1 = min(cpr, c0 + seg);
+    float acc[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+    const uint4* wrow = tile + (size_t)row * cpr;
+#pragma unroll 4
+    for (int c = c0 + lane; c < c1; c += 32) {
+      const uint4 w = wrow[c];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const uint4 x = xs[m * cpr + c];
+        acc[m] = dot8(w, x, acc[m]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const float v = warp_sum(acc[m]);
+      if (lane == m) part[u * MT + m] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+
+// Finalise one tile: sum k-segment partials, apply the epilogue with PyTorch's bf16 rounding points.
+__device__ void gemv_tile_epilogue(const Phase& ph, const LaunchParams& p, const float* part, int row_base, int rt,
+                                   int wpr, int M) {
+  const bool swi = (ph.flags & F_SWIGLU) != 0;
+  const int nout = swi ? rt / 2 : rt;
+  const bf16* bias = nullptr;
+  if (ph.flags & F_BIAS)
+    bias = (ph.flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias)
+                                 : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+  const int ldo = p.ld[ph.out_buf];
+  for (int o = threadIdx.x; o < nout * M; o += kConsumerThreads) {
+    const int j = o / M, m = o - j * M;
+    float y;
+    int ocol;
+    if (swi) {
+      float g = 0.f, u = 0.f;
+      for (int s = 0; s < wpr; ++s) {
+        g += part[((2 * j) * wpr + s) * M + m];
+        u += part[((2 * j + 1) * wpr + s) * M + m];
+      }
+      g = bf16r(g);
+      u = bf16r(u);
+      y = bf16r(bf16r(silu_f(g)) * u);
+      ocol = (row_base >> 1) + j;
+    } else {
+      y = 0.f;
+      for (int s = 0; s < wpr; ++s) y += part[(j * wpr + s) * M + m];
+      ocol = row_base + j;
+      if (bias) y += __bfloat162float(bias[ocol]);
+      y = bf16r(y);
+    }
+    if (ph.flags & F_RESID) {
+      const bf16* res = reinterpret_cast<const bf16*>(p.bufs[ph.res_buf]);
+      y = bf16r(__bfloat162float(res[(size_t)m * p.ld[ph.res_buf] + ocol]) + y);
+    }
+    if (ph.flags & F_OUT_F32)
+      reinterpret_cast<float*>(p.bufs[ph.out_buf])[(size_t)m * ldo + ocol] = y;
+    else
+      reinterpret_cast<bf16*>(p.bufs[ph.out_buf])[(size_t)m * ldo + ocol] = __float2bfloat16_rn(y);
+  }
+}
+
+__device__ void gemv_phase_consume(const Phase& ph, const LaunchParams& p, const Smem& sm, unsigned& tile_it, int pidx) {
+  const int G = gridDim.x, cta = blockIdx.x;
+  const GemvPlan g = gemv_plan(ph, cta, G);
+  int M = phase_rows(ph, p), row_off = 0;
+  if (ph.flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
+  load_x(ph, p, sm, M, row_off);
+  cbar_sync();
+  const int cpr = (int)ph.K >> 3;
+  const uint4* xs = reinterpret_cast<const uint4*>(sm.xbuf);
+  float* partbuf = reinterpret_cast<float*>(sm.scratch);  // 2 x 1024 floats (rt*wpr*M <= 1024)
+  for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
+    const int stage = tile_it % p.n_stages;
+    const uint32_t parity = (tile_it / p.n_stages) & 1u;
+    const int row_base = g.r0 + t * g.rt;
+    const int rt = min(g.rt, g.r1 - row_base);
+    int wpr = 1;
+    while (rt * wpr < kConsumerWarps) wpr <<= 1;
+    float* part = partbuf + (tile_it & 1u) * 1024;
+    mbar_wait(&sm.full[stage], parity, p, DE_FULL_WAIT, pidx);
+    const uint4* tile = reinterpret_cast<const uint4*>(sm.ring + (size_t)stage * kStageBytes);
+    switch (M) {
+      case 1: gemv_tile_compute<1>(tile, xs, rt, cpr, wpr, part); break;
+      case 2: gemv_tile_compute<2>(tile, xs, rt, cpr, wpr, part); break;
+      case 3: gemv_tile_compute<3>(tile, xs, rt, cpr, wpr, part); break;
+      case 4: gemv_tile_compute<4>(tile, xs, rt, cpr, wpr, part); break;
+      case 5: gemv_tile_compute<5>(tile, xs, rt, cpr, wpr, part); break;
+      case 6: gemv_tile_compute<6>(tile, xs, rt, cpr, wpr, part); break;
+      case 7: gemv_tile_compute<7>(tile, xs, rt, cpr, wpr, part); break;
+      default: gemv_tile_compute<8>(tile, xs, rt, cpr, wpr, part); break;
+    }
+    cbar_sync();                                         // partials visible, weight tile fully read
+    if (threadIdx.x == 0) mbar_arrive(&sm.empty[stage]);  // hand the stage back to the producer
+    gemv_tile_epilogue(ph, p, part, row_base, rt, wpr, M);
+  }
+}
+
+// Producer side of one GEMV phase: stream this CTA's rows through the ring.
+__device__ void gemv_phase_produce(const Phase& ph, const LaunchParams& p, const Smem& sm, unsigned& tile_it, int pidx,
+                                   uint64_t pol_stream, uint64_t pol_keep) {
+  const GemvPlan g = gemv_plan(ph, blockIdx.x, gridDim.x);
+  const unsigned char* W = (ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_W)
+                                                 : p.arena + (size_t)ph.w_off * 16;
+  const size_t row_bytes = (size_t)ph.K * 2;
+  const uint64_t pol = (ph.flags & F_L2_KEEP) ? pol_keep : pol_stream;
+  for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
+    const int stage = tile_it % p.n_stages;
+    const uint32_t parity = ((tile_it / p.n_stages) & 1u) ^ 1u;
+    const int row_base = g.r0 + t * g.rt;
+    const int rt = min(g.rt, g.r1 - row_base);
+    const uint32_t bytes = (uint32_t)(rt * row_bytes);
+    mbar_wait(&sm.empty[stage], parity, p, DE_EMPTY_WAIT, pidx);
+    mbar_arrive_expect_tx(&sm.full[stage], bytes);
+    bulk_g2s(sm.ring + (size_t)stage * kStageBytes, W + (size_t)row_base * row_bytes, bytes, &sm.full[stage], pol);
+  }
+}
+
+// =================================================================================================
+// Attention phase: q/k RMSNorm + RoPE + KV append + split-KV GQA decode attention + combine.
+// =================================================================================================
+struct Group {
+  int first_row, nrows, slot, pos0, n_pad, rope_delta;
+};
+__device__ __forceinline__ int num_groups(const LaunchParams& p) { return p.mode == MODE_PREFILL ? 1 : p.n_rows; }
+__device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& p, int g) {
+  Group r;
+  if (p.mode == MODE_PREFILL) {
+    r.first_row = 0; r.nrows = p.n_rows; r.slot = p.stream0; r.pos0 = p.pf_pos0; r.n_pad = p.pf_n_pad;
+    r.rope_delta = p.pf_rope_delta;
+    return r;
+  }
+  r.nrows = (ph.flags & F_ROWS2) ? 2 : 1;
+  r.first_row = g * r.nrows;
+  r.slot = p.stream0 + g;
+  if (ph.stack == ST_TALKER) {
+    const StreamState* st = p.st + r.slot;
+    r.pos0 = (p.pos_override >= 0) ? p.pos_override : __ldcg(&st->position);
+    r.n_pad = __ldcg(&st->n_pad);
+    r.rope_delta = __ldcg(&st->rope_delta);
+  } else {
+    r.pos0 = (ph.flags & F_ROWS2) ? 0 : (int)ph.aux + 1;
+    r.n_pad = 0;
+    r.rope_delta = 0;
+  }
+  return r;
+}
+__device__ __forceinline__ int num_splits(int L, int ngroups, int nkv, int G) {
+  int cap = G / max(1, ngroups * nkv);
+  cap = max(1, min(cap, kMaxSplits));
+  int want = (L + 63) / 64;
+  return max(1, min(want, cap));
+}
+
+// RMSNorm over the 128-wide head + rotary embedding; lane owns elements [4*lane, 4*lane+4).
+__device__ __forceinline__ void head_norm_rope(float (&x)[4], const bf16* gamma, float eps, const bf16* cosr,
+                                               const bf16* sinr, int lane) {
+  float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+  ss = warp_sum(ss);
+  const float rs = rsqrtf(ss * (1.f / kHeadDim) + eps);
+  float y[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) y[i] = bf16r(bf16r(x[i] * rs) * __bfloat162float(gamma[lane * 4 + i]));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float partner = __shfl_xor_sync(0xffffffffu, y[i], 16);
+    const float rot = (lane < 16) ? -partner : partner;
+    const float c = __bfloat162float(cosr[lane * 4 + i]), s = __bfloat162float(sinr[lane * 4 + i]);
+    x[i] = bf16r(bf16r(y[i] * c) + bf16r(rot * s));
+  }
+}
+
+__device__ __forceinline__ void load4(const bf16* p, float (&x)[4]) {
+  const uint2 v = __ldcg(reinterpret_cast<const uint2*>(p));
+  x[0] = bf_lo(v.x); x[1] = bf_hi(v.x); x[2] = bf_lo(v.y); x[3] = bf_hi(v.y);
+}
+
+__device__ void attn_item(const Phase& ph, const LaunchParams& p, const Smem& sm, const Group& gr, int kvh, int sp,
+                          int nsplit) {
+  const StackRt& S = p.stacks[ph.stack];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = S.nq / S.nkv;
+  const int npairs = gr.nrows * gq;
+  const bf16* qkv = reinterpret_cast<const bf16*>(p.bufs[ph.stack == ST_TALKER ? BUF_TQKV : BUF_PQKV]);
+  const int ldq = p.ld[ph.stack == ST_TALKER ? BUF_TQKV : BUF_PQKV];
+  bf16* att = reinterpret_cast<bf16*>(p.bufs[ph.stack == ST_TALKER ? BUF_TATT : BUF_PATT]);
+  const int lda = p.ld[ph.stack == ST_TALKER ? BUF_TATT : BUF_PATT];
+  const bf16* qn = reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
+  const bf16* kn = reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+  const size_t head_base = (((size_t)ph.layer * S.n_slots + gr.slot) * S.nkv + kvh) * (size_t)S.max_pos * kHeadDim;
+  bf16* Kc = S.kcache + head_base;
+  bf16* Vc = S.vcache + head_base;
+  const int pos_last = gr.pos0 + gr.nrows - 1;
+  const int L = pos_last + 1 - gr.n_pad;
+  const int per = (L + nsplit - 1) / nsplit;
+  const int a = gr.n_pad + sp * per;
+  const int b = min(a + per, gr.n_pad + L);
+  float* qs = reinterpret_cast<float*>(sm.scratch);                  // [npairs<=16][128]
+  float* wp = reinterpret_cast<float*>(sm.scratch) + 16 * kHeadDim;  // [8][kPartStride]
+  const float scale = rsqrtf((float)kHeadDim);
+
+  // -- step 1: queries (norm + rope) to smem; new K/V rows of this chunk to the cache
+  for (int j = warp; j < npairs; j += kConsumerWarps) {
+    const int r = j / gq, qh = kvh * gq + (j - r * gq);
+    const int rp = min(max(gr.pos0 + r + gr.rope_delta, 0), S.rope_len - 1);
+    float x[4];
+    load4(qkv + (size_t)(gr.first_row + r) * ldq + qh * kHeadDim + lane * 4, x);
+    head_norm_rope(x, qn, S.eps, S.rope_cos + (size_t)rp * kHeadDim, S.rope_sin + (size_t)rp * kHeadDim, lane);
+    *reinterpret_cast<float4*>(qs + j * kHeadDim + lane * 4) = make_float4(x[0], x[1], x[2], x[3]);
+  }
+  for (int r = warp; r < gr.nrows; r += kConsumerWarps) {
+    const int pos = gr.pos0 + r;
+    if (pos >= a && pos < b) {
+      const int rp = min(max(pos + gr.rope_delta, 0), S.rope_len - 1);
+      float x[4];
+      load4(qkv + (size_t)(gr.first_row + r) * ldq + S.nq * kHeadDim + kvh * kHeadDim + lane * 4, x);
+      head_norm_rope(x, kn, S.eps, S.rope_cos + (size_t)rp * kHeadDim, S.rope_sin + (size_t)rp * kHeadDim, lane);
+      uint2 kk;
+      kk.x = pack_bf16x2(x[0], x[1]);
+      kk.y = pack_bf16x2(x[2], x[3]);
+      *reinterpret_cast<uint2*>(Kc + (size_t)pos * kHeadDim + lane * 4) = kk;
+      const uint2 vv = __ldcg(reinterpret_cast<const uint2*>(
+          qkv + (size_t)(gr.first_row + r) * ldq + (S.nq + S.nkv) * kHeadDim + kvh * kHeadDim + lane * 4));
+      *reinterpret_cast<uint2*>(Vc + (size_t)pos * kHeadDim + lane * 4) = vv;
+    }
+  }
+  cbar_sync();
+
+  // -- step 2: online-softmax attention over [a, b)
+  int wpp = 1;
+  if (npairs < kConsumerWarps) { wpp = kConsumerWarps / npairs; }
+  const bool split_warps = (npairs < kConsumerWarps) && (npairs * wpp == kConsumerWarps);
+  if (!split_warps) wpp = 1;
+  float* part_g = p.attn_part;
+  for (int j0 = (split_warps ? warp / wpp : warp); j0 < npairs; j0 += (split_warps ? npairs : kConsumerWarps)) {
+    const int j = j0;
+    const int sub = split_warps ? (warp - j * wpp) : 0;
+    const int r = j / gq, qh = kvh * gq + (j - r * gq);
+    const float4 q4 = *reinterpret_cast<const float4*>(qs + j * kHeadDim + lane * 4);
+    const int pend = min(b, gr.pos0 + r + 1);
+    float m_run = -INFINITY, l_run = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int pp = a + sub; pp < pend; pp += 4 * wpp) {
+      uint2 kk[4], vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = pp + u * wpp;
+        if (q < pend) {
+          kk[u] = __ldcg(reinterpret_cast<const uint2*>(Kc + (size_t)q * kHeadDim + lane * 4));
+          vv[u] = __ldcg(reinterpret_cast<const uint2*>(Vc + (size_t)q * kHeadDim + lane * 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = pp + u * wpp;
+        if (q < pend) {
+          float s = q4.x * bf_lo(kk[u].x) + q4.y * bf_hi(kk[u].x) + q4.z * bf_lo(kk[u].y) + q4.w * bf_hi(kk[u].y);
+          s = warp_sum(s) * scale;
+          const float m_new = fmaxf(m_run, s);
+          const float corr = expf(m_run - m_new);
+          const float pr = expf(s - m_new);
+          l_run = l_run * corr + pr;
+          acc[0] = acc[0] * corr + pr * bf_lo(vv[u].x);
+          acc[1] = acc[1] * corr + pr * bf_hi(vv[u].x);
+          acc[2] = acc[2] * corr + pr * bf_lo(vv[u].y);
+          acc[3] = acc[3] * corr + pr * bf_hi(vv[u].y);
+          m_run = m_new;
+        }
+      }
+    }
+    if (split_warps) {
+      float* w = wp + warp * kPartStride;
+      if (lane == 0) { w[0] = m_run; w[1] = l_run; }
+      *reinterpret_cast<float4*>(w + 4 + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+      // this warp owns the whole pair: emit directly
+      const int row = gr.first_row + r;
+      if (nsplit == 1) {
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        uint2 o;
+        o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+        o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+        *reinterpret_cast<uint2*>(att + (size_t)row * lda + qh * kHeadDim + lane * 4) = o;
+      } else {
+        float* dst = part_g + (((size_t)row * S.nq + qh) * kMaxSplits + sp) * kPartStride;
+        if (lane == 0) { dst[0] = m_run; dst[1] = l_run; }
+        *reinterpret_cast<float4*>(dst + 4 + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      }
+    }
+  }
+  if (split_warps) {
+    cbar_sync();
+    // merge the wpp warps of each pair
+    for (int o = threadIdx.x; o < npairs * kHeadDim; o += kConsumerThreads) {
+      const int j = o / kHeadDim, dd = o - j * kHeadDim;
+      const int r = j / gq, qh = kvh * gq + (j - r * gq);
+      const int row = gr.first_row + r;
+      float M = -INFINITY;
+      for (int s = 0; s < wpp; ++s) M = fmaxf(M, wp[(j * wpp + s) * kPartStride]);
+      float Lsum = 0.f, O = 0.f;
+      for (int s = 0; s < wpp; ++s) {
+        const float* w = wp + (j * wpp + s) * kPartStride;
+        const float f = (w[0] == -INFINITY) ? 0.f : expf(w[0] - M);
+        Lsum += w[1] * f;
+        O += w[4 + dd] * f;
+      }
+      if (nsplit == 1) {
+        att[(size_t)row * lda + qh * kHeadDim + dd] = __float2bfloat16_rn(Lsum > 0.f ? O / Lsum : 0.f);
+      } else {
+        float* dst = part_g + (((size_t)row * S.nq + qh) * kMaxSplits + sp) * kPartStride;
+        if (dd == 0) { dst[0] = M; dst[1] = Lsum; }
+        dst[4 + dd] = O;
+      }
+    }
+  }
+  if (nsplit > 1) {
+    // -- step 3: last-arriving split of this (sequence, kv head) combines the partials (fixed order => deterministic)
+    __threadfence();
+    cbar_sync();
+    int* flag = sm.ctl + 4;
+    if (threadIdx.x == 0) {
+      unsigned* cnt = p.attn_cnt + (gr.slot - p.stream0) * S.nkv + kvh;
+      const unsigned old = atomicAdd(cnt, 1u);
+      const int last = (old == (unsigned)(nsplit - 1));
+      if (last) { *cnt = 0; __threadfence(); }
+      *flag = last;
+    }
+    cbar_sync();
+    if (*flag) {
+      for (int o = threadIdx.x; o < npairs * kHeadDim; o += kConsumerThreads) {
+        const int j = o / kHeadDim, dd = o - j * kHeadDim;
+        const int r = j / gq, qh = kvh * gq + (j - r * gq);
+        const int row = gr.first_row + r;
+        const float* src = part_g + (((size_t)row * S.nq + qh) * kMaxSplits) * kPartStride;
+        float M = -INFINITY;
+        for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(src + s * kPartStride));
+        float Lsum = 0.f, O = 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+          const float ms = __ldcg(src + s * kPartStride);
+          const float f = (ms == -INFINITY) ? 0.f : expf(ms - M);
+          Lsum += __ldcg(src + s * kPartStride + 1) * f;
+          O += __ldcg(src + s * kPartStride + 4 + dd) * f;
+        }
+        att[(size_t)row * lda + qh * kHeadDim + dd] = __float2bfloat16_rn(Lsum > 0.f ? O / Lsum : 0.f);
+      }
+    }
+  }
+  cbar_sync();
+}
+
+__device__ void attn_phase(const Phase& ph, const LaunchParams& p, const Smem& sm) {
+  const StackRt& S = p.stacks[ph.stack];
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int ng = num_groups(p);
+  int item = 0;
+  for (int g = 0; g < ng; ++g) {
+    const Group gr = get_group(ph, p, g);
+    const int L = gr.pos0 + gr.nrows - gr.n_pad;
+    const int nsplit = num_splits(L, ng, S.nkv, G);
+    const int nitems = S.nkv * nsplit;
+    // first item of this group that belongs to this CTA
+    int first = (cta - item % G + G) % G;
+    for (int it = first; it < nitems; it += G) attn_item(ph, p, sm, gr, it / nsplit, it % nsplit, nsplit);
+    item += nitems;
+  }
+}
+
+// =================================================================================================
+// Sampling (sampling.py:10-66) — block-wide, 256 consumer threads, one stream per CTA
+// =================================================================================================
+__device__ __forceinline__ uint32_t f2key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+struct SampleScratch {
+  float* sl;       // [V] working logits
+  unsigned* hist;  // [256]
+  float* redf;     // [32]
+  int* redi;       // [32]
+};
+__device__ __forceinline__ SampleScratch sample_scratch(const Smem& sm) {
+  SampleScratch s;
+  s.sl = reinterpret_cast<float*>(sm.scratch);
+  s.hist = reinterpret_cast<unsigned*>(sm.scratch + 13 * 1024);
+  s.redf = reinterpret_cast<float*>(sm.scratch + 14 * 1024);
+  s.redi = reinterpret_cast<int*>(sm.scratch + 14 * 1024 + 256);
+  return s;
+}
+
+__device__ float block_sum(float v, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_sum(v);
+  cbar_sync();
+  if (lane == 0) red[warp] = v;
+  cbar_sync();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kConsumerWarps; ++w) t += red[w];
+  return t;
+}
+__device__ float block_max(float v, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_max(v);
+  cbar_sync();
+  if (lane == 0) red[warp] = v;
+  cbar_sync();
+  float t = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < kConsumerWarps; ++w) t = fmaxf(t, red[w]);
+  return t;
+}
+// argmax with lowest-index tie-break (torch.argmax on a 1-row tensor)
+__device__ int block_argmax(const float* sl, int V, float* redf, int* redi, float* out_val) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += kConsumerThreads) {
+    const float x = sl[i];
+    if (x > bv || (x == bv && i < bi)) { bv = x; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  cbar_sync();
+  if (lane == 0) { redf[warp] = bv; redi[warp] = bi; }
+  cbar_sync();
+  bv = redf[0]; bi = redi[0];
+#pragma unroll
+  for (int w = 1; w < kConsumerWarps; ++w) {
+    const float ov = redf[w]; const int oi = redi[w];
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (out_val) *out_val = bv;
+  return bi == 0x7fffffff ? 0 : bi;
+}
+
+// k-th largest value (counting multiplicity) by 4-pass radix select on order-preserving keys.
+__device__ float kth_largest(const float* sl, int V, int k, unsigned* hist, int* redi) {
+  uint32_t prefix = 0;
+  int krem = k;
+  const int lane = threadIdx.x & 31;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    cbar_sync();
+    hist[threadIdx.x] = 0;
+    cbar_sync();
+    for (int i = threadIdx.x; i < V; i += kConsumerThreads) {
+      const uint32_t key = f2key(sl[i]);
+      const bool match = (pass == 0) || ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+      if (match) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    }
+    cbar_sync();
+    if (threadIdx.x < 32) {
+      // lane l covers bins [255-8l-7, 255-8l], scanned from the top
+      unsigned s = 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s += hist[255 - 8 * lane - t];
+      unsigned incl = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, incl >= (unsigned)krem);
+      const int sel = __ffs(ballot) - 1;
+      if (lane == sel) {
+        unsigned above = incl - s;
+        int digit = 255 - 8 * lane;
+        for (int t = 0; t < 8; ++t) {
+          const unsigned c = hist[255 - 8 * lane - t];
+          if (above + c >= (unsigned)krem) { digit = 255 - 8 * lane - t; break; }
+          above += c;
+        }
+        redi[0] = digit;
+        redi[1] = krem - (int)above;
+      }
+    }
+    cbar_sync();
+    prefix |= ((uint32_t)redi[0]) << shift;
+    krem = redi[1];
+  }
+  cbar_sync();
+  return key2f(prefix);
+}
+
+struct SampleArgs {
+  int V;
+  int do_sample, top_k;
+  float top_p, temperature, rep_pen;
+  const uint8_t* seen;  // may be null
+  int suppress_start;   // ids >= this (except eos) are masked; V => none
+  int eos;
+  int suppress_eos;
+  int round_bf16;       // logits came from a bf16 tensor: round every intermediate like the reference's bf16 ops
+  unsigned long long seed, draw;
+};
+
+__device__ int sample_row(const float* logits_g, const SampleArgs& a, const SampleScratch& sc) {
+  float* sl = sc.sl;
+  const int V = a.V;
+  // 1. load + repetition penalty (sampling.py:22-29, before suppression) + suppression + temperature
+  for (int i = threadIdx.x; i < V; i += kConsumerThreads) {
+    float x = __ldcg(logits_g + i);
+    if (a.seen && a.rep_pen != 1.0f && __ldcg(a.seen + i)) {
+      x = (x > 0.f) ? x / a.rep_pen : x * a.rep_pen;
+      if (a.round_bf16) x = bf16r(x);
+    }
+    if (i >= a.suppress_start && i != a.eos) x = -INFINITY;
+    if (a.suppress_eos && i == a.eos) x = -INFINITY;
+    if (a.do_sample) {
+      x = x / a.temperature;
+      if (a.round_bf16) x = bf16r(x);
+    }
+    sl[i] = x;
+  }
+  cbar_sync();
+  float vmax;
+  const int imax = block_argmax(sl, V, sc.redf, sc.redi, &vmax);
+  if (!a.do_sample) return imax;
+  // 2. top-k: keep x >= k-th largest (ties survive, sampling.py:54-56)
+  if (a.top_k > 0 && a.top_k < V) {
+    const float thr = kth_largest(sl, V, a.top_k, sc.hist, sc.redi);
+    for (int i = threadIdx.x; i < V; i += kConsumerThreads)
+      if (sl[i] < thr) sl[i] = -INFINITY;
+    cbar_sync();
+  }
+  // 3. top-p on the sorted distribution (sampling.py:57-65): rank j is dropped iff cum_j > top_p and j > 0
+  if (a.top_p < 1.0f) {
+    float loc = 0.f;
+    for (int i = threadIdx.x; i < V; i += kConsumerThreads) loc += expf(sl[i] - vmax);
+    const float total = block_sum(loc, sc.redf);
+    const float P = a.top_p * total;
+    uint32_t lo = 0u, hi = 0xffffffffu;  // smallest key t with mass(key >= t) <= P
+    for (int it = 0; it < 32; ++it) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      float msum = 0.f;
+      for (int i = threadIdx.x; i < V; i += kConsumerThreads) {
+        const float x = sl[i];
+        if (f2key(x) >= mid) msum += expf(x - vmax);
+      }
+      msum = block_sum(msum, sc.redf);
+      if (msum <= P) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t tkey = hi;
+    // boundary value v* = largest key below tkey; its first j ties (index order) may still fit under P
+    uint32_t bk = 0;
+    for (int i = threadIdx.x; i < V; i += kConsumerThreads) {
+      const uint32_t k = f2key(sl[i]);
+      if (k < tkey && k > bk) bk = k;
+    }
+    const float bval = block_max(key2f(bk), sc.redf);
+    float above = 0.f;
+    for (int i = threadIdx.x; i < V; i += kConsumerThreads)
+      if (f2key(sl[i]) >= tkey) above += expf(sl[i] - vmax);
+    above = block_sum(above, sc.redf);
+    int keep_ties = 0;
+    if (bval > -INFINITY) {
+      const float pe = expf(bval - vmax);
+      keep_ties = (int)floorf((P - above) / pe);
+      if (keep_ties < 0) keep_ties = 0;
+    }
+    // rank ties by index with a serial walk per thread over a contiguous segment + block scan
+    const int seg = (V + kConsumerThreads - 1) / kConsumerThreads;
+    const int i0 = threadIdx.x * seg, i1 = min(V, i0 + seg);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += (sl[i] == bval) ? 1 : 0;
+    // exclusive scan of cnt across threads
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    cbar_sync();
+    if (lane == 31) sc.redi[warp] = incl;
+    cbar_sync();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += sc.redi[w];
+    int rank = base + incl - cnt;
+    for (int i = i0; i < i1; ++i) {
+      const float x = sl[i];
+      if (f2key(x) >= tkey) continue;
+      if (x == bval && bval > -INFINITY) {
+        if (rank < keep_ties) { ++rank; continue; }
+        ++rank;
+      }
+      if (i != imax) sl[i] = -INFINITY;
+    }
+    cbar_sync();
+  }
+  // 4. multinomial(softmax) by inverse CDF on one Philox uniform
+  const int seg = (V + kConsumerThreads - 1) / kConsumerThreads;
+  const int i0 = threadIdx.x * seg, i1 = min(V, i0 + seg);
+  float loc = 0.f;
+  for (int i = i0; i < i1; ++i) loc += expf(sl[i] - vmax);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float incl = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  cbar_sync();
+  if (lane == 31) sc.redf[warp] = incl;
+  if (threadIdx.x == 0) sc.redi[16] = 0x7fffffff;
+  cbar_sync();
+  float base = 0.f, total = 0.f;
+  for (int w = 0; w < kConsumerWarps; ++w) {
+    if (w < warp) base += sc.redf[w];
+    total += sc.redf[w];
+  }
+  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)a.draw, (uint32_t)(a.draw >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+  const float u = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
+  const float target = u * total;
+  const float excl = base + incl - loc;
+  if (loc > 0.f && target >= excl && target < excl + loc) {
+    float c = excl;
+    int pick = -1;
+    for (int i = i0; i < i1; ++i) {
+      const float e = expf(sl[i] - vmax);
+      if (e > 0.f) { pick = i; c += e; if (target < c) break; }
+    }
+    if (pick >= 0) atomicMin(&sc.redi[16], pick);
+  }
+  cbar_sync();
+  int tok = sc.redi[16];
+  if (tok == 0x7fffffff) tok = imax;  // rounding fell off the end of the CDF
+  return tok;
+}
+
+// Copy one bf16 row (n elements, multiple of 8) between global buffers with all consumer threads.
+__device__ __forceinline__ void copy_row(bf16* dst, const bf16* src, int n) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (int c = threadIdx.x; c < (n >> 3); c += kConsumerThreads) d[c] = __ldcg(s + c);
+}
+
+__device__ void sample_phase(const Phase& ph, const LaunchParams& p, const Smem& sm, int iter) {
+  const SampleScratch sc = sample_scratch(sm);
+  const int Ht = p.stacks[ST_TALKER].hidden;
+  const int ncb = p.n_code_groups - 1;
+  int* bc = sm.ctl + 8;
+  for (int b = blockIdx.x; b < (p.mode == MODE_PREFILL ? 1 : p.n_rows); b += gridDim.x) {
+    const int slot = p.stream0 + b;
+    StreamState* st = p.st + slot;
+    const int done = __ldcg(&st->done);
+    bf16* pin = reinterpret_cast<bf16*>(p.bufs[p.has_s2m ? BUF_PIN : BUF_PX]);
+    const int ldpin = p.ld[p.has_s2m ? BUF_PIN : BUF_PX];
+    if (ph.kind == SMP_PRED || ph.kind == SMP_PRED_ONLY) {
+      const int i = ph.aux;  // codebook step 0..ncb-1
+      const int Vp = p.stacks[ST_PRED].vocab;
+      const int lrow = (ph.flags & F_ROWS2) ? 2 * b + 1 : b;
+      const float* lg = reinterpret_cast<const float*>(p.bufs[BUF_LOGITS]) + (size_t)lrow * p.ld[BUF_LOGITS];
+      if (p.pred_logits_all) {
+        for (int v = threadIdx.x; v < Vp; v += kConsumerThreads) p.pred_logits_all[(size_t)i * Vp + v] = __ldcg(lg + v);
+      }
+      SampleArgs a;
+      a.V = Vp; a.do_sample = p.sub.do_sample; a.top_k = p.sub.top_k; a.top_p = p.sub.top_p;
+      a.temperature = p.sub.temperature; a.rep_pen = 1.0f; a.seen = nullptr; a.suppress_start = Vp; a.eos = -1;
+      a.suppress_eos = 0; a.round_bf16 = 1; a.seed = p.pol.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(slot + 1));
+      a.draw = __ldcg(&st->draws) + (unsigned long long)(i + 1);
+      const int tok = sample_row(lg, a, sc);
+      if (threadIdx.x == 0) st->cur_codes[i + 1] = tok;
+      if (i + 1 < ncb) {
+        // next predictor input row: codec_embeds[i](tok)  (predictor_graph.py:144)
+        copy_row(pin + (size_t)b * ldpin, p.pred_embeds[i] + (size_t)tok * Ht, Ht);
+      } else if (ph.kind == SMP_PRED) {
+        // frame complete: append [c0..c15], then build the next talker input (generate.py:159-171)
+        const int nfr = __ldcg(&st->n_frames);
+        const int c0 = __ldcg(&st->token);
+        if (!done) {
+          if (threadIdx.x < p.n_code_groups && nfr < p.max_frames) {
+            const int code = (threadIdx.x == 0) ? c0 : (threadIdx.x == ncb ? tok : __ldcg(&st->cur_codes[threadIdx.x]));
+            st->codes[(size_t)nfr * p.n_code_groups + threadIdx.x] = code;
+          }
+          if (threadIdx.x == 0) {
+            st->n_frames = nfr + 1;
+            st->seen[c0] = 1;
+            st->draws = __ldcg(&st->draws) + 32ull;
+          }
+        }
+        cbar_sync();
+        const int gs = __ldcg(&st->gen_step);
+        const int ntr = __ldcg(&st->n_trailing);
+        const bf16* text = (gs < ntr) ? st->trailing + (size_t)gs * Ht : st->pad_embed;
+        bf16* tx = reinterpret_cast<bf16*>(p.bufs[BUF_TX]) + (size_t)b * p.ld[BUF_TX];
+        for (int c = threadIdx.x; c < Ht; c += kConsumerThreads) {
+          float s = __bfloat162float(p.codec_embed[(size_t)c0 * Ht + c]);
+          for (int g = 0; g < ncb; ++g) {
+            const int code = (g == ncb - 1) ? tok : __ldcg(&st->cur_codes[g + 1]);
+            s += __bfloat162float(p.pred_embeds[g][(size_t)code * Ht + c]);
+          }
+          const float e = bf16r(s);
+          tx[c] = __float2bfloat16_rn(e + __bfloat162float(text[c]));
+        }
+        // static-cache bound (generate.py:174-177): the frame stays, decoding stops
+        if (threadIdx.x == 0 && !done) {
+          const int pos = __ldcg(&st->position);
+          if (pos >= p.stacks[ST_TALKER].max_pos - 1) st->done = 2;
+        }
+      }
+    } else {
+      // SMP_TALKER / SMP_PREFILL: first-codebook sampler (generate.py:124-134, :182-197)
+      const int Vt = p.stacks[ST_TALKER].vocab;
+      const float* lg = reinterpret_cast<const float*>(p.bufs[BUF_LOGITS]) + (size_t)b * p.ld[BUF_LOGITS];
+      const int nfr = __ldcg(&st->n_frames);
+      SampleArgs a;
+      a.V = Vt; a.do_sample = p.pol.do_sample; a.top_k = p.pol.top_k; a.top_p = p.pol.top_p;
+      a.temperature = p.pol.temperature; a.rep_pen = p.pol.rep_pen;
+      a.seen = (ph.kind == SMP_TALKER && nfr > 0) ? st->seen : nullptr;
+      a.suppress_start = max(0, Vt - p.pol.suppress_tail); a.eos = p.eos_id;
+      a.suppress_eos = (ph.kind == SMP_PREFILL) ? (p.pol.min_new_tokens > 0) : (nfr < p.pol.min_new_tokens);
+      a.round_bf16 = 1;
+      a.seed = p.pol.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(slot + 1));
+      a.draw = __ldcg(&st->draws);
+      const int tok = sample_row(lg, a, sc);
+      const bool live = (ph.kind == SMP_PREFILL) || !done;
+      if (threadIdx.x == 0 && live) {
+        st->token = tok;
+        st->draws = a.draw + 1ull;
+        if (ph.kind == SMP_TALKER) {
+          st->position = __ldcg(&st->position) + 1;
+          st->gen_step = __ldcg(&st->gen_step) + 1;
+        }
+        if (tok == p.eos_id) st->done = 1;  // generate.py:150 — checked before the next frame is built
+      }
+      if (live) {
+        // predictor pass-0 input rows: [past_hidden ; codec_embed(token)]  (generate.py:154-155)
+        // (addressed by stream slot so a later prefill of another stream cannot clobber them)
+        const bf16* hid = reinterpret_cast<const bf16*>(p.bufs[BUF_HID]) + (size_t)b * p.ld[BUF_HID];
+        copy_row(pin + (size_t)(2 * slot) * ldpin, hid, Ht);
+        copy_row(pin + (size_t)(2 * slot + 1) * ldpin, p.codec_embed + (size_t)tok * Ht, Ht);
+      }
+    }
+    cbar_sync();
+  }
+  (void)bc;
+  (void)iter;
+}
+
+// =================================================================================================
+// Kernel
+// =================================================================================================
+__global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_constant__ LaunchParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const Smem sm = carve_smem(smem_raw, p);
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    sm.ctl[0] = 0;
+    fence_barrier_init();
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.prog);
+    uint4* dst = reinterpret_cast<uint4*>(sm.prog);
+    for (int i = tid; i < p.n_phases * 2; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  if (tid >= kConsumerThreads) {
+    // ------------------------------ producer warp ------------------------------
+    if (tid == kConsumerThreads) {
+      const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+      unsigned tile_it = 0;
+      for (int iter = 0; iter < p.n_iters; ++iter) {
+        if (iter > 0) {
+          Spin s;
+          int go;
+          while ((go = ld_volatile_shared_i32(&sm.ctl[0])) >= 0 && go < iter) {
+            __nanosleep(64);
+            s.tick(p, DE_HANDSHAKE, -1, iter);
+          }
+          if (go < 0) break;
+        }
+        for (int i = 0; i < p.n_phases; ++i) {
+          const Phase& ph = sm.prog[i];
+          if (ph.type == PH_GEMV) gemv_phase_produce(ph, p, sm, tile_it, i, pol_stream, pol_keep);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------- consumer warps --------------------------------
+  unsigned epoch = 0, tile_it = 0;
+  for (int iter = 0; iter < p.n_iters; ++iter) {
+    for (int i = 0; i < p.n_phases; ++i) {
+      const Phase& ph = sm.prog[i];
+      switch (ph.type) {
+        case PH_GEMV: gemv_phase_consume(ph, p, sm, tile_it, i); break;
+        case PH_ATTN: attn_phase(ph, p, sm); break;
+        case PH_SAMPLE: sample_phase(ph, p, sm, iter); break;
+        default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
+      }
+      grid_sync(p, epoch, i);
+    }
+    if (p.mode == MODE_FRAMES && iter + 1 < p.n_iters) {
+      // every CTA evaluates the same predicate on the same (barrier-ordered) state
+      int all_done = 1;
+      for (int b = 0; b < p.n_rows; ++b) all_done &= (__ldcg(&p.st[p.stream0 + b].done) != 0);
+      if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], all_done ? -1 : iter + 1);
+      if (all_done) break;
+    }
+  }
+}
+
+// Small single-CTA kernels -----------------------------------------------------------------------
+// Stand-alone sampler behind fq3_sample (sampling.py parity tests and the duck-typed host loop).
+__global__ void __launch_bounds__(kConsumerThreads, 1)
+fq3_sample_kernel(const float* logits, SampleArgs a, const long long* history, int n_history, uint8_t* seen_scratch,
+                  long long* out) {
+  __shared__ __align__(16) unsigned char scratch[kScratchBytes];
+  Smem sm;
+  sm.scratch = scratch;
+  const SampleScratch sc = sample_scratch(sm);
+  if (history && n_history > 0 && a.rep_pen != 1.0f) {
+    for (int i = threadIdx.x; i < a.V; i += kConsumerThreads) seen_scratch[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_history; i += kConsumerThreads) {
+      const long long t = history[i];
+      if (t >= 0 && t < a.V) seen_scratch[t] = 1;
+    }
+    __syncthreads();
+    a.seen = seen_scratch;
+  } else {
+    a.seen = nullptr;
+  }
+  const int tok = sample_row(logits, a, sc);
+  if (threadIdx.x == 0) out[0] = tok;
+}
+
+// apply_repetition_penalty (sampling.py:10-29) in place on fp32 logits; history marks a bitmap first.
+__global__ void __launch_bounds__(kConsumerThreads, 1)
+fq3_rep_penalty_kernel(float* logits, int V, const long long* history, int n_history, float penalty, int round_bf16,
+                       uint8_t* seen) {
+  for (int i = threadIdx.x; i < V; i += kConsumerThreads) seen[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_history; i += kConsumerThreads) {
+    const long long t = history[i];
+    if (t >= 0 && t < V) seen[t] = 1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V; i += kConsumerThreads) {
+    if (__ldcg(seen + i)) {
+      float x = logits[i];
+      x = (x > 0.f) ? x / penalty : x * penalty;
+      logits[i] = round_bf16 ? bf16r(x) : x;
+    }
+  }
+}
+
+__global__ void fq3_reset_stream_kernel(StreamState* st, int V) {
+  for (int i = threadIdx.x; i < V; i += blockDim.x) st->seen[i] = 0;
+  if (threadIdx.x == 0) {
+    st->token = 0; st->position = 0; st->gen_step = 0; st->n_frames = 0; st->done = 0; st->n_pad = 0;
+    st->rope_delta = 0; st->n_trailing = 0; st->draws = 0ull;
+    for (int i = 0; i < 32; ++i) st->cur_codes[i] = 0;
+  }
+}
+
+__global__ void fq3_set_state_kernel(StreamState* st, int token, int position, int gen_step, int set_mask, int n_pad,
+                                     int rope_delta, int n_trailing) {
+  if (threadIdx.x == 0) {
+    if (set_mask & 1) st->token = token;
+    if (set_mask & 2) { st->n_pad = n_pad; st->rope_delta = rope_delta; }
+    if (set_mask & 4) st->n_trailing = n_trailing;
+    if (set_mask & 8) { st->position = position; st->gen_step = gen_step; }
+    if (set_mask & 16) st->done = 0;
+  }
+}
+
+// K/V import: src [nkv, T, 128] -> cache [nkv, max_pos, 128] of one (layer, slot)
+__global__ void fq3_import_kv_kernel(bf16* kdst, bf16* vdst, const bf16* k, const bf16* v, int nkv, int T, int max_pos) {
+  const size_t n = (size_t)nkv * T * (kHeadDim / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (kHeadDim / 8));
+    const size_t t = (i / (kHeadDim / 8)) % T;
+    const size_t h = i / ((size_t)(kHeadDim / 8) * T);
+    const size_t d = (h * max_pos + t) * (kHeadDim / 8) + c;
+    reinterpret_cast<uint4*>(kdst)[d] = reinterpret_cast<const uint4*>(k)[i];
+    reinterpret_cast<uint4*>(vdst)[d] = reinterpret_cast<const uint4*>(v)[i];
+  }
+}
+
+__global__ void fq3_codes_to_i64_kernel(const int* cur_codes, int n, long long* out) {
+  if (threadIdx.x < n) out[threadIdx.x] = cur_codes[threadIdx.x + 1];
+}
+
+}  // namespace fq3
