@@ -169,6 +169,8 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   p.pred_logits_all = nullptr;
   p.pos_override = -1;
   p.watchdog_ns = e->watchdog_ns;
+  p.debug = 0;
+  if (const char* d = getenv("FQ3_DEBUG")) p.debug = atoi(d);
   p.n_iters = 1;
   p.stream0 = 0;
 }

@@ -149,6 +149,7 @@ struct LaunchParams {
   // smem carve-up
   int n_stages, xbuf_bytes, prog_bytes;
   unsigned long long watchdog_ns;
+  int debug;  // timing ablations (FQ3_DEBUG): 1 no grid barrier, 2 no GEMV math, 4 no attention, 8 no activation load
 };
 
 enum DevErr : int { DE_NONE = 0, DE_GRID_BAR = 1, DE_FULL_WAIT = 2, DE_EMPTY_WAIT = 3, DE_HANDSHAKE = 4, DE_BAD_PHASE = 5 };

@@ -338,7 +338,7 @@ __device__ void gemv_phase_consume(const Phase& ph, const LaunchParams& p, const
   const GemvPlan g = gemv_plan(ph, cta, G);
   int M = phase_rows(ph, p), row_off = 0;
   if (ph.flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
-  load_x(ph, p, sm, M, row_off);
+  if (!(p.debug & 8)) load_x(ph, p, sm, M, row_off);
   cbar_sync();
   const int cpr = (int)ph.K >> 3;
   const uint4* xs = reinterpret_cast<const uint4*>(sm.xbuf);
@@ -353,7 +353,7 @@ __device__ void gemv_phase_consume(const Phase& ph, const LaunchParams& p, const
     float* part = partbuf + (tile_it & 1u) * 1024;
     mbar_wait(&sm.full[stage], parity, p, DE_FULL_WAIT, pidx);
     const uint4* tile = reinterpret_cast<const uint4*>(sm.ring + (size_t)stage * kStageBytes);
-    switch (M) {
+    if (!(p.debug & 2)) switch (M) {
       case 1: gemv_tile_compute<1>(tile, xs, rt, cpr, wpr, part); break;
       case 2: gemv_tile_compute<2>(tile, xs, rt, cpr, wpr, part); break;
       case 3: gemv_tile_compute<3>(tile, xs, rt, cpr, wpr, part); break;
@@ -365,7 +365,7 @@ __device__ void gemv_phase_consume(const Phase& ph, const LaunchParams& p, const
     }
     cbar_sync();                                         // partials visible, weight tile fully read
     if (threadIdx.x == 0) mbar_arrive(&sm.empty[stage]);  // hand the stage back to the producer
-    gemv_tile_epilogue(ph, p, part, row_base, rt, wpr, M);
+    if (!(p.debug & 2)) gemv_tile_epilogue(ph, p, part, row_base, rt, wpr, M);
   }
 }
 
@@ -1085,11 +1085,11 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
       const Phase& ph = sm.prog[i];
       switch (ph.type) {
         case PH_GEMV: gemv_phase_consume(ph, p, sm, tile_it, i); break;
-        case PH_ATTN: attn_phase(ph, p, sm); break;
+        case PH_ATTN: if (!(p.debug & 4)) attn_phase(ph, p, sm); break;
         case PH_SAMPLE: sample_phase(ph, p, sm, iter); break;
         default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
       }
-      grid_sync(p, epoch, i);
+      if (p.debug & 1) cbar_sync(); else grid_sync(p, epoch, i);
     }
     if (p.mode == MODE_FRAMES && iter + 1 < p.n_iters) {
       // every CTA evaluates the same predicate on the same (barrier-ordered) state
@@ -1150,7 +1150,7 @@ __global__ void fq3_reset_stream_kernel(StreamState* st, int V) {
   for (int i = threadIdx.x; i < V; i += blockDim.x) st->seen[i] = 0;
   if (threadIdx.x == 0) {
     st->token = 0; st->position = 0; st->gen_step = 0; st->n_frames = 0; st->done = 0; st->n_pad = 0;
-    st->rope_delta = 0; st->n_trailing = 0; st->draws = 0ull;
+    st->rope_delta = 0; st->draws = 0ull;  // text conditioning (n_trailing) is set separately and survives a reset
     for (int i = 0; i < 32; ++i) st->cur_codes[i] = 0;
   }
 }
