@@ -20,6 +20,50 @@ __device__ __forceinline__ void bulk(void* d, const void* s, uint32_t n, uint64_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(d)), "l"(s), "r"(n), "r"(s32(b)) : "memory");
 }
 
+__device__ __forceinline__ void bulk_hint(void* d, const void* s, uint32_t n, uint64_t* b, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(s32(d)), "l"(s), "r"(n), "r"(s32(b)), "l"(pol) : "memory");
+}
+// kernel-like pattern: the buffer is a sequence of "matrices" of G*chunk bytes; CTA c reads bytes [c*chunk, (c+1)*chunk) of
+// each matrix in turn, in tiles of <= S bytes (last tile of a chunk partial).  hint: 0 none, 1 evict_first, 2 evict_last.
+// CW consumer warps each arrive on every tile (like the decode kernel).
+__global__ void __launch_bounds__(512, 1) k_chunk(const uint8_t* __restrict__ base, int nmat, int chunk, int S, int NS, int CW, int hint, unsigned* sink) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint64_t* full = (uint64_t*)sm;
+  uint64_t* empty = full + 64;
+  uint8_t* ring = sm + 1024;
+  const int tid = threadIdx.x;
+  if (tid == 0) { for (int i = 0; i < NS; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], CW); } asm volatile("fence.mbarrier_init.release.cluster;"); }
+  __syncthreads();
+  const size_t mat_bytes = (size_t)gridDim.x * chunk;
+  const int tpc = (chunk + S - 1) / S;
+  if (tid == CW * 32) {
+    uint64_t pol = 0;
+    if (hint == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (hint == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    int t = 0;
+    for (int m = 0; m < nmat; ++m) {
+      const uint8_t* src = base + (size_t)m * mat_bytes + (size_t)blockIdx.x * chunk;
+      for (int j = 0; j < tpc; ++j, ++t) {
+        const int s = t % NS; const uint32_t ph = ((t / NS) & 1) ^ 1;
+        const uint32_t n = min(S, chunk - j * S);
+        mb_wait(&empty[s], ph);
+        mb_expect(&full[s], n);
+        if (hint) bulk_hint(ring + (size_t)s * S, src + (size_t)j * S, n, &full[s], pol);
+        else bulk(ring + (size_t)s * S, src + (size_t)j * S, n, &full[s]);
+      }
+    }
+  } else if (tid < CW * 32) {
+    const int l = tid & 31;
+    const int total = nmat * tpc;
+    for (int t = 0; t < total; ++t) {
+      const int s = t % NS; const uint32_t ph = (t / NS) & 1;
+      if (l == 0) mb_wait(&full[s], ph);
+      __syncwarp();
+      if (l == 0) mb_arrive(&empty[s]);
+    }
+  }
+}
+
 // each CTA streams `per_cta` bytes starting at base + cta*per_cta (contiguous slice), in tiles of S bytes
 template <int MODE>
 __global__ void __launch_bounds__(512, 1) k_tma(const uint8_t* __restrict__ base, size_t per_cta, int S, int NS, int P, int CW, unsigned* sink) {
@@ -102,6 +146,13 @@ int main(int argc, char** argv) {
     const size_t smem = 1024 + (size_t)NS * S;
     if (mode == 0) run(nm, [&] { k_tma<0><<<sms, CW * 32 + 32 * ((P + 31) / 32), smem>>>(buf, per, S, NS, P, CW, sink); }, per * sms);
     else run(nm, [&] { k_tma<2><<<sms, CW * 32 + 32, smem>>>(buf, per, S, NS, P, CW, sink); }, per * sms);
+  }
+  CK(cudaFuncSetAttribute(k_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  for (int hint : {0, 1, 2}) for (int chunk : {28672, 57344, 86016, 1 << 20}) for (int CW : {1, 15}) {
+    const int S = 16384, NS = 9;
+    const int nmat = (int)(total / ((size_t)sms * chunk));
+    snprintf(nm, sizeof nm, "chunk pattern hint=%d chunk=%dK CW=%d", hint, chunk / 1024, CW);
+    run(nm, [&] { k_chunk<<<sms, 512, 1024 + (size_t)NS * S>>>(buf, nmat, chunk, S, NS, CW, hint, sink); }, (size_t)nmat * sms * chunk);
   }
   for (int NSx : {2, 4, 6, 12}) {   // in-flight sweep at S=16K
     const int S = 16384; size_t per = (total / sms) / S * S;

@@ -155,6 +155,9 @@ int fq3_read_codes(fq3_engine* e, int stream_idx, int first_frame, int n, int32_
 /* Device address of the codes buffer int32 [max_frames, 16] of one stream (zero-copy consumers). */
 void* fq3_codes_device_ptr(fq3_engine* e, int stream_idx);
 
+/* Debug aid: per-phase clock64 marks of one CTA (enable with env FQ3_PROF=<cta index> at create time). */
+int fq3_debug_read_prof(fq3_engine* e, long long* out, int n_words);
+
 /* ---- building block exposed for parity tests ------------------------------------------------ */
 /* y[M,N] = epilogue(W[N,K] · prologue(x[M,K])) through the same persistent streaming kernel.
  * flags: bit0 pre-RMSNorm with gamma, bit1 bias, bit2 residual add, bit3 SwiGLU pairing (N = 2*I

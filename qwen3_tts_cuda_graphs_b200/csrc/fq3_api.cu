@@ -48,12 +48,12 @@ struct fq3_engine {
   int ncb = 15;
   void* bufs[kNumBufs] = {};
   int ld[kNumBufs] = {};
+  size_t buf_bytes[kNumBufs] = {};
   StackRt rt[2]{};
   StreamState* d_st = nullptr;
   std::vector<StreamState> h_st;
   float* attn_part = nullptr;
   unsigned* attn_cnt = nullptr;
-  unsigned* grid_bar = nullptr;
   int* err_host = nullptr;
   int* err_dev = nullptr;
   float* pred_logits_all = nullptr;
@@ -61,6 +61,11 @@ struct fq3_engine {
   Phase *d_frames = nullptr, *d_pred = nullptr, *d_talker = nullptr, *d_prefill = nullptr, *d_linear = nullptr;
   int n_frames_ph = 0, n_pred_ph = 0, n_talker_ph = 0, n_prefill_ph = 0;
   int64_t launches = 0;
+  long long* prof = nullptr;
+  int max_stages = 6;     // 6 x 16 KB in flight per SM saturates HBM (bench_micro/stream_bw.cu); the rest stays L1
+  int prof_cta = -1;
+  uint32_t epoch = 1;     // LL epoch counter (monotonic across launches)
+  int lin_words = 0;      // capacity (words per row) of the fq3_linear staging buffers
   unsigned long long watchdog_ns = 4000000000ull;
   std::vector<void*> owned;
 };
@@ -158,7 +163,6 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   p.st = e->d_st;
   p.attn_part = e->attn_part;
   p.attn_cnt = e->attn_cnt;
-  p.grid_bar = e->grid_bar;
   p.err = e->err_dev;
   p.n_code_groups = e->desc.n_code_groups;
   p.eos_id = e->desc.eos_id;
@@ -170,6 +174,8 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   p.pos_override = -1;
   p.watchdog_ns = e->watchdog_ns;
   p.debug = 0;
+  p.prof = e->prof;
+  p.prof_cta = e->prof_cta;
   if (const char* d = getenv("FQ3_DEBUG")) p.debug = atoi(d);
   p.n_iters = 1;
   p.stream0 = 0;
@@ -191,14 +197,54 @@ int launch(fq3_engine* e, LaunchParams& p, int xrows, int kmax, cudaStream_t s) 
   if (int r = check_device_fault(e)) return r;
   p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 128);
   p.xbuf_bytes = (int)round_up((size_t)xrows * kmax * 2, 128);
+  p.stage_bytes = kStageBytesDefault;
   const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - p.prog_bytes - p.xbuf_bytes;
-  p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
+  p.n_stages = (int)std::min<long>(e->max_stages, avail / p.stage_bytes);
   if (p.n_stages < 2) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
-  const size_t smem = kHeaderBytes + kScratchBytes + p.prog_bytes + p.xbuf_bytes + (size_t)p.n_stages * kStageBytes;
-  CK(cudaMemsetAsync(e->grid_bar, 0, sizeof(unsigned), s));
+  const size_t smem = kHeaderBytes + kScratchBytes + p.prog_bytes + p.xbuf_bytes + (size_t)p.n_stages * p.stage_bytes;
+  // LL epochs: phase i of iteration it carries epoch_base + it*n_phases + i + 1
+  const uint64_t span = (uint64_t)p.n_iters * (uint64_t)p.n_phases + 2;
+  if ((uint64_t)e->epoch + span >= 0xFFFFFF00ull) {
+    // wrap: drain, clear every LL buffer so stale epochs cannot alias, restart the counter
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < kNumBufs; ++i)
+      if (e->buf_bytes[i]) CK(cudaMemsetAsync(e->bufs[i], 0, e->buf_bytes[i], s));
+    e->epoch = 1;
+  }
+  p.epoch_base = e->epoch;
+  e->epoch += (uint32_t)span;
   void* args[] = {&p};
   CK(cudaLaunchCooperativeKernel((void*)fq3_stream_kernel, dim3(e->G), dim3(kThreads), args, smem, s));
   e->launches += 1;
+  return 0;
+}
+
+// ---- plain <-> LL conversions at the ABI boundary ----
+int pack_ll(fq3_engine* e, int buf, int row0, const void* src, int ld_src, int rows, int cols, cudaStream_t s) {
+  LLWord* dst = reinterpret_cast<LLWord*>(e->bufs[buf]) + (size_t)row0 * e->ld[buf];
+  const int n = rows * cols;
+  fq3_pack_ll_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, s>>>(dst, e->ld[buf], reinterpret_cast<const bf16*>(src),
+                                                                          ld_src, rows, cols);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+int unpack_f32(fq3_engine* e, void* dst, int ld_dst, int buf, int row0, int rows, int cols, cudaStream_t s) {
+  const LLWord* src = reinterpret_cast<const LLWord*>(e->bufs[buf]) + (size_t)row0 * e->ld[buf];
+  const int n = rows * cols;
+  fq3_unpack_ll_f32_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, s>>>(reinterpret_cast<float*>(dst), ld_dst, src,
+                                                                                e->ld[buf], rows, cols);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+int unpack_bf16(fq3_engine* e, void* dst, int ld_dst, int buf, int row0, int rows, int cols, cudaStream_t s) {
+  const LLWord* src = reinterpret_cast<const LLWord*>(e->bufs[buf]) + (size_t)row0 * e->ld[buf];
+  const int n = rows * cols;
+  fq3_unpack_ll_bf16_kernel<<<std::max(1, std::min(64, (n + 255) / 256)), 256, 0, s>>>(reinterpret_cast<bf16*>(dst), ld_dst, src,
+                                                                                 e->ld[buf], rows, cols);
+  e->launches += 1;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -221,7 +267,7 @@ int check_stack(const fq3_stack_desc& d, const char* name) {
   if (d.n_q_heads % d.n_kv_heads) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": nq % nkv != 0");
   if (d.vocab > kMaxVocab) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": vocab exceeds sampling scratch");
   const int kmax = std::max(std::max(d.hidden, d.inter), d.n_q_heads * d.head_dim);
-  if (kmax * 2 > kStageBytes) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": a weight row exceeds one ring stage");
+  if (kmax * 2 > kStageBytesDefault) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": a weight row exceeds one ring stage");
   return 0;
 }
 
@@ -251,6 +297,11 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   if (!coop) return fail(FQ3_E_UNSUPPORTED, "device lacks cooperative launch");
   e->G = sms;
   if (const char* g = getenv("FQ3_GRID")) e->G = std::max(1, std::min(sms, atoi(g)));
+  if (const char* ms = getenv("FQ3_STAGES")) e->max_stages = std::max(2, std::min((int)kMaxStages, atoi(ms)));
+  if (const char* pc = getenv("FQ3_PROF")) {
+    e->prof_cta = atoi(pc);
+    if (dalloc(e, &e->prof, 1024 * 8)) return -FQ3_E_CUDA;
+  }
   if (const char* w = getenv("FQ3_WATCHDOG_MS")) e->watchdog_ns = (unsigned long long)atoll(w) * 1000000ull;
   e->smem_max = (size_t)smem_optin;
   CK(cudaFuncSetAttribute(fq3_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
@@ -286,29 +337,35 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
     r.rope_sin = reinterpret_cast<const bf16*>(arena + sh.d.rope_sin_off);
   }
   // --- activation buffers ---
-  auto mk = [&](int id, int width, size_t elt) -> int {
+  auto mk = [&](int id, int width, size_t elt, int rows) -> int {
     void* q = nullptr;
-    if (dalloc(e, reinterpret_cast<uint8_t**>(&q), (size_t)R * width * elt)) return -1;
+    if (dalloc(e, reinterpret_cast<uint8_t**>(&q), (size_t)rows * width * elt)) return -1;
     e->bufs[id] = q;
     e->ld[id] = width;
+    e->buf_bytes[id] = (size_t)rows * width * elt;
     return 0;
   };
   const int Ht = e->tk.d.hidden, Hp = e->pr.d.hidden;
-  if (mk(BUF_TX, Ht, 2) || mk(BUF_TQKV, e->tk.qkvdim(), 2) || mk(BUF_TATT, e->tk.qdim(), 2) ||
-      mk(BUF_TACT, e->tk.d.inter, 2) || mk(BUF_PX, Hp, 2) || mk(BUF_PQKV, e->pr.qkvdim(), 2) ||
-      mk(BUF_PATT, e->pr.qdim(), 2) || mk(BUF_PACT, e->pr.d.inter, 2) ||
-      mk(BUF_LOGITS, std::max(e->tk.d.vocab, e->pr.d.vocab), 4) || mk(BUF_HID, Ht, 2))
+  const size_t LL = sizeof(LLWord);
+  if (mk(BUF_TX, Ht, LL, R) || mk(BUF_TQKV, e->tk.qkvdim(), LL, R) || mk(BUF_TATT, e->tk.qdim(), LL, R) ||
+      mk(BUF_TACT, e->tk.d.inter, LL, R) || mk(BUF_PX, Hp, LL, R) || mk(BUF_PQKV, e->pr.qkvdim(), LL, R) ||
+      mk(BUF_PATT, e->pr.qdim(), LL, R) || mk(BUF_PACT, e->pr.d.inter, LL, R) ||
+      mk(BUF_LOGITS, std::max(e->tk.d.vocab, e->pr.d.vocab), LL, R) || mk(BUF_HID, Ht, 2, R))
     return -FQ3_E_CUDA;
+  e->buf_bytes[BUF_HID] = 0;  // plain bf16, not an LL buffer
   if (desc->has_s2m) {
-    if (mk(BUF_PIN, Ht, 2)) return -FQ3_E_CUDA;
+    if (mk(BUF_PIN, Ht, LL, R)) return -FQ3_E_CUDA;
   } else {
     e->bufs[BUF_PIN] = e->bufs[BUF_PX];
     e->ld[BUF_PIN] = e->ld[BUF_PX];
   }
+  e->lin_words = 32768;
+  if (mk(BUF_LIN_IN, e->lin_words, LL, kMaxRows) || mk(BUF_LIN_OUT, e->lin_words, LL, kMaxRows) ||
+      mk(BUF_LIN_RES, e->lin_words, LL, kMaxRows))
+    return -FQ3_E_CUDA;
   const int nqmax = std::max(e->tk.d.n_q_heads, e->pr.d.n_q_heads);
   if (dalloc(e, &e->attn_part, (size_t)R * nqmax * kMaxSplits * kPartStride)) return -FQ3_E_CUDA;
   if (dalloc(e, &e->attn_cnt, (size_t)std::max(B, 1) * std::max(e->tk.d.n_kv_heads, e->pr.d.n_kv_heads))) return -FQ3_E_CUDA;
-  if (dalloc(e, &e->grid_bar, 4)) return -FQ3_E_CUDA;
   if (dalloc(e, &e->pred_logits_all, (size_t)e->ncb * e->pr.d.vocab)) return -FQ3_E_CUDA;
   if (dalloc(e, &e->seen_scratch, (size_t)kMaxVocab * 4)) return -FQ3_E_CUDA;
   CK(cudaHostAlloc(reinterpret_cast<void**>(&e->err_host), 64, cudaHostAllocMapped));
@@ -359,7 +416,7 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   if (upload(e, v, &e->d_prefill)) return fail(FQ3_E_CUDA, "program upload");
   if (dalloc(e, &e->d_linear, 1)) return -FQ3_E_CUDA;
   const size_t frames_need = kHeaderBytes + kScratchBytes + round_up((size_t)e->n_frames_ph * sizeof(Phase), 128) +
-                             2 * (size_t)kStageBytes;
+                             2 * (size_t)kStageBytesDefault;
   if (frames_need > e->smem_max) return fail(FQ3_E_UNSUPPORTED, "frame program does not fit in shared memory");
   CK(cudaDeviceSynchronize());
   *out = e;
@@ -446,20 +503,18 @@ int fq3_set_loop_state(fq3_engine* e, int idx, int token, const void* past_hidde
   e->launches += 1;
   CK(cudaGetLastError());
   bf16* hid = reinterpret_cast<bf16*>(e->bufs[BUF_HID]) + (size_t)idx * e->ld[BUF_HID];
-  bf16* pin = reinterpret_cast<bf16*>(e->bufs[BUF_PIN]);
-  const int ldp = e->ld[BUF_PIN];
   const bf16* emb = reinterpret_cast<const bf16*>(reinterpret_cast<const uint8_t*>(e->desc.arena) + e->desc.codec_embed_off) +
                     (size_t)token * Ht;
   CK(cudaMemcpyAsync(hid, past_hidden, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
-  CK(cudaMemcpyAsync(pin + (size_t)(2 * idx) * ldp, past_hidden, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
-  CK(cudaMemcpyAsync(pin + (size_t)(2 * idx + 1) * ldp, emb, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  if (int r = pack_ll(e, BUF_PIN, 2 * idx, past_hidden, Ht, 1, Ht, s)) return r;
+  if (int r = pack_ll(e, BUF_PIN, 2 * idx + 1, emb, Ht, 1, Ht, s)) return r;
   return 0;
 }
 
 static int prefill_rows(const fq3_engine* e) {
   // rows per pass are bounded by the activation staging buffer: keep >= 4 ring stages
   const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes -
-                     (long)round_up((size_t)e->n_prefill_ph * sizeof(Phase), 128) - 4L * kStageBytes;
+                     (long)round_up((size_t)e->n_prefill_ph * sizeof(Phase), 128) - 6L * kStageBytesDefault;
   long rows = avail / ((long)e->tk.kmax() * 2);
   const int gq = e->tk.d.n_q_heads / e->tk.d.n_kv_heads;
   rows = std::min<long>(rows, 16 / gq);
@@ -485,8 +540,7 @@ int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pa
   for (int c0 = 0; c0 < T; c0 += Mmax) {
     const int rows = std::min(Mmax, T - c0);
     const bool final = (c0 + rows == T);
-    CK(cudaMemcpyAsync(e->bufs[BUF_TX], reinterpret_cast<const bf16*>(embeds) + (size_t)c0 * Ht, (size_t)rows * Ht * 2,
-                       cudaMemcpyDeviceToDevice, s));
+    if (int r = pack_ll(e, BUF_TX, 0, reinterpret_cast<const bf16*>(embeds) + (size_t)c0 * Ht, Ht, rows, Ht, s)) return r;
     LaunchParams p{};
     fill_common(e, p);
     p.prog = e->d_prefill;
@@ -502,7 +556,7 @@ int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pa
   e->launches += 1;
   CK(cudaGetLastError());
   if (out_logits)
-    CK(cudaMemcpyAsync(out_logits, e->bufs[BUF_LOGITS], (size_t)e->tk.d.vocab * 4, cudaMemcpyDeviceToDevice, s));
+    if (int r = unpack_f32(e, out_logits, e->tk.d.vocab, BUF_LOGITS, 0, 1, e->tk.d.vocab, s)) return r;
   return 0;
 }
 
@@ -512,7 +566,7 @@ int fq3_talker_step(fq3_engine* e, int idx, const void* embeds, int position, vo
   if (position < 0 || position >= e->tk.d.max_pos) return fail(FQ3_E_TOO_LONG, "position outside the static KV cache");
   cudaStream_t s = (cudaStream_t)stream;
   const int Ht = e->tk.d.hidden;
-  CK(cudaMemcpyAsync(e->bufs[BUF_TX], embeds, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  if (int r = pack_ll(e, BUF_TX, 0, embeds, Ht, 1, Ht, s)) return r;
   LaunchParams p{};
   fill_common(e, p);
   p.prog = e->d_talker;
@@ -524,7 +578,7 @@ int fq3_talker_step(fq3_engine* e, int idx, const void* embeds, int position, vo
   if (int r = launch(e, p, 1, e->tk.kmax(), s)) return r;
   if (out_hidden) CK(cudaMemcpyAsync(out_hidden, e->bufs[BUF_HID], (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
   if (out_logits)
-    CK(cudaMemcpyAsync(out_logits, e->bufs[BUF_LOGITS], (size_t)e->tk.d.vocab * 4, cudaMemcpyDeviceToDevice, s));
+    if (int r = unpack_f32(e, out_logits, e->tk.d.vocab, BUF_LOGITS, 0, 1, e->tk.d.vocab, s)) return r;
   return 0;
 }
 
@@ -534,7 +588,7 @@ int fq3_predictor_run(fq3_engine* e, int idx, const void* pred_input, const fq3_
   if (!pred_input || !sub || !out_codes_i64) return fail(FQ3_E_INVALID, "bad predictor arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const int Ht = e->tk.d.hidden;
-  CK(cudaMemcpyAsync(e->bufs[BUF_PIN], pred_input, (size_t)2 * Ht * 2, cudaMemcpyDeviceToDevice, s));
+  if (int r = pack_ll(e, BUF_PIN, 0, pred_input, Ht, 2, Ht, s)) return r;
   LaunchParams p{};
   fill_common(e, p);
   p.prog = e->d_pred;
@@ -630,6 +684,15 @@ int fq3_read_codes(fq3_engine* e, int idx, int first, int n, int32_t* codes_out,
   return 0;
 }
 
+/* debug: copy the per-phase clock marks of the profiled CTA (FQ3_PROF=<cta>) */
+int fq3_debug_read_prof(fq3_engine* e, long long* out, int n_words) {
+  if (!e || !e->prof) return fail(FQ3_E_INVALID, "profiling not enabled (FQ3_PROF)");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, e->prof, sizeof(long long) * std::min(n_words, 1024 * 8), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(e->prof, 0, sizeof(long long) * 1024 * 8));
+  return 0;
+}
+
 void* fq3_codes_device_ptr(fq3_engine* e, int idx) {
   if (!e || idx < 0 || idx >= e->desc.max_streams) return nullptr;
   return e->h_st[idx].codes;
@@ -639,7 +702,7 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
                float eps, const void* bias, const void* residual, void* stream) {
   if (!e || !W || !x || !y) return fail(FQ3_E_INVALID, "null argument");
   if (M < 1 || M > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "M must be in [1, 8]");
-  if (K % 8 || K * 2 > kStageBytes || N < 1) return fail(FQ3_E_UNSUPPORTED, "K must be a multiple of 8 and fit one stage");
+  if (K % 8 || K * 2 > kStageBytesDefault || N < 1 || K > e->lin_words || N > e->lin_words) return fail(FQ3_E_UNSUPPORTED, "K must be a multiple of 8 and fit one stage");
   if ((flags & 8) && (N % 2)) return fail(FQ3_E_INVALID, "SwiGLU needs an even N");
   cudaStream_t s = (cudaStream_t)stream;
   Phase ph{};
@@ -655,11 +718,16 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
   p.n_phases = 1;
   p.mode = MODE_LINEAR;
   p.n_rows = M;
-  p.bufs[BUF_LIN_IN] = const_cast<void*>(x); p.ld[BUF_LIN_IN] = K;
-  p.bufs[BUF_LIN_OUT] = y; p.ld[BUF_LIN_OUT] = (flags & 8) ? N / 2 : N;
-  p.bufs[BUF_LIN_RES] = const_cast<void*>(residual); p.ld[BUF_LIN_RES] = (flags & 8) ? N / 2 : N;
+  const int No = (flags & 8) ? N / 2 : N;
+  if (int r = pack_ll(e, BUF_LIN_IN, 0, x, K, M, K, s)) return r;
+  if (flags & 4) {
+    if (!residual) return fail(FQ3_E_INVALID, "residual flag without a residual pointer");
+    if (int r = pack_ll(e, BUF_LIN_RES, 0, residual, No, M, No, s)) return r;
+  }
   p.lin_W = W; p.lin_gamma = gamma; p.lin_bias = bias; p.lin_eps = eps;
-  return launch(e, p, M, K, s);
+  if (int r = launch(e, p, M, K, s)) return r;
+  if (flags & 16) return unpack_f32(e, y, No, BUF_LIN_OUT, 0, M, No, s);
+  return unpack_bf16(e, y, No, BUF_LIN_OUT, 0, M, No, s);
 }
 
 }  // extern "C"

@@ -16,21 +16,27 @@ namespace fq3 {
 typedef __nv_bfloat16 bf16;
 
 // ---- geometry ---------------------------------------------------------------------------------
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumerThreads = kConsumerWarps * 32;  // 256
+constexpr int kConsumerWarps = 15;  // 15 consumers + 1 producer = 512 threads -> 128 registers per thread
+constexpr int kConsumerThreads = kConsumerWarps * 32;  // 480
 constexpr int kThreads = kConsumerThreads + 32;        // + one producer warp
-constexpr int kStageBytes = 16 * 1024;                 // one ring stage (weight tile)
+constexpr int kStageBytesDefault = 16 * 1024;  // one ring stage (weight tile)
 constexpr int kMaxStages = 12;
 constexpr int kRowsPerTileMax = 128;
-constexpr int kScratchBytes = 16 * 1024;  // GEMV partials / attention scratch / sampling scratch
+constexpr int kScratchBytes = 44 * 1024;  // attention scratch (q rows + 16x4 warp partials) / sampling scratch
 constexpr int kHeadDim = 128;             // talker and predictor heads (asserted on the host)
 constexpr int kMaxRows = 8;               // activation rows (tokens) per launch, GEMV register tile
 constexpr int kMaxSplits = 32;            // split-KV partitions per (sequence, kv head)
 constexpr int kPartStride = 132;          // floats per attention partial: m, l, pad, pad, o[128]
 constexpr int kNumBufs = 16;
-constexpr int kMaxVocab = 3328;              // sampling scratch holds V fp32 logits in 13 KB
+constexpr int kMaxVocab = 5120;              // sampling scratch holds V fp32 logits in 20 KB
 constexpr int kCtlOffset = 192;            // smem: full[12] | empty[12] | ctl[16] | scratch ...
 constexpr int kHeaderBytes = 256;
+
+// ---- LL (low-latency) activation words ---------------------------------------------------------
+// Every activation that crosses CTAs is an 8-byte word {fp32 value (bf16-rounded), epoch}.  A single
+// 8-byte store is atomic, so a reader that sees the expected epoch also sees the value: consumers poll
+// the data itself and no grid-wide barrier, fence or atomic sits between two phases.
+typedef uint2 LLWord;
 
 // ---- phase descriptors ------------------------------------------------------------------------
 enum PhaseType : uint8_t { PH_END = 0, PH_GEMV = 1, PH_ATTN = 2, PH_SAMPLE = 3 };
@@ -70,7 +76,7 @@ static_assert(sizeof(Phase) == 32, "Phase must stay 32 bytes");
 
 enum BufId : uint8_t {
   BUF_TX = 0, BUF_TQKV, BUF_TATT, BUF_TACT, BUF_PX, BUF_PQKV, BUF_PATT, BUF_PACT, BUF_PIN,
-  BUF_LOGITS, BUF_HID, BUF_LIN_IN, BUF_LIN_OUT, BUF_LIN_RES, BUF_PLOG_ALL, BUF_COUNT
+  BUF_LOGITS, BUF_HID, BUF_LIN_IN, BUF_LIN_OUT, BUF_LIN_RES, BUF_COUNT
 };
 
 // ---- run-time structures ----------------------------------------------------------------------
@@ -101,6 +107,7 @@ struct StreamState {  // one per stream, device memory
   int* codes;             // [max_frames, 16]
   uint8_t* seen;          // [V_t] first-codebook history bitmap (repetition penalty)
   int cur_codes[32];
+  LLWord ctl[4];          // per-frame control record published by the talker sampler: done, position, gen_step, n_frames
 };
 
 struct Policy {
@@ -134,7 +141,6 @@ struct LaunchParams {
   SubPolicy sub;
   float* attn_part;
   unsigned* attn_cnt;
-  unsigned* grid_bar;
   int* err;  // mapped host memory: [0]=code [1]=cta [2]=phase [3]=detail
   // model constants used by the sampling phases
   int n_code_groups, eos_id, has_s2m, max_frames;
@@ -147,11 +153,14 @@ struct LaunchParams {
   const void* lin_bias;
   float lin_eps;
   // smem carve-up
-  int n_stages, xbuf_bytes, prog_bytes;
+  int n_stages, xbuf_bytes, prog_bytes, stage_bytes;
+  unsigned epoch_base;  // LL epoch of the phase before this launch's first phase
   unsigned long long watchdog_ns;
-  int debug;  // timing ablations (FQ3_DEBUG): 1 no grid barrier, 2 no GEMV math, 4 no attention, 8 no activation load
+  long long* prof;  // optional per-phase clock64 marks [n_phases][8] of CTA prof_cta (FQ3_PROF)
+  int prof_cta;
+  int debug;  // timing ablations (FQ3_DEBUG): 1 no LL wait, 2 no GEMV math, 4 no attention, 8 no activation load
 };
 
-enum DevErr : int { DE_NONE = 0, DE_GRID_BAR = 1, DE_FULL_WAIT = 2, DE_EMPTY_WAIT = 3, DE_HANDSHAKE = 4, DE_BAD_PHASE = 5 };
+enum DevErr : int { DE_NONE = 0, DE_LL_WAIT = 1, DE_FULL_WAIT = 2, DE_EMPTY_WAIT = 3, DE_HANDSHAKE = 4, DE_BAD_PHASE = 5, DE_CTL_WAIT = 6 };
 
 }  // namespace fq3

@@ -1,7 +1,16 @@
-// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a).
+// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a), v2.
 //
 // Replaces the CUDA-graph replays of talker_graph.py:97-107,198-214 and predictor_graph.py:115-167 and
 // the eager per-frame glue of generate.py:149-199 (reference paths under /root/reference/faster_qwen3_tts).
+//
+// Structure of one CTA (one per SM, all co-resident):
+//   warp 16      producer: walks the phase program and streams this CTA's weight rows of every GEMV phase
+//                through a shared-memory ring with cp.async.bulk (TMA bulk copy).  Weight addresses never
+//                depend on activations or sampled ids, so it runs ahead of the consumers across phases.
+//   warps 0..15  consumers: per phase, poll-read the input activations (LL words), then each warp consumes
+//                the ring tiles independently (row -> warp round-robin, no CTA barrier per tile) and
+//                publishes its output elements as LL words.
+// There is no grid barrier: phases are chained by the data itself (value + epoch in one 8-byte word).
 #pragma once
 #include "fq3_common.cuh"
 
@@ -18,6 +27,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -33,7 +45,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
@@ -56,11 +67,6 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 
 __device__ __forceinline__ void cbar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -73,6 +79,20 @@ __device__ __forceinline__ int ld_volatile_shared_i32(const int* p) {
 }
 __device__ __forceinline__ void st_volatile_shared_i32(int* p, int v) {
   asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// LL words: relaxed gpu-scope 8-byte accesses served by L2 (the coherence point).
+__device__ __forceinline__ LLWord ll_ld(const LLWord* p) {
+  LLWord w;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p) : "memory");
+  return w;
+}
+// two adjacent words with one 16-byte request (each word is validated by its own epoch, so tearing is harmless)
+__device__ __forceinline__ void ll_ld2(const LLWord* p, LLWord& a, LLWord& b) {
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(b.x), "=r"(b.y) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ll_st(LLWord* p, float v, uint32_t ep) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(ep) : "memory");
 }
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -92,16 +112,16 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
-  acc = fmaf(bf_lo(w.x), bf_lo(x.x), acc);
-  acc = fmaf(bf_hi(w.x), bf_hi(x.x), acc);
-  acc = fmaf(bf_lo(w.y), bf_lo(x.y), acc);
-  acc = fmaf(bf_hi(w.y), bf_hi(x.y), acc);
-  acc = fmaf(bf_lo(w.z), bf_lo(x.z), acc);
-  acc = fmaf(bf_hi(w.z), bf_hi(x.z), acc);
-  acc = fmaf(bf_lo(w.w), bf_lo(x.w), acc);
-  acc = fmaf(bf_hi(w.w), bf_hi(x.w), acc);
-  return acc;
+// 8 bf16 products into two independent accumulators (halves the dependent FMA chain)
+__device__ __forceinline__ void dot8(const uint4& w, const uint4& x, float& a0, float& a1) {
+  a0 = fmaf(bf_lo(w.x), bf_lo(x.x), a0);
+  a1 = fmaf(bf_hi(w.x), bf_hi(x.x), a1);
+  a0 = fmaf(bf_lo(w.y), bf_lo(x.y), a0);
+  a1 = fmaf(bf_hi(w.y), bf_hi(x.y), a1);
+  a0 = fmaf(bf_lo(w.z), bf_lo(x.z), a0);
+  a1 = fmaf(bf_hi(w.z), bf_hi(x.z), a1);
+  a0 = fmaf(bf_lo(w.w), bf_lo(x.w), a0);
+  a1 = fmaf(bf_hi(w.w), bf_hi(x.w), a1);
 }
 
 // =================================================================================================
@@ -110,7 +130,7 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc)
 struct Smem {
   uint64_t* full;    // [kMaxStages]
   uint64_t* empty;   // [kMaxStages]
-  int* ctl;          // [0] producer go flag, [1..] broadcast scratch
+  int* ctl;          // [0] producer go flag, [4..] broadcast scratch
   unsigned char* scratch;
   Phase* prog;
   unsigned char* xbuf;
@@ -157,44 +177,62 @@ struct Spin {
   }
 };
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const LaunchParams& p, int code, int phase) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, const LaunchParams& p, int code, int phase) {
   Spin s;
   while (!mbar_try_wait(bar, parity)) s.tick(p, code, phase, (int)parity);
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const LaunchParams& p, int code, int phase) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, p, code, phase);
+}
 
-// Grid-wide barrier among the consumer threads of all CTAs (monotonic counter, reset by the host).
-__device__ __forceinline__ void grid_sync(const LaunchParams& p, unsigned& epoch, int phase) {
-  cbar_sync();
-  ++epoch;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(p.grid_bar, 1u);
-    const unsigned target = epoch * gridDim.x;
-    Spin s;
-    while (ld_acquire_u32(p.grid_bar) < target) s.tick(p, DE_GRID_BAR, phase, (int)epoch);
-    __threadfence();
-  }
-  cbar_sync();
+// Slow path of an LL read: poll until the word carries `ep`.
+__device__ __noinline__ LLWord ll_spin(const LLWord* ptr, uint32_t ep, const LaunchParams& p, int phase) {
+  Spin s;
+  LLWord w;
+  unsigned ns = 64;
+  do {
+    // back off: thousands of threads polling L2 at full rate starve the weight stream of L2 request slots
+    __nanosleep(ns);
+    if (ns < 256) ns += 64;
+    s.tick(p, DE_LL_WAIT, phase, (int)ep);
+    w = ll_ld(ptr);
+  } while (w.y != ep);
+  return w;
+}
+// Validate a word that was loaded earlier (loads are issued in batches so their L2 round trips overlap);
+// ep == 0 accepts whatever is there — inputs written before the launch.
+__device__ __forceinline__ float ll_check(LLWord w, const LLWord* ptr, uint32_t ep, const LaunchParams& p, int phase) {
+  if (ep != 0 && w.y != ep && !(p.debug & 1)) w = ll_spin(ptr, ep, p, phase);
+  return __uint_as_float(w.x);
+}
+__device__ __forceinline__ float ll_wait(const LLWord* ptr, uint32_t ep, const LaunchParams& p, int phase) {
+  return ll_check(ll_ld(ptr), ptr, ep, p, phase);
+}
+
+__device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int slot) {
+  if (p.prof && threadIdx.x == 0 && (int)blockIdx.x == p.prof_cta && pidx >= 0) p.prof[(size_t)pidx * 8 + slot] = clock64();
 }
 
 // =================================================================================================
 // GEMV phase
 // =================================================================================================
 struct GemvPlan {
-  int r0, r1, rt, ntiles;
+  int r0, r1, rt, ntiles, rpu;
 };
-__device__ __forceinline__ GemvPlan gemv_plan(const Phase& ph, int cta, int G) {
+__device__ __forceinline__ GemvPlan gemv_plan(const Phase& ph, const LaunchParams& p, int cta, int G) {
   GemvPlan g;
-  const int unit = (ph.flags & F_SWIGLU) ? 2 : 1;
+  g.rpu = (ph.flags & F_SWIGLU) ? 2 : 1;
   const int N = (int)ph.N, K = (int)ph.K;
-  const int nunits = N / unit;
-  const int upc = (nunits + G - 1) / G;
-  g.r0 = min(N, cta * upc * unit);
-  g.r1 = min(N, g.r0 + upc * unit);
-  int rt = min(kRowsPerTileMax, kStageBytes / (K * 2));
-  rt -= rt % unit;
-  g.rt = max(rt, unit);
+  const int nunits = N / g.rpu;
+  const int base = nunits / G, rem = nunits - base * G;  // balanced: the first `rem` CTAs take one more unit
+  const int u0 = cta * base + min(cta, rem);
+  const int u1 = u0 + base + (cta < rem ? 1 : 0);
+  g.r0 = u0 * g.rpu;
+  g.r1 = u1 * g.rpu;
+  int rt = min(kRowsPerTileMax, p.stage_bytes / (K * 2));
+  rt -= rt % g.rpu;
+  g.rt = max(rt, g.rpu);
   g.ntiles = (g.r1 - g.r0 + g.rt - 1) / g.rt;
   return g;
 }
@@ -205,178 +243,229 @@ __device__ __forceinline__ int phase_rows(const Phase& ph, const LaunchParams& p
 
 // Load the activation rows of a GEMV phase into shared memory (bf16), optionally RMS-normalised.
 // HF rounding points (Qwen3RMSNorm): fp32 mean-square, x*rsqrt -> bf16, * weight -> bf16.
-__device__ void load_x(const Phase& ph, const LaunchParams& p, const Smem& sm, int M, int row_off) {
+// All 512 consumer threads take part: one LL round trip, gamma fetched alongside.
+__device__ __noinline__ void load_x(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, int M, int row_off, uint32_t ep_in,
+                       int pidx) {
+  const Smem sm = carve_smem(smem_base, p);
   const int K = (int)ph.K;
-  const int cpr = K >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bf16* in = reinterpret_cast<const bf16*>(p.bufs[ph.in_buf]);
+  const LLWord* in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]);
   const int ld = p.ld[ph.in_buf];
-  uint4* xs = reinterpret_cast<uint4*>(sm.xbuf);
+  bf16* xs = reinterpret_cast<bf16*>(sm.xbuf);
   const bool norm = (ph.flags & F_PRENORM) != 0;
-  const bf16* gamma = nullptr;
-  float eps = 0.f;
-  if (norm) {
-    gamma = (ph.flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_gamma)
-                                  : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
-    eps = (ph.flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
+  float* red = reinterpret_cast<float*>(sm.scratch);  // [kMaxRows][kConsumerWarps]
+  constexpr int kPairs = 7;  // K <= 6720: each thread owns the element pairs 2*(tid + i*480), +1 of every row
+  if (!norm) {
+    for (int m = 0; m < M; ++m) {
+      const LLWord* src = in + (size_t)(m + row_off) * ld;
+      LLWord w[kPairs][2];
+#pragma unroll
+      for (int i = 0; i < kPairs; ++i) {
+        const int k = 2 * (threadIdx.x + i * kConsumerThreads);
+        if (k < K) ll_ld2(src + k, w[i][0], w[i][1]);
+      }
+#pragma unroll
+      for (int i = 0; i < kPairs; ++i) {
+        const int k = 2 * (threadIdx.x + i * kConsumerThreads);
+        if (k < K) {
+          const float v0 = ll_check(w[i][0], src + k, ep_in, p, pidx), v1 = ll_check(w[i][1], src + k + 1, ep_in, p, pidx);
+          *reinterpret_cast<uint32_t*>(xs + (size_t)m * K + k) = pack_bf16x2(v0, v1);
+        }
+      }
+    }
+    cbar_sync();
+    return;
   }
-  for (int m = warp; m < M; m += kConsumerWarps) {
-    const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)(m + row_off) * ld);
-    uint4* dst = xs + (size_t)m * cpr;
+  const bf16* gamma = (ph.flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_gamma)
+                                            : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
+  const float eps = (ph.flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
+  for (int m = 0; m < M; ++m) {
+    const LLWord* src = in + (size_t)(m + row_off) * ld;
+    float v[kPairs][2];
+    uint32_t g[kPairs];
+    LLWord w[kPairs][2];
     float ss = 0.f;
-    for (int c = lane; c < cpr; c += 32) {
-      uint4 v = __ldcg(src + c);
-      dst[c] = v;
-      if (norm) {
-        float a;
-        a = bf_lo(v.x); ss = fmaf(a, a, ss); a = bf_hi(v.x); ss = fmaf(a, a, ss);
-        a = bf_lo(v.y); ss = fmaf(a, a, ss); a = bf_hi(v.y); ss = fmaf(a, a, ss);
-        a = bf_lo(v.z); ss = fmaf(a, a, ss); a = bf_hi(v.z); ss = fmaf(a, a, ss);
-        a = bf_lo(v.w); ss = fmaf(a, a, ss); a = bf_hi(v.w); ss = fmaf(a, a, ss);
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      const int k = 2 * (threadIdx.x + i * kConsumerThreads);
+      if (k < K) {
+        ll_ld2(src + k, w[i][0], w[i][1]);
+        g[i] = __ldg(reinterpret_cast<const uint32_t*>(gamma + k));
       }
     }
-    if (norm) {
-      ss = warp_sum(ss);
-      const float rs = rsqrtf(ss / (float)K + eps);
-      __syncwarp();
-      const uint4* g4 = reinterpret_cast<const uint4*>(gamma);
-      for (int c = lane; c < cpr; c += 32) {
-        uint4 v = dst[c];
-        uint4 g = __ldg(g4 + c);
-        uint4 o;
-        o.x = pack_bf16x2(bf16r(bf_lo(v.x) * rs) * bf_lo(g.x), bf16r(bf_hi(v.x) * rs) * bf_hi(g.x));
-        o.y = pack_bf16x2(bf16r(bf_lo(v.y) * rs) * bf_lo(g.y), bf16r(bf_hi(v.y) * rs) * bf_hi(g.y));
-        o.z = pack_bf16x2(bf16r(bf_lo(v.z) * rs) * bf_lo(g.z), bf16r(bf_hi(v.z) * rs) * bf_hi(g.z));
-        o.w = pack_bf16x2(bf16r(bf_lo(v.w) * rs) * bf_lo(g.w), bf16r(bf_hi(v.w) * rs) * bf_hi(g.w));
-        dst[c] = o;
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      const int k = 2 * (threadIdx.x + i * kConsumerThreads);
+      if (k < K) {
+        v[i][0] = ll_check(w[i][0], src + k, ep_in, p, pidx);
+        v[i][1] = ll_check(w[i][1], src + k + 1, ep_in, p, pidx);
+        ss = fmaf(v[i][0], v[i][0], ss);
+        ss = fmaf(v[i][1], v[i][1], ss);
       }
-      if ((ph.flags & F_WRITE_NORMED) && blockIdx.x == 0) {
-        __syncwarp();
-        uint4* hid = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID]);
-        for (int c = lane; c < cpr; c += 32) hid[c] = dst[c];
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[m * kConsumerWarps + warp] = ss;
+    cbar_sync();
+    float tot = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < kConsumerWarps; ++wi) tot += red[m * kConsumerWarps + wi];
+    const float rs = rsqrtf(tot / (float)K + eps);
+    const bool wr = (ph.flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      const int k = 2 * (threadIdx.x + i * kConsumerThreads);
+      if (k < K) {
+        const float y0 = bf16r(bf16r(v[i][0] * rs) * bf_lo(g[i])), y1 = bf16r(bf16r(v[i][1] * rs) * bf_hi(g[i]));
+        const uint32_t pk = pack_bf16x2(y0, y1);
+        *reinterpret_cast<uint32_t*>(xs + (size_t)m * K + k) = pk;
+        if (wr) *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID] + k) = pk;
       }
     }
   }
-}
-
-template <int MT>
-__device__ __forceinline__ void gemv_tile_compute(const uint4* __restrict__ tile, const uint4* __restrict__ xs, int rt,
-                                                  int cpr, int wpr, float* __restrict__ part) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seg = (cpr + wpr - 1) / wpr;
-  const int nunits = rt * wpr;
-  for (int u = warp; u < nunits; u += kConsumerWarps) {
-    const int row = u / wpr, s = u - row * wpr;
-    const int c0 = s * seg, c1 = min(cpr, c0 + seg);
-    float acc[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) acc[m] = 0.f;
-    const uint4* wrow = tile + (size_t)row * cpr;
-#pragma unroll 4
-    for (int c = c0 + lane; c < c1; c += 32) {
-      const uint4 w = wrow[c];
-#pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        const uint4 x = xs[m * cpr + c];
-        acc[m] = dot8(w, x, acc[m]);
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      const float v = warp_sum(acc[m]);
-      if (lane == m) part[u * MT + m] = v;
-    }
-  }
+  cbar_sync();
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
-// Finalise one tile: sum k-segment partials, apply the epilogue with PyTorch's bf16 rounding points.
-__device__ void gemv_tile_epilogue(const Phase& ph, const LaunchParams& p, const float* part, int row_base, int rt,
-                                   int wpr, int M) {
-  const bool swi = (ph.flags & F_SWIGLU) != 0;
-  const int nout = swi ? rt / 2 : rt;
-  const bf16* bias = nullptr;
-  if (ph.flags & F_BIAS)
-    bias = (ph.flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias)
-                                 : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-  const int ldo = p.ld[ph.out_buf];
-  for (int o = threadIdx.x; o < nout * M; o += kConsumerThreads) {
-    const int j = o / M, m = o - j * M;
-    float y;
-    int ocol;
-    if (swi) {
-      float g = 0.f, u = 0.f;
-      for (int s = 0; s < wpr; ++s) {
-        g += part[((2 * j) * wpr + s) * M + m];
-        u += part[((2 * j + 1) * wpr + s) * M + m];
-      }
-      g = bf16r(g);
-      u = bf16r(u);
-      y = bf16r(bf16r(silu_f(g)) * u);
-      ocol = (row_base >> 1) + j;
+// One warp computes one unit (1 row, or a gate/up pair) of one tile for MT activation rows and publishes it.
+template <int MT, int RPU>
+__device__ __noinline__ void gemv_unit(const Phase& ph, const LaunchParams& p, const uint4* __restrict__ wrow,
+                                          const uint4* __restrict__ xs, int cpr, int out_col, int M, uint32_t ep) {
+  const int lane = threadIdx.x & 31;
+  // residual value: issue the L2 read now, consume it in the epilogue (hides the round trip behind the dot product)
+  LLWord resw = make_uint2(0u, 0u);
+  if ((ph.flags & F_RESID) && lane < M)
+    resw = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)lane * p.ld[ph.res_buf] + out_col);
+  float a0[RPU][MT], a1[RPU][MT];
+#pragma unroll
+  for (int r = 0; r < RPU; ++r)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) a0[r][m] = a1[r][m] = 0.f;
+#pragma unroll 2
+  for (int c = lane; c < cpr; c += 32) {
+    uint4 w[RPU];
+#pragma unroll
+    for (int r = 0; r < RPU; ++r) w[r] = wrow[(size_t)r * cpr + c];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const uint4 x = xs[(size_t)m * cpr + c];
+#pragma unroll
+      for (int r = 0; r < RPU; ++r) dot8(w[r], x, a0[r][m], a1[r][m]);
+    }
+  }
+  float y[RPU];
+#pragma unroll
+  for (int r = 0; r < RPU; ++r) y[r] = 0.f;
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int r = 0; r < RPU; ++r) {
+      const float v = warp_sum(a0[r][m] + a1[r][m]);
+      if (lane == m) y[r] = v;
+    }
+  }
+  if (lane < M) {
+    // epilogue with PyTorch's bf16 rounding points; lane m owns activation row m
+    const int m = lane;
+    float out;
+    if (RPU == 2) {
+      const float g = bf16r(y[0]), u = bf16r(y[1]);
+      out = bf16r(bf16r(silu_f(g)) * u);
     } else {
-      y = 0.f;
-      for (int s = 0; s < wpr; ++s) y += part[(j * wpr + s) * M + m];
-      ocol = row_base + j;
-      if (bias) y += __bfloat162float(bias[ocol]);
-      y = bf16r(y);
+      out = y[0];
+      if (ph.flags & F_BIAS) {
+        const bf16* bias = (ph.flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias)
+                                                 : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+        out += __bfloat162float(bias[out_col]);
+      }
+      out = bf16r(out);
     }
-    if (ph.flags & F_RESID) {
-      const bf16* res = reinterpret_cast<const bf16*>(p.bufs[ph.res_buf]);
-      y = bf16r(__bfloat162float(res[(size_t)m * p.ld[ph.res_buf] + ocol]) + y);
-    }
-    if (ph.flags & F_OUT_F32)
-      reinterpret_cast<float*>(p.bufs[ph.out_buf])[(size_t)m * ldo + ocol] = y;
-    else
-      reinterpret_cast<bf16*>(p.bufs[ph.out_buf])[(size_t)m * ldo + ocol] = __float2bfloat16_rn(y);
+    if (ph.flags & F_RESID) out = bf16r(__uint_as_float(resw.x) + out);
+    ll_st(reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]) + (size_t)m * p.ld[ph.out_buf] + out_col, out, ep);
   }
 }
 
-__device__ void gemv_phase_consume(const Phase& ph, const LaunchParams& p, const Smem& sm, unsigned& tile_it, int pidx) {
+__device__ void gemv_phase_consume(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, unsigned& tile_it, int pidx,
+                                   uint32_t ep) {
+  const Smem sm = carve_smem(smem_base, p);
   const int G = gridDim.x, cta = blockIdx.x;
-  const GemvPlan g = gemv_plan(ph, cta, G);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const GemvPlan g = gemv_plan(ph, p, cta, G);
   int M = phase_rows(ph, p), row_off = 0;
   if (ph.flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
-  if (!(p.debug & 8)) load_x(ph, p, sm, M, row_off);
-  cbar_sync();
+  const uint32_t ep_in = (pidx == 0 && ep == p.epoch_base + 1) ? 0u : ep - 1;
+  prof_mark(p, pidx, 0);
+  if (!(p.debug & 8)) load_x(ph, p, smem_base, M, row_off, ep_in, pidx);
+  prof_mark(p, pidx, 1);
   const int cpr = (int)ph.K >> 3;
   const uint4* xs = reinterpret_cast<const uint4*>(sm.xbuf);
-  float* partbuf = reinterpret_cast<float*>(sm.scratch);  // 2 x 1024 floats (rt*wpr*M <= 1024)
-  for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
-    const int stage = tile_it % p.n_stages;
-    const uint32_t parity = (tile_it / p.n_stages) & 1u;
-    const int row_base = g.r0 + t * g.rt;
-    const int rt = min(g.rt, g.r1 - row_base);
-    int wpr = 1;
-    while (rt * wpr < kConsumerWarps) wpr <<= 1;
-    float* part = partbuf + (tile_it & 1u) * 1024;
-    mbar_wait(&sm.full[stage], parity, p, DE_FULL_WAIT, pidx);
-    const uint4* tile = reinterpret_cast<const uint4*>(sm.ring + (size_t)stage * kStageBytes);
-    if (!(p.debug & 2)) switch (M) {
-      case 1: gemv_tile_compute<1>(tile, xs, rt, cpr, wpr, part); break;
-      case 2: gemv_tile_compute<2>(tile, xs, rt, cpr, wpr, part); break;
-      case 3: gemv_tile_compute<3>(tile, xs, rt, cpr, wpr, part); break;
-      case 4: gemv_tile_compute<4>(tile, xs, rt, cpr, wpr, part); break;
-      case 5: gemv_tile_compute<5>(tile, xs, rt, cpr, wpr, part); break;
-      case 6: gemv_tile_compute<6>(tile, xs, rt, cpr, wpr, part); break;
-      case 7: gemv_tile_compute<7>(tile, xs, rt, cpr, wpr, part); break;
-      default: gemv_tile_compute<8>(tile, xs, rt, cpr, wpr, part); break;
+  const int upt = g.rt / g.rpu;  // units per tile
+  const int nunits = (g.r1 - g.r0) / g.rpu;
+  // unit u of the CTA's slice belongs to warp (u % 15).  A warp only touches the tiles that hold its units; the
+  // producer pre-arrives on the stage's empty barrier for the warps that have no unit in a tile.
+  // mbarrier parity only disambiguates adjacent phases, so no warp may run a full ring ahead of the data:
+  // tiles are consumed in rounds of n_stages with a consumer barrier between rounds (one round for the
+  // 0.6B shapes, up to three for 12 KB rows).
+  const int nrounds = (g.ntiles + p.n_stages - 1) / p.n_stages;
+  int u = warp;
+#pragma unroll 1
+  for (int round = 0; round < nrounds; ++round) {
+    if (round > 0) cbar_sync();
+    const int t_end = min(g.ntiles, (round + 1) * p.n_stages);
+    int t_prev = -1;
+    int stage = 0;
+#pragma unroll 1
+    for (; u < nunits && u / upt < t_end; u += kConsumerWarps) {
+      const int t = u / upt;
+      const unsigned it = tile_it + (unsigned)t;
+      if (t != t_prev) {
+        if (t_prev >= 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        }
+        stage = it % p.n_stages;
+        if (lane == 0) mbar_wait(&sm.full[stage], (it / p.n_stages) & 1u, p, DE_FULL_WAIT, pidx);
+        __syncwarp();
+        t_prev = t;
+      }
+      if (!(p.debug & 2)) {
+        const int j = u - t * upt;
+        const uint4* wrow = reinterpret_cast<const uint4*>(sm.ring + (size_t)stage * p.stage_bytes) + (size_t)j * g.rpu * cpr;
+        const int oc = g.r0 / g.rpu + u;
+        if (g.rpu == 2) {
+          if (M == 1) gemv_unit<1, 2>(ph, p, wrow, xs, cpr, oc, M, ep);
+          else if (M == 2) gemv_unit<2, 2>(ph, p, wrow, xs, cpr, oc, M, ep);
+          else if (M <= 4) gemv_unit<4, 2>(ph, p, wrow, xs, cpr, oc, M, ep);
+          else gemv_unit<8, 2>(ph, p, wrow, xs, cpr, oc, M, ep);
+        } else {
+          if (M == 1) gemv_unit<1, 1>(ph, p, wrow, xs, cpr, oc, M, ep);
+          else if (M == 2) gemv_unit<2, 1>(ph, p, wrow, xs, cpr, oc, M, ep);
+          else if (M <= 4) gemv_unit<4, 1>(ph, p, wrow, xs, cpr, oc, M, ep);
+          else gemv_unit<8, 1>(ph, p, wrow, xs, cpr, oc, M, ep);
+        }
+      }
     }
-    cbar_sync();                                         // partials visible, weight tile fully read
-    if (threadIdx.x == 0) mbar_arrive(&sm.empty[stage]);  // hand the stage back to the producer
-    if (!(p.debug & 2)) gemv_tile_epilogue(ph, p, part, row_base, rt, wpr, M);
+    if (t_prev >= 0) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+    }
   }
+  tile_it += (unsigned)g.ntiles;
+  prof_mark(p, pidx, 2);
+  cbar_sync();  // xbuf is rewritten by the next phase
+  prof_mark(p, pidx, 3);
 }
 
 // Producer side of one GEMV phase: stream this CTA's rows through the ring.
-__device__ void gemv_phase_produce(const Phase& ph, const LaunchParams& p, const Smem& sm, unsigned& tile_it, int pidx,
+__device__ __noinline__ void gemv_phase_produce(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, unsigned& tile_it, int pidx,
                                    uint64_t pol_stream, uint64_t pol_keep) {
-  const GemvPlan g = gemv_plan(ph, blockIdx.x, gridDim.x);
+  const Smem sm = carve_smem(smem_base, p);
+  const GemvPlan g = gemv_plan(ph, p, blockIdx.x, gridDim.x);
   const unsigned char* W = (ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_W)
                                                  : p.arena + (size_t)ph.w_off * 16;
   const size_t row_bytes = (size_t)ph.K * 2;
   const uint64_t pol = (ph.flags & F_L2_KEEP) ? pol_keep : pol_stream;
+  if (p.prof && (int)blockIdx.x == p.prof_cta) p.prof[(size_t)pidx * 8 + 4] = clock64();
   for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
     const int stage = tile_it % p.n_stages;
     const uint32_t parity = ((tile_it / p.n_stages) & 1u) ^ 1u;
@@ -384,19 +473,22 @@ __device__ void gemv_phase_produce(const Phase& ph, const LaunchParams& p, const
     const int rt = min(g.rt, g.r1 - row_base);
     const uint32_t bytes = (uint32_t)(rt * row_bytes);
     mbar_wait(&sm.empty[stage], parity, p, DE_EMPTY_WAIT, pidx);
+    if (t == g.ntiles - 1 && p.prof && (int)blockIdx.x == p.prof_cta) p.prof[(size_t)pidx * 8 + 5] = clock64();
     mbar_arrive_expect_tx(&sm.full[stage], bytes);
-    bulk_g2s(sm.ring + (size_t)stage * kStageBytes, W + (size_t)row_base * row_bytes, bytes, &sm.full[stage], pol);
+    bulk_g2s(sm.ring + (size_t)stage * p.stage_bytes, W + (size_t)row_base * row_bytes, bytes, &sm.full[stage], pol);
+    const int readers = min(rt / g.rpu, kConsumerWarps);  // units in this tile go to distinct warps (round-robin)
+    if (readers < kConsumerWarps) mbar_arrive_cnt(&sm.empty[stage], (uint32_t)(kConsumerWarps - readers));
   }
 }
 
 // =================================================================================================
-// Attention phase: q/k RMSNorm + RoPE + KV append + split-KV GQA decode attention + combine.
+// Attention phase: q/k RMSNorm + RoPE + KV append + GQA decode attention (+ split-KV combine).
 // =================================================================================================
 struct Group {
   int first_row, nrows, slot, pos0, n_pad, rope_delta;
 };
 __device__ __forceinline__ int num_groups(const LaunchParams& p) { return p.mode == MODE_PREFILL ? 1 : p.n_rows; }
-__device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& p, int g) {
+__device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& p, int g, const int* frame_pos) {
   Group r;
   if (p.mode == MODE_PREFILL) {
     r.first_row = 0; r.nrows = p.n_rows; r.slot = p.stream0; r.pos0 = p.pf_pos0; r.n_pad = p.pf_n_pad;
@@ -408,7 +500,7 @@ __device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& 
   r.slot = p.stream0 + g;
   if (ph.stack == ST_TALKER) {
     const StreamState* st = p.st + r.slot;
-    r.pos0 = (p.pos_override >= 0) ? p.pos_override : __ldcg(&st->position);
+    r.pos0 = (p.pos_override >= 0) ? p.pos_override : frame_pos[g];
     r.n_pad = __ldcg(&st->n_pad);
     r.rope_delta = __ldcg(&st->rope_delta);
   } else {
@@ -418,46 +510,60 @@ __device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& 
   }
   return r;
 }
+// one CTA handles up to 1024 positions of one (sequence, kv head); longer contexts are split
 __device__ __forceinline__ int num_splits(int L, int ngroups, int nkv, int G) {
   int cap = G / max(1, ngroups * nkv);
   cap = max(1, min(cap, kMaxSplits));
-  int want = (L + 63) / 64;
+  int want = (L + 1023) / 1024;
   return max(1, min(want, cap));
 }
 
 // RMSNorm over the 128-wide head + rotary embedding; lane owns elements [4*lane, 4*lane+4).
-__device__ __forceinline__ void head_norm_rope(float (&x)[4], const bf16* gamma, float eps, const bf16* cosr,
-                                               const bf16* sinr, int lane) {
+// gamma / cos / sin arrive as 4 packed bf16 (uint2) loaded before the activation wait.
+__device__ __forceinline__ void head_norm_rope(float (&x)[4], uint2 g2, float eps, uint2 c2, uint2 s2, int lane) {
   float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
   ss = warp_sum(ss);
   const float rs = rsqrtf(ss * (1.f / kHeadDim) + eps);
+  const float g[4] = {bf_lo(g2.x), bf_hi(g2.x), bf_lo(g2.y), bf_hi(g2.y)};
+  const float c[4] = {bf_lo(c2.x), bf_hi(c2.x), bf_lo(c2.y), bf_hi(c2.y)};
+  const float sn[4] = {bf_lo(s2.x), bf_hi(s2.x), bf_lo(s2.y), bf_hi(s2.y)};
   float y[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) y[i] = bf16r(bf16r(x[i] * rs) * __bfloat162float(gamma[lane * 4 + i]));
+  for (int i = 0; i < 4; ++i) y[i] = bf16r(bf16r(x[i] * rs) * g[i]);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float partner = __shfl_xor_sync(0xffffffffu, y[i], 16);
     const float rot = (lane < 16) ? -partner : partner;
-    const float c = __bfloat162float(cosr[lane * 4 + i]), s = __bfloat162float(sinr[lane * 4 + i]);
-    x[i] = bf16r(bf16r(y[i] * c) + bf16r(rot * s));
+    x[i] = bf16r(bf16r(y[i] * c[i]) + bf16r(rot * sn[i]));
   }
 }
+__device__ __forceinline__ uint2 ld_bf16x4(const bf16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 
-__device__ __forceinline__ void load4(const bf16* p, float (&x)[4]) {
-  const uint2 v = __ldcg(reinterpret_cast<const uint2*>(p));
-  x[0] = bf_lo(v.x); x[1] = bf_hi(v.x); x[2] = bf_lo(v.y); x[3] = bf_hi(v.y);
+__device__ __forceinline__ void ll_issue4(const LLWord* ptr, LLWord (&w)[4]) {
+  ll_ld2(ptr, w[0], w[1]);
+  ll_ld2(ptr + 2, w[2], w[3]);
+}
+__device__ __forceinline__ void ll_finish4(const LLWord (&w)[4], const LLWord* ptr, uint32_t ep, const LaunchParams& p, int pidx,
+                                           float (&x)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = ll_check(w[i], ptr + i, ep, p, pidx);
 }
 
-__device__ void attn_item(const Phase& ph, const LaunchParams& p, const Smem& sm, const Group& gr, int kvh, int sp,
-                          int nsplit) {
+constexpr int kAttnPairsMax = 4;  // (row, q-head) pairs sharing one K/V sweep
+
+// Scratch layout (floats): qs[16][128] | wp[16 warps][kAttnPairsMax][kPartStride]
+__device__ __noinline__ void attn_item(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, const Group& gr, int kvh, int sp,
+                          int nsplit, uint32_t ep, int pidx) {
+  const Smem sm = carve_smem(smem_base, p);
   const StackRt& S = p.stacks[ph.stack];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = S.nq / S.nkv;
   const int npairs = gr.nrows * gq;
-  const bf16* qkv = reinterpret_cast<const bf16*>(p.bufs[ph.stack == ST_TALKER ? BUF_TQKV : BUF_PQKV]);
-  const int ldq = p.ld[ph.stack == ST_TALKER ? BUF_TQKV : BUF_PQKV];
-  bf16* att = reinterpret_cast<bf16*>(p.bufs[ph.stack == ST_TALKER ? BUF_TATT : BUF_PATT]);
-  const int lda = p.ld[ph.stack == ST_TALKER ? BUF_TATT : BUF_PATT];
+  const int qb = ph.stack == ST_TALKER ? BUF_TQKV : BUF_PQKV, ab = ph.stack == ST_TALKER ? BUF_TATT : BUF_PATT;
+  const LLWord* qkv = reinterpret_cast<const LLWord*>(p.bufs[qb]);
+  const int ldq = p.ld[qb];
+  LLWord* att = reinterpret_cast<LLWord*>(p.bufs[ab]);
+  const int lda = p.ld[ab];
   const bf16* qn = reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
   const bf16* kn = reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
   const size_t head_base = (((size_t)ph.layer * S.n_slots + gr.slot) * S.nkv + kvh) * (size_t)S.max_pos * kHeadDim;
@@ -468,125 +574,176 @@ __device__ void attn_item(const Phase& ph, const LaunchParams& p, const Smem& sm
   const int per = (L + nsplit - 1) / nsplit;
   const int a = gr.n_pad + sp * per;
   const int b = min(a + per, gr.n_pad + L);
-  float* qs = reinterpret_cast<float*>(sm.scratch);                  // [npairs<=16][128]
-  float* wp = reinterpret_cast<float*>(sm.scratch) + 16 * kHeadDim;  // [8][kPartStride]
+  float* qs = reinterpret_cast<float*>(sm.scratch);
+  float* wp = qs + 16 * kHeadDim;
   const float scale = rsqrtf((float)kHeadDim);
+  const uint32_t ep_in = ep - 1;
+  prof_mark(p, pidx, 0);
 
-  // -- step 1: queries (norm + rope) to smem; new K/V rows of this chunk to the cache
-  for (int j = warp; j < npairs; j += kConsumerWarps) {
-    const int r = j / gq, qh = kvh * gq + (j - r * gq);
-    const int rp = min(max(gr.pos0 + r + gr.rope_delta, 0), S.rope_len - 1);
-    float x[4];
-    load4(qkv + (size_t)(gr.first_row + r) * ldq + qh * kHeadDim + lane * 4, x);
-    head_norm_rope(x, qn, S.eps, S.rope_cos + (size_t)rp * kHeadDim, S.rope_sin + (size_t)rp * kHeadDim, lane);
-    *reinterpret_cast<float4*>(qs + j * kHeadDim + lane * 4) = make_float4(x[0], x[1], x[2], x[3]);
-  }
-  for (int r = warp; r < gr.nrows; r += kConsumerWarps) {
-    const int pos = gr.pos0 + r;
-    if (pos >= a && pos < b) {
-      const int rp = min(max(pos + gr.rope_delta, 0), S.rope_len - 1);
+  // -- step 1: queries (norm + rope, pre-scaled) to smem; new K/V rows of this chunk to the cache.
+  //    Work items 0..npairs-1 are queries, npairs..npairs+nrows-1 are k/v rows; one warp each.
+  for (int it = warp; it < npairs + gr.nrows; it += kConsumerWarps) {
+    if (it < npairs) {
+      const int j = it;
+      const int r = j / gq, qh = kvh * gq + (j - r * gq);
+      const int rp = min(max(gr.pos0 + r + gr.rope_delta, 0), S.rope_len - 1);
+      const LLWord* src = qkv + (size_t)(gr.first_row + r) * ldq + qh * kHeadDim + lane * 4;
+      LLWord w[4];
+      ll_issue4(src, w);
+      const uint2 g2 = ld_bf16x4(qn + lane * 4);
+      const uint2 c2 = ld_bf16x4(S.rope_cos + (size_t)rp * kHeadDim + lane * 4);
+      const uint2 s2 = ld_bf16x4(S.rope_sin + (size_t)rp * kHeadDim + lane * 4);
       float x[4];
-      load4(qkv + (size_t)(gr.first_row + r) * ldq + S.nq * kHeadDim + kvh * kHeadDim + lane * 4, x);
-      head_norm_rope(x, kn, S.eps, S.rope_cos + (size_t)rp * kHeadDim, S.rope_sin + (size_t)rp * kHeadDim, lane);
-      uint2 kk;
-      kk.x = pack_bf16x2(x[0], x[1]);
-      kk.y = pack_bf16x2(x[2], x[3]);
-      *reinterpret_cast<uint2*>(Kc + (size_t)pos * kHeadDim + lane * 4) = kk;
-      const uint2 vv = __ldcg(reinterpret_cast<const uint2*>(
-          qkv + (size_t)(gr.first_row + r) * ldq + (S.nq + S.nkv) * kHeadDim + kvh * kHeadDim + lane * 4));
-      *reinterpret_cast<uint2*>(Vc + (size_t)pos * kHeadDim + lane * 4) = vv;
+      ll_finish4(w, src, ep_in, p, pidx, x);
+      head_norm_rope(x, g2, S.eps, c2, s2, lane);
+      *reinterpret_cast<float4*>(qs + j * kHeadDim + lane * 4) =
+          make_float4(x[0] * scale, x[1] * scale, x[2] * scale, x[3] * scale);
+    } else {
+      const int r = it - npairs;
+      const int pos = gr.pos0 + r;
+      if (pos >= a && pos < b) {
+        const int rp = min(max(pos + gr.rope_delta, 0), S.rope_len - 1);
+        const LLWord* row = qkv + (size_t)(gr.first_row + r) * ldq;
+        const LLWord* ksrc = row + S.nq * kHeadDim + kvh * kHeadDim + lane * 4;
+        const LLWord* vsrc = row + (S.nq + S.nkv) * kHeadDim + kvh * kHeadDim + lane * 4;
+        LLWord wk[4], wv[4];
+        ll_issue4(ksrc, wk);
+        ll_issue4(vsrc, wv);
+        const uint2 g2 = ld_bf16x4(kn + lane * 4);
+        const uint2 c2 = ld_bf16x4(S.rope_cos + (size_t)rp * kHeadDim + lane * 4);
+        const uint2 s2 = ld_bf16x4(S.rope_sin + (size_t)rp * kHeadDim + lane * 4);
+        float x[4], v[4];
+        ll_finish4(wk, ksrc, ep_in, p, pidx, x);
+        ll_finish4(wv, vsrc, ep_in, p, pidx, v);
+        head_norm_rope(x, g2, S.eps, c2, s2, lane);
+        uint2 kk, vv;
+        kk.x = pack_bf16x2(x[0], x[1]); kk.y = pack_bf16x2(x[2], x[3]);
+        vv.x = pack_bf16x2(v[0], v[1]); vv.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(Kc + (size_t)pos * kHeadDim + lane * 4) = kk;
+        *reinterpret_cast<uint2*>(Vc + (size_t)pos * kHeadDim + lane * 4) = vv;
+      }
     }
   }
   cbar_sync();
+  prof_mark(p, pidx, 1);
 
-  // -- step 2: online-softmax attention over [a, b)
-  int wpp = 1;
-  if (npairs < kConsumerWarps) { wpp = kConsumerWarps / npairs; }
-  const bool split_warps = (npairs < kConsumerWarps) && (npairs * wpp == kConsumerWarps);
-  if (!split_warps) wpp = 1;
-  float* part_g = p.attn_part;
-  for (int j0 = (split_warps ? warp / wpp : warp); j0 < npairs; j0 += (split_warps ? npairs : kConsumerWarps)) {
-    const int j = j0;
-    const int sub = split_warps ? (warp - j * wpp) : 0;
-    const int r = j / gq, qh = kvh * gq + (j - r * gq);
-    const float4 q4 = *reinterpret_cast<const float4*>(qs + j * kHeadDim + lane * 4);
-    const int pend = min(b, gr.pos0 + r + 1);
-    float m_run = -INFINITY, l_run = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int pp = a + sub; pp < pend; pp += 4 * wpp) {
-      uint2 kk[4], vv[4];
+  // -- step 2: pairs in batches of <= 4 share one sweep over K/V.  QK^T: one lane per position (no shuffles);
+  //            P·V: lane owns 4 output dims, probabilities broadcast by shuffle.  Warp w sweeps positions
+  //            a+32w, a+32w+512, ...
+  for (int j0 = 0; j0 < npairs; j0 += kAttnPairsMax) {
+    const int np = min(kAttnPairsMax, npairs - j0);
+    float m_run[kAttnPairsMax], l_run[kAttnPairsMax], acc[kAttnPairsMax][4];
+    int pend[kAttnPairsMax];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int q = pp + u * wpp;
-        if (q < pend) {
-          kk[u] = __ldcg(reinterpret_cast<const uint2*>(Kc + (size_t)q * kHeadDim + lane * 4));
-          vv[u] = __ldcg(reinterpret_cast<const uint2*>(Vc + (size_t)q * kHeadDim + lane * 4));
+    for (int j = 0; j < kAttnPairsMax; ++j) {
+      m_run[j] = -INFINITY; l_run[j] = 0.f;
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      const int r = (j0 + j) / gq;
+      pend[j] = (j < np) ? min(b, gr.pos0 + r + 1) : 0;  // causal bound of this pair's row
+    }
+    for (int pb = a + warp * 32; pb < b; pb += 32 * kConsumerWarps) {
+      const int pos = pb + lane;
+      const bool valid = pos < b;
+      float s[kAttnPairsMax];
+#pragma unroll
+      for (int j = 0; j < kAttnPairsMax; ++j) s[j] = 0.f;
+      if (valid) {
+        const uint4* krow = reinterpret_cast<const uint4*>(Kc + (size_t)pos * kHeadDim);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 kreg[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) kreg[c] = __ldcg(krow + h * 8 + c);  // 8 independent loads in flight
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 kk = kreg[c];
+            const float k0 = bf_lo(kk.x), k1 = bf_hi(kk.x), k2 = bf_lo(kk.y), k3 = bf_hi(kk.y);
+            const float k4 = bf_lo(kk.z), k5 = bf_hi(kk.z), k6 = bf_lo(kk.w), k7 = bf_hi(kk.w);
+#pragma unroll
+            for (int j = 0; j < kAttnPairsMax; ++j) {
+              if (j < np) {
+                const float* qp = qs + (j0 + j) * kHeadDim + (h * 8 + c) * 8;
+                const float4 qa = *reinterpret_cast<const float4*>(qp);
+                const float4 qb4 = *reinterpret_cast<const float4*>(qp + 4);
+                s[j] += qa.x * k0 + qa.y * k1 + qa.z * k2 + qa.w * k3 + qb4.x * k4 + qb4.y * k5 + qb4.z * k6 + qb4.w * k7;
+              }
+            }
+          }
         }
       }
+      float pr[kAttnPairsMax];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int q = pp + u * wpp;
-        if (q < pend) {
-          float s = q4.x * bf_lo(kk[u].x) + q4.y * bf_hi(kk[u].x) + q4.z * bf_lo(kk[u].y) + q4.w * bf_hi(kk[u].y);
-          s = warp_sum(s) * scale;
-          const float m_new = fmaxf(m_run, s);
-          const float corr = expf(m_run - m_new);
-          const float pr = expf(s - m_new);
-          l_run = l_run * corr + pr;
-          acc[0] = acc[0] * corr + pr * bf_lo(vv[u].x);
-          acc[1] = acc[1] * corr + pr * bf_hi(vv[u].x);
-          acc[2] = acc[2] * corr + pr * bf_lo(vv[u].y);
-          acc[3] = acc[3] * corr + pr * bf_hi(vv[u].y);
-          m_run = m_new;
+      for (int j = 0; j < kAttnPairsMax; ++j) {
+        const bool ok = valid && (j < np) && (pos < pend[j]);
+        const float sv = ok ? s[j] : -INFINITY;
+        const float m_new = fmaxf(m_run[j], warp_max(sv));
+        const float corr = (m_run[j] == -INFINITY) ? 0.f : expf(m_run[j] - m_new);
+        pr[j] = ok ? expf(sv - m_new) : 0.f;
+        l_run[j] = l_run[j] * corr + warp_sum(pr[j]);
+        acc[j][0] *= corr; acc[j][1] *= corr; acc[j][2] *= corr; acc[j][3] *= corr;
+        m_run[j] = m_new;
+      }
+      const int nvalid = min(32, b - pb);
+      for (int i0 = 0; i0 < nvalid; i0 += 8) {
+        uint2 vreg[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (i0 + u < nvalid) vreg[u] = __ldcg(reinterpret_cast<const uint2*>(Vc + (size_t)(pb + i0 + u) * kHeadDim + lane * 4));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (i0 + u < nvalid) {
+            const float v0 = bf_lo(vreg[u].x), v1 = bf_hi(vreg[u].x), v2 = bf_lo(vreg[u].y), v3 = bf_hi(vreg[u].y);
+#pragma unroll
+            for (int j = 0; j < kAttnPairsMax; ++j) {
+              if (j < np) {
+                const float pj = __shfl_sync(0xffffffffu, pr[j], i0 + u);
+                acc[j][0] = fmaf(pj, v0, acc[j][0]); acc[j][1] = fmaf(pj, v1, acc[j][1]);
+                acc[j][2] = fmaf(pj, v2, acc[j][2]); acc[j][3] = fmaf(pj, v3, acc[j][3]);
+              }
+            }
+          }
         }
       }
     }
-    if (split_warps) {
-      float* w = wp + warp * kPartStride;
-      if (lane == 0) { w[0] = m_run; w[1] = l_run; }
-      *reinterpret_cast<float4*>(w + 4 + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    } else {
-      // this warp owns the whole pair: emit directly
-      const int row = gr.first_row + r;
-      if (nsplit == 1) {
-        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-        uint2 o;
-        o.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
-        o.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
-        *reinterpret_cast<uint2*>(att + (size_t)row * lda + qh * kHeadDim + lane * 4) = o;
-      } else {
-        float* dst = part_g + (((size_t)row * S.nq + qh) * kMaxSplits + sp) * kPartStride;
-        if (lane == 0) { dst[0] = m_run; dst[1] = l_run; }
-        *reinterpret_cast<float4*>(dst + 4 + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+    for (int j = 0; j < kAttnPairsMax; ++j) {
+      if (j < np) {
+        float* w = wp + ((size_t)warp * kAttnPairsMax + j) * kPartStride;
+        if (lane == 0) { w[0] = m_run[j]; w[1] = l_run[j]; }
+        *reinterpret_cast<float4*>(w + 4 + lane * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
       }
     }
-  }
-  if (split_warps) {
+    prof_mark(p, pidx, 2);
     cbar_sync();
-    // merge the wpp warps of each pair
-    for (int o = threadIdx.x; o < npairs * kHeadDim; o += kConsumerThreads) {
+    // merge the warp partials of each pair (fixed order => deterministic)
+    for (int o = threadIdx.x; o < np * kHeadDim; o += kConsumerThreads) {
       const int j = o / kHeadDim, dd = o - j * kHeadDim;
-      const int r = j / gq, qh = kvh * gq + (j - r * gq);
+      const int r = (j0 + j) / gq, qh = kvh * gq + ((j0 + j) - r * gq);
       const int row = gr.first_row + r;
-      float M = -INFINITY;
-      for (int s = 0; s < wpp; ++s) M = fmaxf(M, wp[(j * wpp + s) * kPartStride]);
+      float Mx = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kConsumerWarps; ++w) Mx = fmaxf(Mx, wp[((size_t)w * kAttnPairsMax + j) * kPartStride]);
       float Lsum = 0.f, O = 0.f;
-      for (int s = 0; s < wpp; ++s) {
-        const float* w = wp + (j * wpp + s) * kPartStride;
-        const float f = (w[0] == -INFINITY) ? 0.f : expf(w[0] - M);
-        Lsum += w[1] * f;
-        O += w[4 + dd] * f;
+#pragma unroll
+      for (int w = 0; w < kConsumerWarps; ++w) {
+        const float* q = wp + ((size_t)w * kAttnPairsMax + j) * kPartStride;
+        const float f = (q[0] == -INFINITY) ? 0.f : expf(q[0] - Mx);
+        Lsum += q[1] * f;
+        O += q[4 + dd] * f;
       }
       if (nsplit == 1) {
-        att[(size_t)row * lda + qh * kHeadDim + dd] = __float2bfloat16_rn(Lsum > 0.f ? O / Lsum : 0.f);
+        ll_st(att + (size_t)row * lda + qh * kHeadDim + dd, bf16r(Lsum > 0.f ? O / Lsum : 0.f), ep);
       } else {
-        float* dst = part_g + (((size_t)row * S.nq + qh) * kMaxSplits + sp) * kPartStride;
-        if (dd == 0) { dst[0] = M; dst[1] = Lsum; }
+        float* dst = p.attn_part + (((size_t)row * S.nq + qh) * kMaxSplits + sp) * kPartStride;
+        if (dd == 0) { dst[0] = Mx; dst[1] = Lsum; }
         dst[4 + dd] = O;
       }
     }
+    cbar_sync();
   }
+  prof_mark(p, pidx, 3);
   if (nsplit > 1) {
-    // -- step 3: last-arriving split of this (sequence, kv head) combines the partials (fixed order => deterministic)
+    // -- step 3: last-arriving split of this (sequence, kv head) combines the partials
     __threadfence();
     cbar_sync();
     int* flag = sm.ctl + 4;
@@ -603,42 +760,56 @@ __device__ void attn_item(const Phase& ph, const LaunchParams& p, const Smem& sm
         const int j = o / kHeadDim, dd = o - j * kHeadDim;
         const int r = j / gq, qh = kvh * gq + (j - r * gq);
         const int row = gr.first_row + r;
-        const float* src = part_g + (((size_t)row * S.nq + qh) * kMaxSplits) * kPartStride;
-        float M = -INFINITY;
-        for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(src + s * kPartStride));
+        const float* src = p.attn_part + (((size_t)row * S.nq + qh) * kMaxSplits) * kPartStride;
+        float Mx = -INFINITY;
+        for (int s = 0; s < nsplit; ++s) Mx = fmaxf(Mx, __ldcg(src + s * kPartStride));
         float Lsum = 0.f, O = 0.f;
         for (int s = 0; s < nsplit; ++s) {
           const float ms = __ldcg(src + s * kPartStride);
-          const float f = (ms == -INFINITY) ? 0.f : expf(ms - M);
+          const float f = (ms == -INFINITY) ? 0.f : expf(ms - Mx);
           Lsum += __ldcg(src + s * kPartStride + 1) * f;
           O += __ldcg(src + s * kPartStride + 4 + dd) * f;
         }
-        att[(size_t)row * lda + qh * kHeadDim + dd] = __float2bfloat16_rn(Lsum > 0.f ? O / Lsum : 0.f);
+        ll_st(att + (size_t)row * lda + qh * kHeadDim + dd, bf16r(Lsum > 0.f ? O / Lsum : 0.f), ep);
       }
     }
+    cbar_sync();
   }
-  cbar_sync();
 }
 
-__device__ void attn_phase(const Phase& ph, const LaunchParams& p, const Smem& sm) {
+__device__ void attn_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
+                           const int* frame_pos) {
+  const Smem sm = carve_smem(smem_base, p);
   const StackRt& S = p.stacks[ph.stack];
   const int G = gridDim.x, cta = blockIdx.x;
   const int ng = num_groups(p);
-  int item = 0;
+  // item -> CTA: spread items over the whole grid (stride) so concurrent items sit on distant SMs
+  int total = 0;
   for (int g = 0; g < ng; ++g) {
-    const Group gr = get_group(ph, p, g);
+    const Group gr = get_group(ph, p, g, frame_pos);
+    total += S.nkv * num_splits(gr.pos0 + gr.nrows - gr.n_pad, ng, S.nkv, G);
+  }
+  const int stride = max(1, G / max(1, total));
+  int item = 0;
+  bool any = false;
+  for (int g = 0; g < ng; ++g) {
+    const Group gr = get_group(ph, p, g, frame_pos);
     const int L = gr.pos0 + gr.nrows - gr.n_pad;
     const int nsplit = num_splits(L, ng, S.nkv, G);
     const int nitems = S.nkv * nsplit;
-    // first item of this group that belongs to this CTA
-    int first = (cta - item % G + G) % G;
-    for (int it = first; it < nitems; it += G) attn_item(ph, p, sm, gr, it / nsplit, it % nsplit, nsplit);
+    for (int it = 0; it < nitems; ++it) {
+      if (((item + it) * stride) % G == cta) {
+        attn_item(ph, p, smem_base, gr, it / nsplit, it % nsplit, nsplit, ep, pidx);
+        any = true;
+      }
+    }
     item += nitems;
   }
+  (void)any;  // the KV rows written here are fenced once per step in sample_phase (off the critical path)
 }
 
 // =================================================================================================
-// Sampling (sampling.py:10-66) — block-wide, 256 consumer threads, one stream per CTA
+// Sampling (sampling.py:10-66) — block-wide, 512 consumer threads, one stream per CTA
 // =================================================================================================
 __device__ __forceinline__ uint32_t f2key(float f) {
   uint32_t u = __float_as_uint(f);
@@ -666,16 +837,16 @@ struct SampleScratch {
   float* redf;     // [32]
   int* redi;       // [32]
 };
-__device__ __forceinline__ SampleScratch sample_scratch(const Smem& sm) {
+__device__ __forceinline__ SampleScratch sample_scratch(unsigned char* scratch) {
   SampleScratch s;
-  s.sl = reinterpret_cast<float*>(sm.scratch);
-  s.hist = reinterpret_cast<unsigned*>(sm.scratch + 13 * 1024);
-  s.redf = reinterpret_cast<float*>(sm.scratch + 14 * 1024);
-  s.redi = reinterpret_cast<int*>(sm.scratch + 14 * 1024 + 256);
+  s.sl = reinterpret_cast<float*>(scratch);
+  s.hist = reinterpret_cast<unsigned*>(scratch + 20 * 1024);
+  s.redf = reinterpret_cast<float*>(scratch + 21 * 1024);
+  s.redi = reinterpret_cast<int*>(scratch + 21 * 1024 + 256);
   return s;
 }
 
-__device__ float block_sum(float v, float* red) {
+__device__ __noinline__ float block_sum(float v, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   v = warp_sum(v);
   cbar_sync();
@@ -686,7 +857,7 @@ __device__ float block_sum(float v, float* red) {
   for (int w = 0; w < kConsumerWarps; ++w) t += red[w];
   return t;
 }
-__device__ float block_max(float v, float* red) {
+__device__ __noinline__ float block_max(float v, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   v = warp_max(v);
   cbar_sync();
@@ -698,7 +869,7 @@ __device__ float block_max(float v, float* red) {
   return t;
 }
 // argmax with lowest-index tie-break (torch.argmax on a 1-row tensor)
-__device__ int block_argmax(const float* sl, int V, float* redf, int* redi, float* out_val) {
+__device__ __noinline__ int block_argmax(const float* sl, int V, float* redf, int* redi, float* out_val) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float bv = -INFINITY;
   int bi = 0x7fffffff;
@@ -726,14 +897,14 @@ __device__ int block_argmax(const float* sl, int V, float* redf, int* redi, floa
 }
 
 // k-th largest value (counting multiplicity) by 4-pass radix select on order-preserving keys.
-__device__ float kth_largest(const float* sl, int V, int k, unsigned* hist, int* redi) {
+__device__ __noinline__ float kth_largest(const float* sl, int V, int k, unsigned* hist, int* redi) {
   uint32_t prefix = 0;
   int krem = k;
   const int lane = threadIdx.x & 31;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     cbar_sync();
-    hist[threadIdx.x] = 0;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     cbar_sync();
     for (int i = threadIdx.x; i < V; i += kConsumerThreads) {
       const uint32_t key = f2key(sl[i]);
@@ -786,12 +957,26 @@ struct SampleArgs {
   unsigned long long seed, draw;
 };
 
-__device__ int sample_row(const float* logits_g, const SampleArgs& a, const SampleScratch& sc) {
+// logits arrive either as LL words (ll != null, epoch ep) or as a plain fp32 array.
+__device__ __noinline__ int sample_row(const float* logits_g, const LLWord* ll, uint32_t ep, const LaunchParams* lp, int pidx,
+                          const SampleArgs& a, const SampleScratch& sc) {
   float* sl = sc.sl;
   const int V = a.V;
   // 1. load + repetition penalty (sampling.py:22-29, before suppression) + suppression + temperature
-  for (int i = threadIdx.x; i < V; i += kConsumerThreads) {
-    float x = __ldcg(logits_g + i);
+  constexpr int kLg = (kMaxVocab + kConsumerThreads - 1) / kConsumerThreads;  // 11
+  LLWord lw[kLg];
+  if (ll) {
+#pragma unroll
+    for (int j = 0; j < kLg; ++j) {
+      const int i = threadIdx.x + j * kConsumerThreads;
+      if (i < V) lw[j] = ll_ld(ll + i);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kLg; ++j) {
+    const int i = threadIdx.x + j * kConsumerThreads;
+    if (i >= V) continue;
+    float x = ll ? ll_check(lw[j], ll + i, ep, *lp, pidx) : __ldcg(logits_g + i);
     if (a.seen && a.rep_pen != 1.0f && __ldcg(a.seen + i)) {
       x = (x > 0.f) ? x / a.rep_pen : x * a.rep_pen;
       if (a.round_bf16) x = bf16r(x);
@@ -850,12 +1035,10 @@ __device__ int sample_row(const float* logits_g, const SampleArgs& a, const Samp
       keep_ties = (int)floorf((P - above) / pe);
       if (keep_ties < 0) keep_ties = 0;
     }
-    // rank ties by index with a serial walk per thread over a contiguous segment + block scan
     const int seg = (V + kConsumerThreads - 1) / kConsumerThreads;
     const int i0 = threadIdx.x * seg, i1 = min(V, i0 + seg);
     int cnt = 0;
     for (int i = i0; i < i1; ++i) cnt += (sl[i] == bval) ? 1 : 0;
-    // exclusive scan of cnt across threads
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int incl = cnt;
 #pragma unroll
@@ -921,42 +1104,48 @@ __device__ int sample_row(const float* logits_g, const SampleArgs& a, const Samp
   return tok;
 }
 
-// Copy one bf16 row (n elements, multiple of 8) between global buffers with all consumer threads.
-__device__ __forceinline__ void copy_row(bf16* dst, const bf16* src, int n) {
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  for (int c = threadIdx.x; c < (n >> 3); c += kConsumerThreads) d[c] = __ldcg(s + c);
+// Publish one bf16 row (n elements) as LL words with all consumer threads.
+__device__ __forceinline__ void publish_row(LLWord* dst, const bf16* src, int n, uint32_t ep) {
+  for (int c = threadIdx.x; c < n; c += kConsumerThreads) ll_st(dst + c, __bfloat162float(src[c]), ep);
 }
 
-__device__ void sample_phase(const Phase& ph, const LaunchParams& p, const Smem& sm, int iter) {
-  const SampleScratch sc = sample_scratch(sm);
+__device__ __noinline__ void sample_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
+                             const int* frame_done) {
+  const Smem sm = carve_smem(smem_base, p);
+  const SampleScratch sc = sample_scratch(sm.scratch);
   const int Ht = p.stacks[ST_TALKER].hidden;
   const int ncb = p.n_code_groups - 1;
-  int* bc = sm.ctl + 8;
+  const uint32_t ep_in = ep - 1;
+  // CTAs without a stream idle through sampling phases: the once-per-step fence that makes this step's KV
+  // rows visible to whichever CTA reads them in a later step goes here, off the critical path.
+  if ((int)blockIdx.x >= (p.mode == MODE_PREFILL ? 1 : p.n_rows) && threadIdx.x == 0 && ph.kind != SMP_PRED && ph.kind != SMP_PRED_ONLY)
+    __threadfence();
   for (int b = blockIdx.x; b < (p.mode == MODE_PREFILL ? 1 : p.n_rows); b += gridDim.x) {
     const int slot = p.stream0 + b;
     StreamState* st = p.st + slot;
-    const int done = __ldcg(&st->done);
-    bf16* pin = reinterpret_cast<bf16*>(p.bufs[p.has_s2m ? BUF_PIN : BUF_PX]);
+    const int done = (p.mode == MODE_FRAMES) ? frame_done[b] : 0;
+    LLWord* pin = reinterpret_cast<LLWord*>(p.bufs[p.has_s2m ? BUF_PIN : BUF_PX]);
     const int ldpin = p.ld[p.has_s2m ? BUF_PIN : BUF_PX];
+    const LLWord* lgbuf = reinterpret_cast<const LLWord*>(p.bufs[BUF_LOGITS]);
     if (ph.kind == SMP_PRED || ph.kind == SMP_PRED_ONLY) {
       const int i = ph.aux;  // codebook step 0..ncb-1
       const int Vp = p.stacks[ST_PRED].vocab;
       const int lrow = (ph.flags & F_ROWS2) ? 2 * b + 1 : b;
-      const float* lg = reinterpret_cast<const float*>(p.bufs[BUF_LOGITS]) + (size_t)lrow * p.ld[BUF_LOGITS];
+      const LLWord* lg = lgbuf + (size_t)lrow * p.ld[BUF_LOGITS];
       if (p.pred_logits_all) {
-        for (int v = threadIdx.x; v < Vp; v += kConsumerThreads) p.pred_logits_all[(size_t)i * Vp + v] = __ldcg(lg + v);
+        for (int v = threadIdx.x; v < Vp; v += kConsumerThreads)
+          p.pred_logits_all[(size_t)i * Vp + v] = ll_wait(lg + v, ep_in, p, pidx);
       }
       SampleArgs a;
       a.V = Vp; a.do_sample = p.sub.do_sample; a.top_k = p.sub.top_k; a.top_p = p.sub.top_p;
       a.temperature = p.sub.temperature; a.rep_pen = 1.0f; a.seen = nullptr; a.suppress_start = Vp; a.eos = -1;
       a.suppress_eos = 0; a.round_bf16 = 1; a.seed = p.pol.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(slot + 1));
       a.draw = __ldcg(&st->draws) + (unsigned long long)(i + 1);
-      const int tok = sample_row(lg, a, sc);
+      const int tok = sample_row(nullptr, lg, ep_in, &p, pidx, a, sc);
       if (threadIdx.x == 0) st->cur_codes[i + 1] = tok;
       if (i + 1 < ncb) {
         // next predictor input row: codec_embeds[i](tok)  (predictor_graph.py:144)
-        copy_row(pin + (size_t)b * ldpin, p.pred_embeds[i] + (size_t)tok * Ht, Ht);
+        publish_row(pin + (size_t)b * ldpin, p.pred_embeds[i] + (size_t)tok * Ht, Ht, ep);
       } else if (ph.kind == SMP_PRED) {
         // frame complete: append [c0..c15], then build the next talker input (generate.py:159-171)
         const int nfr = __ldcg(&st->n_frames);
@@ -976,7 +1165,7 @@ __device__ void sample_phase(const Phase& ph, const LaunchParams& p, const Smem&
         const int gs = __ldcg(&st->gen_step);
         const int ntr = __ldcg(&st->n_trailing);
         const bf16* text = (gs < ntr) ? st->trailing + (size_t)gs * Ht : st->pad_embed;
-        bf16* tx = reinterpret_cast<bf16*>(p.bufs[BUF_TX]) + (size_t)b * p.ld[BUF_TX];
+        LLWord* tx = reinterpret_cast<LLWord*>(p.bufs[BUF_TX]) + (size_t)b * p.ld[BUF_TX];
         for (int c = threadIdx.x; c < Ht; c += kConsumerThreads) {
           float s = __bfloat162float(p.codec_embed[(size_t)c0 * Ht + c]);
           for (int g = 0; g < ncb; ++g) {
@@ -984,9 +1173,9 @@ __device__ void sample_phase(const Phase& ph, const LaunchParams& p, const Smem&
             s += __bfloat162float(p.pred_embeds[g][(size_t)code * Ht + c]);
           }
           const float e = bf16r(s);
-          tx[c] = __float2bfloat16_rn(e + __bfloat162float(text[c]));
+          ll_st(tx + c, bf16r(e + __bfloat162float(text[c])), ep);
         }
-        // static-cache bound (generate.py:174-177): the frame stays, decoding stops
+        // static-cache bound (generate.py:174-177): the frame stays, decoding stops after this step
         if (threadIdx.x == 0 && !done) {
           const int pos = __ldcg(&st->position);
           if (pos >= p.stacks[ST_TALKER].max_pos - 1) st->done = 2;
@@ -995,8 +1184,9 @@ __device__ void sample_phase(const Phase& ph, const LaunchParams& p, const Smem&
     } else {
       // SMP_TALKER / SMP_PREFILL: first-codebook sampler (generate.py:124-134, :182-197)
       const int Vt = p.stacks[ST_TALKER].vocab;
-      const float* lg = reinterpret_cast<const float*>(p.bufs[BUF_LOGITS]) + (size_t)b * p.ld[BUF_LOGITS];
+      const LLWord* lg = lgbuf + (size_t)b * p.ld[BUF_LOGITS];
       const int nfr = __ldcg(&st->n_frames);
+      const int done_now = (ph.kind == SMP_PREFILL) ? 0 : __ldcg(&st->done);  // includes this frame's cache-bound stop
       SampleArgs a;
       a.V = Vt; a.do_sample = p.pol.do_sample; a.top_k = p.pol.top_k; a.top_p = p.pol.top_p;
       a.temperature = p.pol.temperature; a.rep_pen = p.pol.rep_pen;
@@ -1006,29 +1196,31 @@ __device__ void sample_phase(const Phase& ph, const LaunchParams& p, const Smem&
       a.round_bf16 = 1;
       a.seed = p.pol.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(slot + 1));
       a.draw = __ldcg(&st->draws);
-      const int tok = sample_row(lg, a, sc);
-      const bool live = (ph.kind == SMP_PREFILL) || !done;
-      if (threadIdx.x == 0 && live) {
-        st->token = tok;
-        st->draws = a.draw + 1ull;
-        if (ph.kind == SMP_TALKER) {
-          st->position = __ldcg(&st->position) + 1;
-          st->gen_step = __ldcg(&st->gen_step) + 1;
-        }
-        if (tok == p.eos_id) st->done = 1;  // generate.py:150 — checked before the next frame is built
-      }
+      int tok = sample_row(nullptr, lg, ep_in, &p, pidx, a, sc);
+      const bool live = !done_now;
+      int new_done = done_now, new_pos = __ldcg(&st->position), new_gs = __ldcg(&st->gen_step);
       if (live) {
-        // predictor pass-0 input rows: [past_hidden ; codec_embed(token)]  (generate.py:154-155)
-        // (addressed by stream slot so a later prefill of another stream cannot clobber them)
-        const bf16* hid = reinterpret_cast<const bf16*>(p.bufs[BUF_HID]) + (size_t)b * p.ld[BUF_HID];
-        copy_row(pin + (size_t)(2 * slot) * ldpin, hid, Ht);
-        copy_row(pin + (size_t)(2 * slot + 1) * ldpin, p.codec_embed + (size_t)tok * Ht, Ht);
+        if (ph.kind == SMP_TALKER) { new_pos += 1; new_gs += 1; }
+        if (tok == p.eos_id) new_done = 1;  // generate.py:150 — checked before the next frame is built
+      } else {
+        tok = __ldcg(&st->token);
       }
+      cbar_sync();  // everyone has read the old state
+      if (threadIdx.x == 0) {
+        if (live) { st->token = tok; st->draws = a.draw + 1ull; st->position = new_pos; st->gen_step = new_gs; st->done = new_done; }
+        // control record every CTA reads at the top of the next frame
+        ll_st(&st->ctl[0], __int_as_float(new_done), ep);
+        ll_st(&st->ctl[1], __int_as_float(new_pos), ep);
+      }
+      // predictor pass-0 input rows [past_hidden ; codec_embed(token)] (generate.py:154-155), addressed by
+      // stream slot; always re-published so every reader sees this phase's epoch
+      const bf16* hid = reinterpret_cast<const bf16*>(p.bufs[BUF_HID]) + (size_t)b * p.ld[BUF_HID];
+      publish_row(pin + (size_t)(2 * slot) * ldpin, hid, Ht, ep);
+      publish_row(pin + (size_t)(2 * slot + 1) * ldpin, p.codec_embed + (size_t)tok * Ht, Ht, ep);
+      if (threadIdx.x == 0) __threadfence();
     }
     cbar_sync();
   }
-  (void)bc;
-  (void)iter;
 }
 
 // =================================================================================================
@@ -1042,7 +1234,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);
+      mbar_init(&sm.empty[s], kConsumerWarps);
     }
     sm.ctl[0] = 0;
     fence_barrier_init();
@@ -1064,14 +1256,14 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
           Spin s;
           int go;
           while ((go = ld_volatile_shared_i32(&sm.ctl[0])) >= 0 && go < iter) {
-            __nanosleep(64);
+            __nanosleep(32);
             s.tick(p, DE_HANDSHAKE, -1, iter);
           }
           if (go < 0) break;
         }
         for (int i = 0; i < p.n_phases; ++i) {
           const Phase& ph = sm.prog[i];
-          if (ph.type == PH_GEMV) gemv_phase_produce(ph, p, sm, tile_it, i, pol_stream, pol_keep);
+          if (ph.type == PH_GEMV) gemv_phase_produce(ph, p, smem_raw, tile_it, i, pol_stream, pol_keep);
         }
       }
     }
@@ -1079,37 +1271,54 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
   }
 
   // -------------------------------- consumer warps --------------------------------
-  unsigned epoch = 0, tile_it = 0;
+  unsigned tile_it = 0;
+  int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
+  int* frame_done = sm.ctl + 12;  // [4]
   for (int iter = 0; iter < p.n_iters; ++iter) {
+    const uint32_t ep0 = p.epoch_base + (uint32_t)iter * (uint32_t)p.n_phases;
+    if (p.mode == MODE_FRAMES || p.mode == MODE_TALKER_STEP) {
+      // per-stream frame state: from the stream state at launch, afterwards from the sampler's control record
+      if (tid < p.n_rows) {
+        const StreamState* st = p.st + p.stream0 + tid;
+        int done, pos;
+        if (iter == 0) {
+          done = __ldcg(&st->done);
+          pos = __ldcg(&st->position);
+        } else {
+          done = __float_as_int(ll_wait(&st->ctl[0], ep0, p, -2));
+          pos = __float_as_int(ll_wait(&st->ctl[1], ep0, p, -2));
+        }
+        frame_pos[tid] = pos;
+        frame_done[tid] = done;
+      }
+      cbar_sync();
+      if (p.mode == MODE_FRAMES) {
+        int all_done = 1;
+        for (int b = 0; b < p.n_rows; ++b) all_done &= (frame_done[b] != 0);
+        if (iter > 0 && tid == 0) st_volatile_shared_i32(&sm.ctl[0], all_done ? -1 : iter);
+        if (all_done && iter > 0) break;
+      }
+    }
     for (int i = 0; i < p.n_phases; ++i) {
       const Phase& ph = sm.prog[i];
+      const uint32_t ep = ep0 + (uint32_t)i + 1u;
       switch (ph.type) {
-        case PH_GEMV: gemv_phase_consume(ph, p, sm, tile_it, i); break;
-        case PH_ATTN: if (!(p.debug & 4)) attn_phase(ph, p, sm); break;
-        case PH_SAMPLE: sample_phase(ph, p, sm, iter); break;
+        case PH_GEMV: gemv_phase_consume(ph, p, smem_raw, tile_it, i, ep); break;
+        case PH_ATTN: if (!(p.debug & 4)) attn_phase(ph, p, smem_raw, ep, i, frame_pos); break;
+        case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
         default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
       }
-      if (p.debug & 1) cbar_sync(); else grid_sync(p, epoch, i);
-    }
-    if (p.mode == MODE_FRAMES && iter + 1 < p.n_iters) {
-      // every CTA evaluates the same predicate on the same (barrier-ordered) state
-      int all_done = 1;
-      for (int b = 0; b < p.n_rows; ++b) all_done &= (__ldcg(&p.st[p.stream0 + b].done) != 0);
-      if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], all_done ? -1 : iter + 1);
-      if (all_done) break;
     }
   }
 }
 
-// Small single-CTA kernels -----------------------------------------------------------------------
-// Stand-alone sampler behind fq3_sample (sampling.py parity tests and the duck-typed host loop).
+// Small kernels -----------------------------------------------------------------------------------
+// Stand-alone sampler behind fq3_sample (sampling.py parity tests and the operator-at-a-time host loop).
 __global__ void __launch_bounds__(kConsumerThreads, 1)
 fq3_sample_kernel(const float* logits, SampleArgs a, const long long* history, int n_history, uint8_t* seen_scratch,
                   long long* out) {
   __shared__ __align__(16) unsigned char scratch[kScratchBytes];
-  Smem sm;
-  sm.scratch = scratch;
-  const SampleScratch sc = sample_scratch(sm);
+  const SampleScratch sc = sample_scratch(scratch);
   if (history && n_history > 0 && a.rep_pen != 1.0f) {
     for (int i = threadIdx.x; i < a.V; i += kConsumerThreads) seen_scratch[i] = 0;
     __syncthreads();
@@ -1122,7 +1331,7 @@ fq3_sample_kernel(const float* logits, SampleArgs a, const long long* history, i
   } else {
     a.seen = nullptr;
   }
-  const int tok = sample_row(logits, a, sc);
+  const int tok = sample_row(logits, nullptr, 0u, nullptr, 0, a, sc);
   if (threadIdx.x == 0) out[0] = tok;
 }
 
@@ -1181,6 +1390,29 @@ __global__ void fq3_import_kv_kernel(bf16* kdst, bf16* vdst, const bf16* k, cons
 
 __global__ void fq3_codes_to_i64_kernel(const int* cur_codes, int n, long long* out) {
   if (threadIdx.x < n) out[threadIdx.x] = cur_codes[threadIdx.x + 1];
+}
+
+// Plain bf16 rows -> LL words (epoch 0: "written before launch") and back.
+__global__ void fq3_pack_ll_kernel(LLWord* dst, int ld_dst, const bf16* src, int ld_src, int rows, int cols) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = make_uint2(__float_as_uint(__bfloat162float(src[r * ld_src + c])), 0u);
+  }
+}
+__global__ void fq3_unpack_ll_bf16_kernel(bf16* dst, int ld_dst, const LLWord* src, int ld_src, int rows, int cols) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = __float2bfloat16_rn(__uint_as_float(src[r * ld_src + c].x));
+  }
+}
+__global__ void fq3_unpack_ll_f32_kernel(float* dst, int ld_dst, const LLWord* src, int ld_src, int rows, int cols) {
+  const size_t n = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols, c = i - r * cols;
+    dst[r * ld_dst + c] = __uint_as_float(src[r * ld_src + c].x);
+  }
 }
 
 }  // namespace fq3
