@@ -152,6 +152,9 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
 /* Copy status / codes back (synchronises `stream`). codes_out: host int32 [n, 16]. */
 int fq3_get_status(fq3_engine* e, int stream_idx, fq3_status* out, void* stream);
 int fq3_read_codes(fq3_engine* e, int stream_idx, int first_frame, int n, int32_t* codes_out, void* stream);
+/* Post-final-norm hidden of the last talker pass (`past_hidden`, generate.py:121,198): bf16 [H_t] device.
+ * row = 0 after fq3_prefill / fq3_talker_step, = stream index inside the frame loop. */
+int fq3_last_hidden(fq3_engine* e, int row, void* out_bf16, void* stream);
 /* Device address of the codes buffer int32 [max_frames, 16] of one stream (zero-copy consumers). */
 void* fq3_codes_device_ptr(fq3_engine* e, int stream_idx);
 
@@ -161,7 +164,7 @@ int fq3_debug_read_prof(fq3_engine* e, long long* out, int n_words);
 /* ---- building block exposed for parity tests ------------------------------------------------ */
 /* y[M,N] = epilogue(W[N,K] · prologue(x[M,K])) through the same persistent streaming kernel.
  * flags: bit0 pre-RMSNorm with gamma, bit1 bias, bit2 residual add, bit3 SwiGLU pairing (N = 2*I
- * interleaved rows, output width N/2), bit4 fp32 output.  All pointers device; W inside or outside
+ * interleaved rows, output width N/2), bit4 fp32 output, bit5 SiLU after bias.  All pointers device; W inside or outside
  * the arena. */
 int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int N, int K, int flags,
                const void* gamma, float eps, const void* bias, const void* residual, void* stream);

@@ -1,0 +1,68 @@
+/*
+ * fq3_codec.h — C ABI of the 12 Hz speech-tokenizer decoder kernels (libfq3codec.so).
+ *
+ * Replaces `speech_tokenizer.decode({"audio_codes": [1,T,16]})` of the un-vendored qwen_tts package, which the
+ * reference calls eagerly (cuDNN/ATen conv1d, conv_transpose1d, cuBLAS; SURVEY.md §2c last row) at
+ * faster_qwen3_tts/model.py:642, :782, :811, :884, :971, :988, :1054, :1136, :1153.
+ *
+ * The library is a kernel-launch interpreter: the host (Python, mirroring the reference's Python host) lowers the
+ * decoder for a given frame count T to a flat list of ops over channels-last bf16 activations; every dense
+ * contraction (pointwise / dilated / transposed convs as implicit GEMMs, transformer projections) goes through one
+ * tensor-core GEMM kernel with fused epilogues, the rest (RVQ gather, norms, RoPE, sliding-window attention,
+ * depthwise conv) are small CUDA-core kernels.  Plain pointers only; all pointers are device addresses.
+ */
+#ifndef FQ3_CODEC_H_
+#define FQ3_CODEC_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum fq3c_kind {
+  FQ3C_GEMM = 0,      /* C[M,N] = epi(sum_t A[m + tap_off[t], :cin] . B[n, t*cin:(t+1)*cin])            */
+  FQ3C_RVQ = 1,       /* A=codes i64 [M,Q]; B=codebooks bf16 [Q,cb,dim]; C[M, 2*dim] = [sum first | sum rest] */
+  FQ3C_RMSNORM = 2,   /* C[M,N] = rmsnorm(A[M,N]) * scale(f32 [N]), eps=f0                                  */
+  FQ3C_ROPE = 3,      /* in place on A[M, lda]: i0 heads of dim i1 starting at column i2, theta=f0          */
+  FQ3C_ATTN = 4,      /* A=qkv [M, lda] (q | k | v), i0 heads, i1 kv heads, i2 head_dim, window K; C[M, i0*i2] */
+  FQ3C_DWCONV = 5,    /* depthwise causal conv k=taps: C[m,c] = bias[c] + sum_j B(f32)[c,j] A[m-(taps-1)+j, c]  */
+  FQ3C_LAYERNORM = 6, /* C = layernorm(A) * scale + bias (f32), eps=f0                                      */
+  FQ3C_SNAKE = 7      /* C = A + p1[c] * sin(A * p0[c])^2   (p0 = exp(alpha), p1 = 1/(exp(beta)+1e-9))      */
+};
+
+enum fq3c_flags {
+  FQ3C_BIAS = 1, FQ3C_GELU = 2, FQ3C_RESID = 4, FQ3C_SCALE = 8, FQ3C_SWIGLU = 16, FQ3C_CLAMP = 32,
+  FQ3C_OUT_F32 = 64, FQ3C_SNAKE2 = 128 /* also write C2 = snake(C) */
+};
+
+typedef struct fq3c_op {
+  int32_t kind, flags;
+  int32_t M, N, K;       /* GEMM: K = taps * cin */
+  int32_t taps, cin;
+  int32_t a_rows;        /* valid rows of A (rows outside [0, a_rows) read as zero) */
+  int32_t col_mod;       /* bias / scale / snake parameter index = col % col_mod */
+  int32_t tap_off[8];
+  int32_t lda, ldc, ldr;
+  int32_t i0, i1, i2;
+  float f0, f1;
+  const void* A;
+  const void* B;
+  const void* bias;      /* f32 */
+  const void* res;       /* bf16 [M, ldr] */
+  const void* scale;     /* f32 */
+  const void* p0;        /* f32 */
+  const void* p1;        /* f32 */
+  void* C;
+  void* C2;
+} fq3c_op;
+
+int fq3c_abi_version(void);
+const char* fq3c_last_error(void);
+/* Launch every op in order on `stream` (no synchronisation). Returns 0 or a negative error code. */
+int fq3c_run(const fq3c_op* ops, int n_ops, void* stream);
+/* number of kernel launches issued so far by this process through fq3c_run */
+int64_t fq3c_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

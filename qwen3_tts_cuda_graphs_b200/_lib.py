@@ -69,6 +69,7 @@ SYMBOLS = {
     "fq3_decode_frames": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Policy), C.POINTER(SubPolicy), _P]),
     "fq3_get_status": (C.c_int, [_P, C.c_int, C.POINTER(Status), _P]),
     "fq3_read_codes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _P]),
+    "fq3_last_hidden": (C.c_int, [_P, C.c_int, _P, _P]),
     "fq3_codes_device_ptr": (_P, [_P, C.c_int]),
     "fq3_debug_read_prof": (C.c_int, [_P, C.POINTER(C.c_longlong), C.c_int]),
     "fq3_linear": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_float, _P, _P, _P]),

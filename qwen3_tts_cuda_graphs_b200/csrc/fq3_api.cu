@@ -693,6 +693,14 @@ int fq3_debug_read_prof(fq3_engine* e, long long* out, int n_words) {
   return 0;
 }
 
+int fq3_last_hidden(fq3_engine* e, int row, void* out_bf16, void* stream) {
+  if (!e || !out_bf16 || row < 0 || row >= e->max_rows) return fail(FQ3_E_INVALID, "bad arguments");
+  const int Ht = e->tk.d.hidden;
+  CK(cudaMemcpyAsync(out_bf16, reinterpret_cast<const bf16*>(e->bufs[BUF_HID]) + (size_t)row * e->ld[BUF_HID], (size_t)Ht * 2,
+                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 void* fq3_codes_device_ptr(fq3_engine* e, int idx) {
   if (!e || idx < 0 || idx >= e->desc.max_streams) return nullptr;
   return e->h_st[idx].codes;
@@ -708,7 +716,7 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
   Phase ph{};
   ph.type = PH_GEMV;
   ph.flags = F_ABSPTR | ((flags & 1) ? F_PRENORM : 0) | ((flags & 2) ? F_BIAS : 0) | ((flags & 4) ? F_RESID : 0) |
-             ((flags & 8) ? F_SWIGLU : 0) | ((flags & 16) ? F_OUT_F32 : 0);
+             ((flags & 8) ? F_SWIGLU : 0) | ((flags & 16) ? F_OUT_F32 : 0) | ((flags & 32) ? F_SILU : 0);
   ph.in_buf = BUF_LIN_IN; ph.out_buf = BUF_LIN_OUT; ph.res_buf = BUF_LIN_RES;
   ph.N = (uint32_t)N; ph.K = (uint32_t)K;
   CK(cudaMemcpyAsync(e->d_linear, &ph, sizeof ph, cudaMemcpyHostToDevice, s));

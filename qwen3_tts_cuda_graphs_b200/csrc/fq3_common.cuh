@@ -53,7 +53,8 @@ enum PhaseFlags : uint16_t {
   F_LAST_ROW = 64,      // only the last input row is used (prefill head)
   F_WRITE_NORMED = 128, // CTA 0 also stores the normalised input rows (past_hidden)
   F_L2_KEEP = 256,      // weights are re-read soon (predictor): L2 evict_last hint
-  F_ABSPTR = 512        // fq3_linear: absolute pointers taken from LaunchParams
+  F_ABSPTR = 512,       // fq3_linear: absolute pointers taken from LaunchParams
+  F_SILU = 1024         // out = silu(out) after bias (text_projection fc1, model.py:395-403)
 };
 
 struct __align__(16) Phase {

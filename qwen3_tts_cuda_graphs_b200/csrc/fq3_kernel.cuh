@@ -379,6 +379,7 @@ __device__ __noinline__ void gemv_unit(const Phase& ph, const LaunchParams& p, c
         out += __bfloat162float(bias[out_col]);
       }
       out = bf16r(out);
+      if (ph.flags & F_SILU) out = bf16r(silu_f(out));
     }
     if (ph.flags & F_RESID) out = bf16r(__uint_as_float(resw.x) + out);
     ll_st(reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]) + (size_t)m * p.ld[ph.out_buf] + out_col, out, ep);

@@ -209,6 +209,11 @@ class Engine:
         pol, s = policy.c(), sub.c()
         _lib.check(self.lib.fq3_decode_frames(self.h, int(n_streams), int(n_frames), C.byref(pol), C.byref(s), _stream()))
 
+    def last_hidden(self, row: int = 0) -> torch.Tensor:
+        out = torch.empty(self.cfg.talker.hidden_size, dtype=torch.bfloat16, device=self.device)
+        _lib.check(self.lib.fq3_last_hidden(self.h, int(row), out.data_ptr(), _stream()))
+        return out
+
     def status(self, idx: int = 0) -> _lib.Status:
         st = _lib.Status()
         _lib.check(self.lib.fq3_get_status(self.h, idx, C.byref(st), _stream()))
@@ -223,12 +228,12 @@ class Engine:
         return torch.from_numpy(buf.astype(np.int64))
 
     def linear(self, W: torch.Tensor, x: torch.Tensor, *, gamma=None, eps: float = 1e-6, bias=None, residual=None,
-               swiglu: bool = False, out_f32: bool = False) -> torch.Tensor:
+               swiglu: bool = False, out_f32: bool = False, silu: bool = False) -> torch.Tensor:
         """Parity-test hook: y = epilogue(W @ prologue(x)) through the streaming kernel."""
         M, K = x.shape
         N = W.shape[0]
         flags = (1 if gamma is not None else 0) | (2 if bias is not None else 0) | (4 if residual is not None else 0) | \
-                (8 if swiglu else 0) | (16 if out_f32 else 0)
+                (8 if swiglu else 0) | (16 if out_f32 else 0) | (32 if silu else 0)
         y = torch.empty(M, N // 2 if swiglu else N, dtype=torch.float32 if out_f32 else torch.bfloat16, device=self.device)
         _lib.check(self.lib.fq3_linear(
             self.h, W.data_ptr(), x.data_ptr(), y.data_ptr(), M, N, K, flags, _ptr(gamma), float(eps), _ptr(bias),

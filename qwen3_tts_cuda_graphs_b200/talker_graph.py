@@ -41,6 +41,14 @@ class TalkerGraph:
 
     def prefill_kv(self, past_key_values) -> int:
         """talker_graph.py:153-170: import a prefix KV ([1, kv_heads, T, head_dim] per layer)."""
+        if hasattr(past_key_values, "engine") and hasattr(past_key_values, "length"):
+            # prefix already written in place by the engine's own prefill (base_model.Talker.forward)
+            if past_key_values.length > self.max_seq_len:
+                raise RuntimeError(
+                    f"Input is too long: prefill has {past_key_values.length} tokens but max_seq_len={self.max_seq_len}. "
+                    "Use shorter text or shorter reference audio."
+                )
+            return past_key_values.length
         seq_len = 0
         self.engine.reset_stream(self.stream_idx)
         for li in range(self.num_layers):
