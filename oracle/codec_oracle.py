@@ -100,7 +100,6 @@ class CodecOracle:
 
     def convnext(self, x, p):
         w = self.w
-        h = causal_conv1d(x, w[f"{p}.dwconv.conv.weight"], w[f"{p}.dwconv.conv.bias"])
         h = F.conv1d(F.pad(x, (6, 0)), w[f"{p}.dwconv.conv.weight"], w[f"{p}.dwconv.conv.bias"], groups=x.shape[1])
         h = h.permute(0, 2, 1)
         h = F.layer_norm(h, (h.shape[-1],), w[f"{p}.norm.weight"], w[f"{p}.norm.bias"], 1e-6)
@@ -125,6 +124,11 @@ class CodecOracle:
         x = self.dequant(codes.to(self.device))
         x = causal_conv1d(x, w["pre_conv.conv.weight"], w["pre_conv.conv.bias"])
         x = self.transformer(x.permute(0, 2, 1)).permute(0, 2, 1)
+        return self.upsample_and_vocode(x)
+
+    def upsample_and_vocode(self, x: torch.Tensor) -> torch.Tensor:
+        """[1, hidden, T] -> waveform; sibling Code2Wav.forward after pre_transformer (:3768-3778)."""
+        c, w = self.cfg, self.w
         for i, f in enumerate(c.upsampling_ratios):
             x = causal_trans_conv1d(x, w[f"upsample.{i}.0.conv.weight"], w[f"upsample.{i}.0.conv.bias"], f)
             x = self.convnext(x, f"upsample.{i}.1")

@@ -1,0 +1,436 @@
+"""12 Hz speech-tokenizer DECODER on libfq3codec.so — `speech_tokenizer.decode` of the reference's base model.
+
+The reference calls `m.speech_tokenizer.decode({"audio_codes": codes[1,T,16]}) -> ([wav], sr)` eagerly through
+cuDNN/ATen/cuBLAS (faster_qwen3_tts/model.py:642,782,811,884,971,988,1054,1136,1153; module body in the un-vendored
+`qwen_tts`, architecture per SURVEY.md §8c: split-RVQ dequantiser -> causal conv -> 8-layer sliding-window transformer
+-> 2x(transposed conv + ConvNeXt) -> conv7 -> 4x{SnakeBeta, transposed conv, 3 residual units} -> SnakeBeta -> conv7).
+
+Here the host lowers the decoder for a given frame count T to a flat list of `fq3c_op` records over channels-last
+bf16 activations (include/fq3_codec.h) and hands the list to ONE C call, `fq3c_run`.  Every dense contraction is the
+same tensor-core implicit-GEMM kernel:
+  * causal conv k, dilation d  -> taps k, row offsets -(k-1-j)*d, weights [C_out, k*C_in]
+  * transposed conv k=s (ConvNeXt stage) -> one tap, N = s*C_out, output rows [T, s*C_out] == [T*s, C_out]
+  * transposed conv k=2s, stride s, trimmed s on both sides (vocoder) -> two taps (+1, 0), N = s*C_out, M = T-1
+SnakeBeta is fused into the epilogue of the GEMM that produces its input; bias, GELU, layer-scale and residual adds
+are epilogue flags as well.  Plans (op list + activation buffers) are cached per T, so steady-state streaming
+decode issues no allocation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import shutil
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import build as _build
+from .config import CodecDecoderConfig
+
+K_GEMM, K_RVQ, K_RMSNORM, K_ROPE, K_ATTN, K_DWCONV, K_LAYERNORM, K_SNAKE = range(8)
+F_BIAS, F_GELU, F_RESID, F_SCALE, F_SWIGLU, F_CLAMP, F_OUT_F32, F_SNAKE2 = 1, 2, 4, 8, 16, 32, 64, 128
+
+
+class Op(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("flags", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("taps", C.c_int32), ("cin", C.c_int32), ("a_rows", C.c_int32), ("col_mod", C.c_int32),
+        ("tap_off", C.c_int32 * 8), ("lda", C.c_int32), ("ldc", C.c_int32), ("ldr", C.c_int32),
+        ("i0", C.c_int32), ("i1", C.c_int32), ("i2", C.c_int32), ("f0", C.c_float), ("f1", C.c_float),
+        ("A", C.c_void_p), ("B", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("scale", C.c_void_p),
+        ("p0", C.c_void_p), ("p1", C.c_void_p), ("C", C.c_void_p), ("C2", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+class CodecError(RuntimeError):
+    pass
+
+
+def load_lib():
+    """dlopen libfq3codec.so (built in-tree by build.py).  No fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.lib_path("libfq3codec.so")
+    if (not os.path.exists(path) or _build.is_stale("libfq3codec.so")) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        _build.build_lib("libfq3codec.so")
+    if not os.path.exists(path):
+        raise CodecError(f"{path} is missing: run `python -m qwen3_tts_cuda_graphs_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.fq3c_abi_version.restype = C.c_int
+    lib.fq3c_last_error.restype = C.c_char_p
+    lib.fq3c_run.restype = C.c_int
+    lib.fq3c_run.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p]
+    lib.fq3c_launch_count.restype = C.c_int64
+    if lib.fq3c_abi_version() != 1:
+        raise CodecError("libfq3codec.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic weights (no checkpoint offline): names follow the sibling transformers module tree
+# ------------------------------------------------------------------------------------------------
+def codec_tensor_specs(c: CodecDecoderConfig, pre_conv_kernel: int = 3) -> List[tuple]:
+    H, I, d = c.hidden_size, c.intermediate_size, c.head_dim
+    s: List[tuple] = []
+    for g in range(c.num_quantizers):
+        s.append((f"quantizer.codebook.{g}", (c.codebook_size, c.codebook_dim), "emb"))
+    s += [("quantizer.rvq_first.output_proj.weight", (c.latent_dim, c.codebook_dim), "lin"),
+          ("quantizer.rvq_rest.output_proj.weight", (c.latent_dim, c.codebook_dim), "lin"),
+          ("pre_conv.conv.weight", (H, c.latent_dim, pre_conv_kernel), "conv"), ("pre_conv.conv.bias", (H,), "bias")]
+    for l in range(c.num_hidden_layers):
+        p = f"pre_transformer.layers.{l}"
+        s += [(f"{p}.input_layernorm.weight", (H,), "norm"),
+              (f"{p}.self_attn.q_proj.weight", (c.num_attention_heads * d, H), "lin"),
+              (f"{p}.self_attn.k_proj.weight", (c.num_key_value_heads * d, H), "lin"),
+              (f"{p}.self_attn.v_proj.weight", (c.num_key_value_heads * d, H), "lin"),
+              (f"{p}.self_attn.o_proj.weight", (H, c.num_attention_heads * d), "lin"),
+              (f"{p}.self_attn_layer_scale.scale", (H,), "lscale"),
+              (f"{p}.post_attention_layernorm.weight", (H,), "norm"),
+              (f"{p}.mlp.gate_proj.weight", (I, H), "lin"), (f"{p}.mlp.up_proj.weight", (I, H), "lin"),
+              (f"{p}.mlp.down_proj.weight", (H, I), "lin"), (f"{p}.mlp_layer_scale.scale", (H,), "lscale")]
+    s.append(("pre_transformer.norm.weight", (H,), "norm"))
+    for i, f in enumerate(c.upsampling_ratios):
+        p = f"upsample.{i}"
+        s += [(f"{p}.0.conv.weight", (H, H, f), "tconv"), (f"{p}.0.conv.bias", (H,), "bias"),
+              (f"{p}.1.dwconv.conv.weight", (H, 1, 7), "dw"), (f"{p}.1.dwconv.conv.bias", (H,), "bias"),
+              (f"{p}.1.norm.weight", (H,), "norm"), (f"{p}.1.norm.bias", (H,), "bias"),
+              (f"{p}.1.pwconv1.weight", (4 * H, H), "lin"), (f"{p}.1.pwconv1.bias", (4 * H,), "bias"),
+              (f"{p}.1.pwconv2.weight", (H, 4 * H), "lin"), (f"{p}.1.pwconv2.bias", (H,), "bias"),
+              (f"{p}.1.gamma", (H,), "gamma")]
+    D = c.decoder_dim
+    s += [("decoder.0.conv.weight", (D, H, 7), "conv"), ("decoder.0.conv.bias", (D,), "bias")]
+    for i, r in enumerate(c.upsample_rates):
+        cin, cout = D // 2 ** i, D // 2 ** (i + 1)
+        p = f"decoder.{i + 1}.block"
+        s += [(f"{p}.0.alpha", (cin,), "snake"), (f"{p}.0.beta", (cin,), "snake"),
+              (f"{p}.1.conv.weight", (cin, cout, 2 * r), "tconv"), (f"{p}.1.conv.bias", (cout,), "bias")]
+        for j in range(3):
+            q = f"{p}.{j + 2}"
+            s += [(f"{q}.act1.alpha", (cout,), "snake"), (f"{q}.act1.beta", (cout,), "snake"),
+                  (f"{q}.conv1.conv.weight", (cout, cout, 7), "conv"), (f"{q}.conv1.conv.bias", (cout,), "bias"),
+                  (f"{q}.act2.alpha", (cout,), "snake"), (f"{q}.act2.beta", (cout,), "snake"),
+                  (f"{q}.conv2.conv.weight", (cout, cout, 1), "conv"), (f"{q}.conv2.conv.bias", (cout,), "bias")]
+    n = len(c.upsample_rates) + 1
+    out_dim = D // 2 ** len(c.upsample_rates)
+    s += [(f"decoder.{n}.alpha", (out_dim,), "snake"), (f"decoder.{n}.beta", (out_dim,), "snake"),
+          (f"decoder.{n + 1}.conv.weight", (1, out_dim, 7), "conv"), (f"decoder.{n + 1}.conv.bias", (1,), "bias")]
+    return s
+
+
+def init_codec_synthetic(c: CodecDecoderConfig, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Seeded random init with fan-in scaling (activations stay O(1) through ~60 layers, so the waveform is a
+    non-degenerate signal in [-1, 1] and parity tolerances mean something)."""
+    g = torch.Generator().manual_seed(seed)
+    out: Dict[str, torch.Tensor] = {}
+    for name, shape, kind in codec_tensor_specs(c):
+        if kind == "norm":
+            w = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif kind == "bias":
+            w = 0.02 * torch.randn(shape, generator=g)
+        elif kind == "lscale":
+            w = torch.full(shape, 0.3) + 0.05 * torch.randn(shape, generator=g)
+        elif kind == "gamma":
+            w = torch.full(shape, 0.3) + 0.05 * torch.randn(shape, generator=g)
+        elif kind == "snake":
+            w = 0.3 * torch.randn(shape, generator=g)
+        elif kind == "emb":
+            w = torch.randn(shape, generator=g) / math.sqrt(c.num_quantizers)
+        elif kind == "dw":
+            w = torch.randn(shape, generator=g) / math.sqrt(shape[-1])
+        elif kind == "tconv":  # [cin, cout, k]; each output sample sums k/stride taps of cin channels
+            taps = 1 if shape[2] <= 2 else 2
+            w = torch.randn(shape, generator=g) / math.sqrt(shape[0] * taps)
+        elif kind == "conv":  # [cout, cin, k]
+            w = torch.randn(shape, generator=g) / math.sqrt(shape[1] * shape[2])
+            if name.endswith("conv2.conv.weight"):
+                w = 0.3 * w  # residual branches stay small: the stack neither explodes nor saturates the clamp
+            if shape[0] == 1:
+                w = 0.25 * w  # output conv: waveform rms ~0.3
+        else:  # lin [out, in]
+            w = torch.randn(shape, generator=g) / math.sqrt(shape[-1])
+        # the CUDA path holds matrices in bf16: round here so oracle and engine see identical parameters
+        out[name] = w.to(torch.bfloat16).to(dtype) if kind in ("lin", "conv", "tconv", "emb") else w.to(dtype)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder
+# ------------------------------------------------------------------------------------------------
+class _Plan:
+    def __init__(self):
+        self.ops: List[Op] = []
+        self.keep: List[torch.Tensor] = []
+        self.codes: Optional[torch.Tensor] = None
+        self.wav: Optional[torch.Tensor] = None
+        self.arr = None
+
+
+class CodecDecoder:
+    """Weights repacked for the implicit-GEMM kernels + per-T launch plans."""
+
+    def __init__(self, cfg: CodecDecoderConfig, weights: Dict[str, torch.Tensor], device):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("the fq3 codec decoder runs on CUDA only (no CPU fallback)")
+        self.lib = load_lib()
+        self._plans: Dict[int, _Plan] = {}
+        self.g: Dict[str, torch.Tensor] = {}
+        self._pack(weights)
+
+    # ---- weight packing -------------------------------------------------------------------------
+    def _bf(self, t):
+        return t.to(self.device, torch.bfloat16).contiguous()
+
+    def _f32(self, t):
+        return t.to(self.device, torch.float32).contiguous()
+
+    def _conv_w(self, w):  # [cout, cin, k] -> [cout, k*cin]
+        return self._bf(w.permute(0, 2, 1).reshape(w.shape[0], -1))
+
+    def _pack(self, w):
+        c, g = self.cfg, self.g
+        g["cb"] = self._bf(torch.stack([w[f"quantizer.codebook.{q}"] for q in range(c.num_quantizers)]))
+        g["rvq_proj"] = self._bf(torch.cat([w["quantizer.rvq_first.output_proj.weight"],
+                                            w["quantizer.rvq_rest.output_proj.weight"]], dim=1))
+        g["pre_conv.w"] = self._conv_w(w["pre_conv.conv.weight"])
+        g["pre_conv.b"] = self._f32(w["pre_conv.conv.bias"])
+        for l in range(c.num_hidden_layers):
+            p = f"pre_transformer.layers.{l}"
+            g[f"{p}.ln1"] = self._f32(w[f"{p}.input_layernorm.weight"])
+            g[f"{p}.wqkv"] = self._bf(torch.cat([w[f"{p}.self_attn.q_proj.weight"], w[f"{p}.self_attn.k_proj.weight"],
+                                                 w[f"{p}.self_attn.v_proj.weight"]], 0))
+            g[f"{p}.wo"] = self._bf(w[f"{p}.self_attn.o_proj.weight"])
+            g[f"{p}.ls1"] = self._f32(w[f"{p}.self_attn_layer_scale.scale"])
+            g[f"{p}.ln2"] = self._f32(w[f"{p}.post_attention_layernorm.weight"])
+            gate, up = w[f"{p}.mlp.gate_proj.weight"], w[f"{p}.mlp.up_proj.weight"]
+            g[f"{p}.wgu"] = self._bf(torch.stack([gate, up], dim=1).reshape(2 * gate.shape[0], gate.shape[1]))
+            g[f"{p}.wdown"] = self._bf(w[f"{p}.mlp.down_proj.weight"])
+            g[f"{p}.ls2"] = self._f32(w[f"{p}.mlp_layer_scale.scale"])
+        g["norm"] = self._f32(w["pre_transformer.norm.weight"])
+        for i, f in enumerate(c.upsampling_ratios):
+            p = f"upsample.{i}"
+            tw = w[f"{p}.0.conv.weight"]  # [cin, cout, f] -> rows (phase, cout), cols cin
+            g[f"{p}.t.w"] = self._bf(tw.permute(2, 1, 0).reshape(f * tw.shape[1], tw.shape[0]))
+            g[f"{p}.t.b"] = self._f32(w[f"{p}.0.conv.bias"])
+            g[f"{p}.dw.w"] = self._f32(w[f"{p}.1.dwconv.conv.weight"].reshape(-1, 7))
+            g[f"{p}.dw.b"] = self._f32(w[f"{p}.1.dwconv.conv.bias"])
+            g[f"{p}.ln.w"] = self._f32(w[f"{p}.1.norm.weight"])
+            g[f"{p}.ln.b"] = self._f32(w[f"{p}.1.norm.bias"])
+            g[f"{p}.pw1.w"] = self._bf(w[f"{p}.1.pwconv1.weight"])
+            g[f"{p}.pw1.b"] = self._f32(w[f"{p}.1.pwconv1.bias"])
+            g[f"{p}.pw2.w"] = self._bf(w[f"{p}.1.pwconv2.weight"])
+            g[f"{p}.pw2.b"] = self._f32(w[f"{p}.1.pwconv2.bias"])
+            g[f"{p}.gamma"] = self._f32(w[f"{p}.1.gamma"])
+        g["dec0.w"] = self._conv_w(w["decoder.0.conv.weight"])
+        g["dec0.b"] = self._f32(w["decoder.0.conv.bias"])
+
+        def snake(prefix, name):
+            g[f"{name}.ea"] = self._f32(torch.exp(w[f"{prefix}.alpha"].float()))
+            g[f"{name}.ib"] = self._f32(1.0 / (torch.exp(w[f"{prefix}.beta"].float()) + 1e-9))
+
+        for i, r in enumerate(c.upsample_rates):
+            p = f"decoder.{i + 1}.block"
+            snake(f"{p}.0", f"{p}.0")
+            tw = w[f"{p}.1.conv.weight"]  # [cin, cout, 2r]
+            cin, cout = tw.shape[0], tw.shape[1]
+            a = tw[:, :, :r].permute(2, 1, 0).reshape(r * cout, cin)   # tap 0: x[m+1]
+            b = tw[:, :, r:].permute(2, 1, 0).reshape(r * cout, cin)   # tap 1: x[m]
+            g[f"{p}.1.w"] = self._bf(torch.cat([a, b], dim=1))
+            g[f"{p}.1.b"] = self._f32(w[f"{p}.1.conv.bias"])
+            for j in range(3):
+                q = f"{p}.{j + 2}"
+                snake(f"{q}.act1", f"{q}.act1")
+                snake(f"{q}.act2", f"{q}.act2")
+                g[f"{q}.c1.w"] = self._conv_w(w[f"{q}.conv1.conv.weight"])
+                g[f"{q}.c1.b"] = self._f32(w[f"{q}.conv1.conv.bias"])
+                g[f"{q}.c2.w"] = self._conv_w(w[f"{q}.conv2.conv.weight"])
+                g[f"{q}.c2.b"] = self._f32(w[f"{q}.conv2.conv.bias"])
+        n = len(c.upsample_rates) + 1
+        snake(f"decoder.{n}", "final")
+        g["final.w"] = self._conv_w(w[f"decoder.{n + 1}.conv.weight"])
+        g["final.b"] = self._f32(w[f"decoder.{n + 1}.conv.bias"])
+
+    # ---- plan construction ----------------------------------------------------------------------
+    def _buf(self, plan: _Plan, rows: int, cols: int, dtype=torch.bfloat16) -> torch.Tensor:
+        t = torch.empty(max(rows, 1), cols, dtype=dtype, device=self.device)
+        plan.keep.append(t)
+        return t
+
+    @staticmethod
+    def _p(t: Optional[torch.Tensor]):
+        return None if t is None else t.data_ptr()
+
+    def _gemm(self, plan, A, W, M, N, cin, taps=1, tap_off=(0,), flags=0, bias=None, res=None, scale=None, snake=None,
+              col_mod=None, out=None, out2=None, out_f32=False):
+        o = Op()
+        o.kind, o.flags = K_GEMM, flags | (F_OUT_F32 if out_f32 else 0)
+        o.M, o.N, o.K, o.taps, o.cin = M, N, taps * cin, taps, cin
+        o.a_rows, o.lda = A.shape[0], A.shape[1]
+        o.col_mod = col_mod or N
+        for i, t in enumerate(tap_off):
+            o.tap_off[i] = t
+        width = N // 2 if flags & F_SWIGLU else N
+        if out is None:
+            out = self._buf(plan, M, width, torch.float32 if out_f32 else torch.bfloat16)
+        o.ldc = out.shape[1]
+        o.A, o.B, o.C = A.data_ptr(), W.data_ptr(), out.data_ptr()
+        plan.keep += [t for t in (A, W, bias, res, scale, out) if t is not None]  # ops hold raw pointers
+        if bias is not None:
+            o.flags |= F_BIAS
+            o.bias = bias.data_ptr()
+        if res is not None:
+            o.flags |= F_RESID
+            o.res, o.ldr = res.data_ptr(), res.shape[1]
+        if scale is not None:
+            o.flags |= F_SCALE
+            o.scale = scale.data_ptr()
+        if snake is not None:
+            o.flags |= F_SNAKE2
+            if out2 is None:
+                out2 = self._buf(plan, M, width)
+            o.p0, o.p1, o.C2 = self.g[snake + ".ea"].data_ptr(), self.g[snake + ".ib"].data_ptr(), out2.data_ptr()
+        plan.ops.append(o)
+        return out, out2
+
+    def _simple(self, plan, kind, A, M, N, out=None, **kw):
+        o = Op()
+        o.kind, o.M, o.N = kind, M, N
+        o.A, o.lda, o.a_rows = A.data_ptr(), A.shape[1], A.shape[0]
+        if out is None:
+            out = self._buf(plan, M, N)
+        o.C, o.ldc = out.data_ptr(), out.shape[1]
+        o.col_mod = N
+        for k, v in kw.items():
+            setattr(o, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+        plan.keep += [A, out] + [v for v in kw.values() if isinstance(v, torch.Tensor)]
+        plan.ops.append(o)
+        return out
+
+    def _build(self, T: int) -> _Plan:
+        c, g = self.cfg, self.g
+        plan = _Plan()
+        H, d, nh, nkv = c.hidden_size, c.head_dim, c.num_attention_heads, c.num_key_value_heads
+        plan.codes = torch.zeros(T, c.num_quantizers, dtype=torch.int64, device=self.device)
+        # 1. split-RVQ dequantiser: gather+sum, then both output projections as one GEMM over [first | rest]
+        q = self._simple(plan, K_RVQ, plan.codes, T, 2 * c.codebook_dim, B=g["cb"], K=c.codebook_size,
+                         i0=c.num_semantic_quantizers, i1=c.num_quantizers, i2=c.codebook_dim)
+        plan.ops[-1].lda = c.num_quantizers
+        x, _ = self._gemm(plan, q, g["rvq_proj"], T, c.latent_dim, 2 * c.codebook_dim)
+        # 2. causal pre-conv
+        k = g["pre_conv.w"].shape[1] // c.latent_dim
+        x, _ = self._gemm(plan, x, g["pre_conv.w"], T, H, c.latent_dim, taps=k, tap_off=[j - (k - 1) for j in range(k)],
+                          bias=g["pre_conv.b"])
+        # 3. sliding-window transformer
+        qkv_dim = (nh + 2 * nkv) * d
+        for l in range(c.num_hidden_layers):
+            p = f"pre_transformer.layers.{l}"
+            h = self._simple(plan, K_RMSNORM, x, T, H, scale=g[f"{p}.ln1"], f0=c.rms_norm_eps)
+            qkv, _ = self._gemm(plan, h, g[f"{p}.wqkv"], T, qkv_dim, H)
+            self._simple(plan, K_ROPE, qkv, T, qkv_dim, out=qkv, i0=nh + nkv, i1=d, i2=0, f0=c.rope_theta)
+            a = self._simple(plan, K_ATTN, qkv, T, nh * d, i0=nh, i1=nkv, i2=d, K=c.sliding_window)
+            x, _ = self._gemm(plan, a, g[f"{p}.wo"], T, H, nh * d, scale=g[f"{p}.ls1"], res=x)
+            h = self._simple(plan, K_RMSNORM, x, T, H, scale=g[f"{p}.ln2"], f0=c.rms_norm_eps)
+            m, _ = self._gemm(plan, h, g[f"{p}.wgu"], T, 2 * c.intermediate_size, H, flags=F_SWIGLU)
+            x, _ = self._gemm(plan, m, g[f"{p}.wdown"], T, H, c.intermediate_size, scale=g[f"{p}.ls2"], res=x)
+        x = self._simple(plan, K_RMSNORM, x, T, H, scale=g["norm"], f0=c.rms_norm_eps)
+        # 4. ConvNeXt upsampling stages
+        rows = T
+        for i, f in enumerate(c.upsampling_ratios):
+            p = f"upsample.{i}"
+            y, _ = self._gemm(plan, x, g[f"{p}.t.w"], rows, f * H, H, bias=g[f"{p}.t.b"], col_mod=H)
+            rows *= f
+            x = y.view(rows, H)
+            h = self._simple(plan, K_DWCONV, x, rows, H, B=g[f"{p}.dw.w"], bias=g[f"{p}.dw.b"], taps=7)
+            h = self._simple(plan, K_LAYERNORM, h, rows, H, scale=g[f"{p}.ln.w"], bias=g[f"{p}.ln.b"], f0=1e-6)
+            h, _ = self._gemm(plan, h, g[f"{p}.pw1.w"], rows, 4 * H, H, bias=g[f"{p}.pw1.b"], flags=F_GELU)
+            x, _ = self._gemm(plan, h, g[f"{p}.pw2.w"], rows, H, 4 * H, bias=g[f"{p}.pw2.b"], scale=g[f"{p}.gamma"], res=x)
+        # 5. vocoder
+        D = c.decoder_dim
+        _, xs = self._gemm(plan, x, g["dec0.w"], rows, D, H, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["dec0.b"],
+                           snake="decoder.1.block.0")
+        nblk = len(c.upsample_rates)
+        for i, r in enumerate(c.upsample_rates):
+            cin, cout = D // 2 ** i, D // 2 ** (i + 1)
+            p = f"decoder.{i + 1}.block"
+            m_out = rows - 1
+            y, ys = self._gemm(plan, xs, g[f"{p}.1.w"], m_out, r * cout, cin, taps=2, tap_off=[1, 0], bias=g[f"{p}.1.b"],
+                               col_mod=cout, snake=f"{p}.2.act1")
+            rows = m_out * r
+            x, xs = y.view(-1, cout)[:max(rows, 1)], ys.view(-1, cout)[:max(rows, 1)]
+            for j, dil in enumerate((1, 3, 9)):
+                q_ = f"{p}.{j + 2}"
+                _, hs = self._gemm(plan, xs, g[f"{q_}.c1.w"], rows, cout, cout, taps=7, tap_off=[(t - 6) * dil for t in range(7)],
+                                   bias=g[f"{q_}.c1.b"], snake=f"{q_}.act2")
+                nxt = f"{p}.{j + 3}.act1" if j < 2 else (f"decoder.{i + 2}.block.0" if i + 1 < nblk else "final")
+                x, xs = self._gemm(plan, hs, g[f"{q_}.c2.w"], rows, cout, cout, bias=g[f"{q_}.c2.b"], res=x, snake=nxt)
+        out_dim = D // 2 ** nblk
+        plan.wav = torch.empty(max(rows, 1), 1, dtype=torch.float32, device=self.device)
+        self._gemm(plan, xs, g["final.w"], rows, 1, out_dim, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["final.b"],
+                   flags=F_CLAMP, out=plan.wav, out_f32=True)
+        plan.n_samples = rows
+        plan.arr = (Op * len(plan.ops))(*plan.ops)
+        return plan
+
+    def run_plan(self, plan: _Plan):
+        """Launch a plan's op list on the current stream (also the hook the per-op parity tests use)."""
+        if plan.arr is None:
+            plan.arr = (Op * len(plan.ops))(*plan.ops)
+        rc = self.lib.fq3c_run(plan.arr, len(plan.ops), torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise CodecError(self.lib.fq3c_last_error().decode())
+
+    def n_samples(self, T: int) -> int:
+        rows = T
+        for f in self.cfg.upsampling_ratios:
+            rows *= f
+        for r in self.cfg.upsample_rates:
+            rows = (rows - 1) * r
+        return max(rows, 0)
+
+    # ---- run ------------------------------------------------------------------------------------
+    @torch.inference_mode()
+    def decode(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes int64 [T, Q] (any device) -> float32 waveform [n_samples] on the decoder's device."""
+        T = int(codes.shape[0])
+        if T == 0 or self.n_samples(T) <= 0:
+            return torch.zeros(0, dtype=torch.float32, device=self.device)
+        plan = self._plans.get(T)
+        if plan is None:
+            # streaming revisits a handful of sizes (chunk multiples, then chunk+25); long one-shot decodes are
+            # not worth pinning gigabytes of activation buffers for
+            for k in [k for k in self._plans if k > 96 or len(self._plans) >= 24]:
+                self._plans.pop(k)
+            plan = self._plans[T] = self._build(T)
+        plan.codes.copy_(codes.to(torch.int64), non_blocking=True)
+        self.run_plan(plan)
+        return plan.wav.view(-1)[: plan.n_samples].clone()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.fq3c_launch_count())
+
+
+class SpeechTokenizer:
+    """`model.speech_tokenizer` surface the reference uses: `.decode({"audio_codes": [B,T,Q]}) -> ([wav], sr)` and
+    `.sample_rate` (model.py:56-58, :642)."""
+
+    def __init__(self, decoder: CodecDecoder):
+        self.decoder = decoder
+        self.sample_rate = decoder.cfg.sample_rate
+
+    @classmethod
+    def synthetic(cls, cfg: CodecDecoderConfig, device, seed: int = 1):
+        return cls(CodecDecoder(cfg, init_codec_synthetic(cfg, seed=seed), device))
+
+    def decode(self, inputs) -> Tuple[List[torch.Tensor], int]:
+        codes = inputs["audio_codes"] if isinstance(inputs, dict) else inputs
+        if codes.dim() == 2:
+            codes = codes.unsqueeze(0)
+        return [self.decoder.decode(codes[b]) for b in range(codes.shape[0])], self.sample_rate

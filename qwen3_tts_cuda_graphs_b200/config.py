@@ -191,7 +191,7 @@ def preset(name: str) -> TTSConfig:
         )
         codec = CodecDecoderConfig(
             codebook_dim=32, latent_dim=64, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
-            num_attention_heads=4, num_key_value_heads=4, head_dim=16, sliding_window=8, decoder_dim=64,
+            num_attention_heads=4, num_key_value_heads=4, head_dim=16, sliding_window=8, decoder_dim=128,
         )
         return TTSConfig(
             talker=talker, predictor=pred, codec=codec, tts_model_type=kind if kind != "" else "base",

@@ -259,9 +259,10 @@ class FasterQwen3TTS:
             logger.info(f"Generated {n / 12.5:.2f}s audio in {total:.2f}s ({timing['ms_per_step']:.1f}ms/step, "
                         f"RTF: {n * 0.08 / total:.2f})")
 
-    def _stream_audio(self, m, stream, ref_codes, chunk_size):
+    def _stream_audio(self, m, stream, ref_codes, chunk_size, to_host: bool = True):
         """Hybrid streaming decode policy of model.py:737-826 (accumulate until 25 frames, then a 25-frame
-        left-context sliding window)."""
+        left-context sliding window).  to_host=False keeps each chunk as a device tensor (bench.py's
+        device-resident leg); the public generators always yield host numpy like the reference."""
         context_frames = 25
         min_cal = max(context_frames, chunk_size)
         all_codes, prev_len, spf = [], 0, None
@@ -274,7 +275,7 @@ class FasterQwen3TTS:
             if spf is None:
                 codes_in = flat if ref_codes is None else torch.cat([ref_codes.to(flat.device), flat], dim=0)
                 audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0)})
-                audio = self._to_numpy(audio_list[0])
+                audio = audio_list[0].flatten()
                 if ref_codes is not None:
                     audio = audio[int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * len(audio)):]
                 new_audio = audio[prev_len:]
@@ -286,9 +287,9 @@ class FasterQwen3TTS:
                 window = flat[start:]
                 n_ctx = window.shape[0] - n_new
                 audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0)})
-                audio = self._to_numpy(audio_list[0])
+                audio = audio_list[0].flatten()
                 new_audio = audio[int(round(n_ctx * spf)):] if n_ctx > 0 else audio
-            yield new_audio, sr, timing
+            yield (self._to_numpy(new_audio) if to_host else new_audio), sr, timing
 
     def _gen_kwargs(self, max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty):
         return dict(max_new_tokens=max_new_tokens, min_new_tokens=min_new_tokens, temperature=temperature, top_k=top_k,

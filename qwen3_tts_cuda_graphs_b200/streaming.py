@@ -35,6 +35,7 @@ def fast_generate_streaming(
     repetition_penalty: float = 1.05,
     chunk_size: int = 12,
     seed: Optional[int] = None,
+    launch_events: Optional[list] = None,
 ) -> Generator[Tuple[torch.Tensor, dict], None, None]:
     dev = talker_input_embeds.device
     if is_fused(talker, predictor_graph, talker_graph):
@@ -53,7 +54,13 @@ def fast_generate_streaming(
         emitted, chunk_idx = 0, 0
         while emitted < budget:
             t1 = time.time()
+            if launch_events is not None:  # bench.py: CUDA-event bracket of the persistent-kernel launch alone
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             eng.decode_frames(1, min(chunk_size, budget - emitted), policy, sub)
+            if launch_events is not None:
+                e1.record()
+                launch_events.append((e0, e1, min(chunk_size, budget - emitted)))
             st = eng.status(idx)
             dt = time.time() - t1
             n_new = st.n_frames - emitted

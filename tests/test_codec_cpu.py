@@ -1,0 +1,126 @@
+"""Pins the codec-decoder oracle (test infrastructure) against the sibling transformers modules run live.
+
+The 12 Hz decoder lives in the un-vendored `qwen_tts`; the in-container sibling is transformers'
+Qwen3OmniMoeCode2Wav.  The oracle's transformer and its upsample+vocoder stack must reproduce the
+sibling module on the sibling's own random weights; the split-RVQ dequantiser has no sibling and is checked against
+a direct restatement.
+"""
+import pytest
+import torch
+
+from qwen3_tts_cuda_graphs_b200.codec import codec_tensor_specs, init_codec_synthetic
+from qwen3_tts_cuda_graphs_b200.config import preset
+
+
+def _sibling(cfg):
+    mod = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    conf = pytest.importorskip("transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe")
+    c = conf.Qwen3OmniMoeCode2WavConfig(
+        codebook_size=cfg.codebook_size, hidden_size=cfg.hidden_size, max_position_embeddings=8000,
+        rope_theta=cfg.rope_theta, num_attention_heads=cfg.num_attention_heads,
+        num_key_value_heads=cfg.num_key_value_heads, attention_bias=False, sliding_window=cfg.sliding_window,
+        intermediate_size=cfg.intermediate_size, hidden_act="silu", layer_scale_initial_scale=0.3,
+        rms_norm_eps=cfg.rms_norm_eps, num_hidden_layers=cfg.num_hidden_layers, num_quantizers=cfg.num_quantizers,
+        upsample_rates=list(cfg.upsample_rates), upsampling_ratios=list(cfg.upsampling_ratios),
+        decoder_dim=cfg.decoder_dim, attention_dropout=0.0,
+    )
+    c._attn_implementation = "eager"
+    torch.manual_seed(0)
+    m = mod.Qwen3OmniMoeCode2Wav(c).eval()
+    # default init leaves SnakeBeta / layer-scale / gamma at constants: randomise so every term is exercised
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("alpha") or n.endswith("beta"):
+                p.copy_(0.3 * torch.randn_like(p))
+            elif n.endswith("gamma") or n.endswith("scale"):
+                p.copy_(0.3 + 0.05 * torch.randn_like(p))
+            elif "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn_like(p))
+            elif n.endswith("bias"):
+                p.copy_(0.02 * torch.randn_like(p))
+    return m
+
+
+def _oracle_from_sibling(cfg, m):
+    from oracle.codec_oracle import CodecOracle
+
+    sd = m.state_dict()
+    w = init_codec_synthetic(cfg, seed=5)  # quantizer / pre_conv entries (no sibling counterpart)
+    for name, shape, _ in codec_tensor_specs(cfg):
+        if name.startswith("quantizer.") or name.startswith("pre_conv."):
+            continue
+        assert name in sd, name
+        assert tuple(sd[name].shape) == tuple(shape), (name, tuple(sd[name].shape), shape)
+        w[name] = sd[name].clone().float()
+    return CodecOracle(cfg, w)
+
+
+@pytest.fixture(scope="module")
+def pair():
+    cfg = preset("tiny").codec
+    m = _sibling(cfg)
+    return cfg, m, _oracle_from_sibling(cfg, m)
+
+
+def test_head_dim_matches_sibling(pair):
+    cfg, m, _ = pair
+    assert m.pre_transformer.layers[0].self_attn.head_dim == cfg.head_dim
+
+
+@pytest.mark.parametrize("T", [1, 5, 19])
+def test_transformer_equals_sibling(pair, T):
+    cfg, m, orc = pair
+    x = torch.randn(1, T, cfg.hidden_size, generator=torch.Generator().manual_seed(T))
+    with torch.no_grad():
+        ref = m.pre_transformer(inputs_embeds=x).last_hidden_state
+        got = orc.transformer(x)
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4), float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize("T", [1, 2, 9])
+def test_upsample_and_vocoder_equal_sibling(pair, T):
+    cfg, m, orc = pair
+    h = torch.randn(1, cfg.hidden_size, T, generator=torch.Generator().manual_seed(10 + T))
+    with torch.no_grad():
+        x = h
+        for blocks in m.upsample:
+            for b in blocks:
+                x = b(x)
+        for b in m.decoder:
+            x = b(x)
+        ref = x.clamp(min=-1, max=1).reshape(-1)
+        got = orc.upsample_and_vocode(h)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-4), float((got - ref).abs().max())
+    # length law of the trimmed transposed convolutions (1920*T - 555 for the full-size rates)
+    n = T
+    for f in cfg.upsampling_ratios:
+        n *= f
+    for r in cfg.upsample_rates:
+        n = (n - 1) * r
+    assert got.numel() == n
+
+
+def test_dequantiser_restatement(pair):
+    cfg, _, orc = pair
+    g = torch.Generator().manual_seed(3)
+    codes = torch.randint(0, cfg.codebook_size, (7, cfg.num_quantizers), generator=g)
+    got = orc.dequant(codes)[0].t()
+    w = orc.w
+    ref = torch.zeros(7, cfg.latent_dim)
+    for t in range(7):
+        first = sum(w[f"quantizer.codebook.{q}"][codes[t, q]] for q in range(cfg.num_semantic_quantizers))
+        rest = sum(w[f"quantizer.codebook.{q}"][codes[t, q]] for q in range(cfg.num_semantic_quantizers, cfg.num_quantizers))
+        ref[t] = w["quantizer.rvq_first.output_proj.weight"] @ first + w["quantizer.rvq_rest.output_proj.weight"] @ rest
+    assert torch.allclose(got, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_full_decode_is_causal_and_bounded(pair):
+    """Streaming relies on causality: the first frames' samples do not change when later frames are appended."""
+    cfg, _, orc = pair
+    g = torch.Generator().manual_seed(4)
+    codes = torch.randint(0, cfg.codebook_size, (6, cfg.num_quantizers), generator=g)
+    a = orc.decode(codes[:4])
+    b = orc.decode(codes)
+    assert float(b.abs().max()) <= 1.0
+    assert torch.allclose(a, b[: a.numel()], atol=1e-5)
