@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round evidence run: all GPU parity tests, smoke, bench (both arms), ncu launch list + one full capture.
+# usage: scripts/evidence.sh <tag>
+tag=${1:-r01}
+mkdir -p gpurun_out
+export FQ3_WATCHDOG_MS=${FQ3_WATCHDOG_MS:-3000}
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu_${tag}.txt 2>&1
+timeout 1500 python -m pytest tests -q -m gpu --tb=short 2>&1 | tail -40 > gpurun_out/tests_gpu_${tag}.log
+echo "tests rc=$?" >> gpurun_out/tests_gpu_${tag}.log
+tail -3 gpurun_out/tests_gpu_${tag}.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${tag}.log 2>&1; tail -1 gpurun_out/smoke_${tag}.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_${tag}.log 2>gpurun_out/bench_${tag}.err; tail -1 gpurun_out/bench_${tag}.log | cut -c1-600
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${tag}.log 2>&1; tail -1 gpurun_out/bench_ref_${tag}.log | cut -c1-400
+if [ "$2" != "nonu" ]; then
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_${tag}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fq3_stream -s 6 -c 1 -o gpurun_out/prof_frames_${tag} python scripts/prof_frames.py > gpurun_out/ncu_full_${tag}.log 2>&1
+tail -2 gpurun_out/ncu_full_${tag}.log
+fi
