@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "../../include/fq3.h"
@@ -52,8 +53,8 @@ struct fq3_engine {
   StackRt rt[2]{};
   StreamState* d_st = nullptr;
   std::vector<StreamState> h_st;
-  float* attn_part = nullptr;
-  unsigned* attn_cnt = nullptr;
+  LLWord* attn_part = nullptr;
+  size_t attn_part_bytes = 0;
   int* err_host = nullptr;
   int* err_dev = nullptr;
   float* pred_logits_all = nullptr;
@@ -62,7 +63,9 @@ struct fq3_engine {
   int n_frames_ph = 0, n_pred_ph = 0, n_talker_ph = 0, n_prefill_ph = 0;
   int64_t launches = 0;
   long long* prof = nullptr;
-  int max_stages = 6;     // 6 x 16 KB in flight per SM saturates HBM (bench_micro/stream_bw.cu); the rest stays L1
+  std::vector<Plan> plans;                 // GEMV partitions, one per distinct (N, K, SwiGLU)
+  std::vector<std::array<int, 3>> plan_keys;
+  long ring_cap = 0;      // optional cap on the weight ring (FQ3_RING_KB), 0 = all remaining shared memory
   int prof_cta = -1;
   uint32_t epoch = 1;     // LL epoch counter (monotonic across launches)
   int lin_words = 0;      // capacity (words per row) of the fq3_linear staging buffers
@@ -84,8 +87,40 @@ int dalloc(fq3_engine* e, T** p, size_t n, bool zero = true) {
 
 uint32_t off16(uint64_t byte_off) { return (uint32_t)(byte_off >> 4); }
 
+// Partition of one GEMV shape over the grid (fq3_common.cuh: Plan): super-units = packed output words.
+bool make_plan(int G, int N, int K, bool swiglu, Plan* out) {
+  if (N < 2 || (N & 1) || K < 64 || (K & 63)) return false;
+  if (swiglu && (N & 3)) return false;
+  Plan pl{};
+  pl.ro = swiglu ? 4 : 2;
+  const int n_su = N / pl.ro;
+  pl.su_base = n_su / G;
+  pl.su_rem = n_su - pl.su_base * G;
+  pl.nkq = (K + kStageCols - 1) / kStageCols;
+  pl.tpb = std::max(1, kBatchStages / pl.nkq);
+  if (pl.nkq > kBatchStages) return false;
+  *out = pl;
+  return true;
+}
+int plan_for(fq3_engine* e, int N, int K, bool swiglu) {
+  const std::array<int, 3> key{N, K, swiglu ? 1 : 0};
+  for (size_t i = 0; i < e->plan_keys.size(); ++i)
+    if (e->plan_keys[i] == key) return (int)i;
+  Plan pl{};
+  if (!make_plan(e->G, N, K, swiglu, &pl) || (int)e->plans.size() >= kMaxPlans - 1) return -1;
+  e->plans.push_back(pl);
+  e->plan_keys.push_back(key);
+  return (int)e->plans.size() - 1;
+}
+static bool g_plan_fail = false;
+uint8_t plan_id(fq3_engine* e, int N, int K, bool swiglu) {
+  const int id = plan_for(e, N, K, swiglu);
+  if (id < 0) { g_plan_fail = true; return 0; }
+  return (uint8_t)id;
+}
+
 // One decoder layer = 5 phases.
-void push_layer(std::vector<Phase>& v, const StackHost& s, uint8_t stack, int layer, bool rows2, uint8_t aux,
+void push_layer(fq3_engine* e, std::vector<Phase>& v, const StackHost& s, uint8_t stack, int layer, bool rows2, uint8_t aux,
                 bool keep) {
   const uint64_t* o = &s.offs[(size_t)layer * 8];
   const uint16_t r2 = rows2 ? F_ROWS2 : 0, kp = keep ? F_L2_KEEP : 0;
@@ -96,26 +131,30 @@ void push_layer(std::vector<Phase>& v, const StackHost& s, uint8_t stack, int la
   // 1. RMSNorm + fused QKV projection
   p.type = PH_GEMV; p.flags = F_PRENORM | r2 | kp; p.in_buf = X; p.out_buf = Q; p.res_buf = 0;
   p.w_off = off16(o[1]); p.g_off = off16(o[0]); p.b_off = 0; p.N = s.qkvdim(); p.K = s.d.hidden;
+  p.plan = plan_id(e, p.N, p.K, false);
   v.push_back(p);
   // 2. q/k norm + RoPE + KV append + attention
   p.type = PH_ATTN; p.flags = r2; p.in_buf = Q; p.out_buf = A; p.w_off = 0; p.g_off = off16(o[2]); p.b_off = off16(o[3]);
-  p.N = 0; p.K = 0;
+  p.N = 0; p.K = 0; p.plan = 0;
   v.push_back(p);
   // 3. o_proj + residual
   p.type = PH_GEMV; p.flags = F_RESID | r2 | kp; p.in_buf = A; p.out_buf = X; p.res_buf = X;
   p.w_off = off16(o[4]); p.g_off = 0; p.b_off = 0; p.N = s.d.hidden; p.K = s.qdim();
+  p.plan = plan_id(e, p.N, p.K, false);
   v.push_back(p);
   // 4. RMSNorm + gate/up + SiLU*mul
   p.flags = F_PRENORM | F_SWIGLU | r2 | kp; p.in_buf = X; p.out_buf = C; p.res_buf = 0;
   p.w_off = off16(o[6]); p.g_off = off16(o[5]); p.N = 2 * s.d.inter; p.K = s.d.hidden;
+  p.plan = plan_id(e, p.N, p.K, true);
   v.push_back(p);
   // 5. down_proj + residual
   p.flags = F_RESID | r2 | kp; p.in_buf = C; p.out_buf = X; p.res_buf = X;
   p.w_off = off16(o[7]); p.g_off = 0; p.N = s.d.hidden; p.K = s.d.inter;
+  p.plan = plan_id(e, p.N, p.K, false);
   v.push_back(p);
 }
 
-void push_predictor(std::vector<Phase>& v, const fq3_engine* e, bool only) {
+void push_predictor(std::vector<Phase>& v, fq3_engine* e, bool only) {
   for (int i = 0; i < e->ncb; ++i) {
     const bool r2 = (i == 0);
     if (e->desc.has_s2m) {
@@ -123,14 +162,16 @@ void push_predictor(std::vector<Phase>& v, const fq3_engine* e, bool only) {
       p.type = PH_GEMV; p.stack = ST_PRED; p.aux = (uint8_t)i; p.flags = F_BIAS | F_L2_KEEP | (r2 ? F_ROWS2 : 0);
       p.in_buf = BUF_PIN; p.out_buf = BUF_PX; p.w_off = off16(e->desc.s2m_w_off); p.b_off = off16(e->desc.s2m_b_off);
       p.N = e->pr.d.hidden; p.K = e->tk.d.hidden;
+      p.plan = plan_id(e, p.N, p.K, false);
       v.push_back(p);
     }
-    for (int l = 0; l < e->pr.d.n_layers; ++l) push_layer(v, e->pr, ST_PRED, l, r2, (uint8_t)i, true);
+    for (int l = 0; l < e->pr.d.n_layers; ++l) push_layer(e, v, e->pr, ST_PRED, l, r2, (uint8_t)i, true);
     Phase h{};
     h.type = PH_GEMV; h.stack = ST_PRED; h.aux = (uint8_t)i;
     h.flags = F_PRENORM | F_OUT_F32 | F_L2_KEEP | (r2 ? F_ROWS2 : 0);
     h.in_buf = BUF_PX; h.out_buf = BUF_LOGITS; h.w_off = off16(e->lm_head_offs[i]);
     h.g_off = off16(e->pr.d.final_norm_off); h.N = e->pr.d.vocab; h.K = e->pr.d.hidden;
+    h.plan = plan_id(e, h.N, h.K, false);
     v.push_back(h);
     Phase s{};
     s.type = PH_SAMPLE; s.stack = ST_PRED; s.aux = (uint8_t)i; s.kind = only ? SMP_PRED_ONLY : SMP_PRED;
@@ -139,13 +180,14 @@ void push_predictor(std::vector<Phase>& v, const fq3_engine* e, bool only) {
   }
 }
 
-void push_talker(std::vector<Phase>& v, const fq3_engine* e, bool last_row_head) {
-  for (int l = 0; l < e->tk.d.n_layers; ++l) push_layer(v, e->tk, ST_TALKER, l, false, 0, false);
+void push_talker(std::vector<Phase>& v, fq3_engine* e, bool last_row_head) {
+  for (int l = 0; l < e->tk.d.n_layers; ++l) push_layer(e, v, e->tk, ST_TALKER, l, false, 0, false);
   Phase h{};
   h.type = PH_GEMV; h.stack = ST_TALKER;
   h.flags = F_PRENORM | F_OUT_F32 | F_WRITE_NORMED | (last_row_head ? F_LAST_ROW : 0);
   h.in_buf = BUF_TX; h.out_buf = BUF_LOGITS; h.w_off = off16(e->desc.codec_head_off);
   h.g_off = off16(e->tk.d.final_norm_off); h.N = e->tk.d.vocab; h.K = e->tk.d.hidden;
+  h.plan = plan_id(e, h.N, h.K, false);
   v.push_back(h);
 }
 
@@ -162,7 +204,7 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   p.stacks[1] = e->rt[1];
   p.st = e->d_st;
   p.attn_part = e->attn_part;
-  p.attn_cnt = e->attn_cnt;
+  for (size_t i = 0; i < e->plans.size(); ++i) p.plans[i] = e->plans[i];
   p.err = e->err_dev;
   p.n_code_groups = e->desc.n_code_groups;
   p.eos_id = e->desc.eos_id;
@@ -192,16 +234,16 @@ int check_device_fault(fq3_engine* e) {
   return 0;
 }
 
-// Launch the persistent kernel: one CTA per SM, cooperative (all CTAs co-resident, the grid barrier needs it).
-int launch(fq3_engine* e, LaunchParams& p, int xrows, int kmax, cudaStream_t s) {
+// Launch the persistent kernel: one CTA per SM, cooperative (all CTAs must be co-resident: they poll each other's words).
+// smem: header | scratch | activation staging buffer (xrows x kmax bf16) | weight ring (16 KB stages, everything that is left).
+int launch(fq3_engine* e, LaunchParams& p, size_t x_elems, cudaStream_t s) {
   if (int r = check_device_fault(e)) return r;
-  p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 128);
-  p.xbuf_bytes = (int)round_up((size_t)xrows * kmax * 2, 128);
-  p.stage_bytes = kStageBytesDefault;
-  const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - p.prog_bytes - p.xbuf_bytes;
-  p.n_stages = (int)std::min<long>(e->max_stages, avail / p.stage_bytes);
-  if (p.n_stages < 2) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
-  const size_t smem = kHeaderBytes + kScratchBytes + p.prog_bytes + p.xbuf_bytes + (size_t)p.n_stages * p.stage_bytes;
+  p.xbuf_bytes = (int)round_up(x_elems * 2, 1024);
+  long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - (long)p.xbuf_bytes;
+  if (e->ring_cap > 0) avail = std::min(avail, e->ring_cap);
+  p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
+  if (p.n_stages < 4) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
+  const size_t smem = kHeaderBytes + kScratchBytes + (size_t)p.xbuf_bytes + (size_t)p.n_stages * kStageBytes;
   // LL epochs: phase i of iteration it carries epoch_base + it*n_phases + i + 1
   const uint64_t span = (uint64_t)p.n_iters * (uint64_t)p.n_phases + 2;
   if ((uint64_t)e->epoch + span >= 0xFFFFFF00ull) {
@@ -209,12 +251,13 @@ int launch(fq3_engine* e, LaunchParams& p, int xrows, int kmax, cudaStream_t s) 
     CK(cudaStreamSynchronize(s));
     for (int i = 0; i < kNumBufs; ++i)
       if (e->buf_bytes[i]) CK(cudaMemsetAsync(e->bufs[i], 0, e->buf_bytes[i], s));
+    CK(cudaMemsetAsync(e->attn_part, 0, e->attn_part_bytes, s));
     e->epoch = 1;
   }
   p.epoch_base = e->epoch;
   e->epoch += (uint32_t)span;
   void* args[] = {&p};
-  CK(cudaLaunchCooperativeKernel((void*)fq3_stream_kernel, dim3(e->G), dim3(kThreads), args, smem, s));
+  CK(cudaLaunchCooperativeKernel(p.prof ? (void*)fq3_stream_kernel<true> : (void*)fq3_stream_kernel<false>, dim3(e->G), dim3(kThreads), args, smem, s));
   e->launches += 1;
   return 0;
 }
@@ -263,11 +306,11 @@ SubPolicy to_sub(const fq3_subpolicy* q) {
 
 int check_stack(const fq3_stack_desc& d, const char* name) {
   if (d.head_dim != kHeadDim) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": head_dim must be 128");
-  if (d.hidden % 8 || d.inter % 8) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": dims must be multiples of 8");
+  if (d.hidden % 64 || d.inter % 64) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": dims must be multiples of 64");
   if (d.n_q_heads % d.n_kv_heads) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": nq % nkv != 0");
+  if (d.n_q_heads / d.n_kv_heads > kGq) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": more than 2 q heads per kv head");
   if (d.vocab > kMaxVocab) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": vocab exceeds sampling scratch");
-  const int kmax = std::max(std::max(d.hidden, d.inter), d.n_q_heads * d.head_dim);
-  if (kmax * 2 > kStageBytesDefault) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": a weight row exceeds one ring stage");
+  if (d.vocab % 4) return fail(FQ3_E_UNSUPPORTED, std::string(name) + ": vocab must be a multiple of 4");
   return 0;
 }
 
@@ -297,16 +340,17 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   if (!coop) return fail(FQ3_E_UNSUPPORTED, "device lacks cooperative launch");
   e->G = sms;
   if (const char* g = getenv("FQ3_GRID")) e->G = std::max(1, std::min(sms, atoi(g)));
-  if (const char* ms = getenv("FQ3_STAGES")) e->max_stages = std::max(2, std::min((int)kMaxStages, atoi(ms)));
+  if (const char* rk = getenv("FQ3_RING_KB")) e->ring_cap = std::max(16L, atol(rk)) * 1024L;
   if (const char* pc = getenv("FQ3_PROF")) {
     e->prof_cta = atoi(pc);
-    if (dalloc(e, &e->prof, 1024 * 8)) return -FQ3_E_CUDA;
+    if (dalloc(e, &e->prof, 512 * 16)) return -FQ3_E_CUDA;
   }
   if (const char* w = getenv("FQ3_WATCHDOG_MS")) e->watchdog_ns = (unsigned long long)atoll(w) * 1000000ull;
   e->smem_max = (size_t)smem_optin;
-  CK(cudaFuncSetAttribute(fq3_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  CK(cudaFuncSetAttribute(fq3_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  CK(cudaFuncSetAttribute(fq3_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fq3_stream_kernel, kThreads, smem_optin));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fq3_stream_kernel<false>, kThreads, smem_optin));
   if (occ < 1) return fail(FQ3_E_UNSUPPORTED, "stream kernel does not fit on an SM");
 
   e->ncb = desc->n_code_groups - 1;
@@ -346,15 +390,15 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
     return 0;
   };
   const int Ht = e->tk.d.hidden, Hp = e->pr.d.hidden;
-  const size_t LL = sizeof(LLWord);
-  if (mk(BUF_TX, Ht, LL, R) || mk(BUF_TQKV, e->tk.qkvdim(), LL, R) || mk(BUF_TATT, e->tk.qdim(), LL, R) ||
-      mk(BUF_TACT, e->tk.d.inter, LL, R) || mk(BUF_PX, Hp, LL, R) || mk(BUF_PQKV, e->pr.qkvdim(), LL, R) ||
-      mk(BUF_PATT, e->pr.qdim(), LL, R) || mk(BUF_PACT, e->pr.d.inter, LL, R) ||
-      mk(BUF_LOGITS, std::max(e->tk.d.vocab, e->pr.d.vocab), LL, R) || mk(BUF_HID, Ht, 2, R))
+  const size_t LL = sizeof(LLWord);  // LL buffers: width in packed words (two bf16 per word)
+  if (mk(BUF_TX, Ht / 2, LL, R) || mk(BUF_TQKV, e->tk.qkvdim() / 2, LL, R) || mk(BUF_TATT, e->tk.qdim() / 2, LL, R) ||
+      mk(BUF_TACT, e->tk.d.inter / 2, LL, R) || mk(BUF_PX, Hp / 2, LL, R) || mk(BUF_PQKV, e->pr.qkvdim() / 2, LL, R) ||
+      mk(BUF_PATT, e->pr.qdim() / 2, LL, R) || mk(BUF_PACT, e->pr.d.inter / 2, LL, R) ||
+      mk(BUF_LOGITS, std::max(e->tk.d.vocab, e->pr.d.vocab) / 2, LL, R) || mk(BUF_HID, Ht, 2, R))
     return -FQ3_E_CUDA;
   e->buf_bytes[BUF_HID] = 0;  // plain bf16, not an LL buffer
   if (desc->has_s2m) {
-    if (mk(BUF_PIN, Ht, LL, R)) return -FQ3_E_CUDA;
+    if (mk(BUF_PIN, Ht / 2, LL, R)) return -FQ3_E_CUDA;
   } else {
     e->bufs[BUF_PIN] = e->bufs[BUF_PX];
     e->ld[BUF_PIN] = e->ld[BUF_PX];
@@ -364,8 +408,8 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
       mk(BUF_LIN_RES, e->lin_words, LL, kMaxRows))
     return -FQ3_E_CUDA;
   const int nqmax = std::max(e->tk.d.n_q_heads, e->pr.d.n_q_heads);
+  e->attn_part_bytes = (size_t)R * nqmax * kMaxSplits * kPartStride * sizeof(LLWord);
   if (dalloc(e, &e->attn_part, (size_t)R * nqmax * kMaxSplits * kPartStride)) return -FQ3_E_CUDA;
-  if (dalloc(e, &e->attn_cnt, (size_t)std::max(B, 1) * std::max(e->tk.d.n_kv_heads, e->pr.d.n_kv_heads))) return -FQ3_E_CUDA;
   if (dalloc(e, &e->pred_logits_all, (size_t)e->ncb * e->pr.d.vocab)) return -FQ3_E_CUDA;
   if (dalloc(e, &e->seen_scratch, (size_t)kMaxVocab * 4)) return -FQ3_E_CUDA;
   CK(cudaHostAlloc(reinterpret_cast<void**>(&e->err_host), 64, cudaHostAllocMapped));
@@ -415,9 +459,7 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   e->n_prefill_ph = (int)v.size();
   if (upload(e, v, &e->d_prefill)) return fail(FQ3_E_CUDA, "program upload");
   if (dalloc(e, &e->d_linear, 1)) return -FQ3_E_CUDA;
-  const size_t frames_need = kHeaderBytes + kScratchBytes + round_up((size_t)e->n_frames_ph * sizeof(Phase), 128) +
-                             2 * (size_t)kStageBytesDefault;
-  if (frames_need > e->smem_max) return fail(FQ3_E_UNSUPPORTED, "frame program does not fit in shared memory");
+  if (g_plan_fail) { g_plan_fail = false; return fail(FQ3_E_UNSUPPORTED, "a GEMV shape of this model cannot be partitioned (odd N or K % 64)"); }
   CK(cudaDeviceSynchronize());
   *out = e;
   return 0;
@@ -512,13 +554,18 @@ int fq3_set_loop_state(fq3_engine* e, int idx, int token, const void* past_hidde
 }
 
 static int prefill_rows(const fq3_engine* e) {
-  // rows per pass are bounded by the activation staging buffer: keep >= 4 ring stages
-  const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes -
-                     (long)round_up((size_t)e->n_prefill_ph * sizeof(Phase), 128) - 6L * kStageBytesDefault;
-  long rows = avail / ((long)e->tk.kmax() * 2);
-  const int gq = e->tk.d.n_q_heads / e->tk.d.n_kv_heads;
-  rows = std::min<long>(rows, 16 / gq);
+  // rows per pass are bounded by the activation staging buffer: keep a ring of >= 6 stages
+  const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - 6L * kStageBytes;
+  const long rows = avail / ((long)e->tk.kmax() * 2);
   return (int)std::max<long>(1, std::min<long>(rows, kMaxRows));
+}
+
+// activation staging elements of the decode programs: predictor pass 0 stages two rows per stream
+static size_t decode_x_elems(const fq3_engine* e, int n_streams, bool talker, bool predictor) {
+  size_t n = 0;
+  if (talker) n = std::max(n, (size_t)n_streams * e->tk.kmax());
+  if (predictor) n = std::max(n, (size_t)2 * n_streams * std::max(e->pr.kmax(), e->desc.has_s2m ? e->tk.d.hidden : 0));
+  return n;
 }
 
 int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pad, const fq3_policy* policy,
@@ -550,7 +597,7 @@ int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pa
     p.stream0 = idx;
     p.pf_pos0 = c0; p.pf_n_pad = n_left_pad; p.pf_rope_delta = -n_left_pad; p.pf_final = final;
     p.pol = to_policy(policy);
-    if (int r = launch(e, p, rows, e->tk.kmax(), s)) return r;
+    if (int r = launch(e, p, (size_t)rows * e->tk.kmax(), s)) return r;
   }
   fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, T, 0, 8, 0, 0, 0);
   e->launches += 1;
@@ -575,7 +622,7 @@ int fq3_talker_step(fq3_engine* e, int idx, const void* embeds, int position, vo
   p.n_rows = 1;
   p.stream0 = idx;
   p.pos_override = position;
-  if (int r = launch(e, p, 1, e->tk.kmax(), s)) return r;
+  if (int r = launch(e, p, decode_x_elems(e, 1, true, false), s)) return r;
   if (out_hidden) CK(cudaMemcpyAsync(out_hidden, e->bufs[BUF_HID], (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
   if (out_logits)
     if (int r = unpack_f32(e, out_logits, e->tk.d.vocab, BUF_LOGITS, 0, 1, e->tk.d.vocab, s)) return r;
@@ -599,8 +646,7 @@ int fq3_predictor_run(fq3_engine* e, int idx, const void* pred_input, const fq3_
   p.sub = to_sub(sub);
   p.pol.seed = seed;
   p.pred_logits_all = out_logits ? e->pred_logits_all : nullptr;
-  const int kmax = std::max(e->pr.kmax(), e->desc.has_s2m ? e->tk.d.hidden : 0);
-  if (int r = launch(e, p, 2, kmax, s)) return r;
+  if (int r = launch(e, p, decode_x_elems(e, 1, false, true), s)) return r;
   fq3_codes_to_i64_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(e->d_st + idx) +
                                                                          offsetof(StreamState, cur_codes)),
                                            e->ncb, reinterpret_cast<long long*>(out_codes_i64));
@@ -657,8 +703,7 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
   p.n_iters = n_frames;
   p.pol = to_policy(policy);
   p.sub = to_sub(sub);
-  const int kmax = std::max(e->pr.kmax(), e->tk.kmax());
-  return launch(e, p, 2 * n_streams, kmax, (cudaStream_t)stream);
+  return launch(e, p, decode_x_elems(e, n_streams, true, true), (cudaStream_t)stream);
 }
 
 int fq3_get_status(fq3_engine* e, int idx, fq3_status* out, void* stream) {
@@ -688,8 +733,8 @@ int fq3_read_codes(fq3_engine* e, int idx, int first, int n, int32_t* codes_out,
 int fq3_debug_read_prof(fq3_engine* e, long long* out, int n_words) {
   if (!e || !e->prof) return fail(FQ3_E_INVALID, "profiling not enabled (FQ3_PROF)");
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, e->prof, sizeof(long long) * std::min(n_words, 1024 * 8), cudaMemcpyDeviceToHost));
-  CK(cudaMemset(e->prof, 0, sizeof(long long) * 1024 * 8));
+  CK(cudaMemcpy(out, e->prof, sizeof(long long) * std::min(n_words, 512 * 16), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(e->prof, 0, sizeof(long long) * 512 * 16));
   return 0;
 }
 
@@ -710,8 +755,11 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
                float eps, const void* bias, const void* residual, void* stream) {
   if (!e || !W || !x || !y) return fail(FQ3_E_INVALID, "null argument");
   if (M < 1 || M > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "M must be in [1, 8]");
-  if (K % 8 || K * 2 > kStageBytesDefault || N < 1 || K > e->lin_words || N > e->lin_words) return fail(FQ3_E_UNSUPPORTED, "K must be a multiple of 8 and fit one stage");
-  if ((flags & 8) && (N % 2)) return fail(FQ3_E_INVALID, "SwiGLU needs an even N");
+  if (K % 64 || N < 2 || (N & 1) || K / 2 > e->lin_words || N / 2 > e->lin_words)
+    return fail(FQ3_E_UNSUPPORTED, "K must be a multiple of 64 and N even");
+  if ((flags & 8) && (N % 4)) return fail(FQ3_E_INVALID, "SwiGLU needs N to be a multiple of 4");
+  Plan lin_plan{};
+  if (!make_plan(e->G, N, K, (flags & 8) != 0, &lin_plan)) return fail(FQ3_E_UNSUPPORTED, "shape cannot be partitioned");
   cudaStream_t s = (cudaStream_t)stream;
   Phase ph{};
   ph.type = PH_GEMV;
@@ -719,6 +767,7 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
              ((flags & 8) ? F_SWIGLU : 0) | ((flags & 16) ? F_OUT_F32 : 0) | ((flags & 32) ? F_SILU : 0);
   ph.in_buf = BUF_LIN_IN; ph.out_buf = BUF_LIN_OUT; ph.res_buf = BUF_LIN_RES;
   ph.N = (uint32_t)N; ph.K = (uint32_t)K;
+  ph.plan = (uint8_t)(kMaxPlans - 1);
   CK(cudaMemcpyAsync(e->d_linear, &ph, sizeof ph, cudaMemcpyHostToDevice, s));
   LaunchParams p{};
   fill_common(e, p);
@@ -733,7 +782,8 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
     if (int r = pack_ll(e, BUF_LIN_RES, 0, residual, No, M, No, s)) return r;
   }
   p.lin_W = W; p.lin_gamma = gamma; p.lin_bias = bias; p.lin_eps = eps;
-  if (int r = launch(e, p, M, K, s)) return r;
+  p.plans[kMaxPlans - 1] = lin_plan;
+  if (int r = launch(e, p, (size_t)M * K, s)) return r;
   if (flags & 16) return unpack_f32(e, y, No, BUF_LIN_OUT, 0, M, No, s);
   return unpack_bf16(e, y, No, BUF_LIN_OUT, 0, M, No, s);
 }

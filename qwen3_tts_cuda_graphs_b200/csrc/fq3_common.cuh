@@ -2,10 +2,10 @@
 //
 // The kernel is a small "phase machine": a program is a flat list of 32-byte phase descriptors (GEMV /
 // attention / sampling).  One CTA per SM runs the whole program; a producer warp streams the weight
-// tiles of every GEMV phase through a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS
-// UBLKCP) while eight consumer warps do the arithmetic.  Because weight addresses never depend on
-// activations or sampled tokens, the producer runs ahead across phase and grid barriers, so HBM stays
-// busy while the consumers wait for each other.  See DESIGN.md §3.
+// rows of every GEMV phase through a shared-memory ring of 16 KB stages (8 rows x 1024 columns) with
+// cp.async.bulk (TMA bulk copy, SASS UBLKCP) while sixteen consumer warps do the arithmetic.  Because
+// weight addresses never depend on activations or sampled tokens, the producer runs ahead across
+// phases, so HBM stays busy while the consumers wait for each other.  See DESIGN.md §3.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -16,25 +16,40 @@ namespace fq3 {
 typedef __nv_bfloat16 bf16;
 
 // ---- geometry ---------------------------------------------------------------------------------
-constexpr int kConsumerWarps = 15;  // 15 consumers + 1 producer = 512 threads -> 128 registers per thread
-constexpr int kConsumerThreads = kConsumerWarps * 32;  // 480
+constexpr int kConsumerWarps = 12;  // 12 consumers + 1 producer = 13 warps; registers are allotted per 4 warps -> 128 per thread
+constexpr int kConsumerThreads = kConsumerWarps * 32;  // 384
 constexpr int kThreads = kConsumerThreads + 32;        // + one producer warp
-constexpr int kStageBytesDefault = 16 * 1024;  // one ring stage (weight tile)
-constexpr int kMaxStages = 12;
-constexpr int kRowsPerTileMax = 128;
-constexpr int kScratchBytes = 44 * 1024;  // attention scratch (q rows + 16x4 warp partials) / sampling scratch
-constexpr int kHeadDim = 128;             // talker and predictor heads (asserted on the host)
-constexpr int kMaxRows = 8;               // activation rows (tokens) per launch, GEMV register tile
-constexpr int kMaxSplits = 32;            // split-KV partitions per (sequence, kv head)
-constexpr int kPartStride = 132;          // floats per attention partial: m, l, pad, pad, o[128]
+constexpr int kMaxStages = 16;             // mbarrier pairs: ring stages in flight per SM (12 fit beside the scratch)
+constexpr int kStageRows = 8;              // weight rows per stage = one mma n-tile
+constexpr int kStageCols = 1024;           // columns per stage
+constexpr int kRowPitch = kStageCols * 2;  // bytes between two rows of a stage in shared memory
+constexpr int kStageBytes = kStageRows * kRowPitch;  // 16 KB
+constexpr int kUnitCols = 256;             // one warp's share of a stage: 8 rows x 256 columns (4 warps per stage)
+constexpr int kGroups = kConsumerWarps / 4;  // stages consumed concurrently
+constexpr int kBatchStages = 12;           // stages between two partial-sum reductions
+constexpr int kHeadDim = 128;              // talker and predictor heads (asserted on the host)
+constexpr int kMaxRows = 8;                // activation rows (tokens) per launch, GEMV register tile
+constexpr int kMaxSplits = 16;             // split-KV partitions per (sequence, kv head)
+constexpr int kSplitLen = 4 * kConsumerWarps;              // positions one CTA sweeps per (row, kv head) before the context is split over CTAs
+constexpr int kPartStride = 132;           // floats per attention partial: m, l, pad, pad, o[128]
 constexpr int kNumBufs = 16;
-constexpr int kMaxVocab = 5120;              // sampling scratch holds V fp32 logits in 20 KB
-constexpr int kCtlOffset = 192;            // smem: full[12] | empty[12] | ctl[16] | scratch ...
-constexpr int kHeaderBytes = 256;
+constexpr int kMaxVocab = 5120;            // sampling scratch holds V fp32 logits in 20 KB
+// scratch: GEMV partial sums [kBatchStages][4][M<=8][8] fp32 = 12 KB;
+//          attention q rows fp32 [2][128] | fresh K/V rows bf16 [8][2][128] | warp partials [12][2][132] = 17.4 KB;
+//          sampling 20 KB logits + histogram + reductions = 21.5 KB
+constexpr int kScratchBytes = 24 * 1024;
+// smem header: full[16] | empty[16] | ctl[16] | red[8][16]
+constexpr int kEmptyOffset = 128;
+constexpr int kCtlOffset = 256;
+constexpr int kRedOffset = 320;
+constexpr int kHeaderBytes = 1024;
+constexpr int kMaxPlans = 24;
 
 // ---- LL (low-latency) activation words ---------------------------------------------------------
-// Every activation that crosses CTAs is an 8-byte word {fp32 value (bf16-rounded), epoch}.  A single
-// 8-byte store is atomic, so a reader that sees the expected epoch also sees the value: consumers poll
+// Every activation that crosses CTAs travels in 8-byte words {payload, epoch}.  payload = two bf16 values
+// (elements 2w, 2w+1 of the vector: every exchanged activation is bf16-rounded at that point in the
+// reference as well), one fp32 (split-attention partials) or one int (frame control record).  A single
+// 8-byte store is atomic, so a reader that sees the expected epoch also sees the payload: consumers poll
 // the data itself and no grid-wide barrier, fence or atomic sits between two phases.
 typedef uint2 LLWord;
 
@@ -71,13 +86,25 @@ struct __align__(16) Phase {
   uint32_t K;
   uint8_t res_buf;
   uint8_t kind;  // SAMPLE: SampleKind
-  uint8_t pad0, pad1;
+  uint8_t plan;  // GEMV: index into LaunchParams::plans
+  uint8_t pad1;
 };
 static_assert(sizeof(Phase) == 32, "Phase must stay 32 bytes");
 
 enum BufId : uint8_t {
   BUF_TX = 0, BUF_TQKV, BUF_TATT, BUF_TACT, BUF_PX, BUF_PQKV, BUF_PATT, BUF_PACT, BUF_PIN,
   BUF_LOGITS, BUF_HID, BUF_LIN_IN, BUF_LIN_OUT, BUF_LIN_RES, BUF_COUNT
+};
+
+// Host-computed partition of one GEMV shape (N, K, SwiGLU) over the grid.  A super-unit (SU) is the `ro` consecutive
+// weight rows behind one packed output word: 2 rows (plain) or 4 rows (SwiGLU: two (gate, up) pairs).  A CTA's rows are
+// cut into tiles of 8 rows and every tile into nkq stages of <= 1024 columns (stage index = tile * nkq + kq).
+struct Plan {
+  int su_base, su_rem;  // SUs (= output words) per CTA: the first su_rem CTAs take su_base + 1
+  int ro;               // weight rows per SU
+  int nkq;              // stages per tile = ceil(K / 1024)
+  int tpb;              // tiles per batch = max(1, kBatchStages / nkq)
+  int pad;
 };
 
 // ---- run-time structures ----------------------------------------------------------------------
@@ -140,8 +167,7 @@ struct LaunchParams {
   StreamState* st;
   Policy pol;
   SubPolicy sub;
-  float* attn_part;
-  unsigned* attn_cnt;
+  LLWord* attn_part;  // split-attention partials as fp32 LL words [row][q head][split][kPartStride]
   int* err;  // mapped host memory: [0]=code [1]=cta [2]=phase [3]=detail
   // model constants used by the sampling phases
   int n_code_groups, eos_id, has_s2m, max_frames;
@@ -154,14 +180,15 @@ struct LaunchParams {
   const void* lin_bias;
   float lin_eps;
   // smem carve-up
-  int n_stages, xbuf_bytes, prog_bytes, stage_bytes;
+  int n_stages, xbuf_bytes;  // ring stages of 16 KB; bytes of the activation staging buffer
+  Plan plans[kMaxPlans];
   unsigned epoch_base;  // LL epoch of the phase before this launch's first phase
   unsigned long long watchdog_ns;
   long long* prof;  // optional per-phase clock64 marks [n_phases][8] of CTA prof_cta (FQ3_PROF)
   int prof_cta;
-  int debug;  // timing ablations (FQ3_DEBUG): 1 no LL wait, 2 no GEMV math, 4 no attention, 8 no activation load
+  int debug;  // timing ablations (FQ3_DEBUG): 1 no LL wait, 2 no GEMV math, 4 no attention
 };
 
-enum DevErr : int { DE_NONE = 0, DE_LL_WAIT = 1, DE_FULL_WAIT = 2, DE_EMPTY_WAIT = 3, DE_HANDSHAKE = 4, DE_BAD_PHASE = 5, DE_CTL_WAIT = 6 };
+enum DevErr : int { DE_NONE = 0, DE_LL_WAIT = 1, DE_FULL_WAIT = 2, DE_EMPTY_WAIT = 3, DE_HANDSHAKE = 4, DE_BAD_PHASE = 5, DE_CTL_WAIT = 6, DE_ASSERT = 7 };
 
 }  // namespace fq3

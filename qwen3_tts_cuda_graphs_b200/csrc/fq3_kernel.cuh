@@ -1,16 +1,19 @@
-// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a), v2.
+// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a), v4.
 //
 // Replaces the CUDA-graph replays of talker_graph.py:97-107,198-214 and predictor_graph.py:115-167 and
 // the eager per-frame glue of generate.py:149-199 (reference paths under /root/reference/faster_qwen3_tts).
 //
 // Structure of one CTA (one per SM, all co-resident):
 //   warp 16      producer: walks the phase program and streams this CTA's weight rows of every GEMV phase
-//                through a shared-memory ring with cp.async.bulk (TMA bulk copy).  Weight addresses never
-//                depend on activations or sampled ids, so it runs ahead of the consumers across phases.
-//   warps 0..15  consumers: per phase, poll-read the input activations (LL words), then each warp consumes
-//                the ring tiles independently (row -> warp round-robin, no CTA barrier per tile) and
-//                publishes its output elements as LL words.
-// There is no grid barrier: phases are chained by the data itself (value + epoch in one 8-byte word).
+//                through a shared-memory ring of 16 KB stages (8 rows x 1024 columns) with cp.async.bulk
+//                (TMA bulk copy).  Weight addresses never depend on activations or sampled ids, so it runs
+//                ahead of the consumers across phases and frames.
+//   warps 0..15  consumers: per phase, poll-read the input activations (LL words), then four warps share a
+//                stage (8 rows x 256 columns each) and multiply it with mma.sync.m16n8k16 (weights are the
+//                B operand, up to 8 activation rows ride in the A operand), drop their partial sums in shared
+//                memory, and after one barrier one thread per output word reduces, applies the epilogue and
+//                publishes.
+// There is no grid barrier: phases are chained by the data itself (payload + epoch in one 8-byte word).
 #pragma once
 #include "fq3_common.cuh"
 
@@ -26,9 +29,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t n) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -47,11 +47,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
@@ -80,6 +85,11 @@ __device__ __forceinline__ int ld_volatile_shared_i32(const int* p) {
 __device__ __forceinline__ void st_volatile_shared_i32(int* p, int v) {
   asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 
 // LL words: relaxed gpu-scope 8-byte accesses served by L2 (the coherence point).
 __device__ __forceinline__ LLWord ll_ld(const LLWord* p) {
@@ -91,9 +101,13 @@ __device__ __forceinline__ LLWord ll_ld(const LLWord* p) {
 __device__ __forceinline__ void ll_ld2(const LLWord* p, LLWord& a, LLWord& b) {
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(b.x), "=r"(b.y) : "l"(p) : "memory");
 }
-__device__ __forceinline__ void ll_st(LLWord* p, float v, uint32_t ep) {
-  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(ep) : "memory");
+__device__ __forceinline__ void ll_st(LLWord* p, uint32_t payload, uint32_t ep) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(ep) : "memory");
 }
+__device__ __forceinline__ void ll_st2(LLWord* p, uint32_t pay0, uint32_t pay1, uint32_t ep) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(p), "r"(pay0), "r"(ep), "r"(pay1) : "memory");
+}
+__device__ __forceinline__ void ll_stf(LLWord* p, float v, uint32_t ep) { ll_st(p, __float_as_uint(v), ep); }
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -112,16 +126,12 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// 8 bf16 products into two independent accumulators (halves the dependent FMA chain)
-__device__ __forceinline__ void dot8(const uint4& w, const uint4& x, float& a0, float& a1) {
-  a0 = fmaf(bf_lo(w.x), bf_lo(x.x), a0);
-  a1 = fmaf(bf_hi(w.x), bf_hi(x.x), a1);
-  a0 = fmaf(bf_lo(w.y), bf_lo(x.y), a0);
-  a1 = fmaf(bf_hi(w.y), bf_hi(x.y), a1);
-  a0 = fmaf(bf_lo(w.z), bf_lo(x.z), a0);
-  a1 = fmaf(bf_hi(w.z), bf_hi(x.z), a1);
-  a0 = fmaf(bf_lo(w.w), bf_lo(x.w), a0);
-  a1 = fmaf(bf_hi(w.w), bf_hi(x.w), a1);
+// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // =================================================================================================
@@ -130,9 +140,9 @@ __device__ __forceinline__ void dot8(const uint4& w, const uint4& x, float& a0, 
 struct Smem {
   uint64_t* full;    // [kMaxStages]
   uint64_t* empty;   // [kMaxStages]
-  int* ctl;          // [0] producer go flag, [4..] broadcast scratch
+  int* ctl;          // [0] producer go flag, [8..11] frame positions, [12..15] frame done flags
+  float* red;        // [kMaxRows][16] RMSNorm partial sums
   unsigned char* scratch;
-  Phase* prog;
   unsigned char* xbuf;
   unsigned char* ring;
 };
@@ -140,12 +150,12 @@ struct Smem {
 __device__ __forceinline__ Smem carve_smem(unsigned char* base, const LaunchParams& p) {
   Smem s;
   s.full = reinterpret_cast<uint64_t*>(base);
-  s.empty = s.full + kMaxStages;
+  s.empty = reinterpret_cast<uint64_t*>(base + kEmptyOffset);
   s.ctl = reinterpret_cast<int*>(base + kCtlOffset);
+  s.red = reinterpret_cast<float*>(base + kRedOffset);
   s.scratch = base + kHeaderBytes;
-  s.prog = reinterpret_cast<Phase*>(s.scratch + kScratchBytes);
-  s.xbuf = reinterpret_cast<unsigned char*>(s.prog) + p.prog_bytes;
-  s.ring = s.xbuf + p.xbuf_bytes;
+  s.xbuf = s.scratch + kScratchBytes;
+  s.ring = s.xbuf + p.xbuf_bytes;  // header + scratch are 1 KB multiples and xbuf_bytes is a multiple of 1 KB
   return s;
 }
 
@@ -186,304 +196,540 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const 
   mbar_wait_slow(bar, parity, p, code, phase);
 }
 
-// Slow path of an LL read: poll until the word carries `ep`.
+// Slow path of an LL read: poll until the word carries `ep`.  The first retries are immediate (the common case is
+// a word that lands within one more L2 round trip); after that back off a little.
 __device__ __noinline__ LLWord ll_spin(const LLWord* ptr, uint32_t ep, const LaunchParams& p, int phase) {
   Spin s;
   LLWord w;
-  unsigned ns = 64;
+  unsigned tries = 0;
   do {
-    // back off: thousands of threads polling L2 at full rate starve the weight stream of L2 request slots
-    __nanosleep(ns);
-    if (ns < 256) ns += 64;
+    if (++tries > 4) __nanosleep(40);
     s.tick(p, DE_LL_WAIT, phase, (int)ep);
     w = ll_ld(ptr);
   } while (w.y != ep);
   return w;
 }
 // Validate a word that was loaded earlier (loads are issued in batches so their L2 round trips overlap);
-// ep == 0 accepts whatever is there — inputs written before the launch.
-__device__ __forceinline__ float ll_check(LLWord w, const LLWord* ptr, uint32_t ep, const LaunchParams& p, int phase) {
-  if (ep != 0 && w.y != ep && !(p.debug & 1)) w = ll_spin(ptr, ep, p, phase);
-  return __uint_as_float(w.x);
+// ep == 0 accepts whatever is there — inputs written before the launch.  Returns the 32-bit payload.
+__device__ __forceinline__ uint32_t ll_check(LLWord w, const LLWord* ptr, uint32_t ep, const LaunchParams& p, int phase) {
+  if (ep != 0 && w.y != ep) w = ll_spin(ptr, ep, p, phase);
+  return w.x;
 }
-__device__ __forceinline__ float ll_wait(const LLWord* ptr, uint32_t ep, const LaunchParams& p, int phase) {
+__device__ __forceinline__ uint32_t ll_wait(const LLWord* ptr, uint32_t ep, const LaunchParams& p, int phase) {
   return ll_check(ll_ld(ptr), ptr, ep, p, phase);
 }
 
+// Device-side bounds checks (compute-sanitizer is not available on the GPU pool): a violated invariant surfaces as
+// FQ3_E_DEVICE_FAULT with code DE_ASSERT, the phase index and a site-specific detail.
+#ifndef FQ3_CHECKS
+#define FQ3_CHECKS 0
+#endif
+#if FQ3_CHECKS
+#define FQ3_ASSERT(cond, pidx, detail) do { if (!(cond)) device_fault(p, DE_ASSERT, (pidx), (detail)); } while (0)
+#else
+#define FQ3_ASSERT(cond, pidx, detail) do { } while (0)
+#endif
+
 __device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int slot) {
-  if (p.prof && threadIdx.x == 0 && (int)blockIdx.x == p.prof_cta && pidx >= 0) p.prof[(size_t)pidx * 8 + slot] = clock64();
+  if (p.prof && threadIdx.x == 0 && (int)blockIdx.x == p.prof_cta && pidx >= 0 && pidx < 512) p.prof[(size_t)pidx * 16 + slot] = clock64();
 }
 
-// =================================================================================================
-// GEMV phase
-// =================================================================================================
-struct GemvPlan {
-  int r0, r1, rt, ntiles, rpu;
-};
-__device__ __forceinline__ GemvPlan gemv_plan(const Phase& ph, const LaunchParams& p, int cta, int G) {
-  GemvPlan g;
-  g.rpu = (ph.flags & F_SWIGLU) ? 2 : 1;
-  const int N = (int)ph.N, K = (int)ph.K;
-  const int nunits = N / g.rpu;
-  const int base = nunits / G, rem = nunits - base * G;  // balanced: the first `rem` CTAs take one more unit
-  const int u0 = cta * base + min(cta, rem);
-  const int u1 = u0 + base + (cta < rem ? 1 : 0);
-  g.r0 = u0 * g.rpu;
-  g.r1 = u1 * g.rpu;
-  int rt = min(kRowsPerTileMax, p.stage_bytes / (K * 2));
-  rt -= rt % g.rpu;
-  g.rt = max(rt, g.rpu);
-  g.ntiles = (g.r1 - g.r0 + g.rt - 1) / g.rt;
-  return g;
-}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
 __device__ __forceinline__ int phase_rows(const Phase& ph, const LaunchParams& p) {
   return (ph.flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows;
 }
 
-// Load the activation rows of a GEMV phase into shared memory (bf16), optionally RMS-normalised.
-// HF rounding points (Qwen3RMSNorm): fp32 mean-square, x*rsqrt -> bf16, * weight -> bf16.
-// All 512 consumer threads take part: one LL round trip, gamma fetched alongside.
-__device__ __noinline__ void load_x(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, int M, int row_off, uint32_t ep_in,
-                       int pidx) {
+__device__ __forceinline__ uint2 ldg_keep_u2(const void* ptr, uint64_t pol) {
+  uint2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(ptr), "l"(pol));
+  return v;
+}
+
+// =================================================================================================
+// GEMV phase, consumer side
+//
+// A lone warp issues a dependent instruction only every ~5 cycles, so what bounds a phase is the number of instructions
+// between "the input words are visible" and "the output words are stored".  Everything that does not depend on the input
+// (partition, ring positions, addresses, gamma / residual / bias fetches) is therefore computed between issuing the first
+// poll loads and looking at their result — that window (an L2 round trip) is otherwise idle.
+// =================================================================================================
+struct Ctx {  // per-thread constants (shared-memory addresses as 32-bit shared-window offsets)
+  uint32_t full, empty, red, scratch, xs, ring;
+  int n_stages;
+};
+__device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchParams& p) {
   const Smem sm = carve_smem(smem_base, p);
-  const int K = (int)ph.K;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const LLWord* in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]);
-  const int ld = p.ld[ph.in_buf];
-  bf16* xs = reinterpret_cast<bf16*>(sm.xbuf);
-  const bool norm = (ph.flags & F_PRENORM) != 0;
-  float* red = reinterpret_cast<float*>(sm.scratch);  // [kMaxRows][kConsumerWarps]
-  constexpr int kPairs = 7;  // K <= 6720: each thread owns the element pairs 2*(tid + i*480), +1 of every row
-  if (!norm) {
-    for (int m = 0; m < M; ++m) {
-      const LLWord* src = in + (size_t)(m + row_off) * ld;
-      LLWord w[kPairs][2];
+  Ctx c;
+  c.full = smem_u32(sm.full);
+  c.empty = smem_u32(sm.empty);
+  c.red = smem_u32(sm.red);
+  c.scratch = smem_u32(sm.scratch);
+  c.xs = smem_u32(sm.xbuf);
+  c.ring = smem_u32(sm.ring);
+  c.n_stages = p.n_stages;
+  return c;
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+// Ring cursor: slot and lap parity of the next stage of this CTA (same sequence on the producer and on every consumer).
+struct RingCur {
+  int slot;
+  uint32_t lap;
+  __device__ __forceinline__ void advance(int n, int n_stages) {
+    slot += n;
+    while (slot >= n_stages) { slot -= n_stages; lap ^= 1u; }
+  }
+};
+
+// General activation load (several rows, or rows too long for the register path): raw payloads go through shared
+// memory, each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square,
+// x*rsqrt -> bf16, * weight -> bf16.
+__device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, const bf16* gamma, float eps,
+                                            int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red) {
+  const int Kw = K >> 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool norm = (flags & F_PRENORM) != 0;
+#pragma unroll 1
+  for (int m = 0; m < M; ++m) {
+    const LLWord* src = in + (size_t)m * ld;
+    float ss = 0.f;
+#pragma unroll 1
+    for (int w0 = 0; w0 < Kw; w0 += 4 * kConsumerThreads) {
+      LLWord w[4];
+      Spin spin;
+      bool bad;
+      unsigned tries = 0;
+      do {
+        bad = false;
 #pragma unroll
-      for (int i = 0; i < kPairs; ++i) {
-        const int k = 2 * (threadIdx.x + i * kConsumerThreads);
-        if (k < K) ll_ld2(src + k, w[i][0], w[i][1]);
-      }
+        for (int i = 0; i < 4; ++i) {
+          const int wi = w0 + tid + i * kConsumerThreads;
+          if (wi < Kw) {
+            w[i] = ll_ld(src + wi);
+            bad |= (w[i].y != ep_in);
+          }
+        }
+        if (ep_in == 0) break;
+        if (bad) {
+          if (++tries > 4) __nanosleep(40);
+          spin.tick(p, DE_LL_WAIT, pidx, (int)ep_in);
+        }
+      } while (bad);
 #pragma unroll
-      for (int i = 0; i < kPairs; ++i) {
-        const int k = 2 * (threadIdx.x + i * kConsumerThreads);
-        if (k < K) {
-          const float v0 = ll_check(w[i][0], src + k, ep_in, p, pidx), v1 = ll_check(w[i][1], src + k + 1, ep_in, p, pidx);
-          *reinterpret_cast<uint32_t*>(xs + (size_t)m * K + k) = pack_bf16x2(v0, v1);
+      for (int i = 0; i < 4; ++i) {
+        const int wi = w0 + tid + i * kConsumerThreads;
+        if (wi < Kw) {
+          sts_u32(xs + (uint32_t)(m * Kw + wi) * 4u, w[i].x);
+          const float x0 = bf_lo(w[i].x), x1 = bf_hi(w[i].x);
+          ss = fmaf(x0, x0, ss);
+          ss = fmaf(x1, x1, ss);
         }
       }
     }
-    cbar_sync();
-    return;
+    if (norm) {
+      ss = warp_sum(ss);
+      if (lane == 0) sts_f32(red + (uint32_t)(m * 16 + warp) * 4u, ss);
+    }
   }
-  const bf16* gamma = (ph.flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_gamma)
-                                            : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
-  const float eps = (ph.flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
+  cbar_sync();
+  if (!norm) return;
+#pragma unroll 1
   for (int m = 0; m < M; ++m) {
-    const LLWord* src = in + (size_t)(m + row_off) * ld;
-    float v[kPairs][2];
-    uint32_t g[kPairs];
-    LLWord w[kPairs][2];
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < kPairs; ++i) {
-      const int k = 2 * (threadIdx.x + i * kConsumerThreads);
-      if (k < K) {
-        ll_ld2(src + k, w[i][0], w[i][1]);
-        g[i] = __ldg(reinterpret_cast<const uint32_t*>(gamma + k));
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kPairs; ++i) {
-      const int k = 2 * (threadIdx.x + i * kConsumerThreads);
-      if (k < K) {
-        v[i][0] = ll_check(w[i][0], src + k, ep_in, p, pidx);
-        v[i][1] = ll_check(w[i][1], src + k + 1, ep_in, p, pidx);
-        ss = fmaf(v[i][0], v[i][0], ss);
-        ss = fmaf(v[i][1], v[i][1], ss);
-      }
-    }
-    ss = warp_sum(ss);
-    if (lane == 0) red[m * kConsumerWarps + warp] = ss;
-    cbar_sync();
     float tot = 0.f;
 #pragma unroll
-    for (int wi = 0; wi < kConsumerWarps; ++wi) tot += red[m * kConsumerWarps + wi];
+    for (int wi = 0; wi < kConsumerWarps; ++wi) tot += lds_f32(red + (uint32_t)(m * 16 + wi) * 4u);
     const float rs = rsqrtf(tot / (float)K + eps);
-    const bool wr = (ph.flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
-#pragma unroll
-    for (int i = 0; i < kPairs; ++i) {
-      const int k = 2 * (threadIdx.x + i * kConsumerThreads);
-      if (k < K) {
-        const float y0 = bf16r(bf16r(v[i][0] * rs) * bf_lo(g[i])), y1 = bf16r(bf16r(v[i][1] * rs) * bf_hi(g[i]));
-        const uint32_t pk = pack_bf16x2(y0, y1);
-        *reinterpret_cast<uint32_t*>(xs + (size_t)m * K + k) = pk;
-        if (wr) *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID] + k) = pk;
-      }
+    const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
+#pragma unroll 1
+    for (int wi = tid; wi < Kw; wi += kConsumerThreads) {
+      const uint32_t gg = __ldg(reinterpret_cast<const uint32_t*>(gamma) + wi);
+      const uint32_t v = lds_u32(xs + (uint32_t)(m * Kw + wi) * 4u);
+      const uint32_t y = pack_bf16x2(bf16r(bf16r(bf_lo(v) * rs) * bf_lo(gg)), bf16r(bf16r(bf_hi(v) * rs) * bf_hi(gg)));
+      sts_u32(xs + (uint32_t)(m * Kw + wi) * 4u, y);
+      if (wr) reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID])[wi] = y;
     }
   }
   cbar_sync();
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
-
-// One warp computes one unit (1 row, or a gate/up pair) of one tile for MT activation rows and publishes it.
-template <int MT, int RPU>
-__device__ __noinline__ void gemv_unit(const Phase& ph, const LaunchParams& p, const uint4* __restrict__ wrow,
-                                          const uint4* __restrict__ xs, int cpr, int out_col, int M, uint32_t ep) {
-  const int lane = threadIdx.x & 31;
-  // residual value: issue the L2 read now, consume it in the epilogue (hides the round trip behind the dot product)
-  LLWord resw = make_uint2(0u, 0u);
-  if ((ph.flags & F_RESID) && lane < M)
-    resw = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)lane * p.ld[ph.res_buf] + out_col);
-  float a0[RPU][MT], a1[RPU][MT];
+// One warp's share of a stage: 8 weight rows x (nblk * 64) columns against up to 8 activation rows.
+//
+// Fragment mapping (lane = 4*g + t).  The weights are the B operand: column n = g is weight row g of the stage.  The
+// activations are the A operand: row g carries activation row g>>1 (row g+8: activation row 4 + (g>>1)).  A lane reads
+// 16 contiguous bytes (8 columns) of its weight row and of its activation row per load; which 8 columns depends on
+// (g & 1, t) so that a quarter-warp (rows 2j, 2j+1) covers 128 contiguous bytes -> conflict-free although all rows of a
+// stage start in the same bank.  A and B of one lane always use the same columns, and D[m][n] is only read where
+// m and n have the same parity, so the per-parity column permutation cancels out.  Result: the lane holds
+// dot(activation row g>>1, weight row 2t + (g&1)) in c[g&1]  (and row 4 + (g>>1) in c[2 + (g&1)]).
+// Four independent accumulators keep the dependent HMMA chain at a quarter of the block count.
+template <bool HI>
+__device__ __forceinline__ void gemv_unit(uint32_t wA, uint32_t wB, uint32_t xA, uint32_t xB, uint32_t yA, uint32_t yB, int nblk, int h0,
+                                          float& v_lo, float& v_hi) {
+  float c[4][4];
 #pragma unroll
-  for (int r = 0; r < RPU; ++r)
+  for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int m = 0; m < MT; ++m) a0[r][m] = a1[r][m] = 0.f;
-#pragma unroll 2
-  for (int c = lane; c < cpr; c += 32) {
-    uint4 w[RPU];
-#pragma unroll
-    for (int r = 0; r < RPU; ++r) w[r] = wrow[(size_t)r * cpr + c];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      const uint4 x = xs[(size_t)m * cpr + c];
-#pragma unroll
-      for (int r = 0; r < RPU; ++r) dot8(w[r], x, a0[r][m], a1[r][m]);
-    }
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
   }
-  float y[RPU];
-#pragma unroll
-  for (int r = 0; r < RPU; ++r) y[r] = 0.f;
-#pragma unroll
-  for (int m = 0; m < MT; ++m) {
-#pragma unroll
-    for (int r = 0; r < RPU; ++r) {
-      const float v = warp_sum(a0[r][m] + a1[r][m]);
-      if (lane == m) y[r] = v;
+  auto block = [&](uint32_t o, float (&ca)[4], float (&cb)[4]) {
+    const uint4 a = lds128(wA + o), b = lds128(wB + o);
+    const uint4 x = lds128(xA + o), y = lds128(xB + o);
+    uint4 xh = make_uint4(0u, 0u, 0u, 0u), yh = make_uint4(0u, 0u, 0u, 0u);
+    if (HI) {
+      xh = lds128(yA + o);
+      yh = lds128(yB + o);
     }
+    mma_bf16(ca, x.x, xh.x, x.y, xh.y, a.x, a.y);
+    mma_bf16(cb, y.x, yh.x, y.y, yh.y, b.x, b.y);
+    mma_bf16(ca, x.z, xh.z, x.w, xh.w, a.z, a.w);
+    mma_bf16(cb, y.z, yh.z, y.w, yh.w, b.z, b.w);
+  };
+  if (nblk == 4) {
+    block(0u, c[0], c[1]);
+    block(128u, c[2], c[3]);
+    block(256u, c[0], c[1]);
+    block(384u, c[2], c[3]);
+  } else {
+#pragma unroll 1
+    for (int b = 0; b < nblk; ++b) block((uint32_t)b * 128u, c[0], c[1]);
   }
-  if (lane < M) {
-    // epilogue with PyTorch's bf16 rounding points; lane m owns activation row m
-    const int m = lane;
-    float out;
-    if (RPU == 2) {
-      const float g = bf16r(y[0]), u = bf16r(y[1]);
-      out = bf16r(bf16r(silu_f(g)) * u);
-    } else {
-      out = y[0];
-      if (ph.flags & F_BIAS) {
-        const bf16* bias = (ph.flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias)
-                                                 : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-        out += __bfloat162float(bias[out_col]);
-      }
-      out = bf16r(out);
-      if (ph.flags & F_SILU) out = bf16r(silu_f(out));
-    }
-    if (ph.flags & F_RESID) out = bf16r(__uint_as_float(resw.x) + out);
-    ll_st(reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]) + (size_t)m * p.ld[ph.out_buf] + out_col, out, ep);
+  const float s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]), s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+  v_lo = h0 ? s1 : s0;
+  if (HI) {
+    const float s2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]), s3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
+    v_hi = h0 ? s3 : s2;
+  } else {
+    v_hi = 0.f;
   }
 }
 
-__device__ void gemv_phase_consume(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, unsigned& tile_it, int pidx,
-                                   uint32_t ep) {
-  const Smem sm = carve_smem(smem_base, p);
-  const int G = gridDim.x, cta = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const GemvPlan g = gemv_plan(ph, p, cta, G);
-  int M = phase_rows(ph, p), row_off = 0;
-  if (ph.flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
+// This CTA's share of a GEMV phase (producer and consumers must agree).
+struct Slab {
+  int n_su, su0, n_rows, n_tiles, nkq, n_stages;
+};
+__device__ __forceinline__ Slab get_slab(const Phase& ph, const LaunchParams& p) {
+  const Plan& pl = p.plans[ph.plan];
+  const int cta = blockIdx.x;
+  Slab s;
+  s.n_su = pl.su_base + (cta < pl.su_rem ? 1 : 0);
+  s.su0 = cta * pl.su_base + min(cta, pl.su_rem);
+  s.n_rows = s.n_su * pl.ro;
+  s.n_tiles = (s.n_rows + kStageRows - 1) / kStageRows;
+  s.nkq = pl.nkq;
+  s.n_stages = s.n_tiles * s.nkq;
+  return s;
+}
+
+// Partial sums of one batch in shared memory: part[((tile * M + m) * 8 + n) * (nkq * 4) + kq * 4 + wk] — the nkq*4 partial
+// sums of one output row are contiguous, so the finishing thread reads them with 16-byte loads in a fixed order.
+template <bool PROF>
+__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, int pidx, uint32_t ep) {
+  const uint32_t flags = ph.flags;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int M = (flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows, row_off = 0;
+  if (flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
   const uint32_t ep_in = (pidx == 0 && ep == p.epoch_base + 1) ? 0u : ep - 1;
-  prof_mark(p, pidx, 0);
-  if (!(p.debug & 8)) load_x(ph, p, smem_base, M, row_off, ep_in, pidx);
-  prof_mark(p, pidx, 1);
-  const int cpr = (int)ph.K >> 3;
-  const uint4* xs = reinterpret_cast<const uint4*>(sm.xbuf);
-  const int upt = g.rt / g.rpu;  // units per tile
-  const int nunits = (g.r1 - g.r0) / g.rpu;
-  // unit u of the CTA's slice belongs to warp (u % 15).  A warp only touches the tiles that hold its units; the
-  // producer pre-arrives on the stage's empty barrier for the warps that have no unit in a tile.
-  // mbarrier parity only disambiguates adjacent phases, so no warp may run a full ring ahead of the data:
-  // tiles are consumed in rounds of n_stages with a consumer barrier between rounds (one round for the
-  // 0.6B shapes, up to three for 12 KB rows).
-  const int nrounds = (g.ntiles + p.n_stages - 1) / p.n_stages;
-  int u = warp;
-#pragma unroll 1
-  for (int round = 0; round < nrounds; ++round) {
-    if (round > 0) cbar_sync();
-    const int t_end = min(g.ntiles, (round + 1) * p.n_stages);
-    int t_prev = -1;
-    int stage = 0;
-#pragma unroll 1
-    for (; u < nunits && u / upt < t_end; u += kConsumerWarps) {
-      const int t = u / upt;
-      const unsigned it = tile_it + (unsigned)t;
-      if (t != t_prev) {
-        if (t_prev >= 0) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.empty[stage]);
-        }
-        stage = it % p.n_stages;
-        if (lane == 0) mbar_wait(&sm.full[stage], (it / p.n_stages) & 1u, p, DE_FULL_WAIT, pidx);
-        __syncwarp();
-        t_prev = t;
-      }
-      if (!(p.debug & 2)) {
-        const int j = u - t * upt;
-        const uint4* wrow = reinterpret_cast<const uint4*>(sm.ring + (size_t)stage * p.stage_bytes) + (size_t)j * g.rpu * cpr;
-        const int oc = g.r0 / g.rpu + u;
-        if (g.rpu == 2) {
-          if (M == 1) gemv_unit<1, 2>(ph, p, wrow, xs, cpr, oc, M, ep);
-          else if (M == 2) gemv_unit<2, 2>(ph, p, wrow, xs, cpr, oc, M, ep);
-          else if (M <= 4) gemv_unit<4, 2>(ph, p, wrow, xs, cpr, oc, M, ep);
-          else gemv_unit<8, 2>(ph, p, wrow, xs, cpr, oc, M, ep);
-        } else {
-          if (M == 1) gemv_unit<1, 1>(ph, p, wrow, xs, cpr, oc, M, ep);
-          else if (M == 2) gemv_unit<2, 1>(ph, p, wrow, xs, cpr, oc, M, ep);
-          else if (M <= 4) gemv_unit<4, 1>(ph, p, wrow, xs, cpr, oc, M, ep);
-          else gemv_unit<8, 1>(ph, p, wrow, xs, cpr, oc, M, ep);
-        }
-      }
-    }
-    if (t_prev >= 0) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+  const int K = (int)ph.K, Kw = K >> 1;
+  const int ldin = p.ld[ph.in_buf];
+  const LLWord* in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]) + (size_t)row_off * ldin;
+  const bool norm = (flags & F_PRENORM) != 0;
+  constexpr int kXW = 4;  // words per thread held in registers on the one-row path: K <= 3072
+  const bool fast = (M == 1) && (Kw <= kXW * kConsumerThreads);
+  if (PROF) prof_mark(p, pidx, 0);
+
+  // ---- issue the first poll of this thread's input words
+  LLWord w[kXW];
+  if (fast) {
+#pragma unroll
+    for (int i = 0; i < kXW; ++i) {
+      const int wi = tid + i * kConsumerThreads;
+      w[i] = make_uint2(0u, ep_in);
+      if (wi < Kw) w[i] = ll_ld(in + wi);
     }
   }
-  tile_it += (unsigned)g.ntiles;
-  prof_mark(p, pidx, 2);
-  cbar_sync();  // xbuf is rewritten by the next phase
-  prof_mark(p, pidx, 3);
+
+  // ---- everything that does not depend on the input: overlaps the round trip of the poll
+  const Plan& pl = p.plans[ph.plan];
+  const Slab sb = get_slab(ph, p);
+  const int ro = pl.ro, tpb = pl.tpb, nkq = sb.nkq;
+  const int grp = warp >> 2, wk = warp & 3;
+  const int g = lane >> 2, t = lane & 3, h0 = g & 1;
+  const bf16* gamma = nullptr;
+  uint32_t gm[kXW];
+  if (norm) {
+    gamma = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_gamma) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
+    if (fast) {
+#pragma unroll
+      for (int i = 0; i < kXW; ++i) {
+        const int wi = tid + i * kConsumerThreads;
+        gm[i] = 0x3f803f80u;
+        if (wi < Kw) gm[i] = __ldg(reinterpret_cast<const uint32_t*>(gamma) + wi);
+      }
+    }
+  }
+  const float eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
+  // finishing thread t owns (word wl, row m) of the first batch: residual / bias words are fetched now
+  const int fin_total = sb.n_su * M;
+  const int f_wl = (M == 1) ? tid : tid / M, f_m = (M == 1) ? 0 : tid - f_wl * M;
+  const int f_word = sb.su0 + f_wl;
+  uint32_t res0 = 0u, bias0 = 0u;
+  LLWord* out = reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]);
+  const int ldout = p.ld[ph.out_buf];
+  if (tid < fin_total) {
+    if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)f_m * p.ld[ph.res_buf] + f_word).x;
+    if (flags & F_BIAS) {
+      const bf16* bias = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+      bias0 = __ldg(reinterpret_cast<const uint32_t*>(bias) + f_word);
+    }
+  }
+  // shared-memory addresses of this lane's fragments
+  RingCur base = cur;  // ring position of the first stage of the current batch
+  const uint32_t lane_w = (uint32_t)g * kRowPitch + (uint32_t)wk * (kUnitCols * 2);
+  const uint32_t oA = (uint32_t)(h0 * 64 + t * 16), oB = (uint32_t)((h0 ^ 1) * 64 + t * 16);
+  const int xr_lo = min(g >> 1, M - 1), xr_hi = min(4 + (g >> 1), M - 1);
+  const uint32_t x_lo = c.xs + (uint32_t)xr_lo * (uint32_t)K * 2u + (uint32_t)wk * (kUnitCols * 2);
+  const uint32_t x_hi = c.xs + (uint32_t)xr_hi * (uint32_t)K * 2u + (uint32_t)wk * (kUnitCols * 2);
+  const int npart = nkq * 4;
+  const int n_out = 2 * t + h0;  // weight row (inside the tile) whose dot product this lane ends up holding
+
+  // ---- wait for the input, normalise, stage it in shared memory
+  if (fast) {
+    if (ep_in != 0) {
+      unsigned tries = 0;
+      Spin spin;
+      while (true) {
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < kXW; ++i) bad |= (w[i].y != ep_in);
+        if (!bad) break;
+        if (++tries > 4) __nanosleep(32);
+        spin.tick(p, DE_LL_WAIT, pidx, (int)ep_in);
+#pragma unroll
+        for (int i = 0; i < kXW; ++i) {
+          const int wi = tid + i * kConsumerThreads;
+          if (wi < Kw && w[i].y != ep_in) w[i] = ll_ld(in + wi);
+        }
+      }
+    }
+    if (PROF) prof_mark(p, pidx, 7);
+    if (!norm) {
+#pragma unroll
+      for (int i = 0; i < kXW; ++i) {
+        const int wi = tid + i * kConsumerThreads;
+        if (wi < Kw) sts_u32(c.xs + (uint32_t)wi * 4u, w[i].x);
+      }
+      cbar_sync();
+    } else {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < kXW; ++i) {  // absent words carry payload 0
+        const float x0 = bf_lo(w[i].x), x1 = bf_hi(w[i].x);
+        ss = fmaf(x0, x0, ss);
+        ss = fmaf(x1, x1, ss);
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) sts_f32(c.red + (uint32_t)warp * 4u, ss);
+      cbar_sync();
+      float tot = 0.f;
+      {
+        const float4 r0 = lds_f32x4(c.red), r1 = lds_f32x4(c.red + 16u), r2 = lds_f32x4(c.red + 32u);
+        static_assert(kConsumerWarps == 12, "the RMSNorm reduction reads twelve per-warp sums");
+        tot = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w)) + ((r2.x + r2.y) + (r2.z + r2.w));
+      }
+      const float rs = rsqrtf(tot / (float)K + eps);
+      const bool wr = (flags & F_WRITE_NORMED) && blockIdx.x == 0;
+#pragma unroll
+      for (int i = 0; i < kXW; ++i) {
+        const int wi = tid + i * kConsumerThreads;
+        if (wi < Kw) {
+          const uint32_t y = pack_bf16x2(bf16r(bf16r(bf_lo(w[i].x) * rs) * bf_lo(gm[i])), bf16r(bf16r(bf_hi(w[i].x) * rs) * bf_hi(gm[i])));
+          sts_u32(c.xs + (uint32_t)wi * 4u, y);
+          if (wr) reinterpret_cast<uint32_t*>(p.bufs[BUF_HID])[wi] = y;
+        }
+      }
+      cbar_sync();  // xs complete; also protects red[] against the next phase
+    }
+  } else {
+    load_x_general(p, flags, in, ldin, gamma, eps, K, M, ep_in, pidx, c.xs, c.red);
+  }
+  if (PROF) prof_mark(p, pidx, 1);
+
+  // ---- multiply: batches of <= kBatchStages stages, three stages (one per warp group) at a time
+#pragma unroll 1
+  for (int tile0 = 0; tile0 < sb.n_tiles; tile0 += tpb) {
+    const int tiles = min(tpb, sb.n_tiles - tile0);
+    const int s_count = tiles * nkq;
+    RingCur my = base;  // this warp's next stage
+    my.advance(grp, c.n_stages);
+    int kq = grp, tl = 0;  // stage sl = tl * nkq + kq of the batch
+    while (kq >= nkq) { kq -= nkq; ++tl; }
+#pragma unroll 1
+    for (int sl = grp; sl < s_count; sl += kGroups) {
+      const int kw = min(kStageCols, K - kq * kStageCols);
+      const int kcols = min(kUnitCols, kw - wk * kUnitCols);  // may be <= 0
+      const int nblk = kcols > 0 ? (kcols + 63) >> 6 : 0;
+      const uint32_t fullb = c.full + (uint32_t)my.slot * 8u;
+      if (!mbar_try_wait_a(fullb, my.lap)) {
+        Spin spin;
+        while (!mbar_try_wait_a(fullb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+      }
+      if (PROF && sl == 0) prof_mark(p, pidx, 8);
+      float v_lo = 0.f, v_hi = 0.f;
+      if (nblk > 0) {
+        const uint32_t wrow = c.ring + (uint32_t)my.slot * kStageBytes + lane_w;
+        const uint32_t xo = (uint32_t)kq * (kStageCols * 2);
+        if (M > 4) gemv_unit<true>(wrow + oA, wrow + oB, x_lo + xo + oA, x_lo + xo + oB, x_hi + xo + oA, x_hi + xo + oB, nblk, h0, v_lo, v_hi);
+        else gemv_unit<false>(wrow + oA, wrow + oB, x_lo + xo + oA, x_lo + xo + oB, 0u, 0u, nblk, h0, v_lo, v_hi);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(c.empty + (uint32_t)my.slot * 8u);
+      if (PROF && sl == 0) prof_mark(p, pidx, 9);
+      const uint32_t dst = c.scratch + (uint32_t)((((tl * M) * 8 + n_out) * npart) + kq * 4 + wk) * 4u;
+      if ((g >> 1) < M) sts_f32(dst + (uint32_t)((g >> 1) * 8 * npart) * 4u, v_lo);
+      if (4 + (g >> 1) < M) sts_f32(dst + (uint32_t)((4 + (g >> 1)) * 8 * npart) * 4u, v_hi);
+      my.advance(kGroups, c.n_stages);
+      kq += kGroups;
+      while (kq >= nkq) { kq -= nkq; ++tl; }
+    }
+    if (PROF) prof_mark(p, pidx, 6);
+    cbar_sync();
+    if (PROF) prof_mark(p, pidx, 2);
+    // ---- finish: one thread per (output word, activation row); words whose rows lie in tiles [tile0, tile0 + tiles)
+    const int w_first = tile0 * kStageRows / ro;
+    const int w_end = min(sb.n_su, (tile0 + tiles) * kStageRows / ro);
+    const int fin = (w_end - w_first) * M;
+#pragma unroll 1
+    for (int ft = tid; ft < fin; ft += kConsumerThreads) {
+      int wl, m;
+      uint32_t res = res0, bias = bias0;
+      if (tile0 == 0 && ft == tid) {
+        wl = f_wl; m = f_m;
+      } else {
+        wl = w_first + ft / M; m = ft % M;
+        if (flags & F_RESID) res = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)m * p.ld[ph.res_buf] + sb.su0 + wl).x;
+        if (flags & F_BIAS) {
+          const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+          bias = __ldg(reinterpret_cast<const uint32_t*>(bp) + sb.su0 + wl);
+        }
+      }
+      const int rr0 = wl * ro - tile0 * kStageRows;  // first row of the word inside the batch
+      float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (r < ro) {
+          const int rr = rr0 + r;
+          const uint32_t q = c.scratch + (uint32_t)(((((rr >> 3) * M + m) * 8 + (rr & 7)) * npart)) * 4u;
+          float s = 0.f;
+#pragma unroll 1
+          for (int k = 0; k < nkq; ++k) {
+            const float4 v = lds_f32x4(q + (uint32_t)k * 16u);
+            s += (v.x + v.y) + (v.z + v.w);
+          }
+          y[r] = s;
+        }
+      }
+      float lo, hi;
+      if (flags & F_SWIGLU) {
+        lo = bf16r(bf16r(silu_f(bf16r(y[0]))) * bf16r(y[1]));
+        hi = bf16r(bf16r(silu_f(bf16r(y[2]))) * bf16r(y[3]));
+      } else {
+        lo = y[0]; hi = y[1];
+        if (flags & F_BIAS) { lo += bf_lo(bias); hi += bf_hi(bias); }
+        lo = bf16r(lo); hi = bf16r(hi);
+        if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
+      }
+      if (flags & F_RESID) { lo = bf16r(bf_lo(res) + lo); hi = bf16r(bf_hi(res) + hi); }
+      ll_st(out + (size_t)m * ldout + sb.su0 + wl, pack_bf16x2(lo, hi), ep);
+    }
+    base.advance(s_count, c.n_stages);
+    if (tile0 + tpb < sb.n_tiles) cbar_sync();  // the next batch overwrites the partial sums
+  }
+  cur = base;
+  if (PROF) prof_mark(p, pidx, 3);
 }
 
-// Producer side of one GEMV phase: stream this CTA's rows through the ring.
-__device__ __noinline__ void gemv_phase_produce(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, unsigned& tile_it, int pidx,
-                                   uint64_t pol_stream, uint64_t pol_keep) {
-  const Smem sm = carve_smem(smem_base, p);
-  const GemvPlan g = gemv_plan(ph, p, blockIdx.x, gridDim.x);
-  const unsigned char* W = (ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_W)
-                                                 : p.arena + (size_t)ph.w_off * 16;
-  const size_t row_bytes = (size_t)ph.K * 2;
+// Producer side of one GEMV phase: stream this CTA's rows through the ring, one 16 KB stage (8 rows x <= 1024 columns)
+// per mbarrier.  When a stage is contiguous in HBM (K == 1024) one bulk copy moves it, otherwise one copy per row.
+// Returns false when the consumers asked to stop (frame loop finished early).
+template <bool PROF>
+__device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph, const LaunchParams& p, int* ctl, RingCur& cur, uint32_t& issued,
+                                                   int pidx, uint64_t pol_stream, uint64_t pol_keep, int lane) {
+  const Slab sb = get_slab(ph, p);
+  const int K = (int)ph.K;
+  const uint32_t row_bytes = (uint32_t)K * 2u;
+  const unsigned char* W = ((ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_W) : p.arena + (size_t)ph.w_off * 16) +
+                           (size_t)sb.su0 * p.plans[ph.plan].ro * row_bytes;
   const uint64_t pol = (ph.flags & F_L2_KEEP) ? pol_keep : pol_stream;
-  if (p.prof && (int)blockIdx.x == p.prof_cta) p.prof[(size_t)pidx * 8 + 4] = clock64();
-  for (int t = 0; t < g.ntiles; ++t, ++tile_it) {
-    const int stage = tile_it % p.n_stages;
-    const uint32_t parity = ((tile_it / p.n_stages) & 1u) ^ 1u;
-    const int row_base = g.r0 + t * g.rt;
-    const int rt = min(g.rt, g.r1 - row_base);
-    const uint32_t bytes = (uint32_t)(rt * row_bytes);
-    mbar_wait(&sm.empty[stage], parity, p, DE_EMPTY_WAIT, pidx);
-    if (t == g.ntiles - 1 && p.prof && (int)blockIdx.x == p.prof_cta) p.prof[(size_t)pidx * 8 + 5] = clock64();
-    mbar_arrive_expect_tx(&sm.full[stage], bytes);
-    bulk_g2s(sm.ring + (size_t)stage * p.stage_bytes, W + (size_t)row_base * row_bytes, bytes, &sm.full[stage], pol);
-    const int readers = min(rt / g.rpu, kConsumerWarps);  // units in this tile go to distinct warps (round-robin)
-    if (readers < kConsumerWarps) mbar_arrive_cnt(&sm.empty[stage], (uint32_t)(kConsumerWarps - readers));
+  if (PROF && (int)blockIdx.x == p.prof_cta && lane == 0 && pidx < 512) p.prof[(size_t)pidx * 16 + 4] = clock64();
+#pragma unroll 1
+  for (int tile = 0; tile < sb.n_tiles; ++tile) {
+    const int rows = min(kStageRows, sb.n_rows - tile * kStageRows);
+#pragma unroll 1
+    for (int kq = 0; kq < sb.nkq; ++kq) {
+      const uint32_t kw_bytes = (uint32_t)min(kStageCols, K - kq * kStageCols) * 2u;
+      const uint32_t fullb = c.full + (uint32_t)cur.slot * 8u, emptyb = c.empty + (uint32_t)cur.slot * 8u;
+      int stop = 0;
+      if (lane == 0) {
+        Spin spin;
+        if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
+        while (!stop && !mbar_try_wait_a(emptyb, cur.lap ^ 1u)) {
+          if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
+          spin.tick(p, DE_EMPTY_WAIT, pidx, cur.slot);
+        }
+        if (!stop)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"((uint32_t)rows * kw_bytes) : "memory");
+      }
+      stop = __shfl_sync(0xffffffffu, stop, 0);
+      if (stop) return false;
+      const uint32_t dst = c.ring + (uint32_t)cur.slot * kStageBytes;
+      const unsigned char* src = W + (size_t)tile * kStageRows * row_bytes + (size_t)kq * kRowPitch;
+      if (kw_bytes == row_bytes && row_bytes == (uint32_t)kRowPitch) {
+        if (lane == 0) bulk_g2s_a(dst, src, (uint32_t)rows * kw_bytes, fullb, pol);
+      } else if (lane < rows) {
+        bulk_g2s_a(dst + (uint32_t)lane * kRowPitch, src + (size_t)lane * row_bytes, kw_bytes, fullb, pol);
+      }
+      cur.advance(1, c.n_stages);
+      ++issued;
+    }
   }
+  if (PROF && (int)blockIdx.x == p.prof_cta && lane == 0 && pidx < 512) p.prof[(size_t)pidx * 16 + 5] = clock64();
+  return true;
 }
 
 // =================================================================================================
 // Attention phase: q/k RMSNorm + RoPE + KV append + GQA decode attention (+ split-KV combine).
+// One work item = (group, query row, kv head, split): one query row and its (<= 2) q heads.  A decode step has one
+// row per stream; a prefill chunk spreads its rows over CTAs — every item re-derives the chunk's K/V rows up to its own
+// (identical bytes from every writer, so the redundant stores are benign) and needs no cross-CTA ordering.
 // =================================================================================================
 struct Group {
   int first_row, nrows, slot, pos0, n_pad, rope_delta;
@@ -511,17 +757,26 @@ __device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& 
   }
   return r;
 }
-// one CTA handles up to 1024 positions of one (sequence, kv head); longer contexts are split
-__device__ __forceinline__ int num_splits(int L, int ngroups, int nkv, int G) {
-  int cap = G / max(1, ngroups * nkv);
-  cap = max(1, min(cap, kMaxSplits));
-  int want = (L + 1023) / 1024;
+// one CTA sweeps up to kSplitLen positions of one (row, kv head); longer contexts are split over CTAs
+__device__ __forceinline__ int num_splits(int L, int cap) {
+  const int want = (L + kSplitLen - 1) / kSplitLen;
   return max(1, min(want, cap));
 }
 
 // RMSNorm over the 128-wide head + rotary embedding; lane owns elements [4*lane, 4*lane+4).
-// gamma / cos / sin arrive as 4 packed bf16 (uint2) loaded before the activation wait.
-__device__ __forceinline__ void head_norm_rope(float (&x)[4], uint2 g2, float eps, uint2 c2, uint2 s2, int lane) {
+struct RopeRegs {
+  uint2 g2, c2, s2;
+};
+// issued before the q/k words are polled, so the table reads overlap the wait
+__device__ __forceinline__ RopeRegs rope_load(const bf16* gamma, const bf16* cosp, const bf16* sinp, int lane) {
+  RopeRegs r;
+  r.g2 = __ldg(reinterpret_cast<const uint2*>(gamma + lane * 4));
+  r.c2 = __ldg(reinterpret_cast<const uint2*>(cosp + lane * 4));
+  r.s2 = __ldg(reinterpret_cast<const uint2*>(sinp + lane * 4));
+  return r;
+}
+__device__ __forceinline__ void head_norm_rope(float (&x)[4], const RopeRegs& rr, float eps, int lane) {
+  const uint2 g2 = rr.g2, c2 = rr.c2, s2 = rr.s2;
   float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
   ss = warp_sum(ss);
   const float rs = rsqrtf(ss * (1.f / kHeadDim) + eps);
@@ -538,275 +793,328 @@ __device__ __forceinline__ void head_norm_rope(float (&x)[4], uint2 g2, float ep
     x[i] = bf16r(bf16r(y[i] * c[i]) + bf16r(rot * sn[i]));
   }
 }
-__device__ __forceinline__ uint2 ld_bf16x4(const bf16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 
-__device__ __forceinline__ void ll_issue4(const LLWord* ptr, LLWord (&w)[4]) {
-  ll_ld2(ptr, w[0], w[1]);
-  ll_ld2(ptr + 2, w[2], w[3]);
+// a warp reads one 128-wide head (64 LL words, two per lane) of the qkv row
+__device__ __forceinline__ void ll_head_wait(const LLWord* src, uint32_t ep, LLWord& a, LLWord& b, const LaunchParams& p, int phase) {
+  ll_ld2(src, a, b);
+  if (ep == 0) return;
+  Spin spin;
+  unsigned tries = 0;
+  while (__any_sync(0xffffffffu, a.y != ep || b.y != ep)) {
+    if (++tries > 4) __nanosleep(40);
+    spin.tick(p, DE_LL_WAIT, phase, (int)ep);
+    ll_ld2(src, a, b);
+  }
 }
-__device__ __forceinline__ void ll_finish4(const LLWord (&w)[4], const LLWord* ptr, uint32_t ep, const LaunchParams& p, int pidx,
-                                           float (&x)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) x[i] = ll_check(w[i], ptr + i, ep, p, pidx);
-}
 
-constexpr int kAttnPairsMax = 4;  // (row, q-head) pairs sharing one K/V sweep
+constexpr int kGq = 2;  // q heads per kv head handled by one item (talker and predictor: 16 / 8)
+constexpr int kAttnPre = 2;  // cached positions per half-warp whose K/V rows are requested before the q/k/v poll
 
-// Scratch layout (floats): qs[16][128] | wp[16 warps][kAttnPairsMax][kPartStride]
-__device__ __noinline__ void attn_item(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, const Group& gr, int kvh, int sp,
-                          int nsplit, uint32_t ep, int pidx) {
+// Scratch layout: qs fp32 [kGq][128] (1 KB) | fresh K,V rows bf16 [kMaxRows][2][128] (4 KB) | warp partials fp32 [16][kGq][kPartStride]
+// Positions are dealt to half-warps (position a + 2*warp + half, stride 2 * kConsumerWarps); a lane owns 8 of the 128 dims (one 16-byte
+// piece of the K row and of the V row).  Every half-warp keeps its own online softmax; the 32 partial states are merged in
+// a fixed order, so the result is deterministic.
+template <bool PROF>
+__device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, const Group& gr, int r, int kvh, int sp,
+                                      int nsplit, uint32_t ep, int pidx) {
   const Smem sm = carve_smem(smem_base, p);
   const StackRt& S = p.stacks[ph.stack];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = S.nq / S.nkv;
-  const int npairs = gr.nrows * gq;
   const int qb = ph.stack == ST_TALKER ? BUF_TQKV : BUF_PQKV, ab = ph.stack == ST_TALKER ? BUF_TATT : BUF_PATT;
-  const LLWord* qkv = reinterpret_cast<const LLWord*>(p.bufs[qb]);
+  const LLWord* qkv = reinterpret_cast<const LLWord*>(p.bufs[qb]) + (size_t)gr.first_row * p.ld[qb];
   const int ldq = p.ld[qb];
-  LLWord* att = reinterpret_cast<LLWord*>(p.bufs[ab]);
-  const int lda = p.ld[ab];
-  const bf16* qn = reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
-  const bf16* kn = reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+  constexpr int HW = kHeadDim / 2;  // words per head
   const size_t head_base = (((size_t)ph.layer * S.n_slots + gr.slot) * S.nkv + kvh) * (size_t)S.max_pos * kHeadDim;
   bf16* Kc = S.kcache + head_base;
   bf16* Vc = S.vcache + head_base;
-  const int pos_last = gr.pos0 + gr.nrows - 1;
-  const int L = pos_last + 1 - gr.n_pad;
+  const int pos = gr.pos0 + r;         // position of this query row; it attends to [n_pad, pos]
+  FQ3_ASSERT(pos >= 0 && pos < S.max_pos && gr.n_pad >= 0 && gr.n_pad <= pos && gq <= kGq, pidx, 200000 + pos);
+  const int L = pos + 1 - gr.n_pad;
   const int per = (L + nsplit - 1) / nsplit;
   const int a = gr.n_pad + sp * per;
-  const int b = min(a + per, gr.n_pad + L);
+  const int b = min(a + per, pos + 1);
   float* qs = reinterpret_cast<float*>(sm.scratch);
-  float* wp = qs + 16 * kHeadDim;
-  const float scale = rsqrtf((float)kHeadDim);
+  uint4* fresh = reinterpret_cast<uint4*>(sm.scratch + 1024);  // [row][K|V][16 pieces of 16 bytes]
+  float* wp = reinterpret_cast<float*>(sm.scratch + 1024 + 4096);
   const uint32_t ep_in = ep - 1;
-  prof_mark(p, pidx, 0);
+  const int hw = lane >> 4, dl = lane & 15;
+  if (PROF) prof_mark(p, pidx, 0);
 
-  // -- step 1: queries (norm + rope, pre-scaled) to smem; new K/V rows of this chunk to the cache.
-  //    Work items 0..npairs-1 are queries, npairs..npairs+nrows-1 are k/v rows; one warp each.
-  for (int it = warp; it < npairs + gr.nrows; it += kConsumerWarps) {
-    if (it < npairs) {
-      const int j = it;
-      const int r = j / gq, qh = kvh * gq + (j - r * gq);
-      const int rp = min(max(gr.pos0 + r + gr.rope_delta, 0), S.rope_len - 1);
-      const LLWord* src = qkv + (size_t)(gr.first_row + r) * ldq + qh * kHeadDim + lane * 4;
-      LLWord w[4];
-      ll_issue4(src, w);
-      const uint2 g2 = ld_bf16x4(qn + lane * 4);
-      const uint2 c2 = ld_bf16x4(S.rope_cos + (size_t)rp * kHeadDim + lane * 4);
-      const uint2 s2 = ld_bf16x4(S.rope_sin + (size_t)rp * kHeadDim + lane * 4);
-      float x[4];
-      ll_finish4(w, src, ep_in, p, pidx, x);
-      head_norm_rope(x, g2, S.eps, c2, s2, lane);
-      *reinterpret_cast<float4*>(qs + j * kHeadDim + lane * 4) =
-          make_float4(x[0] * scale, x[1] * scale, x[2] * scale, x[3] * scale);
+  // -- step 0: request the first cached K/V rows of this half-warp before waiting for q (their addresses are known)
+  uint4 kpre[kAttnPre], vpre[kAttnPre];
+#pragma unroll
+  for (int u = 0; u < kAttnPre; ++u) {
+    const int i = a + warp * 2 + hw + u * 2 * kConsumerWarps;
+    kpre[u] = make_uint4(0u, 0u, 0u, 0u);
+    vpre[u] = kpre[u];
+    if (i < b && i < gr.pos0) {
+      kpre[u] = __ldcg(reinterpret_cast<const uint4*>(Kc + (size_t)i * kHeadDim) + dl);
+      vpre[u] = __ldcg(reinterpret_cast<const uint4*>(Vc + (size_t)i * kHeadDim) + dl);
+    }
+  }
+  cbar_sync();  // the scratch may still be read by the previous phase's finishing threads
+
+  // -- step 1: one warp per item: q heads (norm + rope, pre-scaled) to smem; K/V rows pos0..pos of this chunk that fall
+  //    into [a, b) to the cache and to smem (norm + rope on K).
+  for (int it = warp; it < gq + r + 1; it += kConsumerWarps) {
+    if (it < gq) {
+      const int rp = min(max(pos + gr.rope_delta, 0), S.rope_len - 1);
+      const LLWord* src = qkv + (size_t)r * ldq + (kvh * gq + it) * HW + lane * 2;
+      const RopeRegs rr = rope_load(reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16), S.rope_cos + (size_t)rp * kHeadDim,
+                                    S.rope_sin + (size_t)rp * kHeadDim, lane);
+      LLWord w0, w1;
+      ll_head_wait(src, ep_in, w0, w1, p, pidx);
+      float x[4] = {bf_lo(w0.x), bf_hi(w0.x), bf_lo(w1.x), bf_hi(w1.x)};
+      head_norm_rope(x, rr, S.eps, lane);
+      const float scale = rsqrtf((float)kHeadDim);
+      *reinterpret_cast<float4*>(qs + it * kHeadDim + lane * 4) = make_float4(x[0] * scale, x[1] * scale, x[2] * scale, x[3] * scale);
     } else {
-      const int r = it - npairs;
-      const int pos = gr.pos0 + r;
-      if (pos >= a && pos < b) {
-        const int rp = min(max(pos + gr.rope_delta, 0), S.rope_len - 1);
-        const LLWord* row = qkv + (size_t)(gr.first_row + r) * ldq;
-        const LLWord* ksrc = row + S.nq * kHeadDim + kvh * kHeadDim + lane * 4;
-        const LLWord* vsrc = row + (S.nq + S.nkv) * kHeadDim + kvh * kHeadDim + lane * 4;
-        LLWord wk[4], wv[4];
-        ll_issue4(ksrc, wk);
-        ll_issue4(vsrc, wv);
-        const uint2 g2 = ld_bf16x4(kn + lane * 4);
-        const uint2 c2 = ld_bf16x4(S.rope_cos + (size_t)rp * kHeadDim + lane * 4);
-        const uint2 s2 = ld_bf16x4(S.rope_sin + (size_t)rp * kHeadDim + lane * 4);
-        float x[4], v[4];
-        ll_finish4(wk, ksrc, ep_in, p, pidx, x);
-        ll_finish4(wv, vsrc, ep_in, p, pidx, v);
-        head_norm_rope(x, g2, S.eps, c2, s2, lane);
-        uint2 kk, vv;
-        kk.x = pack_bf16x2(x[0], x[1]); kk.y = pack_bf16x2(x[2], x[3]);
-        vv.x = pack_bf16x2(v[0], v[1]); vv.y = pack_bf16x2(v[2], v[3]);
-        *reinterpret_cast<uint2*>(Kc + (size_t)pos * kHeadDim + lane * 4) = kk;
-        *reinterpret_cast<uint2*>(Vc + (size_t)pos * kHeadDim + lane * 4) = vv;
+      const int r2 = it - gq;
+      const int kp = gr.pos0 + r2;
+      if (kp >= a && kp < b) {
+        const int rp = min(max(kp + gr.rope_delta, 0), S.rope_len - 1);
+        const LLWord* row = qkv + (size_t)r2 * ldq;
+        const LLWord* ksrc = row + (S.nq + kvh) * HW + lane * 2;
+        const LLWord* vsrc = row + (S.nq + S.nkv + kvh) * HW + lane * 2;
+        const RopeRegs rr = rope_load(reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16), S.rope_cos + (size_t)rp * kHeadDim,
+                                      S.rope_sin + (size_t)rp * kHeadDim, lane);
+        LLWord k0, k1, v0, v1;
+        ll_head_wait(ksrc, ep_in, k0, k1, p, pidx);
+        ll_head_wait(vsrc, ep_in, v0, v1, p, pidx);
+        float x[4] = {bf_lo(k0.x), bf_hi(k0.x), bf_lo(k1.x), bf_hi(k1.x)};
+        head_norm_rope(x, rr, S.eps, lane);
+        const uint2 kk = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+        const uint2 vv = make_uint2(v0.x, v1.x);
+        *reinterpret_cast<uint2*>(Kc + (size_t)kp * kHeadDim + lane * 4) = kk;
+        *reinterpret_cast<uint2*>(Vc + (size_t)kp * kHeadDim + lane * 4) = vv;
+        uint2* f = reinterpret_cast<uint2*>(fresh + (size_t)r2 * 32);
+        f[lane] = kk;
+        f[32 + lane] = vv;
       }
     }
   }
   cbar_sync();
-  prof_mark(p, pidx, 1);
+  if (PROF) prof_mark(p, pidx, 1);
 
-  // -- step 2: pairs in batches of <= 4 share one sweep over K/V.  QK^T: one lane per position (no shuffles);
-  //            P·V: lane owns 4 output dims, probabilities broadcast by shuffle.  Warp w sweeps positions
-  //            a+32w, a+32w+512, ...
-  for (int j0 = 0; j0 < npairs; j0 += kAttnPairsMax) {
-    const int np = min(kAttnPairsMax, npairs - j0);
-    float m_run[kAttnPairsMax], l_run[kAttnPairsMax], acc[kAttnPairsMax][4];
-    int pend[kAttnPairsMax];
+  // -- step 2: online softmax per half-warp
+  float qr[kGq][8];
 #pragma unroll
-    for (int j = 0; j < kAttnPairsMax; ++j) {
-      m_run[j] = -INFINITY; l_run[j] = 0.f;
-      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      const int r = (j0 + j) / gq;
-      pend[j] = (j < np) ? min(b, gr.pos0 + r + 1) : 0;  // causal bound of this pair's row
+  for (int j = 0; j < kGq; ++j) {
+    const float4 q0 = *reinterpret_cast<const float4*>(qs + j * kHeadDim + dl * 8);
+    const float4 q1 = *reinterpret_cast<const float4*>(qs + j * kHeadDim + dl * 8 + 4);
+    qr[j][0] = q0.x; qr[j][1] = q0.y; qr[j][2] = q0.z; qr[j][3] = q0.w;
+    qr[j][4] = q1.x; qr[j][5] = q1.y; qr[j][6] = q1.z; qr[j][7] = q1.w;
+  }
+  float m_run[kGq], l_run[kGq], acc[kGq][8];
+#pragma unroll
+  for (int j = 0; j < kGq; ++j) {
+    m_run[j] = -INFINITY; l_run[j] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[j][d] = 0.f;
+  }
+  auto step = [&](const uint4& kk, const uint4& vv, bool valid) {
+    const float k[8] = {bf_lo(kk.x), bf_hi(kk.x), bf_lo(kk.y), bf_hi(kk.y), bf_lo(kk.z), bf_hi(kk.z), bf_lo(kk.w), bf_hi(kk.w)};
+    const float v[8] = {bf_lo(vv.x), bf_hi(vv.x), bf_lo(vv.y), bf_hi(vv.y), bf_lo(vv.z), bf_hi(vv.z), bf_lo(vv.w), bf_hi(vv.w)};
+    float s[kGq];
+#pragma unroll
+    for (int j = 0; j < kGq; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) t = fmaf(qr[j][d], k[d], t);
+      s[j] = t;
     }
-    for (int pb = a + warp * 32; pb < b; pb += 32 * kConsumerWarps) {
-      const int pos = pb + lane;
-      const bool valid = pos < b;
-      float s[kAttnPairsMax];
 #pragma unroll
-      for (int j = 0; j < kAttnPairsMax; ++j) s[j] = 0.f;
-      if (valid) {
-        const uint4* krow = reinterpret_cast<const uint4*>(Kc + (size_t)pos * kHeadDim);
+    for (int o = 8; o > 0; o >>= 1) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 kreg[8];
+      for (int j = 0; j < kGq; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    }
+    if (valid) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) kreg[c] = __ldcg(krow + h * 8 + c);  // 8 independent loads in flight
+      for (int j = 0; j < kGq; ++j) {
+        const float m_new = fmaxf(m_run[j], s[j]);
+        const float corr = expf(m_run[j] - m_new);  // exp(-inf) = 0 on the first position
+        const float pj = expf(s[j] - m_new);
+        l_run[j] = l_run[j] * corr + pj;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 kk = kreg[c];
-            const float k0 = bf_lo(kk.x), k1 = bf_hi(kk.x), k2 = bf_lo(kk.y), k3 = bf_hi(kk.y);
-            const float k4 = bf_lo(kk.z), k5 = bf_hi(kk.z), k6 = bf_lo(kk.w), k7 = bf_hi(kk.w);
-#pragma unroll
-            for (int j = 0; j < kAttnPairsMax; ++j) {
-              if (j < np) {
-                const float* qp = qs + (j0 + j) * kHeadDim + (h * 8 + c) * 8;
-                const float4 qa = *reinterpret_cast<const float4*>(qp);
-                const float4 qb4 = *reinterpret_cast<const float4*>(qp + 4);
-                s[j] += qa.x * k0 + qa.y * k1 + qa.z * k2 + qa.w * k3 + qb4.x * k4 + qb4.y * k5 + qb4.z * k6 + qb4.w * k7;
-              }
-            }
-          }
-        }
-      }
-      float pr[kAttnPairsMax];
-#pragma unroll
-      for (int j = 0; j < kAttnPairsMax; ++j) {
-        const bool ok = valid && (j < np) && (pos < pend[j]);
-        const float sv = ok ? s[j] : -INFINITY;
-        const float m_new = fmaxf(m_run[j], warp_max(sv));
-        const float corr = (m_run[j] == -INFINITY) ? 0.f : expf(m_run[j] - m_new);
-        pr[j] = ok ? expf(sv - m_new) : 0.f;
-        l_run[j] = l_run[j] * corr + warp_sum(pr[j]);
-        acc[j][0] *= corr; acc[j][1] *= corr; acc[j][2] *= corr; acc[j][3] *= corr;
+        for (int d = 0; d < 8; ++d) acc[j][d] = fmaf(pj, v[d], acc[j][d] * corr);
         m_run[j] = m_new;
       }
-      const int nvalid = min(32, b - pb);
-      for (int i0 = 0; i0 < nvalid; i0 += 8) {
-        uint2 vreg[8];
+    }
+  };
+  {
+    // both halves of a warp run the same trip count (the shuffles name all 32 lanes); a half past the end skips the update
+    int u = 0;
+#pragma unroll 1
+    for (int i0 = a + warp * 2; i0 < b; i0 += 2 * kConsumerWarps, ++u) {
+      const int i = i0 + hw;
+      const bool valid = i < b;
+      uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
+      if (valid) {
+        if (i >= gr.pos0) {
+          const uint4* f = fresh + (size_t)(i - gr.pos0) * 32;
+          kk = f[dl];
+          vv = f[16 + dl];
+        } else if (u < kAttnPre) {
+          kk = (u == 0) ? kpre[0] : kpre[1];
+          vv = (u == 0) ? vpre[0] : vpre[1];
+        } else {
+          kk = __ldcg(reinterpret_cast<const uint4*>(Kc + (size_t)i * kHeadDim) + dl);
+          vv = __ldcg(reinterpret_cast<const uint4*>(Vc + (size_t)i * kHeadDim) + dl);
+        }
+      }
+      step(kk, vv, valid);
+    }
+  }
+  // merge the two halves of a warp (fixed order: half 0, then half 1), then one state per warp and head to shared memory
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (i0 + u < nvalid) vreg[u] = __ldcg(reinterpret_cast<const uint2*>(Vc + (size_t)(pb + i0 + u) * kHeadDim + lane * 4));
+  for (int j = 0; j < kGq; ++j) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, m_run[j], 16);
+    const float l_o = __shfl_xor_sync(0xffffffffu, l_run[j], 16);
+    const float m_new = fmaxf(m_run[j], m_o);
+    const float c_s = (m_run[j] == -INFINITY) ? 0.f : expf(m_run[j] - m_new);
+    const float c_o = (m_o == -INFINITY) ? 0.f : expf(m_o - m_new);
+    float o8[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (i0 + u < nvalid) {
-            const float v0 = bf_lo(vreg[u].x), v1 = bf_hi(vreg[u].x), v2 = bf_lo(vreg[u].y), v3 = bf_hi(vreg[u].y);
+    for (int d = 0; d < 8; ++d) {
+      const float a_o = __shfl_xor_sync(0xffffffffu, acc[j][d], 16);
+      o8[d] = acc[j][d] * c_s + a_o * c_o;
+    }
+    const float l_new = l_run[j] * c_s + l_o * c_o;
+    if (hw == 0) {
+      float* w = wp + ((size_t)warp * kGq + j) * kPartStride;
+      if (dl == 0) { w[0] = m_new; w[1] = l_new; }
+      *reinterpret_cast<float4*>(w + 4 + dl * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+      *reinterpret_cast<float4*>(w + 8 + dl * 8) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+    }
+  }
+  if (PROF) prof_mark(p, pidx, 2);
+  cbar_sync();
+  if (threadIdx.x < gq * HW) {  // a thread owns one packed output word
+    const int j = threadIdx.x / HW, wd = threadIdx.x - j * HW;
+    const int qh = kvh * gq + j;
+    const int row = gr.first_row + r;
+    float Mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < kAttnPairsMax; ++j) {
-              if (j < np) {
-                const float pj = __shfl_sync(0xffffffffu, pr[j], i0 + u);
-                acc[j][0] = fmaf(pj, v0, acc[j][0]); acc[j][1] = fmaf(pj, v1, acc[j][1]);
-                acc[j][2] = fmaf(pj, v2, acc[j][2]); acc[j][3] = fmaf(pj, v3, acc[j][3]);
-              }
-            }
+    for (int w = 0; w < kConsumerWarps; ++w) Mx = fmaxf(Mx, wp[((size_t)w * kGq + j) * kPartStride]);
+    float Lsum = 0.f, O0 = 0.f, O1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kConsumerWarps; ++w) {
+      const float* q = wp + ((size_t)w * kGq + j) * kPartStride;
+      const float f = (q[0] == -INFINITY) ? 0.f : expf(q[0] - Mx);
+      Lsum += q[1] * f;
+      const float2 o2 = *reinterpret_cast<const float2*>(q + 4 + 2 * wd);
+      O0 += o2.x * f; O1 += o2.y * f;
+    }
+    if (nsplit == 1) {
+      const float y0 = bf16r(Lsum > 0.f ? O0 / Lsum : 0.f), y1 = bf16r(Lsum > 0.f ? O1 / Lsum : 0.f);
+      ll_st(reinterpret_cast<LLWord*>(p.bufs[ab]) + (size_t)row * p.ld[ab] + qh * HW + wd, pack_bf16x2(y0, y1), ep);
+    } else {
+      LLWord* dst = p.attn_part + (((size_t)row * S.nq + qh) * kMaxSplits + sp) * kPartStride;
+      if (wd == 0) ll_st2(dst, __float_as_uint(Mx), __float_as_uint(Lsum), ep);
+      ll_st2(dst + 4 + 2 * wd, __float_as_uint(O0), __float_as_uint(O1), ep);
+    }
+  }
+  if (PROF) prof_mark(p, pidx, 3);
+}
+
+// Split-KV combine (contexts beyond kSplitLen): the CTA of split 0 polls the partials of all splits (its own included)
+// and merges them in split order.
+__device__ __forceinline__ void attn_combine(const Phase& ph, const LaunchParams& p, const Group& gr, int r, int kvh, int nsplit, uint32_t ep,
+                                          int pidx) {
+  const StackRt& S = p.stacks[ph.stack];
+  const int gq = S.nq / S.nkv;
+  const int ab = ph.stack == ST_TALKER ? BUF_TATT : BUF_PATT;
+  constexpr int HW = kHeadDim / 2;
+  if (threadIdx.x < gq * HW) {
+    const int j = threadIdx.x / HW, wd = threadIdx.x - j * HW;
+    const int qh = kvh * gq + j;
+    const int row = gr.first_row + r;
+    const LLWord* src = p.attn_part + (((size_t)row * S.nq + qh) * kMaxSplits) * kPartStride;
+    // four splits at a time: issue the loads first (the round trips overlap), then validate / re-poll and fold them into
+    // the running state in split order
+    float Mx = -INFINITY, Lsum = 0.f, O0 = 0.f, O1 = 0.f;
+#pragma unroll 1
+    for (int s0 = 0; s0 < nsplit; s0 += 4) {
+      LLWord wm[4], wl[4], wa[4], wb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u < nsplit) {
+          const LLWord* q = src + (size_t)(s0 + u) * kPartStride;
+          ll_ld2(q, wm[u], wl[u]);
+          ll_ld2(q + 4 + 2 * wd, wa[u], wb[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u < nsplit) {
+          const LLWord* q = src + (size_t)(s0 + u) * kPartStride;
+          const float ms = __uint_as_float(ll_check(wm[u], q, ep, p, pidx));
+          const float ls = __uint_as_float(ll_check(wl[u], q + 1, ep, p, pidx));
+          const float a0 = __uint_as_float(ll_check(wa[u], q + 4 + 2 * wd, ep, p, pidx));
+          const float a1 = __uint_as_float(ll_check(wb[u], q + 5 + 2 * wd, ep, p, pidx));
+          if (ms != -INFINITY) {
+            const float m_new = fmaxf(Mx, ms);
+            const float c_old = (Mx == -INFINITY) ? 0.f : expf(Mx - m_new);
+            const float c_new = expf(ms - m_new);
+            Lsum = Lsum * c_old + ls * c_new;
+            O0 = O0 * c_old + a0 * c_new;
+            O1 = O1 * c_old + a1 * c_new;
+            Mx = m_new;
           }
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < kAttnPairsMax; ++j) {
-      if (j < np) {
-        float* w = wp + ((size_t)warp * kAttnPairsMax + j) * kPartStride;
-        if (lane == 0) { w[0] = m_run[j]; w[1] = l_run[j]; }
-        *reinterpret_cast<float4*>(w + 4 + lane * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-      }
-    }
-    prof_mark(p, pidx, 2);
-    cbar_sync();
-    // merge the warp partials of each pair (fixed order => deterministic)
-    for (int o = threadIdx.x; o < np * kHeadDim; o += kConsumerThreads) {
-      const int j = o / kHeadDim, dd = o - j * kHeadDim;
-      const int r = (j0 + j) / gq, qh = kvh * gq + ((j0 + j) - r * gq);
-      const int row = gr.first_row + r;
-      float Mx = -INFINITY;
-#pragma unroll
-      for (int w = 0; w < kConsumerWarps; ++w) Mx = fmaxf(Mx, wp[((size_t)w * kAttnPairsMax + j) * kPartStride]);
-      float Lsum = 0.f, O = 0.f;
-#pragma unroll
-      for (int w = 0; w < kConsumerWarps; ++w) {
-        const float* q = wp + ((size_t)w * kAttnPairsMax + j) * kPartStride;
-        const float f = (q[0] == -INFINITY) ? 0.f : expf(q[0] - Mx);
-        Lsum += q[1] * f;
-        O += q[4 + dd] * f;
-      }
-      if (nsplit == 1) {
-        ll_st(att + (size_t)row * lda + qh * kHeadDim + dd, bf16r(Lsum > 0.f ? O / Lsum : 0.f), ep);
-      } else {
-        float* dst = p.attn_part + (((size_t)row * S.nq + qh) * kMaxSplits + sp) * kPartStride;
-        if (dd == 0) { dst[0] = Mx; dst[1] = Lsum; }
-        dst[4 + dd] = O;
-      }
-    }
-    cbar_sync();
-  }
-  prof_mark(p, pidx, 3);
-  if (nsplit > 1) {
-    // -- step 3: last-arriving split of this (sequence, kv head) combines the partials
-    __threadfence();
-    cbar_sync();
-    int* flag = sm.ctl + 4;
-    if (threadIdx.x == 0) {
-      unsigned* cnt = p.attn_cnt + (gr.slot - p.stream0) * S.nkv + kvh;
-      const unsigned old = atomicAdd(cnt, 1u);
-      const int last = (old == (unsigned)(nsplit - 1));
-      if (last) { *cnt = 0; __threadfence(); }
-      *flag = last;
-    }
-    cbar_sync();
-    if (*flag) {
-      for (int o = threadIdx.x; o < npairs * kHeadDim; o += kConsumerThreads) {
-        const int j = o / kHeadDim, dd = o - j * kHeadDim;
-        const int r = j / gq, qh = kvh * gq + (j - r * gq);
-        const int row = gr.first_row + r;
-        const float* src = p.attn_part + (((size_t)row * S.nq + qh) * kMaxSplits) * kPartStride;
-        float Mx = -INFINITY;
-        for (int s = 0; s < nsplit; ++s) Mx = fmaxf(Mx, __ldcg(src + s * kPartStride));
-        float Lsum = 0.f, O = 0.f;
-        for (int s = 0; s < nsplit; ++s) {
-          const float ms = __ldcg(src + s * kPartStride);
-          const float f = (ms == -INFINITY) ? 0.f : expf(ms - Mx);
-          Lsum += __ldcg(src + s * kPartStride + 1) * f;
-          O += __ldcg(src + s * kPartStride + 4 + dd) * f;
-        }
-        ll_st(att + (size_t)row * lda + qh * kHeadDim + dd, bf16r(Lsum > 0.f ? O / Lsum : 0.f), ep);
-      }
-    }
-    cbar_sync();
+    const float y0 = bf16r(Lsum > 0.f ? O0 / Lsum : 0.f), y1 = bf16r(Lsum > 0.f ? O1 / Lsum : 0.f);
+    ll_st(reinterpret_cast<LLWord*>(p.bufs[ab]) + (size_t)row * p.ld[ab] + qh * HW + wd, pack_bf16x2(y0, y1), ep);
   }
 }
 
-__device__ void attn_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
-                           const int* frame_pos) {
-  const Smem sm = carve_smem(smem_base, p);
+template <bool PROF>
+__device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
+                                           const int* frame_pos) {
   const StackRt& S = p.stacks[ph.stack];
   const int G = gridDim.x, cta = blockIdx.x;
   const int ng = num_groups(p);
-  // item -> CTA: spread items over the whole grid (stride) so concurrent items sit on distant SMs
+  int nrows_tot = 0;
+  for (int g = 0; g < ng; ++g) nrows_tot += get_group(ph, p, g, frame_pos).nrows;
+  const int cap = max(1, min(G / max(1, nrows_tot * S.nkv), kMaxSplits));
   int total = 0;
   for (int g = 0; g < ng; ++g) {
     const Group gr = get_group(ph, p, g, frame_pos);
-    total += S.nkv * num_splits(gr.pos0 + gr.nrows - gr.n_pad, ng, S.nkv, G);
+    for (int r = 0; r < gr.nrows; ++r) total += S.nkv * num_splits(gr.pos0 + r + 1 - gr.n_pad, cap);
   }
-  const int stride = max(1, G / max(1, total));
-  int item = 0;
-  bool any = false;
-  for (int g = 0; g < ng; ++g) {
-    const Group gr = get_group(ph, p, g, frame_pos);
-    const int L = gr.pos0 + gr.nrows - gr.n_pad;
-    const int nsplit = num_splits(L, ng, S.nkv, G);
-    const int nitems = S.nkv * nsplit;
-    for (int it = 0; it < nitems; ++it) {
-      if (((item + it) * stride) % G == cta) {
-        attn_item(ph, p, smem_base, gr, it / nsplit, it % nsplit, nsplit, ep, pidx);
-        any = true;
+  // item -> CTA: spread the items over the whole grid (stride) so concurrent items sit on distant SMs
+  const int stride = (total <= G) ? G / total : 1;
+  int first, step;
+  if (stride > 1) {
+    const int q = cta / stride;
+    first = (cta - q * stride == 0 && q < total) ? q : total;
+    step = total;
+  } else {
+    first = cta;
+    step = G;
+  }
+  for (int item = first; item < total; item += step) {
+    int base = 0;
+    bool found = false;
+    for (int g = 0; g < ng && !found; ++g) {
+      const Group gr = get_group(ph, p, g, frame_pos);
+      for (int r = 0; r < gr.nrows; ++r) {
+        const int nsplit = num_splits(gr.pos0 + r + 1 - gr.n_pad, cap);
+        const int nitems = S.nkv * nsplit;
+        if (item < base + nitems) {
+          const int it = item - base;
+          const int kvh = it / nsplit, sp = it - kvh * nsplit;
+          attn_row<PROF>(ph, p, smem_base, gr, r, kvh, sp, nsplit, ep, pidx);
+          if (nsplit > 1 && sp == 0) attn_combine(ph, p, gr, r, kvh, nsplit, ep, pidx);
+          found = true;
+          break;
+        }
+        base += nitems;
       }
     }
-    item += nitems;
   }
-  (void)any;  // the KV rows written here are fenced once per step in sample_phase (off the critical path)
 }
 
 // =================================================================================================
@@ -964,20 +1272,7 @@ __device__ __noinline__ int sample_row(const float* logits_g, const LLWord* ll, 
   float* sl = sc.sl;
   const int V = a.V;
   // 1. load + repetition penalty (sampling.py:22-29, before suppression) + suppression + temperature
-  constexpr int kLg = (kMaxVocab + kConsumerThreads - 1) / kConsumerThreads;  // 11
-  LLWord lw[kLg];
-  if (ll) {
-#pragma unroll
-    for (int j = 0; j < kLg; ++j) {
-      const int i = threadIdx.x + j * kConsumerThreads;
-      if (i < V) lw[j] = ll_ld(ll + i);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < kLg; ++j) {
-    const int i = threadIdx.x + j * kConsumerThreads;
-    if (i >= V) continue;
-    float x = ll ? ll_check(lw[j], ll + i, ep, *lp, pidx) : __ldcg(logits_g + i);
+  auto prep = [&](int i, float x) {
     if (a.seen && a.rep_pen != 1.0f && __ldcg(a.seen + i)) {
       x = (x > 0.f) ? x / a.rep_pen : x * a.rep_pen;
       if (a.round_bf16) x = bf16r(x);
@@ -989,6 +1284,41 @@ __device__ __noinline__ int sample_row(const float* logits_g, const LLWord* ll, 
       if (a.round_bf16) x = bf16r(x);
     }
     sl[i] = x;
+  };
+  if (ll) {
+    // packed words: word w carries logits 2w, 2w+1 (bf16-rounded by the head phase, like the reference's bf16 Linear)
+    constexpr int kLw = (kMaxVocab / 2 + kConsumerThreads - 1) / kConsumerThreads;  // 6
+    const int Vw = V >> 1;
+    LLWord lw[kLw];
+    Spin spin;
+    unsigned tries = 0;
+    bool bad;
+    do {
+      bad = false;
+#pragma unroll
+      for (int j = 0; j < kLw; ++j) {
+        const int wi = threadIdx.x + j * kConsumerThreads;
+        if (wi < Vw) {
+          lw[j] = ll_ld(ll + wi);
+          bad |= (lw[j].y != ep);
+        }
+      }
+      if (ep == 0) break;
+      if (bad) {
+        if (++tries > 4) __nanosleep(40);
+        spin.tick(*lp, DE_LL_WAIT, pidx, (int)ep);
+      }
+    } while (bad);
+#pragma unroll
+    for (int j = 0; j < kLw; ++j) {
+      const int wi = threadIdx.x + j * kConsumerThreads;
+      if (wi < Vw) {
+        prep(2 * wi, bf_lo(lw[j].x));
+        prep(2 * wi + 1, bf_hi(lw[j].x));
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < V; i += kConsumerThreads) prep(i, __ldcg(logits_g + i));
   }
   cbar_sync();
   float vmax;
@@ -1107,10 +1437,10 @@ __device__ __noinline__ int sample_row(const float* logits_g, const LLWord* ll, 
 
 // Publish one bf16 row (n elements) as LL words with all consumer threads.
 __device__ __forceinline__ void publish_row(LLWord* dst, const bf16* src, int n, uint32_t ep) {
-  for (int c = threadIdx.x; c < n; c += kConsumerThreads) ll_st(dst + c, __bfloat162float(src[c]), ep);
+  for (int c = threadIdx.x; c < (n >> 1); c += kConsumerThreads) ll_st(dst + c, __ldg(reinterpret_cast<const uint32_t*>(src) + c), ep);
 }
 
-__device__ __noinline__ void sample_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
+__device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
                              const int* frame_done) {
   const Smem sm = carve_smem(smem_base, p);
   const SampleScratch sc = sample_scratch(sm.scratch);
@@ -1120,8 +1450,9 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const LaunchParams& p
   // CTAs without a stream idle through sampling phases: the once-per-step fence that makes this step's KV
   // rows visible to whichever CTA reads them in a later step goes here, off the critical path.
   if ((int)blockIdx.x >= (p.mode == MODE_PREFILL ? 1 : p.n_rows) && threadIdx.x == 0 && ph.kind != SMP_PRED && ph.kind != SMP_PRED_ONLY)
-    __threadfence();
+    __threadfence();  // cumulative: covers the K/V rows its CTA mates stored (ordered before by the consumer barriers)
   for (int b = blockIdx.x; b < (p.mode == MODE_PREFILL ? 1 : p.n_rows); b += gridDim.x) {
+    cbar_sync();  // the scratch may still be read by the previous GEMV phase's finishing threads
     const int slot = p.stream0 + b;
     StreamState* st = p.st + slot;
     const int done = (p.mode == MODE_FRAMES) ? frame_done[b] : 0;
@@ -1134,8 +1465,11 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const LaunchParams& p
       const int lrow = (ph.flags & F_ROWS2) ? 2 * b + 1 : b;
       const LLWord* lg = lgbuf + (size_t)lrow * p.ld[BUF_LOGITS];
       if (p.pred_logits_all) {
-        for (int v = threadIdx.x; v < Vp; v += kConsumerThreads)
-          p.pred_logits_all[(size_t)i * Vp + v] = ll_wait(lg + v, ep_in, p, pidx);
+        for (int v = threadIdx.x; v < (Vp >> 1); v += kConsumerThreads) {
+          const uint32_t pay = ll_wait(lg + v, ep_in, p, pidx);
+          p.pred_logits_all[(size_t)i * Vp + 2 * v] = bf_lo(pay);
+          p.pred_logits_all[(size_t)i * Vp + 2 * v + 1] = bf_hi(pay);
+        }
       }
       SampleArgs a;
       a.V = Vp; a.do_sample = p.sub.do_sample; a.top_k = p.sub.top_k; a.top_p = p.sub.top_p;
@@ -1143,6 +1477,7 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const LaunchParams& p
       a.suppress_eos = 0; a.round_bf16 = 1; a.seed = p.pol.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(slot + 1));
       a.draw = __ldcg(&st->draws) + (unsigned long long)(i + 1);
       const int tok = sample_row(nullptr, lg, ep_in, &p, pidx, a, sc);
+      FQ3_ASSERT(tok >= 0 && tok < Vp, pidx, 100000 + tok);
       if (threadIdx.x == 0) st->cur_codes[i + 1] = tok;
       if (i + 1 < ncb) {
         // next predictor input row: codec_embeds[i](tok)  (predictor_graph.py:144)
@@ -1167,14 +1502,18 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const LaunchParams& p
         const int ntr = __ldcg(&st->n_trailing);
         const bf16* text = (gs < ntr) ? st->trailing + (size_t)gs * Ht : st->pad_embed;
         LLWord* tx = reinterpret_cast<LLWord*>(p.bufs[BUF_TX]) + (size_t)b * p.ld[BUF_TX];
-        for (int c = threadIdx.x; c < Ht; c += kConsumerThreads) {
-          float s = __bfloat162float(p.codec_embed[(size_t)c0 * Ht + c]);
+        const uint32_t* ce = reinterpret_cast<const uint32_t*>(p.codec_embed + (size_t)c0 * Ht);
+        const uint32_t* tx32 = reinterpret_cast<const uint32_t*>(text);
+        for (int c = threadIdx.x; c < (Ht >> 1); c += kConsumerThreads) {
+          uint32_t v = __ldg(ce + c);
+          float s0 = bf_lo(v), s1 = bf_hi(v);
           for (int g = 0; g < ncb; ++g) {
             const int code = (g == ncb - 1) ? tok : __ldcg(&st->cur_codes[g + 1]);
-            s += __bfloat162float(p.pred_embeds[g][(size_t)code * Ht + c]);
+            v = __ldg(reinterpret_cast<const uint32_t*>(p.pred_embeds[g] + (size_t)code * Ht) + c);
+            s0 += bf_lo(v); s1 += bf_hi(v);
           }
-          const float e = bf16r(s);
-          ll_st(tx + c, bf16r(e + __bfloat162float(text[c])), ep);
+          const uint32_t t = __ldg(tx32 + c);
+          ll_st(tx + c, pack_bf16x2(bf16r(bf16r(s0) + bf_lo(t)), bf16r(bf16r(s1) + bf_hi(t))), ep);
         }
         // static-cache bound (generate.py:174-177): the frame stays, decoding stops after this step
         if (threadIdx.x == 0 && !done) {
@@ -1210,15 +1549,15 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const LaunchParams& p
       if (threadIdx.x == 0) {
         if (live) { st->token = tok; st->draws = a.draw + 1ull; st->position = new_pos; st->gen_step = new_gs; st->done = new_done; }
         // control record every CTA reads at the top of the next frame
-        ll_st(&st->ctl[0], __int_as_float(new_done), ep);
-        ll_st(&st->ctl[1], __int_as_float(new_pos), ep);
+        ll_st(&st->ctl[0], (uint32_t)new_done, ep);
+        ll_st(&st->ctl[1], (uint32_t)new_pos, ep);
       }
       // predictor pass-0 input rows [past_hidden ; codec_embed(token)] (generate.py:154-155), addressed by
       // stream slot; always re-published so every reader sees this phase's epoch
       const bf16* hid = reinterpret_cast<const bf16*>(p.bufs[BUF_HID]) + (size_t)b * p.ld[BUF_HID];
       publish_row(pin + (size_t)(2 * slot) * ldpin, hid, Ht, ep);
       publish_row(pin + (size_t)(2 * slot + 1) * ldpin, p.codec_embed + (size_t)tok * Ht, Ht, ep);
-      if (threadIdx.x == 0) __threadfence();
+      if (threadIdx.x == 0) __threadfence();  // once per step: K/V rows stored by this CTA (see above)
     }
     cbar_sync();
   }
@@ -1227,52 +1566,67 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const LaunchParams& p
 // =================================================================================================
 // Kernel
 // =================================================================================================
+__device__ __forceinline__ Phase load_phase(const Phase* prog, int i) {
+  // uniform address: one L1-resident 32-byte read, broadcast to the warp
+  union { Phase ph; uint4 q[2]; } u;
+  const uint4* src = reinterpret_cast<const uint4*>(prog + i);
+  u.q[0] = __ldg(src);
+  u.q[1] = __ldg(src + 1);
+  return u.ph;
+}
+
+template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_constant__ LaunchParams p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem sm = carve_smem(smem_raw, p);
+  const Ctx c = make_ctx(smem_raw, p);
   const int tid = threadIdx.x;
 
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], kConsumerWarps);
+      mbar_init(&sm.empty[s], 4);  // the four warps that share a stage
     }
     sm.ctl[0] = 0;
     fence_barrier_init();
   }
   {
-    const uint4* src = reinterpret_cast<const uint4*>(p.prog);
-    uint4* dst = reinterpret_cast<uint4*>(sm.prog);
-    for (int i = tid; i < p.n_phases * 2; i += kThreads) dst[i] = __ldg(src + i);
+    // Partially filled stages (last rows of a slab, K < 1024) leave stale bytes under the mma; they only reach outputs
+    // nobody reads, but they must be finite — start from zeros.
+    uint4* r = reinterpret_cast<uint4*>(sm.ring);
+    const int n16 = p.n_stages * (kStageBytes / 16);
+    for (int i = tid; i < n16; i += kThreads) r[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
   }
   __syncthreads();
 
   if (tid >= kConsumerThreads) {
     // ------------------------------ producer warp ------------------------------
-    if (tid == kConsumerThreads) {
-      const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
-      unsigned tile_it = 0;
-      for (int iter = 0; iter < p.n_iters; ++iter) {
-        if (iter > 0) {
-          Spin s;
-          int go;
-          while ((go = ld_volatile_shared_i32(&sm.ctl[0])) >= 0 && go < iter) {
-            __nanosleep(32);
-            s.tick(p, DE_HANDSHAKE, -1, iter);
-          }
-          if (go < 0) break;
-        }
-        for (int i = 0; i < p.n_phases; ++i) {
-          const Phase& ph = sm.prog[i];
-          if (ph.type == PH_GEMV) gemv_phase_produce(ph, p, smem_raw, tile_it, i, pol_stream, pol_keep);
-        }
+    const int lane = tid & 31;
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    RingCur cur{0, 0u};
+    uint32_t issued = 0;
+    bool ok = true;
+    for (int iter = 0; iter < p.n_iters && ok; ++iter) {
+      for (int i = 0; i < p.n_phases && ok; ++i) {
+        const Phase ph = load_phase(p.prog, i);
+        if (ph.type == PH_GEMV) ok = gemv_phase_produce<PROF>(c, ph, p, sm.ctl, cur, issued, i, pol_stream, pol_keep, lane);
+      }
+    }
+    // drain: shared memory must not be released with bulk copies in flight (the frame loop may stop early)
+    if (lane == 0) {
+      const int n = (int)min(issued, (uint32_t)p.n_stages);
+      RingCur d = cur;
+      for (int k = 0; k < n; ++k) {
+        if (d.slot == 0) { d.slot = p.n_stages - 1; d.lap ^= 1u; } else { --d.slot; }
+        mbar_wait(&sm.full[d.slot], d.lap, p, DE_FULL_WAIT, -3);
       }
     }
     return;
   }
 
   // -------------------------------- consumer warps --------------------------------
-  unsigned tile_it = 0;
+  RingCur cur{0, 0u};
   int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
   int* frame_done = sm.ctl + 12;  // [4]
   for (int iter = 0; iter < p.n_iters; ++iter) {
@@ -1286,29 +1640,33 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
           done = __ldcg(&st->done);
           pos = __ldcg(&st->position);
         } else {
-          done = __float_as_int(ll_wait(&st->ctl[0], ep0, p, -2));
-          pos = __float_as_int(ll_wait(&st->ctl[1], ep0, p, -2));
+          done = (int)ll_wait(&st->ctl[0], ep0, p, -2);
+          pos = (int)ll_wait(&st->ctl[1], ep0, p, -2);
         }
         frame_pos[tid] = pos;
         frame_done[tid] = done;
       }
       cbar_sync();
-      if (p.mode == MODE_FRAMES) {
+      if (p.mode == MODE_FRAMES && iter > 0) {
         int all_done = 1;
         for (int b = 0; b < p.n_rows; ++b) all_done &= (frame_done[b] != 0);
-        if (iter > 0 && tid == 0) st_volatile_shared_i32(&sm.ctl[0], all_done ? -1 : iter);
-        if (all_done && iter > 0) break;
+        if (all_done) {
+          if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], -1);  // tells the producer (which prefetches across frames) to stop
+          break;
+        }
       }
     }
+    Phase ph = load_phase(p.prog, 0);
     for (int i = 0; i < p.n_phases; ++i) {
-      const Phase& ph = sm.prog[i];
+      const Phase nxt = load_phase(p.prog, (i + 1 < p.n_phases) ? i + 1 : 0);  // in flight while this phase runs
       const uint32_t ep = ep0 + (uint32_t)i + 1u;
       switch (ph.type) {
-        case PH_GEMV: gemv_phase_consume(ph, p, smem_raw, tile_it, i, ep); break;
-        case PH_ATTN: if (!(p.debug & 4)) attn_phase(ph, p, smem_raw, ep, i, frame_pos); break;
+        case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, cur, i, ep); break;
+        case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
         case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
         default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
       }
+      ph = nxt;
     }
   }
 }
@@ -1318,7 +1676,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
 __global__ void __launch_bounds__(kConsumerThreads, 1)
 fq3_sample_kernel(const float* logits, SampleArgs a, const long long* history, int n_history, uint8_t* seen_scratch,
                   long long* out) {
-  __shared__ __align__(16) unsigned char scratch[kScratchBytes];
+  __shared__ __align__(16) unsigned char scratch[24 * 1024];
   const SampleScratch sc = sample_scratch(scratch);
   if (history && n_history > 0 && a.rep_pen != 1.0f) {
     for (int i = threadIdx.x; i < a.V; i += kConsumerThreads) seen_scratch[i] = 0;
@@ -1393,26 +1751,34 @@ __global__ void fq3_codes_to_i64_kernel(const int* cur_codes, int n, long long* 
   if (threadIdx.x < n) out[threadIdx.x] = cur_codes[threadIdx.x + 1];
 }
 
-// Plain bf16 rows -> LL words (epoch 0: "written before launch") and back.
+// Plain bf16 rows -> packed LL words (epoch 0: "written before launch") and back.  cols is even; ld_* in words / elements.
 __global__ void fq3_pack_ll_kernel(LLWord* dst, int ld_dst, const bf16* src, int ld_src, int rows, int cols) {
-  const size_t n = (size_t)rows * cols;
+  const int cw = cols >> 1;
+  const size_t n = (size_t)rows * cw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / cols, c = i - r * cols;
-    dst[r * ld_dst + c] = make_uint2(__float_as_uint(__bfloat162float(src[r * ld_src + c])), 0u);
+    const size_t r = i / cw, c = i - r * cw;
+    const uint32_t lo = __bfloat16_as_ushort(src[r * ld_src + 2 * c]), hi = __bfloat16_as_ushort(src[r * ld_src + 2 * c + 1]);
+    dst[r * ld_dst + c] = make_uint2(lo | (hi << 16), 0u);
   }
 }
 __global__ void fq3_unpack_ll_bf16_kernel(bf16* dst, int ld_dst, const LLWord* src, int ld_src, int rows, int cols) {
-  const size_t n = (size_t)rows * cols;
+  const int cw = cols >> 1;
+  const size_t n = (size_t)rows * cw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / cols, c = i - r * cols;
-    dst[r * ld_dst + c] = __float2bfloat16_rn(__uint_as_float(src[r * ld_src + c].x));
+    const size_t r = i / cw, c = i - r * cw;
+    const uint32_t pay = src[r * ld_src + c].x;
+    dst[r * ld_dst + 2 * c] = __ushort_as_bfloat16((unsigned short)(pay & 0xffffu));
+    dst[r * ld_dst + 2 * c + 1] = __ushort_as_bfloat16((unsigned short)(pay >> 16));
   }
 }
 __global__ void fq3_unpack_ll_f32_kernel(float* dst, int ld_dst, const LLWord* src, int ld_src, int rows, int cols) {
-  const size_t n = (size_t)rows * cols;
+  const int cw = cols >> 1;
+  const size_t n = (size_t)rows * cw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / cols, c = i - r * cols;
-    dst[r * ld_dst + c] = __uint_as_float(src[r * ld_src + c].x);
+    const size_t r = i / cw, c = i - r * cw;
+    const uint32_t pay = src[r * ld_src + c].x;
+    dst[r * ld_dst + 2 * c] = bf_lo(pay);
+    dst[r * ld_dst + 2 * c + 1] = bf_hi(pay);
   }
 }
 

@@ -15,27 +15,35 @@ eng.prefill(0, tie[0].cuda(), 0, pol)
 x = torch.randn(cfg.talker.hidden_size).to(torch.bfloat16).cuda()
 for _ in range(3): eng.talker_step(0, x, 14, want_logits=False)
 torch.cuda.synchronize()
-buf = (C.c_longlong * (1024 * 8))()
-eng.lib.fq3_debug_read_prof(eng.h, buf, 1024 * 8)   # clear
+buf = (C.c_longlong * (512 * 16))()
+eng.lib.fq3_debug_read_prof(eng.h, buf, 512 * 16)   # clear
 eng.talker_step(0, x, 14, want_logits=False)
-eng.lib.fq3_debug_read_prof(eng.h, buf, 1024 * 8)
+eng.lib.fq3_debug_read_prof(eng.h, buf, 512 * 16)
 n = 141
 names = {0: "qkv", 1: "attn", 2: "o", 3: "gu", 4: "down"}
-t0 = min(buf[i * 8] for i in range(n) if buf[i * 8])
-print("phase kind     start  d(load/step1) d(tiles/sweep) d(tail)   [cycles]")
-agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0])
+S = 16
+t0 = min(buf[i * S] for i in range(n) if buf[i * S])
+print("GEMV: poll = wait for input words; norm = barrier+rescale+barrier; ring = wait full; mma; pst = partial store; rest = other rounds;")
+print("      bar = barrier; f0 = finish prologue; sum; epi; st; tail")
+hdr = f"{'ph':>4s} {'kind':5s} {'start':>9s} " + " ".join(f"{x:>6s}" for x in ["poll", "norm", "ring", "mma", "pst", "rest", "bar", "f0", "sum", "epi", "st", "tail"])
+print(hdr)
+agg = collections.defaultdict(lambda: [0] + [0] * 13)
 prev_end = None
 for i in range(n):
-    m = [buf[i * 8 + k] for k in range(4)]
+    m = [buf[i * S + k] for k in range(S)]
     if m[0] == 0: continue
     kind = names.get(i % 5, "?") if i < 140 else "head"
-    d = [m[1] - m[0], m[2] - m[1], m[3] - m[2]]
-    pr = [buf[i * 8 + 4], buf[i * 8 + 5]]
-    if i < 12: print("       gemv_tile cycles", buf[i * 8 + 6], "calls", buf[i * 8 + 7])
-    if i < 12 or i >= 136: print(f"{i:4d} {kind:5s} {m[0]-t0:9d} {d[0]:9d} {d[1]:9d} {d[2]:9d}   producer first/last issue at {pr[0]-t0 if pr[0] else 0:9d} {pr[1]-t0 if pr[1] else 0:9d}")
-    a = agg[kind]; a[0] += 1; a[1] += d[0]; a[2] += d[1]; a[3] += d[2]
-    if prev_end is not None: a[4] += m[0] - prev_end
+    if kind == "attn":
+        d = [m[1] - m[0], m[2] - m[1], m[3] - m[2]] + [0] * 9
+    else:
+        d = [m[7] - m[0], m[1] - m[7], m[8] - m[1], m[9] - m[8], m[10] - m[9], m[6] - m[10], m[2] - m[6],
+             m[11] - m[2], m[12] - m[11], m[13] - m[12], m[14] - m[13], m[3] - m[14]]
+    if i < 12 or i >= 136:
+        print(f"{i:4d} {kind:5s} {m[0]-t0:9d} " + " ".join(f"{x:6d}" for x in d) + f"   prod {m[4]-t0 if m[4] else 0} {m[5]-t0 if m[5] else 0}")
+    a = agg[kind]; a[0] += 1
+    for k in range(12): a[1 + k] += d[k]
+    if prev_end is not None: a[13] += m[0] - prev_end
     prev_end = m[3]
-print("kind    n  avg load/step1  avg tiles/sweep  avg tail  avg gap-before")
-for k, a in agg.items(): print(f"{k:5s} {a[0]:3d} {a[1]/a[0]:12.0f} {a[2]/a[0]:14.0f} {a[3]/a[0]:10.0f} {a[4]/a[0]:12.0f}")
-last = max(buf[i * 8 + 3] for i in range(n)); print("total cycles", last - t0)
+print("averages (last column: gap before the phase)")
+for k, a in agg.items(): print(f"{k:5s} {a[0]:3d}           " + " ".join(f"{a[1+j]/a[0]:6.0f}" for j in range(12)) + f" {a[13]/a[0]:8.0f}")
+last = max(buf[i * S + 3] for i in range(n)); print("total cycles", last - t0)
