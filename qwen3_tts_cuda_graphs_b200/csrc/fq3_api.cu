@@ -215,7 +215,7 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   p.pred_logits_all = nullptr;
   p.pos_override = -1;
   p.watchdog_ns = e->watchdog_ns;
-  p.debug = 0;
+  p.debug = (4 << 16) | 32;  // poll back-off: sleep 32 ns after 4 immediate retries (FQ3_DEBUG = tries << 16 | ns)
   p.prof = e->prof;
   p.prof_cta = e->prof_cta;
   if (const char* d = getenv("FQ3_DEBUG")) p.debug = atoi(d);
@@ -236,14 +236,17 @@ int check_device_fault(fq3_engine* e) {
 
 // Launch the persistent kernel: one CTA per SM, cooperative (all CTAs must be co-resident: they poll each other's words).
 // smem: header | scratch | activation staging buffer (xrows x kmax bf16) | weight ring (16 KB stages, everything that is left).
-int launch(fq3_engine* e, LaunchParams& p, size_t x_elems, cudaStream_t s) {
+int launch(fq3_engine* e, LaunchParams& p, size_t x_elems, size_t gamma_elems, cudaStream_t s) {
   if (int r = check_device_fault(e)) return r;
   p.xbuf_bytes = (int)round_up(x_elems * 2, 1024);
-  long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - (long)p.xbuf_bytes;
+  p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 1024);
+  p.gam_bytes = (int)round_up(gamma_elems * 2, 1024);
+  long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - (long)p.xbuf_bytes - (long)p.prog_bytes - (long)kGammaSlots * p.gam_bytes;
   if (e->ring_cap > 0) avail = std::min(avail, e->ring_cap);
   p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
   if (p.n_stages < 4) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
-  const size_t smem = kHeaderBytes + kScratchBytes + (size_t)p.xbuf_bytes + (size_t)p.n_stages * kStageBytes;
+  const size_t smem = kHeaderBytes + kScratchBytes + (size_t)p.prog_bytes + (size_t)kGammaSlots * p.gam_bytes + (size_t)p.xbuf_bytes +
+                      (size_t)p.n_stages * kStageBytes;
   // LL epochs: phase i of iteration it carries epoch_base + it*n_phases + i + 1
   const uint64_t span = (uint64_t)p.n_iters * (uint64_t)p.n_phases + 2;
   if ((uint64_t)e->epoch + span >= 0xFFFFFF00ull) {
@@ -555,7 +558,8 @@ int fq3_set_loop_state(fq3_engine* e, int idx, int token, const void* past_hidde
 
 static int prefill_rows(const fq3_engine* e) {
   // rows per pass are bounded by the activation staging buffer: keep a ring of >= 6 stages
-  const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - 6L * kStageBytes;
+  const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - (long)round_up((size_t)e->n_prefill_ph * sizeof(Phase), 1024) -
+                     (long)kGammaSlots * (long)round_up((size_t)e->tk.d.hidden * 2, 1024) - 6L * kStageBytes;
   const long rows = avail / ((long)e->tk.kmax() * 2);
   return (int)std::max<long>(1, std::min<long>(rows, kMaxRows));
 }
@@ -597,7 +601,7 @@ int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pa
     p.stream0 = idx;
     p.pf_pos0 = c0; p.pf_n_pad = n_left_pad; p.pf_rope_delta = -n_left_pad; p.pf_final = final;
     p.pol = to_policy(policy);
-    if (int r = launch(e, p, (size_t)rows * e->tk.kmax(), s)) return r;
+    if (int r = launch(e, p, (size_t)rows * e->tk.kmax(), e->tk.d.hidden, s)) return r;
   }
   fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, T, 0, 8, 0, 0, 0);
   e->launches += 1;
@@ -622,7 +626,7 @@ int fq3_talker_step(fq3_engine* e, int idx, const void* embeds, int position, vo
   p.n_rows = 1;
   p.stream0 = idx;
   p.pos_override = position;
-  if (int r = launch(e, p, decode_x_elems(e, 1, true, false), s)) return r;
+  if (int r = launch(e, p, decode_x_elems(e, 1, true, false), e->tk.d.hidden, s)) return r;
   if (out_hidden) CK(cudaMemcpyAsync(out_hidden, e->bufs[BUF_HID], (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
   if (out_logits)
     if (int r = unpack_f32(e, out_logits, e->tk.d.vocab, BUF_LOGITS, 0, 1, e->tk.d.vocab, s)) return r;
@@ -646,7 +650,7 @@ int fq3_predictor_run(fq3_engine* e, int idx, const void* pred_input, const fq3_
   p.sub = to_sub(sub);
   p.pol.seed = seed;
   p.pred_logits_all = out_logits ? e->pred_logits_all : nullptr;
-  if (int r = launch(e, p, decode_x_elems(e, 1, false, true), s)) return r;
+  if (int r = launch(e, p, decode_x_elems(e, 1, false, true), e->pr.d.hidden, s)) return r;
   fq3_codes_to_i64_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(e->d_st + idx) +
                                                                          offsetof(StreamState, cur_codes)),
                                            e->ncb, reinterpret_cast<long long*>(out_codes_i64));
@@ -703,7 +707,7 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
   p.n_iters = n_frames;
   p.pol = to_policy(policy);
   p.sub = to_sub(sub);
-  return launch(e, p, decode_x_elems(e, n_streams, true, true), (cudaStream_t)stream);
+  return launch(e, p, decode_x_elems(e, n_streams, true, true), std::max(e->tk.d.hidden, e->pr.d.hidden), (cudaStream_t)stream);
 }
 
 int fq3_get_status(fq3_engine* e, int idx, fq3_status* out, void* stream) {
@@ -783,7 +787,7 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
   }
   p.lin_W = W; p.lin_gamma = gamma; p.lin_bias = bias; p.lin_eps = eps;
   p.plans[kMaxPlans - 1] = lin_plan;
-  if (int r = launch(e, p, (size_t)M * K, s)) return r;
+  if (int r = launch(e, p, (size_t)M * K, (flags & 1) ? (size_t)K : 0, s)) return r;
   if (flags & 16) return unpack_f32(e, y, No, BUF_LIN_OUT, 0, M, No, s);
   return unpack_bf16(e, y, No, BUF_LIN_OUT, 0, M, No, s);
 }

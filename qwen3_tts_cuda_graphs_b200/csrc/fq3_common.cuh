@@ -38,11 +38,14 @@ constexpr int kMaxVocab = 5120;            // sampling scratch holds V fp32 logi
 //          attention q rows fp32 [2][128] | fresh K/V rows bf16 [8][2][128] | warp partials [12][2][132] = 17.4 KB;
 //          sampling 20 KB logits + histogram + reductions = 21.5 KB
 constexpr int kScratchBytes = 24 * 1024;
-// smem header: full[16] | empty[16] | ctl[16] | red[8][16]
+// smem header: full[16] | empty[16] | ctl[16] | red[8][16] | gfull[4] | gempty[4]
 constexpr int kEmptyOffset = 128;
 constexpr int kCtlOffset = 256;
 constexpr int kRedOffset = 320;
+constexpr int kGFullOffset = 832;
+constexpr int kGEmptyOffset = 864;
 constexpr int kHeaderBytes = 1024;
+constexpr int kGammaSlots = 4;             // norm-weight vectors in flight (streamed by the producer like the weights)
 constexpr int kMaxPlans = 24;
 
 // ---- LL (low-latency) activation words ---------------------------------------------------------
@@ -180,7 +183,7 @@ struct LaunchParams {
   const void* lin_bias;
   float lin_eps;
   // smem carve-up
-  int n_stages, xbuf_bytes;  // ring stages of 16 KB; bytes of the activation staging buffer
+  int n_stages, xbuf_bytes, prog_bytes, gam_bytes;  // ring stages of 16 KB; bytes of the activation staging buffer / of the program copy / of ONE norm-weight slot (1 KB multiples)
   Plan plans[kMaxPlans];
   unsigned epoch_base;  // LL epoch of the phase before this launch's first phase
   unsigned long long watchdog_ns;

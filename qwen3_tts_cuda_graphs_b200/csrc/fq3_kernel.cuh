@@ -64,6 +64,12 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// a fixed 40 % of the lines stay (evict_last), the rest is streamed: weights that are re-read every pass but exceed L2
+__device__ __forceinline__ uint64_t policy_keep_fraction() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.4;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -143,6 +149,8 @@ struct Smem {
   int* ctl;          // [0] producer go flag, [8..11] frame positions, [12..15] frame done flags
   float* red;        // [kMaxRows][16] RMSNorm partial sums
   unsigned char* scratch;
+  Phase* prog;       // copy of the phase program (a global read per phase would sit on the critical path)
+  unsigned char* gam;  // [kGammaSlots][gam_bytes] norm weights, streamed by the producer
   unsigned char* xbuf;
   unsigned char* ring;
 };
@@ -154,8 +162,10 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base, const LaunchPara
   s.ctl = reinterpret_cast<int*>(base + kCtlOffset);
   s.red = reinterpret_cast<float*>(base + kRedOffset);
   s.scratch = base + kHeaderBytes;
-  s.xbuf = s.scratch + kScratchBytes;
-  s.ring = s.xbuf + p.xbuf_bytes;  // header + scratch are 1 KB multiples and xbuf_bytes is a multiple of 1 KB
+  s.prog = reinterpret_cast<Phase*>(s.scratch + kScratchBytes);
+  s.gam = s.scratch + kScratchBytes + p.prog_bytes;
+  s.xbuf = s.gam + kGammaSlots * p.gam_bytes;
+  s.ring = s.xbuf + p.xbuf_bytes;  // header, scratch, program, norm-weight slots and xbuf are 1 KB multiples
   return s;
 }
 
@@ -246,6 +256,15 @@ __device__ __forceinline__ uint2 ldg_keep_u2(const void* ptr, uint64_t pol) {
   return v;
 }
 
+__device__ __forceinline__ Phase load_phase(const Phase* prog_smem, int i) {
+  // uniform shared-memory address: two broadcast 16-byte reads
+  union { Phase ph; uint4 q[2]; } u;
+  const uint32_t a = smem_u32(prog_smem + i);
+  u.q[0] = lds128(a);
+  u.q[1] = lds128(a + 16u);
+  return u.ph;
+}
+
 // =================================================================================================
 // GEMV phase, consumer side
 //
@@ -255,8 +274,10 @@ __device__ __forceinline__ uint2 ldg_keep_u2(const void* ptr, uint64_t pol) {
 // poll loads and looking at their result — that window (an L2 round trip) is otherwise idle.
 // =================================================================================================
 struct Ctx {  // per-thread constants (shared-memory addresses as 32-bit shared-window offsets)
-  uint32_t full, empty, red, scratch, xs, ring;
-  int n_stages;
+  uint32_t full, empty, red, scratch, xs, ring, gfull, gempty, gam;
+  int n_stages, gam_bytes;
+  uint64_t keep;  // L2 evict_last policy for the small read-mostly tables (norm weights, rope rows)
+  const Phase* prog;
 };
 __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchParams& p) {
   const Smem sm = carve_smem(smem_base, p);
@@ -268,6 +289,12 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchPa
   c.xs = smem_u32(sm.xbuf);
   c.ring = smem_u32(sm.ring);
   c.n_stages = p.n_stages;
+  c.gfull = smem_u32(smem_base + kGFullOffset);
+  c.gempty = smem_u32(smem_base + kGEmptyOffset);
+  c.gam = smem_u32(sm.gam);
+  c.gam_bytes = p.gam_bytes;
+  c.keep = policy_evict_last();
+  c.prog = sm.prog;
   return c;
 }
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
@@ -313,7 +340,7 @@ struct RingCur {
 // General activation load (several rows, or rows too long for the register path): raw payloads go through shared
 // memory, each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square,
 // x*rsqrt -> bf16, * weight -> bf16.
-__device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, const bf16* gamma, float eps,
+__device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
                                             int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red) {
   const int Kw = K >> 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -371,7 +398,7 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
     const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
 #pragma unroll 1
     for (int wi = tid; wi < Kw; wi += kConsumerThreads) {
-      const uint32_t gg = __ldg(reinterpret_cast<const uint32_t*>(gamma) + wi);
+      const uint32_t gg = lds_u32(gam + (uint32_t)wi * 4u);
       const uint32_t v = lds_u32(xs + (uint32_t)(m * Kw + wi) * 4u);
       const uint32_t y = pack_bf16x2(bf16r(bf16r(bf_lo(v) * rs) * bf_lo(gg)), bf16r(bf16r(bf_hi(v) * rs) * bf_hi(gg)));
       sts_u32(xs + (uint32_t)(m * Kw + wi) * 4u, y);
@@ -452,28 +479,32 @@ __device__ __forceinline__ Slab get_slab(const Phase& ph, const LaunchParams& p)
 // Partial sums of one batch in shared memory: part[((tile * M + m) * 8 + n) * (nkq * 4) + kq * 4 + wk] — the nkq*4 partial
 // sums of one output row are contiguous, so the finishing thread reads them with 16-byte loads in a fixed order.
 template <bool PROF>
-__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, int pidx, uint32_t ep) {
+__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, RingCur& gcur, int pidx,
+                                                   uint32_t ep) {
   const uint32_t flags = ph.flags;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int M = (flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows, row_off = 0;
   if (flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
   const uint32_t ep_in = (pidx == 0 && ep == p.epoch_base + 1) ? 0u : ep - 1;
-  const int K = (int)ph.K, Kw = K >> 1;
+  const int K = (int)ph.K;
   const int ldin = p.ld[ph.in_buf];
   const LLWord* in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]) + (size_t)row_off * ldin;
   const bool norm = (flags & F_PRENORM) != 0;
-  constexpr int kXW = 4;  // words per thread held in registers on the one-row path: K <= 3072
+  constexpr int kXW = 4;  // 8-byte words per thread held in registers on the one-row path: K <= 2 * kXW * 384 = 3072
+  const int Kw = K >> 1;  // words per row
   const bool fast = (M == 1) && (Kw <= kXW * kConsumerThreads);
   if (PROF) prof_mark(p, pidx, 0);
 
-  // ---- issue the first poll of this thread's input words
+  // ---- issue the first poll of this thread's input words (word tid + i * 384 holds elements 2w, 2w+1)
   LLWord w[kXW];
+  const LLWord* src = in + tid;
+  bool have[kXW];
   if (fast) {
 #pragma unroll
     for (int i = 0; i < kXW; ++i) {
-      const int wi = tid + i * kConsumerThreads;
+      have[i] = tid + i * kConsumerThreads < Kw;
       w[i] = make_uint2(0u, ep_in);
-      if (wi < Kw) w[i] = ll_ld(in + wi);
+      if (have[i]) w[i] = ll_ld(src + i * kConsumerThreads);
     }
   }
 
@@ -483,19 +514,11 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const int ro = pl.ro, tpb = pl.tpb, nkq = sb.nkq;
   const int grp = warp >> 2, wk = warp & 3;
   const int g = lane >> 2, t = lane & 3, h0 = g & 1;
-  const bf16* gamma = nullptr;
-  uint32_t gm[kXW];
-  if (norm) {
-    gamma = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_gamma) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16);
-    if (fast) {
-#pragma unroll
-      for (int i = 0; i < kXW; ++i) {
-        const int wi = tid + i * kConsumerThreads;
-        gm[i] = 0x3f803f80u;
-        if (wi < Kw) gm[i] = __ldg(reinterpret_cast<const uint32_t*>(gamma) + wi);
-      }
-    }
-  }
+  // norm weights arrive through the producer's stream (slot gcur of the small gamma ring)
+  const uint32_t gslot = c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes;
+  const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
+  const uint32_t glap = gcur.lap;
+  if (norm) gcur.advance(1, kGammaSlots);
   const float eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
   // finishing thread t owns (word wl, row m) of the first batch: residual / bias words are fetched now
   const int fin_total = sb.n_su * M;
@@ -525,28 +548,24 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   if (fast) {
     if (ep_in != 0) {
       unsigned tries = 0;
-      Spin spin;
       while (true) {
         bool bad = false;
 #pragma unroll
         for (int i = 0; i < kXW; ++i) bad |= (w[i].y != ep_in);
         if (!bad) break;
-        if (++tries > 4) __nanosleep(32);
-        spin.tick(p, DE_LL_WAIT, pidx, (int)ep_in);
+        if (++tries > (unsigned)(p.debug >> 16)) __nanosleep((unsigned)(p.debug & 0xffff));
+        if (tries > (unsigned)(p.watchdog_ns >> 8)) device_fault(p, DE_LL_WAIT, pidx, (int)ep_in);
 #pragma unroll
-        for (int i = 0; i < kXW; ++i) {
-          const int wi = tid + i * kConsumerThreads;
-          if (wi < Kw && w[i].y != ep_in) w[i] = ll_ld(in + wi);
-        }
+        for (int i = 0; i < kXW; ++i)
+          if (have[i] && w[i].y != ep_in) w[i] = ll_ld(src + i * kConsumerThreads);
       }
     }
     if (PROF) prof_mark(p, pidx, 7);
+    const uint32_t xdst = c.xs + (uint32_t)tid * 4u;
     if (!norm) {
 #pragma unroll
-      for (int i = 0; i < kXW; ++i) {
-        const int wi = tid + i * kConsumerThreads;
-        if (wi < Kw) sts_u32(c.xs + (uint32_t)wi * 4u, w[i].x);
-      }
+      for (int i = 0; i < kXW; ++i)
+        if (have[i]) sts_u32(xdst + (uint32_t)i * (kConsumerThreads * 4), w[i].x);
       cbar_sync();
     } else {
       float ss = 0.f;
@@ -567,19 +586,38 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       }
       const float rs = rsqrtf(tot / (float)K + eps);
       const bool wr = (flags & F_WRITE_NORMED) && blockIdx.x == 0;
+      if (!mbar_try_wait_a(gfullb, glap)) {
+        Spin spin;
+        while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100 + gcur.slot);
+      }
+      uint32_t gm[kXW];
 #pragma unroll
       for (int i = 0; i < kXW; ++i) {
-        const int wi = tid + i * kConsumerThreads;
-        if (wi < Kw) {
-          const uint32_t y = pack_bf16x2(bf16r(bf16r(bf_lo(w[i].x) * rs) * bf_lo(gm[i])), bf16r(bf16r(bf_hi(w[i].x) * rs) * bf_hi(gm[i])));
-          sts_u32(c.xs + (uint32_t)wi * 4u, y);
-          if (wr) reinterpret_cast<uint32_t*>(p.bufs[BUF_HID])[wi] = y;
+        gm[i] = 0x3f803f80u;
+        if (have[i]) gm[i] = lds_u32(gslot + (uint32_t)(tid + i * kConsumerThreads) * 4u);
+      }
+#pragma unroll
+      for (int i = 0; i < kXW; ++i) {
+        if (have[i]) {
+          const uint32_t a0 = w[i].x;
+          const uint32_t y0 = pack_bf16x2(bf16r(bf16r(bf_lo(a0) * rs) * bf_lo(gm[i])), bf16r(bf16r(bf_hi(a0) * rs) * bf_hi(gm[i])));
+          sts_u32(xdst + (uint32_t)i * (kConsumerThreads * 4), y0);
+          if (wr) reinterpret_cast<uint32_t*>(p.bufs[BUF_HID])[tid + i * kConsumerThreads] = y0;
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(gemptyb);
       cbar_sync();  // xs complete; also protects red[] against the next phase
     }
   } else {
-    load_x_general(p, flags, in, ldin, gamma, eps, K, M, ep_in, pidx, c.xs, c.red);
+    if (norm && !mbar_try_wait_a(gfullb, glap)) {
+      Spin spin;
+      while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100 + gcur.slot);
+    }
+    load_x_general(p, flags, in, ldin, gslot, eps, K, M, ep_in, pidx, c.xs, c.red);
+    if (norm) {  // load_x_general ends with a barrier after the last read of the norm weights
+      if (lane == 0) mbar_arrive_a(gemptyb);
+    }
   }
   if (PROF) prof_mark(p, pidx, 1);
 
@@ -641,6 +679,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
           bias = __ldg(reinterpret_cast<const uint32_t*>(bp) + sb.su0 + wl);
         }
       }
+      if (PROF) prof_mark(p, pidx, 10);
       const int rr0 = wl * ro - tile0 * kStageRows;  // first row of the word inside the batch
       float y[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -657,6 +696,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
           y[r] = s;
         }
       }
+      if (PROF) prof_mark(p, pidx, 11);
       float lo, hi;
       if (flags & F_SWIGLU) {
         lo = bf16r(bf16r(silu_f(bf16r(y[0]))) * bf16r(y[1]));
@@ -668,7 +708,9 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
         if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
       }
       if (flags & F_RESID) { lo = bf16r(bf_lo(res) + lo); hi = bf16r(bf_hi(res) + hi); }
+      if (PROF) prof_mark(p, pidx, 12);
       ll_st(out + (size_t)m * ldout + sb.su0 + wl, pack_bf16x2(lo, hi), ep);
+      if (PROF) prof_mark(p, pidx, 13);
     }
     base.advance(s_count, c.n_stages);
     if (tile0 + tpb < sb.n_tiles) cbar_sync();  // the next batch overwrites the partial sums
@@ -681,8 +723,8 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
 // per mbarrier.  When a stage is contiguous in HBM (K == 1024) one bulk copy moves it, otherwise one copy per row.
 // Returns false when the consumers asked to stop (frame loop finished early).
 template <bool PROF>
-__device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph, const LaunchParams& p, int* ctl, RingCur& cur, uint32_t& issued,
-                                                   int pidx, uint64_t pol_stream, uint64_t pol_keep, int lane) {
+__device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph, const LaunchParams& p, int* ctl, RingCur& cur, RingCur& gcur, uint32_t& issued,
+                                                   uint32_t& gissued, int pidx, uint64_t pol_stream, uint64_t pol_keep, uint64_t pol_gamma, int lane) {
   const Slab sb = get_slab(ph, p);
   const int K = (int)ph.K;
   const uint32_t row_bytes = (uint32_t)K * 2u;
@@ -690,6 +732,28 @@ __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph
                            (size_t)sb.su0 * p.plans[ph.plan].ro * row_bytes;
   const uint64_t pol = (ph.flags & F_L2_KEEP) ? pol_keep : pol_stream;
   if (PROF && (int)blockIdx.x == p.prof_cta && lane == 0 && pidx < 512) p.prof[(size_t)pidx * 16 + 4] = clock64();
+  if (ph.flags & F_PRENORM) {
+    // the phase's norm weights travel in the same stream, ahead of its first stage
+    const unsigned char* gp = (ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_gamma) : p.arena + (size_t)ph.g_off * 16;
+    const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
+    int stop = 0;
+    if (lane == 0) {
+      Spin spin;
+      if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
+      while (!stop && !mbar_try_wait_a(gemptyb, gcur.lap ^ 1u)) {
+        if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
+        spin.tick(p, DE_EMPTY_WAIT, pidx, 100 + gcur.slot);
+      }
+      if (!stop) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfullb), "r"(row_bytes) : "memory");
+        bulk_g2s_a(c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes, gp, row_bytes, gfullb, pol_gamma);
+      }
+    }
+    stop = __shfl_sync(0xffffffffu, stop, 0);
+    if (stop) return false;
+    gcur.advance(1, kGammaSlots);
+    ++gissued;
+  }
 #pragma unroll 1
   for (int tile = 0; tile < sb.n_tiles; ++tile) {
     const int rows = min(kStageRows, sb.n_rows - tile * kStageRows);
@@ -770,9 +834,10 @@ struct RopeRegs {
 // issued before the q/k words are polled, so the table reads overlap the wait
 __device__ __forceinline__ RopeRegs rope_load(const bf16* gamma, const bf16* cosp, const bf16* sinp, int lane) {
   RopeRegs r;
-  r.g2 = __ldg(reinterpret_cast<const uint2*>(gamma + lane * 4));
-  r.c2 = __ldg(reinterpret_cast<const uint2*>(cosp + lane * 4));
-  r.s2 = __ldg(reinterpret_cast<const uint2*>(sinp + lane * 4));
+  const uint64_t keep = policy_evict_last();
+  r.g2 = ldg_keep_u2(gamma + lane * 4, keep);
+  r.c2 = ldg_keep_u2(cosp + lane * 4, keep);
+  r.s2 = ldg_keep_u2(sinp + lane * 4, keep);
   return r;
 }
 __device__ __forceinline__ void head_norm_rope(float (&x)[4], const RopeRegs& rr, float eps, int lane) {
@@ -1070,25 +1135,43 @@ __device__ __forceinline__ void attn_combine(const Phase& ph, const LaunchParams
   }
 }
 
+// exact a / b for 0 <= a < 2^20, 1 <= b < 2^12 (the +0.5 keeps the float quotient away from integer boundaries)
+__device__ __forceinline__ int small_div(int a, int b) { return (int)__fdividef((float)a + 0.5f, (float)b); }
+
 template <bool PROF>
 __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
                                            const int* frame_pos) {
   const StackRt& S = p.stacks[ph.stack];
   const int G = gridDim.x, cta = blockIdx.x;
   const int ng = num_groups(p);
+  if (ng == 1 && p.mode != MODE_PREFILL && !(ph.flags & F_ROWS2)) {
+    // one stream, one row (every decode phase except predictor pass 0): items = kv heads x splits, spread over the grid
+    const Group gr = get_group(ph, p, 0, frame_pos);
+    const int cap = max(1, min(small_div(G, S.nkv), kMaxSplits));
+    const int nsplit = num_splits(gr.pos0 + 1 - gr.n_pad, cap);
+    const int total = S.nkv * nsplit;
+    const int stride = max(1, small_div(G, total));
+    const int q = small_div(cta, stride);
+    if (cta == q * stride && q < total) {
+      const int kvh = small_div(q, nsplit), sp = q - kvh * nsplit;
+      attn_row<PROF>(ph, p, smem_base, gr, 0, kvh, sp, nsplit, ep, pidx);
+      if (nsplit > 1 && sp == 0) attn_combine(ph, p, gr, 0, kvh, nsplit, ep, pidx);
+    }
+    return;
+  }
   int nrows_tot = 0;
   for (int g = 0; g < ng; ++g) nrows_tot += get_group(ph, p, g, frame_pos).nrows;
-  const int cap = max(1, min(G / max(1, nrows_tot * S.nkv), kMaxSplits));
+  const int cap = max(1, min(small_div(G, max(1, nrows_tot * S.nkv)), kMaxSplits));
   int total = 0;
   for (int g = 0; g < ng; ++g) {
     const Group gr = get_group(ph, p, g, frame_pos);
     for (int r = 0; r < gr.nrows; ++r) total += S.nkv * num_splits(gr.pos0 + r + 1 - gr.n_pad, cap);
   }
   // item -> CTA: spread the items over the whole grid (stride) so concurrent items sit on distant SMs
-  const int stride = (total <= G) ? G / total : 1;
+  const int stride = (total <= G) ? small_div(G, total) : 1;
   int first, step;
   if (stride > 1) {
-    const int q = cta / stride;
+    const int q = small_div(cta, stride);
     first = (cta - q * stride == 0 && q < total) ? q : total;
     step = total;
   } else {
@@ -1105,7 +1188,7 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& 
         const int nitems = S.nkv * nsplit;
         if (item < base + nitems) {
           const int it = item - base;
-          const int kvh = it / nsplit, sp = it - kvh * nsplit;
+          const int kvh = small_div(it, nsplit), sp = it - kvh * nsplit;
           attn_row<PROF>(ph, p, smem_base, gr, r, kvh, sp, nsplit, ep, pidx);
           if (nsplit > 1 && sp == 0) attn_combine(ph, p, gr, r, kvh, nsplit, ep, pidx);
           found = true;
@@ -1566,15 +1649,6 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
 // =================================================================================================
 // Kernel
 // =================================================================================================
-__device__ __forceinline__ Phase load_phase(const Phase* prog, int i) {
-  // uniform address: one L1-resident 32-byte read, broadcast to the warp
-  union { Phase ph; uint4 q[2]; } u;
-  const uint4* src = reinterpret_cast<const uint4*>(prog + i);
-  u.q[0] = __ldg(src);
-  u.q[1] = __ldg(src + 1);
-  return u.ph;
-}
-
 template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -1587,6 +1661,10 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 4);  // the four warps that share a stage
     }
+    for (int s = 0; s < kGammaSlots; ++s) {
+      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGFullOffset) + s, 1);
+      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGEmptyOffset) + s, kConsumerWarps);
+    }
     sm.ctl[0] = 0;
     fence_barrier_init();
   }
@@ -1597,20 +1675,24 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
     const int n16 = p.n_stages * (kStageBytes / 16);
     for (int i = tid; i < n16; i += kThreads) r[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
+    const uint4* src = reinterpret_cast<const uint4*>(p.prog);
+    uint4* dst = reinterpret_cast<uint4*>(sm.prog);
+    for (int i = tid; i < p.n_phases * 2; i += kThreads) dst[i] = __ldg(src + i);
   }
   __syncthreads();
 
   if (tid >= kConsumerThreads) {
     // ------------------------------ producer warp ------------------------------
     const int lane = tid & 31;
-    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
-    RingCur cur{0, 0u};
-    uint32_t issued = 0;
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_keep_fraction();
+    const uint64_t pol_gamma = policy_evict_last();
+    RingCur cur{0, 0u}, gcur{0, 0u};
+    uint32_t issued = 0, gissued = 0;
     bool ok = true;
     for (int iter = 0; iter < p.n_iters && ok; ++iter) {
       for (int i = 0; i < p.n_phases && ok; ++i) {
-        const Phase ph = load_phase(p.prog, i);
-        if (ph.type == PH_GEMV) ok = gemv_phase_produce<PROF>(c, ph, p, sm.ctl, cur, issued, i, pol_stream, pol_keep, lane);
+        const Phase ph = load_phase(sm.prog, i);
+        if (ph.type == PH_GEMV) ok = gemv_phase_produce<PROF>(c, ph, p, sm.ctl, cur, gcur, issued, gissued, i, pol_stream, pol_keep, pol_gamma, lane);
       }
     }
     // drain: shared memory must not be released with bulk copies in flight (the frame loop may stop early)
@@ -1621,12 +1703,18 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
         if (d.slot == 0) { d.slot = p.n_stages - 1; d.lap ^= 1u; } else { --d.slot; }
         mbar_wait(&sm.full[d.slot], d.lap, p, DE_FULL_WAIT, -3);
       }
+      const int gn = (int)min(gissued, (uint32_t)kGammaSlots);
+      d = gcur;
+      for (int k = 0; k < gn; ++k) {
+        if (d.slot == 0) { d.slot = kGammaSlots - 1; d.lap ^= 1u; } else { --d.slot; }
+        mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + kGFullOffset) + d.slot, d.lap, p, DE_FULL_WAIT, -4);
+      }
     }
     return;
   }
 
   // -------------------------------- consumer warps --------------------------------
-  RingCur cur{0, 0u};
+  RingCur cur{0, 0u}, gcur{0, 0u};
   int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
   int* frame_done = sm.ctl + 12;  // [4]
   for (int iter = 0; iter < p.n_iters; ++iter) {
@@ -1656,17 +1744,15 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
         }
       }
     }
-    Phase ph = load_phase(p.prog, 0);
     for (int i = 0; i < p.n_phases; ++i) {
-      const Phase nxt = load_phase(p.prog, (i + 1 < p.n_phases) ? i + 1 : 0);  // in flight while this phase runs
+      const Phase ph = load_phase(sm.prog, i);
       const uint32_t ep = ep0 + (uint32_t)i + 1u;
       switch (ph.type) {
-        case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, cur, i, ep); break;
+        case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, cur, gcur, i, ep); break;
         case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
         case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
         default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
       }
-      ph = nxt;
     }
   }
 }

@@ -1,0 +1,7 @@
+#!/bin/bash
+# quick perf + phase profile (no tests)
+tag=${1:-q}
+mkdir -p gpurun_out
+export FQ3_WATCHDOG_MS=3000
+timeout 300 python scripts/quick_perf.py 0.6B-Base 64 2>&1 | tail -5 | tee gpurun_out/perf_${tag}.log
+FQ3_PROF=0 timeout 200 python scripts/phase_prof.py 2>&1 | tail -28 | tee gpurun_out/phase_prof_${tag}.log
