@@ -98,6 +98,7 @@ bool make_plan(int G, int N, int K, bool swiglu, Plan* out) {
   pl.su_rem = n_su - pl.su_base * G;
   pl.nkq = (K + kStageCols - 1) / kStageCols;
   pl.tpb = std::max(1, kBatchStages / pl.nkq);
+  pl.inv_k = 1.0f / (float)K;
   if (pl.nkq > kBatchStages) return false;
   *out = pl;
   return true;
@@ -219,6 +220,8 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   p.prof = e->prof;
   p.prof_cta = e->prof_cta;
   if (const char* d = getenv("FQ3_DEBUG")) p.debug = atoi(d);
+  p.ll_mode = 0;
+  if (const char* d = getenv("FQ3_LLMODE")) p.ll_mode = atoi(d);
   p.n_iters = 1;
   p.stream0 = 0;
 }
@@ -241,7 +244,11 @@ int launch(fq3_engine* e, LaunchParams& p, size_t x_elems, size_t gamma_elems, c
   p.xbuf_bytes = (int)round_up(x_elems * 2, 1024);
   p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 1024);
   p.gam_bytes = (int)round_up(gamma_elems * 2, 1024);
-  long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - (long)p.xbuf_bytes - (long)p.prog_bytes - (long)kGammaSlots * p.gam_bytes;
+  // Shared memory and L1 share 256 KB per SM: staying at or below the 196 KB carve-out leaves 60 KB of L1, which the
+  // kernel's register spills and table reads need (measured: 28 KB of L1 costs 20 % of the step time).
+  const long budget = e->ring_cap > 0 ? (long)e->smem_max : std::min<long>((long)e->smem_max, 196L * 1024);
+  long avail = budget - kHeaderBytes - kScratchBytes - (long)p.xbuf_bytes - (long)p.prog_bytes - (long)kGammaSlots * p.gam_bytes;
+  if (avail < 6L * kStageBytes) avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - (long)p.xbuf_bytes - (long)p.prog_bytes - (long)kGammaSlots * p.gam_bytes;
   if (e->ring_cap > 0) avail = std::min(avail, e->ring_cap);
   p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
   if (p.n_stages < 4) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
@@ -346,7 +353,7 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   if (const char* rk = getenv("FQ3_RING_KB")) e->ring_cap = std::max(16L, atol(rk)) * 1024L;
   if (const char* pc = getenv("FQ3_PROF")) {
     e->prof_cta = atoi(pc);
-    if (dalloc(e, &e->prof, 512 * 16)) return -FQ3_E_CUDA;
+    if (dalloc(e, &e->prof, 512 * 160 * 2)) return -FQ3_E_CUDA;
   }
   if (const char* w = getenv("FQ3_WATCHDOG_MS")) e->watchdog_ns = (unsigned long long)atoll(w) * 1000000ull;
   e->smem_max = (size_t)smem_optin;
@@ -737,8 +744,8 @@ int fq3_read_codes(fq3_engine* e, int idx, int first, int n, int32_t* codes_out,
 int fq3_debug_read_prof(fq3_engine* e, long long* out, int n_words) {
   if (!e || !e->prof) return fail(FQ3_E_INVALID, "profiling not enabled (FQ3_PROF)");
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, e->prof, sizeof(long long) * std::min(n_words, 512 * 16), cudaMemcpyDeviceToHost));
-  CK(cudaMemset(e->prof, 0, sizeof(long long) * 512 * 16));
+  CK(cudaMemcpy(out, e->prof, sizeof(long long) * std::min(n_words, 512 * 160 * 2), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(e->prof, 0, sizeof(long long) * 512 * 160 * 2));
   return 0;
 }
 

@@ -2,7 +2,7 @@
 //
 // The kernel is a small "phase machine": a program is a flat list of 32-byte phase descriptors (GEMV /
 // attention / sampling).  One CTA per SM runs the whole program; a producer warp streams the weight
-// rows of every GEMV phase through a shared-memory ring of 16 KB stages (8 rows x 1024 columns) with
+// rows of every GEMV phase through a shared-memory ring of 16 KB stages (16 rows x 512 columns) with
 // cp.async.bulk (TMA bulk copy, SASS UBLKCP) while sixteen consumer warps do the arithmetic.  Because
 // weight addresses never depend on activations or sampled tokens, the producer runs ahead across
 // phases, so HBM stays busy while the consumers wait for each other.  See DESIGN.md §3.
@@ -20,12 +20,12 @@ constexpr int kConsumerWarps = 12;  // 12 consumers + 1 producer = 13 warps; reg
 constexpr int kConsumerThreads = kConsumerWarps * 32;  // 384
 constexpr int kThreads = kConsumerThreads + 32;        // + one producer warp
 constexpr int kMaxStages = 16;             // mbarrier pairs: ring stages in flight per SM (12 fit beside the scratch)
-constexpr int kStageRows = 8;              // weight rows per stage = one mma n-tile
-constexpr int kStageCols = 1024;           // columns per stage
+constexpr int kStageRows = 16;             // weight rows per stage = one mma m-tile
+constexpr int kStageCols = 512;            // columns per stage
 constexpr int kRowPitch = kStageCols * 2;  // bytes between two rows of a stage in shared memory
 constexpr int kStageBytes = kStageRows * kRowPitch;  // 16 KB
-constexpr int kUnitCols = 256;             // one warp's share of a stage: 8 rows x 256 columns (4 warps per stage)
-constexpr int kGroups = kConsumerWarps / 4;  // stages consumed concurrently
+constexpr int kUnitCols = 256;             // one warp's share of a stage: 16 rows x 256 columns (2 warps per stage)
+constexpr int kGroups = kConsumerWarps / 2;  // stages consumed concurrently
 constexpr int kBatchStages = 12;           // stages between two partial-sum reductions
 constexpr int kHeadDim = 128;              // talker and predictor heads (asserted on the host)
 constexpr int kMaxRows = 8;                // activation rows (tokens) per launch, GEMV register tile
@@ -34,7 +34,7 @@ constexpr int kSplitLen = 4 * kConsumerWarps;              // positions one CTA 
 constexpr int kPartStride = 132;           // floats per attention partial: m, l, pad, pad, o[128]
 constexpr int kNumBufs = 16;
 constexpr int kMaxVocab = 5120;            // sampling scratch holds V fp32 logits in 20 KB
-// scratch: GEMV partial sums [kBatchStages][4][M<=8][8] fp32 = 12 KB;
+// scratch: GEMV partial sums [kBatchStages][2][M<=8][16] fp32 = 12 KB;
 //          attention q rows fp32 [2][128] | fresh K/V rows bf16 [8][2][128] | warp partials [12][2][132] = 17.4 KB;
 //          sampling 20 KB logits + histogram + reductions = 21.5 KB
 constexpr int kScratchBytes = 24 * 1024;
@@ -101,13 +101,13 @@ enum BufId : uint8_t {
 
 // Host-computed partition of one GEMV shape (N, K, SwiGLU) over the grid.  A super-unit (SU) is the `ro` consecutive
 // weight rows behind one packed output word: 2 rows (plain) or 4 rows (SwiGLU: two (gate, up) pairs).  A CTA's rows are
-// cut into tiles of 8 rows and every tile into nkq stages of <= 1024 columns (stage index = tile * nkq + kq).
+// cut into tiles of 16 rows and every tile into nkq stages of <= 512 columns (stage index = tile * nkq + kq).
 struct Plan {
   int su_base, su_rem;  // SUs (= output words) per CTA: the first su_rem CTAs take su_base + 1
   int ro;               // weight rows per SU
-  int nkq;              // stages per tile = ceil(K / 1024)
+  int nkq;              // stages per tile = ceil(K / 512)
   int tpb;              // tiles per batch = max(1, kBatchStages / nkq)
-  int pad;
+  float inv_k;          // 1 / K
 };
 
 // ---- run-time structures ----------------------------------------------------------------------
@@ -189,6 +189,7 @@ struct LaunchParams {
   unsigned long long watchdog_ns;
   long long* prof;  // optional per-phase clock64 marks [n_phases][8] of CTA prof_cta (FQ3_PROF)
   int prof_cta;
+  int ll_mode;  // experiment: instruction flavour of the LL loads (bits 0-2) and stores (bits 3-5) of the GEMV phases
   int debug;  // timing ablations (FQ3_DEBUG): 1 no LL wait, 2 no GEMV math, 4 no attention
 };
 

@@ -107,11 +107,16 @@ __device__ __forceinline__ LLWord ll_ld(const LLWord* p) {
 __device__ __forceinline__ void ll_ld2(const LLWord* p, LLWord& a, LLWord& b) {
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(b.x), "=r"(b.y) : "l"(p) : "memory");
 }
+// Publishing store.  A plain st.relaxed.gpu may linger in the SM's write path for about a microsecond before L2 (and the
+// pollers) see it; a reduction is sent to L2 at once and needs no reply.  Epochs only grow, so with the epoch in the high
+// half max.u64 installs exactly {payload, epoch} (measured: 17 % off the step time against st.relaxed.gpu).
 __device__ __forceinline__ void ll_st(LLWord* p, uint32_t payload, uint32_t ep) {
-  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(ep) : "memory");
+  const unsigned long long val = ((unsigned long long)ep << 32) | payload;
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(val) : "memory");
 }
 __device__ __forceinline__ void ll_st2(LLWord* p, uint32_t pay0, uint32_t pay1, uint32_t ep) {
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(p), "r"(pay0), "r"(ep), "r"(pay1) : "memory");
+  ll_st(p, pay0, ep);
+  ll_st(p + 1, pay1, ep);
 }
 __device__ __forceinline__ void ll_stf(LLWord* p, float v, uint32_t ep) { ll_st(p, __float_as_uint(v), ep); }
 
@@ -240,6 +245,16 @@ __device__ __forceinline__ uint32_t ll_wait(const LLWord* ptr, uint32_t ep, cons
 #define FQ3_ASSERT(cond, pidx, detail) do { } while (0)
 #endif
 
+// FQ3_PROF=-2: every CTA records the global-timer time of its phase start (k = 0) and of its first output store (k = 1)
+__device__ __forceinline__ void prof_cta_time(const LaunchParams& p, int pidx, int k) {
+  if (p.prof && p.prof_cta == -2 && threadIdx.x == 0 && pidx >= 0 && pidx < 512)
+    p.prof[((size_t)pidx * 160 + blockIdx.x) * 2 + k] = (long long)globaltimer_ns();
+}
+// FQ3_PROF=-3: every warp of CTA 0 records clock64 at two points of a phase (k = 0, 1)
+__device__ __forceinline__ void prof_warp_time(const LaunchParams& p, int pidx, int k) {
+  if (p.prof && p.prof_cta == -3 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && pidx >= 0 && pidx < 512)
+    p.prof[((size_t)pidx * 160 + (threadIdx.x >> 5)) * 2 + k] = clock64();
+}
 __device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int slot) {
   if (p.prof && threadIdx.x == 0 && (int)blockIdx.x == p.prof_cta && pidx >= 0 && pidx < 512) p.prof[(size_t)pidx * 16 + slot] = clock64();
 }
@@ -408,55 +423,43 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
   cbar_sync();
 }
 
-// One warp's share of a stage: 8 weight rows x (nblk * 64) columns against up to 8 activation rows.
+// One warp's share of a stage: 16 weight rows x (nblk * 64) columns against up to 4 activation rows.
 //
-// Fragment mapping (lane = 4*g + t).  The weights are the B operand: column n = g is weight row g of the stage.  The
-// activations are the A operand: row g carries activation row g>>1 (row g+8: activation row 4 + (g>>1)).  A lane reads
-// 16 contiguous bytes (8 columns) of its weight row and of its activation row per load; which 8 columns depends on
-// (g & 1, t) so that a quarter-warp (rows 2j, 2j+1) covers 128 contiguous bytes -> conflict-free although all rows of a
-// stage start in the same bank.  A and B of one lane always use the same columns, and D[m][n] is only read where
-// m and n have the same parity, so the per-parity column permutation cancels out.  Result: the lane holds
-// dot(activation row g>>1, weight row 2t + (g&1)) in c[g&1]  (and row 4 + (g>>1) in c[2 + (g&1)]).
-// Four independent accumulators keep the dependent HMMA chain at a quarter of the block count.
-template <bool HI>
-__device__ __forceinline__ void gemv_unit(uint32_t wA, uint32_t wB, uint32_t xA, uint32_t xB, uint32_t yA, uint32_t yB, int nblk, int h0,
-                                          float& v_lo, float& v_hi) {
+// Fragment mapping of mma.m16n8k16 (lane = 4*g + t).  The weights are the A operand: rows g and g+8 of the stage.  A lane
+// reads 16 contiguous bytes (8 columns) of each of its two weight rows per load; which 8 columns depends on (g & 1, t) so
+// that a quarter-warp (rows 2j, 2j+1) covers 128 contiguous bytes -> conflict-free although all rows of a stage start in
+// the same bank.  The activations are the B operand (broadcast loads: 64 distinct bytes per request): column n = g of B carries
+// activation row g>>1 under the column permutation of parity g&1, i.e. exactly the columns this lane also reads of its
+// weight rows.  D[m][n] is only read where m and n have the same parity, so the permutation cancels out.
+// Result: the lane holds dot(weight row g, activation row t) in c[g&1] and dot(weight row g+8, activation row t) in c[2 + (g&1)].
+// Two accumulator sets per half keep the dependent HMMA chain at a quarter of the MMA count.
+__device__ __forceinline__ void gemv_unit(uint32_t w0, uint32_t xrow, uint32_t oA, uint32_t oB, int nblk, int h0, float& v_lo, float& v_hi) {
   float c[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
   }
+  const uint32_t w1 = w0 + 8u * kRowPitch;
   auto block = [&](uint32_t o, float (&ca)[4], float (&cb)[4]) {
-    const uint4 a = lds128(wA + o), b = lds128(wB + o);
-    const uint4 x = lds128(xA + o), y = lds128(xB + o);
-    uint4 xh = make_uint4(0u, 0u, 0u, 0u), yh = make_uint4(0u, 0u, 0u, 0u);
-    if (HI) {
-      xh = lds128(yA + o);
-      yh = lds128(yB + o);
-    }
-    mma_bf16(ca, x.x, xh.x, x.y, xh.y, a.x, a.y);
-    mma_bf16(cb, y.x, yh.x, y.y, yh.y, b.x, b.y);
-    mma_bf16(ca, x.z, xh.z, x.w, xh.w, a.z, a.w);
-    mma_bf16(cb, y.z, yh.z, y.w, yh.w, b.z, b.w);
+    const uint4 xa = lds128(xrow + o + oA), xb = lds128(xrow + o + oB);
+    const uint4 a0 = lds128(w0 + o + oA), a1 = lds128(w1 + o + oA);
+    const uint4 b0 = lds128(w0 + o + oB), b1 = lds128(w1 + o + oB);
+    mma_bf16(ca, a0.x, a1.x, a0.y, a1.y, xa.x, xa.y);
+    mma_bf16(cb, b0.x, b1.x, b0.y, b1.y, xb.x, xb.y);
+    mma_bf16(ca, a0.z, a1.z, a0.w, a1.w, xa.z, xa.w);
+    mma_bf16(cb, b0.z, b1.z, b0.w, b1.w, xb.z, xb.w);
   };
-  if (nblk == 4) {
-    block(0u, c[0], c[1]);
-    block(128u, c[2], c[3]);
-    block(256u, c[0], c[1]);
-    block(384u, c[2], c[3]);
-  } else {
 #pragma unroll 1
-    for (int b = 0; b < nblk; ++b) block((uint32_t)b * 128u, c[0], c[1]);
+  for (int i = 0; i + 1 < nblk; i += 2) {
+    block((uint32_t)i * 128u, c[0], c[1]);
+    block((uint32_t)i * 128u + 128u, c[2], c[3]);
   }
+  if (nblk & 1) block((uint32_t)(nblk - 1) * 128u, c[0], c[1]);
   const float s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]), s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+  const float s2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]), s3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
   v_lo = h0 ? s1 : s0;
-  if (HI) {
-    const float s2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]), s3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
-    v_hi = h0 ? s3 : s2;
-  } else {
-    v_hi = 0.f;
-  }
+  v_hi = h0 ? s3 : s2;
 }
 
 // This CTA's share of a GEMV phase (producer and consumers must agree).
@@ -476,7 +479,34 @@ __device__ __forceinline__ Slab get_slab(const Phase& ph, const LaunchParams& p)
   return s;
 }
 
-// Partial sums of one batch in shared memory: part[((tile * M + m) * 8 + n) * (nkq * 4) + kq * 4 + wk] — the nkq*4 partial
+// Values computed before the poll must not be sunk behind it by the compiler: an empty asm pins them in a register.
+__device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin(float& v) { asm volatile("" : "+f"(v)); }
+template <class T>
+__device__ __forceinline__ void pin(T*& v) { asm volatile("" : "+l"(v)); }
+
+__device__ __forceinline__ uint4 ll_ld_pair(const LLWord* p, int mode = 0) {
+  uint4 v;
+  switch (mode & 7) {
+    default: asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
+    case 1: asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
+    case 2: asm volatile("ld.global.cv.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
+    case 3: asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
+    case 4: asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
+    case 5: asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
+  }
+  return v;
+}
+// bf16(bf16(x * rs) * g) for two packed elements: fp32 product + one packed round, then a packed bf16 multiply (the bf16 x bf16
+// product is exact in fp32, so rounding it once to bf16 is what the fp32 route does as well)
+__device__ __forceinline__ uint32_t norm_pair(uint32_t x, float rs, uint32_t g) {
+  const __nv_bfloat162 xr = __floats2bfloat162_rn(bf_lo(x) * rs, bf_hi(x) * rs);
+  const __nv_bfloat162 y = __hmul2(xr, *reinterpret_cast<const __nv_bfloat162*>(&g));
+  return *reinterpret_cast<const uint32_t*>(&y);
+}
+
+// Partial sums of one batch in shared memory: part[((tile * M + m) * 16 + row) * (nkq * 2) + kq * 2 + u] — the nkq*2 partial
 // sums of one output row are contiguous, so the finishing thread reads them with 16-byte loads in a fixed order.
 template <bool PROF>
 __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, RingCur& gcur, int pidx,
@@ -490,120 +520,131 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const int ldin = p.ld[ph.in_buf];
   const LLWord* in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]) + (size_t)row_off * ldin;
   const bool norm = (flags & F_PRENORM) != 0;
-  constexpr int kXW = 4;  // 8-byte words per thread held in registers on the one-row path: K <= 2 * kXW * 384 = 3072
-  const int Kw = K >> 1;  // words per row
-  const bool fast = (M == 1) && (Kw <= kXW * kConsumerThreads);
+  const int Kp = K >> 2;  // 16-byte word pairs per row; thread tid owns pairs tid and tid + 384 (elements 4q .. 4q+3)
+  const bool fast = (M == 1) && (Kp <= 2 * kConsumerThreads);  // K <= 3072
   if (PROF) prof_mark(p, pidx, 0);
+  if (PROF) prof_cta_time(p, pidx, 0);
 
-  // ---- issue the first poll of this thread's input words (word tid + i * 384 holds elements 2w, 2w+1)
-  LLWord w[kXW];
-  const LLWord* src = in + tid;
-  bool have[kXW];
+  // ---- issue the first poll of this thread's input words
+  const bool have0 = tid < Kp, have1 = tid + kConsumerThreads < Kp;
+  const LLWord* src = in + 2 * tid;
+  uint4 w0 = make_uint4(0u, ep_in, 0u, ep_in), w1 = w0;
   if (fast) {
-#pragma unroll
-    for (int i = 0; i < kXW; ++i) {
-      have[i] = tid + i * kConsumerThreads < Kw;
-      w[i] = make_uint2(0u, ep_in);
-      if (have[i]) w[i] = ll_ld(src + i * kConsumerThreads);
-    }
+    if (have0) w0 = ll_ld_pair(src, p.ll_mode);
+    if (have1) w1 = ll_ld_pair(src + 2 * kConsumerThreads, p.ll_mode);
   }
 
   // ---- everything that does not depend on the input: overlaps the round trip of the poll
   const Plan& pl = p.plans[ph.plan];
   const Slab sb = get_slab(ph, p);
-  const int ro = pl.ro, tpb = pl.tpb, nkq = sb.nkq;
-  const int grp = warp >> 2, wk = warp & 3;
+  const int ro_shift = pl.ro == 4 ? 2 : 1, tpb = pl.tpb, nkq = sb.nkq;
+  const int grp = warp >> 1, u = warp & 1;
   const int g = lane >> 2, t = lane & 3, h0 = g & 1;
   // norm weights arrive through the producer's stream (slot gcur of the small gamma ring)
-  const uint32_t gslot = c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes;
-  const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
+  uint32_t gsrc = c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes + (uint32_t)tid * 8u;
+  uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
   const uint32_t glap = gcur.lap;
   if (norm) gcur.advance(1, kGammaSlots);
-  const float eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
-  // finishing thread t owns (word wl, row m) of the first batch: residual / bias words are fetched now
-  const int fin_total = sb.n_su * M;
+  float eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
+  float inv_k = pl.inv_k;
+  uint32_t xdst = c.xs + (uint32_t)tid * 8u;
+  // finishing thread: (word wl, row m) of the first batch; residual / bias words are fetched now
+  const int npart = nkq * 2;
+  const int tiles0 = min(tpb, sb.n_tiles);
+  int fin0 = min(sb.n_su, (tiles0 * kStageRows) >> ro_shift) * M;
   const int f_wl = (M == 1) ? tid : tid / M, f_m = (M == 1) ? 0 : tid - f_wl * M;
-  const int f_word = sb.su0 + f_wl;
   uint32_t res0 = 0u, bias0 = 0u;
   LLWord* out = reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]);
   const int ldout = p.ld[ph.out_buf];
-  if (tid < fin_total) {
-    if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)f_m * p.ld[ph.res_buf] + f_word).x;
+  LLWord* fout = out + (size_t)f_m * ldout + sb.su0 + f_wl;
+  if (tid < fin0) {
+    if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)f_m * p.ld[ph.res_buf] + sb.su0 + f_wl).x;
     if (flags & F_BIAS) {
       const bf16* bias = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-      bias0 = __ldg(reinterpret_cast<const uint32_t*>(bias) + f_word);
+      bias0 = __ldg(reinterpret_cast<const uint32_t*>(bias) + sb.su0 + f_wl);
     }
   }
-  // shared-memory addresses of this lane's fragments
+  const int f_rr = f_wl << ro_shift;  // first weight row of the word (inside the first batch)
+  uint32_t fq = c.scratch + (uint32_t)((((f_rr >> 4) * M + f_m) * 16 + (f_rr & 15)) * npart) * 4u;
+  // this warp's first stage of the first batch
   RingCur base = cur;  // ring position of the first stage of the current batch
-  const uint32_t lane_w = (uint32_t)g * kRowPitch + (uint32_t)wk * (kUnitCols * 2);
   const uint32_t oA = (uint32_t)(h0 * 64 + t * 16), oB = (uint32_t)((h0 ^ 1) * 64 + t * 16);
-  const int xr_lo = min(g >> 1, M - 1), xr_hi = min(4 + (g >> 1), M - 1);
-  const uint32_t x_lo = c.xs + (uint32_t)xr_lo * (uint32_t)K * 2u + (uint32_t)wk * (kUnitCols * 2);
-  const uint32_t x_hi = c.xs + (uint32_t)xr_hi * (uint32_t)K * 2u + (uint32_t)wk * (kUnitCols * 2);
-  const int npart = nkq * 4;
-  const int n_out = 2 * t + h0;  // weight row (inside the tile) whose dot product this lane ends up holding
+  const uint32_t lane_w = (uint32_t)g * kRowPitch + (uint32_t)u * (kUnitCols * 2);
+  RingCur my = base;
+  my.advance(grp, c.n_stages);
+  int s_count = tiles0 * nkq;
+  int kq = grp, tl = 0;  // stage sl = tl * nkq + kq of the batch
+  while (kq >= nkq) { kq -= nkq; ++tl; }
+  int nblk;
+  uint32_t fullb, wrow, xcol, pdst;
+  auto stage_params = [&]() {
+    const int kw = min(kStageCols, K - kq * kStageCols);
+    const int kcols = min(kUnitCols, kw - u * kUnitCols);  // may be <= 0
+    nblk = kcols > 0 ? (kcols + 63) >> 6 : 0;
+    fullb = c.full + (uint32_t)my.slot * 8u;
+    wrow = c.ring + (uint32_t)my.slot * kStageBytes + lane_w;
+    xcol = c.xs + (uint32_t)(kq * kStageCols + u * kUnitCols) * 2u;
+    pdst = c.scratch + (uint32_t)(((tl * M + t) * 16 + g) * npart + kq * 2 + u) * 4u;
+  };
+  stage_params();
+  pin(gsrc); pin(gfullb); pin(gemptyb); pin(eps); pin(inv_k); pin(xdst); pin(fin0); pin(fout); pin(fq);
+  pin(nblk); pin(fullb); pin(wrow); pin(xcol); pin(pdst); pin(s_count);
 
   // ---- wait for the input, normalise, stage it in shared memory
   if (fast) {
     if (ep_in != 0) {
       unsigned tries = 0;
-      while (true) {
-        bool bad = false;
-#pragma unroll
-        for (int i = 0; i < kXW; ++i) bad |= (w[i].y != ep_in);
-        if (!bad) break;
+      while ((w0.y != ep_in) | (w0.w != ep_in) | (w1.y != ep_in) | (w1.w != ep_in)) {
         if (++tries > (unsigned)(p.debug >> 16)) __nanosleep((unsigned)(p.debug & 0xffff));
         if (tries > (unsigned)(p.watchdog_ns >> 8)) device_fault(p, DE_LL_WAIT, pidx, (int)ep_in);
-#pragma unroll
-        for (int i = 0; i < kXW; ++i)
-          if (have[i] && w[i].y != ep_in) w[i] = ll_ld(src + i * kConsumerThreads);
+        if (have0 && ((w0.y != ep_in) | (w0.w != ep_in))) w0 = ll_ld_pair(src, p.ll_mode);
+        if (have1 && ((w1.y != ep_in) | (w1.w != ep_in))) w1 = ll_ld_pair(src + 2 * kConsumerThreads, p.ll_mode);
       }
     }
     if (PROF) prof_mark(p, pidx, 7);
-    const uint32_t xdst = c.xs + (uint32_t)tid * 4u;
+    if (PROF) prof_warp_time(p, pidx, 0);
     if (!norm) {
-#pragma unroll
-      for (int i = 0; i < kXW; ++i)
-        if (have[i]) sts_u32(xdst + (uint32_t)i * (kConsumerThreads * 4), w[i].x);
+      if (have0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xdst), "r"(w0.x), "r"(w0.z) : "memory");
+      if (have1) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xdst + kConsumerThreads * 8), "r"(w1.x), "r"(w1.z) : "memory");
       cbar_sync();
     } else {
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < kXW; ++i) {  // absent words carry payload 0
-        const float x0 = bf_lo(w[i].x), x1 = bf_hi(w[i].x);
-        ss = fmaf(x0, x0, ss);
-        ss = fmaf(x1, x1, ss);
+      float ss;
+      {  // absent pairs carry payload 0
+        const float a0 = bf_lo(w0.x), a1 = bf_hi(w0.x), a2 = bf_lo(w0.z), a3 = bf_hi(w0.z);
+        const float b0 = bf_lo(w1.x), b1 = bf_hi(w1.x), b2 = bf_lo(w1.z), b3 = bf_hi(w1.z);
+        ss = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3) + (fmaf(b0, b0, b1 * b1) + fmaf(b2, b2, b3 * b3));
       }
       ss = warp_sum(ss);
       if (lane == 0) sts_f32(c.red + (uint32_t)warp * 4u, ss);
+      // the norm weights were queued by the producer long ago: read them while the barrier gathers the warps
+      if (!mbar_try_wait_a(gfullb, glap)) {
+        Spin spin;
+        while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
+      }
+      uint2 g0 = make_uint2(0u, 0u), g1 = g0;
+      if (have0) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(g0.x), "=r"(g0.y) : "r"(gsrc));
+      if (have1) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(g1.x), "=r"(g1.y) : "r"(gsrc + kConsumerThreads * 8));
+      if (PROF) prof_mark(p, pidx, 15);
+      if (PROF) prof_warp_time(p, pidx, 1);
       cbar_sync();
-      float tot = 0.f;
+      if (PROF) prof_mark(p, pidx, 14);
+      float tot;
       {
         const float4 r0 = lds_f32x4(c.red), r1 = lds_f32x4(c.red + 16u), r2 = lds_f32x4(c.red + 32u);
         static_assert(kConsumerWarps == 12, "the RMSNorm reduction reads twelve per-warp sums");
         tot = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w)) + ((r2.x + r2.y) + (r2.z + r2.w));
       }
-      const float rs = rsqrtf(tot / (float)K + eps);
+      const float rs = rsqrtf(fmaf(tot, inv_k, eps));
       const bool wr = (flags & F_WRITE_NORMED) && blockIdx.x == 0;
-      if (!mbar_try_wait_a(gfullb, glap)) {
-        Spin spin;
-        while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100 + gcur.slot);
+      if (have0) {
+        const uint32_t y0 = norm_pair(w0.x, rs, g0.x), y1 = norm_pair(w0.z, rs, g0.y);
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xdst), "r"(y0), "r"(y1) : "memory");
+        if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid] = make_uint2(y0, y1);
       }
-      uint32_t gm[kXW];
-#pragma unroll
-      for (int i = 0; i < kXW; ++i) {
-        gm[i] = 0x3f803f80u;
-        if (have[i]) gm[i] = lds_u32(gslot + (uint32_t)(tid + i * kConsumerThreads) * 4u);
-      }
-#pragma unroll
-      for (int i = 0; i < kXW; ++i) {
-        if (have[i]) {
-          const uint32_t a0 = w[i].x;
-          const uint32_t y0 = pack_bf16x2(bf16r(bf16r(bf_lo(a0) * rs) * bf_lo(gm[i])), bf16r(bf16r(bf_hi(a0) * rs) * bf_hi(gm[i])));
-          sts_u32(xdst + (uint32_t)i * (kConsumerThreads * 4), y0);
-          if (wr) reinterpret_cast<uint32_t*>(p.bufs[BUF_HID])[tid + i * kConsumerThreads] = y0;
-        }
+      if (have1) {
+        const uint32_t y0 = norm_pair(w1.x, rs, g1.x), y1 = norm_pair(w1.z, rs, g1.y);
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xdst + kConsumerThreads * 8), "r"(y0), "r"(y1) : "memory");
+        if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid + kConsumerThreads] = make_uint2(y0, y1);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(gemptyb);
@@ -612,116 +653,141 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   } else {
     if (norm && !mbar_try_wait_a(gfullb, glap)) {
       Spin spin;
-      while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100 + gcur.slot);
+      while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
     }
-    load_x_general(p, flags, in, ldin, gslot, eps, K, M, ep_in, pidx, c.xs, c.red);
+    load_x_general(p, flags, in, ldin, gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.xs, c.red);
     if (norm) {  // load_x_general ends with a barrier after the last read of the norm weights
       if (lane == 0) mbar_arrive_a(gemptyb);
     }
   }
   if (PROF) prof_mark(p, pidx, 1);
 
-  // ---- multiply: batches of <= kBatchStages stages, three stages (one per warp group) at a time
-#pragma unroll 1
-  for (int tile0 = 0; tile0 < sb.n_tiles; tile0 += tpb) {
-    const int tiles = min(tpb, sb.n_tiles - tile0);
-    const int s_count = tiles * nkq;
-    RingCur my = base;  // this warp's next stage
-    my.advance(grp, c.n_stages);
-    int kq = grp, tl = 0;  // stage sl = tl * nkq + kq of the batch
-    while (kq >= nkq) { kq -= nkq; ++tl; }
+  // ---- multiply: batches of <= kBatchStages stages, six stages (one per warp pair) at a time; the parameters of the
+  //      next stage are always computed one iteration ahead (the first ones before the poll)
+  int tile0 = 0, tiles = tiles0, fin = fin0;
+  while (true) {
 #pragma unroll 1
     for (int sl = grp; sl < s_count; sl += kGroups) {
-      const int kw = min(kStageCols, K - kq * kStageCols);
-      const int kcols = min(kUnitCols, kw - wk * kUnitCols);  // may be <= 0
-      const int nblk = kcols > 0 ? (kcols + 63) >> 6 : 0;
-      const uint32_t fullb = c.full + (uint32_t)my.slot * 8u;
-      if (!mbar_try_wait_a(fullb, my.lap)) {
-        Spin spin;
-        while (!mbar_try_wait_a(fullb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
-      }
-      if (PROF && sl == 0) prof_mark(p, pidx, 8);
-      float v_lo = 0.f, v_hi = 0.f;
-      if (nblk > 0) {
-        const uint32_t wrow = c.ring + (uint32_t)my.slot * kStageBytes + lane_w;
-        const uint32_t xo = (uint32_t)kq * (kStageCols * 2);
-        if (M > 4) gemv_unit<true>(wrow + oA, wrow + oB, x_lo + xo + oA, x_lo + xo + oB, x_hi + xo + oA, x_hi + xo + oB, nblk, h0, v_lo, v_hi);
-        else gemv_unit<false>(wrow + oA, wrow + oB, x_lo + xo + oA, x_lo + xo + oB, 0u, 0u, nblk, h0, v_lo, v_hi);
+#pragma unroll 1
+      for (int mg = 0; mg < M; mg += 4) {  // activation rows in groups of four (one group in every decode phase)
+        const uint32_t xrow = xcol + (uint32_t)min(mg + (g >> 1), M - 1) * (uint32_t)K * 2u;
+        if (mg == 0 && !mbar_try_wait_a(fullb, my.lap)) {
+          Spin spin;
+          while (!mbar_try_wait_a(fullb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+        }
+        if (PROF && sl == 0) prof_mark(p, pidx, 8);
+        float v_lo = 0.f, v_hi = 0.f;
+        if (nblk > 0) gemv_unit(wrow, xrow, oA, oB, nblk, h0, v_lo, v_hi);
+        if (PROF && sl == 0) prof_mark(p, pidx, 9);
+        if (mg + t < M) {
+          const uint32_t d = pdst + (uint32_t)(mg * 16 * npart) * 4u;
+          sts_f32(d, v_lo);
+          sts_f32(d + (uint32_t)(8 * npart) * 4u, v_hi);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(c.empty + (uint32_t)my.slot * 8u);
-      if (PROF && sl == 0) prof_mark(p, pidx, 9);
-      const uint32_t dst = c.scratch + (uint32_t)((((tl * M) * 8 + n_out) * npart) + kq * 4 + wk) * 4u;
-      if ((g >> 1) < M) sts_f32(dst + (uint32_t)((g >> 1) * 8 * npart) * 4u, v_lo);
-      if (4 + (g >> 1) < M) sts_f32(dst + (uint32_t)((4 + (g >> 1)) * 8 * npart) * 4u, v_hi);
-      my.advance(kGroups, c.n_stages);
-      kq += kGroups;
-      while (kq >= nkq) { kq -= nkq; ++tl; }
+      if (sl + kGroups < s_count) {
+        my.advance(kGroups, c.n_stages);
+        kq += kGroups;
+        while (kq >= nkq) { kq -= nkq; ++tl; }
+        stage_params();
+      }
     }
     if (PROF) prof_mark(p, pidx, 6);
     cbar_sync();
     if (PROF) prof_mark(p, pidx, 2);
     // ---- finish: one thread per (output word, activation row); words whose rows lie in tiles [tile0, tile0 + tiles)
-    const int w_first = tile0 * kStageRows / ro;
-    const int w_end = min(sb.n_su, (tile0 + tiles) * kStageRows / ro);
-    const int fin = (w_end - w_first) * M;
-#pragma unroll 1
-    for (int ft = tid; ft < fin; ft += kConsumerThreads) {
-      int wl, m;
-      uint32_t res = res0, bias = bias0;
-      if (tile0 == 0 && ft == tid) {
-        wl = f_wl; m = f_m;
-      } else {
-        wl = w_first + ft / M; m = ft % M;
-        if (flags & F_RESID) res = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)m * p.ld[ph.res_buf] + sb.su0 + wl).x;
+    if (tid < fin) {
+      // first (usually only) word of this thread: everything but the sums was prepared before the poll
+      if (tile0 != 0) {
+        const int w_first = (tile0 * kStageRows) >> ro_shift;
+        const int wl = w_first + tid / M, m = tid % M;
+        if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)m * p.ld[ph.res_buf] + sb.su0 + wl).x;
         if (flags & F_BIAS) {
           const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-          bias = __ldg(reinterpret_cast<const uint32_t*>(bp) + sb.su0 + wl);
+          bias0 = __ldg(reinterpret_cast<const uint32_t*>(bp) + sb.su0 + wl);
         }
+        const int rr = (wl << ro_shift) - tile0 * kStageRows;
+        fq = c.scratch + (uint32_t)((((rr >> 4) * M + m) * 16 + (rr & 15)) * npart) * 4u;
+        fout = out + (size_t)m * ldout + sb.su0 + wl;
       }
-      if (PROF) prof_mark(p, pidx, 10);
-      const int rr0 = wl * ro - tile0 * kStageRows;  // first row of the word inside the batch
-      float y[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (r < ro) {
-          const int rr = rr0 + r;
-          const uint32_t q = c.scratch + (uint32_t)(((((rr >> 3) * M + m) * 8 + (rr & 7)) * npart)) * 4u;
-          float s = 0.f;
 #pragma unroll 1
-          for (int k = 0; k < nkq; ++k) {
-            const float4 v = lds_f32x4(q + (uint32_t)k * 16u);
-            s += (v.x + v.y) + (v.z + v.w);
+      for (int ft = tid;;) {
+        if (PROF) prof_mark(p, pidx, 10);
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (r < (1 << ro_shift)) {
+            const uint32_t q = fq + (uint32_t)(r * npart) * 4u;
+            float s = 0.f;
+            if (npart == 4) {
+              const float4 v = lds_f32x4(q);
+              s = (v.x + v.y) + (v.z + v.w);
+            } else if ((npart & 3) == 0) {
+#pragma unroll 1
+              for (int k = 0; k < npart; k += 4) {
+                const float4 v = lds_f32x4(q + (uint32_t)k * 4u);
+                s += (v.x + v.y) + (v.z + v.w);
+              }
+            } else {
+#pragma unroll 1
+              for (int k = 0; k < npart; ++k) s += lds_f32(q + (uint32_t)k * 4u);
+            }
+            y[r] = s;
           }
-          y[r] = s;
         }
+        if (PROF) prof_mark(p, pidx, 11);
+        float lo, hi;
+        if (flags & F_SWIGLU) {
+          lo = bf16r(bf16r(silu_f(bf16r(y[0]))) * bf16r(y[1]));
+          hi = bf16r(bf16r(silu_f(bf16r(y[2]))) * bf16r(y[3]));
+        } else {
+          lo = y[0]; hi = y[1];
+          if (flags & F_BIAS) { lo += bf_lo(bias0); hi += bf_hi(bias0); }
+          lo = bf16r(lo); hi = bf16r(hi);
+          if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
+        }
+        if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
+        if (PROF) prof_mark(p, pidx, 12);
+        if (PROF) prof_cta_time(p, pidx, 1);
+        ll_st(fout, pack_bf16x2(lo, hi), ep);
+        ft += kConsumerThreads;
+        if (ft >= fin) break;
+        // further words of this thread (more than 384 outputs per CTA and batch: generic shapes only)
+        const int w_first = (tile0 * kStageRows) >> ro_shift;
+        const int wl = w_first + ft / M, m = ft % M;
+        if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)m * p.ld[ph.res_buf] + sb.su0 + wl).x;
+        if (flags & F_BIAS) {
+          const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+          bias0 = __ldg(reinterpret_cast<const uint32_t*>(bp) + sb.su0 + wl);
+        }
+        const int rr = (wl << ro_shift) - tile0 * kStageRows;
+        fq = c.scratch + (uint32_t)((((rr >> 4) * M + m) * 16 + (rr & 15)) * npart) * 4u;
+        fout = out + (size_t)m * ldout + sb.su0 + wl;
       }
-      if (PROF) prof_mark(p, pidx, 11);
-      float lo, hi;
-      if (flags & F_SWIGLU) {
-        lo = bf16r(bf16r(silu_f(bf16r(y[0]))) * bf16r(y[1]));
-        hi = bf16r(bf16r(silu_f(bf16r(y[2]))) * bf16r(y[3]));
-      } else {
-        lo = y[0]; hi = y[1];
-        if (flags & F_BIAS) { lo += bf_lo(bias); hi += bf_hi(bias); }
-        lo = bf16r(lo); hi = bf16r(hi);
-        if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
-      }
-      if (flags & F_RESID) { lo = bf16r(bf_lo(res) + lo); hi = bf16r(bf_hi(res) + hi); }
-      if (PROF) prof_mark(p, pidx, 12);
-      ll_st(out + (size_t)m * ldout + sb.su0 + wl, pack_bf16x2(lo, hi), ep);
-      if (PROF) prof_mark(p, pidx, 13);
     }
     base.advance(s_count, c.n_stages);
-    if (tile0 + tpb < sb.n_tiles) cbar_sync();  // the next batch overwrites the partial sums
+    tile0 += tpb;
+    if (tile0 >= sb.n_tiles) break;
+    // next batch (generic shapes / 1.7B gate-up only)
+    cbar_sync();  // the next batch overwrites the partial sums
+    tiles = min(tpb, sb.n_tiles - tile0);
+    s_count = tiles * nkq;
+    fin = (min(sb.n_su, ((tile0 + tiles) * kStageRows) >> ro_shift) - ((tile0 * kStageRows) >> ro_shift)) * M;
+    my = base;
+    my.advance(grp, c.n_stages);
+    kq = grp; tl = 0;
+    while (kq >= nkq) { kq -= nkq; ++tl; }
+    stage_params();
   }
   cur = base;
   if (PROF) prof_mark(p, pidx, 3);
 }
 
-// Producer side of one GEMV phase: stream this CTA's rows through the ring, one 16 KB stage (8 rows x <= 1024 columns)
-// per mbarrier.  When a stage is contiguous in HBM (K == 1024) one bulk copy moves it, otherwise one copy per row.
-// Returns false when the consumers asked to stop (frame loop finished early).
+// Producer side of one GEMV phase: stream this CTA's rows through the ring, one 16 KB stage (16 rows x <= 512 columns)
+// per mbarrier: one bulk copy per row (a single one when the stage is contiguous in HBM, K == 512).  The phase's norm
+// weights travel in the same stream.  Returns false when the consumers asked to stop (frame loop finished early).
 template <bool PROF>
 __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph, const LaunchParams& p, int* ctl, RingCur& cur, RingCur& gcur, uint32_t& issued,
                                                    uint32_t& gissued, int pidx, uint64_t pol_stream, uint64_t pol_keep, uint64_t pol_gamma, int lane) {
@@ -733,7 +799,6 @@ __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph
   const uint64_t pol = (ph.flags & F_L2_KEEP) ? pol_keep : pol_stream;
   if (PROF && (int)blockIdx.x == p.prof_cta && lane == 0 && pidx < 512) p.prof[(size_t)pidx * 16 + 4] = clock64();
   if (ph.flags & F_PRENORM) {
-    // the phase's norm weights travel in the same stream, ahead of its first stage
     const unsigned char* gp = (ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_gamma) : p.arena + (size_t)ph.g_off * 16;
     const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
     int stop = 0;
@@ -1659,7 +1724,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 4);  // the four warps that share a stage
+      mbar_init(&sm.empty[s], 2);  // the two warps that share a stage
     }
     for (int s = 0; s < kGammaSlots; ++s) {
       mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGFullOffset) + s, 1);

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export FQ3_WATCHDOG_MS=3000
-export FQ3_RING_KB=96
+
 for c in 0 147; do
   echo "=== CTA $c"
   FQ3_PROF=$c timeout 200 python scripts/phase_prof.py 2>&1 | tail -34

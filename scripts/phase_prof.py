@@ -23,10 +23,10 @@ n = 141
 names = {0: "qkv", 1: "attn", 2: "o", 3: "gu", 4: "down"}
 S = 16
 t0 = min(buf[i * S] for i in range(n) if buf[i * S])
-print("GEMV: poll = wait for input words; norm = barrier+rescale+barrier; ring = wait full; mma; pst = partial store; rest = other rounds;")
-print("      bar = barrier; f0 = finish prologue; sum; epi; st; tail")
-hdr = f"{'ph':>4s} {'kind':5s} {'start':>9s} " + " ".join(f"{x:>6s}" for x in ["poll", "norm", "ring", "mma", "-", "rest", "bar", "f0", "sum", "epi", "st", "tail"])
-print(hdr)
+cols = ["poll", "n0", "n1", "n2", "ring", "mma", "rest", "bar", "f0", "sum", "epi", "st+tl"]
+print("GEMV: poll = own input words visible; n0 = sum of squares + norm weights; n1 = first barrier (all warps' words visible); n2 = rescale + barrier;")
+print("      ring = loop set-up + wait full; mma = one unit; rest = partial store / other rounds; bar = barrier; f0/sum/epi/st/tail = finish")
+print(f"{'ph':>4s} {'kind':5s} {'start':>9s} " + " ".join(f"{x:>6s}" for x in cols))
 agg = collections.defaultdict(lambda: [0] + [0] * 13)
 dist = collections.defaultdict(list)
 prev_end = None
@@ -37,11 +37,15 @@ for i in range(n):
     if kind == "attn":
         d = [m[1] - m[0], m[2] - m[1], m[3] - m[2]] + [0] * 9
     else:
-        d = [m[7] - m[0], m[1] - m[7], m[8] - m[1], m[9] - m[8], 0, m[6] - m[9], m[2] - m[6],
-             m[10] - m[2], m[11] - m[10], m[12] - m[11], m[13] - m[12], m[3] - m[13]]
+        n1 = (m[14] - m[7]) if m[14] else (m[1] - m[7])
+        n2 = (m[1] - m[14]) if m[14] else 0
+        n0 = (m[15] - m[7]) if m[15] else 0
+        if m[15]: n1 = m[14] - m[15]
+        d = [m[7] - m[0], n0, n1, n2, m[8] - m[1], m[9] - m[8], m[6] - m[9], m[2] - m[6],
+             m[10] - m[2], m[11] - m[10], m[12] - m[11], m[3] - m[12]]
     if i < 12 or i >= 136:
         print(f"{i:4d} {kind:5s} {m[0]-t0:9d} " + " ".join(f"{x:6d}" for x in d) + f"   prod {m[4]-t0 if m[4] else 0} {m[5]-t0 if m[5] else 0}")
-    dist[kind].append((d[0] + d[1], d[2], d[3] + d[5], sum(d[7:12])))
+    dist[kind].append((d[0] + d[1] + d[2] + d[3], d[4], d[5] + d[6], sum(d[8:12])))
     a = agg[kind]; a[0] += 1
     for k in range(12): a[1 + k] += d[k]
     if prev_end is not None: a[13] += m[0] - prev_end
@@ -49,8 +53,8 @@ for i in range(n):
 print("averages (last column: gap before the phase)")
 for k, a in agg.items(): print(f"{k:5s} {a[0]:3d}           " + " ".join(f"{a[1+j]/a[0]:6.0f}" for j in range(12)) + f" {a[13]/a[0]:8.0f}")
 last = max(buf[i * S + 3] for i in range(n)); print("total cycles", last - t0)
-print("distribution per kind: min / median / max of  wait(poll+norm) | ring | mma(all rounds) | finish(all)")
+print("distribution per kind: min / median / max of  wait(poll+n1+n2) | ring | mma+rest | finish(all)")
 for k, v in dist.items():
-    cols = list(zip(*v))
+    cs = list(zip(*v))
     def q(c): c = sorted(c); return f"{c[0]:6d}/{c[len(c)//2]:6d}/{c[-1]:6d}"
-    print(f"{k:5s} " + " | ".join(q(c) for c in cols))
+    print(f"{k:5s} " + " | ".join(q(c) for c in cs))
