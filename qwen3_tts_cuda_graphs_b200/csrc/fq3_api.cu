@@ -678,6 +678,7 @@ int fq3_sample(fq3_engine* e, const void* logits_f32, int V, const void* history
   a.temperature = policy->temperature; a.rep_pen = policy->repetition_penalty; a.seen = nullptr;
   a.suppress_start = policy->suppress_tail > 0 ? std::max(0, V - policy->suppress_tail) : V;
   a.eos = eos_id; a.suppress_eos = suppress_eos; a.round_bf16 = flags & 1; a.seed = policy->seed; a.draw = draw_index;
+  a.next_emb = nullptr; a.emb_row_bytes = 0;
   fq3_sample_kernel<<<1, kConsumerThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float*>(logits_f32), a, reinterpret_cast<const long long*>(history_i64), n_history,
       e->seen_scratch, reinterpret_cast<long long*>(out_token_i64));

@@ -1412,6 +1412,8 @@ struct SampleArgs {
   int suppress_eos;
   int round_bf16;       // logits came from a bf16 tensor: round every intermediate like the reference's bf16 ops
   unsigned long long seed, draw;
+  const bf16* next_emb;  // optional: embedding table whose row [token] is read right after the draw (L2 prefetch of the candidates)
+  int emb_row_bytes;
 };
 
 // logits arrive either as LL words (ll != null, epoch ep) or as a plain fp32 array.
@@ -1583,6 +1585,196 @@ __device__ __noinline__ int sample_row(const float* logits_g, const LLWord* ll, 
   return tok;
 }
 
+// In-kernel sampler for logits that arrive as packed bf16 LL words (V <= 8 * 384 = 3072), top_p >= 1.
+// Thread t owns logits [8t, 8t+8) in registers (four words, two 16-byte loads).  Every intermediate of the reference is a
+// bf16 tensor here (round_bf16), so the order-preserving keys have 16 bits and the k-th largest value needs two 8-bit
+// radix passes.  Eight barriers in total (the generic sampler behind fq3_sample needs about twenty-five).
+// Same semantics as sample_row: penalty -> suppression -> temperature -> keep x >= k-th largest (ties survive) ->
+// multinomial by inverse CDF in index order on one Philox uniform; greedy = lowest index of the maximum.
+__device__ __forceinline__ uint32_t bf16_key(float x) {  // x is bf16-representable (or -inf)
+  const uint32_t b = __float_as_uint(x) >> 16;
+  return (b & 0x8000u) ? (~b & 0xffffu) : (b | 0x8000u);
+}
+__device__ __forceinline__ float bf16_key_value(uint32_t k) {
+  const uint32_t b = (k & 0x8000u) ? (k & 0x7fffu) : (~k & 0xffffu);
+  return __uint_as_float(b << 16);
+}
+__device__ __noinline__ int sample_fast(const LLWord* ll, uint32_t ep, const LaunchParams* lp, int pidx, const SampleArgs& a, unsigned char* scratch) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = a.V, nw = V >> 1;
+  unsigned* hist = reinterpret_cast<unsigned*>(scratch);         // [2][256]
+  float* redf = reinterpret_cast<float*>(scratch + 2048);         // [0..15] per-warp maxima, [16..31] per-warp sums
+  int* redi = reinterpret_cast<int*>(scratch + 2048 + 128);       // [0..15] argmax indices, [16..19] select state, [20] result
+  // ---- poll this thread's four words
+  const int w0i = 4 * tid;
+  const bool h0 = w0i < nw, h1 = w0i + 2 < nw;
+  uint4 wa = make_uint4(0u, ep, 0u, ep), wb = wa;
+  if (h0) wa = ll_ld_pair(ll + w0i);
+  if (h1) wb = ll_ld_pair(ll + w0i + 2);
+  if (tid < 256) { hist[tid] = 0u; hist[256 + tid] = 0u; }
+  cbar_sync();  // (0) histograms cleared before anybody adds to them (overlaps the poll round trip)
+  if (ep != 0) {
+    unsigned tries = 0;
+    while ((wa.y != ep) | (wa.w != ep) | (wb.y != ep) | (wb.w != ep)) {
+      if (++tries > 4) __nanosleep(32);
+      if (tries > (unsigned)(lp->watchdog_ns >> 8)) device_fault(*lp, DE_LL_WAIT, pidx, (int)ep);
+      if (h0 && ((wa.y != ep) | (wa.w != ep))) wa = ll_ld_pair(ll + w0i);
+      if (h1 && ((wb.y != ep) | (wb.w != ep))) wb = ll_ld_pair(ll + w0i + 2);
+    }
+  }
+  prof_mark(*lp, pidx, 1);
+  float x[8] = {bf_lo(wa.x), bf_hi(wa.x), bf_lo(wa.z), bf_hi(wa.z), bf_lo(wb.x), bf_hi(wb.x), bf_lo(wb.z), bf_hi(wb.z)};
+  // ---- penalty, suppression, temperature (each result rounded to bf16 like the reference's bf16 tensor ops)
+  unsigned long long seen8 = 0ull;
+  if (a.seen && a.rep_pen != 1.0f && 8 * tid < V) seen8 = __ldcg(reinterpret_cast<const unsigned long long*>(a.seen + 8 * tid));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = 8 * tid + j;
+    float v = x[j];
+    if ((seen8 >> (8 * j)) & 0xffull) v = bf16r((v > 0.f) ? v / a.rep_pen : v * a.rep_pen);
+    if (i >= a.suppress_start && i != a.eos) v = -INFINITY;
+    if (a.suppress_eos && i == a.eos) v = -INFINITY;
+    if (a.do_sample) v = bf16r(v / a.temperature);
+    if (i >= V) v = -INFINITY;
+    x[j] = v;
+  }
+  // ---- maximum and its lowest index; the first radix pass (high byte of the 16-bit keys) shares its barrier
+  const bool want_k = a.do_sample && a.top_k > 0 && a.top_k < V;
+  uint32_t key[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) key[j] = bf16_key(x[j]);
+  if (want_k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (8 * tid + j < V) atomicAdd(&hist[key[j] >> 8], 1u);
+  }
+  float bv = x[0];
+  int bi = 8 * tid;
+#pragma unroll
+  for (int j = 1; j < 8; ++j)
+    if (x[j] > bv) { bv = x[j]; bi = 8 * tid + j; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) { redf[warp] = bv; redi[warp] = bi; }
+  cbar_sync();  // (1)
+  auto select = [&](unsigned* h, int krem, int slot) {  // warp 0: highest digit whose cumulative count (from the top) reaches krem
+    if (warp == 0) {
+      unsigned s = 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s += h[255 - 8 * lane - t];
+      unsigned incl = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, incl >= (unsigned)krem);
+      const int sel = __ffs(ballot) - 1;
+      if (lane == sel) {
+        unsigned above = incl - s;
+        int digit = 255 - 8 * lane;
+        for (int t = 0; t < 8; ++t) {
+          const unsigned c = h[255 - 8 * lane - t];
+          if (above + c >= (unsigned)krem) { digit = 255 - 8 * lane - t; break; }
+          above += c;
+        }
+        redi[16 + 2 * slot] = digit;
+        redi[17 + 2 * slot] = krem - (int)above;
+      }
+    }
+  };
+  if (want_k) select(hist, a.top_k, 0);
+  float vmax = redf[0];
+  int imax = redi[0];
+#pragma unroll
+  for (int w = 1; w < kConsumerWarps; ++w) {
+    const float ov = redf[w];
+    const int oi = redi[w];
+    if (ov > vmax || (ov == vmax && oi < imax)) { vmax = ov; imax = oi; }
+  }
+  prof_mark(*lp, pidx, 2);
+  if (!a.do_sample) return imax;
+  // ---- k-th largest value (counting multiplicity): second radix pass over the low byte
+  float thr = -INFINITY;
+  if (want_k) {
+    cbar_sync();  // (2)
+    const uint32_t d1 = (uint32_t)redi[16];
+    const int krem = redi[17];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (8 * tid + j < V && (key[j] >> 8) == d1) atomicAdd(&hist[256 + (key[j] & 0xffu)], 1u);
+    cbar_sync();  // (3)
+    select(hist + 256, krem, 1);
+    cbar_sync();  // (4)
+    thr = bf16_key_value((d1 << 8) | (uint32_t)redi[18]);
+  }
+  // the row of the drawn token is read from HBM right after the draw: pull the rows of all surviving candidates into L2 now
+  if (a.next_emb && (a.top_k > 0 && a.top_k <= 64)) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (x[j] >= thr && x[j] > -INFINITY)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char*>(a.next_emb) +
+                                                                       (size_t)(8 * tid + j) * a.emb_row_bytes),
+                     "r"(a.emb_row_bytes)
+                     : "memory");
+  }
+  prof_mark(*lp, pidx, 4);
+  // ---- multinomial(softmax) by inverse CDF in index order
+  float e[8], loc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    e[j] = (x[j] >= thr) ? expf(x[j] - vmax) : 0.f;  // exp(-inf) = 0
+    loc += e[j];
+  }
+  float incl = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) redf[16 + warp] = incl;
+  if (tid == 0) redi[20] = 0x7fffffff;
+  cbar_sync();  // (6)
+  float base = 0.f, total = 0.f;
+#pragma unroll
+  for (int w = 0; w < kConsumerWarps; ++w) {
+    const float s = redf[16 + w];
+    if (w < warp) base += s;
+    total += s;
+  }
+  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)a.draw, (uint32_t)(a.draw >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+  const float u = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
+  const float target = u * total;
+  const float excl = base + incl - loc;
+  if (loc > 0.f && target >= excl && target < excl + loc) {
+    float c = excl;
+    int pick = -1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (e[j] > 0.f && (pick < 0 || target >= c)) { pick = 8 * tid + j; }
+      c += e[j];
+    }
+    // pick = last index whose cumulative start is <= target among kept entries == first index with target < cumulative end
+    if (pick >= 0) atomicMin(&redi[20], pick);
+  }
+  cbar_sync();  // (7)
+  int tok = redi[20];
+  if (tok == 0x7fffffff) tok = imax;  // rounding fell off the end of the CDF
+  prof_mark(*lp, pidx, 5);
+  return tok;
+}
+
+// logits as LL words: the register sampler whenever it applies (top-p needs the sorted distribution: generic path)
+__device__ __forceinline__ int sample_ll(const LLWord* ll, uint32_t ep, const LaunchParams& p, int pidx, const SampleArgs& a, unsigned char* scratch) {
+  if (a.top_p >= 1.0f && a.V <= 8 * kConsumerThreads && (a.V & 3) == 0) return sample_fast(ll, ep, &p, pidx, a, scratch);
+  return sample_row(nullptr, ll, ep, &p, pidx, a, sample_scratch(scratch));
+}
+
 // Publish one bf16 row (n elements) as LL words with all consumer threads.
 __device__ __forceinline__ void publish_row(LLWord* dst, const bf16* src, int n, uint32_t ep) {
   for (int c = threadIdx.x; c < (n >> 1); c += kConsumerThreads) ll_st(dst + c, __ldg(reinterpret_cast<const uint32_t*>(src) + c), ep);
@@ -1600,6 +1792,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
   if ((int)blockIdx.x >= (p.mode == MODE_PREFILL ? 1 : p.n_rows) && threadIdx.x == 0 && ph.kind != SMP_PRED && ph.kind != SMP_PRED_ONLY)
     __threadfence();  // cumulative: covers the K/V rows its CTA mates stored (ordered before by the consumer barriers)
   for (int b = blockIdx.x; b < (p.mode == MODE_PREFILL ? 1 : p.n_rows); b += gridDim.x) {
+    prof_mark(p, pidx, 0);
     cbar_sync();  // the scratch may still be read by the previous GEMV phase's finishing threads
     const int slot = p.stream0 + b;
     StreamState* st = p.st + slot;
@@ -1624,7 +1817,8 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
       a.temperature = p.sub.temperature; a.rep_pen = 1.0f; a.seen = nullptr; a.suppress_start = Vp; a.eos = -1;
       a.suppress_eos = 0; a.round_bf16 = 1; a.seed = p.pol.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(slot + 1));
       a.draw = __ldcg(&st->draws) + (unsigned long long)(i + 1);
-      const int tok = sample_row(nullptr, lg, ep_in, &p, pidx, a, sc);
+      a.next_emb = p.pred_embeds[i]; a.emb_row_bytes = Ht * 2;
+      const int tok = sample_ll(lg, ep_in, p, pidx, a, sm.scratch);
       FQ3_ASSERT(tok >= 0 && tok < Vp, pidx, 100000 + tok);
       if (threadIdx.x == 0) st->cur_codes[i + 1] = tok;
       if (i + 1 < ncb) {
@@ -1684,7 +1878,8 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
       a.round_bf16 = 1;
       a.seed = p.pol.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(slot + 1));
       a.draw = __ldcg(&st->draws);
-      int tok = sample_row(nullptr, lg, ep_in, &p, pidx, a, sc);
+      a.next_emb = p.codec_embed; a.emb_row_bytes = Ht * 2;
+      int tok = sample_ll(lg, ep_in, p, pidx, a, sm.scratch);
       const bool live = !done_now;
       int new_done = done_now, new_pos = __ldcg(&st->position), new_gs = __ldcg(&st->gen_step);
       if (live) {
@@ -1707,7 +1902,9 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
       publish_row(pin + (size_t)(2 * slot + 1) * ldpin, p.codec_embed + (size_t)tok * Ht, Ht, ep);
       if (threadIdx.x == 0) __threadfence();  // once per step: K/V rows stored by this CTA (see above)
     }
+    prof_mark(p, pidx, 6);
     cbar_sync();
+    prof_mark(p, pidx, 3);
   }
 }
 

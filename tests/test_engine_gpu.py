@@ -323,3 +323,64 @@ def test_two_streams_match_single_stream(tiny):
         assert st.error == 0 and st.n_frames == 12
         assert torch.equal(eng.read_codes(i, 0, 12), singles[i]), i
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# in-kernel samplers (sampling.py:32-66 semantics inside the persistent kernel)
+# ------------------------------------------------------------------------------------------------
+def _bf16_div(x, t):
+    return (x.to(torch.bfloat16) / t).float()  # the reference divides a bf16 tensor: the quotient is rounded to bf16
+
+
+def test_predictor_sampler_draws_from_reference_candidate_set(tiny):
+    """Every code the in-kernel predictor sampler draws must be one sample_logits could draw from the same logits
+    (top-k support with ties, sampling.py:54-56), for several seeds; greedy must be the lowest-index argmax."""
+    from oracle.qwen3_tts_oracle import candidate_set
+    cfg, w, eng = tiny
+    g = torch.Generator().manual_seed(3)
+    x = (0.5 * torch.randn(1, 2, cfg.talker.hidden_size, generator=g)).to(torch.bfloat16).cuda()
+    seen_codes = set()
+    for seed in range(6):
+        for k in (50, 5, 1):
+            codes, logits = eng.predictor_run(0, x, _sub(do_sample=True, top_k=k, temperature=0.9), seed=seed, want_logits=True)
+            torch.cuda.synchronize()
+            for i in range(eng.ncb):
+                lg = logits[i].cpu().to(torch.bfloat16)
+                cand = candidate_set(_bf16_div(lg, 0.9).unsqueeze(0), temperature=1.0, top_k=k, top_p=1.0)[0]
+                assert bool(cand[int(codes[i])]), (seed, k, i, int(codes[i]))
+                if k == 1:  # only the maximum survives (bf16 ties at the maximum all do, sampling.py:54-56)
+                    scaled = _bf16_div(lg, 0.9)
+                    assert float(scaled[int(codes[i])]) == float(scaled.max()), (seed, i)
+            seen_codes.add(tuple(int(c) for c in codes))
+    assert len(seen_codes) > 3  # different seeds / k really draw different codes
+
+
+def test_first_token_sampler_respects_suppression_and_top_k(tiny):
+    """SMP_PREFILL: suppress tail (except EOS), EOS while min_new_tokens > 0, temperature, top-k (generate.py:124-134)."""
+    from oracle.qwen3_tts_oracle import candidate_set
+    cfg, w, eng = tiny
+    tie, tam, tth, tpe = synth_prompt(cfg, T=9)
+    V = cfg.talker.vocab_size
+    eos = cfg.talker.codec_eos_token_id
+    smask = torch.zeros(V, dtype=torch.bool)
+    smask[V - 1024:] = True
+    smask[eos] = False
+    drawn = set()
+    for seed in range(8):
+        pol = _sp(do_sample=True, top_k=20, temperature=0.8, repetition_penalty=1.0, min_new_tokens=2, seed=seed)
+        lg = eng.prefill(0, tie[0].cuda(), 0, pol, want_logits=True)
+        torch.cuda.synchronize()
+        tok = eng.status(0).token
+        cand = candidate_set(_bf16_div(lg.cpu(), 0.8).unsqueeze(0), temperature=1.0, top_k=20, top_p=1.0, suppress_mask=smask,
+                             suppress_tokens=[eos])[0]
+        assert bool(cand[tok]), (seed, tok)
+        assert tok < V - 1024 and tok != eos
+        drawn.add(tok)
+    assert len(drawn) > 1
+    pol = _sp(do_sample=False, repetition_penalty=1.0, min_new_tokens=2)
+    lg = eng.prefill(0, tie[0].cuda(), 0, pol, want_logits=True)
+    torch.cuda.synchronize()
+    ref = lg.cpu().clone()
+    ref[smask] = float("-inf")
+    ref[eos] = float("-inf")
+    assert eng.status(0).token == int(ref.argmax())
