@@ -181,6 +181,31 @@ def workload_config(args) -> dict:
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def aggregate_over_ranks(times_ms, totals, device, world):
+    """Replicas only: the job time is the MAX over ranks of each timed leg, the work is the SUM.
+    times_ms / totals: sequences of floats of this rank; returns (max-reduced times, sum-reduced totals)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(list(times_ms), dtype=torch.float64, device=device)
+    tot = torch.tensor(list(totals), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t], [float(x) for x in tot]
+
+
+def ncu_traffic(frames_per_launch):
+    """DRAM bytes per launch of the decode kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if int(d.get("frames_per_launch", -1)) == int(frames_per_launch):
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -292,13 +317,7 @@ def main():
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
 
-    t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
-    tot = torch.tensor([audio_s, e2e_audio_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    audio_all, e2e_audio_all = float(tot[0]), float(tot[1])
+    (dev_ms, e2e_ms), (audio_all, e2e_audio_all) = aggregate_over_ranks([dev_ms, e2e_s * 1000.0], [audio_s, e2e_audio_s], dev, world)
 
     if rank == 0:
         pb = param_bytes(model.model.cfg)
@@ -336,7 +355,7 @@ def main():
                 "bound": "hbm", "kernel": "fq3_stream_kernel (persistent decode: predictor + talker + sampling)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                "traffic": None, "bytes_per_launch": alg_bytes, "launch_ms": avg_ms, "frames_per_launch": args.chunk,
+                "traffic": ncu_traffic(args.chunk), "bytes_per_launch": alg_bytes, "launch_ms": avg_ms, "frames_per_launch": args.chunk,
                 "bytes_model": "streaming bound: 15 predictor passes + heads + talker step + valid KV per frame (SURVEY.md 8d)",
             },
             "decode_ms_per_frame": avg_ms / args.chunk,
