@@ -259,7 +259,8 @@ __device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int s
   if (p.prof && threadIdx.x == 0 && (int)blockIdx.x == p.prof_cta && pidx >= 0 && pidx < 512) p.prof[(size_t)pidx * 16 + slot] = clock64();
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+// SiLU in fp32; the result is rounded to bf16 right away, so the fast exp / divide (a few ulp of fp32) do not show
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ int phase_rows(const Phase& ph, const LaunchParams& p) {
   return (ph.flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows;
@@ -724,6 +725,12 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
             if (npart == 4) {
               const float4 v = lds_f32x4(q);
               s = (v.x + v.y) + (v.z + v.w);
+            } else if (npart == 8) {
+              const float4 v0 = lds_f32x4(q), v1 = lds_f32x4(q + 16u);
+              s = ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
+            } else if (npart == 12) {
+              const float4 v0 = lds_f32x4(q), v1 = lds_f32x4(q + 16u), v2 = lds_f32x4(q + 32u);
+              s = (((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w))) + ((v2.x + v2.y) + (v2.z + v2.w));
             } else if ((npart & 3) == 0) {
 #pragma unroll 1
               for (int k = 0; k < npart; k += 4) {
@@ -987,7 +994,7 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
 
   // -- step 1: one warp per item: q heads (norm + rope, pre-scaled) to smem; K/V rows pos0..pos of this chunk that fall
   //    into [a, b) to the cache and to smem (norm + rope on K).
-  for (int it = warp; it < gq + r + 1; it += kConsumerWarps) {
+  for (int it = warp; it < gq + 2 * (r + 1); it += kConsumerWarps) {  // q heads, then (K row, V row) of every chunk row
     if (it < gq) {
       const int rp = min(max(pos + gr.rope_delta, 0), S.rope_len - 1);
       const LLWord* src = qkv + (size_t)r * ldq + (kvh * gq + it) * HW + lane * 2;
@@ -1000,27 +1007,32 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
       const float scale = rsqrtf((float)kHeadDim);
       *reinterpret_cast<float4*>(qs + it * kHeadDim + lane * 4) = make_float4(x[0] * scale, x[1] * scale, x[2] * scale, x[3] * scale);
     } else {
-      const int r2 = it - gq;
+      const int r2 = (it - gq) >> 1;
+      const bool is_v = ((it - gq) & 1) != 0;
       const int kp = gr.pos0 + r2;
       if (kp >= a && kp < b) {
-        const int rp = min(max(kp + gr.rope_delta, 0), S.rope_len - 1);
         const LLWord* row = qkv + (size_t)r2 * ldq;
-        const LLWord* ksrc = row + (S.nq + kvh) * HW + lane * 2;
-        const LLWord* vsrc = row + (S.nq + S.nkv + kvh) * HW + lane * 2;
-        const RopeRegs rr = rope_load(reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16), S.rope_cos + (size_t)rp * kHeadDim,
-                                      S.rope_sin + (size_t)rp * kHeadDim, lane);
-        LLWord k0, k1, v0, v1;
-        ll_head_wait(ksrc, ep_in, k0, k1, p, pidx);
-        ll_head_wait(vsrc, ep_in, v0, v1, p, pidx);
-        float x[4] = {bf_lo(k0.x), bf_hi(k0.x), bf_lo(k1.x), bf_hi(k1.x)};
-        head_norm_rope(x, rr, S.eps, lane);
-        const uint2 kk = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
-        const uint2 vv = make_uint2(v0.x, v1.x);
-        *reinterpret_cast<uint2*>(Kc + (size_t)kp * kHeadDim + lane * 4) = kk;
-        *reinterpret_cast<uint2*>(Vc + (size_t)kp * kHeadDim + lane * 4) = vv;
         uint2* f = reinterpret_cast<uint2*>(fresh + (size_t)r2 * 32);
-        f[lane] = kk;
-        f[32 + lane] = vv;
+        if (is_v) {
+          const LLWord* vsrc = row + (S.nq + S.nkv + kvh) * HW + lane * 2;
+          LLWord v0, v1;
+          ll_head_wait(vsrc, ep_in, v0, v1, p, pidx);
+          const uint2 vv = make_uint2(v0.x, v1.x);
+          *reinterpret_cast<uint2*>(Vc + (size_t)kp * kHeadDim + lane * 4) = vv;
+          f[32 + lane] = vv;
+        } else {
+          const int rp = min(max(kp + gr.rope_delta, 0), S.rope_len - 1);
+          const LLWord* ksrc = row + (S.nq + kvh) * HW + lane * 2;
+          const RopeRegs rr = rope_load(reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16), S.rope_cos + (size_t)rp * kHeadDim,
+                                        S.rope_sin + (size_t)rp * kHeadDim, lane);
+          LLWord k0, k1;
+          ll_head_wait(ksrc, ep_in, k0, k1, p, pidx);
+          float x[4] = {bf_lo(k0.x), bf_hi(k0.x), bf_lo(k1.x), bf_hi(k1.x)};
+          head_norm_rope(x, rr, S.eps, lane);
+          const uint2 kk = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+          *reinterpret_cast<uint2*>(Kc + (size_t)kp * kHeadDim + lane * 4) = kk;
+          f[lane] = kk;
+        }
       }
     }
   }
@@ -1124,12 +1136,11 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
     const int j = threadIdx.x / HW, wd = threadIdx.x - j * HW;
     const int qh = kvh * gq + j;
     const int row = gr.first_row + r;
+    const int nw = min(kConsumerWarps, (b - a + 1) >> 1);  // warps that saw at least one position
     float Mx = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < kConsumerWarps; ++w) Mx = fmaxf(Mx, wp[((size_t)w * kGq + j) * kPartStride]);
+    for (int w = 0; w < nw; ++w) Mx = fmaxf(Mx, wp[((size_t)w * kGq + j) * kPartStride]);
     float Lsum = 0.f, O0 = 0.f, O1 = 0.f;
-#pragma unroll
-    for (int w = 0; w < kConsumerWarps; ++w) {
+    for (int w = 0; w < nw; ++w) {
       const float* q = wp + ((size_t)w * kGq + j) * kPartStride;
       const float f = (q[0] == -INFINITY) ? 0.f : expf(q[0] - Mx);
       Lsum += q[1] * f;
