@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/fq3_codec.h"
@@ -93,6 +94,81 @@ __device__ __forceinline__ void epilogue_pair(const fq3c_op& o, int row, int col
   }
 }
 
+// Epilogue for eight consecutive columns of one row (the tcgen05 path: a thread owns a row of the accumulator, so it
+// must move whole 16-byte pieces or every store is a partial sector).  Same arithmetic and order as epilogue_pair.
+__device__ __forceinline__ void epilogue_row8(const fq3c_op& o, int row, int col, const float (&acc)[8]) {
+  const bool vec = (col + 8 <= o.N) && !(o.flags & (FQ3C_SWIGLU | FQ3C_OUT_F32)) && ((o.ldc & 7) == 0) &&
+                   (!(o.flags & FQ3C_RESID) || (o.ldr & 7) == 0);
+  if (!vec) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) epilogue_pair(o, row, col + 2 * j, acc[2 * j], acc[2 * j + 1]);
+    return;
+  }
+  if (row >= o.M) return;
+  float v[8];
+  int cm[8];
+  {
+    int c0 = col % o.col_mod;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      cm[j] = c0;
+      if (++c0 == o.col_mod) c0 = 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = acc[j];
+  if (o.flags & FQ3C_BIAS) {
+    const float* b = reinterpret_cast<const float*>(o.bias);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += b[cm[j]];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = bf16r(v[j]);
+  if (o.flags & FQ3C_GELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = bf16r(gelu_f(v[j]));
+  }
+  if (o.flags & FQ3C_SCALE) {
+    const float* sc = reinterpret_cast<const float*>(o.scale);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = bf16r(v[j] * sc[cm[j]]);
+  }
+  if (o.flags & FQ3C_RESID) {
+    const uint4 rr = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(o.res) + (size_t)row * o.ldr + col);
+    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = bf16r(v[2 * j] + __uint_as_float(rw[j] << 16));
+      v[2 * j + 1] = bf16r(v[2 * j + 1] + __uint_as_float(rw[j] & 0xffff0000u));
+    }
+  }
+  if (o.flags & FQ3C_CLAMP) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fminf(fmaxf(v[j], -1.f), 1.f);
+  }
+  {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(o.C) + (size_t)row * o.ldc + col) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (o.flags & FQ3C_SNAKE2) {
+    const float* ea = reinterpret_cast<const float*>(o.p0);
+    const float* ib = reinterpret_cast<const float*>(o.p1);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float s0 = sinf(v[2 * j] * ea[cm[2 * j]]), s1 = sinf(v[2 * j + 1] * ea[cm[2 * j + 1]]);
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j] + ib[cm[2 * j]] * s0 * s0, v[2 * j + 1] + ib[cm[2 * j + 1]] * s1 * s1);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(o.C2) + (size_t)row * o.ldc + col) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // Implicit-GEMM convolution / linear layer on the bf16 tensor cores (mma.sync m16n8k16, fp32 accumulate).
 __global__ void __launch_bounds__(128) fq3c_gemm_kernel(const fq3c_op o) {
   __shared__ __align__(16) bf16 As[2][BM][LDS];
@@ -175,6 +251,187 @@ __global__ void __launch_bounds__(128) fq3c_gemm_kernel(const fq3c_op o) {
       epilogue_pair(o, row, col, acc[i][j][0], acc[i][j][1]);
       epilogue_pair(o, row + 8, col, acc[i][j][2], acc[i][j][3]);
     }
+}
+
+// =================================================================================================
+// tcgen05 path of the implicit GEMM (sm_100a): 128 x BN x 64 tiles, accumulator in tensor memory.
+//
+// A tile is K-major with the 128-byte swizzle the tensor core expects (the layout a TMA box with SWIZZLE_128B writes):
+// row r of the tile is one 128-byte line (64 bf16), its 16-byte chunk c lives at r * 128 + ((c ^ (r & 7)) << 4).  The
+// tiles are filled with cp.async so that the time-shifted (tap) rows of the implicit GEMM and the zero padding stay a
+// per-chunk address computation; eight lanes cover one 128-byte line of a row, so global reads are coalesced and the
+// swizzle makes the shared-memory writes conflict-free.  One thread issues tcgen05.mma (4 x k16 per stage) and commits to
+// the stage's mbarrier; the epilogue reads the accumulator with tcgen05.ld (one TMEM lane = one output row per thread).
+// =================================================================================================
+constexpr int TM = 128, TK = 64, TSTAGES = 6;
+constexpr int TLOADERS = 256;                 // warps 0-3 fill A, warps 4-7 fill B; warp 8 issues the MMAs
+constexpr int TTHREADS = TLOADERS + 32;
+constexpr int TMAXN = 128;
+constexpr int T_A_BYTES = TM * TK * 2;        // 16 KB
+constexpr int T_B_BYTES = TMAXN * TK * 2;     // 16 KB
+constexpr int T_SMEM = TSTAGES * (T_A_BYTES + T_B_BYTES) + 1024 /*alignment*/ + 256 /*barriers + tmem pointer*/;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(20);
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B: start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 1024 B (8 rows) | version 1 | layout 2
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// Warp-specialised: the loader warps run up to TSTAGES k-blocks ahead of the tensor core (full / empty mbarriers per stage,
+// cp.async completion counted straight into the full barrier), one thread issues the MMAs, all eight loader warps drain
+// the accumulator.  No block-wide barrier inside the k loop.
+__global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_op o, const int BN) {
+  extern __shared__ unsigned char tsmem_raw[];
+  const uint32_t raw = smem_u32(tsmem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
+  unsigned char* gbase = tsmem_raw + (base - raw);
+  const uint32_t a_smem = base, b_smem = base + TSTAGES * T_A_BYTES;
+  const uint32_t bars = base + TSTAGES * (T_A_BYTES + T_B_BYTES);  // full[TSTAGES] | empty[TSTAGES] | done | tmem base address
+  const uint32_t full = bars, empty = bars + 8u * TSTAGES, done = bars + 16u * TSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + TSTAGES * (T_A_BYTES + T_B_BYTES) + 16 * TSTAGES + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
+  const bf16* A = reinterpret_cast<const bf16*>(o.A);
+  const bf16* B = reinterpret_cast<const bf16*>(o.B);
+  const int KT = (o.K + TK - 1) / TK;
+
+  if (tid == 0) {
+    for (int s = 0; s < TSTAGES; ++s) {
+      mbar_init(full + 8u * s, TLOADERS);
+      mbar_init(empty + 8u * s, 1);
+    }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMAXN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      for (int kt = 0; kt < KT; ++kt) {
+        const int st = kt % TSTAGES;
+        mbar_wait(full + 8u * st, (uint32_t)((kt / TSTAGES) & 1));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) writes -> tensor core (async proxy) reads
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = a_smem + (uint32_t)st * T_A_BYTES, b0 = b_smem + (uint32_t)st * T_B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TK / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(a0 + kk * 32), db = umma_desc_sw128(b0 + kk * 32);
+          const uint32_t acc = (kt > 0 || kk > 0) ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+              ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+              : "memory");
+        }
+        // frees the stage once its MMAs have read it (implies tcgen05.fence::before_thread_sync)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8u * st) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done) : "memory");
+    }
+  } else {
+    // ------------------------------ loaders ------------------------------
+    // warps 0-3: A rows r0 + 16 i (i < 8), chunk c; warps 4-7: B rows likewise.  Eight lanes cover one 128-byte line of a row.
+    const int lt = tid & 127, c = lt & 7, r0 = lt >> 3;
+    const bool is_a = warp < 4;
+    for (int kt = 0; kt < KT; ++kt) {
+      const int st = kt % TSTAGES;
+      if (kt >= TSTAGES) {  // one lane per warp polls: 256 spinning threads would swamp the shared-memory pipe the copies need
+        if (lane == 0) mbar_wait(empty + 8u * st, (uint32_t)(((kt / TSTAGES) - 1) & 1));
+        __syncwarp();
+      }
+      const int k0 = kt * TK + c * 8;
+      const bool kok = k0 < o.K;
+      if (is_a) {
+        const int tap = k0 / o.cin, ci = k0 - tap * o.cin;
+        const int toff = (tap < 8) ? o.tap_off[tap] : 0;
+        const uint32_t sbase = a_smem + (uint32_t)st * T_A_BYTES;
+#pragma unroll
+        for (int i = 0; i < TM / 16; ++i) {
+          const int r = r0 + i * 16;
+          const int m = m0 + r;
+          const int srow = m + toff;
+          const bool ok = kok && (m < o.M) && (srow >= 0) && (srow < o.a_rows);
+          const bf16* src = ok ? (A + (size_t)srow * o.lda + ci) : A;
+          const uint32_t dst = sbase + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+          const int sz = ok ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+        }
+      } else {
+        const uint32_t sbase = b_smem + (uint32_t)st * T_B_BYTES;
+        for (int r = r0; r < BN; r += 16) {
+          const int n = n0 + r;
+          const bool ok = kok && (n < o.N);
+          const bf16* src = ok ? (B + (size_t)n * o.K + k0) : B;
+          const uint32_t dst = sbase + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+          const int sz = ok ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+        }
+      }
+      // counted as one arrival on the stage's full barrier when this thread's copies have landed
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full + 8u * st) : "memory");
+    }
+    // ------------------------------ epilogue ------------------------------
+    if (lane == 0) mbar_wait(done, 0u);
+    __syncwarp();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // warp w reads TMEM lanes 32 * (w & 3) .. +31 (= output rows); warps 0-3 take the first half of the columns, 4-7 the second
+    const int row = m0 + (warp & 3) * 32 + lane;
+    const int chunks = (BN + 31) / 32;  // 32-column chunks in the tile
+    const int per = (chunks + 1) / 2;
+    const int c_begin = (warp >> 2) * per, c_end = min(chunks, c_begin + per);
+    for (int cc = c_begin; cc < c_end; ++cc) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(cc * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+          "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (cc * 32 + 8 * j < BN) {
+          float a8[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) a8[q] = __uint_as_float(v[8 * j + q]);
+          epilogue_row8(o, row, n0 + cc * 32 + 8 * j, a8);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMAXN) : "memory");
 }
 
 // RVQ dequantiser front half: gather + sum codebook rows. C[m, 0:dim] = sum of the first i0 groups, C[m, dim:2dim] = rest.
@@ -344,6 +601,35 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
     switch (o.kind) {
       case FQ3C_GEMM: {
         if (o.K % 8 || o.cin % 8 || o.taps > 8 || o.col_mod <= 0) return fail("gemm: K and cin must be multiples of 8, taps <= 8");
+        static int use_tc5 = -1;
+        if (use_tc5 < 0) {
+          const char* e = getenv("FQ3C_TCGEN05");
+          use_tc5 = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+          if (use_tc5 && cudaFuncSetAttribute(fq3c_gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess)
+            return fail("cannot reserve shared memory for the tcgen05 GEMM");
+        }
+        if (use_tc5 && o.N >= 16 && o.K >= 4 * TK) {
+          // Tile width: a multiple of 16 columns (a legal UMMA N at M = 128), chosen so that the grid covers the SMs.
+          // Tall operands (M >= 128) keep BN >= 64 (every column tile re-reads the A rows); short ones (the transformer at
+          // 8-33 frames) are weight-streaming problems: the width that minimises waves x tile cost, down to 16 columns.
+          const int mt = (o.M + TM - 1) / TM;
+          int bn = TMAXN;
+          if (o.M >= TM) {
+            if (((o.N + bn - 1) / bn) * mt < 100) bn = 64;
+          } else {
+            long best = -1;
+            for (int cand = TMAXN; cand >= 16; cand >>= 1) {
+              const long tiles = (long)((o.N + cand - 1) / cand) * mt;
+              const long cost = ((tiles + 147) / 148) * (cand + 48);  // waves x (columns + fixed per-tile work)
+              if (best < 0 || cost < best) { best = cost; bn = cand; }
+            }
+          }
+          const int nt = (o.N + bn - 1) / bn;
+          bn = std::min(TMAXN, (((o.N + nt - 1) / nt) + 15) / 16 * 16);
+          dim3 grid((o.N + bn - 1) / bn, mt);
+          fq3c_gemm_tc5_kernel<<<grid, TTHREADS, T_SMEM, s>>>(o, bn);
+          break;
+        }
         dim3 grid((o.N + BN - 1) / BN, (o.M + BM - 1) / BM);
         fq3c_gemm_kernel<<<grid, 128, 0, s>>>(o);
         break;
