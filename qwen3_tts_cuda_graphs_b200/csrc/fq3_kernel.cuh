@@ -813,6 +813,7 @@ __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph
       Spin spin;
       if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
       while (!stop && !mbar_try_wait_a(gemptyb, gcur.lap ^ 1u)) {
+        __nanosleep(100);
         if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
         spin.tick(p, DE_EMPTY_WAIT, pidx, 100 + gcur.slot);
       }
@@ -838,6 +839,7 @@ __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph
         Spin spin;
         if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
         while (!stop && !mbar_try_wait_a(emptyb, cur.lap ^ 1u)) {
+          __nanosleep(100);  // the ring is full most of the time: do not compete with the consumer warps for issue slots
           if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
           spin.tick(p, DE_EMPTY_WAIT, pidx, cur.slot);
         }
@@ -1634,30 +1636,62 @@ __device__ __noinline__ int sample_fast(const LLWord* ll, uint32_t ep, const Lau
     }
   }
   prof_mark(*lp, pidx, 1);
+  prof_warp_time(*lp, pidx, 0);
   float x[8] = {bf_lo(wa.x), bf_hi(wa.x), bf_lo(wa.z), bf_hi(wa.z), bf_lo(wb.x), bf_hi(wb.x), bf_lo(wb.z), bf_hi(wb.z)};
   // ---- penalty, suppression, temperature (each result rounded to bf16 like the reference's bf16 tensor ops)
   unsigned long long seen8 = 0ull;
   if (a.seen && a.rep_pen != 1.0f && 8 * tid < V) seen8 = __ldcg(reinterpret_cast<const unsigned long long*>(a.seen + 8 * tid));
+  {
+    // copies of the policy in registers (the argument block lives in local memory), and a fast path for the common
+    // thread whose eight logits need neither penalty nor suppression
+    const int V_ = a.V, sup0 = a.suppress_start, eos = a.eos, sup_eos = a.suppress_eos, smp = a.do_sample;
+    const float temp = a.temperature, pen = a.rep_pen;
+    const int i0 = 8 * tid;
+    const bool plain = (seen8 == 0ull) && (i0 + 8 <= V_) && (i0 + 8 <= sup0) && !(sup_eos && eos >= i0 && eos < i0 + 8);
+    // x / T, correctly rounded for the finite, normal values that occur here: reciprocal + one fused residual correction
+    const float rcp = __frcp_rn(temp);
+    auto div_t = [&](float v) {
+      const float q = v * rcp;
+      return fmaf(fmaf(-q, temp, v), rcp, q);
+    };
+    if (i0 >= V_) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = 8 * tid + j;
-    float v = x[j];
-    if ((seen8 >> (8 * j)) & 0xffull) v = bf16r((v > 0.f) ? v / a.rep_pen : v * a.rep_pen);
-    if (i >= a.suppress_start && i != a.eos) v = -INFINITY;
-    if (a.suppress_eos && i == a.eos) v = -INFINITY;
-    if (a.do_sample) v = bf16r(v / a.temperature);
-    if (i >= V) v = -INFINITY;
-    x[j] = v;
+      for (int j = 0; j < 8; ++j) x[j] = -INFINITY;
+    } else if (plain) {
+      if (smp) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = bf16r(div_t(x[j]));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j;
+        float v = x[j];
+        if ((seen8 >> (8 * j)) & 0xffull) v = bf16r((v > 0.f) ? v / pen : v * pen);
+        if (i >= sup0 && i != eos) v = -INFINITY;
+        if (sup_eos && i == eos) v = -INFINITY;
+        if (smp && v > -INFINITY) v = bf16r(div_t(v));
+        if (i >= V_) v = -INFINITY;
+        x[j] = v;
+      }
+    }
   }
   // ---- maximum and its lowest index; the first radix pass (high byte of the 16-bit keys) shares its barrier
   const bool want_k = a.do_sample && a.top_k > 0 && a.top_k < V;
   uint32_t key[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) key[j] = bf16_key(x[j]);
-  if (want_k) {
+  if (want_k && 8 * tid < V) {
+    // logits sit in a handful of binades: a thread's eight keys mostly share their high byte, so count those once
+    const uint32_t d0 = key[0] >> 8;
+    unsigned same = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (8 * tid + j < V) atomicAdd(&hist[key[j] >> 8], 1u);
+    for (int j = 0; j < 8; ++j) {
+      const bool in = 8 * tid + j < V;
+      if (in && (key[j] >> 8) == d0) ++same;
+      else if (in) atomicAdd(&hist[key[j] >> 8], 1u);
+    }
+    if (same) atomicAdd(&hist[d0], same);
   }
   float bv = x[0];
   int bi = 8 * tid;
@@ -1671,6 +1705,7 @@ __device__ __noinline__ int sample_fast(const LLWord* ll, uint32_t ep, const Lau
     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
   }
   if (lane == 0) { redf[warp] = bv; redi[warp] = bi; }
+  prof_warp_time(*lp, pidx, 1);
   cbar_sync();  // (1)
   auto select = [&](unsigned* h, int krem, int slot) {  // warp 0: highest digit whose cumulative count (from the top) reaches krem
     if (warp == 0) {

@@ -37,6 +37,7 @@ for i in range(15 * per_pass - 1):
         agg[kind].append(ends[i] - starts[i])
 tot = 0
 for k, v in agg.items():
+    if not v: continue
     v2 = sorted(v)
     print(f"{k:7s} n={len(v):3d} median {v2[len(v2)//2]:6d} cycles  min {v2[0]:6d} max {v2[-1]:6d}  sum {sum(v):8d}")
     tot += sum(v)
@@ -49,5 +50,14 @@ for i in range(26, 15 * per_pass, per_pass):
     if not m[0] or not m[3]: continue
     rows.append((m[1] - m[0], m[2] - m[1], m[4] - m[2], m[5] - m[4], m[6] - m[5], m[3] - m[6], m[3] - m[0]))
 for r in rows[:4]: print("   ", r)
-n = len(rows)
+n = max(len(rows), 1)
 print("avg ", tuple(int(sum(r[k] for r in rows) / n) for k in range(7)))
+
+if os.environ.get("FQ3_PROF") == "-3":
+    for i in (26, 53, 80):
+        a = [buf[(i * 160 + wp) * 2] for wp in range(12)]
+        b = [buf[(i * 160 + wp) * 2 + 1] for wp in range(12)]
+        if not any(a): continue
+        t0 = min(v for v in a + b if v)
+        print(f"sample phase {i}: poll-done per warp " + " ".join(f"{v - t0:6d}" for v in a))
+        print(f"                 at barrier 1      " + " ".join(f"{v - t0:6d}" for v in b))
