@@ -59,8 +59,13 @@ int fq3c_abi_version(void);
 const char* fq3c_last_error(void);
 /* Launch every op in order on `stream` (no synchronisation). Returns 0 or a negative error code. */
 int fq3c_run(const fq3c_op* ops, int n_ops, void* stream);
-/* number of kernel launches issued so far by this process through fq3c_run */
+/* number of kernel launches issued so far by this process through fq3c_run / fq3c_graph_launch */
 int64_t fq3c_launch_count(void);
+/* A decode plan is static for a given frame count: capture its launches once (stream capture of fq3c_run) and replay
+ * them as one CUDA graph.  The ops' buffers must stay alive and at the same addresses for the life of the graph. */
+int fq3c_graph_create(const fq3c_op* ops, int n_ops, void** out_graph);
+int fq3c_graph_launch(void* graph, void* stream);
+int fq3c_graph_destroy(void* graph);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,12 @@ def load_lib():
     lib.fq3c_run.restype = C.c_int
     lib.fq3c_run.argtypes = [C.POINTER(Op), C.c_int, C.c_void_p]
     lib.fq3c_launch_count.restype = C.c_int64
+    lib.fq3c_graph_create.restype = C.c_int
+    lib.fq3c_graph_create.argtypes = [C.POINTER(Op), C.c_int, C.POINTER(C.c_void_p)]
+    lib.fq3c_graph_launch.restype = C.c_int
+    lib.fq3c_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fq3c_graph_destroy.restype = C.c_int
+    lib.fq3c_graph_destroy.argtypes = [C.c_void_p]
     if lib.fq3c_abi_version() != 1:
         raise CodecError("libfq3codec.so ABI version mismatch")
     _lib = lib
@@ -169,6 +175,9 @@ class _Plan:
         self.codes: Optional[torch.Tensor] = None
         self.wav: Optional[torch.Tensor] = None
         self.arr = None
+        self.runs = 0
+        self.graph = None          # fq3c_graph handle once the plan has been captured
+        self.graph_failed = False
 
 
 class CodecDecoder:
@@ -180,6 +189,7 @@ class CodecDecoder:
         if self.device.type != "cuda":
             raise ValueError("the fq3 codec decoder runs on CUDA only (no CPU fallback)")
         self.lib = load_lib()
+        self.use_graphs = os.environ.get("FQ3C_GRAPH", "1") != "0"
         self._plans: Dict[int, _Plan] = {}
         self.g: Dict[str, torch.Tensor] = {}
         self._pack(weights)
@@ -382,7 +392,19 @@ class CodecDecoder:
         """Launch a plan's op list on the current stream (also the hook the per-op parity tests use)."""
         if plan.arr is None:
             plan.arr = (Op * len(plan.ops))(*plan.ops)
-        rc = self.lib.fq3c_run(plan.arr, len(plan.ops), torch.cuda.current_stream().cuda_stream)
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.use_graphs and plan.runs >= 1 and getattr(plan, "graph", None) is None and not plan.graph_failed:
+            # second use of a cached plan: its launches are static, replay them as one CUDA graph from now on
+            h = C.c_void_p()
+            if self.lib.fq3c_graph_create(plan.arr, len(plan.ops), C.byref(h)) == 0:
+                plan.graph = h
+            else:
+                plan.graph_failed = True
+        plan.runs += 1
+        if getattr(plan, "graph", None) is not None:
+            rc = self.lib.fq3c_graph_launch(plan.graph, stream)
+        else:
+            rc = self.lib.fq3c_run(plan.arr, len(plan.ops), stream)
         if rc != 0:
             raise CodecError(self.lib.fq3c_last_error().decode())
 
@@ -406,7 +428,9 @@ class CodecDecoder:
             # streaming revisits a handful of sizes (chunk multiples, then chunk+25); long one-shot decodes are
             # not worth pinning gigabytes of activation buffers for
             for k in [k for k in self._plans if k > 96 or len(self._plans) >= 24]:
-                self._plans.pop(k)
+                old = self._plans.pop(k)
+                if old.graph is not None:
+                    self.lib.fq3c_graph_destroy(old.graph)
             plan = self._plans[T] = self._build(T)
         plan.codes.copy_(codes.to(torch.int64), non_blocking=True)
         self.run_plan(plan)

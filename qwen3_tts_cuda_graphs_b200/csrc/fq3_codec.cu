@@ -663,4 +663,54 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
   return 0;
 }
 
+
+/* A plan is static (same ops, same buffers for a given frame count): capture its launches once and replay them as one
+ * CUDA graph (about a hundred short kernels per decode; the replay removes the per-launch CPU and scheduling gaps). */
+struct fq3c_graph {
+  cudaGraphExec_t exec;
+  int n_kernels;
+};
+int fq3c_graph_create(const fq3c_op* ops, int n_ops, void** out) {
+  if (!ops || !out || n_ops <= 0) return fail("graph: bad arguments");
+  cudaStream_t cs;
+  if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) return fail("graph: stream create failed");
+  const int64_t before = g_launches;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  int rc = 0;
+  if (e == cudaSuccess) {
+    rc = fq3c_run(ops, n_ops, cs);
+    e = cudaStreamEndCapture(cs, &g);
+  }
+  const int n_kernels = (int)(g_launches - before);
+  g_launches = before;  // nothing ran yet
+  cudaStreamDestroy(cs);
+  if (rc != 0 || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    return rc != 0 ? rc : fail(std::string("graph: capture failed: ") + cudaGetErrorString(e));
+  }
+  cudaGraphExec_t ex = nullptr;
+  e = cudaGraphInstantiate(&ex, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(std::string("graph: instantiate failed: ") + cudaGetErrorString(e));
+  *out = new fq3c_graph{ex, n_kernels};
+  return 0;
+}
+int fq3c_graph_launch(void* graph, void* stream) {
+  fq3c_graph* g = reinterpret_cast<fq3c_graph*>(graph);
+  if (!g) return fail("graph: null handle");
+  const cudaError_t e = cudaGraphLaunch(g->exec, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(std::string("graph: launch failed: ") + cudaGetErrorString(e));
+  g_launches += g->n_kernels;
+  return 0;
+}
+int fq3c_graph_destroy(void* graph) {
+  fq3c_graph* g = reinterpret_cast<fq3c_graph*>(graph);
+  if (g) {
+    cudaGraphExecDestroy(g->exec);
+    delete g;
+  }
+  return 0;
+}
+
 }  // extern "C"
