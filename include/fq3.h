@@ -124,6 +124,14 @@ int fq3_set_loop_state(fq3_engine* e, int stream_idx, int token, const void* pas
  * fq3_decode_frames.  out_logits (optional) receives the last-row logits as fp32 [V_t]. */
 int fq3_prefill(fq3_engine* e, int stream_idx, const void* embeds, int T, int n_left_pad,
                 const fq3_policy* policy, void* out_logits, void* stream);
+/* Prefill whose first T - n_tail rows were computed elsewhere (the dense tensor-core prefill writes their K/V straight
+ * into the static cache, fq3_kv_cache_ptr): only rows [T - n_tail, T) go through the decode kernel, then head + first-token
+ * sample exactly as fq3_prefill.  embeds_tail: bf16 [n_tail, H_t].  No left padding on this path. */
+int fq3_prefill_tail(fq3_engine* e, int stream_idx, const void* embeds_tail, int T, int n_tail, const fq3_policy* policy,
+                     void* out_logits, void* stream);
+/* Device address of one layer's static talker cache of one stream: bf16 [n_kv_heads][max_seq_len][head_dim];
+ * which = 0 keys, 1 values (the StaticCache of talker_graph.py:43). */
+void* fq3_kv_cache_ptr(fq3_engine* e, int stream_idx, int layer, int which);
 /* TalkerGraph.run (talker_graph.py:198-214): one decode step of the 28-layer backbone.
  * embeds bf16 [H_t]; out_hidden bf16 [H_t] (post final norm); out_logits optional fp32 [V_t]
  * (= codec_head(out_hidden), generate.py:182). */

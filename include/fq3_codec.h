@@ -26,7 +26,11 @@ enum fq3c_kind {
   FQ3C_ATTN = 4,      /* A=qkv [M, lda] (q | k | v), i0 heads, i1 kv heads, i2 head_dim, window K; C[M, i0*i2] */
   FQ3C_DWCONV = 5,    /* depthwise causal conv k=taps: C[m,c] = bias[c] + sum_j B(f32)[c,j] A[m-(taps-1)+j, c]  */
   FQ3C_LAYERNORM = 6, /* C = layernorm(A) * scale + bias (f32), eps=f0                                      */
-  FQ3C_SNAKE = 7      /* C = A + p1[c] * sin(A * p0[c])^2   (p0 = exp(alpha), p1 = 1/(exp(beta)+1e-9))      */
+  FQ3C_SNAKE = 7,     /* C = A + p1[c] * sin(A * p0[c])^2   (p0 = exp(alpha), p1 = 1/(exp(beta)+1e-9))      */
+  FQ3C_QKNORM_ROPE_KV = 8 /* dense talker prefill: A = fused qkv rows [M, lda], i0 q heads, i1 kv heads of dim 128; q/k heads get the
+                             per-head RMSNorm (bf16 gamma p0 / p1, eps f0) and the rotary embedding from the bf16 tables B (cos) /
+                             bias (sin) at position row + i2, in place; finished k / v rows also go to the static KV cache
+                             C (K) / C2 (V), each [kv_head][ldc][128] (talker_graph.py:153-170 without the copy)            */
 };
 
 enum fq3c_flags {

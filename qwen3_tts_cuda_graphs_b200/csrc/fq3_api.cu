@@ -579,10 +579,11 @@ static size_t decode_x_elems(const fq3_engine* e, int n_streams, bool talker, bo
   return n;
 }
 
-int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pad, const fq3_policy* policy,
-                void* out_logits, void* stream) {
+// rows [start, T) of the prompt go through the persistent kernel; the K/V rows of [0, start) must already be in the cache
+static int prefill_impl(fq3_engine* e, int idx, const void* embeds_from_start, int T, int start, int n_left_pad, const fq3_policy* policy,
+                        void* out_logits, void* stream) {
   if (int r = check_stream(e, idx)) return r;
-  if (!embeds || !policy || T <= 0) return fail(FQ3_E_INVALID, "bad prefill arguments");
+  if (!embeds_from_start || !policy || T <= 0 || start < 0 || start >= T) return fail(FQ3_E_INVALID, "bad prefill arguments");
   if (T > e->tk.d.max_pos) {
     char b[200];
     snprintf(b, sizeof b, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter "
@@ -595,10 +596,10 @@ int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pa
   fq3_reset_stream_kernel<<<1, 256, 0, s>>>(e->d_st + idx, e->tk.d.vocab);
   fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, 0, 0, 2, n_left_pad, -n_left_pad, 0);
   e->launches += 2;
-  for (int c0 = 0; c0 < T; c0 += Mmax) {
+  for (int c0 = start; c0 < T; c0 += Mmax) {
     const int rows = std::min(Mmax, T - c0);
     const bool final = (c0 + rows == T);
-    if (int r = pack_ll(e, BUF_TX, 0, reinterpret_cast<const bf16*>(embeds) + (size_t)c0 * Ht, Ht, rows, Ht, s)) return r;
+    if (int r = pack_ll(e, BUF_TX, 0, reinterpret_cast<const bf16*>(embeds_from_start) + (size_t)(c0 - start) * Ht, Ht, rows, Ht, s)) return r;
     LaunchParams p{};
     fill_common(e, p);
     p.prog = e->d_prefill;
@@ -616,6 +617,24 @@ int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pa
   if (out_logits)
     if (int r = unpack_f32(e, out_logits, e->tk.d.vocab, BUF_LOGITS, 0, 1, e->tk.d.vocab, s)) return r;
   return 0;
+}
+
+int fq3_prefill(fq3_engine* e, int idx, const void* embeds, int T, int n_left_pad, const fq3_policy* policy,
+                void* out_logits, void* stream) {
+  return prefill_impl(e, idx, embeds, T, 0, n_left_pad, policy, out_logits, stream);
+}
+
+int fq3_prefill_tail(fq3_engine* e, int idx, const void* embeds_tail, int T, int n_tail, const fq3_policy* policy, void* out_logits,
+                     void* stream) {
+  if (n_tail < 1 || n_tail > T) return fail(FQ3_E_INVALID, "bad prefill tail");
+  return prefill_impl(e, idx, embeds_tail, T, T - n_tail, 0, policy, out_logits, stream);
+}
+
+void* fq3_kv_cache_ptr(fq3_engine* e, int idx, int layer, int which) {
+  if (!e || idx < 0 || idx >= e->desc.max_streams || layer < 0 || layer >= e->rt[0].n_layers) return nullptr;
+  const StackRt& S = e->rt[0];
+  const size_t base = ((size_t)layer * S.n_slots + idx) * S.nkv * (size_t)S.max_pos * kHeadDim;
+  return (which ? S.vcache : S.kcache) + base;
 }
 
 int fq3_talker_step(fq3_engine* e, int idx, const void* embeds, int position, void* out_hidden, void* out_logits,

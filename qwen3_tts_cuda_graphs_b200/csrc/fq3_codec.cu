@@ -552,6 +552,50 @@ __global__ void fq3c_attn_kernel(const fq3c_op o) {
   }
 }
 
+// Dense prefill helper (talker): one warp per (row, head) of the fused qkv rows A [M, lda] = (q heads | k heads | v heads).
+//   q / k heads: per-head RMSNorm with bf16 gamma (q: p0, k: p1), HF rounding points, then rotary embedding from the bf16
+//                tables B (cos) / bias (sin) at position row + i2 (rotate-half), in place;
+//   k / v heads: the finished row is also written to the static KV cache C (K) / C2 (V), laid out [kv_head][ldc][128].
+// Same arithmetic as head_norm_rope / the KV append of the decode kernel (fq3_kernel.cuh), so decode steps can attend to it.
+__global__ void fq3c_qknorm_rope_kv_kernel(const fq3c_op o) {
+  const int nq = o.i0, nkv = o.i1, pos0 = o.i2, nheads = nq + 2 * nkv;
+  const int wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gw >= o.M * nheads) return;
+  const int t = gw / nheads, h = gw - t * nheads;
+  bf16* row = reinterpret_cast<bf16*>(const_cast<void*>(o.A)) + (size_t)t * o.lda + (size_t)h * 128 + lane * 4;
+  uint2 raw = *reinterpret_cast<const uint2*>(row);
+  const int pos = pos0 + t;
+  if (h < nq + nkv) {
+    const bf16* gamma = reinterpret_cast<const bf16*>(h < nq ? o.p0 : o.p1) + lane * 4;
+    const bf16* cosp = reinterpret_cast<const bf16*>(o.B) + (size_t)pos * 128 + lane * 4;
+    const bf16* sinp = reinterpret_cast<const bf16*>(o.bias) + (size_t)pos * 128 + lane * 4;
+    float x[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                  __uint_as_float(raw.y & 0xffff0000u)};
+    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float rs = rsqrtf(ss * (1.f / 128.f) + o.f0);
+    float y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = bf16r(bf16r(x[i] * rs) * __bfloat162float(gamma[i]));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float partner = __shfl_xor_sync(0xffffffffu, y[i], 16);
+      const float rot = (lane < 16) ? -partner : partner;
+      x[i] = bf16r(bf16r(y[i] * __bfloat162float(cosp[i])) + bf16r(rot * __bfloat162float(sinp[i])));
+    }
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+    raw = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    *reinterpret_cast<uint2*>(row) = raw;
+  }
+  if (h >= nq) {
+    const bool is_v = h >= nq + nkv;
+    const int kvh = is_v ? h - nq - nkv : h - nq;
+    bf16* dst = reinterpret_cast<bf16*>(is_v ? o.C2 : o.C) + ((size_t)kvh * o.ldc + pos) * 128 + lane * 4;
+    *reinterpret_cast<uint2*>(dst) = raw;
+  }
+}
+
 __global__ void fq3c_dwconv_kernel(const fq3c_op o) {
   const size_t n = (size_t)o.M * o.N;
   const bf16* x = reinterpret_cast<const bf16*>(o.A);
@@ -647,6 +691,12 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
       case FQ3C_DWCONV: {
         const size_t n = (size_t)o.M * o.N;
         fq3c_dwconv_kernel<<<(unsigned)std::min<size_t>(2048, (n + 255) / 256), 256, 0, s>>>(o);
+        break;
+      }
+      case FQ3C_QKNORM_ROPE_KV: {
+        if (o.lda % 4 || !o.C || !o.C2 || !o.p0 || !o.p1 || !o.B || !o.bias) return fail("qknorm_rope_kv: missing operand");
+        const int warps = o.M * (o.i0 + 2 * o.i1);
+        fq3c_qknorm_rope_kv_kernel<<<(warps + 7) / 8, 256, 0, s>>>(o);
         break;
       }
       case FQ3C_SNAKE: {

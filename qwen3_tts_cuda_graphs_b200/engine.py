@@ -100,6 +100,8 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.fq3_create(C.byref(desc), C.byref(h)))
         self.h = h
+        self._dense = None        # dense tensor-core prefill plan (prefill_dense.py), built on first use
+        self._dense_tried = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -150,12 +152,27 @@ class Engine:
         _lib.check(self.lib.fq3_set_loop_state(self.h, idx, int(token), ph.data_ptr(), int(position), int(gen_step), _stream()))
 
     # ---- hot path ----
-    def prefill(self, idx: int, embeds: torch.Tensor, n_left_pad: int, policy: SamplingPolicy, want_logits: bool = False):
+    def prefill(self, idx: int, embeds: torch.Tensor, n_left_pad: int, policy: SamplingPolicy, want_logits: bool = False,
+                dense: Optional[bool] = None):
+        """Prompt prefill (generate.py:107-134).  Prompts of more than a few rows take the dense tensor-core path for rows
+        [0, T-1) (prefill_dense.py) and the decode kernel for the last row; `dense=False` forces the chunked path."""
         H = self.cfg.talker.hidden_size
         e = self._bf16(embeds.reshape(-1, H))
+        T = e.shape[0]
         logits = torch.empty(self.cfg.talker.vocab_size, dtype=torch.float32, device=self.device) if want_logits else None
         pol = policy.c()
-        _lib.check(self.lib.fq3_prefill(self.h, idx, e.data_ptr(), e.shape[0], int(n_left_pad), C.byref(pol), _ptr(logits), _stream()))
+        if dense is None:
+            dense = True
+        if dense and int(n_left_pad) == 0 and T <= self.max_seq_len:
+            if self._dense is None and not self._dense_tried:
+                self._dense_tried = True
+                from . import prefill_dense
+                self._dense = prefill_dense.make(self)
+            if self._dense is not None and T - 1 >= self._dense.MIN_ROWS:
+                self._dense.run(idx, e, T - 1)
+                _lib.check(self.lib.fq3_prefill_tail(self.h, idx, e[T - 1:].data_ptr(), T, 1, C.byref(pol), _ptr(logits), _stream()))
+                return logits
+        _lib.check(self.lib.fq3_prefill(self.h, idx, e.data_ptr(), T, int(n_left_pad), C.byref(pol), _ptr(logits), _stream()))
         return logits
 
     def talker_step(self, idx: int, embeds: torch.Tensor, position: int, want_logits: bool = True):
