@@ -510,13 +510,68 @@ __global__ void fq3c_rope_kernel(const fq3c_op o) {
   }
 }
 
-// Sliding-window causal attention, one warp per (query, head); head_dim <= 128.
-__global__ void fq3c_attn_kernel(const fq3c_op o) {
-  const int nh = o.i0, nkv = o.i1, d = o.i2, win = o.K, T = o.M;
-  const int wpb = blockDim.x >> 5;
-  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (gw >= T * nh) return;
-  const int t = gw / nh, h = gw - t * nh, kvh = h / (nh / nkv);
+// Sliding-window causal attention, one warp per (query, head); head_dim in {32, 64, 128}: a lane owns d/32 contiguous
+// dims (one 2/4/8-byte load per K and V row), four keys are scored per step so their shuffle reductions overlap; the
+// online-softmax updates are applied key by key in order.
+template <int PER>
+__device__ __forceinline__ void attn_load(const bf16* p, float (&v)[4]) {
+  if (PER == 4) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+  } else if (PER == 2) {
+    const uint32_t r = *reinterpret_cast<const uint32_t*>(p);
+    v[0] = __uint_as_float(r << 16); v[1] = __uint_as_float(r & 0xffff0000u); v[2] = 0.f; v[3] = 0.f;
+  } else {
+    v[0] = __bfloat162float(p[0]); v[1] = 0.f; v[2] = 0.f; v[3] = 0.f;
+  }
+}
+template <int PER>
+__device__ __forceinline__ void attn_warp(const fq3c_op& o, int t, int h, int lane) {
+  const int nh = o.i0, nkv = o.i1, d = o.i2, win = o.K;
+  const int kvh = h / (nh / nkv);
+  const bf16* base = reinterpret_cast<const bf16*>(o.A);
+  const int qoff = h * d + lane * PER, koff = nh * d + kvh * d + lane * PER, voff = nh * d + nkv * d + kvh * d + lane * PER;
+  float q[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+  attn_load<PER>(base + (size_t)t * o.lda + qoff, q);
+  const float scale = rsqrtf((float)d);
+  float m = -INFINITY, l = 0.f;
+  const int j0 = max(0, t - win + 1);
+  for (int jb = j0; jb <= t; jb += 4) {
+    float s[4], v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = min(jb + u, t);
+      float k[4];
+      attn_load<PER>(base + (size_t)j * o.lda + koff, k);
+      attn_load<PER>(base + (size_t)j * o.lda + voff, v[u]);
+      s[u] = q[0] * k[0] + q[1] * k[1] + q[2] * k[2] + q[3] * k[3];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (jb + u <= t) {
+        const float su = bf16r(bf16r(s[u]) * scale);
+        const float mn = fmaxf(m, su), corr = expf(m - mn), p = expf(su - mn);
+        l = l * corr + p;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) acc[i] = acc[i] * corr + p * v[u][i];
+        m = mn;
+      }
+    }
+  }
+  bf16* out = reinterpret_cast<bf16*>(o.C) + (size_t)t * o.ldc + h * d + lane * PER;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) out[i] = __float2bfloat16_rn(acc[i] / l);
+}
+// any head_dim <= 128 (lane owns dims lane, lane + 32, ...): the small test configurations
+__device__ __forceinline__ void attn_warp_generic(const fq3c_op& o, int t, int h, int lane) {
+  const int nh = o.i0, nkv = o.i1, d = o.i2, win = o.K;
+  const int kvh = h / (nh / nkv);
   const bf16* base = reinterpret_cast<const bf16*>(o.A);
   const int qoff = h * d, koff = nh * d + kvh * d, voff = nh * d + nkv * d + kvh * d;
   const int per = (d + 31) / 32;  // <= 4
@@ -550,6 +605,17 @@ __global__ void fq3c_attn_kernel(const fq3c_op o) {
     const int c = lane + i * 32;
     if (c < d) out[c] = __float2bfloat16_rn(acc[i] / l);
   }
+}
+__global__ void fq3c_attn_kernel(const fq3c_op o) {
+  const int nh = o.i0, T = o.M;
+  const int wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gw >= T * nh) return;
+  const int t = gw / nh, h = gw - t * nh;
+  const bool aligned = ((o.lda * 2) % 8 == 0) && ((o.ldc * 2) % 8 == 0);
+  if (o.i2 == 128 && aligned) attn_warp<4>(o, t, h, lane);
+  else if (o.i2 == 64 && aligned) attn_warp<2>(o, t, h, lane);
+  else attn_warp_generic(o, t, h, lane);
 }
 
 // Dense prefill helper (talker): one warp per (row, head) of the fused qkv rows A [M, lda] = (q heads | k heads | v heads).
