@@ -97,6 +97,8 @@ def load():
             f"{path} is missing: build it with `python -m qwen3_tts_cuda_graphs_b200.build`. "
             "This engine has no CPU or PyTorch fallback."
         )
+    if os.environ.get("FQ3_LIB_PATH"):  # development: A/B a differently compiled build of the same sources
+        path = os.environ["FQ3_LIB_PATH"]
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol

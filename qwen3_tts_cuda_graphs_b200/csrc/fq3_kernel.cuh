@@ -253,7 +253,7 @@ __device__ __forceinline__ void prof_cta_time(const LaunchParams& p, int pidx, i
 // FQ3_PROF=-3: every warp of CTA 0 records clock64 at two points of a phase (k = 0, 1)
 __device__ __forceinline__ void prof_warp_time(const LaunchParams& p, int pidx, int k) {
   if (p.prof && p.prof_cta == -3 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && pidx >= 0 && pidx < 512)
-    p.prof[((size_t)pidx * 160 + (threadIdx.x >> 5)) * 2 + k] = clock64();
+    p.prof[((size_t)pidx * 160 + 16 * (k >> 1) + (threadIdx.x >> 5)) * 2 + (k & 1)] = clock64();
 }
 __device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int slot) {
   if (p.prof && threadIdx.x == 0 && (int)blockIdx.x == p.prof_cta && pidx >= 0 && pidx < 512) p.prof[(size_t)pidx * 16 + slot] = clock64();
@@ -353,6 +353,17 @@ struct RingCur {
   }
 };
 
+// Position of activation word wi (two bf16) in the shared-memory copy of a row: words 1 and 2 of every 16-byte chunk trade
+// places, so that one 16-byte load yields {cols 0-1, cols 4-5, cols 2-3, cols 6-7} of an 8-column chunk — the k-slot order
+// both operand assignments of gemv_unit want.
+__device__ __forceinline__ int xword(int wi) { return (wi & ~3) | ((wi & 1) << 1) | ((wi >> 1) & 1); }
+// the two consecutive words (2q, 2q+1) of pair q land 8 bytes apart
+__device__ __forceinline__ uint32_t xpair_addr(uint32_t xs, int q) { return xs + (uint32_t)(q >> 1) * 16u + (uint32_t)(q & 1) * 4u; }
+__device__ __forceinline__ void xpair_store(uint32_t addr, uint32_t lo, uint32_t hi) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(lo) : "memory");
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + 8u), "r"(hi) : "memory");
+}
+
 // General activation load (several rows, or rows too long for the register path): raw payloads go through shared
 // memory, each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square,
 // x*rsqrt -> bf16, * weight -> bf16.
@@ -391,7 +402,7 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
       for (int i = 0; i < 4; ++i) {
         const int wi = w0 + tid + i * kConsumerThreads;
         if (wi < Kw) {
-          sts_u32(xs + (uint32_t)(m * Kw + wi) * 4u, w[i].x);
+          sts_u32(xs + (uint32_t)(m * Kw + xword(wi)) * 4u, w[i].x);
           const float x0 = bf_lo(w[i].x), x1 = bf_hi(w[i].x);
           ss = fmaf(x0, x0, ss);
           ss = fmaf(x1, x1, ss);
@@ -415,25 +426,35 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
 #pragma unroll 1
     for (int wi = tid; wi < Kw; wi += kConsumerThreads) {
       const uint32_t gg = lds_u32(gam + (uint32_t)wi * 4u);
-      const uint32_t v = lds_u32(xs + (uint32_t)(m * Kw + wi) * 4u);
+      const uint32_t v = lds_u32(xs + (uint32_t)(m * Kw + xword(wi)) * 4u);
       const uint32_t y = pack_bf16x2(bf16r(bf16r(bf_lo(v) * rs) * bf_lo(gg)), bf16r(bf16r(bf_hi(v) * rs) * bf_hi(gg)));
-      sts_u32(xs + (uint32_t)(m * Kw + wi) * 4u, y);
+      sts_u32(xs + (uint32_t)(m * Kw + xword(wi)) * 4u, y);
       if (wr) reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID])[wi] = y;
     }
   }
   cbar_sync();
 }
 
-// One warp's share of a stage: 16 weight rows x (nblk * 64) columns against up to 4 activation rows.
+// One warp's share of a stage: 16 weight rows x (nblk * 64) columns against up to 4 activation rows, on mma.m16n8k16
+// (lane = 4*g + t).  A lane reads 16 contiguous bytes (8 columns) of each of its two weight rows (g, g+8) per load; which 8
+// columns depends on (g & 1, t) so that a quarter-warp (rows 2j, 2j+1) covers 128 contiguous bytes -> conflict-free although
+// all rows of a stage start in the same bank.  It reads the SAME chunk of activation row g >> 1 (stored as cols
+// {0-1, 4-5, 2-3, 6-7}, see xword).  Lanes of different parity therefore disagree on which column a k-slot means; every
+// product the MMA forms between an even and an odd lane is garbage and lands in accumulator entries nobody reads.
 //
-// Fragment mapping of mma.m16n8k16 (lane = 4*g + t).  The weights are the A operand: rows g and g+8 of the stage.  A lane
-// reads 16 contiguous bytes (8 columns) of each of its two weight rows per load; which 8 columns depends on (g & 1, t) so
-// that a quarter-warp (rows 2j, 2j+1) covers 128 contiguous bytes -> conflict-free although all rows of a stage start in
-// the same bank.  The activations are the B operand (broadcast loads: 64 distinct bytes per request): column n = g of B carries
-// activation row g>>1 under the column permutation of parity g&1, i.e. exactly the columns this lane also reads of its
-// weight rows.  D[m][n] is only read where m and n have the same parity, so the permutation cancels out.
-// Result: the lane holds dot(weight row g, activation row t) in c[g&1] and dot(weight row g+8, activation row t) in c[2 + (g&1)].
-// Two accumulator sets per half keep the dependent HMMA chain at a quarter of the MMA count.
+// HI = true (stages with more than 8 rows), weights = A operand: A = {w(g).x, w(g+8).x, w(g).z, w(g+8).z} (cols 0-1 | 4-5) against
+// B = (x.x, x.y), then the (y, w) / (z, w) halves.  D[row][n] is valid where row and n have the same parity and n >> 1 is the
+// activation row: the lane holds dot(weight row g, activation row t) in c[g&1] and row g+8 in c[2 + (g&1)].  Needs four
+// register moves per HMMA (the A registers come from two loads) but only half the HMMAs of the other assignment.
+//
+// HI = false (<= 8 rows: o_proj / down_proj slices), activations = A operand: A = the activation load as it is (row g of A sees
+// cols 0-3, row g+8 cols 4-7), B = (w.x, w.y) -> valid in D row g, B = (w.z, w.w) -> valid in D row g+8; no moves, and rows 8-15
+// are neither loaded nor multiplied.  The lane holds dot(weight row 2t + (g&1), activation row g >> 1) in c0[g&1] + c1[2 + (g&1)].
+//
+// For nblk == 4 (every K % 512 == 0, i.e. all real shapes) the code is straight-line with the loads of block i+2 issued right
+// behind the MMAs of block i: the warps of a CTA start their stages at the same barrier, so without the overlap inside the
+// warp they alternate between the shared-memory pipe and the tensor pipe in lock-step.
+template <bool HI>
 __device__ __forceinline__ void gemv_unit(uint32_t w0, uint32_t xrow, uint32_t oA, uint32_t oB, int nblk, int h0, float& v_lo, float& v_hi) {
   float c[4][4];
 #pragma unroll
@@ -442,25 +463,54 @@ __device__ __forceinline__ void gemv_unit(uint32_t w0, uint32_t xrow, uint32_t o
     for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
   }
   const uint32_t w1 = w0 + 8u * kRowPitch;
-  auto block = [&](uint32_t o, float (&ca)[4], float (&cb)[4]) {
-    const uint4 xa = lds128(xrow + o + oA), xb = lds128(xrow + o + oB);
-    const uint4 a0 = lds128(w0 + o + oA), a1 = lds128(w1 + o + oA);
-    const uint4 b0 = lds128(w0 + o + oB), b1 = lds128(w1 + o + oB);
-    mma_bf16(ca, a0.x, a1.x, a0.y, a1.y, xa.x, xa.y);
-    mma_bf16(cb, b0.x, b1.x, b0.y, b1.y, xb.x, xb.y);
-    mma_bf16(ca, a0.z, a1.z, a0.w, a1.w, xa.z, xa.w);
-    mma_bf16(cb, b0.z, b1.z, b0.w, b1.w, xb.z, xb.w);
+  struct Frag { uint4 xa, xb, a0, a1, b0, b1; };
+  auto ldblk = [&](Frag& f, uint32_t o) {
+    f.xa = lds128(xrow + o + oA); f.xb = lds128(xrow + o + oB);
+    f.a0 = lds128(w0 + o + oA);
+    if constexpr (HI) f.a1 = lds128(w1 + o + oA);
+    f.b0 = lds128(w0 + o + oB);
+    if constexpr (HI) f.b1 = lds128(w1 + o + oB);
   };
+  auto mmablk = [&](const Frag& f, float (&ca)[4], float (&cb)[4]) {
+    if constexpr (HI) {
+      mma_bf16(ca, f.a0.x, f.a1.x, f.a0.z, f.a1.z, f.xa.x, f.xa.y);
+      mma_bf16(cb, f.b0.x, f.b1.x, f.b0.z, f.b1.z, f.xb.x, f.xb.y);
+      mma_bf16(ca, f.a0.y, f.a1.y, f.a0.w, f.a1.w, f.xa.z, f.xa.w);
+      mma_bf16(cb, f.b0.y, f.b1.y, f.b0.w, f.b1.w, f.xb.z, f.xb.w);
+    } else {
+      mma_bf16(ca, f.xa.x, f.xa.y, f.xa.z, f.xa.w, f.a0.x, f.a0.y);
+      mma_bf16(cb, f.xa.x, f.xa.y, f.xa.z, f.xa.w, f.a0.z, f.a0.w);
+      mma_bf16(ca, f.xb.x, f.xb.y, f.xb.z, f.xb.w, f.b0.x, f.b0.y);
+      mma_bf16(cb, f.xb.x, f.xb.y, f.xb.z, f.xb.w, f.b0.z, f.b0.w);
+    }
+  };
+  if (nblk == 4) {
+    Frag f0, f1;
+    ldblk(f0, 0u);
+    ldblk(f1, 128u);
+    mmablk(f0, c[0], c[1]);
+    ldblk(f0, 256u);
+    mmablk(f1, c[2], c[3]);
+    ldblk(f1, 384u);
+    mmablk(f0, c[0], c[1]);
+    mmablk(f1, c[2], c[3]);
+  } else {
 #pragma unroll 1
-  for (int i = 0; i + 1 < nblk; i += 2) {
-    block((uint32_t)i * 128u, c[0], c[1]);
-    block((uint32_t)i * 128u + 128u, c[2], c[3]);
+    for (int i = 0; i < nblk; ++i) {
+      Frag f0;
+      ldblk(f0, (uint32_t)i * 128u);
+      mmablk(f0, c[0], c[1]);
+    }
   }
-  if (nblk & 1) block((uint32_t)(nblk - 1) * 128u, c[0], c[1]);
-  const float s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]), s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
-  const float s2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]), s3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
-  v_lo = h0 ? s1 : s0;
-  v_hi = h0 ? s3 : s2;
+  if constexpr (HI) {
+    const float s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]), s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
+    const float s2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]), s3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
+    v_lo = h0 ? s1 : s0;
+    v_hi = h0 ? s3 : s2;
+  } else {  // ca = c[0], c[2] (valid in D row g), cb = c[1], c[3] (valid in D row g+8)
+    v_lo = h0 ? ((c[0][1] + c[2][1]) + (c[1][3] + c[3][3])) : ((c[0][0] + c[2][0]) + (c[1][2] + c[3][2]));
+    v_hi = 0.f;
+  }
 }
 
 // This CTA's share of a GEMV phase (producer and consumers must agree).
@@ -548,7 +598,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   if (norm) gcur.advance(1, kGammaSlots);
   float eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
   float inv_k = pl.inv_k;
-  uint32_t xdst = c.xs + (uint32_t)tid * 8u;
+  uint32_t xdst = xpair_addr(c.xs, tid);
   // finishing thread: (word wl, row m) of the first batch; residual / bias words are fetched now
   const int npart = nkq * 2;
   const int tiles0 = min(tpb, sb.n_tiles);
@@ -578,14 +628,18 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   while (kq >= nkq) { kq -= nkq; ++tl; }
   int nblk;
   uint32_t fullb, wrow, xcol, pdst;
+  int tile0 = 0;
+  bool hi_rows = true;
   auto stage_params = [&]() {
+    hi_rows = sb.n_rows - (tile0 + tl) * kStageRows > 8;
     const int kw = min(kStageCols, K - kq * kStageCols);
     const int kcols = min(kUnitCols, kw - u * kUnitCols);  // may be <= 0
     nblk = kcols > 0 ? (kcols + 63) >> 6 : 0;
     fullb = c.full + (uint32_t)my.slot * 8u;
     wrow = c.ring + (uint32_t)my.slot * kStageBytes + lane_w;
     xcol = c.xs + (uint32_t)(kq * kStageCols + u * kUnitCols) * 2u;
-    pdst = c.scratch + (uint32_t)(((tl * M + t) * 16 + g) * npart + kq * 2 + u) * 4u;
+    // (activation row, weight row) this lane ends up holding: see gemv_unit
+    pdst = c.scratch + (uint32_t)(((tl * M + (hi_rows ? t : (g >> 1))) * 16 + (hi_rows ? g : 2 * t + h0)) * npart + kq * 2 + u) * 4u;
   };
   stage_params();
   pin(gsrc); pin(gfullb); pin(gemptyb); pin(eps); pin(inv_k); pin(xdst); pin(fin0); pin(fout); pin(fq);
@@ -605,8 +659,8 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
     if (PROF) prof_mark(p, pidx, 7);
     if (PROF) prof_warp_time(p, pidx, 0);
     if (!norm) {
-      if (have0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xdst), "r"(w0.x), "r"(w0.z) : "memory");
-      if (have1) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xdst + kConsumerThreads * 8), "r"(w1.x), "r"(w1.z) : "memory");
+      if (have0) xpair_store(xdst, w0.x, w0.z);
+      if (have1) xpair_store(xdst + kConsumerThreads * 8, w1.x, w1.z);
       cbar_sync();
     } else {
       float ss;
@@ -639,12 +693,12 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       const bool wr = (flags & F_WRITE_NORMED) && blockIdx.x == 0;
       if (have0) {
         const uint32_t y0 = norm_pair(w0.x, rs, g0.x), y1 = norm_pair(w0.z, rs, g0.y);
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xdst), "r"(y0), "r"(y1) : "memory");
+        xpair_store(xdst, y0, y1);
         if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid] = make_uint2(y0, y1);
       }
       if (have1) {
         const uint32_t y0 = norm_pair(w1.x, rs, g1.x), y1 = norm_pair(w1.z, rs, g1.y);
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(xdst + kConsumerThreads * 8), "r"(y0), "r"(y1) : "memory");
+        xpair_store(xdst + kConsumerThreads * 8, y0, y1);
         if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid + kConsumerThreads] = make_uint2(y0, y1);
       }
       __syncwarp();
@@ -665,7 +719,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
 
   // ---- multiply: batches of <= kBatchStages stages, six stages (one per warp pair) at a time; the parameters of the
   //      next stage are always computed one iteration ahead (the first ones before the poll)
-  int tile0 = 0, tiles = tiles0, fin = fin0;
+  int tiles = tiles0, fin = fin0;
   while (true) {
 #pragma unroll 1
     for (int sl = grp; sl < s_count; sl += kGroups) {
@@ -677,10 +731,14 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
           while (!mbar_try_wait_a(fullb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
         }
         if (PROF && sl == 0) prof_mark(p, pidx, 8);
+        if (PROF && sl == grp && mg == 0) prof_warp_time(p, pidx, 2);
         float v_lo = 0.f, v_hi = 0.f;
-        if (nblk > 0) gemv_unit(wrow, xrow, oA, oB, nblk, h0, v_lo, v_hi);
+        if (nblk > 0) {
+          if (hi_rows) gemv_unit<true>(wrow, xrow, oA, oB, nblk, h0, v_lo, v_hi);
+          else gemv_unit<false>(wrow, xrow, oA, oB, nblk, h0, v_lo, v_hi);
+        }
         if (PROF && sl == 0) prof_mark(p, pidx, 9);
-        if (mg + t < M) {
+        if (mg + (hi_rows ? t : (g >> 1)) < M) {
           const uint32_t d = pdst + (uint32_t)(mg * 16 * npart) * 4u;
           sts_f32(d, v_lo);
           sts_f32(d + (uint32_t)(8 * npart) * 4u, v_hi);
@@ -696,6 +754,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       }
     }
     if (PROF) prof_mark(p, pidx, 6);
+    if (PROF && tile0 == 0) prof_warp_time(p, pidx, 3);
     cbar_sync();
     if (PROF) prof_mark(p, pidx, 2);
     // ---- finish: one thread per (output word, activation row); words whose rows lie in tiles [tile0, tile0 + tiles)
@@ -790,6 +849,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   }
   cur = base;
   if (PROF) prof_mark(p, pidx, 3);
+  if (PROF) prof_warp_time(p, pidx, 4);
 }
 
 // Producer side of one GEMV phase: stream this CTA's rows through the ring, one 16 KB stage (16 rows x <= 512 columns)

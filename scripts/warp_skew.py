@@ -29,3 +29,6 @@ for ph in list(range(0, 15)) + list(range(135, 141)):
     t0 = min(v for v in a if v)
     print(f"ph {ph:3d} {kind:5s} poll-done per warp: " + " ".join(f"{(v - t0) if v else -1:5d}" for v in a))
     if any(b): print(f"             at-barrier per warp: " + " ".join(f"{(v - t0) if v else -1:5d}" for v in b))
+    for k, nm in ((2, "mma-start"), (3, "mma-end"), (4, "phase-end")):
+        c = [buf[(ph * 160 + 16 * (k >> 1) + wp) * 2 + (k & 1)] for wp in range(12)]
+        if any(c): print(f"             {nm:>10s} per warp: " + " ".join(f"{(v - t0) if v else -1:5d}" for v in c))
