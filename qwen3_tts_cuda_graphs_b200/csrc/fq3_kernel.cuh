@@ -1008,6 +1008,7 @@ __device__ __forceinline__ void ll_head_wait(const LLWord* src, uint32_t ep, LLW
 
 constexpr int kGq = 2;  // q heads per kv head handled by one item (talker and predictor: 16 / 8)
 constexpr int kAttnPre = 2;  // cached positions per half-warp whose K/V rows are requested before the q/k/v poll
+constexpr int kAttnShort = 2 * kAttnPre * kConsumerWarps;  // 48 positions: at most kAttnPre per half-warp
 
 // Scratch layout: qs fp32 [kGq][128] (1 KB) | fresh K,V rows bf16 [kMaxRows][2][128] (4 KB) | warp partials fp32 [16][kGq][kPartStride]
 // Positions are dealt to half-warps (position a + 2*warp + half, stride 2 * kConsumerWarps); a lane owns 8 of the 128 dims (one 16-byte
@@ -1101,7 +1102,6 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
   cbar_sync();
   if (PROF) prof_mark(p, pidx, 1);
 
-  // -- step 2: online softmax per half-warp
   float qr[kGq][8];
 #pragma unroll
   for (int j = 0; j < kGq; ++j) {
@@ -1110,6 +1110,89 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
     qr[j][0] = q0.x; qr[j][1] = q0.y; qr[j][2] = q0.z; qr[j][3] = q0.w;
     qr[j][4] = q1.x; qr[j][5] = q1.y; qr[j][6] = q1.z; qr[j][7] = q1.w;
   }
+  // -- step 2 (short range, <= two positions per half-warp: every decode item, since a split never exceeds kSplitLen): two
+  //    passes instead of an online softmax.  Every half-warp scores its positions and parks the V rows in shared memory;
+  //    after ONE barrier the 128 output threads run max / exp / weighted sum over the <= 48 scores in position order.
+  if (b - a <= kAttnShort) {
+    float* sc = wp;                                                  // [kGq][kAttnShort]
+    uint4* vst = reinterpret_cast<uint4*>(wp + kGq * kAttnShort);    // [kAttnShort][16 pieces]
+    float sv[2][kGq];
+    uint4 vv[2];
+    int idx[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = a + warp * 2 + hw + u * 2 * kConsumerWarps;
+      idx[u] = (i < b) ? i - a : -1;
+      uint4 kk = make_uint4(0u, 0u, 0u, 0u);
+      vv[u] = kk;
+      if (i < b) {
+        if (i >= gr.pos0) {
+          const uint4* f = fresh + (size_t)(i - gr.pos0) * 32;
+          kk = f[dl];
+          vv[u] = f[16 + dl];
+        } else {
+          kk = kpre[u];
+          vv[u] = vpre[u];
+        }
+      }
+      const float k[8] = {bf_lo(kk.x), bf_hi(kk.x), bf_lo(kk.y), bf_hi(kk.y), bf_lo(kk.z), bf_hi(kk.z), bf_lo(kk.w), bf_hi(kk.w)};
+#pragma unroll
+      for (int j = 0; j < kGq; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) t = fmaf(qr[j][d], k[d], t);
+        sv[u][j] = t;
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int j = 0; j < kGq; ++j) sv[u][j] += __shfl_xor_sync(0xffffffffu, sv[u][j], o);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (idx[u] >= 0) {
+        vst[idx[u] * 16 + dl] = vv[u];
+        if (dl < kGq) sc[dl * kAttnShort + idx[u]] = (dl == 0) ? sv[u][0] : sv[u][1];
+      }
+    }
+    if (PROF) prof_mark(p, pidx, 2);
+    cbar_sync();
+    if (threadIdx.x < gq * HW) {  // a thread owns one packed output word
+      const int j = threadIdx.x / HW, wd = threadIdx.x - j * HW;
+      const int qh = kvh * gq + j;
+      const int row = gr.first_row + r;
+      const int n = b - a;
+      const float* sj = sc + j * kAttnShort;
+      float Mx = -INFINITY;
+      for (int i = 0; i < n; ++i) Mx = fmaxf(Mx, sj[i]);
+      const uint32_t* vw = reinterpret_cast<const uint32_t*>(vst) + wd;
+      float Lsum = 0.f, O0 = 0.f, O1 = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) {
+        const float pe = expf(sj[i] - Mx);
+        const uint32_t v2 = vw[i * HW];
+        Lsum += pe;
+        O0 = fmaf(pe, bf_lo(v2), O0);
+        O1 = fmaf(pe, bf_hi(v2), O1);
+      }
+      if (n <= 0) Mx = -INFINITY;
+      if (nsplit == 1) {
+        const float y0 = bf16r(Lsum > 0.f ? O0 / Lsum : 0.f), y1 = bf16r(Lsum > 0.f ? O1 / Lsum : 0.f);
+        ll_st(reinterpret_cast<LLWord*>(p.bufs[ab]) + (size_t)row * p.ld[ab] + qh * HW + wd, pack_bf16x2(y0, y1), ep);
+      } else {
+        LLWord* dst = p.attn_part + (((size_t)row * S.nq + qh) * kMaxSplits + sp) * kPartStride;
+        if (wd == 0) ll_st2(dst, __float_as_uint(Mx), __float_as_uint(Lsum), ep);
+        ll_st2(dst + 4 + 2 * wd, __float_as_uint(O0), __float_as_uint(O1), ep);
+      }
+    }
+    if (PROF) prof_mark(p, pidx, 3);
+    return;
+  }
+  // -- step 2 (long range): online softmax per half-warp
   float m_run[kGq], l_run[kGq], acc[kGq][8];
 #pragma unroll
   for (int j = 0; j < kGq; ++j) {
