@@ -44,6 +44,7 @@ constexpr int kCtlOffset = 256;
 constexpr int kRedOffset = 320;
 constexpr int kGFullOffset = 832;
 constexpr int kGEmptyOffset = 864;
+constexpr int kStreamConstOffset = 896;  // int [4] n_pad | [4] rope_delta of the streams of this launch
 constexpr int kHeaderBytes = 1024;
 constexpr int kGammaSlots = 4;             // norm-weight vectors in flight (streamed by the producer like the weights)
 constexpr int kMaxPlans = 24;

@@ -944,10 +944,11 @@ __device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& 
   r.first_row = g * r.nrows;
   r.slot = p.stream0 + g;
   if (ph.stack == ST_TALKER) {
-    const StreamState* st = p.st + r.slot;
     r.pos0 = (p.pos_override >= 0) ? p.pos_override : frame_pos[g];
-    r.n_pad = __ldcg(&st->n_pad);
-    r.rope_delta = __ldcg(&st->rope_delta);
+    // launch constants of the stream, parked in shared memory by the frame loop (two L2 round trips per attention phase otherwise)
+    const int* sconst = frame_pos + (kStreamConstOffset - kCtlOffset) / 4 - 8;
+    r.n_pad = sconst[g];
+    r.rope_delta = sconst[4 + g];
   } else {
     r.pos0 = (ph.flags & F_ROWS2) ? 0 : (int)ph.aux + 1;
     r.n_pad = 0;
@@ -1054,6 +1055,7 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
     }
   }
   cbar_sync();  // the scratch may still be read by the previous phase's finishing threads
+  if (threadIdx.x < kGq * kAttnShort) wp[threadIdx.x] = -INFINITY;  // score slots of the short-range path
 
   // -- step 1: one warp per item: q heads (norm + rope, pre-scaled) to smem; K/V rows pos0..pos of this chunk that fall
   //    into [a, b) to the cache and to smem (norm + rope on K).
@@ -1167,19 +1169,30 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
       const int row = gr.first_row + r;
       const int n = b - a;
       const float* sj = sc + j * kAttnShort;
+      // the scores beyond n are -inf (cleared at the top of the phase): four at a time
+      const float4* s4 = reinterpret_cast<const float4*>(sj);
+      const int n4 = (n + 3) >> 2;
       float Mx = -INFINITY;
-      for (int i = 0; i < n; ++i) Mx = fmaxf(Mx, sj[i]);
+      for (int g4 = 0; g4 < n4; ++g4) {
+        const float4 v = s4[g4];
+        Mx = fmaxf(Mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      }
       const uint32_t* vw = reinterpret_cast<const uint32_t*>(vst) + wd;
       float Lsum = 0.f, O0 = 0.f, O1 = 0.f;
-#pragma unroll 4
-      for (int i = 0; i < n; ++i) {
-        const float pe = expf(sj[i] - Mx);
-        const uint32_t v2 = vw[i * HW];
-        Lsum += pe;
-        O0 = fmaf(pe, bf_lo(v2), O0);
-        O1 = fmaf(pe, bf_hi(v2), O1);
+#pragma unroll 2
+      for (int g4 = 0; g4 < n4; ++g4) {
+        const float4 v = s4[g4];
+        const float sx[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * g4 + e;
+          const float pe = expf(sx[e] - Mx);  // 0 beyond n
+          const uint32_t v2 = (i < n) ? vw[i * HW] : 0u;
+          Lsum += pe;
+          O0 = fmaf(pe, bf_lo(v2), O0);
+          O1 = fmaf(pe, bf_hi(v2), O1);
+        }
       }
-      if (n <= 0) Mx = -INFINITY;
       if (nsplit == 1) {
         const float y0 = bf16r(Lsum > 0.f ? O0 / Lsum : 0.f), y1 = bf16r(Lsum > 0.f ? O1 / Lsum : 0.f);
         ll_st(reinterpret_cast<LLWord*>(p.bufs[ab]) + (size_t)row * p.ld[ab] + qh * HW + wd, pack_bf16x2(y0, y1), ep);
@@ -2178,6 +2191,9 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
         if (iter == 0) {
           done = __ldcg(&st->done);
           pos = __ldcg(&st->position);
+          int* sconst = reinterpret_cast<int*>(smem_raw + kStreamConstOffset);
+          sconst[tid] = __ldcg(&st->n_pad);
+          sconst[4 + tid] = __ldcg(&st->rope_delta);
         } else {
           done = (int)ll_wait(&st->ctl[0], ep0, p, -2);
           pos = (int)ll_wait(&st->ctl[1], ep0, p, -2);
