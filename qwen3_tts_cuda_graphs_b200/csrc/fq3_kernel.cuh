@@ -537,16 +537,11 @@ __device__ __forceinline__ void pin(float& v) { asm volatile("" : "+f"(v)); }
 template <class T>
 __device__ __forceinline__ void pin(T*& v) { asm volatile("" : "+l"(v)); }
 
-__device__ __forceinline__ uint4 ll_ld_pair(const LLWord* p, int mode = 0) {
+// Two neighbouring LL words in one 16-byte request.  ld.relaxed.gpu was the fastest of the flavours tried (volatile, .cv, .cg,
+// relaxed.sys, acquire.gpu: profiles/r01b_ll_store_flavours.log); the run-time switch between them cost a branch chain per poll.
+__device__ __forceinline__ uint4 ll_ld_pair(const LLWord* p) {
   uint4 v;
-  switch (mode & 7) {
-    default: asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
-    case 1: asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
-    case 2: asm volatile("ld.global.cv.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
-    case 3: asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
-    case 4: asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
-    case 5: asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); break;
-  }
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 // bf16(bf16(x * rs) * g) for two packed elements: fp32 product + one packed round, then a packed bf16 multiply (the bf16 x bf16
@@ -581,8 +576,8 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const LLWord* src = in + 2 * tid;
   uint4 w0 = make_uint4(0u, ep_in, 0u, ep_in), w1 = w0;
   if (fast) {
-    if (have0) w0 = ll_ld_pair(src, p.ll_mode);
-    if (have1) w1 = ll_ld_pair(src + 2 * kConsumerThreads, p.ll_mode);
+    if (have0) w0 = ll_ld_pair(src);
+    if (have1) w1 = ll_ld_pair(src + 2 * kConsumerThreads);
   }
 
   // ---- everything that does not depend on the input: overlaps the round trip of the poll
@@ -652,8 +647,8 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       while ((w0.y != ep_in) | (w0.w != ep_in) | (w1.y != ep_in) | (w1.w != ep_in)) {
         if (++tries > (unsigned)(p.debug >> 16)) __nanosleep((unsigned)(p.debug & 0xffff));
         if (tries > (unsigned)(p.watchdog_ns >> 8)) device_fault(p, DE_LL_WAIT, pidx, (int)ep_in);
-        if (have0 && ((w0.y != ep_in) | (w0.w != ep_in))) w0 = ll_ld_pair(src, p.ll_mode);
-        if (have1 && ((w1.y != ep_in) | (w1.w != ep_in))) w1 = ll_ld_pair(src + 2 * kConsumerThreads, p.ll_mode);
+        if (have0 && ((w0.y != ep_in) | (w0.w != ep_in))) w0 = ll_ld_pair(src);
+        if (have1 && ((w1.y != ep_in) | (w1.w != ep_in))) w1 = ll_ld_pair(src + 2 * kConsumerThreads);
       }
     }
     if (PROF) prof_mark(p, pidx, 7);
