@@ -416,3 +416,39 @@ def test_dense_prefill_matches_chunked_prefill(pair, T):
     assert margin_argmax_agree(out[True][0], out[False][0], TOL * scale)
     assert rel_err(out[True][2], ref_h) <= TOL, rel_err(out[True][2], ref_h)
     assert rel_err(out[True][2], out[False][2]) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# long contexts: split-KV attention (48 positions per CTA) with the combine step, up to ten splits
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def long_pair():
+    name, tl, pl = CONFIGS[0]
+    cfg = make_cfg(name, tl, pl)
+    w = make_weights(cfg, seed=13)
+    eng = make_engine(cfg, w, max_seq_len=512)
+    orc = make_oracle(cfg, w)
+    yield cfg, w, eng, orc
+    eng.close()
+
+
+@pytest.mark.parametrize("T", [49, 97, 150, 192, 193, 300, 470])
+def test_talker_step_long_context_matches_oracle(long_pair, T):
+    """A decode step at position T attends to T+1 positions: one CTA per (kv head, split of <= 48 positions) and the combine
+    step of split 0, for 2 to 10 splits (three combine rounds).  Hidden state and the prefill logits against the oracle."""
+    cfg, w, eng, orc = long_pair
+    tie, tam, tth, tpe = synth_prompt(cfg, T=T, seed=100 + T)
+    pol = _sp(do_sample=False, repetition_penalty=1.0, min_new_tokens=2)
+    ref_logits, _, _ = orc.talker_prefill(tie, tam)
+    eng.set_text_conditioning(0, tth[0].cuda(), tpe.cuda())
+    lg = eng.prefill(0, tie[0].cuda(), 0, pol, want_logits=True, dense=False)
+    assert eng.status(0).error == 0
+    assert rel_err(lg, ref_logits[0]) <= TOL, rel_err(lg, ref_logits[0])
+    g = torch.Generator().manual_seed(T)
+    for step in range(2):
+        xg = (0.05 * torch.randn(1, 1, cfg.talker.hidden_size, generator=g)).to(torch.bfloat16)
+        ref_h = orc.talker_step(xg, T + step)
+        h, _ = eng.talker_step(0, xg.cuda(), T + step)
+        torch.cuda.synchronize()
+        assert eng.status(0).error == 0
+        assert rel_err(h, ref_h) <= TOL, (step, rel_err(h, ref_h))
