@@ -42,6 +42,10 @@ for k, v in agg.items():
     print(f"{k:7s} n={len(v):3d} median {v2[len(v2)//2]:6d} cycles  min {v2[0]:6d} max {v2[-1]:6d}  sum {sum(v):8d}")
     tot += sum(v)
 print("sum of phases", tot, "cycles =", tot / 1.965e3, "us")
+pp = [starts[(k + 1) * per_pass] - starts[k * per_pass] for k in range(14) if (k + 1) * per_pass in starts and k * per_pass in starts]
+print("cycles per pass (start of qkv to start of the next pass's qkv):", pp)
+for k in (0, 1):
+    print(f"pass {k} phases:", [(starts[k * per_pass + j + 1] - starts[k * per_pass + j]) for j in range(per_pass) if k * per_pass + j + 1 in starts and k * per_pass + j in starts])
 
 print("sample phases: start->logits polled | prep+max | top-k | softmax+draw | publish | end barrier   (cycles)")
 rows = []
