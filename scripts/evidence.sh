@@ -13,6 +13,6 @@ timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_${tag}.log 2
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${tag}.log 2>&1; tail -1 gpurun_out/bench_ref_${tag}.log | cut -c1-400
 if [ "$2" != "nonu" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_${tag}.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fq3_stream -s 6 -c 1 -o gpurun_out/prof_frames_${tag} python scripts/prof_frames.py > gpurun_out/ncu_full_${tag}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fq3_stream -s 3 -c 1 -o gpurun_out/prof_frames_${tag} python scripts/prof_frames.py > gpurun_out/ncu_full_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_full_${tag}.log
 fi
