@@ -570,6 +570,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const bool fast = (M == 1) && (Kp <= 2 * kConsumerThreads);  // K <= 3072
   if (PROF) prof_mark(p, pidx, 0);
   if (PROF) prof_cta_time(p, pidx, 0);
+  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0 && M * K * 2 <= p.xbuf_bytes, pidx, 300000 + M);
 
   // ---- issue the first poll of this thread's input words
   const bool have0 = tid < Kp, have1 = tid + kConsumerThreads < Kp;
@@ -597,6 +598,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   // finishing thread: (word wl, row m) of the first batch; residual / bias words are fetched now
   const int npart = nkq * 2;
   const int tiles0 = min(tpb, sb.n_tiles);
+  FQ3_ASSERT(tiles0 * M * 16 * npart * 4 <= kScratchBytes, pidx, 310000 + tiles0 * npart);
   int fin0 = min(sb.n_su, (tiles0 * kStageRows) >> ro_shift) * M;
   const int f_wl = (M == 1) ? tid : tid / M, f_m = (M == 1) ? 0 : tid - f_wl * M;
   uint32_t res0 = 0u, bias0 = 0u;
@@ -1025,8 +1027,10 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
   bf16* Kc = S.kcache + head_base;
   bf16* Vc = S.vcache + head_base;
   const int pos = gr.pos0 + r;         // position of this query row; it attends to [n_pad, pos]
-  FQ3_ASSERT(pos >= 0 && pos < S.max_pos && gr.n_pad >= 0 && gr.n_pad <= pos && gq <= kGq, pidx, 200000 + pos);
+  // rows in front of n_pad are the left padding of a batched prompt: they attend to nothing (L <= 0) and publish zeros
+  FQ3_ASSERT(pos >= 0 && pos < S.max_pos && gr.n_pad >= 0 && gq <= kGq, pidx, 200000 + pos);
   const int L = pos + 1 - gr.n_pad;
+  FQ3_ASSERT(r >= 0 && r < kMaxRows && sp >= 0 && sp < nsplit && nsplit <= kMaxSplits, pidx, 210000 + sp);
   const int per = (L + nsplit - 1) / nsplit;
   const int a = gr.n_pad + sp * per;
   const int b = min(a + per, pos + 1);
