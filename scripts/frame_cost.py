@@ -15,7 +15,7 @@ pols = {
     "sample": (SamplingPolicy(do_sample=True, temperature=0.9, top_k=50, repetition_penalty=1.05, min_new_tokens=10000),
                SubPolicy(do_sample=True, top_k=50, temperature=0.9)),
 }
-for T in (14, 39, 240):
+for T in [int(x) for x in os.environ.get("FC_T", "14,39,240").split(",")]:
     tie, tam, tth, tpe = synth_prompt(cfg, T=T)
     eng.set_text_conditioning(0, tth[0].cuda(), tpe.cuda())
     tiec = tie[0].cuda()
