@@ -104,6 +104,9 @@ class Engine:
         self._dense_tried = False
 
     def close(self):
+        if getattr(self, "_dense", None) is not None:
+            self._dense.close()
+            self._dense = None
         if getattr(self, "h", None):
             self.lib.fq3_destroy(self.h)
             self.h = None

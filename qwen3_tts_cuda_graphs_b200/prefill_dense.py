@@ -29,6 +29,7 @@ class DensePrefill:
     """Op list for rows [0, R) of a prompt, built once for a row capacity and re-used with M patched per call."""
 
     MIN_ROWS = 16  # below this the chunked path (<= 2 launches of the decode kernel) is at least as fast
+    MAX_GRAPHS = 8  # captured (rows, stream) plans kept
 
     def __init__(self, engine):
         self.eng = engine
@@ -38,6 +39,10 @@ class DensePrefill:
         self.ops = None
         self.arr = None
         self.keep = []
+        self.graphs = {}
+        self.seen = {}
+        self.graph_failed = set()
+        self.use_graphs = os.environ.get("FQ3C_GRAPH", "1") != "0"
         a, t = engine.arena, self.cfg
         dev = engine.device
         L = t.num_hidden_layers
@@ -110,11 +115,19 @@ class DensePrefill:
             gemm(h, self.off(f"{p}.wgu"), 2 * I, H, mid, flags=F_SWIGLU)
             gemm(mid, self.off(f"{p}.wdown"), H, I, x[cur ^ 1], flags=F_RESID, res=x[cur])
             cur ^= 1
+        for h in self.graphs.values():
+            self.lib.fq3c_graph_destroy(h)
+        self.graphs, self.seen = {}, {}
         self.ops = ops
         self.kv_ops = [(i, o) for i, o in enumerate(ops) if o.kind == K_QKNORM_ROPE_KV]
         self.arr = (Op * len(ops))(*ops)
         self.cap = cap
         self.cur_stream = 0
+
+    def close(self):
+        for h in self.graphs.values():
+            self.lib.fq3c_graph_destroy(h)
+        self.graphs = {}
 
     def run(self, stream_idx: int, embeds: torch.Tensor, R: int):
         """rows [0, R) of `embeds` (bf16 [T, H], device): fills the K/V cache of every layer for positions [0, R)."""
@@ -130,7 +143,21 @@ class DensePrefill:
             for i in range(len(self.ops)):
                 arr[i].M = R
         self.x0[:R].copy_(embeds[:R])
-        rc = self.lib.fq3c_run(arr, len(self.ops), torch.cuda.current_stream().cuda_stream)
+        stream = torch.cuda.current_stream().cuda_stream
+        # ~250 small launches: the second prompt of the same length on the same stream replays them as one CUDA graph
+        key = (R, stream_idx)
+        g = self.graphs.get(key)
+        if g is None and self.use_graphs and self.seen.get(key, 0) >= 1 and key not in self.graph_failed:
+            h = C.c_void_p()
+            if self.lib.fq3c_graph_create(arr, len(self.ops), C.byref(h)) == 0:
+                if len(self.graphs) >= self.MAX_GRAPHS:
+                    _, old = self.graphs.popitem()
+                    self.lib.fq3c_graph_destroy(old)
+                self.graphs[key] = g = h
+            else:
+                self.graph_failed.add(key)
+        self.seen[key] = self.seen.get(key, 0) + 1
+        rc = self.lib.fq3c_graph_launch(g, stream) if g is not None else self.lib.fq3c_run(arr, len(self.ops), stream)
         if rc != 0:
             raise _codec.CodecError(self.lib.fq3c_last_error().decode())
 
