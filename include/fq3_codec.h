@@ -57,6 +57,8 @@ typedef struct fq3c_op {
   const void* p1;        /* f32 */
   void* C;
   void* C2;
+  void* ws;              /* GEMM, optional: fp32 workspace for split-K partial tiles (>= splits * M * round8(N) * 4 bytes are used); */
+  int64_t ws_bytes;      /* NULL / 0 = never split.  Ops of one stream-ordered list may share it.                                  */
 } fq3c_op;
 
 int fq3c_abi_version(void);

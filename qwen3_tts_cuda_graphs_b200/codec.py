@@ -40,7 +40,27 @@ class Op(C.Structure):
         ("i0", C.c_int32), ("i1", C.c_int32), ("i2", C.c_int32), ("f0", C.c_float), ("f1", C.c_float),
         ("A", C.c_void_p), ("B", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("scale", C.c_void_p),
         ("p0", C.c_void_p), ("p1", C.c_void_p), ("C", C.c_void_p), ("C2", C.c_void_p),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_int64),
     ]
+
+
+SPLITK_MAX_ROWS = 512          # GEMMs up to this many rows may be split over K (include/fq3_codec.h: fq3c_op.ws)
+SPLITK_WS_CAP = 64 << 20       # bytes of fp32 workspace one plan may pin
+
+
+def attach_splitk_workspace(ops, device, keep) -> None:
+    """One fp32 workspace per stream-ordered op list: every short GEMM of the list may use it for split-K partial tiles."""
+    need = 0
+    for o in ops:
+        if o.kind == K_GEMM and 0 < o.M <= SPLITK_MAX_ROWS and o.K >= 512:
+            need = max(need, 8 * o.M * ((o.N + 7) // 8 * 8) * 4)
+    if need == 0:
+        return
+    ws = torch.empty(min(need, SPLITK_WS_CAP) // 4, dtype=torch.float32, device=device)
+    keep.append(ws)
+    for o in ops:
+        if o.kind == K_GEMM and 0 < o.M <= SPLITK_MAX_ROWS and o.K >= 512:
+            o.ws, o.ws_bytes = ws.data_ptr(), ws.numel() * 4
 
 
 _lib = None
@@ -72,7 +92,7 @@ def load_lib():
     lib.fq3c_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
     lib.fq3c_graph_destroy.restype = C.c_int
     lib.fq3c_graph_destroy.argtypes = [C.c_void_p]
-    if lib.fq3c_abi_version() != 1:
+    if lib.fq3c_abi_version() != 2:
         raise CodecError("libfq3codec.so ABI version mismatch")
     _lib = lib
     return lib
@@ -385,6 +405,8 @@ class CodecDecoder:
         self._gemm(plan, xs, g["final.w"], rows, 1, out_dim, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["final.b"],
                    flags=F_CLAMP, out=plan.wav, out_f32=True)
         plan.n_samples = rows
+        if os.environ.get("FQ3C_SPLITK", "1") != "0":
+            attach_splitk_workspace(plan.ops, self.device, plan.keep)
         plan.arr = (Op * len(plan.ops))(*plan.ops)
         return plan
 

@@ -295,7 +295,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Warp-specialised: the loader warps run up to TSTAGES k-blocks ahead of the tensor core (full / empty mbarriers per stage,
 // cp.async completion counted straight into the full barrier), one thread issues the MMAs, all eight loader warps drain
 // the accumulator.  No block-wide barrier inside the k loop.
-__global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_op o, const int BN) {
+// Split-K (splits > 1, short-and-wide problems that would leave most SMs idle): blockIdx.z takes a contiguous range of
+// k-blocks and stores its raw fp32 tile into the workspace [split][M][Nw]; fq3c_splitk_reduce_kernel adds the splits in
+// order and applies the fused epilogue.
+__global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_op o, const int BN, const int splits, const int Nw) {
   extern __shared__ unsigned char tsmem_raw[];
   const uint32_t raw = smem_u32(tsmem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
@@ -308,7 +311,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_o
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
   const bf16* A = reinterpret_cast<const bf16*>(o.A);
   const bf16* B = reinterpret_cast<const bf16*>(o.B);
-  const int KT = (o.K + TK - 1) / TK;
+  const int KT_all = (o.K + TK - 1) / TK;
+  const int kt_begin = (int)(((long)blockIdx.z * KT_all) / splits), kt_end = (int)(((long)(blockIdx.z + 1) * KT_all) / splits);
+  const int KT = kt_end - kt_begin;  // k-blocks of this CTA; `it` below counts them from 0
 
   if (tid == 0) {
     for (int s = 0; s < TSTAGES; ++s) {
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_o
         if (lane == 0) mbar_wait(empty + 8u * st, (uint32_t)(((kt / TSTAGES) - 1) & 1));
         __syncwarp();
       }
-      const int k0 = kt * TK + c * 8;
+      const int k0 = (kt_begin + kt) * TK + c * 8;
       const bool kok = k0 < o.K;
       if (is_a) {
         const int tap = k0 / o.cin, ci = k0 - tap * o.cin;
@@ -424,7 +429,16 @@ __global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_o
           float a8[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) a8[q] = __uint_as_float(v[8 * j + q]);
-          epilogue_row8(o, row, n0 + cc * 32 + 8 * j, a8);
+          const int col = n0 + cc * 32 + 8 * j;
+          if (splits > 1) {
+            if (row < o.M && col < o.N) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(o.ws) + ((size_t)blockIdx.z * o.M + row) * Nw + col);
+              dst[0] = make_float4(a8[0], a8[1], a8[2], a8[3]);
+              dst[1] = make_float4(a8[4], a8[5], a8[6], a8[7]);
+            }
+          } else {
+            epilogue_row8(o, row, col, a8);
+          }
         }
       }
     }
@@ -435,6 +449,24 @@ __global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_o
 }
 
 // RVQ dequantiser front half: gather + sum codebook rows. C[m, 0:dim] = sum of the first i0 groups, C[m, dim:2dim] = rest.
+// second half of a split-K GEMM: a thread owns eight consecutive columns of a row, adds the splits in order (deterministic)
+// and runs the same fused epilogue the single-pass kernel would have run
+__global__ void __launch_bounds__(256) fq3c_splitk_reduce_kernel(const fq3c_op o, const int splits, const int Nw) {
+  const int groups = Nw >> 3;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)o.M * groups) return;
+  const int row = (int)(idx / groups), col = (int)(idx - (long)row * groups) * 8;
+  float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* ws = reinterpret_cast<const float*>(o.ws);
+  for (int z = 0; z < splits; ++z) {
+    const float4* src = reinterpret_cast<const float4*>(ws + ((size_t)z * o.M + row) * Nw + col);
+    const float4 v0 = src[0], v1 = src[1];
+    a8[0] += v0.x; a8[1] += v0.y; a8[2] += v0.z; a8[3] += v0.w;
+    a8[4] += v1.x; a8[5] += v1.y; a8[6] += v1.z; a8[7] += v1.w;
+  }
+  epilogue_row8(o, row, col, a8);
+}
+
 __global__ void fq3c_rvq_kernel(const fq3c_op o) {
   const long long* codes = reinterpret_cast<const long long*>(o.A);
   const bf16* cb = reinterpret_cast<const bf16*>(o.B);
@@ -699,7 +731,7 @@ int fail(const std::string& m) { g_err = m; return -1; }
 
 extern "C" {
 
-int fq3c_abi_version(void) { return 1; }
+int fq3c_abi_version(void) { return 2; }
 const char* fq3c_last_error(void) { return g_err.c_str(); }
 int64_t fq3c_launch_count(void) { return g_launches; }
 
@@ -734,10 +766,28 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
               if (best < 0 || cost < best) { best = cost; bn = cand; }
             }
           }
+          // Split-K when the tiles would cover less than half of the SMs and the reduction is long (the transformer's
+          // o / down projections at 8-240 rows: 16-32 tiles each walking 32-96 k-blocks alone): wider tiles, every tile
+          // split over up to eight CTAs, partial tiles through the caller's workspace.
+          const int KT = (o.K + TK - 1) / TK;
+          const int Nw = (o.N + 7) & ~7;
+          int splits = 1;
+          if (o.ws && o.M <= 4 * TM && KT >= 8) {
+            const int bn_s = o.N >= 64 ? 64 : 32;
+            const int tiles_s = ((o.N + bn_s - 1) / bn_s) * mt;
+            int sp = std::min(std::min(8, KT / 4), 148 / std::max(1, tiles_s));
+            while (sp > 1 && (int64_t)sp * o.M * Nw * 4 > o.ws_bytes) --sp;
+            if (sp > 1) { splits = sp; bn = bn_s; }
+          }
           const int nt = (o.N + bn - 1) / bn;
           bn = std::min(TMAXN, (((o.N + nt - 1) / nt) + 15) / 16 * 16);
-          dim3 grid((o.N + bn - 1) / bn, mt);
-          fq3c_gemm_tc5_kernel<<<grid, TTHREADS, T_SMEM, s>>>(o, bn);
+          dim3 grid((o.N + bn - 1) / bn, mt, splits);
+          fq3c_gemm_tc5_kernel<<<grid, TTHREADS, T_SMEM, s>>>(o, bn, splits, Nw);
+          if (splits > 1) {
+            const long n = (long)o.M * (Nw >> 3);
+            fq3c_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o, splits, Nw);
+            g_launches += 1;
+          }
           break;
         }
         dim3 grid((o.N + BN - 1) / BN, (o.M + BM - 1) / BM);

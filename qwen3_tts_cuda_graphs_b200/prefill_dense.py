@@ -118,6 +118,8 @@ class DensePrefill:
         for h in self.graphs.values():
             self.lib.fq3c_graph_destroy(h)
         self.graphs, self.seen = {}, {}
+        if os.environ.get("FQ3C_SPLITK", "1") != "0":
+            _codec.attach_splitk_workspace(ops, dev, self.keep)
         self.ops = ops
         self.kv_ops = [(i, o) for i, o in enumerate(ops) if o.kind == K_QKNORM_ROPE_KV]
         self.arr = (Op * len(ops))(*ops)
