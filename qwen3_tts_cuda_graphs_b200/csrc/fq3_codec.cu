@@ -269,7 +269,8 @@ constexpr int TTHREADS = TLOADERS + 32;
 constexpr int TMAXN = 128;
 constexpr int T_A_BYTES = TM * TK * 2;        // 16 KB
 constexpr int T_B_BYTES = TMAXN * TK * 2;     // 16 KB
-constexpr int T_SMEM = TSTAGES * (T_A_BYTES + T_B_BYTES) + 1024 /*alignment*/ + 256 /*barriers + tmem pointer*/;
+constexpr int t_smem(int stages) { return stages * (T_A_BYTES + T_B_BYTES) + 1024 /*alignment*/ + 256 /*barriers + tmem pointer*/; }
+constexpr int T_SMEM = t_smem(TSTAGES);
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -298,15 +299,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Split-K (splits > 1, short-and-wide problems that would leave most SMs idle): blockIdx.z takes a contiguous range of
 // k-blocks and stores its raw fp32 tile into the workspace [split][M][Nw]; fq3c_splitk_reduce_kernel adds the splits in
 // order and applies the fused epilogue.
-__global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_op o, const int BN, const int splits, const int Nw) {
+template <int MINB>  // CTAs per SM the register budget is planned for: 2 with three stages, 1 with six
+__global__ void __launch_bounds__(TTHREADS, MINB) fq3c_gemm_tc5_kernel(const fq3c_op o, const int BN, const int splits, const int Nw, const int NST) {
   extern __shared__ unsigned char tsmem_raw[];
   const uint32_t raw = smem_u32(tsmem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
   unsigned char* gbase = tsmem_raw + (base - raw);
-  const uint32_t a_smem = base, b_smem = base + TSTAGES * T_A_BYTES;
-  const uint32_t bars = base + TSTAGES * (T_A_BYTES + T_B_BYTES);  // full[TSTAGES] | empty[TSTAGES] | done | tmem base address
-  const uint32_t full = bars, empty = bars + 8u * TSTAGES, done = bars + 16u * TSTAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + TSTAGES * (T_A_BYTES + T_B_BYTES) + 16 * TSTAGES + 16);
+  const uint32_t a_smem = base, b_smem = base + NST * T_A_BYTES;
+  const uint32_t bars = base + NST * (T_A_BYTES + T_B_BYTES);  // full[NST] | empty[NST] | done | tmem base address
+  const uint32_t full = bars, empty = bars + 8u * NST, done = bars + 16u * NST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + NST * (T_A_BYTES + T_B_BYTES) + 16 * NST + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
   const bf16* A = reinterpret_cast<const bf16*>(o.A);
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_o
   const int KT = kt_end - kt_begin;  // k-blocks of this CTA; `it` below counts them from 0
 
   if (tid == 0) {
-    for (int s = 0; s < TSTAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(full + 8u * s, TLOADERS);
       mbar_init(empty + 8u * s, 1);
     }
@@ -338,8 +340,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_o
       // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       for (int kt = 0; kt < KT; ++kt) {
-        const int st = kt % TSTAGES;
-        mbar_wait(full + 8u * st, (uint32_t)((kt / TSTAGES) & 1));
+        const int st = kt % NST;
+        mbar_wait(full + 8u * st, (uint32_t)((kt / NST) & 1));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) writes -> tensor core (async proxy) reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = a_smem + (uint32_t)st * T_A_BYTES, b0 = b_smem + (uint32_t)st * T_B_BYTES;
@@ -365,9 +367,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) fq3c_gemm_tc5_kernel(const fq3c_o
     const int lt = tid & 127, c = lt & 7, r0 = lt >> 3;
     const bool is_a = warp < 4;
     for (int kt = 0; kt < KT; ++kt) {
-      const int st = kt % TSTAGES;
-      if (kt >= TSTAGES) {  // one lane per warp polls: 256 spinning threads would swamp the shared-memory pipe the copies need
-        if (lane == 0) mbar_wait(empty + 8u * st, (uint32_t)(((kt / TSTAGES) - 1) & 1));
+      const int st = kt % NST;
+      if (kt >= NST) {  // one lane per warp polls: 256 spinning threads would swamp the shared-memory pipe the copies need
+        if (lane == 0) mbar_wait(empty + 8u * st, (uint32_t)(((kt / NST) - 1) & 1));
         __syncwarp();
       }
       const int k0 = (kt_begin + kt) * TK + c * 8;
@@ -747,10 +749,13 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
         if (use_tc5 < 0) {
           const char* e = getenv("FQ3C_TCGEN05");
           use_tc5 = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-          if (use_tc5 && cudaFuncSetAttribute(fq3c_gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess)
+          if (use_tc5 && (cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess ||
+                          cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(3)) != cudaSuccess))
             return fail("cannot reserve shared memory for the tcgen05 GEMM");
         }
-        if (use_tc5 && o.N >= 16 && o.K >= 4 * TK) {
+        static int tc5_min_k = -1;
+        if (tc5_min_k < 0) { const char* e3 = getenv("FQ3C_TC5_MINK"); tc5_min_k = e3 ? atoi(e3) : TK; }  // one k-block is enough: the vectorised epilogue beats the mma.sync kernel even at K = 96
+        if (use_tc5 && o.N >= 16 && o.K >= tc5_min_k) {
           // Tile width: a multiple of 16 columns (a legal UMMA N at M = 128), chosen so that the grid covers the SMs.
           // Tall operands (M >= 128) keep BN >= 64 (every column tile re-reads the A rows); short ones (the transformer at
           // 8-33 frames) are weight-streaming problems: the width that minimises waves x tile cost, down to 16 columns.
@@ -782,7 +787,15 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
           const int nt = (o.N + bn - 1) / bn;
           bn = std::min(TMAXN, (((o.N + nt - 1) / nt) + 15) / 16 * 16);
           dim3 grid((o.N + bn - 1) / bn, mt, splits);
-          fq3c_gemm_tc5_kernel<<<grid, TTHREADS, T_SMEM, s>>>(o, bn, splits, Nw);
+          // Many tiles (the vocoder convolutions: hundreds of 128-row tiles with 2-11 k-blocks and a long SnakeBeta epilogue):
+          // three stages instead of six so that two CTAs share an SM and one's epilogue overlaps the other's main loop.
+          static int two_ctas = -1;
+          if (two_ctas < 0) { const char* e2 = getenv("FQ3C_TWO_CTAS"); two_ctas = (e2 == nullptr || atoi(e2) != 0) ? 1 : 0; }
+          const long n_ctas = (long)grid.x * grid.y * grid.z;
+          if (two_ctas && n_ctas >= 2 * 148 && KT <= 24)
+            fq3c_gemm_tc5_kernel<2><<<grid, TTHREADS, t_smem(3), s>>>(o, bn, splits, Nw, 3);
+          else
+            fq3c_gemm_tc5_kernel<1><<<grid, TTHREADS, T_SMEM, s>>>(o, bn, splits, Nw, TSTAGES);
           if (splits > 1) {
             const long n = (long)o.M * (Nw >> 3);
             fq3c_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o, splits, Nw);
