@@ -15,11 +15,11 @@ __global__ void probe(unsigned long long* buf, const size_t* offs, int n_addr, i
     unsigned long long* p = buf + offs[a] / 8;
     unsigned long long v = 0;
     // warm
-    for (int i = 0; i < 4; ++i) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p + (v & 0)) : "memory");
+    for (int i = 0; i < 4; ++i) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p + v) : "memory");
     long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p + (v & 0)) : "memory");
+    for (int i = 0; i < iters; ++i) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p + v) : "memory");
     long long t1 = clock64();
-    out[(size_t)a * gridDim.x + blockIdx.x] = (unsigned)((t1 - t0) / iters) + (unsigned)(v & 0);
+    out[(size_t)a * gridDim.x + blockIdx.x] = (unsigned)((t1 - t0) / iters) + (unsigned)v;
   }
 }
 int main() {

@@ -216,7 +216,7 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   p.pred_logits_all = nullptr;
   p.pos_override = -1;
   p.watchdog_ns = e->watchdog_ns;
-  p.debug = (4 << 16) | 32;  // poll back-off: sleep 32 ns after 4 immediate retries (FQ3_DEBUG = tries << 16 | ns)
+  p.debug = (16 << 16) | 32;  // poll back-off: sleep 32 ns after 16 immediate retries (FQ3_DEBUG = tries << 16 | ns)
   p.prof = e->prof;
   p.prof_cta = e->prof_cta;
   if (const char* d = getenv("FQ3_DEBUG")) p.debug = atoi(d);

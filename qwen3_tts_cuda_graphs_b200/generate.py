@@ -118,6 +118,46 @@ def fast_generate(
     )
 
 
+@torch.inference_mode()
+def fast_generate_batch(talker_graph, predictor_graph, requests, max_new_tokens: int = 2048, min_new_tokens: int = 2,
+                        temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0, do_sample: bool = True,
+                        repetition_penalty: float = 1.05, seed: Optional[int] = None):
+    """Request-parallel generation (BASELINE configs[4]; no counterpart in the reference, which is bs = 1): up to
+    `engine.max_streams` independent utterances share every weight sweep of the persistent kernel (lock-step frames; a
+    stream that hit EOS idles until the group is done).  `requests` = list of (talker_input_embeds, attention_mask,
+    trailing_text_hiddens, tts_pad_embed) as built for fast_generate.  Returns ([codec_ids | None per request], timing).
+    Each stream draws from its own Philox stream (seed ^ slot), so a request's tokens do not depend on its neighbours."""
+    eng = talker_graph.engine
+    policy = SamplingPolicy(
+        do_sample=do_sample, top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
+        min_new_tokens=min_new_tokens, suppress_tail=1024, seed=_fresh_seed() if seed is None else seed,
+    )
+    sub = predictor_graph.policy()
+    out = [None] * len(requests)
+    frames = 0
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for g0 in range(0, len(requests), eng.max_streams):
+        group = requests[g0:g0 + eng.max_streams]
+        for s, (tie, tam, tth, tpe) in enumerate(group):
+            if tie.shape[1] > eng.max_seq_len:
+                raise RuntimeError(
+                    f"Input is too long: prefill has {tie.shape[1]} tokens but max_seq_len={eng.max_seq_len}. "
+                    "Use shorter text or shorter reference audio."
+                )
+            eng.set_text_conditioning(s, tth[0], tpe)
+            eng.prefill(s, tie[0], _left_pads(tam), policy)
+        eng.decode_frames(len(group), min(max_new_tokens, eng.max_frames), policy, sub)
+        for s in range(len(group)):
+            n = eng.status(s).n_frames
+            frames += n
+            if n > 0:
+                out[g0 + s] = eng.read_codes(s, 0, n).to(group[s][0].device)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    return out, {"total_s": dt, "frames": frames, "audio_s_per_s": frames * 0.08 / dt if dt > 0 else 0.0}
+
+
 def suppress_mask_for(config, device) -> torch.Tensor:
     """generate.py:46-50 without the 1024 single-element writes."""
     V, eos = config.vocab_size, config.codec_eos_token_id

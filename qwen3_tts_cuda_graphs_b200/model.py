@@ -319,6 +319,36 @@ class FasterQwen3TTS:
         return audio, sr
 
     @torch.inference_mode()
+    def generate_voice_clone_batch(self, texts: List[str], language: str, ref_audio, ref_text: str, max_new_tokens: int = 2048,
+                                   min_new_tokens: int = 2, temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0,
+                                   do_sample: bool = True, repetition_penalty: float = 1.05, xvec_only: bool = True,
+                                   non_streaming_mode: bool = True, append_silence: bool = True) -> Tuple[List[np.ndarray], int]:
+        """Several texts in one voice, decoded `max_streams` at a time in lock-step (load the model with
+        `from_pretrained(..., max_streams=4)`).  An extension over the reference's bs = 1 API; returns one waveform per text."""
+        from .generate import fast_generate_batch
+
+        reqs, metas = [], []
+        for text in texts:
+            m, talker, config, tie, tam, tth, tpe, ref_codes = self._prepare_generation(
+                text, ref_audio, ref_text, language=language, xvec_only=xvec_only, non_streaming_mode=non_streaming_mode,
+                append_silence=append_silence)
+            reqs.append((tie, tam, tth, tpe))
+            metas.append((m, ref_codes))
+        codes, timing = fast_generate_batch(self.talker_graph, self.predictor_graph, reqs, max_new_tokens=max_new_tokens,
+                                            min_new_tokens=min_new_tokens, temperature=temperature, top_k=top_k, top_p=top_p,
+                                            do_sample=do_sample, repetition_penalty=repetition_penalty)
+        audio = []
+        for c, (m, ref_codes) in zip(codes, metas):
+            if c is None:
+                audio.append(np.zeros(1, dtype=np.float32))
+            else:
+                a, _ = self._decode_full(m, c, ref_codes)
+                audio.append(a[0])
+        logger.info(f"batch of {len(texts)}: {timing['frames']} frames in {timing['total_s']:.2f}s "
+                    f"({timing['audio_s_per_s']:.1f} audio-s/s before the codec)")
+        return audio, self.sample_rate
+
+    @torch.inference_mode()
     def generate_voice_clone_streaming(self, text: str, language: str, ref_audio, ref_text: str,
                                        max_new_tokens: int = 2048, min_new_tokens: int = 2, temperature: float = 0.9,
                                        top_k: int = 50, top_p: float = 1.0, do_sample: bool = True,

@@ -162,3 +162,20 @@ def test_voice_design():
         assert len(chunks) == 2
     finally:
         m.model.engine.close()
+
+
+def test_voice_clone_batch_matches_single_requests(ref_wav):
+    """Request-parallel decode (BASELINE configs[4]): greedy, three texts through a 2-stream engine (one full group and one
+    partial) must give, per text, exactly the waveform the bs = 1 call gives."""
+    m = load("tiny-Base", max_streams=2)
+    m.predictor_graph.do_sample = False  # the sub-talker policy is the graph's own mutable state (predictor_graph.py:34-60)
+    try:
+        texts = [TEXT, "A second, somewhat longer sentence for the batch.", "Third."]
+        kw = dict(max_new_tokens=10, do_sample=False, repetition_penalty=1.0)
+        singles = [m.generate_voice_clone(t, "English", ref_wav, "", **kw)[0][0] for t in texts]
+        batch, sr = m.generate_voice_clone_batch(texts, "English", ref_wav, "", **kw)
+        assert sr == m.sample_rate and len(batch) == len(texts)
+        for a, b in zip(singles, batch):
+            assert a.shape == b.shape and np.array_equal(a, b)
+    finally:
+        m.model.engine.close()
