@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=8, dest="cpu_frames")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batched-streams", type=int, default=4, dest="batched_streams",
+                    help="extra (reported, not the headline) leg at N=1: this many utterances decoded in lock-step; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -360,6 +362,33 @@ def main():
             },
             "decode_ms_per_frame": avg_ms / args.chunk,
         }
+        if world == 1 and args.batched_streams > 1:
+            # request-parallel decode inside one GPU (BASELINE configs[4]): the same prompt on every stream, non-streaming,
+            # codec decode of every utterance included; wall clock between synchronisations
+            from qwen3_tts_cuda_graphs_b200.generate import fast_generate_batch
+            ns = args.batched_streams
+            model_b = FasterQwen3TTS.from_pretrained(f"Qwen/Qwen3-TTS-12Hz-{args.model}", device=dev, dtype=torch.bfloat16,
+                                                     attn_implementation="eager", max_seq_len=2048, seed=0, max_streams=ns)
+            mb, _, _, tie_b, tam_b, tth_b, tpe_b, _ = model_b._prepare_generation(TEXT, ref_wav, REF_TEXT, language="English",
+                                                                                  non_streaming_mode=True)
+            reqs = [(tie_b, tam_b, tth_b, tpe_b)] * ns
+
+            def batched_step():
+                codes, _ = fast_generate_batch(model_b.talker_graph, model_b.predictor_graph, reqs, **gen_kw)
+                n = 0
+                for c in codes:
+                    a, sr_b = model_b._decode_full(mb, c)
+                    n += len(a[0])
+                return n / sr_b
+
+            batched_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            a_s = sum(batched_step() for _ in range(max(1, args.steps - 1)))
+            torch.cuda.synchronize()
+            line["batched"] = {"streams": ns, "value": a_s / (time.perf_counter() - t0), "unit": UNIT,
+                               "what": "lock-step request-parallel decode of identical prompts on one GPU, non-streaming, codec included"}
+            model_b.model.engine.close()
         if world == 1 and not args.no_cpu_baseline:
             arm = CpuOracleArm(args.model, args.cpu_frames)
             arm.step()
