@@ -59,6 +59,8 @@ typedef struct fq3c_op {
   void* C2;
   void* ws;              /* GEMM, optional: fp32 workspace for split-K partial tiles (>= splits * M * round8(N) * 4 bytes are used); */
   int64_t ws_bytes;      /* NULL / 0 = never split.  Ops of one stream-ordered list may share it.                                  */
+  int32_t m_begin;       /* GEMM: only output rows [m_begin, M) are computed (tail-only streaming decode); pointers stay at row 0 */
+  int32_t reserved;
 } fq3c_op;
 
 int fq3c_abi_version(void);

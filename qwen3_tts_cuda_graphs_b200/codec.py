@@ -40,7 +40,7 @@ class Op(C.Structure):
         ("i0", C.c_int32), ("i1", C.c_int32), ("i2", C.c_int32), ("f0", C.c_float), ("f1", C.c_float),
         ("A", C.c_void_p), ("B", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("scale", C.c_void_p),
         ("p0", C.c_void_p), ("p1", C.c_void_p), ("C", C.c_void_p), ("C2", C.c_void_p),
-        ("ws", C.c_void_p), ("ws_bytes", C.c_int64),
+        ("ws", C.c_void_p), ("ws_bytes", C.c_int64), ("m_begin", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -92,7 +92,7 @@ def load_lib():
     lib.fq3c_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
     lib.fq3c_graph_destroy.restype = C.c_int
     lib.fq3c_graph_destroy.argtypes = [C.c_void_p]
-    if lib.fq3c_abi_version() != 2:
+    if lib.fq3c_abi_version() != 3:
         raise CodecError("libfq3codec.so ABI version mismatch")
     _lib = lib
     return lib
@@ -298,8 +298,9 @@ class CodecDecoder:
         return None if t is None else t.data_ptr()
 
     def _gemm(self, plan, A, W, M, N, cin, taps=1, tap_off=(0,), flags=0, bias=None, res=None, scale=None, snake=None,
-              col_mod=None, out=None, out2=None, out_f32=False):
+              col_mod=None, out=None, out2=None, out_f32=False, m_begin=0):
         o = Op()
+        o.m_begin = max(0, min(int(m_begin), M - 1))
         o.kind, o.flags = K_GEMM, flags | (F_OUT_F32 if out_f32 else 0)
         o.M, o.N, o.K, o.taps, o.cin = M, N, taps * cin, taps, cin
         o.a_rows, o.lda = A.shape[0], A.shape[1]
@@ -343,7 +344,7 @@ class CodecDecoder:
         plan.ops.append(o)
         return out
 
-    def _build(self, T: int) -> _Plan:
+    def _build(self, T: int, skip: int = 0) -> _Plan:
         c, g = self.cfg, self.g
         plan = _Plan()
         H, d, nh, nkv = c.hidden_size, c.head_dim, c.num_attention_heads, c.num_key_value_heads
@@ -381,29 +382,49 @@ class CodecDecoder:
             h = self._simple(plan, K_LAYERNORM, h, rows, H, scale=g[f"{p}.ln.w"], bias=g[f"{p}.ln.b"], f0=1e-6)
             h, _ = self._gemm(plan, h, g[f"{p}.pw1.w"], rows, 4 * H, H, bias=g[f"{p}.pw1.b"], flags=F_GELU)
             x, _ = self._gemm(plan, h, g[f"{p}.pw2.w"], rows, H, 4 * H, bias=g[f"{p}.pw2.b"], scale=g[f"{p}.gamma"], res=x)
-        # 5. vocoder
+        # 5. vocoder.  Every layer is causal with a finite reach, so when the caller only wants the samples from `skip` on
+        #    (streaming: the 25 context frames of a window are decoded for their state, not for their audio) each layer only
+        #    has to produce the rows the wanted samples can see: walk the receptive field back from the output to get the
+        #    first row of every op (exactly the same samples come out; the rows in front are never computed nor read).
         D = c.decoder_dim
-        _, xs = self._gemm(plan, x, g["dec0.w"], rows, D, H, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["dec0.b"],
-                           snake="decoder.1.block.0")
         nblk = len(c.upsample_rates)
+        dils = (1, 3, 9)
+        lvl_rows = [rows]
+        for r in c.upsample_rates:
+            lvl_rows.append((lvl_rows[-1] - 1) * r)
+        s_need = max(0, min(int(skip), max(lvl_rows[-1] - 1, 0)))
+        fin_begin = s_need
+        s_need -= 6
+        unit_begin = [[0] * 3 for _ in range(nblk)]
+        tconv_begin = [0] * nblk
+        for i in range(nblk - 1, -1, -1):
+            for j in (2, 1, 0):
+                unit_begin[i][j] = max(0, s_need)
+                s_need -= 6 * dils[j]
+            tconv_begin[i] = max(0, s_need) // c.upsample_rates[i]
+            s_need = tconv_begin[i]
+        dec0_begin = max(0, s_need)
+        _, xs = self._gemm(plan, x, g["dec0.w"], rows, D, H, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["dec0.b"],
+                           snake="decoder.1.block.0", m_begin=dec0_begin)
         for i, r in enumerate(c.upsample_rates):
             cin, cout = D // 2 ** i, D // 2 ** (i + 1)
             p = f"decoder.{i + 1}.block"
             m_out = rows - 1
             y, ys = self._gemm(plan, xs, g[f"{p}.1.w"], m_out, r * cout, cin, taps=2, tap_off=[1, 0], bias=g[f"{p}.1.b"],
-                               col_mod=cout, snake=f"{p}.2.act1")
+                               col_mod=cout, snake=f"{p}.2.act1", m_begin=tconv_begin[i])
             rows = m_out * r
             x, xs = y.view(-1, cout)[:max(rows, 1)], ys.view(-1, cout)[:max(rows, 1)]
-            for j, dil in enumerate((1, 3, 9)):
+            for j, dil in enumerate(dils):
                 q_ = f"{p}.{j + 2}"
                 _, hs = self._gemm(plan, xs, g[f"{q_}.c1.w"], rows, cout, cout, taps=7, tap_off=[(t - 6) * dil for t in range(7)],
-                                   bias=g[f"{q_}.c1.b"], snake=f"{q_}.act2")
+                                   bias=g[f"{q_}.c1.b"], snake=f"{q_}.act2", m_begin=unit_begin[i][j])
                 nxt = f"{p}.{j + 3}.act1" if j < 2 else (f"decoder.{i + 2}.block.0" if i + 1 < nblk else "final")
-                x, xs = self._gemm(plan, hs, g[f"{q_}.c2.w"], rows, cout, cout, bias=g[f"{q_}.c2.b"], res=x, snake=nxt)
+                x, xs = self._gemm(plan, hs, g[f"{q_}.c2.w"], rows, cout, cout, bias=g[f"{q_}.c2.b"], res=x, snake=nxt,
+                                   m_begin=unit_begin[i][j])
         out_dim = D // 2 ** nblk
-        plan.wav = torch.empty(max(rows, 1), 1, dtype=torch.float32, device=self.device)
+        plan.wav = torch.zeros(max(rows, 1), 1, dtype=torch.float32, device=self.device)
         self._gemm(plan, xs, g["final.w"], rows, 1, out_dim, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["final.b"],
-                   flags=F_CLAMP, out=plan.wav, out_f32=True)
+                   flags=F_CLAMP, out=plan.wav, out_f32=True, m_begin=fin_begin)
         plan.n_samples = rows
         if os.environ.get("FQ3C_SPLITK", "1") != "0":
             attach_splitk_workspace(plan.ops, self.device, plan.keep)
@@ -440,20 +461,24 @@ class CodecDecoder:
 
     # ---- run ------------------------------------------------------------------------------------
     @torch.inference_mode()
-    def decode(self, codes: torch.Tensor) -> torch.Tensor:
-        """codes int64 [T, Q] (any device) -> float32 waveform [n_samples] on the decoder's device."""
+    def decode(self, codes: torch.Tensor, skip_samples: int = 0) -> torch.Tensor:
+        """codes int64 [T, Q] (any device) -> float32 waveform [n_samples] on the decoder's device.  With `skip_samples` = k
+        the caller promises to ignore samples [0, k) (the context part of a streaming window): they come back as zeros and
+        the vocoder only computes what samples [k, n) can see — those are bit-identical to a full decode."""
         T = int(codes.shape[0])
         if T == 0 or self.n_samples(T) <= 0:
             return torch.zeros(0, dtype=torch.float32, device=self.device)
-        plan = self._plans.get(T)
+        skip = int(skip_samples) if (skip_samples and os.environ.get("FQ3C_TAIL_ONLY", "1") != "0") else 0
+        key = T if skip == 0 else (T, skip)
+        plan = self._plans.get(key)
         if plan is None:
             # streaming revisits a handful of sizes (chunk multiples, then chunk+25); long one-shot decodes are
             # not worth pinning gigabytes of activation buffers for
-            for k in [k for k in self._plans if k > 96 or len(self._plans) >= 24]:
+            for k in [k for k in self._plans if (k[0] if isinstance(k, tuple) else k) > 96 or len(self._plans) >= 24]:
                 old = self._plans.pop(k)
                 if old.graph is not None:
                     self.lib.fq3c_graph_destroy(old.graph)
-            plan = self._plans[T] = self._build(T)
+            plan = self._plans[key] = self._build(T, skip)
         plan.codes.copy_(codes.to(torch.int64), non_blocking=True)
         self.run_plan(plan)
         return plan.wav.view(-1)[: plan.n_samples].clone()
@@ -477,6 +502,7 @@ class SpeechTokenizer:
 
     def decode(self, inputs) -> Tuple[List[torch.Tensor], int]:
         codes = inputs["audio_codes"] if isinstance(inputs, dict) else inputs
+        skip = int(inputs.get("skip_samples", 0)) if isinstance(inputs, dict) else 0  # extension: see CodecDecoder.decode
         if codes.dim() == 2:
             codes = codes.unsqueeze(0)
-        return [self.decoder.decode(codes[b]) for b in range(codes.shape[0])], self.sample_rate
+        return [self.decoder.decode(codes[b], skip) for b in range(codes.shape[0])], self.sample_rate

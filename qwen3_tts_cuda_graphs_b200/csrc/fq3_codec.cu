@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128) fq3c_gemm_kernel(const fq3c_op o) {
   __shared__ __align__(16) bf16 Bs[2][BN][LDS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 1, wn = warp & 1;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = o.m_begin + blockIdx.y * BM, n0 = blockIdx.x * BN;
   const bf16* A = reinterpret_cast<const bf16*>(o.A);
   const bf16* B = reinterpret_cast<const bf16*>(o.B);
   const int KT = (o.K + BK - 1) / BK;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(TTHREADS, MINB) fq3c_gemm_tc5_kernel(const fq3
   const uint32_t full = bars, empty = bars + 8u * NST, done = bars + 16u * NST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + NST * (T_A_BYTES + T_B_BYTES) + 16 * NST + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
+  const int m0 = o.m_begin + blockIdx.y * TM, n0 = blockIdx.x * BN;
   const bf16* A = reinterpret_cast<const bf16*>(o.A);
   const bf16* B = reinterpret_cast<const bf16*>(o.B);
   const int KT_all = (o.K + TK - 1) / TK;
@@ -456,8 +456,9 @@ __global__ void __launch_bounds__(TTHREADS, MINB) fq3c_gemm_tc5_kernel(const fq3
 __global__ void __launch_bounds__(256) fq3c_splitk_reduce_kernel(const fq3c_op o, const int splits, const int Nw) {
   const int groups = Nw >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)o.M * groups) return;
-  const int row = (int)(idx / groups), col = (int)(idx - (long)row * groups) * 8;
+  if (idx >= (long)(o.M - o.m_begin) * groups) return;
+  const int r_rel = (int)(idx / groups);
+  const int row = o.m_begin + r_rel, col = (int)(idx - (long)r_rel * groups) * 8;
   float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float* ws = reinterpret_cast<const float*>(o.ws);
   for (int z = 0; z < splits; ++z) {
@@ -733,7 +734,7 @@ int fail(const std::string& m) { g_err = m; return -1; }
 
 extern "C" {
 
-int fq3c_abi_version(void) { return 2; }
+int fq3c_abi_version(void) { return 3; }
 const char* fq3c_last_error(void) { return g_err.c_str(); }
 int64_t fq3c_launch_count(void) { return g_launches; }
 
@@ -745,6 +746,7 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
     switch (o.kind) {
       case FQ3C_GEMM: {
         if (o.K % 8 || o.cin % 8 || o.taps > 8 || o.col_mod <= 0) return fail("gemm: K and cin must be multiples of 8, taps <= 8");
+        if (o.m_begin < 0 || o.m_begin >= o.M) return fail("gemm: m_begin outside [0, M)");
         static int use_tc5 = -1;
         if (use_tc5 < 0) {
           const char* e = getenv("FQ3C_TCGEN05");
@@ -759,7 +761,7 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
           // Tile width: a multiple of 16 columns (a legal UMMA N at M = 128), chosen so that the grid covers the SMs.
           // Tall operands (M >= 128) keep BN >= 64 (every column tile re-reads the A rows); short ones (the transformer at
           // 8-33 frames) are weight-streaming problems: the width that minimises waves x tile cost, down to 16 columns.
-          const int mt = (o.M + TM - 1) / TM;
+          const int mt = (o.M - o.m_begin + TM - 1) / TM;
           int bn = TMAXN;
           if (o.M >= TM) {
             if (((o.N + bn - 1) / bn) * mt < 100) bn = 64;
@@ -779,7 +781,8 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
           int splits = 1;
           if (o.ws && o.M <= 4 * TM && KT >= 8) {
             const int bn_s = o.N >= 64 ? 64 : 32;
-            const int tiles_s = ((o.N + bn_s - 1) / bn_s) * mt;
+            // the split count must not depend on m_begin: a tail-only decode has to add the same partial sums in the same order
+            const int tiles_s = ((o.N + bn_s - 1) / bn_s) * ((o.M + TM - 1) / TM);
             int sp = std::min(std::min(8, KT / 4), 148 / std::max(1, tiles_s));
             while (sp > 1 && (int64_t)sp * o.M * Nw * 4 > o.ws_bytes) --sp;
             if (sp > 1) { splits = sp; bn = bn_s; }
@@ -797,13 +800,13 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
           else
             fq3c_gemm_tc5_kernel<1><<<grid, TTHREADS, T_SMEM, s>>>(o, bn, splits, Nw, TSTAGES);
           if (splits > 1) {
-            const long n = (long)o.M * (Nw >> 3);
+            const long n = (long)(o.M - o.m_begin) * (Nw >> 3);
             fq3c_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o, splits, Nw);
             g_launches += 1;
           }
           break;
         }
-        dim3 grid((o.N + BN - 1) / BN, (o.M + BM - 1) / BM);
+        dim3 grid((o.N + BN - 1) / BN, (o.M - o.m_begin + BM - 1) / BM);
         fq3c_gemm_kernel<<<grid, 128, 0, s>>>(o);
         break;
       }

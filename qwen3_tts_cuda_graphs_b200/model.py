@@ -286,9 +286,11 @@ class FasterQwen3TTS:
                 start = max(0, n_total - n_new - context_frames)
                 window = flat[start:]
                 n_ctx = window.shape[0] - n_new
-                audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0)})
+                cut = int(round(n_ctx * spf)) if n_ctx > 0 else 0
+                # the context frames are decoded for their state only: tell the decoder which samples will be thrown away
+                audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0), "skip_samples": cut})
                 audio = audio_list[0].flatten()
-                new_audio = audio[int(round(n_ctx * spf)):] if n_ctx > 0 else audio
+                new_audio = audio[cut:] if n_ctx > 0 else audio
             yield (self._to_numpy(new_audio) if to_host else new_audio), sr, timing
 
     def _gen_kwargs(self, max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty):

@@ -75,6 +75,30 @@ def test_decode_is_causal_on_device(tiny):
     assert torch.equal(a, b[: a.numel()])
 
 
+@pytest.mark.parametrize("T,skip_frames", [(33, 25), (33, 32), (16, 8), (9, 1), (8, 0)])
+def test_tail_only_decode_is_bit_identical(tiny, T, skip_frames):
+    """Streaming window: the caller throws the context samples away, the vocoder only computes what the kept samples can see
+    (receptive-field walk in CodecDecoder._build).  The kept samples must be bit-identical to the full decode, the rest zero."""
+    cfg, dec, _ = tiny
+    codes = torch.randint(0, cfg.codebook_size, (T, cfg.num_quantizers), generator=torch.Generator().manual_seed(100 + T)).cuda()
+    full = dec.decode(codes)
+    for skip in sorted({int(round(skip_frames * full.numel() / T)), max(0, dec.n_samples(skip_frames)), min(full.numel() - 1, 7)}):
+        part = dec.decode(codes, skip_samples=skip)
+        assert part.shape == full.shape
+        assert torch.equal(part[skip:], full[skip:]), skip
+        assert skip == 0 or float(part[:skip].abs().max()) == 0.0
+
+
+def test_tail_only_decode_full_size():
+    cfg, dec, _ = make("0.6B-Base", seed=2)
+    T = 33
+    codes = torch.randint(0, cfg.codebook_size, (T, cfg.num_quantizers), generator=torch.Generator().manual_seed(3)).cuda()
+    full = dec.decode(codes)
+    skip = int(round(25 * full.numel() / T))
+    part = dec.decode(codes, skip_samples=skip)
+    assert torch.equal(part[skip:], full[skip:])
+
+
 def test_full_size_decoder_matches_oracle():
     """Real dims (hidden 1024, 8 layers, window 72, decoder_dim 1536): one streaming chunk of 8 frames."""
     cfg, dec, orc = make("0.6B-Base", seed=2)
