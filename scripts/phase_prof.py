@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import make_cfg, make_weights, make_engine, synth_prompt
 from qwen3_tts_cuda_graphs_b200.engine import SamplingPolicy, SubPolicy
-cfg = make_cfg("0.6B-Base")
+cfg = make_cfg(sys.argv[1] if len(sys.argv) > 1 else "0.6B-Base")
 w = make_weights(cfg, seed=0, norm_jitter=0.0)
 eng = make_engine(cfg, w, max_seq_len=2048, max_frames=64)
 tie, tam, tth, tpe = synth_prompt(cfg, T=14)
