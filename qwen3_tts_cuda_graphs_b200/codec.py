@@ -48,6 +48,33 @@ SPLITK_MAX_ROWS = 512          # GEMMs up to this many rows may be split over K 
 SPLITK_WS_CAP = 64 << 20       # bytes of fp32 workspace one plan may pin
 
 
+VOCODER_DILATIONS = (1, 3, 9)  # the three residual units of a decoder block (7-tap causal convs)
+
+
+def vocoder_tail_starts(rows0: int, upsample_rates, skip: int):
+    """First output row every vocoder op must produce so that waveform samples [skip, n) come out exactly as in a full
+    decode.  Layers, in order: dec0 (7-tap causal conv over `rows0` rows); per block i: transposed conv (kernel 2r, stride r,
+    right-trimmed: output row m*r + k reads input rows m and m+1; (rows-1)*r output rows), then three residual units
+    (7-tap causal conv with dilation d -> reads back 6*d rows; 1x1 conv + residual -> same row); final 7-tap causal conv.
+    Returns (dec0_begin, tconv_begin[i] in the transposed conv's own (input) rows, unit_begin[i][j], final_begin)."""
+    nblk = len(upsample_rates)
+    lvl_rows = [rows0]
+    for r in upsample_rates:
+        lvl_rows.append((lvl_rows[-1] - 1) * r)
+    s_need = max(0, min(int(skip), max(lvl_rows[-1] - 1, 0)))
+    fin_begin = s_need
+    s_need -= 6
+    unit_begin = [[0] * 3 for _ in range(nblk)]
+    tconv_begin = [0] * nblk
+    for i in range(nblk - 1, -1, -1):
+        for j in (2, 1, 0):
+            unit_begin[i][j] = max(0, s_need)
+            s_need -= 6 * VOCODER_DILATIONS[j]
+        tconv_begin[i] = max(0, s_need) // upsample_rates[i]
+        s_need = tconv_begin[i]
+    return max(0, s_need), tconv_begin, unit_begin, fin_begin
+
+
 def attach_splitk_workspace(ops, device, keep) -> None:
     """One fp32 workspace per stream-ordered op list: every short GEMM of the list may use it for split-K partial tiles."""
     need = 0
@@ -388,22 +415,8 @@ class CodecDecoder:
         #    first row of every op (exactly the same samples come out; the rows in front are never computed nor read).
         D = c.decoder_dim
         nblk = len(c.upsample_rates)
-        dils = (1, 3, 9)
-        lvl_rows = [rows]
-        for r in c.upsample_rates:
-            lvl_rows.append((lvl_rows[-1] - 1) * r)
-        s_need = max(0, min(int(skip), max(lvl_rows[-1] - 1, 0)))
-        fin_begin = s_need
-        s_need -= 6
-        unit_begin = [[0] * 3 for _ in range(nblk)]
-        tconv_begin = [0] * nblk
-        for i in range(nblk - 1, -1, -1):
-            for j in (2, 1, 0):
-                unit_begin[i][j] = max(0, s_need)
-                s_need -= 6 * dils[j]
-            tconv_begin[i] = max(0, s_need) // c.upsample_rates[i]
-            s_need = tconv_begin[i]
-        dec0_begin = max(0, s_need)
+        dils = VOCODER_DILATIONS
+        dec0_begin, tconv_begin, unit_begin, fin_begin = vocoder_tail_starts(rows, c.upsample_rates, skip)
         _, xs = self._gemm(plan, x, g["dec0.w"], rows, D, H, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["dec0.b"],
                            snake="decoder.1.block.0", m_begin=dec0_begin)
         for i, r in enumerate(c.upsample_rates):
