@@ -28,7 +28,7 @@ K_QKNORM_ROPE_KV = 8
 class DensePrefill:
     """Op list for rows [0, R) of a prompt, built once for a row capacity and re-used with M patched per call."""
 
-    MIN_ROWS = 16  # below this the chunked path (<= 2 launches of the decode kernel) is at least as fast
+    MIN_ROWS = int(os.environ.get("FQ3_DENSE_MIN_ROWS", "16"))  # below this the chunked path (<= 2 launches of the decode kernel) is at least as fast
     MAX_GRAPHS = 8  # captured (rows, stream) plans kept
 
     def __init__(self, engine):

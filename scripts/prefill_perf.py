@@ -10,7 +10,7 @@ w = make_weights(cfg, seed=0, norm_jitter=0.0)
 eng = make_engine(cfg, w, max_seq_len=2048, max_frames=64)
 pol = SamplingPolicy(do_sample=False, repetition_penalty=1.0)
 ev = lambda: torch.cuda.Event(enable_timing=True)
-for T in (39, 120, 240, 480):
+for T in [int(t) for t in os.environ.get("PF_T", "39,120,240,480").split(",")]:
     tie, tam, tth, tpe = synth_prompt(cfg, T=T)
     x = tie[0].cuda()
     res = {}
