@@ -35,7 +35,7 @@ enum fq3c_kind {
 
 enum fq3c_flags {
   FQ3C_BIAS = 1, FQ3C_GELU = 2, FQ3C_RESID = 4, FQ3C_SCALE = 8, FQ3C_SWIGLU = 16, FQ3C_CLAMP = 32,
-  FQ3C_OUT_F32 = 64, FQ3C_SNAKE2 = 128 /* also write C2 = snake(C) */
+  FQ3C_OUT_F32 = 64, FQ3C_SNAKE2 = 128 /* also write C2 = snake(C) */, FQ3C_SILU = 256 /* text_projection: Linear -> SiLU */
 };
 
 typedef struct fq3c_op {

@@ -104,7 +104,10 @@ class _CodecHead:
 
 
 class _TextProjection:
-    """`talker.text_projection`: Linear(+bias) -> SiLU -> Linear(+bias) on the streaming kernel, 8 rows a launch."""
+    """`talker.text_projection`: Linear(+bias) -> SiLU -> Linear(+bias).  All rows of a call in two tensor-core GEMMs of
+    libfq3codec.so reading the arena weights in place (a prompt has 3-60 text rows: this is a small dense contraction, and
+    twelve 8-row launches of the streaming kernel were half of the host time of the prompt build); the streaming kernel's
+    `fq3_linear` stays the path for shapes the GEMM does not take (K < 64) and when FQ3_TEXTPROJ_GEMM=0."""
 
     def __init__(self, engine: Engine, arena: Arena):
         self.engine = engine
@@ -112,12 +115,51 @@ class _TextProjection:
         self.b1 = arena.view("talker.text_projection.linear_fc1.bias")
         self.w2 = arena.view("talker.text_projection.linear_fc2.weight")
         self.b2 = arena.view("talker.text_projection.linear_fc2.bias")
+        self._gemm = None
+        self._plans = {}
+        if os.environ.get("FQ3_TEXTPROJ_GEMM", "1") != "0" and self.w1.shape[1] % 64 == 0 and self.w2.shape[1] % 64 == 0:
+            from . import codec as _codec
+            self._gemm = _codec
+            self._lib = _codec.load_lib()
+            self._b1f, self._b2f = self.b1.float().contiguous(), self.b2.float().contiguous()  # the GEMM epilogue adds an fp32 bias
+
+    def _plan(self, M: int):
+        c = self._gemm
+        dev = self.w1.device
+        with torch.inference_mode(False):  # cached staging buffers are written in place from either mode
+            x = torch.empty(M, self.w1.shape[1], dtype=torch.bfloat16, device=dev)
+            h = torch.empty(M, self.w1.shape[0], dtype=torch.bfloat16, device=dev)
+            y = torch.empty(M, self.w2.shape[0], dtype=torch.bfloat16, device=dev)
+        ops = []
+        for A, W, b, out, fl in ((x, self.w1, self._b1f, h, c.F_BIAS | c.F_SILU), (h, self.w2, self._b2f, y, c.F_BIAS)):
+            o = c.Op()
+            o.kind, o.flags = c.K_GEMM, fl
+            o.M, o.N, o.K, o.taps, o.cin = M, W.shape[0], W.shape[1], 1, W.shape[1]
+            o.a_rows, o.lda, o.col_mod, o.ldc = M, A.shape[1], W.shape[0], out.shape[1]
+            o.A, o.B, o.C, o.bias = A.data_ptr(), W.data_ptr(), out.data_ptr(), b.data_ptr()
+            ops.append(o)
+        keep = [x, h, y]
+        with torch.inference_mode(False):
+            c.attach_splitk_workspace(ops, dev, keep)
+        return (c.Op * 2)(*ops), x, y, keep
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         shape = x.shape
         rows = x.reshape(-1, shape[-1]).to(torch.bfloat16).contiguous()
+        M = rows.shape[0]
+        if self._gemm is not None and 0 < M <= 512:
+            plan = self._plans.get(M)
+            if plan is None:
+                if len(self._plans) >= 32:
+                    self._plans.clear()
+                plan = self._plans[M] = self._plan(M)
+            arr, xin, yout, _ = plan
+            xin.copy_(rows)
+            if self._lib.fq3c_run(arr, 2, torch.cuda.current_stream().cuda_stream) != 0:
+                raise self._gemm.CodecError(self._lib.fq3c_last_error().decode())
+            return yout.clone().reshape(*shape[:-1], -1)
         outs = []
-        for i in range(0, rows.shape[0], 8):
+        for i in range(0, M, 8):
             h = self.engine.linear(self.w1, rows[i:i + 8].contiguous(), bias=self.b1, silu=True)
             outs.append(self.engine.linear(self.w2, h, bias=self.b2))
         return torch.cat(outs, 0).reshape(*shape[:-1], -1)

@@ -29,7 +29,7 @@ from . import build as _build
 from .config import CodecDecoderConfig
 
 K_GEMM, K_RVQ, K_RMSNORM, K_ROPE, K_ATTN, K_DWCONV, K_LAYERNORM, K_SNAKE = range(8)
-F_BIAS, F_GELU, F_RESID, F_SCALE, F_SWIGLU, F_CLAMP, F_OUT_F32, F_SNAKE2 = 1, 2, 4, 8, 16, 32, 64, 128
+F_BIAS, F_GELU, F_RESID, F_SCALE, F_SWIGLU, F_CLAMP, F_OUT_F32, F_SNAKE2, F_SILU = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
 class Op(C.Structure):

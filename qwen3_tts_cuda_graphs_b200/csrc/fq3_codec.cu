@@ -61,6 +61,7 @@ __device__ __forceinline__ void epilogue_pair(const fq3c_op& o, int row, int col
     return;
   }
   if (o.flags & FQ3C_GELU) { v0 = bf16r(gelu_f(v0)); v1 = bf16r(gelu_f(v1)); }
+  if (o.flags & FQ3C_SILU) { v0 = bf16r(silu_f(v0)); v1 = bf16r(silu_f(v1)); }
   if (o.flags & FQ3C_SCALE) {
     const float* s = reinterpret_cast<const float*>(o.scale);
     v0 = bf16r(v0 * s[cm0]);
@@ -127,6 +128,10 @@ __device__ __forceinline__ void epilogue_row8(const fq3c_op& o, int row, int col
   if (o.flags & FQ3C_GELU) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = bf16r(gelu_f(v[j]));
+  }
+  if (o.flags & FQ3C_SILU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = bf16r(silu_f(v[j]));
   }
   if (o.flags & FQ3C_SCALE) {
     const float* sc = reinterpret_cast<const float*>(o.scale);
