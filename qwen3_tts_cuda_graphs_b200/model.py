@@ -8,6 +8,7 @@ codec kernels (csrc/fq3_codec.cu).
 """
 from __future__ import annotations
 
+import contextlib
 import logging
 import wave
 from pathlib import Path
@@ -35,6 +36,7 @@ class FasterQwen3TTS:
         self.max_seq_len = max_seq_len
         self.sample_rate = self._infer_sample_rate(base_model)
         self._warmed_up = False
+        self._codec_stream = None  # side stream of the overlapped streaming decode (FQ3_OVERLAP_CODEC)
         self._voice_prompt_cache = {}
 
     @staticmethod
@@ -268,29 +270,39 @@ class FasterQwen3TTS:
         all_codes, prev_len, spf = [], 0, None
         tok = m.speech_tokenizer
         for chunk, timing in stream:
-            all_codes.append(chunk)
-            n_new = chunk.shape[0]
-            flat = torch.cat(all_codes, dim=0)
-            n_total = flat.shape[0]
-            if spf is None:
-                codes_in = flat if ref_codes is None else torch.cat([ref_codes.to(flat.device), flat], dim=0)
-                audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0)})
-                audio = audio_list[0].flatten()
-                if ref_codes is not None:
-                    audio = audio[int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * len(audio)):]
-                new_audio = audio[prev_len:]
-                prev_len = len(audio)
-                if n_total >= min_cal:
-                    spf = len(audio) / n_total
-            else:
-                start = max(0, n_total - n_new - context_frames)
-                window = flat[start:]
-                n_ctx = window.shape[0] - n_new
-                cut = int(round(n_ctx * spf)) if n_ctx > 0 else 0
-                # the context frames are decoded for their state only: tell the decoder which samples will be thrown away
-                audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0), "skip_samples": cut})
-                audio = audio_list[0].flatten()
-                new_audio = audio[cut:] if n_ctx > 0 else audio
+            # FQ3_OVERLAP_CODEC (streaming.py): the next chunk is already running on the main stream, so everything below — the
+            # window gather and the codec decode — goes to a side stream that only waits for THIS chunk's codes
+            ready = timing.get("codes_ready") if isinstance(timing, dict) else None
+            if ready is not None:
+                if self._codec_stream is None:
+                    self._codec_stream = torch.cuda.Stream(device=chunk.device)
+                self._codec_stream.wait_event(ready)
+            with (torch.cuda.stream(self._codec_stream) if ready is not None else contextlib.nullcontext()):
+                all_codes.append(chunk)
+                n_new = chunk.shape[0]
+                flat = torch.cat(all_codes, dim=0)
+                n_total = flat.shape[0]
+                if spf is None:
+                    codes_in = flat if ref_codes is None else torch.cat([ref_codes.to(flat.device), flat], dim=0)
+                    audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0)})
+                    audio = audio_list[0].flatten()
+                    if ref_codes is not None:
+                        audio = audio[int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * len(audio)):]
+                    new_audio = audio[prev_len:]
+                    prev_len = len(audio)
+                    if n_total >= min_cal:
+                        spf = len(audio) / n_total
+                else:
+                    start = max(0, n_total - n_new - context_frames)
+                    window = flat[start:]
+                    n_ctx = window.shape[0] - n_new
+                    cut = int(round(n_ctx * spf)) if n_ctx > 0 else 0
+                    # the context frames are decoded for their state only: tell the decoder which samples will be thrown away
+                    audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0), "skip_samples": cut})
+                    audio = audio_list[0].flatten()
+                    new_audio = audio[cut:] if n_ctx > 0 else audio
+            if ready is not None:
+                self._codec_stream.synchronize()
             yield (self._to_numpy(new_audio) if to_host else new_audio), sr, timing
 
     def _gen_kwargs(self, max_new_tokens, min_new_tokens, temperature, top_k, top_p, do_sample, repetition_penalty):

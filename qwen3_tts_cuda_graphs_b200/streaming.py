@@ -7,6 +7,7 @@ frames and one host synchronisation — the same frames, in the same order, as t
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import Generator, Optional, Tuple
 
@@ -52,15 +53,26 @@ def fast_generate_streaming(
         t_prefill = time.time() - t0
         budget = min(max_new_tokens, eng.max_frames)
         emitted, chunk_idx = 0, 0
-        while emitted < budget:
-            t1 = time.time()
+        # FQ3_OVERLAP_CODEC=1 (with FQ3_GRID=128 so that the decode kernel leaves SMs free): from the second chunk on, the next
+        # chunk is launched BEFORE the current one is yielded, so the caller's codec decode (on a side stream, model.py) runs
+        # beside it.  The first chunk keeps the plain order: time to first audio must not wait behind a speculative launch.
+        overlap = os.environ.get("FQ3_OVERLAP_CODEC", "0") == "1"
+        in_flight = 0  # frames of a chunk that is already running
+
+        def launch(n):
             if launch_events is not None:  # bench.py: CUDA-event bracket of the persistent-kernel launch alone
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            eng.decode_frames(1, min(chunk_size, budget - emitted), policy, sub)
+            eng.decode_frames(1, n, policy, sub)
             if launch_events is not None:
                 e1.record()
-                launch_events.append((e0, e1, min(chunk_size, budget - emitted)))
+                launch_events.append((e0, e1, n))
+
+        while emitted < budget:
+            t1 = time.time()
+            if in_flight == 0:
+                launch(min(chunk_size, budget - emitted))
+            in_flight = 0
             st = eng.status(idx)
             dt = time.time() - t1
             n_new = st.n_frames - emitted
@@ -72,8 +84,19 @@ def fast_generate_streaming(
                     "decode_ms": dt * 1000, "total_steps_so_far": emitted, "is_final": n_new < chunk_size,
                 }
                 chunk_idx += 1
+                if overlap and chunk_idx >= 2 and n_new == chunk_size and not st.done and emitted < budget:
+                    ready = torch.cuda.Event()
+                    ready.record()                       # the codes of this chunk are complete here ...
+                    info["codes_ready"] = ready          # ... the side stream waits for this, not for the next chunk
+                    in_flight = min(chunk_size, budget - emitted)
+                    launch(in_flight)
                 # like the reference, only a trailing partial chunk is flagged final (streaming.py:175-188)
-                yield chunk, info
+                try:
+                    yield chunk, info
+                except GeneratorExit:
+                    if in_flight:
+                        eng.status(idx)                  # the consumer left: let the speculative chunk finish
+                    raise
                 if n_new < chunk_size:
                     break
             if st.done or n_new == 0:
