@@ -157,6 +157,13 @@ int fq3_apply_repetition_penalty(fq3_engine* e, void* logits_f32, int V, const v
  * stream's codes buffer.  One launch, zero host synchronisations inside. */
 int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_policy* policy,
                       const fq3_subpolicy* sub, void* stream);
+
+/* The frame loop may run on a reduced grid (128 of 148 CTAs: the frame time is flat down to there) so that other work — the
+ * codec decode of the previous streaming chunk — runs beside it on the free SMs.  fq3_reduced_grid: that grid, or 0 when
+ * the engine has none; fq3_set_decode_grid: n_ctas = fq3_num_sms() (or <= 0) for the full grid, = fq3_reduced_grid() for the
+ * reduced one; it applies to the following fq3_decode_frames calls only (prefill, talker step, predictor keep the full grid). */
+int fq3_reduced_grid(const fq3_engine* e);
+int fq3_set_decode_grid(fq3_engine* e, int n_ctas);
 /* Copy status / codes back (synchronises `stream`). codes_out: host int32 [n, 16]. */
 int fq3_get_status(fq3_engine* e, int stream_idx, fq3_status* out, void* stream);
 int fq3_read_codes(fq3_engine* e, int stream_idx, int first_frame, int n, int32_t* codes_out, void* stream);

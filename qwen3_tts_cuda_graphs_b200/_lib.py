@@ -69,6 +69,8 @@ SYMBOLS = {
     "fq3_sample": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.POINTER(Policy), C.c_int, C.c_int, C.c_int, C.c_uint64, _P, _P]),
     "fq3_apply_repetition_penalty": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_float, C.c_int, _P]),
     "fq3_decode_frames": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Policy), C.POINTER(SubPolicy), _P]),
+    "fq3_reduced_grid": (C.c_int, [_P]),
+    "fq3_set_decode_grid": (C.c_int, [_P, C.c_int]),
     "fq3_get_status": (C.c_int, [_P, C.c_int, C.POINTER(Status), _P]),
     "fq3_read_codes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _P]),
     "fq3_last_hidden": (C.c_int, [_P, C.c_int, _P, _P]),

@@ -64,6 +64,9 @@ struct fq3_engine {
   int64_t launches = 0;
   long long* prof = nullptr;
   std::vector<Plan> plans;                 // GEMV partitions, one per distinct (N, K, SwiGLU)
+  std::vector<Plan> plans_alt;             // the same partitions for the reduced grid G_alt (fq3_set_decode_grid)
+  int G_alt = 0;                           // 0 = none
+  int G_frames = 0;                        // grid fq3_decode_frames launches with (G or G_alt)
   std::vector<std::array<int, 3>> plan_keys;
   long ring_cap = 0;      // optional cap on the weight ring (FQ3_RING_KB), 0 = all remaining shared memory
   int prof_cta = -1;
@@ -110,6 +113,11 @@ int plan_for(fq3_engine* e, int N, int K, bool swiglu) {
   Plan pl{};
   if (!make_plan(e->G, N, K, swiglu, &pl) || (int)e->plans.size() >= kMaxPlans - 1) return -1;
   e->plans.push_back(pl);
+  if (e->G_alt > 0) {
+    Plan pa{};
+    if (make_plan(e->G_alt, N, K, swiglu, &pa)) e->plans_alt.push_back(pa);
+    else e->G_alt = 0;  // a shape the reduced grid cannot partition: the reduced grid is not offered
+  }
   e->plan_keys.push_back(key);
   return (int)e->plans.size() - 1;
 }
@@ -239,7 +247,8 @@ int check_device_fault(fq3_engine* e) {
 
 // Launch the persistent kernel: one CTA per SM, cooperative (all CTAs must be co-resident: they poll each other's words).
 // smem: header | scratch | activation staging buffer (xrows x kmax bf16) | weight ring (16 KB stages, everything that is left).
-int launch(fq3_engine* e, LaunchParams& p, size_t x_elems, size_t gamma_elems, cudaStream_t s) {
+int launch(fq3_engine* e, LaunchParams& p, size_t x_elems, size_t gamma_elems, cudaStream_t s, int grid = 0) {
+  if (grid <= 0) grid = e->G;
   if (int r = check_device_fault(e)) return r;
   p.xbuf_bytes = (int)round_up(x_elems * 2, 1024);
   p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 1024);
@@ -267,7 +276,7 @@ int launch(fq3_engine* e, LaunchParams& p, size_t x_elems, size_t gamma_elems, c
   p.epoch_base = e->epoch;
   e->epoch += (uint32_t)span;
   void* args[] = {&p};
-  CK(cudaLaunchCooperativeKernel(p.prof ? (void*)fq3_stream_kernel<true> : (void*)fq3_stream_kernel<false>, dim3(e->G), dim3(kThreads), args, smem, s));
+  CK(cudaLaunchCooperativeKernel(p.prof ? (void*)fq3_stream_kernel<true> : (void*)fq3_stream_kernel<false>, dim3(grid), dim3(kThreads), args, smem, s));
   e->launches += 1;
   return 0;
 }
@@ -350,6 +359,10 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   if (!coop) return fail(FQ3_E_UNSUPPORTED, "device lacks cooperative launch");
   e->G = sms;
   if (const char* g = getenv("FQ3_GRID")) e->G = std::max(1, std::min(sms, atoi(g)));
+  // a second, smaller grid for the frame loop (fq3_set_decode_grid): leaves SMs free for the codec of the previous chunk
+  e->G_alt = e->G > 128 ? 128 : 0;
+  if (const char* g = getenv("FQ3_GRID_ALT")) e->G_alt = std::max(0, std::min(e->G - 1, atoi(g)));
+  e->G_frames = e->G;
   if (const char* rk = getenv("FQ3_RING_KB")) e->ring_cap = std::max(16L, atol(rk)) * 1024L;
   if (const char* pc = getenv("FQ3_PROF")) {
     e->prof_cta = atoi(pc);
@@ -734,8 +747,21 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
   p.n_iters = n_frames;
   p.pol = to_policy(policy);
   p.sub = to_sub(sub);
-  return launch(e, p, decode_x_elems(e, n_streams, true, true), std::max(e->tk.d.hidden, e->pr.d.hidden), (cudaStream_t)stream);
+  int grid = e->G;
+  if (e->G_frames == e->G_alt && e->G_alt > 0 && e->plans_alt.size() == e->plans.size()) {
+    grid = e->G_alt;
+    for (size_t i = 0; i < e->plans_alt.size(); ++i) p.plans[i] = e->plans_alt[i];
+  }
+  return launch(e, p, decode_x_elems(e, n_streams, true, true), std::max(e->tk.d.hidden, e->pr.d.hidden), (cudaStream_t)stream, grid);
 }
+
+int fq3_set_decode_grid(fq3_engine* e, int n_ctas) {
+  if (!e) return fail(FQ3_E_INVALID, "null engine");
+  if (n_ctas <= 0 || n_ctas == e->G) { e->G_frames = e->G; return 0; }
+  if (n_ctas == e->G_alt && e->G_alt > 0 && e->plans_alt.size() == e->plans.size()) { e->G_frames = e->G_alt; return 0; }
+  return fail(FQ3_E_UNSUPPORTED, "decode grid must be the full grid or the engine's reduced grid");
+}
+int fq3_reduced_grid(const fq3_engine* e) { return (e && e->plans_alt.size() == e->plans.size()) ? e->G_alt : 0; }
 
 int fq3_get_status(fq3_engine* e, int idx, fq3_status* out, void* stream) {
   if (int r = check_stream(e, idx)) return r;

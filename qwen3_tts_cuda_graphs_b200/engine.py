@@ -117,6 +117,14 @@ class Engine:
         except Exception:
             pass
 
+    def reduced_grid(self) -> int:
+        """CTAs of the engine's reduced frame-loop grid (0 = none): see include/fq3.h, fq3_set_decode_grid."""
+        return int(self.lib.fq3_reduced_grid(self.h))
+
+    def set_decode_grid(self, n_ctas: int = 0) -> None:
+        """Grid of the following decode_frames launches: 0 / num_sms = full, reduced_grid() = leave SMs free for the codec."""
+        _lib.check(self.lib.fq3_set_decode_grid(self.h, int(n_ctas)))
+
     # ---- helpers ----
     def _bf16(self, x: torch.Tensor) -> torch.Tensor:
         x = x.to(device=self.device, dtype=torch.bfloat16).contiguous()

@@ -53,11 +53,15 @@ def fast_generate_streaming(
         t_prefill = time.time() - t0
         budget = min(max_new_tokens, eng.max_frames)
         emitted, chunk_idx = 0, 0
-        # FQ3_OVERLAP_CODEC=1 (with FQ3_GRID=128 so that the decode kernel leaves SMs free): from the second chunk on, the next
-        # chunk is launched BEFORE the current one is yielded, so the caller's codec decode (on a side stream, model.py) runs
-        # beside it.  The first chunk keeps the plain order: time to first audio must not wait behind a speculative launch.
-        overlap = os.environ.get("FQ3_OVERLAP_CODEC", "0") == "1"
+        # Overlapped streaming (FQ3_OVERLAP_CODEC=0 turns it off): from the second chunk on, the frame loop runs on the engine's
+        # reduced grid (128 of 148 CTAs: the frame time is flat down to there) and the next chunk is launched BEFORE the current
+        # one is yielded, so the caller's codec decode (on a side stream, model.py) runs beside it on the free SMs.  The first
+        # chunk keeps the full grid and the plain order: time to first audio must not wait behind a speculative launch.
+        reduced = eng.reduced_grid() if hasattr(eng, "reduced_grid") else 0
+        overlap = os.environ.get("FQ3_OVERLAP_CODEC", "1") != "0" and reduced > 0
         in_flight = 0  # frames of a chunk that is already running
+        if reduced > 0:
+            eng.set_decode_grid(0)  # first chunk (and a stream left behind by an aborted generator): full grid
 
         def launch(n):
             if launch_events is not None:  # bench.py: CUDA-event bracket of the persistent-kernel launch alone
@@ -85,6 +89,7 @@ def fast_generate_streaming(
                 }
                 chunk_idx += 1
                 if overlap and chunk_idx >= 2 and n_new == chunk_size and not st.done and emitted < budget:
+                    eng.set_decode_grid(reduced)
                     ready = torch.cuda.Event()
                     ready.record()                       # the codes of this chunk are complete here ...
                     info["codes_ready"] = ready          # ... the side stream waits for this, not for the next chunk
@@ -96,11 +101,15 @@ def fast_generate_streaming(
                 except GeneratorExit:
                     if in_flight:
                         eng.status(idx)                  # the consumer left: let the speculative chunk finish
+                    if overlap:
+                        eng.set_decode_grid(0)
                     raise
                 if n_new < chunk_size:
                     break
             if st.done or n_new == 0:
                 break
+        if overlap:
+            eng.set_decode_grid(0)                       # other callers of the engine get the full grid back
         return
 
     tinfo: dict = {}
