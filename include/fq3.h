@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define FQ3_ABI_VERSION 1
+#define FQ3_ABI_VERSION 2
 #define FQ3_MAX_CODE_GROUPS 32
 
 typedef struct fq3_engine fq3_engine; /* opaque */
@@ -95,6 +95,7 @@ const char* fq3_last_error(void);
  * programs.  Nothing is captured lazily; the first call after create is already the steady state. */
 int fq3_create(const fq3_model_desc* desc, fq3_engine** out);
 int fq3_destroy(fq3_engine* e);
+/* CTAs of the engine's persistent grid (one per SM; 128 by default, env FQ3_GRID overrides at create time) */
 int fq3_num_sms(const fq3_engine* e);
 /* number of kernel launches issued by this engine since creation (bench.py "gpu_launches") */
 int64_t fq3_launch_count(const fq3_engine* e);
@@ -158,12 +159,18 @@ int fq3_apply_repetition_penalty(fq3_engine* e, void* logits_f32, int V, const v
 int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_policy* policy,
                       const fq3_subpolicy* sub, void* stream);
 
-/* The frame loop may run on a reduced grid (128 of 148 CTAs: the frame time is flat down to there) so that other work — the
- * codec decode of the previous streaming chunk — runs beside it on the free SMs.  fq3_reduced_grid: that grid, or 0 when
- * the engine has none; fq3_set_decode_grid: n_ctas = fq3_num_sms() (or <= 0) for the full grid, = fq3_reduced_grid() for the
- * reduced one; it applies to the following fq3_decode_frames calls only (prefill, talker step, predictor keep the full grid). */
+/* The engine's grid may be smaller than the device (128 of 148 SMs by default: every model shape partitions evenly over
+ * 128 CTAs) so that other work — the codec decode of the previous streaming chunk — runs beside the frame loop on the
+ * free SMs.  fq3_reduced_grid: that grid when SMs are left free, else 0.  fq3_set_decode_grid is kept for callers of ABI 1:
+ * it accepts 0, the engine's grid or the device's SM count and changes nothing (the grid is fixed at fq3_create because
+ * the weight images are tiled for it). */
 int fq3_reduced_grid(const fq3_engine* e);
 int fq3_set_decode_grid(fq3_engine* e, int n_ctas);
+/* The device watchdog turns a protocol fault into FQ3_E_DEVICE_FAULT on every later call.  fq3_clear_fault drains the
+ * stream, clears the flag and forgets all exchange epochs; streams must be prefilled again afterwards. */
+int fq3_clear_fault(fq3_engine* e, void* stream);
+/* Test hook: set the 32-bit exchange-epoch counter (the wrap-around path is otherwise hours of serving away). */
+int fq3_debug_set_epoch(fq3_engine* e, uint32_t epoch);
 /* Copy status / codes back (synchronises `stream`). codes_out: host int32 [n, 16]. */
 int fq3_get_status(fq3_engine* e, int stream_idx, fq3_status* out, void* stream);
 int fq3_read_codes(fq3_engine* e, int stream_idx, int first_frame, int n, int32_t* codes_out, void* stream);
@@ -177,7 +184,8 @@ void* fq3_codes_device_ptr(fq3_engine* e, int stream_idx);
 int fq3_debug_read_prof(fq3_engine* e, long long* out, int n_words);
 
 /* ---- building block exposed for parity tests ------------------------------------------------ */
-/* y[M,N] = epilogue(W[N,K] · prologue(x[M,K])) through the same persistent streaming kernel.
+/* y[M,N] = epilogue(W[N,K] · prologue(x[M,K])) through the same persistent streaming kernel (W row-major, any device
+ * address: its tiled image is built on the fly).
  * flags: bit0 pre-RMSNorm with gamma, bit1 bias, bit2 residual add, bit3 SwiGLU pairing (N = 2*I
  * interleaved rows, output width N/2), bit4 fp32 output, bit5 SiLU after bias.  All pointers device; W inside or outside
  * the arena. */

@@ -47,6 +47,8 @@ class Status(C.Structure):
     ]
 
 
+ABI_VERSION = 2  # FQ3_ABI_VERSION of include/fq3.h
+
 # every symbol include/fq3.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -71,6 +73,8 @@ SYMBOLS = {
     "fq3_decode_frames": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Policy), C.POINTER(SubPolicy), _P]),
     "fq3_reduced_grid": (C.c_int, [_P]),
     "fq3_set_decode_grid": (C.c_int, [_P, C.c_int]),
+    "fq3_clear_fault": (C.c_int, [_P, _P]),
+    "fq3_debug_set_epoch": (C.c_int, [_P, C.c_uint32]),
     "fq3_get_status": (C.c_int, [_P, C.c_int, C.POINTER(Status), _P]),
     "fq3_read_codes": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), _P]),
     "fq3_last_hidden": (C.c_int, [_P, C.c_int, _P, _P]),
@@ -106,7 +110,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.fq3_abi_version() != 1:
+    if lib.fq3_abi_version() != ABI_VERSION:
         raise Fq3Error("libfq3.so ABI version mismatch")
     _lib = lib
     return lib

@@ -60,13 +60,18 @@ struct fq3_engine {
   float* pred_logits_all = nullptr;
   uint8_t* seen_scratch = nullptr;
   Phase *d_frames = nullptr, *d_pred = nullptr, *d_talker = nullptr, *d_prefill = nullptr, *d_linear = nullptr;
+  std::vector<Phase> h_frames, h_pred, h_talker, h_prefill;  // host copies (shared-memory sizing)
   int n_frames_ph = 0, n_pred_ph = 0, n_talker_ph = 0, n_prefill_ph = 0;
+  uint8_t* tiled = nullptr;               // tiled images of every GEMV matrix (fq3_common.cuh: Plan); Phase::w_off indexes it
+  size_t tiled_bytes = 0;
+  std::vector<std::pair<uint64_t, uint64_t>> tiled_map;  // arena byte offset -> image byte offset
+  uint8_t* lin_img = nullptr;             // scratch image of fq3_linear's matrix
+  size_t lin_img_bytes = 0;
+  size_t tiled_used = 0;
   int64_t launches = 0;
   long long* prof = nullptr;
   std::vector<Plan> plans;                 // GEMV partitions, one per distinct (N, K, SwiGLU)
-  std::vector<Plan> plans_alt;             // the same partitions for the reduced grid G_alt (fq3_set_decode_grid)
-  int G_alt = 0;                           // 0 = none
-  int G_frames = 0;                        // grid fq3_decode_frames launches with (G or G_alt)
+  int n_sms = 0;                           // SMs of the device (G <= n_sms: the rest stays free for the codec)
   std::vector<std::array<int, 3>> plan_keys;
   long ring_cap = 0;      // optional cap on the weight ring (FQ3_RING_KB), 0 = all remaining shared memory
   int prof_cta = -1;
@@ -90,19 +95,24 @@ int dalloc(fq3_engine* e, T** p, size_t n, bool zero = true) {
 
 uint32_t off16(uint64_t byte_off) { return (uint32_t)(byte_off >> 4); }
 
-// Partition of one GEMV shape over the grid (fq3_common.cuh: Plan): super-units = packed output words.
+// Partition of one GEMV shape over the grid (fq3_common.cuh: Plan): 8-row groups per CTA, K-splits that fill the 128
+// virtual rows of an MMA tile.
 bool make_plan(int G, int N, int K, bool swiglu, Plan* out) {
-  if (N < 2 || (N & 1) || K < 64 || (K & 63)) return false;
+  if (N < 2 || (N & 1) || K < kBlockK || (K % kBlockK)) return false;
   if (swiglu && (N & 3)) return false;
   Plan pl{};
-  pl.ro = swiglu ? 4 : 2;
-  const int n_su = N / pl.ro;
-  pl.su_base = n_su / G;
-  pl.su_rem = n_su - pl.su_base * G;
-  pl.nkq = (K + kStageCols - 1) / kStageCols;
-  pl.tpb = std::max(1, kBatchStages / pl.nkq);
+  pl.ro_shift = swiglu ? 2 : 1;
+  const int n_groups = (N + 7) / 8;
+  pl.g_base = n_groups / G;
+  pl.g_rem = n_groups - pl.g_base * G;
+  const int g_max = pl.g_base + (pl.g_rem ? 1 : 0);
+  const int kblocks = K / kBlockK;
+  int s_log = 0;
+  while (s_log < kMaxSplitLog && (g_max << (s_log + 1)) <= 16 && (kblocks % (2 << s_log)) == 0) ++s_log;
+  pl.s_log = s_log;
+  pl.kbs = kblocks >> s_log;
+  pl.tile_groups = 16 >> s_log;
   pl.inv_k = 1.0f / (float)K;
-  if (pl.nkq > kBatchStages) return false;
   *out = pl;
   return true;
 }
@@ -113,11 +123,6 @@ int plan_for(fq3_engine* e, int N, int K, bool swiglu) {
   Plan pl{};
   if (!make_plan(e->G, N, K, swiglu, &pl) || (int)e->plans.size() >= kMaxPlans - 1) return -1;
   e->plans.push_back(pl);
-  if (e->G_alt > 0) {
-    Plan pa{};
-    if (make_plan(e->G_alt, N, K, swiglu, &pa)) e->plans_alt.push_back(pa);
-    else e->G_alt = 0;  // a shape the reduced grid cannot partition: the reduced grid is not offered
-  }
   e->plan_keys.push_back(key);
   return (int)e->plans.size() - 1;
 }
@@ -200,7 +205,30 @@ void push_talker(std::vector<Phase>& v, fq3_engine* e, bool last_row_head) {
   v.push_back(h);
 }
 
-int upload(fq3_engine* e, const std::vector<Phase>& v, Phase** d) {
+// Point every GEMV phase of a program at the tiled image of its matrix (built on first use), then upload the program.
+int upload(fq3_engine* e, std::vector<Phase>& v, Phase** d) {
+  const uint8_t* arena = reinterpret_cast<const uint8_t*>(e->desc.arena);
+  for (Phase& ph : v) {
+    if (ph.type != PH_GEMV) continue;
+    if (ph.N % 8) return -1;  // model matrices: whole 8-row groups (the image has the size of the matrix)
+    const uint64_t aoff = (uint64_t)ph.w_off * 16;
+    uint64_t ioff = ~0ull;
+    for (auto& m : e->tiled_map)
+      if (m.first == aoff) ioff = m.second;
+    if (ioff == ~0ull) {
+      size_t used = 0;
+      if (!e->tiled_map.empty()) used = e->tiled_used;
+      ioff = used;
+      const size_t bytes = (size_t)ph.N * ph.K * 2;
+      if (ioff + bytes > e->tiled_bytes) return -1;
+      fq3_tile_weights_kernel<<<e->G, 256>>>(reinterpret_cast<const bf16*>(arena + aoff), reinterpret_cast<uint4*>(e->tiled + ioff), (int)ph.N,
+                                            (int)ph.K, e->plans[ph.plan]);
+      if (cudaGetLastError() != cudaSuccess) return -1;
+      e->tiled_map.push_back({aoff, ioff});
+      e->tiled_used = (ioff + bytes + 1023) / 1024 * 1024;
+    }
+    ph.w_off = off16(ioff);
+  }
   if (dalloc(e, d, v.size(), false)) return -1;
   if (cudaMemcpy(*d, v.data(), v.size() * sizeof(Phase), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
   return 0;
@@ -208,6 +236,7 @@ int upload(fq3_engine* e, const std::vector<Phase>& v, Phase** d) {
 
 void fill_common(fq3_engine* e, LaunchParams& p) {
   p.arena = reinterpret_cast<const uint8_t*>(e->desc.arena);
+  p.tiled = e->tiled;
   for (int i = 0; i < kNumBufs; ++i) { p.bufs[i] = e->bufs[i]; p.ld[i] = e->ld[i]; }
   p.stacks[0] = e->rt[0];
   p.stacks[1] = e->rt[1];
@@ -228,8 +257,6 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   p.prof = e->prof;
   p.prof_cta = e->prof_cta;
   if (const char* d = getenv("FQ3_DEBUG")) p.debug = atoi(d);
-  p.ll_mode = 0;
-  if (const char* d = getenv("FQ3_LLMODE")) p.ll_mode = atoi(d);
   p.n_iters = 1;
   p.stream0 = 0;
 }
@@ -245,34 +272,59 @@ int check_device_fault(fq3_engine* e) {
   return 0;
 }
 
-// Launch the persistent kernel: one CTA per SM, cooperative (all CTAs must be co-resident: they poll each other's words).
-// smem: header | scratch | activation staging buffer (xrows x kmax bf16) | weight ring (16 KB stages, everything that is left).
-int launch(fq3_engine* e, LaunchParams& p, size_t x_elems, size_t gamma_elems, cudaStream_t s, int grid = 0) {
-  if (grid <= 0) grid = e->G;
+// rows of the B operand a GEMV phase stages (kernel: phase_m / b_rows)
+int phase_rows_host(const Phase& ph, int n_rows) {
+  if (ph.flags & F_LAST_ROW) return 1;
+  return (ph.flags & F_ROWS2) ? 2 * n_rows : n_rows;
+}
+
+// Every API entry that launches the persistent kernel reserves its LL epochs first — before it stages any input.  Phase i
+// of iteration `it` of a launch carries epoch_base + it * n_phases + i + 1; the 32-bit counter wraps after ~4e9 phases
+// (hours of serving).  On a wrap the epoch halves of all LL words are reset to 0 ("written before the launch") and the
+// payloads are kept, so the state that crosses launches (predictor input rows, frame control records) survives.
+int reserve_epochs(fq3_engine* e, uint64_t span, cudaStream_t s) {
   if (int r = check_device_fault(e)) return r;
-  p.xbuf_bytes = (int)round_up(x_elems * 2, 1024);
-  p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 1024);
-  p.gam_bytes = (int)round_up(gamma_elems * 2, 1024);
-  // Shared memory and L1 share 256 KB per SM: staying at or below the 196 KB carve-out leaves 60 KB of L1, which the
-  // kernel's register spills and table reads need (measured: 28 KB of L1 costs 20 % of the step time).
-  const long budget = e->ring_cap > 0 ? (long)e->smem_max : std::min<long>((long)e->smem_max, 196L * 1024);
-  long avail = budget - kHeaderBytes - kScratchBytes - (long)p.xbuf_bytes - (long)p.prog_bytes - (long)kGammaSlots * p.gam_bytes;
-  if (avail < 6L * kStageBytes) avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - (long)p.xbuf_bytes - (long)p.prog_bytes - (long)kGammaSlots * p.gam_bytes;
-  if (e->ring_cap > 0) avail = std::min(avail, e->ring_cap);
-  p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
-  if (p.n_stages < 4) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
-  const size_t smem = kHeaderBytes + kScratchBytes + (size_t)p.prog_bytes + (size_t)kGammaSlots * p.gam_bytes + (size_t)p.xbuf_bytes +
-                      (size_t)p.n_stages * kStageBytes;
-  // LL epochs: phase i of iteration it carries epoch_base + it*n_phases + i + 1
-  const uint64_t span = (uint64_t)p.n_iters * (uint64_t)p.n_phases + 2;
   if ((uint64_t)e->epoch + span >= 0xFFFFFF00ull) {
-    // wrap: drain, clear every LL buffer so stale epochs cannot alias, restart the counter
-    CK(cudaStreamSynchronize(s));
     for (int i = 0; i < kNumBufs; ++i)
-      if (e->buf_bytes[i]) CK(cudaMemsetAsync(e->bufs[i], 0, e->buf_bytes[i], s));
-    CK(cudaMemsetAsync(e->attn_part, 0, e->attn_part_bytes, s));
+      if (e->buf_bytes[i]) fq3_ll_clear_epochs_kernel<<<64, 256, 0, s>>>(reinterpret_cast<LLWord*>(e->bufs[i]), e->buf_bytes[i] / sizeof(LLWord));
+    fq3_ll_clear_epochs_kernel<<<64, 256, 0, s>>>(e->attn_part, e->attn_part_bytes / sizeof(LLWord));
+    fq3_ctl_clear_epochs_kernel<<<1, 64, 0, s>>>(e->d_st, e->desc.max_streams);
+    e->launches += 2;
+    CK(cudaGetLastError());
     e->epoch = 1;
   }
+  return 0;
+}
+
+// Launch the persistent kernel: one CTA per SM, cooperative (all CTAs must be co-resident: they poll each other's words).
+// smem: header | scratch | program | norm-weight slots | B operand | weight ring (16 KB stages, everything that is left).
+int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t s) {
+  const int grid = e->G;
+  size_t bbytes = 0, gamma_elems = 0;
+  for (int i = 0; i < p.n_phases; ++i) {
+    const Phase& ph = prog_host[i];
+    if (ph.type != PH_GEMV) continue;
+    const Plan& pl = (ph.flags & F_ABSPTR) ? p.plans[ph.plan] : e->plans[ph.plan];
+    const int M = phase_rows_host(ph, p.n_rows);
+    if (M > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "more activation rows than the GEMV stage takes");
+    bbytes = std::max(bbytes, (size_t)pl.kbs * (size_t)((((size_t)M << pl.s_log) + 15) / 16 * 16) * 128);
+    if (ph.flags & F_PRENORM) gamma_elems = std::max(gamma_elems, (size_t)ph.K);
+  }
+  p.bbuf_bytes = (int)round_up(bbytes, 1024);
+  p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 1024);
+  p.gam_bytes = (int)round_up(gamma_elems * 2, 1024);
+  // Shared memory and L1 share 256 KB per SM: staying at or below the 196 KB carve-out leaves 60 KB of L1 for the table
+  // reads of the attention and sampling phases.
+  const long fixed = kHeaderBytes + kScratchBytes + (long)p.bbuf_bytes + (long)p.prog_bytes + (long)kGammaSlots * p.gam_bytes;
+  const long budget = e->ring_cap > 0 ? (long)e->smem_max : std::min<long>((long)e->smem_max, 196L * 1024);
+  long avail = budget - fixed;
+  if (avail < 6L * kStageBytes) avail = (long)e->smem_max - fixed;
+  if (e->ring_cap > 0) avail = std::min(avail, e->ring_cap);
+  p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
+  if (p.n_stages < 2) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
+  const size_t smem = (size_t)fixed + (size_t)p.n_stages * kStageBytes;
+  const uint64_t span = (uint64_t)p.n_iters * (uint64_t)p.n_phases + 2;
+  if ((uint64_t)e->epoch + span >= 0xFFFFFFF0ull) return fail(FQ3_E_INVALID, "LL epochs were not reserved for this launch");
   p.epoch_base = e->epoch;
   e->epoch += (uint32_t)span;
   void* args[] = {&p};
@@ -340,8 +392,24 @@ extern "C" {
 int fq3_abi_version(void) { return FQ3_ABI_VERSION; }
 const char* fq3_last_error(void) { return g_err.c_str(); }
 
+static int create_impl(const fq3_model_desc* desc, fq3_engine* e);
+
 int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   if (!desc || !out) return fail(FQ3_E_INVALID, "null argument");
+  *out = nullptr;
+  fq3_engine* e = new fq3_engine();
+  const int r = create_impl(desc, e);
+  if (r) {  // every early return of create_impl lands here: nothing leaks
+    const std::string msg = g_err;
+    fq3_destroy(e);
+    g_err = msg;
+    return r;
+  }
+  *out = e;
+  return 0;
+}
+
+static int create_impl(const fq3_model_desc* desc, fq3_engine* e) {
   if (desc->abi_version != FQ3_ABI_VERSION) return fail(FQ3_E_INVALID, "ABI version mismatch");
   if (int r = check_stack(desc->talker, "talker")) return r;
   if (int r = check_stack(desc->predictor, "predictor")) return r;
@@ -349,7 +417,6 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   if (desc->max_streams < 1) return fail(FQ3_E_INVALID, "max_streams");
   if (!desc->has_s2m && desc->talker.hidden != desc->predictor.hidden)
     return fail(FQ3_E_INVALID, "talker/predictor widths differ but no small_to_mtp projection given");
-  fq3_engine* e = new fq3_engine();
   e->desc = *desc;
   CK(cudaGetDevice(&e->dev));
   int sms = 0, smem_optin = 0, coop = 0;
@@ -357,12 +424,12 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
   CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->dev));
   CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->dev));
   if (!coop) return fail(FQ3_E_UNSUPPORTED, "device lacks cooperative launch");
-  e->G = sms;
+  // 128 CTAs: the partitions of every model shape come out even (whole 8-row groups per CTA, the K-splits fill the 128
+  // rows of an MMA tile), the exchange has fewer parties, and the remaining SMs stay free for the codec decode of the
+  // previous streaming chunk.  FQ3_GRID overrides.
+  e->n_sms = sms;
+  e->G = std::min(sms, 128);
   if (const char* g = getenv("FQ3_GRID")) e->G = std::max(1, std::min(sms, atoi(g)));
-  // a second, smaller grid for the frame loop (fq3_set_decode_grid): leaves SMs free for the codec of the previous chunk
-  e->G_alt = e->G > 128 ? 128 : 0;
-  if (const char* g = getenv("FQ3_GRID_ALT")) e->G_alt = std::max(0, std::min(e->G - 1, atoi(g)));
-  e->G_frames = e->G;
   if (const char* rk = getenv("FQ3_RING_KB")) e->ring_cap = std::max(16L, atol(rk)) * 1024L;
   if (const char* pc = getenv("FQ3_PROF")) {
     e->prof_cta = atoi(pc);
@@ -453,8 +520,15 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
     s.pad_embed = pe;
   }
   CK(cudaMemcpy(e->d_st, e->h_st.data(), sizeof(StreamState) * B, cudaMemcpyHostToDevice));
-  // --- programs ---
-  std::vector<Phase> v;
+  // --- programs + tiled weight images ---
+  auto gemv_bytes = [&](const StackHost& sh) {
+    return (size_t)sh.d.n_layers * ((size_t)sh.qkvdim() * sh.d.hidden + (size_t)sh.d.hidden * sh.qdim() + 3ull * sh.d.hidden * sh.d.inter) * 2;
+  };
+  e->tiled_bytes = gemv_bytes(e->tk) + gemv_bytes(e->pr) + (size_t)e->tk.d.vocab * e->tk.d.hidden * 2 +
+                   (size_t)e->ncb * e->pr.d.vocab * e->pr.d.hidden * 2 + (desc->has_s2m ? (size_t)e->pr.d.hidden * e->tk.d.hidden * 2 : 0) +
+                   1024 * (size_t)(8 * (e->tk.d.n_layers + e->pr.d.n_layers) + e->ncb + 8);
+  if (dalloc(e, &e->tiled, e->tiled_bytes, false)) return -FQ3_E_CUDA;
+  std::vector<Phase>& v = e->h_frames;
   push_predictor(v, e, false);
   push_talker(v, e, false);
   {
@@ -462,42 +536,37 @@ int fq3_create(const fq3_model_desc* desc, fq3_engine** out) {
     s.type = PH_SAMPLE; s.stack = ST_TALKER; s.kind = SMP_TALKER;
     v.push_back(s);
   }
-  e->n_frames_ph = (int)v.size();
-  if (upload(e, v, &e->d_frames)) return fail(FQ3_E_CUDA, "program upload");
-  v.clear();
-  push_predictor(v, e, true);
-  e->n_pred_ph = (int)v.size();
-  if (upload(e, v, &e->d_pred)) return fail(FQ3_E_CUDA, "program upload");
-  v.clear();
-  push_talker(v, e, false);
-  e->n_talker_ph = (int)v.size();
-  if (upload(e, v, &e->d_talker)) return fail(FQ3_E_CUDA, "program upload");
-  v.clear();
-  push_talker(v, e, true);
+  push_predictor(e->h_pred, e, true);
+  push_talker(e->h_talker, e, false);
+  push_talker(e->h_prefill, e, true);
   {
     Phase s{};
     s.type = PH_SAMPLE; s.stack = ST_TALKER; s.kind = SMP_PREFILL;
-    v.push_back(s);
+    e->h_prefill.push_back(s);
   }
-  e->n_prefill_ph = (int)v.size();
-  if (upload(e, v, &e->d_prefill)) return fail(FQ3_E_CUDA, "program upload");
-  if (dalloc(e, &e->d_linear, 1)) return -FQ3_E_CUDA;
   if (g_plan_fail) { g_plan_fail = false; return fail(FQ3_E_UNSUPPORTED, "a GEMV shape of this model cannot be partitioned (odd N or K % 64)"); }
+  e->n_frames_ph = (int)e->h_frames.size();
+  e->n_pred_ph = (int)e->h_pred.size();
+  e->n_talker_ph = (int)e->h_talker.size();
+  e->n_prefill_ph = (int)e->h_prefill.size();
+  if (upload(e, e->h_frames, &e->d_frames) || upload(e, e->h_pred, &e->d_pred) || upload(e, e->h_talker, &e->d_talker) ||
+      upload(e, e->h_prefill, &e->d_prefill))
+    return fail(FQ3_E_CUDA, "program upload / weight tiling (matrix rows must be a multiple of 8)");
+  if (dalloc(e, &e->d_linear, 1)) return -FQ3_E_CUDA;
   CK(cudaDeviceSynchronize());
-  *out = e;
   return 0;
 }
 
 int fq3_destroy(fq3_engine* e) {
   if (!e) return 0;
   cudaDeviceSynchronize();
-  for (void* p : e->owned) cudaFree(p);
+  for (void* p : e->owned) if (p) cudaFree(p);
   if (e->err_host) cudaFreeHost(e->err_host);
   delete e;
   return 0;
 }
 
-int fq3_num_sms(const fq3_engine* e) { return e ? e->G : 0; }
+int fq3_num_sms(const fq3_engine* e) { return e ? e->G : 0; }  /* CTAs of the engine's grid */
 int64_t fq3_launch_count(const fq3_engine* e) { return e ? e->launches : 0; }
 
 static int check_stream(fq3_engine* e, int idx) {
@@ -576,21 +645,7 @@ int fq3_set_loop_state(fq3_engine* e, int idx, int token, const void* past_hidde
   return 0;
 }
 
-static int prefill_rows(const fq3_engine* e) {
-  // rows per pass are bounded by the activation staging buffer: keep a ring of >= 6 stages
-  const long avail = (long)e->smem_max - kHeaderBytes - kScratchBytes - (long)round_up((size_t)e->n_prefill_ph * sizeof(Phase), 1024) -
-                     (long)kGammaSlots * (long)round_up((size_t)e->tk.d.hidden * 2, 1024) - 6L * kStageBytes;
-  const long rows = avail / ((long)e->tk.kmax() * 2);
-  return (int)std::max<long>(1, std::min<long>(rows, kMaxRows));
-}
-
-// activation staging elements of the decode programs: predictor pass 0 stages two rows per stream
-static size_t decode_x_elems(const fq3_engine* e, int n_streams, bool talker, bool predictor) {
-  size_t n = 0;
-  if (talker) n = std::max(n, (size_t)n_streams * e->tk.kmax());
-  if (predictor) n = std::max(n, (size_t)2 * n_streams * std::max(e->pr.kmax(), e->desc.has_s2m ? e->tk.d.hidden : 0));
-  return n;
-}
+static int prefill_rows(const fq3_engine* e) { return kMaxRows; }
 
 // rows [start, T) of the prompt go through the persistent kernel; the K/V rows of [0, start) must already be in the cache
 static int prefill_impl(fq3_engine* e, int idx, const void* embeds_from_start, int T, int start, int n_left_pad, const fq3_policy* policy,
@@ -606,6 +661,7 @@ static int prefill_impl(fq3_engine* e, int idx, const void* embeds_from_start, i
   cudaStream_t s = (cudaStream_t)stream;
   const int Ht = e->tk.d.hidden;
   const int Mmax = prefill_rows(e);
+  if (int r = reserve_epochs(e, (uint64_t)((T - start + Mmax - 1) / Mmax) * (uint64_t)(e->n_prefill_ph + 2), s)) return r;
   fq3_reset_stream_kernel<<<1, 256, 0, s>>>(e->d_st + idx, e->tk.d.vocab);
   fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, 0, 0, 2, n_left_pad, -n_left_pad, 0);
   e->launches += 2;
@@ -622,7 +678,7 @@ static int prefill_impl(fq3_engine* e, int idx, const void* embeds_from_start, i
     p.stream0 = idx;
     p.pf_pos0 = c0; p.pf_n_pad = n_left_pad; p.pf_rope_delta = -n_left_pad; p.pf_final = final;
     p.pol = to_policy(policy);
-    if (int r = launch(e, p, (size_t)rows * e->tk.kmax(), e->tk.d.hidden, s)) return r;
+    if (int r = launch(e, p, e->h_prefill.data(), s)) return r;
   }
   fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, T, 0, 8, 0, 0, 0);
   e->launches += 1;
@@ -656,6 +712,7 @@ int fq3_talker_step(fq3_engine* e, int idx, const void* embeds, int position, vo
   if (position < 0 || position >= e->tk.d.max_pos) return fail(FQ3_E_TOO_LONG, "position outside the static KV cache");
   cudaStream_t s = (cudaStream_t)stream;
   const int Ht = e->tk.d.hidden;
+  if (int r = reserve_epochs(e, (uint64_t)e->n_talker_ph + 2, s)) return r;
   if (int r = pack_ll(e, BUF_TX, 0, embeds, Ht, 1, Ht, s)) return r;
   LaunchParams p{};
   fill_common(e, p);
@@ -665,7 +722,7 @@ int fq3_talker_step(fq3_engine* e, int idx, const void* embeds, int position, vo
   p.n_rows = 1;
   p.stream0 = idx;
   p.pos_override = position;
-  if (int r = launch(e, p, decode_x_elems(e, 1, true, false), e->tk.d.hidden, s)) return r;
+  if (int r = launch(e, p, e->h_talker.data(), s)) return r;
   if (out_hidden) CK(cudaMemcpyAsync(out_hidden, e->bufs[BUF_HID], (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
   if (out_logits)
     if (int r = unpack_f32(e, out_logits, e->tk.d.vocab, BUF_LOGITS, 0, 1, e->tk.d.vocab, s)) return r;
@@ -678,6 +735,7 @@ int fq3_predictor_run(fq3_engine* e, int idx, const void* pred_input, const fq3_
   if (!pred_input || !sub || !out_codes_i64) return fail(FQ3_E_INVALID, "bad predictor arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const int Ht = e->tk.d.hidden;
+  if (int r = reserve_epochs(e, (uint64_t)e->n_pred_ph + 2, s)) return r;
   if (int r = pack_ll(e, BUF_PIN, 0, pred_input, Ht, 2, Ht, s)) return r;
   LaunchParams p{};
   fill_common(e, p);
@@ -689,7 +747,7 @@ int fq3_predictor_run(fq3_engine* e, int idx, const void* pred_input, const fq3_
   p.sub = to_sub(sub);
   p.pol.seed = seed;
   p.pred_logits_all = out_logits ? e->pred_logits_all : nullptr;
-  if (int r = launch(e, p, decode_x_elems(e, 1, false, true), e->pr.d.hidden, s)) return r;
+  if (int r = launch(e, p, e->h_pred.data(), s)) return r;
   fq3_codes_to_i64_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(e->d_st + idx) +
                                                                          offsetof(StreamState, cur_codes)),
                                            e->ncb, reinterpret_cast<long long*>(out_codes_i64));
@@ -736,8 +794,9 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
                       void* stream) {
   if (!e || !policy || !sub) return fail(FQ3_E_INVALID, "bad decode arguments");
   if (n_streams < 1 || n_streams > e->desc.max_streams) return fail(FQ3_E_INVALID, "n_streams out of range");
-  if (2 * n_streams > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "batched decode above 4 streams needs the tensor-core path");
+  if (2 * n_streams > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "batched decode above 4 streams is not built");
   if (n_frames <= 0) return 0;
+  if (int r = reserve_epochs(e, (uint64_t)n_frames * (uint64_t)e->n_frames_ph + 2, (cudaStream_t)stream)) return r;
   LaunchParams p{};
   fill_common(e, p);
   p.prog = e->d_frames;
@@ -747,21 +806,36 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
   p.n_iters = n_frames;
   p.pol = to_policy(policy);
   p.sub = to_sub(sub);
-  int grid = e->G;
-  if (e->G_frames == e->G_alt && e->G_alt > 0 && e->plans_alt.size() == e->plans.size()) {
-    grid = e->G_alt;
-    for (size_t i = 0; i < e->plans_alt.size(); ++i) p.plans[i] = e->plans_alt[i];
-  }
-  return launch(e, p, decode_x_elems(e, n_streams, true, true), std::max(e->tk.d.hidden, e->pr.d.hidden), (cudaStream_t)stream, grid);
+  return launch(e, p, e->h_frames.data(), (cudaStream_t)stream);
 }
 
+// The engine runs every launch on one grid of G <= n_sms CTAs.  When G < n_sms the rest of the device is free for other
+// work next to the frame loop (the codec decode of the previous streaming chunk): that is what "reduced grid" reports.
 int fq3_set_decode_grid(fq3_engine* e, int n_ctas) {
   if (!e) return fail(FQ3_E_INVALID, "null engine");
-  if (n_ctas <= 0 || n_ctas == e->G) { e->G_frames = e->G; return 0; }
-  if (n_ctas == e->G_alt && e->G_alt > 0 && e->plans_alt.size() == e->plans.size()) { e->G_frames = e->G_alt; return 0; }
-  return fail(FQ3_E_UNSUPPORTED, "decode grid must be the full grid or the engine's reduced grid");
+  if (n_ctas <= 0 || n_ctas == e->G || n_ctas == e->n_sms) return 0;
+  return fail(FQ3_E_UNSUPPORTED, "the decode grid is fixed at engine creation (FQ3_GRID)");
 }
-int fq3_reduced_grid(const fq3_engine* e) { return (e && e->plans_alt.size() == e->plans.size()) ? e->G_alt : 0; }
+int fq3_reduced_grid(const fq3_engine* e) { return (e && e->G < e->n_sms) ? e->G : 0; }
+
+int fq3_clear_fault(fq3_engine* e, void* stream) {
+  if (!e) return fail(FQ3_E_INVALID, "null engine");
+  cudaStreamSynchronize((cudaStream_t)stream);
+  if (cudaGetLastError() != cudaSuccess) return fail(FQ3_E_CUDA, "the CUDA context is in an error state: rebuild the engine");
+  if (e->err_host) memset(e->err_host, 0, 64);
+  // a faulted launch may have left half-written phases behind: forget every epoch
+  for (int i = 0; i < kNumBufs; ++i)
+    if (e->buf_bytes[i]) CK(cudaMemsetAsync(e->bufs[i], 0, e->buf_bytes[i], (cudaStream_t)stream));
+  CK(cudaMemsetAsync(e->attn_part, 0, e->attn_part_bytes, (cudaStream_t)stream));
+  e->epoch = 1;
+  return 0;
+}
+
+int fq3_debug_set_epoch(fq3_engine* e, uint32_t epoch) {
+  if (!e || epoch == 0) return fail(FQ3_E_INVALID, "bad arguments");
+  e->epoch = epoch;
+  return 0;
+}
 
 int fq3_get_status(fq3_engine* e, int idx, fq3_status* out, void* stream) {
   if (int r = check_stream(e, idx)) return r;
@@ -818,6 +892,23 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
   Plan lin_plan{};
   if (!make_plan(e->G, N, K, (flags & 8) != 0, &lin_plan)) return fail(FQ3_E_UNSUPPORTED, "shape cannot be partitioned");
   cudaStream_t s = (cudaStream_t)stream;
+  if (int r = reserve_epochs(e, 3, s)) return r;
+  // tiled image of this matrix (the model's own matrices are tiled once at fq3_create)
+  const size_t img_bytes = (size_t)((N + 7) / 8 * 8) * K * 2;
+  if (img_bytes > e->lin_img_bytes) {
+    CK(cudaStreamSynchronize(s));
+    if (e->lin_img) {
+      cudaFree(e->lin_img);
+      for (void*& q : e->owned) if (q == e->lin_img) q = nullptr;
+      e->lin_img = nullptr;
+    }
+    e->lin_img_bytes = 0;
+    if (dalloc(e, &e->lin_img, img_bytes, false)) return -FQ3_E_CUDA;
+    e->lin_img_bytes = img_bytes;
+  }
+  fq3_tile_weights_kernel<<<e->G, 256, 0, s>>>(reinterpret_cast<const bf16*>(W), reinterpret_cast<uint4*>(e->lin_img), N, K, lin_plan);
+  e->launches += 1;
+  CK(cudaGetLastError());
   Phase ph{};
   ph.type = PH_GEMV;
   ph.flags = F_ABSPTR | ((flags & 1) ? F_PRENORM : 0) | ((flags & 2) ? F_BIAS : 0) | ((flags & 4) ? F_RESID : 0) |
@@ -838,9 +929,9 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
     if (!residual) return fail(FQ3_E_INVALID, "residual flag without a residual pointer");
     if (int r = pack_ll(e, BUF_LIN_RES, 0, residual, No, M, No, s)) return r;
   }
-  p.lin_W = W; p.lin_gamma = gamma; p.lin_bias = bias; p.lin_eps = eps;
+  p.lin_W = e->lin_img; p.lin_gamma = gamma; p.lin_bias = bias; p.lin_eps = eps;
   p.plans[kMaxPlans - 1] = lin_plan;
-  if (int r = launch(e, p, (size_t)M * K, (flags & 1) ? (size_t)K : 0, s)) return r;
+  if (int r = launch(e, p, &ph, s)) return r;
   if (flags & 16) return unpack_f32(e, y, No, BUF_LIN_OUT, 0, M, No, s);
   return unpack_bf16(e, y, No, BUF_LIN_OUT, 0, M, No, s);
 }

@@ -1,18 +1,19 @@
-// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a), v4.
+// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a), v8: GEMV phases on tcgen05.
 //
 // Replaces the CUDA-graph replays of talker_graph.py:97-107,198-214 and predictor_graph.py:115-167 and
 // the eager per-frame glue of generate.py:149-199 (reference paths under /root/reference/faster_qwen3_tts).
 //
 // Structure of one CTA (one per SM, all co-resident):
-//   warp 16      producer: walks the phase program and streams this CTA's weight rows of every GEMV phase
-//                through a shared-memory ring of 16 KB stages (8 rows x 1024 columns) with cp.async.bulk
-//                (TMA bulk copy).  Weight addresses never depend on activations or sampled ids, so it runs
-//                ahead of the consumers across phases and frames.
-//   warps 0..15  consumers: per phase, poll-read the input activations (LL words), then four warps share a
-//                stage (8 rows x 256 columns each) and multiply it with mma.sync.m16n8k16 (weights are the
-//                B operand, up to 8 activation rows ride in the A operand), drop their partial sums in shared
-//                memory, and after one barrier one thread per output word reduces, applies the epilogue and
-//                publishes.
+//   warp 12      producer: walks the phase program and streams this CTA's tiles of every GEMV phase's weight image
+//                through a shared-memory ring of 16 KB stages with cp.async.bulk (TMA bulk copy), one contiguous
+//                copy per stage.  Weight addresses never depend on activations or sampled ids, so it runs ahead of
+//                the consumers across phases and frames.
+//   warp 13      MMA issuer: per GEMV phase one thread waits for the staged activations, then issues tcgen05.mma
+//                (M = 128 virtual weight rows, N = activation rows x K-splits, accumulator in tensor memory) over
+//                the ring stages and commits them back to the producer.
+//   warps 0..11  consumers: per phase, poll-read the input activations (LL words), normalise and stage them as the
+//                B operand; warps 0-3 read the accumulator with tcgen05.ld, add the K-splits in a fixed order, apply
+//                the epilogue and publish.  Attention and sampling phases run on all twelve.
 // There is no grid barrier: phases are chained by the data itself (payload + epoch in one 8-byte word).
 #pragma once
 #include "fq3_common.cuh"
@@ -137,14 +138,6 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col)
-__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
 // =================================================================================================
 // Shared-memory layout
 // =================================================================================================
@@ -156,7 +149,7 @@ struct Smem {
   unsigned char* scratch;
   Phase* prog;       // copy of the phase program (a global read per phase would sit on the critical path)
   unsigned char* gam;  // [kGammaSlots][gam_bytes] norm weights, streamed by the producer
-  unsigned char* xbuf;
+  unsigned char* bbuf;  // B operand of the current GEMV phase (activations, K-major 128-byte-swizzled k-block tiles)
   unsigned char* ring;
 };
 
@@ -169,8 +162,8 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base, const LaunchPara
   s.scratch = base + kHeaderBytes;
   s.prog = reinterpret_cast<Phase*>(s.scratch + kScratchBytes);
   s.gam = s.scratch + kScratchBytes + p.prog_bytes;
-  s.xbuf = s.gam + kGammaSlots * p.gam_bytes;
-  s.ring = s.xbuf + p.xbuf_bytes;  // header, scratch, program, norm-weight slots and xbuf are 1 KB multiples
+  s.bbuf = s.gam + kGammaSlots * p.gam_bytes;
+  s.ring = s.bbuf + p.bbuf_bytes;  // header, scratch, program, norm-weight slots and the B buffer are 1 KB multiples
   return s;
 }
 
@@ -282,17 +275,20 @@ __device__ __forceinline__ Phase load_phase(const Phase* prog_smem, int i) {
 }
 
 // =================================================================================================
-// GEMV phase, consumer side
+// GEMV phase on tcgen05
 //
 // A lone warp issues a dependent instruction only every ~5 cycles, so what bounds a phase is the number of instructions
-// between "the input words are visible" and "the output words are stored".  Everything that does not depend on the input
-// (partition, ring positions, addresses, gamma / residual / bias fetches) is therefore computed between issuing the first
-// poll loads and looking at their result — that window (an L2 round trip) is otherwise idle.
+// between "the input words are visible" and "the output words are stored".  The multiply itself is a handful of
+// tcgen05.mma instructions issued by one thread of the MMA warp: the weight tiles in the ring are the A operand as they
+// arrived from HBM (the image is stored pre-swizzled), the consumer warps only stage the activations as the B operand
+// and read the accumulator back.  Everything that does not depend on the input (partition, addresses, gamma / residual /
+// bias fetches) is computed between issuing the first poll loads and looking at their result — that window (an L2 round
+// trip) is otherwise idle.
 // =================================================================================================
 struct Ctx {  // per-thread constants (shared-memory addresses as 32-bit shared-window offsets)
-  uint32_t full, empty, red, scratch, xs, ring, gfull, gempty, gam;
+  uint32_t full, empty, red, scratch, bbuf, ring, gfull, gempty, gam, go, done;
   int n_stages, gam_bytes;
-  uint64_t keep;  // L2 evict_last policy for the small read-mostly tables (norm weights, rope rows)
+  uint32_t tmem;
   const Phase* prog;
 };
 __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchParams& p) {
@@ -302,14 +298,16 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchPa
   c.empty = smem_u32(sm.empty);
   c.red = smem_u32(sm.red);
   c.scratch = smem_u32(sm.scratch);
-  c.xs = smem_u32(sm.xbuf);
+  c.bbuf = smem_u32(sm.bbuf);
   c.ring = smem_u32(sm.ring);
   c.n_stages = p.n_stages;
   c.gfull = smem_u32(smem_base + kGFullOffset);
   c.gempty = smem_u32(smem_base + kGEmptyOffset);
+  c.go = smem_u32(smem_base + kGoOffset);
+  c.done = smem_u32(smem_base + kDoneOffset);
   c.gam = smem_u32(sm.gam);
   c.gam_bytes = p.gam_bytes;
-  c.keep = policy_evict_last();
+  c.tmem = 0u;
   c.prog = sm.prog;
   return c;
 }
@@ -337,13 +335,25 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 
-// Ring cursor: slot and lap parity of the next stage of this CTA (same sequence on the producer and on every consumer).
+// Ring cursor: slot and lap parity of the next stage of this CTA (same sequence on the producer and on the MMA warp).
 struct RingCur {
   int slot;
   uint32_t lap;
@@ -353,182 +363,33 @@ struct RingCur {
   }
 };
 
-// Position of activation word wi (two bf16) in the shared-memory copy of a row: words 1 and 2 of every 16-byte chunk trade
-// places, so that one 16-byte load yields {cols 0-1, cols 4-5, cols 2-3, cols 6-7} of an 8-column chunk — the k-slot order
-// both operand assignments of gemv_unit want.
-__device__ __forceinline__ int xword(int wi) { return (wi & ~3) | ((wi & 1) << 1) | ((wi >> 1) & 1); }
-// the two consecutive words (2q, 2q+1) of pair q land 8 bytes apart
-__device__ __forceinline__ uint32_t xpair_addr(uint32_t xs, int q) { return xs + (uint32_t)(q >> 1) * 16u + (uint32_t)(q & 1) * 4u; }
-__device__ __forceinline__ void xpair_store(uint32_t addr, uint32_t lo, uint32_t hi) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(lo) : "memory");
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + 8u), "r"(hi) : "memory");
-}
+// exact a / b for 0 <= a < 2^20, 1 <= b < 2^12 (the +0.5 keeps the float quotient away from integer boundaries)
+__device__ __forceinline__ int small_div(int a, int b) { return (int)__fdividef((float)a + 0.5f, (float)b); }
 
-// General activation load (several rows, or rows too long for the register path): raw payloads go through shared
-// memory, each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square,
-// x*rsqrt -> bf16, * weight -> bf16.
-__device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
-                                            int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red) {
-  const int Kw = K >> 1;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool norm = (flags & F_PRENORM) != 0;
-#pragma unroll 1
-  for (int m = 0; m < M; ++m) {
-    const LLWord* src = in + (size_t)m * ld;
-    float ss = 0.f;
-#pragma unroll 1
-    for (int w0 = 0; w0 < Kw; w0 += 4 * kConsumerThreads) {
-      LLWord w[4];
-      Spin spin;
-      bool bad;
-      unsigned tries = 0;
-      do {
-        bad = false;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int wi = w0 + tid + i * kConsumerThreads;
-          if (wi < Kw) {
-            w[i] = ll_ld(src + wi);
-            bad |= (w[i].y != ep_in);
-          }
-        }
-        if (ep_in == 0) break;
-        if (bad) {
-          if (++tries > 4) __nanosleep(40);
-          spin.tick(p, DE_LL_WAIT, pidx, (int)ep_in);
-        }
-      } while (bad);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int wi = w0 + tid + i * kConsumerThreads;
-        if (wi < Kw) {
-          sts_u32(xs + (uint32_t)(m * Kw + xword(wi)) * 4u, w[i].x);
-          const float x0 = bf_lo(w[i].x), x1 = bf_hi(w[i].x);
-          ss = fmaf(x0, x0, ss);
-          ss = fmaf(x1, x1, ss);
-        }
-      }
-    }
-    if (norm) {
-      ss = warp_sum(ss);
-      if (lane == 0) sts_f32(red + (uint32_t)(m * 16 + warp) * 4u, ss);
-    }
-  }
-  cbar_sync();
-  if (!norm) return;
-#pragma unroll 1
-  for (int m = 0; m < M; ++m) {
-    float tot = 0.f;
-#pragma unroll
-    for (int wi = 0; wi < kConsumerWarps; ++wi) tot += lds_f32(red + (uint32_t)(m * 16 + wi) * 4u);
-    const float rs = rsqrtf(tot / (float)K + eps);
-    const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
-#pragma unroll 1
-    for (int wi = tid; wi < Kw; wi += kConsumerThreads) {
-      const uint32_t gg = lds_u32(gam + (uint32_t)wi * 4u);
-      const uint32_t v = lds_u32(xs + (uint32_t)(m * Kw + xword(wi)) * 4u);
-      const uint32_t y = pack_bf16x2(bf16r(bf16r(bf_lo(v) * rs) * bf_lo(gg)), bf16r(bf16r(bf_hi(v) * rs) * bf_hi(gg)));
-      sts_u32(xs + (uint32_t)(m * Kw + xword(wi)) * 4u, y);
-      if (wr) reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID])[wi] = y;
-    }
-  }
-  cbar_sync();
-}
-
-// One warp's share of a stage: 16 weight rows x (nblk * 64) columns against up to 4 activation rows, on mma.m16n8k16
-// (lane = 4*g + t).  A lane reads 16 contiguous bytes (8 columns) of each of its two weight rows (g, g+8) per load; which 8
-// columns depends on (g & 1, t) so that a quarter-warp (rows 2j, 2j+1) covers 128 contiguous bytes -> conflict-free although
-// all rows of a stage start in the same bank.  It reads the SAME chunk of activation row g >> 1 (stored as cols
-// {0-1, 4-5, 2-3, 6-7}, see xword).  Lanes of different parity therefore disagree on which column a k-slot means; every
-// product the MMA forms between an even and an odd lane is garbage and lands in accumulator entries nobody reads.
-//
-// HI = true (stages with more than 8 rows), weights = A operand: A = {w(g).x, w(g+8).x, w(g).z, w(g+8).z} (cols 0-1 | 4-5) against
-// B = (x.x, x.y), then the (y, w) / (z, w) halves.  D[row][n] is valid where row and n have the same parity and n >> 1 is the
-// activation row: the lane holds dot(weight row g, activation row t) in c[g&1] and row g+8 in c[2 + (g&1)].  Needs four
-// register moves per HMMA (the A registers come from two loads) but only half the HMMAs of the other assignment.
-//
-// HI = false (<= 8 rows: o_proj / down_proj slices), activations = A operand: A = the activation load as it is (row g of A sees
-// cols 0-3, row g+8 cols 4-7), B = (w.x, w.y) -> valid in D row g, B = (w.z, w.w) -> valid in D row g+8; no moves, and rows 8-15
-// are neither loaded nor multiplied.  The lane holds dot(weight row 2t + (g&1), activation row g >> 1) in c0[g&1] + c1[2 + (g&1)].
-//
-// For nblk == 4 (every K % 512 == 0, i.e. all real shapes) the code is straight-line with the loads of block i+2 issued right
-// behind the MMAs of block i: the warps of a CTA start their stages at the same barrier, so without the overlap inside the
-// warp they alternate between the shared-memory pipe and the tensor pipe in lock-step.
-template <bool HI>
-__device__ __forceinline__ void gemv_unit(uint32_t w0, uint32_t xrow, uint32_t oA, uint32_t oB, int nblk, int h0, float& v_lo, float& v_hi) {
-  float c[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
-  }
-  const uint32_t w1 = w0 + 8u * kRowPitch;
-  struct Frag { uint4 xa, xb, a0, a1, b0, b1; };
-  auto ldblk = [&](Frag& f, uint32_t o) {
-    f.xa = lds128(xrow + o + oA); f.xb = lds128(xrow + o + oB);
-    f.a0 = lds128(w0 + o + oA);
-    if constexpr (HI) f.a1 = lds128(w1 + o + oA);
-    f.b0 = lds128(w0 + o + oB);
-    if constexpr (HI) f.b1 = lds128(w1 + o + oB);
-  };
-  auto mmablk = [&](const Frag& f, float (&ca)[4], float (&cb)[4]) {
-    if constexpr (HI) {
-      mma_bf16(ca, f.a0.x, f.a1.x, f.a0.z, f.a1.z, f.xa.x, f.xa.y);
-      mma_bf16(cb, f.b0.x, f.b1.x, f.b0.z, f.b1.z, f.xb.x, f.xb.y);
-      mma_bf16(ca, f.a0.y, f.a1.y, f.a0.w, f.a1.w, f.xa.z, f.xa.w);
-      mma_bf16(cb, f.b0.y, f.b1.y, f.b0.w, f.b1.w, f.xb.z, f.xb.w);
-    } else {
-      mma_bf16(ca, f.xa.x, f.xa.y, f.xa.z, f.xa.w, f.a0.x, f.a0.y);
-      mma_bf16(cb, f.xa.x, f.xa.y, f.xa.z, f.xa.w, f.a0.z, f.a0.w);
-      mma_bf16(ca, f.xb.x, f.xb.y, f.xb.z, f.xb.w, f.b0.x, f.b0.y);
-      mma_bf16(cb, f.xb.x, f.xb.y, f.xb.z, f.xb.w, f.b0.z, f.b0.w);
-    }
-  };
-  if (nblk == 4) {
-    Frag f0, f1;
-    ldblk(f0, 0u);
-    ldblk(f1, 128u);
-    mmablk(f0, c[0], c[1]);
-    ldblk(f0, 256u);
-    mmablk(f1, c[2], c[3]);
-    ldblk(f1, 384u);
-    mmablk(f0, c[0], c[1]);
-    mmablk(f1, c[2], c[3]);
-  } else {
-#pragma unroll 1
-    for (int i = 0; i < nblk; ++i) {
-      Frag f0;
-      ldblk(f0, (uint32_t)i * 128u);
-      mmablk(f0, c[0], c[1]);
-    }
-  }
-  if constexpr (HI) {
-    const float s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]), s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
-    const float s2 = (c[0][2] + c[1][2]) + (c[2][2] + c[3][2]), s3 = (c[0][3] + c[1][3]) + (c[2][3] + c[3][3]);
-    v_lo = h0 ? s1 : s0;
-    v_hi = h0 ? s3 : s2;
-  } else {  // ca = c[0], c[2] (valid in D row g), cb = c[1], c[3] (valid in D row g+8)
-    v_lo = h0 ? ((c[0][1] + c[2][1]) + (c[1][3] + c[3][3])) : ((c[0][0] + c[2][0]) + (c[1][2] + c[3][2]));
-    v_hi = 0.f;
-  }
-}
-
-// This CTA's share of a GEMV phase (producer and consumers must agree).
+// This CTA's share of a GEMV phase (producer, MMA warp and consumers must agree).
 struct Slab {
-  int n_su, su0, n_rows, n_tiles, nkq, n_stages;
+  int g, grp0;       // 8-row groups of this CTA and the index of its first group
+  int s_log, kbs, tile_groups, n_tiles, ro_shift;
 };
 __device__ __forceinline__ Slab get_slab(const Phase& ph, const LaunchParams& p) {
   const Plan& pl = p.plans[ph.plan];
   const int cta = blockIdx.x;
   Slab s;
-  s.n_su = pl.su_base + (cta < pl.su_rem ? 1 : 0);
-  s.su0 = cta * pl.su_base + min(cta, pl.su_rem);
-  s.n_rows = s.n_su * pl.ro;
-  s.n_tiles = (s.n_rows + kStageRows - 1) / kStageRows;
-  s.nkq = pl.nkq;
-  s.n_stages = s.n_tiles * s.nkq;
+  s.g = pl.g_base + (cta < pl.g_rem ? 1 : 0);
+  s.grp0 = cta * pl.g_base + min(cta, pl.g_rem);
+  s.s_log = pl.s_log;
+  s.kbs = pl.kbs;
+  s.tile_groups = pl.tile_groups;
+  s.n_tiles = (s.g + pl.tile_groups - 1) >> (kMaxSplitLog - pl.s_log);
+  s.ro_shift = pl.ro_shift;
   return s;
 }
+__device__ __forceinline__ int phase_m(const Phase& ph, const LaunchParams& p) {
+  if (ph.flags & F_LAST_ROW) return 1;
+  return (ph.flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows;
+}
+// rows of the B operand (MMA N): M activation rows x S splits, in steps of 16
+__device__ __forceinline__ int b_rows(int M, int s_log) { return ((M << s_log) + 15) & ~15; }
 
 // Values computed before the poll must not be sunk behind it by the compiler: an empty asm pins them in a register.
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
@@ -538,7 +399,7 @@ template <class T>
 __device__ __forceinline__ void pin(T*& v) { asm volatile("" : "+l"(v)); }
 
 // Two neighbouring LL words in one 16-byte request.  ld.relaxed.gpu was the fastest of the flavours tried (volatile, .cv, .cg,
-// relaxed.sys, acquire.gpu: profiles/r01b_ll_store_flavours.log); the run-time switch between them cost a branch chain per poll.
+// relaxed.sys, acquire.gpu: profiles/r01b_ll_store_flavours.log).
 __device__ __forceinline__ uint4 ll_ld_pair(const LLWord* p) {
   uint4 v;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -552,11 +413,103 @@ __device__ __forceinline__ uint32_t norm_pair(uint32_t x, float rs, uint32_t g) 
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
-// Partial sums of one batch in shared memory: part[((tile * M + m) * 16 + row) * (nkq * 2) + kq * 2 + u] — the nkq*2 partial
-// sums of one output row are contiguous, so the finishing thread reads them with 16-byte loads in a fixed order.
+// Where elements [4q, 4q+4) of activation row m live in the B operand: k-block tiles of [nb rows x 64 columns], K-major with
+// the 128-byte swizzle (row n is one 128-byte line, its 16-byte chunk c sits at ((c ^ (n & 7)) << 4)); row n = m * S + h
+// holds the h-th K-range of activation row m, so that virtual weight row (group, split h, r) meets its own K-range in
+// accumulator column m * S + h.
+__device__ __forceinline__ uint32_t b_quad_addr(uint32_t bbuf, int q, int m, int s_log, int kbs, uint32_t btile) {
+  const int blk = q >> 4, w = q & 15;
+  const int h = small_div(blk, kbs), kb = blk - h * kbs;
+  const int n = (m << s_log) + h;
+  return bbuf + (uint32_t)kb * btile + (uint32_t)n * 128u + (uint32_t)((((w >> 1) ^ n) & 7) << 4) + (uint32_t)(w & 1) * 8u;
+}
+
+// General activation load (several rows, or rows too long for the register path): raw payloads are parked in their B
+// slots, each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square,
+// x*rsqrt -> bf16, * weight -> bf16.
+__device__ __noinline__ void stage_b_general(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
+                                             int K, int M, uint32_t ep_in, int pidx, uint32_t bbuf, uint32_t red, int s_log, int kbs,
+                                             uint32_t btile) {
+  const int Kq = K >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool norm = (flags & F_PRENORM) != 0;
+#pragma unroll 1
+  for (int m = 0; m < M; ++m) {
+    const LLWord* src = in + (size_t)m * ld;
+    float ss = 0.f;
+#pragma unroll 1
+    for (int q0 = 0; q0 < Kq; q0 += 2 * kConsumerThreads) {
+      uint4 w[2];
+      Spin spin;
+      bool bad;
+      unsigned tries = 0;
+      do {
+        bad = false;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int q = q0 + tid + i * kConsumerThreads;
+          if (q < Kq) {
+            w[i] = ll_ld_pair(src + 2 * q);
+            bad |= (w[i].y != ep_in) | (w[i].w != ep_in);
+          }
+        }
+        if (ep_in == 0) break;
+        if (bad) {
+          if (++tries > 4) __nanosleep(40);
+          spin.tick(p, DE_LL_WAIT, pidx, (int)ep_in);
+        }
+      } while (bad);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = q0 + tid + i * kConsumerThreads;
+        if (q < Kq) {
+          sts_u32x2(b_quad_addr(bbuf, q, m, s_log, kbs, btile), w[i].x, w[i].z);
+          const float x0 = bf_lo(w[i].x), x1 = bf_hi(w[i].x), x2 = bf_lo(w[i].z), x3 = bf_hi(w[i].z);
+          ss += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
+        }
+      }
+    }
+    if (norm) {
+      ss = warp_sum(ss);
+      if (lane == 0) sts_f32(red + (uint32_t)(m * 16 + warp) * 4u, ss);
+    }
+  }
+  if (!norm) return;
+  cbar_sync();
+#pragma unroll 1
+  for (int m = 0; m < M; ++m) {
+    float tot = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < kConsumerWarps; ++wi) tot += lds_f32(red + (uint32_t)(m * 16 + wi) * 4u);
+    const float rs = rsqrtf(tot / (float)K + eps);
+    const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
+#pragma unroll 1
+    for (int q = tid; q < Kq; q += kConsumerThreads) {
+      const uint2 gg = lds_u32x2(gam + (uint32_t)q * 8u);
+      const uint32_t a = b_quad_addr(bbuf, q, m, s_log, kbs, btile);
+      const uint2 v = lds_u32x2(a);
+      const uint32_t y0 = norm_pair(v.x, rs, gg.x), y1 = norm_pair(v.y, rs, gg.y);
+      sts_u32x2(a, y0, y1);
+      if (wr) reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID])[q] = make_uint2(y0, y1);
+    }
+  }
+  cbar_sync();  // protects red[] and the norm-weight slot against the next phase
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+
+// Consumer side of one GEMV phase.  `par` is the phase bit of the go / done barriers (flips once per tile on every warp
+// of a CTA that owns rows of the phase).
 template <bool PROF>
-__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, RingCur& gcur, int pidx,
+__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& gcur, uint32_t& par, int pidx,
                                                    uint32_t ep) {
+  const Slab sb = get_slab(ph, p);
+  if (sb.g == 0) return;  // more CTAs than row groups (o_proj / down_proj of the small model): nothing to do here
   const uint32_t flags = ph.flags;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int M = (flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows, row_off = 0;
@@ -566,14 +519,14 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const int ldin = p.ld[ph.in_buf];
   const LLWord* in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]) + (size_t)row_off * ldin;
   const bool norm = (flags & F_PRENORM) != 0;
-  const int Kp = K >> 2;  // 16-byte word pairs per row; thread tid owns pairs tid and tid + 384 (elements 4q .. 4q+3)
-  const bool fast = (M == 1) && (Kp <= 2 * kConsumerThreads);  // K <= 3072
+  const int Kq = K >> 2;  // 16-byte word pairs ("quads": elements 4q .. 4q+3) per row; thread tid owns quads tid and tid + 384
+  const bool fast = (M == 1) && (Kq <= 2 * kConsumerThreads);  // K <= 3072
   if (PROF) prof_mark(p, pidx, 0);
   if (PROF) prof_cta_time(p, pidx, 0);
-  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0 && M * K * 2 <= p.xbuf_bytes, pidx, 300000 + M);
+  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0, pidx, 300000 + M);
 
   // ---- issue the first poll of this thread's input words
-  const bool have0 = tid < Kp, have1 = tid + kConsumerThreads < Kp;
+  const bool have0 = tid < Kq, have1 = tid + kConsumerThreads < Kq;
   const LLWord* src = in + 2 * tid;
   uint4 w0 = make_uint4(0u, ep_in, 0u, ep_in), w1 = w0;
   if (fast) {
@@ -583,10 +536,10 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
 
   // ---- everything that does not depend on the input: overlaps the round trip of the poll
   const Plan& pl = p.plans[ph.plan];
-  const Slab sb = get_slab(ph, p);
-  const int ro_shift = pl.ro == 4 ? 2 : 1, tpb = pl.tpb, nkq = sb.nkq;
-  const int grp = warp >> 1, u = warp & 1;
-  const int g = lane >> 2, t = lane & 3, h0 = g & 1;
+  const int s_log = sb.s_log, kbs = sb.kbs, ro_shift = sb.ro_shift;
+  const int nb = b_rows(M, s_log);
+  const uint32_t btile = (uint32_t)nb * 128u;
+  FQ3_ASSERT((int)btile * kbs <= p.bbuf_bytes, pidx, 310000 + nb);
   // norm weights arrive through the producer's stream (slot gcur of the small gamma ring)
   uint32_t gsrc = c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes + (uint32_t)tid * 8u;
   uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
@@ -594,55 +547,42 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   if (norm) gcur.advance(1, kGammaSlots);
   float eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
   float inv_k = pl.inv_k;
-  uint32_t xdst = xpair_addr(c.xs, tid);
-  // finishing thread: (word wl, row m) of the first batch; residual / bias words are fetched now
-  const int npart = nkq * 2;
-  const int tiles0 = min(tpb, sb.n_tiles);
-  FQ3_ASSERT(tiles0 * M * 16 * npart * 4 <= kScratchBytes, pidx, 310000 + tiles0 * npart);
-  int fin0 = min(sb.n_su, (tiles0 * kStageRows) >> ro_shift) * M;
-  const int f_wl = (M == 1) ? tid : tid / M, f_m = (M == 1) ? 0 : tid - f_wl * M;
-  uint32_t res0 = 0u, bias0 = 0u;
+  uint32_t bdst0 = b_quad_addr(c.bbuf, tid, 0, s_log, kbs, btile);
+  uint32_t bdst1 = b_quad_addr(c.bbuf, tid + kConsumerThreads, 0, s_log, kbs, btile);
+  // epilogue geometry of this thread (warps 0-3): TMEM lane = 32 * warp + lane = virtual row ((group * S + split) * 8 + r8)
+  const int S = 1 << s_log;
+  const int ml = lane >> 3, r8 = lane & 7;
+  const int mg = warp * 4 + ml;
+  const int rgl = mg >> s_log;                               // local row group inside the tile
+  const int hbase = (s_log >= 2) ? ((warp * 4) & (S - 1)) : 0;  // first split this warp's lanes hold
+  const int sel = (s_log >= 2) ? ml : ((s_log == 1) ? (ml & 1) : 0);
+  const int nq = (s_log >= 2) ? (S >> 2) : 1;               // partial sums per row after the in-warp reduction
+  const int qidx = (s_log >= 3) ? (warp & (nq - 1)) : 0;
+  const bool writer = (s_log >= 2) ? (ml == 0) : ((s_log == 1) ? ((ml & 1) == 0) : true);
+  const uint32_t part = c.scratch;                           // fp32 [M][128]
+  uint32_t pdst = part + (uint32_t)((rgl * 8 + r8) * nq + qidx) * 4u;
+  const uint32_t taddr = c.tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)hbase;
   LLWord* out = reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]);
   const int ldout = p.ld[ph.out_buf];
-  LLWord* fout = out + (size_t)f_m * ldout + sb.su0 + f_wl;
-  if (tid < fin0) {
-    if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)f_m * p.ld[ph.res_buf] + sb.su0 + f_wl).x;
+  const int n_words = (int)ph.N >> ro_shift;  // packed output words of the whole matrix
+  const int f_wl = (M == 1) ? tid : tid / M, f_m = (M == 1) ? 0 : tid - f_wl * M;  // finishing thread: (word, row) of the first tile
+  const int tg0 = min(sb.tile_groups, sb.g);
+  int fin0 = ((tg0 * 8) >> ro_shift) * M;
+  const int word0 = (sb.grp0 * 8) >> ro_shift;
+  uint32_t res0 = 0u, bias0 = 0u;
+  LLWord* fout = out + (size_t)f_m * ldout + word0 + f_wl;
+  const bool f_act = (warp < kEpiWarps) && (tid < fin0) && (word0 + f_wl < n_words);
+  if (f_act) {
+    if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)f_m * p.ld[ph.res_buf] + word0 + f_wl).x;
     if (flags & F_BIAS) {
       const bf16* bias = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-      bias0 = __ldg(reinterpret_cast<const uint32_t*>(bias) + sb.su0 + f_wl);
+      bias0 = __ldg(reinterpret_cast<const uint32_t*>(bias) + word0 + f_wl);
     }
   }
-  const int f_rr = f_wl << ro_shift;  // first weight row of the word (inside the first batch)
-  uint32_t fq = c.scratch + (uint32_t)((((f_rr >> 4) * M + f_m) * 16 + (f_rr & 15)) * npart) * 4u;
-  // this warp's first stage of the first batch
-  RingCur base = cur;  // ring position of the first stage of the current batch
-  const uint32_t oA = (uint32_t)(h0 * 64 + t * 16), oB = (uint32_t)((h0 ^ 1) * 64 + t * 16);
-  const uint32_t lane_w = (uint32_t)g * kRowPitch + (uint32_t)u * (kUnitCols * 2);
-  RingCur my = base;
-  my.advance(grp, c.n_stages);
-  int s_count = tiles0 * nkq;
-  int kq = grp, tl = 0;  // stage sl = tl * nkq + kq of the batch
-  while (kq >= nkq) { kq -= nkq; ++tl; }
-  int nblk;
-  uint32_t fullb, wrow, xcol, pdst;
-  int tile0 = 0;
-  bool hi_rows = true;
-  auto stage_params = [&]() {
-    hi_rows = sb.n_rows - (tile0 + tl) * kStageRows > 8;
-    const int kw = min(kStageCols, K - kq * kStageCols);
-    const int kcols = min(kUnitCols, kw - u * kUnitCols);  // may be <= 0
-    nblk = kcols > 0 ? (kcols + 63) >> 6 : 0;
-    fullb = c.full + (uint32_t)my.slot * 8u;
-    wrow = c.ring + (uint32_t)my.slot * kStageBytes + lane_w;
-    xcol = c.xs + (uint32_t)(kq * kStageCols + u * kUnitCols) * 2u;
-    // (activation row, weight row) this lane ends up holding: see gemv_unit
-    pdst = c.scratch + (uint32_t)(((tl * M + (hi_rows ? t : (g >> 1))) * 16 + (hi_rows ? g : 2 * t + h0)) * npart + kq * 2 + u) * 4u;
-  };
-  stage_params();
-  pin(gsrc); pin(gfullb); pin(gemptyb); pin(eps); pin(inv_k); pin(xdst); pin(fin0); pin(fout); pin(fq);
-  pin(nblk); pin(fullb); pin(wrow); pin(xcol); pin(pdst); pin(s_count);
+  uint32_t fq = part + (uint32_t)((f_m * 128 + (f_wl << ro_shift) * nq)) * 4u;
+  pin(gsrc); pin(gfullb); pin(gemptyb); pin(eps); pin(inv_k); pin(bdst0); pin(bdst1); pin(fin0); pin(fout); pin(fq); pin(pdst);
 
-  // ---- wait for the input, normalise, stage it in shared memory
+  // ---- wait for the input, normalise, stage it as the B operand
   if (fast) {
     if (ep_in != 0) {
       unsigned tries = 0;
@@ -656,9 +596,8 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
     if (PROF) prof_mark(p, pidx, 7);
     if (PROF) prof_warp_time(p, pidx, 0);
     if (!norm) {
-      if (have0) xpair_store(xdst, w0.x, w0.z);
-      if (have1) xpair_store(xdst + kConsumerThreads * 8, w1.x, w1.z);
-      cbar_sync();
+      if (have0) sts_u32x2(bdst0, w0.x, w0.z);
+      if (have1) sts_u32x2(bdst1, w1.x, w1.z);
     } else {
       float ss;
       {  // absent pairs carry payload 0
@@ -674,10 +613,9 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
         while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
       }
       uint2 g0 = make_uint2(0u, 0u), g1 = g0;
-      if (have0) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(g0.x), "=r"(g0.y) : "r"(gsrc));
-      if (have1) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(g1.x), "=r"(g1.y) : "r"(gsrc + kConsumerThreads * 8));
+      if (have0) g0 = lds_u32x2(gsrc);
+      if (have1) g1 = lds_u32x2(gsrc + kConsumerThreads * 8);
       if (PROF) prof_mark(p, pidx, 15);
-      if (PROF) prof_warp_time(p, pidx, 1);
       cbar_sync();
       if (PROF) prof_mark(p, pidx, 14);
       float tot;
@@ -690,233 +628,231 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       const bool wr = (flags & F_WRITE_NORMED) && blockIdx.x == 0;
       if (have0) {
         const uint32_t y0 = norm_pair(w0.x, rs, g0.x), y1 = norm_pair(w0.z, rs, g0.y);
-        xpair_store(xdst, y0, y1);
+        sts_u32x2(bdst0, y0, y1);
         if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid] = make_uint2(y0, y1);
       }
       if (have1) {
         const uint32_t y0 = norm_pair(w1.x, rs, g1.x), y1 = norm_pair(w1.z, rs, g1.y);
-        xpair_store(xdst + kConsumerThreads * 8, y0, y1);
+        sts_u32x2(bdst1, y0, y1);
         if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid + kConsumerThreads] = make_uint2(y0, y1);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(gemptyb);
-      cbar_sync();  // xs complete; also protects red[] against the next phase
+      // red[] is safe against the next norm phase: every warp passes the done barrier of this phase first
     }
   } else {
     if (norm && !mbar_try_wait_a(gfullb, glap)) {
       Spin spin;
       while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
     }
-    load_x_general(p, flags, in, ldin, gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.xs, c.red);
-    if (norm) {  // load_x_general ends with a barrier after the last read of the norm weights
+    stage_b_general(p, flags, in, ldin, gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.bbuf, c.red, s_log, kbs, btile);
+    if (norm) {  // stage_b_general ends with a barrier after the last read of the norm weights
       if (lane == 0) mbar_arrive_a(gemptyb);
     }
   }
   if (PROF) prof_mark(p, pidx, 1);
 
-  // ---- multiply: batches of <= kBatchStages stages, six stages (one per warp pair) at a time; the parameters of the
-  //      next stage are always computed one iteration ahead (the first ones before the poll)
-  int tiles = tiles0, fin = fin0;
-  while (true) {
+  // ---- tiles: hand the B operand to the MMA warp, wait for the accumulator, reduce the splits, publish
+  int fin = fin0;
 #pragma unroll 1
-    for (int sl = grp; sl < s_count; sl += kGroups) {
-#pragma unroll 1
-      for (int mg = 0; mg < M; mg += 4) {  // activation rows in groups of four (one group in every decode phase)
-        const uint32_t xrow = xcol + (uint32_t)min(mg + (g >> 1), M - 1) * (uint32_t)K * 2u;
-        if (mg == 0 && !mbar_try_wait_a(fullb, my.lap)) {
-          Spin spin;
-          while (!mbar_try_wait_a(fullb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
-        }
-        if (PROF && sl == 0) prof_mark(p, pidx, 8);
-        if (PROF && sl == grp && mg == 0) prof_warp_time(p, pidx, 2);
-        float v_lo = 0.f, v_hi = 0.f;
-        if (nblk > 0) {
-          if (hi_rows) gemv_unit<true>(wrow, xrow, oA, oB, nblk, h0, v_lo, v_hi);
-          else gemv_unit<false>(wrow, xrow, oA, oB, nblk, h0, v_lo, v_hi);
-        }
-        if (PROF && sl == 0) prof_mark(p, pidx, 9);
-        if (mg + (hi_rows ? t : (g >> 1)) < M) {
-          const uint32_t d = pdst + (uint32_t)(mg * 16 * npart) * 4u;
-          sts_f32(d, v_lo);
-          sts_f32(d + (uint32_t)(8 * npart) * 4u, v_hi);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(c.empty + (uint32_t)my.slot * 8u);
-      if (sl + kGroups < s_count) {
-        my.advance(kGroups, c.n_stages);
-        kq += kGroups;
-        while (kq >= nkq) { kq -= nkq; ++tl; }
-        stage_params();
-      }
+  for (int t = 0; t < sb.n_tiles; ++t) {
+    const int tg = min(sb.tile_groups, sb.g - t * sb.tile_groups);
+    fence_async_smem();  // this thread's B stores (generic proxy) before the tensor core's reads (async proxy)
+    tc_fence_before();   // this thread's tcgen05.ld of the previous tile before the MMAs that overwrite the accumulator
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(c.go);
+    if (!mbar_try_wait_a(c.done, par)) {
+      Spin spin;
+      while (!mbar_try_wait_a(c.done, par)) spin.tick(p, DE_DONE_WAIT, pidx, t);
     }
-    if (PROF) prof_mark(p, pidx, 6);
-    if (PROF && tile0 == 0) prof_warp_time(p, pidx, 3);
-    cbar_sync();
+    par ^= 1u;
     if (PROF) prof_mark(p, pidx, 2);
-    // ---- finish: one thread per (output word, activation row); words whose rows lie in tiles [tile0, tile0 + tiles)
-    if (tid < fin) {
-      // first (usually only) word of this thread: everything but the sums was prepared before the poll
-      if (tile0 != 0) {
-        const int w_first = (tile0 * kStageRows) >> ro_shift;
-        const int wl = w_first + tid / M, m = tid % M;
-        if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)m * p.ld[ph.res_buf] + sb.su0 + wl).x;
-        if (flags & F_BIAS) {
-          const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-          bias0 = __ldg(reinterpret_cast<const uint32_t*>(bp) + sb.su0 + wl);
-        }
-        const int rr = (wl << ro_shift) - tile0 * kStageRows;
-        fq = c.scratch + (uint32_t)((((rr >> 4) * M + m) * 16 + (rr & 15)) * npart) * 4u;
-        fout = out + (size_t)m * ldout + sb.su0 + wl;
-      }
-#pragma unroll 1
-      for (int ft = tid;;) {
-        if (PROF) prof_mark(p, pidx, 10);
-        float y[4] = {0.f, 0.f, 0.f, 0.f};
+    if (warp < kEpiWarps) {
+      tc_fence_after();
+      const bool live = rgl < tg;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (r < (1 << ro_shift)) {
-            const uint32_t q = fq + (uint32_t)(r * npart) * 4u;
-            float s = 0.f;
-            if (npart == 4) {
-              const float4 v = lds_f32x4(q);
-              s = (v.x + v.y) + (v.z + v.w);
-            } else if (npart == 8) {
-              const float4 v0 = lds_f32x4(q), v1 = lds_f32x4(q + 16u);
-              s = ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
-            } else if (npart == 12) {
-              const float4 v0 = lds_f32x4(q), v1 = lds_f32x4(q + 16u), v2 = lds_f32x4(q + 32u);
-              s = (((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w))) + ((v2.x + v2.y) + (v2.z + v2.w));
-            } else if ((npart & 3) == 0) {
+      for (int m = 0; m < kMaxRows; ++m) {
+        if (m < M) {
+          float v4[4];
+          tmem_ld4(taddr + (uint32_t)(m << s_log), v4);
+          float v = (sel == 0) ? v4[0] : ((sel == 1) ? v4[1] : ((sel == 2) ? v4[2] : v4[3]));
+          if (s_log >= 1) v += __shfl_xor_sync(0xffffffffu, v, 8);
+          if (s_log >= 2) v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (writer && live) sts_f32(pdst + (uint32_t)(m * 128) * 4u, v);
+        }
+      }
+      if (PROF) prof_mark(p, pidx, 10);
+      epi_bar_sync();
+      // finish: one thread per (output word, activation row) of this tile
+      if (tid < fin) {
+        if (t != 0) {
+          const int wl = tid / M, m = tid - wl * M;
+          const int w_first = ((sb.grp0 + t * sb.tile_groups) * 8) >> ro_shift;
+          fq = part + (uint32_t)(m * 128 + (wl << ro_shift) * nq) * 4u;
+          fout = out + (size_t)m * ldout + w_first + wl;
+        }
 #pragma unroll 1
-              for (int k = 0; k < npart; k += 4) {
-                const float4 v = lds_f32x4(q + (uint32_t)k * 4u);
-                s += (v.x + v.y) + (v.z + v.w);
+        for (int ft = tid;;) {
+          const int w_first = ((sb.grp0 + t * sb.tile_groups) * 8) >> ro_shift;
+          const int wl = ft / M, m = ft - wl * M;
+          const int wg = w_first + wl;
+          if (wg < n_words) {
+            if (t != 0 || ft != tid) {
+              if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)m * p.ld[ph.res_buf] + wg).x;
+              if (flags & F_BIAS) {
+                const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+                bias0 = __ldg(reinterpret_cast<const uint32_t*>(bp) + wg);
               }
-            } else {
-#pragma unroll 1
-              for (int k = 0; k < npart; ++k) s += lds_f32(q + (uint32_t)k * 4u);
             }
-            y[r] = s;
+            float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (r < (1 << ro_shift)) {
+                const uint32_t q = fq + (uint32_t)(r * nq) * 4u;
+                float s;
+                if (nq == 1) s = lds_f32(q);
+                else if (nq == 2) s = lds_f32(q) + lds_f32(q + 4u);
+                else { const float4 v = lds_f32x4(q); s = (v.x + v.y) + (v.z + v.w); }
+                y[r] = s;
+              }
+            }
+            float lo, hi;
+            if (flags & F_SWIGLU) {
+              lo = bf16r(bf16r(silu_f(bf16r(y[0]))) * bf16r(y[1]));
+              hi = bf16r(bf16r(silu_f(bf16r(y[2]))) * bf16r(y[3]));
+            } else {
+              lo = y[0]; hi = y[1];
+              if (flags & F_BIAS) { lo += bf_lo(bias0); hi += bf_hi(bias0); }
+              lo = bf16r(lo); hi = bf16r(hi);
+              if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
+            }
+            if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
+            if (PROF) prof_cta_time(p, pidx, 1);
+            ll_st(fout, pack_bf16x2(lo, hi), ep);
           }
+          ft += kEpiWarps * 32;
+          if (ft >= fin) break;
+          const int wl2 = ft / M, m2 = ft - wl2 * M;
+          fq = part + (uint32_t)(m2 * 128 + (wl2 << ro_shift) * nq) * 4u;
+          fout = out + (size_t)m2 * ldout + w_first + wl2;
         }
-        if (PROF) prof_mark(p, pidx, 11);
-        float lo, hi;
-        if (flags & F_SWIGLU) {
-          lo = bf16r(bf16r(silu_f(bf16r(y[0]))) * bf16r(y[1]));
-          hi = bf16r(bf16r(silu_f(bf16r(y[2]))) * bf16r(y[3]));
-        } else {
-          lo = y[0]; hi = y[1];
-          if (flags & F_BIAS) { lo += bf_lo(bias0); hi += bf_hi(bias0); }
-          lo = bf16r(lo); hi = bf16r(hi);
-          if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
-        }
-        if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
-        if (PROF) prof_mark(p, pidx, 12);
-        if (PROF) prof_cta_time(p, pidx, 1);
-        ll_st(fout, pack_bf16x2(lo, hi), ep);
-        ft += kConsumerThreads;
-        if (ft >= fin) break;
-        // further words of this thread (more than 384 outputs per CTA and batch: generic shapes only)
-        const int w_first = (tile0 * kStageRows) >> ro_shift;
-        const int wl = w_first + ft / M, m = ft % M;
-        if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)m * p.ld[ph.res_buf] + sb.su0 + wl).x;
-        if (flags & F_BIAS) {
-          const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-          bias0 = __ldg(reinterpret_cast<const uint32_t*>(bp) + sb.su0 + wl);
-        }
-        const int rr = (wl << ro_shift) - tile0 * kStageRows;
-        fq = c.scratch + (uint32_t)((((rr >> 4) * M + m) * 16 + (rr & 15)) * npart) * 4u;
-        fout = out + (size_t)m * ldout + sb.su0 + wl;
+      }
+      if (t + 1 < sb.n_tiles) {
+        const int tgn = min(sb.tile_groups, sb.g - (t + 1) * sb.tile_groups);
+        fin = ((tgn * 8) >> ro_shift) * M;
+        epi_bar_sync();  // the next tile overwrites the partial sums
       }
     }
-    base.advance(s_count, c.n_stages);
-    tile0 += tpb;
-    if (tile0 >= sb.n_tiles) break;
-    // next batch (generic shapes / 1.7B gate-up only)
-    cbar_sync();  // the next batch overwrites the partial sums
-    tiles = min(tpb, sb.n_tiles - tile0);
-    s_count = tiles * nkq;
-    fin = (min(sb.n_su, ((tile0 + tiles) * kStageRows) >> ro_shift) - ((tile0 * kStageRows) >> ro_shift)) * M;
-    my = base;
-    my.advance(grp, c.n_stages);
-    kq = grp; tl = 0;
-    while (kq >= nkq) { kq -= nkq; ++tl; }
-    stage_params();
   }
-  cur = base;
   if (PROF) prof_mark(p, pidx, 3);
-  if (PROF) prof_warp_time(p, pidx, 4);
 }
 
-// Producer side of one GEMV phase: stream this CTA's rows through the ring, one 16 KB stage (16 rows x <= 512 columns)
-// per mbarrier: one bulk copy per row (a single one when the stage is contiguous in HBM, K == 512).  The phase's norm
-// weights travel in the same stream.  Returns false when the consumers asked to stop (frame loop finished early).
+// Producer side of one GEMV phase: stream this CTA's tiles through the ring, one contiguous bulk copy per 16 KB stage
+// (one k-block of the tile image).  The phase's norm weights travel in the same stream.  Returns false when the
+// consumers asked to stop (frame loop finished early).
 template <bool PROF>
 __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph, const LaunchParams& p, int* ctl, RingCur& cur, RingCur& gcur, uint32_t& issued,
-                                                   uint32_t& gissued, int pidx, uint64_t pol_stream, uint64_t pol_keep, uint64_t pol_gamma, int lane) {
+                                                   uint32_t& gissued, int pidx, uint64_t pol_stream, uint64_t pol_keep, uint64_t pol_gamma) {
   const Slab sb = get_slab(ph, p);
+  if (sb.g == 0) return true;
   const int K = (int)ph.K;
-  const uint32_t row_bytes = (uint32_t)K * 2u;
-  const unsigned char* W = ((ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_W) : p.arena + (size_t)ph.w_off * 16) +
-                           (size_t)sb.su0 * p.plans[ph.plan].ro * row_bytes;
+  // the image keeps a CTA's groups contiguous: group r of the matrix starts at byte r * 8 * K * 2
+  const unsigned char* W = ((ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_W) : p.tiled + (size_t)ph.w_off * 16) +
+                           (size_t)sb.grp0 * 16u * (size_t)K;
   const uint64_t pol = (ph.flags & F_L2_KEEP) ? pol_keep : pol_stream;
-  if (PROF && (int)blockIdx.x == p.prof_cta && lane == 0 && pidx < 512) p.prof[(size_t)pidx * 16 + 4] = clock64();
+  if (PROF && (int)blockIdx.x == p.prof_cta && pidx < 512) p.prof[(size_t)pidx * 16 + 4] = clock64();
   if (ph.flags & F_PRENORM) {
     const unsigned char* gp = (ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_gamma) : p.arena + (size_t)ph.g_off * 16;
     const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
-    int stop = 0;
-    if (lane == 0) {
-      Spin spin;
-      if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
-      while (!stop && !mbar_try_wait_a(gemptyb, gcur.lap ^ 1u)) {
-        __nanosleep(100);
-        if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
-        spin.tick(p, DE_EMPTY_WAIT, pidx, 100 + gcur.slot);
-      }
-      if (!stop) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfullb), "r"(row_bytes) : "memory");
-        bulk_g2s_a(c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes, gp, row_bytes, gfullb, pol_gamma);
-      }
+    Spin spin;
+    while (!mbar_try_wait_a(gemptyb, gcur.lap ^ 1u)) {
+      if (ld_volatile_shared_i32(ctl) < 0) return false;
+      __nanosleep(100);
+      spin.tick(p, DE_EMPTY_WAIT, pidx, 100 + gcur.slot);
     }
-    stop = __shfl_sync(0xffffffffu, stop, 0);
-    if (stop) return false;
+    if (ld_volatile_shared_i32(ctl) < 0) return false;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfullb), "r"((uint32_t)K * 2u) : "memory");
+    bulk_g2s_a(c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes, gp, (uint32_t)K * 2u, gfullb, pol_gamma);
     gcur.advance(1, kGammaSlots);
     ++gissued;
   }
 #pragma unroll 1
-  for (int tile = 0; tile < sb.n_tiles; ++tile) {
-    const int rows = min(kStageRows, sb.n_rows - tile * kStageRows);
+  for (int t = 0; t < sb.n_tiles; ++t) {
+    const int tg = min(sb.tile_groups, sb.g - t * sb.tile_groups);
+    const uint32_t bytes = (uint32_t)(tg << sb.s_log) * 1024u;  // (group, split) pairs x one 8-row swizzle atom
+    const unsigned char* src = W + (size_t)t * sb.tile_groups * 16u * (size_t)K;
 #pragma unroll 1
-    for (int kq = 0; kq < sb.nkq; ++kq) {
-      const uint32_t kw_bytes = (uint32_t)min(kStageCols, K - kq * kStageCols) * 2u;
+    for (int kb = 0; kb < sb.kbs; ++kb) {
       const uint32_t fullb = c.full + (uint32_t)cur.slot * 8u, emptyb = c.empty + (uint32_t)cur.slot * 8u;
-      int stop = 0;
-      if (lane == 0) {
-        Spin spin;
-        if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
-        while (!stop && !mbar_try_wait_a(emptyb, cur.lap ^ 1u)) {
-          __nanosleep(100);  // the ring is full most of the time: do not compete with the consumer warps for issue slots
-          if (ld_volatile_shared_i32(ctl) < 0) stop = 1;
-          spin.tick(p, DE_EMPTY_WAIT, pidx, cur.slot);
-        }
-        if (!stop)
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"((uint32_t)rows * kw_bytes) : "memory");
+      Spin spin;
+      while (!mbar_try_wait_a(emptyb, cur.lap ^ 1u)) {
+        if (ld_volatile_shared_i32(ctl) < 0) return false;
+        __nanosleep(100);  // the ring is full most of the time
+        spin.tick(p, DE_EMPTY_WAIT, pidx, cur.slot);
       }
-      stop = __shfl_sync(0xffffffffu, stop, 0);
-      if (stop) return false;
-      const uint32_t dst = c.ring + (uint32_t)cur.slot * kStageBytes;
-      const unsigned char* src = W + (size_t)tile * kStageRows * row_bytes + (size_t)kq * kRowPitch;
-      if (kw_bytes == row_bytes && row_bytes == (uint32_t)kRowPitch) {
-        if (lane == 0) bulk_g2s_a(dst, src, (uint32_t)rows * kw_bytes, fullb, pol);
-      } else if (lane < rows) {
-        bulk_g2s_a(dst + (uint32_t)lane * kRowPitch, src + (size_t)lane * row_bytes, kw_bytes, fullb, pol);
-      }
+      if (ld_volatile_shared_i32(ctl) < 0) return false;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(bytes) : "memory");
+      bulk_g2s_a(c.ring + (uint32_t)cur.slot * kStageBytes, src + (size_t)kb * bytes, bytes, fullb, pol);
       cur.advance(1, c.n_stages);
       ++issued;
     }
   }
-  if (PROF && (int)blockIdx.x == p.prof_cta && lane == 0 && pidx < 512) p.prof[(size_t)pidx * 16 + 5] = clock64();
+  if (PROF && (int)blockIdx.x == p.prof_cta && pidx < 512) p.prof[(size_t)pidx * 16 + 5] = clock64();
+  return true;
+}
+
+// MMA side of one GEMV phase (one thread).  A tile = kbs stages of the ring; every stage is one k-block [128 x 64] of the
+// A operand (K-major, 128-byte swizzle, 8-row atoms 1024 bytes apart), multiplied against the matching k-block of the B
+// operand with four tcgen05.mma (k = 16 each).  tcgen05.commit hands a stage back to the producer when its MMAs have read
+// it, and signals the consumers when the whole tile has been accumulated.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B: start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 1024 B (8 rows) | version 1 | layout 2
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ bool gemv_phase_mma(const Ctx& c, const Phase& ph, const LaunchParams& p, int* ctl, RingCur& cur, uint32_t& par, int pidx) {
+  const Slab sb = get_slab(ph, p);
+  if (sb.g == 0) return true;
+  const int M = phase_m(ph, p);
+  const int nb = b_rows(M, sb.s_log);
+  // instruction descriptor: D = F32, A = B = BF16, both K-major, N = nb, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  const uint32_t btile = (uint32_t)nb * 128u;
+#pragma unroll 1
+  for (int t = 0; t < sb.n_tiles; ++t) {
+    {
+      Spin spin;
+      while (!mbar_try_wait_a(c.go, par)) {
+        if (ld_volatile_shared_i32(ctl) < 0) return false;
+        spin.tick(p, DE_GO_WAIT, pidx, t);
+      }
+    }
+    tc_fence_after();
+#pragma unroll 1
+    for (int kb = 0; kb < sb.kbs; ++kb) {
+      const uint32_t fullb = c.full + (uint32_t)cur.slot * 8u;
+      if (!mbar_try_wait_a(fullb, cur.lap)) {
+        Spin spin;
+        while (!mbar_try_wait_a(fullb, cur.lap)) spin.tick(p, DE_FULL_WAIT, pidx, cur.slot);
+      }
+      const uint32_t a0 = c.ring + (uint32_t)cur.slot * kStageBytes, b0 = c.bbuf + (uint32_t)kb * btile;
+#pragma unroll
+      for (int kk = 0; kk < kBlockK / 16; ++kk) {
+        const uint64_t da = umma_desc_sw128(a0 + kk * 32), db = umma_desc_sw128(b0 + kk * 32);
+        const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(c.tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+            : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.empty + (uint32_t)cur.slot * 8u) : "memory");
+      cur.advance(1, c.n_stages);
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.done) : "memory");
+    par ^= 1u;
+  }
   return true;
 }
 
@@ -941,7 +877,9 @@ __device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& 
   r.first_row = g * r.nrows;
   r.slot = p.stream0 + g;
   if (ph.stack == ST_TALKER) {
-    r.pos0 = (p.pos_override >= 0) ? p.pos_override : frame_pos[g];
+    // a stream whose prompt filled the whole cache (T == max_seq_len) still runs the talker phases of its last frame; their
+    // result is discarded (done = 2), so any in-range row will do (generate.py:174-177 returns one frame and breaks)
+    r.pos0 = min((p.pos_override >= 0) ? p.pos_override : frame_pos[g], p.stacks[ST_TALKER].max_pos - 1);
     // launch constants of the stream, parked in shared memory by the frame loop (two L2 round trips per attention phase otherwise)
     const int* sconst = frame_pos + (kStreamConstOffset - kCtlOffset) / 4 - 8;
     r.n_pad = sconst[g];
@@ -1368,8 +1306,6 @@ __device__ __forceinline__ void attn_combine(const Phase& ph, const LaunchParams
   }
 }
 
-// exact a / b for 0 <= a < 2^20, 1 <= b < 2^12 (the +0.5 keeps the float quotient away from integer boundaries)
-__device__ __forceinline__ int small_div(int a, int b) { return (int)__fdividef((float)a + 0.5f, (float)b); }
 
 template <bool PROF>
 __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
@@ -2116,50 +2052,59 @@ template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem sm = carve_smem(smem_raw, p);
-  const Ctx c = make_ctx(smem_raw, p);
+  Ctx c = make_ctx(smem_raw, p);
   const int tid = threadIdx.x;
+  const int warp_id = tid >> 5;
 
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 2);  // the two warps that share a stage
+      mbar_init(&sm.empty[s], 1);  // tcgen05.commit of the stage's MMAs
     }
     for (int s = 0; s < kGammaSlots; ++s) {
       mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGFullOffset) + s, 1);
       mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGEmptyOffset) + s, kConsumerWarps);
     }
+    mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGoOffset), kConsumerWarps);
+    mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kDoneOffset), 1);
     sm.ctl[0] = 0;
     fence_barrier_init();
   }
+  if (warp_id == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_raw + kTmemSlotOffset)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   {
-    // Partially filled stages (last rows of a slab, K < 1024) leave stale bytes under the mma; they only reach outputs
-    // nobody reads, but they must be finite — start from zeros.
-    uint4* r = reinterpret_cast<uint4*>(sm.ring);
-    const int n16 = p.n_stages * (kStageBytes / 16);
+    // The MMA always reads 128 rows of a stage and 16-row multiples of the B operand; rows that no copy / no thread wrote
+    // only reach accumulator entries nobody reads, but they must be finite — start from zeros.
+    uint4* r = reinterpret_cast<uint4*>(sm.bbuf);
+    const int n16 = (p.bbuf_bytes + p.n_stages * kStageBytes) / 16;  // the ring follows the B buffer
     for (int i = tid; i < n16; i += kThreads) r[i] = make_uint4(0u, 0u, 0u, 0u);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
+    fence_async_smem();  // generic-proxy zeros before async-proxy (TMA) writes
     const uint4* src = reinterpret_cast<const uint4*>(p.prog);
     uint4* dst = reinterpret_cast<uint4*>(sm.prog);
     for (int i = tid; i < p.n_phases * 2; i += kThreads) dst[i] = __ldg(src + i);
   }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  c.tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + kTmemSlotOffset);
 
-  if (tid >= kConsumerThreads) {
-    // ------------------------------ producer warp ------------------------------
-    const int lane = tid & 31;
-    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_keep_fraction();
-    const uint64_t pol_gamma = policy_evict_last();
-    RingCur cur{0, 0u}, gcur{0, 0u};
-    uint32_t issued = 0, gissued = 0;
-    bool ok = true;
-    for (int iter = 0; iter < p.n_iters && ok; ++iter) {
-      for (int i = 0; i < p.n_phases && ok; ++i) {
-        const Phase ph = load_phase(sm.prog, i);
-        if (ph.type == PH_GEMV) ok = gemv_phase_produce<PROF>(c, ph, p, sm.ctl, cur, gcur, issued, gissued, i, pol_stream, pol_keep, pol_gamma, lane);
+  if (warp_id == kProducerWarp) {
+    // ------------------------------ producer warp (one thread) ------------------------------
+    if ((tid & 31) == 0) {
+      const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_keep_fraction();
+      const uint64_t pol_gamma = policy_evict_last();
+      RingCur cur{0, 0u}, gcur{0, 0u};
+      uint32_t issued = 0, gissued = 0;
+      bool ok = true;
+      for (int iter = 0; iter < p.n_iters && ok; ++iter) {
+        for (int i = 0; i < p.n_phases && ok; ++i) {
+          const Phase ph = load_phase(sm.prog, i);
+          if (ph.type == PH_GEMV) ok = gemv_phase_produce<PROF>(c, ph, p, sm.ctl, cur, gcur, issued, gissued, i, pol_stream, pol_keep, pol_gamma);
+        }
       }
-    }
-    // drain: shared memory must not be released with bulk copies in flight (the frame loop may stop early)
-    if (lane == 0) {
+      // drain: shared memory must not be released with bulk copies in flight (the frame loop may stop early)
       const int n = (int)min(issued, (uint32_t)p.n_stages);
       RingCur d = cur;
       for (int k = 0; k < n; ++k) {
@@ -2173,53 +2118,98 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
         mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + kGFullOffset) + d.slot, d.lap, p, DE_FULL_WAIT, -4);
       }
     }
-    return;
+  } else if (warp_id == kMmaWarp) {
+    // ------------------------------ MMA warp (one thread) ------------------------------
+    if ((tid & 31) == 0) {
+      RingCur cur{0, 0u};
+      uint32_t par = 0u;
+      bool ok = true;
+      for (int iter = 0; iter < p.n_iters && ok; ++iter) {
+        for (int i = 0; i < p.n_phases && ok; ++i) {
+          const Phase ph = load_phase(sm.prog, i);
+          if (ph.type == PH_GEMV) ok = gemv_phase_mma(c, ph, p, sm.ctl, cur, par, i);
+        }
+      }
+    }
+  } else {
+    // -------------------------------- consumer warps --------------------------------
+    RingCur gcur{0, 0u};
+    uint32_t par = 0u;
+    int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
+    int* frame_done = sm.ctl + 12;  // [4]
+    for (int iter = 0; iter < p.n_iters; ++iter) {
+      const uint32_t ep0 = p.epoch_base + (uint32_t)iter * (uint32_t)p.n_phases;
+      if (p.mode == MODE_FRAMES || p.mode == MODE_TALKER_STEP) {
+        // per-stream frame state: from the stream state at launch, afterwards from the sampler's control record
+        if (tid < p.n_rows) {
+          const StreamState* st = p.st + p.stream0 + tid;
+          int done, pos;
+          if (iter == 0) {
+            done = __ldcg(&st->done);
+            pos = __ldcg(&st->position);
+            int* sconst = reinterpret_cast<int*>(smem_raw + kStreamConstOffset);
+            sconst[tid] = __ldcg(&st->n_pad);
+            sconst[4 + tid] = __ldcg(&st->rope_delta);
+          } else {
+            done = (int)ll_wait(&st->ctl[0], ep0, p, -2);
+            pos = (int)ll_wait(&st->ctl[1], ep0, p, -2);
+          }
+          frame_pos[tid] = pos;
+          frame_done[tid] = done;
+        }
+        cbar_sync();
+        if (p.mode == MODE_FRAMES && iter > 0) {
+          int all_done = 1;
+          for (int b = 0; b < p.n_rows; ++b) all_done &= (frame_done[b] != 0);
+          if (all_done) {
+            if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], -1);  // tells the producer and the MMA warp (which wait ahead) to stop
+            break;
+          }
+        }
+      }
+      for (int i = 0; i < p.n_phases; ++i) {
+        const Phase ph = load_phase(sm.prog, i);
+        const uint32_t ep = ep0 + (uint32_t)i + 1u;
+        switch (ph.type) {
+          case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, gcur, par, i, ep); break;
+          case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
+          case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
+          default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
+        }
+      }
+    }
+    if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], -1);
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp_id == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(kTmemCols) : "memory");
+}
 
-  // -------------------------------- consumer warps --------------------------------
-  RingCur cur{0, 0u}, gcur{0, 0u};
-  int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
-  int* frame_done = sm.ctl + 12;  // [4]
-  for (int iter = 0; iter < p.n_iters; ++iter) {
-    const uint32_t ep0 = p.epoch_base + (uint32_t)iter * (uint32_t)p.n_phases;
-    if (p.mode == MODE_FRAMES || p.mode == MODE_TALKER_STEP) {
-      // per-stream frame state: from the stream state at launch, afterwards from the sampler's control record
-      if (tid < p.n_rows) {
-        const StreamState* st = p.st + p.stream0 + tid;
-        int done, pos;
-        if (iter == 0) {
-          done = __ldcg(&st->done);
-          pos = __ldcg(&st->position);
-          int* sconst = reinterpret_cast<int*>(smem_raw + kStreamConstOffset);
-          sconst[tid] = __ldcg(&st->n_pad);
-          sconst[4 + tid] = __ldcg(&st->rope_delta);
-        } else {
-          done = (int)ll_wait(&st->ctl[0], ep0, p, -2);
-          pos = (int)ll_wait(&st->ctl[1], ep0, p, -2);
-        }
-        frame_pos[tid] = pos;
-        frame_done[tid] = done;
-      }
-      cbar_sync();
-      if (p.mode == MODE_FRAMES && iter > 0) {
-        int all_done = 1;
-        for (int b = 0; b < p.n_rows; ++b) all_done &= (frame_done[b] != 0);
-        if (all_done) {
-          if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], -1);  // tells the producer (which prefetches across frames) to stop
-          break;
-        }
-      }
-    }
-    for (int i = 0; i < p.n_phases; ++i) {
-      const Phase ph = load_phase(sm.prog, i);
-      const uint32_t ep = ep0 + (uint32_t)i + 1u;
-      switch (ph.type) {
-        case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, cur, gcur, i, ep); break;
-        case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
-        case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
-        default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
-      }
-    }
+// Tiled image of one GEMV matrix (fq3_common.cuh: Plan).  W is row-major [N][K]; block c writes the slab of CTA c: its
+// 8-row groups, M-tile by M-tile, k-block by k-block, every (group, split) pair as one 1024-byte swizzle atom (row r8 is a
+// 128-byte line whose 16-byte chunk cc sits at position cc ^ r8).  Rows beyond N are zeros.
+__global__ void fq3_tile_weights_kernel(const bf16* __restrict__ W, uint4* __restrict__ out, int N, int K, Plan pl) {
+  const int cta = blockIdx.x;
+  const int g = pl.g_base + (cta < pl.g_rem ? 1 : 0);
+  const int grp0 = cta * pl.g_base + min(cta, pl.g_rem);
+  const int S = 1 << pl.s_log, Kh = K >> pl.s_log;
+  const long chunks = (long)g * K;  // 16-byte chunks of the slab (8 rows x K / 8 per group)
+  const long tile_chunks = (long)pl.tile_groups * K;
+  uint4* dst = out + (long)grp0 * K;
+  for (long idx = threadIdx.x; idx < chunks; idx += blockDim.x) {
+    const int t = (int)(idx / tile_chunks);
+    const long rem = idx - (long)t * tile_chunks;
+    const int tg = min(pl.tile_groups, g - t * pl.tile_groups);
+    const int per_kb = tg * S * 64;
+    const int kb = (int)(rem / per_kb);
+    const int r2 = (int)(rem - (long)kb * per_kb);
+    const int mgl = r2 >> 6, r3 = r2 & 63, r8 = r3 >> 3, pos = r3 & 7, cc = pos ^ r8;
+    const int rgl = mgl >> pl.s_log, h = mgl & (S - 1);
+    const int row = (grp0 + t * pl.tile_groups + rgl) * 8 + r8;
+    const int col = h * Kh + kb * kBlockK + cc * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < N) v = *reinterpret_cast<const uint4*>(W + (size_t)row * K + col);
+    dst[idx] = v;
   }
 }
 
@@ -2264,6 +2254,14 @@ fq3_rep_penalty_kernel(float* logits, int V, const long long* history, int n_his
       logits[i] = round_bf16 ? bf16r(x) : x;
     }
   }
+}
+
+// LL-epoch wrap (fq3_api.cu: reserve_epochs): keep the payloads, mark every word "written before the launch"
+__global__ void fq3_ll_clear_epochs_kernel(LLWord* w, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) w[i].y = 0u;
+}
+__global__ void fq3_ctl_clear_epochs_kernel(StreamState* st, int n) {
+  for (int i = threadIdx.x; i < n * 4; i += blockDim.x) st[i >> 2].ctl[i & 3].y = 0u;
 }
 
 __global__ void fq3_reset_stream_kernel(StreamState* st, int V) {

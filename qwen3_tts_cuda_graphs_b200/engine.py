@@ -87,7 +87,7 @@ class Engine:
         self._keep += [lm, pe]
         has_s2m = t.hidden_size != p.hidden_size
         desc = _lib.ModelDesc(
-            1, arena.buf.data_ptr(), arena.buf.numel(),
+            _lib.ABI_VERSION, arena.buf.data_ptr(), arena.buf.numel(),
             stack("talker.model", t, "talker", max_seq_len, arena.shapes["rope.talker.cos"][0]),
             stack("talker.code_predictor.model", p, "pred", p.num_code_groups + 1, arena.shapes["rope.pred.cos"][0]),
             arena.offsets["talker.codec_head"], arena.offsets["talker.codec_embedding"], p.num_code_groups,

@@ -36,7 +36,7 @@ def test_ctypes_table_covers_header():
 def test_abi_version_without_gpu():
     from qwen3_tts_cuda_graphs_b200 import _lib
     lib = _lib.load()
-    assert lib.fq3_abi_version() == 1
+    assert lib.fq3_abi_version() == 2
 
 
 def test_engine_refuses_cpu_arena():
