@@ -62,7 +62,7 @@ struct fq3_engine {
   Phase *d_frames = nullptr, *d_pred = nullptr, *d_talker = nullptr, *d_prefill = nullptr, *d_linear = nullptr;
   std::vector<Phase> h_frames, h_pred, h_talker, h_prefill;  // host copies (shared-memory sizing)
   int n_frames_ph = 0, n_pred_ph = 0, n_talker_ph = 0, n_prefill_ph = 0;
-  uint8_t* tiled = nullptr;               // tiled images of every GEMV matrix (fq3_common.cuh: Plan); Phase::w_off indexes it
+  uint8_t* tiled = nullptr;               // fragment images of every GEMV matrix (fq3_tile_weights_kernel); Phase::w_off indexes it
   size_t tiled_bytes = 0;
   std::vector<std::pair<uint64_t, uint64_t>> tiled_map;  // arena byte offset -> image byte offset
   uint8_t* lin_img = nullptr;             // scratch image of fq3_linear's matrix
@@ -95,23 +95,21 @@ int dalloc(fq3_engine* e, T** p, size_t n, bool zero = true) {
 
 uint32_t off16(uint64_t byte_off) { return (uint32_t)(byte_off >> 4); }
 
-// Partition of one GEMV shape over the grid (fq3_common.cuh: Plan): 8-row groups per CTA, K-splits that fill the 128
-// virtual rows of an MMA tile.
+// Partition of one GEMV shape over the grid (fq3_common.cuh: Plan): 8-row groups per CTA, the twelve consumer warps of a
+// CTA split between groups and k-parts.
 bool make_plan(int G, int N, int K, bool swiglu, Plan* out) {
-  if (N < 2 || (N & 1) || K < kBlockK || (K % kBlockK)) return false;
+  if (N < 2 || (N & 1) || K < 64 || (K % 64)) return false;
   if (swiglu && (N & 3)) return false;
   Plan pl{};
   pl.ro_shift = swiglu ? 2 : 1;
-  const int n_groups = (N + 7) / 8;
+  const int n_groups = (N + kGroupRows - 1) / kGroupRows;
   pl.g_base = n_groups / G;
   pl.g_rem = n_groups - pl.g_base * G;
   const int g_max = pl.g_base + (pl.g_rem ? 1 : 0);
-  const int kblocks = K / kBlockK;
-  int s_log = 0;
-  while (s_log < kMaxSplitLog && (g_max << (s_log + 1)) <= 16 && (kblocks % (2 << s_log)) == 0) ++s_log;
-  pl.s_log = s_log;
-  pl.kbs = kblocks >> s_log;
-  pl.tile_groups = 16 >> s_log;
+  pl.nch = K / kChunkK;
+  pl.wpg = g_max >= kConsumerWarps ? 1 : std::max(1, std::min(kConsumerWarps / std::max(1, g_max), pl.nch));
+  pl.gpr = kConsumerWarps / pl.wpg;
+  pl.spg = (K * 16 + kStageBytes - 1) / kStageBytes;
   pl.inv_k = 1.0f / (float)K;
   *out = pl;
   return true;
@@ -205,7 +203,7 @@ void push_talker(std::vector<Phase>& v, fq3_engine* e, bool last_row_head) {
   v.push_back(h);
 }
 
-// Point every GEMV phase of a program at the tiled image of its matrix (built on first use), then upload the program.
+// Point every GEMV phase of a program at the fragment image of its matrix (built on first use), then upload the program.
 int upload(fq3_engine* e, std::vector<Phase>& v, Phase** d) {
   const uint8_t* arena = reinterpret_cast<const uint8_t*>(e->desc.arena);
   for (Phase& ph : v) {
@@ -221,8 +219,8 @@ int upload(fq3_engine* e, std::vector<Phase>& v, Phase** d) {
       ioff = used;
       const size_t bytes = (size_t)ph.N * ph.K * 2;
       if (ioff + bytes > e->tiled_bytes) return -1;
-      fq3_tile_weights_kernel<<<e->G, 256>>>(reinterpret_cast<const bf16*>(arena + aoff), reinterpret_cast<uint4*>(e->tiled + ioff), (int)ph.N,
-                                            (int)ph.K, e->plans[ph.plan]);
+      fq3_tile_weights_kernel<<<256, 256>>>(reinterpret_cast<const bf16*>(arena + aoff), reinterpret_cast<uint4*>(e->tiled + ioff), (int)ph.N,
+                                            (int)ph.K);
       if (cudaGetLastError() != cudaSuccess) return -1;
       e->tiled_map.push_back({aoff, ioff});
       e->tiled_used = (ioff + bytes + 1023) / 1024 * 1024;
@@ -297,25 +295,24 @@ int reserve_epochs(fq3_engine* e, uint64_t span, cudaStream_t s) {
 }
 
 // Launch the persistent kernel: one CTA per SM, cooperative (all CTAs must be co-resident: they poll each other's words).
-// smem: header | scratch | program | norm-weight slots | B operand | weight ring (16 KB stages, everything that is left).
+// smem: header | scratch | program | norm-weight slots | activation rows | weight ring (16 KB stages, everything that is left).
 int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t s) {
   const int grid = e->G;
-  size_t bbytes = 0, gamma_elems = 0;
+  size_t xbytes = 0, gamma_elems = 0;
   for (int i = 0; i < p.n_phases; ++i) {
     const Phase& ph = prog_host[i];
     if (ph.type != PH_GEMV) continue;
-    const Plan& pl = (ph.flags & F_ABSPTR) ? p.plans[ph.plan] : e->plans[ph.plan];
     const int M = phase_rows_host(ph, p.n_rows);
     if (M > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "more activation rows than the GEMV stage takes");
-    bbytes = std::max(bbytes, (size_t)pl.kbs * (size_t)((((size_t)M << pl.s_log) + 15) / 16 * 16) * 128);
+    xbytes = std::max(xbytes, (size_t)M * ph.K * 2);
     if (ph.flags & F_PRENORM) gamma_elems = std::max(gamma_elems, (size_t)ph.K);
   }
-  p.bbuf_bytes = (int)round_up(bbytes, 1024);
+  p.xbuf_bytes = (int)round_up(xbytes, 1024);
   p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 1024);
   p.gam_bytes = (int)round_up(gamma_elems * 2, 1024);
   // Shared memory and L1 share 256 KB per SM: staying at or below the 196 KB carve-out leaves 60 KB of L1 for the table
   // reads of the attention and sampling phases.
-  const long fixed = kHeaderBytes + kScratchBytes + (long)p.bbuf_bytes + (long)p.prog_bytes + (long)kGammaSlots * p.gam_bytes;
+  const long fixed = kHeaderBytes + kScratchBytes + (long)p.xbuf_bytes + (long)p.prog_bytes + (long)kGammaSlots * p.gam_bytes;
   const long budget = e->ring_cap > 0 ? (long)e->smem_max : std::min<long>((long)e->smem_max, 196L * 1024);
   long avail = budget - fixed;
   if (avail < 6L * kStageBytes) avail = (long)e->smem_max - fixed;
@@ -906,7 +903,7 @@ int fq3_linear(fq3_engine* e, const void* W, const void* x, void* y, int M, int 
     if (dalloc(e, &e->lin_img, img_bytes, false)) return -FQ3_E_CUDA;
     e->lin_img_bytes = img_bytes;
   }
-  fq3_tile_weights_kernel<<<e->G, 256, 0, s>>>(reinterpret_cast<const bf16*>(W), reinterpret_cast<uint4*>(e->lin_img), N, K, lin_plan);
+  fq3_tile_weights_kernel<<<256, 256, 0, s>>>(reinterpret_cast<const bf16*>(W), reinterpret_cast<uint4*>(e->lin_img), N, K);
   e->launches += 1;
   CK(cudaGetLastError());
   Phase ph{};

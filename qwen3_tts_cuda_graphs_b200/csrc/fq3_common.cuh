@@ -2,13 +2,12 @@
 //
 // The kernel is a small "phase machine": a program is a flat list of 32-byte phase descriptors (GEMV /
 // attention / sampling).  One CTA per SM runs the whole program.  Every GEMV weight matrix is kept in HBM as a
-// *tiled image*: the rows a CTA owns, cut into k-blocks of 64 columns, each k-block stored as the 128-byte-swizzled
-// K-major tile tcgen05.mma reads (up to 128 "virtual rows" x 64 columns = 16 KB).  A producer warp streams these
-// tiles through a shared-memory ring with cp.async.bulk (TMA bulk copy, SASS UBLKCP) — one contiguous copy per
-// stage — and runs ahead of the consumers across phases and frames, so HBM stays busy while the CTAs wait for
-// each other.  One thread of an MMA warp issues tcgen05.mma (weights = A operand from the ring, activations = B
-// operand staged by the consumer warps, accumulator in tensor memory); four consumer warps read the accumulator
-// back with tcgen05.ld and publish.  See DESIGN.md §3.
+// *fragment image*: groups of 8 consecutive rows, each group a run of 512-byte blocks (8 rows x 32 columns) laid out
+// so that one 16-byte shared-memory load per lane yields the mma.m16n8k16 B fragments of two k-steps.  A producer
+// warp streams a CTA's groups through a shared-memory ring of 16 KB stages with cp.async.bulk (TMA bulk copy, SASS
+// UBLKCP) — one contiguous copy per stage — and runs ahead of the consumers across phases and frames, so HBM stays
+// busy while the CTAs wait for each other.  The activations are the A operand (one stream per A row), so after the
+// k loop every lane holds the dot products of one (stream, output word).  See DESIGN.md §3.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -19,18 +18,15 @@ namespace fq3 {
 typedef __nv_bfloat16 bf16;
 
 // ---- geometry ---------------------------------------------------------------------------------
-constexpr int kConsumerWarps = 12;  // 12 consumers + producer + MMA issuer = 14 warps; registers are allotted per 4 warps -> 128 per thread
+constexpr int kConsumerWarps = 12;  // 12 consumers + 1 producer = 13 warps; registers are allotted per 4 warps -> 128 per thread
 constexpr int kConsumerThreads = kConsumerWarps * 32;  // 384
-constexpr int kProducerWarp = kConsumerWarps;          // streams the weight tiles
-constexpr int kMmaWarp = kConsumerWarps + 1;           // one thread issues tcgen05.mma
-constexpr int kThreads = kConsumerThreads + 64;
-constexpr int kEpiWarps = 4;               // consumer warps 0-3 read the accumulator (TMEM lanes 32w .. 32w+31)
+constexpr int kThreads = kConsumerThreads + 32;        // + one producer warp
 constexpr int kMaxStages = 16;             // mbarrier pairs: ring stages in flight per SM
-constexpr int kTileM = 128;                // virtual rows of one MMA tile = TMEM lanes
-constexpr int kBlockK = 64;                // columns of one k-block = one 128-byte swizzled line per row
-constexpr int kStageBytes = kTileM * kBlockK * 2;  // 16 KB: one k-block tile
-constexpr int kMaxSplitLog = 4;            // up to 16 K-splits ride the M dimension (16 groups of 8 rows per tile)
-constexpr int kTmemCols = 512;
+constexpr int kGroupRows = 8;              // weight rows per group = the n dimension of mma.m16n8k16
+constexpr int kChunkK = 32;                // columns per fragment block (two k-steps of 16)
+constexpr int kBlockBytes = kGroupRows * kChunkK * 2;  // 512: one warp-wide 16-byte load
+constexpr int kStageBytes = 16 * 1024;     // ring stage: up to 32 blocks (1024 columns) of ONE group
+constexpr int kStageChunks = kStageBytes / kBlockBytes;  // 32
 constexpr int kHeadDim = 128;              // talker and predictor heads (asserted on the host)
 constexpr int kMaxRows = 8;                // activation rows (tokens) per launch, GEMV register tile
 constexpr int kMaxSplits = 16;             // split-KV partitions per (sequence, kv head)
@@ -38,20 +34,17 @@ constexpr int kSplitLen = 4 * kConsumerWarps;              // positions one CTA 
 constexpr int kPartStride = 132;           // floats per attention partial: m, l, pad, pad, o[128]
 constexpr int kNumBufs = 16;
 constexpr int kMaxVocab = 5120;            // sampling scratch holds V fp32 logits in 20 KB
-// scratch: GEMV split partial sums [M<=8][128] fp32 = 4 KB;
+// scratch: GEMV partial sums of the k-parts [12 warps][32 lanes][4] fp32 = 6 KB;
 //          attention q rows fp32 [2][128] | fresh K/V rows bf16 [8][2][128] | warp partials [12][2][132] = 17.4 KB;
 //          sampling 20 KB logits + histogram + reductions = 21.5 KB
 constexpr int kScratchBytes = 24 * 1024;
-// smem header: full[16] | empty[16] | ctl[16] | red[8][16] | gfull[4] | gempty[4] | stream consts | go | done | tmem base
+// smem header: full[16] | empty[16] | ctl[16] | red[8][16] | gfull[4] | gempty[4] | stream consts
 constexpr int kEmptyOffset = 128;
 constexpr int kCtlOffset = 256;
 constexpr int kRedOffset = 320;
 constexpr int kGFullOffset = 832;
 constexpr int kGEmptyOffset = 864;
 constexpr int kStreamConstOffset = 896;  // int [4] n_pad | [4] rope_delta of the streams of this launch
-constexpr int kGoOffset = 928;           // mbarrier: the B operand of the current tile is staged (one arrival per consumer warp)
-constexpr int kDoneOffset = 936;         // mbarrier: the MMAs of the current tile have completed (tcgen05.commit)
-constexpr int kTmemSlotOffset = 944;     // uint32: tensor-memory base address
 constexpr int kHeaderBytes = 1024;
 constexpr int kGammaSlots = 4;             // norm-weight vectors in flight (streamed by the producer like the weights)
 constexpr int kMaxPlans = 24;
@@ -108,18 +101,17 @@ enum BufId : uint8_t {
 };
 
 // Host-computed partition of one GEMV shape (N, K, SwiGLU) over the grid, in groups of 8 consecutive weight rows.
-// A CTA's groups are cut into M-tiles of `tile_groups` groups; inside a tile every row is split into S = 1 << s_log
-// K-ranges of kbs k-blocks, and the (group, split) pairs are the 8-row groups of the MMA's M dimension (virtual row
-// m = ((group * S + split) * 8 + row), at most 128): S partial dot products per row come out of one pass over K / S
-// columns and are added in split order by the epilogue.
+// Inside a CTA a group is shared by `wpg` warps, each taking a contiguous part of the K / 32 fragment blocks
+// ("k-part"); gpr = 12 / wpg groups are in flight at once and a CTA with more groups goes round again.  A group's
+// image (8 * K * 2 bytes, contiguous) travels through spg = ceil(K / 1024) ring stages.
 struct Plan {
   int g_base, g_rem;  // 8-row groups per CTA: the first g_rem CTAs take g_base + 1
-  int s_log;          // log2 of the K-splits
-  int kbs;            // k-blocks (64 columns) per split = (K / 64) >> s_log
-  int tile_groups;    // groups per M-tile = 16 >> s_log
+  int wpg;            // warps per group (k-parts)
+  int gpr;            // groups per round
+  int spg;            // ring stages per group
+  int nch;            // fragment blocks per group = K / 32
   int ro_shift;       // log2 of the weight rows behind one packed output word: 1 (plain) or 2 (SwiGLU: two (gate, up) pairs)
   float inv_k;        // 1 / K
-  int pad;
 };
 // ---- run-time structures ----------------------------------------------------------------------
 struct StackRt {
@@ -175,7 +167,7 @@ struct LaunchParams {
   int pos_override;  // >=0: talker position for MODE_TALKER_STEP
   int pf_pos0, pf_n_pad, pf_rope_delta, pf_final;
   const uint8_t* arena;
-  const uint8_t* tiled;  // tiled images of the GEMV matrices, same byte offsets as the arena
+  const uint8_t* tiled;  // fragment images of the GEMV matrices (Phase::w_off indexes this buffer)
   void* bufs[kNumBufs];
   int ld[kNumBufs];
   StackRt stacks[2];
@@ -195,7 +187,7 @@ struct LaunchParams {
   const void* lin_bias;
   float lin_eps;
   // smem carve-up
-  int n_stages, bbuf_bytes, prog_bytes, gam_bytes;  // ring stages of 16 KB; bytes of the B-operand staging buffer / of the program copy / of ONE norm-weight slot (1 KB multiples)
+  int n_stages, xbuf_bytes, prog_bytes, gam_bytes;  // ring stages of 16 KB; bytes of the activation staging buffer / of the program copy / of ONE norm-weight slot (1 KB multiples)
   Plan plans[kMaxPlans];
   unsigned epoch_base;  // LL epoch of the phase before this launch's first phase
   unsigned long long watchdog_ns;
@@ -204,6 +196,6 @@ struct LaunchParams {
   int debug;  // timing ablations (FQ3_DEBUG): 1 no LL wait, 2 no GEMV math, 4 no attention
 };
 
-enum DevErr : int { DE_NONE = 0, DE_LL_WAIT = 1, DE_FULL_WAIT = 2, DE_EMPTY_WAIT = 3, DE_HANDSHAKE = 4, DE_BAD_PHASE = 5, DE_CTL_WAIT = 6, DE_ASSERT = 7, DE_GO_WAIT = 8, DE_DONE_WAIT = 9 };
+enum DevErr : int { DE_NONE = 0, DE_LL_WAIT = 1, DE_FULL_WAIT = 2, DE_EMPTY_WAIT = 3, DE_HANDSHAKE = 4, DE_BAD_PHASE = 5, DE_CTL_WAIT = 6, DE_ASSERT = 7 };
 
 }  // namespace fq3

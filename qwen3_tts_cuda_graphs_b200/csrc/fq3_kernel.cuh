@@ -1,19 +1,17 @@
-// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a), v8: GEMV phases on tcgen05.
+// fq3_kernel.cuh — the persistent weight-streaming decode kernel (sm_100a), v9.
 //
 // Replaces the CUDA-graph replays of talker_graph.py:97-107,198-214 and predictor_graph.py:115-167 and
 // the eager per-frame glue of generate.py:149-199 (reference paths under /root/reference/faster_qwen3_tts).
 //
 // Structure of one CTA (one per SM, all co-resident):
-//   warp 12      producer: walks the phase program and streams this CTA's tiles of every GEMV phase's weight image
-//                through a shared-memory ring of 16 KB stages with cp.async.bulk (TMA bulk copy), one contiguous
-//                copy per stage.  Weight addresses never depend on activations or sampled ids, so it runs ahead of
-//                the consumers across phases and frames.
-//   warp 13      MMA issuer: per GEMV phase one thread waits for the staged activations, then issues tcgen05.mma
-//                (M = 128 virtual weight rows, N = activation rows x K-splits, accumulator in tensor memory) over
-//                the ring stages and commits them back to the producer.
-//   warps 0..11  consumers: per phase, poll-read the input activations (LL words), normalise and stage them as the
-//                B operand; warps 0-3 read the accumulator with tcgen05.ld, add the K-splits in a fixed order, apply
-//                the epilogue and publish.  Attention and sampling phases run on all twelve.
+//   warp 12      producer: walks the phase program and streams this CTA's row groups of every GEMV phase's weight
+//                image through a shared-memory ring of 16 KB stages with cp.async.bulk (TMA bulk copy), one
+//                contiguous copy per stage.  Weight addresses never depend on activations or sampled ids, so it
+//                runs ahead of the consumers across phases and frames.
+//   warps 0..11  consumers: per phase, poll-read the input activations (LL words), normalise and stage them; then a
+//                warp multiplies one group of 8 weight rows over its part of K with mma.sync.m16n8k16 (weights = B
+//                operand as they arrived, activations = A operand, one stream per row), the parts of a group meet in
+//                shared memory and the group's first warp applies the epilogue and publishes.
 // There is no grid barrier: phases are chained by the data itself (payload + epoch in one 8-byte word).
 #pragma once
 #include "fq3_common.cuh"
@@ -149,7 +147,7 @@ struct Smem {
   unsigned char* scratch;
   Phase* prog;       // copy of the phase program (a global read per phase would sit on the critical path)
   unsigned char* gam;  // [kGammaSlots][gam_bytes] norm weights, streamed by the producer
-  unsigned char* bbuf;  // B operand of the current GEMV phase (activations, K-major 128-byte-swizzled k-block tiles)
+  unsigned char* xbuf;  // activation rows of the current GEMV phase, in A-fragment order
   unsigned char* ring;
 };
 
@@ -162,8 +160,8 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base, const LaunchPara
   s.scratch = base + kHeaderBytes;
   s.prog = reinterpret_cast<Phase*>(s.scratch + kScratchBytes);
   s.gam = s.scratch + kScratchBytes + p.prog_bytes;
-  s.bbuf = s.gam + kGammaSlots * p.gam_bytes;
-  s.ring = s.bbuf + p.bbuf_bytes;  // header, scratch, program, norm-weight slots and the B buffer are 1 KB multiples
+  s.xbuf = s.gam + kGammaSlots * p.gam_bytes;
+  s.ring = s.xbuf + p.xbuf_bytes;  // header, scratch, program, norm-weight slots and xbuf are 1 KB multiples
   return s;
 }
 
@@ -275,20 +273,27 @@ __device__ __forceinline__ Phase load_phase(const Phase* prog_smem, int i) {
 }
 
 // =================================================================================================
-// GEMV phase on tcgen05
+// GEMV phase
 //
 // A lone warp issues a dependent instruction only every ~5 cycles, so what bounds a phase is the number of instructions
-// between "the input words are visible" and "the output words are stored".  The multiply itself is a handful of
-// tcgen05.mma instructions issued by one thread of the MMA warp: the weight tiles in the ring are the A operand as they
-// arrived from HBM (the image is stored pre-swizzled), the consumer warps only stage the activations as the B operand
-// and read the accumulator back.  Everything that does not depend on the input (partition, addresses, gamma / residual /
-// bias fetches) is computed between issuing the first poll loads and looking at their result — that window (an L2 round
-// trip) is otherwise idle.
+// between "the input words are visible" and "the output words are stored".  The multiply is arranged so that nothing
+// has to be re-shuffled afterwards: a warp takes one group of 8 weight rows and a contiguous part of K; the weights are
+// the B operand of mma.m16n8k16 (n = row inside the group) exactly as they arrive from HBM — the image is stored in
+// fragment order, one 16-byte load per lane feeds two k-steps — and the activations are the A operand, one stream per A
+// row.  After the k loop lane (g, t) holds the dot products of stream g with rows 2t and 2t+1 of the group: one packed
+// output word.  Where a group is shared by several warps (k-parts) the partial words go through shared memory once and
+// the first warp of the group adds them in part order.  Everything that does not depend on the input (partition,
+// addresses, gamma / residual / bias fetches, the wait for the weight stage) happens between issuing the first poll loads
+// and looking at their result — that window (an L2 round trip) is otherwise idle.
+//
+// (A tcgen05 version of this phase — weights as a pre-swizzled A operand, K-splits on the M dimension, accumulator in
+// tensor memory — was built and measured first: an SS-mode tcgen05.mma streams its A rows from shared memory at one row
+// per cycle, 128 cycles per k-step whatever N is, which is slower than shared-memory loads + mma.sync for a GEMV:
+// profiles/r02a_tcgen05_gemv_phase_profile_rejected.log.)
 // =================================================================================================
 struct Ctx {  // per-thread constants (shared-memory addresses as 32-bit shared-window offsets)
-  uint32_t full, empty, red, scratch, bbuf, ring, gfull, gempty, gam, go, done;
+  uint32_t full, empty, red, scratch, xs, ring, gfull, gempty, gam;
   int n_stages, gam_bytes;
-  uint32_t tmem;
   const Phase* prog;
 };
 __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchParams& p) {
@@ -298,16 +303,13 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchPa
   c.empty = smem_u32(sm.empty);
   c.red = smem_u32(sm.red);
   c.scratch = smem_u32(sm.scratch);
-  c.bbuf = smem_u32(sm.bbuf);
+  c.xs = smem_u32(sm.xbuf);
   c.ring = smem_u32(sm.ring);
   c.n_stages = p.n_stages;
   c.gfull = smem_u32(smem_base + kGFullOffset);
   c.gempty = smem_u32(smem_base + kGEmptyOffset);
-  c.go = smem_u32(smem_base + kGoOffset);
-  c.done = smem_u32(smem_base + kDoneOffset);
   c.gam = smem_u32(sm.gam);
   c.gam_bytes = p.gam_bytes;
-  c.tmem = 0u;
   c.prog = sm.prog;
   return c;
 }
@@ -328,16 +330,19 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32x2(uint32_t a, float v0, float v1) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v0), "f"(v1) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u32x2(uint32_t a, uint32_t v0, uint32_t v1) {
-  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1) : "memory");
-}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -348,12 +353,18 @@ __device__ __forceinline__ uint2 lds_u32x2(uint32_t a) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
   return v;
 }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+// named barrier of the warps that share a weight group (ids 2 .. 13; 0 = __syncthreads, 1 = all consumers)
+__device__ __forceinline__ void group_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// Ring cursor: slot and lap parity of the next stage of this CTA (same sequence on the producer and on the MMA warp).
+// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Ring cursor: slot and lap parity of the next stage of this CTA (same sequence on the producer and on every consumer).
 struct RingCur {
   int slot;
   uint32_t lap;
@@ -366,10 +377,10 @@ struct RingCur {
 // exact a / b for 0 <= a < 2^20, 1 <= b < 2^12 (the +0.5 keeps the float quotient away from integer boundaries)
 __device__ __forceinline__ int small_div(int a, int b) { return (int)__fdividef((float)a + 0.5f, (float)b); }
 
-// This CTA's share of a GEMV phase (producer, MMA warp and consumers must agree).
+// This CTA's share of a GEMV phase (producer and consumers must agree).
 struct Slab {
-  int g, grp0;       // 8-row groups of this CTA and the index of its first group
-  int s_log, kbs, tile_groups, n_tiles, ro_shift;
+  int g, grp0;  // 8-row groups of this CTA and the index of its first group
+  int n_stages; // ring stages the phase takes on this CTA = g * spg
 };
 __device__ __forceinline__ Slab get_slab(const Phase& ph, const LaunchParams& p) {
   const Plan& pl = p.plans[ph.plan];
@@ -377,19 +388,9 @@ __device__ __forceinline__ Slab get_slab(const Phase& ph, const LaunchParams& p)
   Slab s;
   s.g = pl.g_base + (cta < pl.g_rem ? 1 : 0);
   s.grp0 = cta * pl.g_base + min(cta, pl.g_rem);
-  s.s_log = pl.s_log;
-  s.kbs = pl.kbs;
-  s.tile_groups = pl.tile_groups;
-  s.n_tiles = (s.g + pl.tile_groups - 1) >> (kMaxSplitLog - pl.s_log);
-  s.ro_shift = pl.ro_shift;
+  s.n_stages = s.g * pl.spg;
   return s;
 }
-__device__ __forceinline__ int phase_m(const Phase& ph, const LaunchParams& p) {
-  if (ph.flags & F_LAST_ROW) return 1;
-  return (ph.flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows;
-}
-// rows of the B operand (MMA N): M activation rows x S splits, in steps of 16
-__device__ __forceinline__ int b_rows(int M, int s_log) { return ((M << s_log) + 15) & ~15; }
 
 // Values computed before the poll must not be sunk behind it by the compiler: an empty asm pins them in a register.
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
@@ -413,29 +414,30 @@ __device__ __forceinline__ uint32_t norm_pair(uint32_t x, float rs, uint32_t g) 
   return *reinterpret_cast<const uint32_t*>(&y);
 }
 
-// Where elements [4q, 4q+4) of activation row m live in the B operand: k-block tiles of [nb rows x 64 columns], K-major with
-// the 128-byte swizzle (row n is one 128-byte line, its 16-byte chunk c sits at ((c ^ (n & 7)) << 4)); row n = m * S + h
-// holds the h-th K-range of activation row m, so that virtual weight row (group, split h, r) meets its own K-range in
-// accumulator column m * S + h.
-__device__ __forceinline__ uint32_t b_quad_addr(uint32_t bbuf, int q, int m, int s_log, int kbs, uint32_t btile) {
-  const int blk = q >> 4, w = q & 15;
-  const int h = small_div(blk, kbs), kb = blk - h * kbs;
-  const int n = (m << s_log) + h;
-  return bbuf + (uint32_t)kb * btile + (uint32_t)n * 128u + (uint32_t)((((w >> 1) ^ n) & 7) << 4) + (uint32_t)(w & 1) * 8u;
+// Shared-memory copy of an activation row, in the order the A fragments want it: a 32-column block is 64 bytes, lane t's
+// 16 bytes hold columns {2t, 2t+1 | 8+2t, 9+2t | 16+2t, 17+2t | 24+2t, 25+2t} (= a0, a2 of k-step 0, a0, a2 of k-step 1).
+// A quad q (columns 4q .. 4q+3, the two LL words a thread polls with one request) lands in two 4-byte slots 16 bytes apart.
+__device__ __forceinline__ uint32_t xquad_off(int q) {
+  const int qq = q & 7;  // quad inside the block
+  return (uint32_t)(q >> 3) * 64u + (uint32_t)(qq & 1) * 32u + (uint32_t)((qq >> 2) * 2 + ((qq >> 1) & 1)) * 4u;
+}
+__device__ __forceinline__ void xquad_store(uint32_t addr, uint32_t lo, uint32_t hi) {
+  sts_u32(addr, lo);
+  sts_u32(addr + 16u, hi);
 }
 
-// General activation load (several rows, or rows too long for the register path): raw payloads are parked in their B
-// slots, each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square,
+// General activation load (several rows, or rows too long for the register path): raw payloads go through shared
+// memory, each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square,
 // x*rsqrt -> bf16, * weight -> bf16.
-__device__ __noinline__ void stage_b_general(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
-                                             int K, int M, uint32_t ep_in, int pidx, uint32_t bbuf, uint32_t red, int s_log, int kbs,
-                                             uint32_t btile) {
+__device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
+                                            int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red) {
   const int Kq = K >> 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool norm = (flags & F_PRENORM) != 0;
 #pragma unroll 1
   for (int m = 0; m < M; ++m) {
     const LLWord* src = in + (size_t)m * ld;
+    const uint32_t xrow = xs + (uint32_t)m * (uint32_t)K * 2u;
     float ss = 0.f;
 #pragma unroll 1
     for (int q0 = 0; q0 < Kq; q0 += 2 * kConsumerThreads) {
@@ -463,7 +465,7 @@ __device__ __noinline__ void stage_b_general(const LaunchParams& p, uint32_t fla
       for (int i = 0; i < 2; ++i) {
         const int q = q0 + tid + i * kConsumerThreads;
         if (q < Kq) {
-          sts_u32x2(b_quad_addr(bbuf, q, m, s_log, kbs, btile), w[i].x, w[i].z);
+          xquad_store(xrow + xquad_off(q), w[i].x, w[i].z);
           const float x0 = bf_lo(w[i].x), x1 = bf_hi(w[i].x), x2 = bf_lo(w[i].z), x3 = bf_hi(w[i].z);
           ss += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
         }
@@ -474,8 +476,8 @@ __device__ __noinline__ void stage_b_general(const LaunchParams& p, uint32_t fla
       if (lane == 0) sts_f32(red + (uint32_t)(m * 16 + warp) * 4u, ss);
     }
   }
-  if (!norm) return;
   cbar_sync();
+  if (!norm) return;
 #pragma unroll 1
   for (int m = 0; m < M; ++m) {
     float tot = 0.f;
@@ -483,33 +485,24 @@ __device__ __noinline__ void stage_b_general(const LaunchParams& p, uint32_t fla
     for (int wi = 0; wi < kConsumerWarps; ++wi) tot += lds_f32(red + (uint32_t)(m * 16 + wi) * 4u);
     const float rs = rsqrtf(tot / (float)K + eps);
     const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
+    const uint32_t xrow = xs + (uint32_t)m * (uint32_t)K * 2u;
 #pragma unroll 1
     for (int q = tid; q < Kq; q += kConsumerThreads) {
       const uint2 gg = lds_u32x2(gam + (uint32_t)q * 8u);
-      const uint32_t a = b_quad_addr(bbuf, q, m, s_log, kbs, btile);
-      const uint2 v = lds_u32x2(a);
-      const uint32_t y0 = norm_pair(v.x, rs, gg.x), y1 = norm_pair(v.y, rs, gg.y);
-      sts_u32x2(a, y0, y1);
+      const uint32_t a = xrow + xquad_off(q);
+      const uint32_t y0 = norm_pair(lds_u32(a), rs, gg.x), y1 = norm_pair(lds_u32(a + 16u), rs, gg.y);
+      xquad_store(a, y0, y1);
       if (wr) reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID])[q] = make_uint2(y0, y1);
     }
   }
-  cbar_sync();  // protects red[] and the norm-weight slot against the next phase
+  cbar_sync();
 }
 
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-  uint32_t r0, r1, r2, r3;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-}
-
-// Consumer side of one GEMV phase.  `par` is the phase bit of the go / done barriers (flips once per tile on every warp
-// of a CTA that owns rows of the phase).
 template <bool PROF>
-__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& gcur, uint32_t& par, int pidx,
+__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, RingCur& gcur, int pidx,
                                                    uint32_t ep) {
   const Slab sb = get_slab(ph, p);
-  if (sb.g == 0) return;  // more CTAs than row groups (o_proj / down_proj of the small model): nothing to do here
+  if (sb.g == 0) return;  // more CTAs than row groups: nothing to do here (the producer skips the phase as well)
   const uint32_t flags = ph.flags;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int M = (flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows, row_off = 0;
@@ -519,11 +512,11 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const int ldin = p.ld[ph.in_buf];
   const LLWord* in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]) + (size_t)row_off * ldin;
   const bool norm = (flags & F_PRENORM) != 0;
-  const int Kq = K >> 2;  // 16-byte word pairs ("quads": elements 4q .. 4q+3) per row; thread tid owns quads tid and tid + 384
+  const int Kq = K >> 2;  // 16-byte word pairs ("quads": columns 4q .. 4q+3) per row; thread tid owns quads tid and tid + 384
   const bool fast = (M == 1) && (Kq <= 2 * kConsumerThreads);  // K <= 3072
   if (PROF) prof_mark(p, pidx, 0);
   if (PROF) prof_cta_time(p, pidx, 0);
-  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0, pidx, 300000 + M);
+  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0 && M * K * 2 <= p.xbuf_bytes, pidx, 300000 + M);
 
   // ---- issue the first poll of this thread's input words
   const bool have0 = tid < Kq, have1 = tid + kConsumerThreads < Kq;
@@ -536,10 +529,12 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
 
   // ---- everything that does not depend on the input: overlaps the round trip of the poll
   const Plan& pl = p.plans[ph.plan];
-  const int s_log = sb.s_log, kbs = sb.kbs, ro_shift = sb.ro_shift;
-  const int nb = b_rows(M, s_log);
-  const uint32_t btile = (uint32_t)nb * 128u;
-  FQ3_ASSERT((int)btile * kbs <= p.bbuf_bytes, pidx, 310000 + nb);
+  const int ro_shift = pl.ro_shift, wpg = pl.wpg, gpr = pl.gpr, spg = pl.spg, nch = pl.nch;
+  const int g8 = lane >> 2, t = lane & 3;
+  // this warp's unit: group (round * gpr + wgrp), k-part kp = blocks [ch0, ch1)
+  const int wgrp = small_div(warp, wpg), kp = warp - wgrp * wpg;
+  const bool w_act = wgrp < gpr;
+  int ch0 = small_div(kp * nch, wpg), ch1 = small_div((kp + 1) * nch, wpg);
   // norm weights arrive through the producer's stream (slot gcur of the small gamma ring)
   uint32_t gsrc = c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes + (uint32_t)tid * 8u;
   uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
@@ -547,42 +542,46 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   if (norm) gcur.advance(1, kGammaSlots);
   float eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
   float inv_k = pl.inv_k;
-  uint32_t bdst0 = b_quad_addr(c.bbuf, tid, 0, s_log, kbs, btile);
-  uint32_t bdst1 = b_quad_addr(c.bbuf, tid + kConsumerThreads, 0, s_log, kbs, btile);
-  // epilogue geometry of this thread (warps 0-3): TMEM lane = 32 * warp + lane = virtual row ((group * S + split) * 8 + r8)
-  const int S = 1 << s_log;
-  const int ml = lane >> 3, r8 = lane & 7;
-  const int mg = warp * 4 + ml;
-  const int rgl = mg >> s_log;                               // local row group inside the tile
-  const int hbase = (s_log >= 2) ? ((warp * 4) & (S - 1)) : 0;  // first split this warp's lanes hold
-  const int sel = (s_log >= 2) ? ml : ((s_log == 1) ? (ml & 1) : 0);
-  const int nq = (s_log >= 2) ? (S >> 2) : 1;               // partial sums per row after the in-warp reduction
-  const int qidx = (s_log >= 3) ? (warp & (nq - 1)) : 0;
-  const bool writer = (s_log >= 2) ? (ml == 0) : ((s_log == 1) ? ((ml & 1) == 0) : true);
-  const uint32_t part = c.scratch;                           // fp32 [M][128]
-  uint32_t pdst = part + (uint32_t)((rgl * 8 + r8) * nq + qidx) * 4u;
-  const uint32_t taddr = c.tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)hbase;
+  uint32_t xdst0 = c.xs + xquad_off(tid), xdst1 = c.xs + xquad_off(tid + kConsumerThreads);
+  // A rows: stream min(g8, M - 1) (rows beyond M repeat the last stream; their results are not read)
+  uint32_t xrow = c.xs + (uint32_t)min(g8, M - 1) * (uint32_t)K * 2u + (uint32_t)t * 16u;
+  const uint32_t lane_w = (uint32_t)lane * 16u;
+  uint32_t pdst = c.scratch + (uint32_t)(warp * 32 + lane) * 8u;  // this lane's partial word (two fp32)
   LLWord* out = reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]);
   const int ldout = p.ld[ph.out_buf];
   const int n_words = (int)ph.N >> ro_shift;  // packed output words of the whole matrix
-  const int f_wl = (M == 1) ? tid : tid / M, f_m = (M == 1) ? 0 : tid - f_wl * M;  // finishing thread: (word, row) of the first tile
-  const int tg0 = min(sb.tile_groups, sb.g);
-  int fin0 = ((tg0 * 8) >> ro_shift) * M;
-  const int word0 = (sb.grp0 * 8) >> ro_shift;
+  // finishing lane: stream g8, rows 2t, 2t+1 of the group -> plain: word 4 * group + t; SwiGLU: element 4 * group + t, the even lane
+  // of a pair publishes word 2 * group + t / 2
+  const bool f_lane = w_act && kp == 0 && g8 < M && (ro_shift == 1 || (t & 1) == 0);
+  const int f_sub = (ro_shift == 1) ? t : (t >> 1);
+  const int wpgrp = 8 >> ro_shift;  // words per group
+  int gi = wgrp;                     // group of round 0
+  int f_word = (sb.grp0 + gi) * wpgrp + f_sub;
   uint32_t res0 = 0u, bias0 = 0u;
-  LLWord* fout = out + (size_t)f_m * ldout + word0 + f_wl;
-  const bool f_act = (warp < kEpiWarps) && (tid < fin0) && (word0 + f_wl < n_words);
-  if (f_act) {
-    if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)f_m * p.ld[ph.res_buf] + word0 + f_wl).x;
+  const bool g_ok0 = w_act && gi < sb.g;
+  if (f_lane && g_ok0 && f_word < n_words) {
+    if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)g8 * p.ld[ph.res_buf] + f_word).x;
     if (flags & F_BIAS) {
       const bf16* bias = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-      bias0 = __ldg(reinterpret_cast<const uint32_t*>(bias) + word0 + f_wl);
+      bias0 = __ldg(reinterpret_cast<const uint32_t*>(bias) + f_word);
     }
   }
-  uint32_t fq = part + (uint32_t)((f_m * 128 + (f_wl << ro_shift) * nq)) * 4u;
-  pin(gsrc); pin(gfullb); pin(gemptyb); pin(eps); pin(inv_k); pin(bdst0); pin(bdst1); pin(fin0); pin(fout); pin(fq); pin(pdst);
+  // the first stage this warp reads: wait for it now (it landed long ago; a wait after the poll would sit on the critical path)
+  RingCur my = cur;
+  if (g_ok0 && sb.n_stages <= c.n_stages && sb.g <= gpr) {
+    my.advance(gi * spg + (ch0 >> 5), c.n_stages);
+    if (!mbar_try_wait_a(c.full + (uint32_t)my.slot * 8u, my.lap)) {
+      Spin spin;
+      while (!mbar_try_wait_a(c.full + (uint32_t)my.slot * 8u, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+    }
+  }
+  pin(gsrc); pin(gfullb); pin(gemptyb); pin(eps); pin(inv_k); pin(xdst0); pin(xdst1); pin(xrow); pin(pdst); pin(f_word); pin(ch0); pin(ch1);
+  // No barrier closes a GEMV phase, so a warp may arrive here while others still multiply the previous phase's activations
+  // or read its partial words / the attention scratch.  Phases with a norm meet at the sum-of-squares barrier before they
+  // write anything; the others meet here, in the shadow of the poll.
+  if (!(fast && norm)) cbar_sync();
 
-  // ---- wait for the input, normalise, stage it as the B operand
+  // ---- wait for the input, normalise, stage it in shared memory
   if (fast) {
     if (ep_in != 0) {
       unsigned tries = 0;
@@ -596,8 +595,9 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
     if (PROF) prof_mark(p, pidx, 7);
     if (PROF) prof_warp_time(p, pidx, 0);
     if (!norm) {
-      if (have0) sts_u32x2(bdst0, w0.x, w0.z);
-      if (have1) sts_u32x2(bdst1, w1.x, w1.z);
+      if (have0) xquad_store(xdst0, w0.x, w0.z);
+      if (have1) xquad_store(xdst1, w1.x, w1.z);
+      cbar_sync();
     } else {
       float ss;
       {  // absent pairs carry payload 0
@@ -628,127 +628,171 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       const bool wr = (flags & F_WRITE_NORMED) && blockIdx.x == 0;
       if (have0) {
         const uint32_t y0 = norm_pair(w0.x, rs, g0.x), y1 = norm_pair(w0.z, rs, g0.y);
-        sts_u32x2(bdst0, y0, y1);
+        xquad_store(xdst0, y0, y1);
         if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid] = make_uint2(y0, y1);
       }
       if (have1) {
         const uint32_t y0 = norm_pair(w1.x, rs, g1.x), y1 = norm_pair(w1.z, rs, g1.y);
-        sts_u32x2(bdst1, y0, y1);
+        xquad_store(xdst1, y0, y1);
         if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid + kConsumerThreads] = make_uint2(y0, y1);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(gemptyb);
-      // red[] is safe against the next norm phase: every warp passes the done barrier of this phase first
+      cbar_sync();  // xs complete; also protects red[] against the next phase
     }
   } else {
     if (norm && !mbar_try_wait_a(gfullb, glap)) {
       Spin spin;
       while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
     }
-    stage_b_general(p, flags, in, ldin, gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.bbuf, c.red, s_log, kbs, btile);
-    if (norm) {  // stage_b_general ends with a barrier after the last read of the norm weights
+    load_x_general(p, flags, in, ldin, gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.xs, c.red);
+    if (norm) {  // load_x_general ends with a barrier after the last read of the norm weights
       if (lane == 0) mbar_arrive_a(gemptyb);
     }
   }
   if (PROF) prof_mark(p, pidx, 1);
 
-  // ---- tiles: hand the B operand to the MMA warp, wait for the accumulator, reduce the splits, publish
-  int fin = fin0;
+  // ---- multiply, reduce the k-parts, publish
+  const bool one_pass = (sb.n_stages <= c.n_stages) && (sb.g <= gpr);  // every model shape: the phase fits in the ring, one round
+  const uint32_t lds_w = c.ring + lane_w;
+  // finish one unit: acc (stream g8, rows 2t, 2t+1 of group gi_) -> partial words -> epilogue -> publish
+  auto finish = [&](float y0, float y1, int gi_, bool first_round) {
+    if (wpg > 1) {
+      if (kp != 0) sts_f32x2(pdst, y0, y1);
+      group_bar_sync(2 + wgrp, wpg * 32);
+      if (kp == 0) {
 #pragma unroll 1
-  for (int t = 0; t < sb.n_tiles; ++t) {
-    const int tg = min(sb.tile_groups, sb.g - t * sb.tile_groups);
-    fence_async_smem();  // this thread's B stores (generic proxy) before the tensor core's reads (async proxy)
-    tc_fence_before();   // this thread's tcgen05.ld of the previous tile before the MMAs that overwrite the accumulator
-    __syncwarp();
-    if (lane == 0) mbar_arrive_a(c.go);
-    if (!mbar_try_wait_a(c.done, par)) {
-      Spin spin;
-      while (!mbar_try_wait_a(c.done, par)) spin.tick(p, DE_DONE_WAIT, pidx, t);
+        for (int k2 = 1; k2 < wpg; ++k2) {
+          const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
+          y0 += v.x; y1 += v.y;
+        }
+      }
     }
-    par ^= 1u;
-    if (PROF) prof_mark(p, pidx, 2);
-    if (warp < kEpiWarps) {
-      tc_fence_after();
-      const bool live = rgl < tg;
-#pragma unroll
-      for (int m = 0; m < kMaxRows; ++m) {
-        if (m < M) {
-          float v4[4];
-          tmem_ld4(taddr + (uint32_t)(m << s_log), v4);
-          float v = (sel == 0) ? v4[0] : ((sel == 1) ? v4[1] : ((sel == 2) ? v4[2] : v4[3]));
-          if (s_log >= 1) v += __shfl_xor_sync(0xffffffffu, v, 8);
-          if (s_log >= 2) v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (writer && live) sts_f32(pdst + (uint32_t)(m * 128) * 4u, v);
-        }
-      }
-      if (PROF) prof_mark(p, pidx, 10);
-      epi_bar_sync();
-      // finish: one thread per (output word, activation row) of this tile
-      if (tid < fin) {
-        if (t != 0) {
-          const int wl = tid / M, m = tid - wl * M;
-          const int w_first = ((sb.grp0 + t * sb.tile_groups) * 8) >> ro_shift;
-          fq = part + (uint32_t)(m * 128 + (wl << ro_shift) * nq) * 4u;
-          fout = out + (size_t)m * ldout + w_first + wl;
-        }
-#pragma unroll 1
-        for (int ft = tid;;) {
-          const int w_first = ((sb.grp0 + t * sb.tile_groups) * 8) >> ro_shift;
-          const int wl = ft / M, m = ft - wl * M;
-          const int wg = w_first + wl;
-          if (wg < n_words) {
-            if (t != 0 || ft != tid) {
-              if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)m * p.ld[ph.res_buf] + wg).x;
-              if (flags & F_BIAS) {
-                const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-                bias0 = __ldg(reinterpret_cast<const uint32_t*>(bp) + wg);
-              }
-            }
-            float y[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              if (r < (1 << ro_shift)) {
-                const uint32_t q = fq + (uint32_t)(r * nq) * 4u;
-                float s;
-                if (nq == 1) s = lds_f32(q);
-                else if (nq == 2) s = lds_f32(q) + lds_f32(q + 4u);
-                else { const float4 v = lds_f32x4(q); s = (v.x + v.y) + (v.z + v.w); }
-                y[r] = s;
-              }
-            }
-            float lo, hi;
-            if (flags & F_SWIGLU) {
-              lo = bf16r(bf16r(silu_f(bf16r(y[0]))) * bf16r(y[1]));
-              hi = bf16r(bf16r(silu_f(bf16r(y[2]))) * bf16r(y[3]));
-            } else {
-              lo = y[0]; hi = y[1];
-              if (flags & F_BIAS) { lo += bf_lo(bias0); hi += bf_hi(bias0); }
-              lo = bf16r(lo); hi = bf16r(hi);
-              if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
-            }
-            if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
-            if (PROF) prof_cta_time(p, pidx, 1);
-            ll_st(fout, pack_bf16x2(lo, hi), ep);
+    if (PROF && first_round) prof_mark(p, pidx, 10);
+    if (kp == 0) {
+      if (!first_round) {
+        f_word = (sb.grp0 + gi_) * wpgrp + f_sub;
+        if (f_lane && f_word < n_words) {
+          if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)g8 * p.ld[ph.res_buf] + f_word).x;
+          if (flags & F_BIAS) {
+            const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
+            bias0 = __ldg(reinterpret_cast<const uint32_t*>(bp) + f_word);
           }
-          ft += kEpiWarps * 32;
-          if (ft >= fin) break;
-          const int wl2 = ft / M, m2 = ft - wl2 * M;
-          fq = part + (uint32_t)(m2 * 128 + (wl2 << ro_shift) * nq) * 4u;
-          fout = out + (size_t)m2 * ldout + w_first + wl2;
         }
       }
-      if (t + 1 < sb.n_tiles) {
-        const int tgn = min(sb.tile_groups, sb.g - (t + 1) * sb.tile_groups);
-        fin = ((tgn * 8) >> ro_shift) * M;
-        epi_bar_sync();  // the next tile overwrites the partial sums
+      float lo, hi;
+      if (flags & F_SWIGLU) {
+        // (y0, y1) = (gate, up) of element 4 * group + t; the odd lane of a pair hands its element to the even one
+        const float e = bf16r(bf16r(silu_f(bf16r(y0))) * bf16r(y1));
+        lo = e;
+        hi = __shfl_down_sync(0xffffffffu, e, 1);
+      } else {
+        lo = y0; hi = y1;
+        if (flags & F_BIAS) { lo += bf_lo(bias0); hi += bf_hi(bias0); }
+        lo = bf16r(lo); hi = bf16r(hi);
+        if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
+      }
+      if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
+      if (PROF) prof_cta_time(p, pidx, 1);
+      if (f_lane && f_word < n_words) ll_st(out + (size_t)g8 * ldout + f_word, pack_bf16x2(lo, hi), ep);
+      if (PROF && first_round) prof_mark(p, pidx, 11);
+    }
+  };
+  // blocks [ch, ce) of one stage against the matching columns of the A rows; two accumulator chains
+  auto mma_span = [&](float (&acc)[4], float (&acc2)[4], uint32_t wa, uint32_t xa, int n) {
+#pragma unroll 1
+    for (; n >= 2; n -= 2) {
+      const uint4 wv0 = lds128(wa), xv0 = lds128(xa);
+      const uint4 wv1 = lds128(wa + kBlockBytes), xv1 = lds128(xa + 64u);
+      mma_bf16(acc, xv0.x, xv0.x, xv0.y, xv0.y, wv0.x, wv0.y);
+      mma_bf16(acc2, xv1.x, xv1.x, xv1.y, xv1.y, wv1.x, wv1.y);
+      mma_bf16(acc, xv0.z, xv0.z, xv0.w, xv0.w, wv0.z, wv0.w);
+      mma_bf16(acc2, xv1.z, xv1.z, xv1.w, xv1.w, wv1.z, wv1.w);
+      wa += 2 * kBlockBytes;
+      xa += 128u;
+    }
+    if (n) {
+      const uint4 wv0 = lds128(wa), xv0 = lds128(xa);
+      mma_bf16(acc, xv0.x, xv0.x, xv0.y, xv0.y, wv0.x, wv0.y);
+      mma_bf16(acc, xv0.z, xv0.z, xv0.w, xv0.w, wv0.z, wv0.w);
+    }
+  };
+  if (one_pass) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g_ok0) {
+      int ch = ch0;
+#pragma unroll 1
+      while (true) {
+        const int ce = min(ch1, (ch | (kStageChunks - 1)) + 1);  // end of this stage's blocks
+        if (PROF && ch == ch0) prof_mark(p, pidx, 8);
+        mma_span(acc, acc2, lds_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch & (kStageChunks - 1)) * kBlockBytes, xrow + (uint32_t)ch * 64u, ce - ch);
+        ch = ce;
+        if (ch >= ch1) break;
+        my.advance(1, c.n_stages);
+        const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
+        if (!mbar_try_wait_a(fb, my.lap)) {
+          Spin spin;
+          while (!mbar_try_wait_a(fb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+        }
+      }
+      if (PROF) prof_mark(p, pidx, 9);
+      finish(acc[0] + acc2[0], acc[1] + acc2[1], gi, true);
+    }
+    // hand the stages back after the output is on its way: every warp passes every stage (waits for the copy — the slot's
+    // previous use is then closed — and releases it)
+    RingCur wk = cur;
+#pragma unroll 1
+    for (int si = 0; si < sb.n_stages; ++si) {
+      const uint32_t fb = c.full + (uint32_t)wk.slot * 8u;
+      if (!mbar_try_wait_a(fb, wk.lap)) {
+        Spin spin;
+        while (!mbar_try_wait_a(fb, wk.lap)) spin.tick(p, DE_FULL_WAIT, pidx, wk.slot);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(c.empty + (uint32_t)wk.slot * 8u);
+      wk.advance(1, c.n_stages);
+    }
+  } else {
+    // generic shapes (more stages than the ring holds, or several rounds): every warp walks the stages in order, multiplies
+    // where a stage belongs to its unit, finishes a unit behind its last stage, and releases every stage as it passes
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    RingCur wk = cur;
+    bool first = true;
+#pragma unroll 1
+    for (int si = 0; si < sb.n_stages; ++si) {
+      const uint32_t fb = c.full + (uint32_t)wk.slot * 8u;
+      if (!mbar_try_wait_a(fb, wk.lap)) {
+        Spin spin;
+        while (!mbar_try_wait_a(fb, wk.lap)) spin.tick(p, DE_FULL_WAIT, pidx, wk.slot);
+      }
+      const int gs = small_div(si, spg), sg = si - gs * spg;
+      const int rs_ = small_div(gs, gpr);
+      bool fin_now = false;
+      if (w_act && gs - rs_ * gpr == wgrp) {
+        const int cb = max(ch0, sg * kStageChunks), ce = min(ch1, (sg + 1) * kStageChunks);
+        if (cb < ce) {
+          mma_span(acc, acc2, lds_w + (uint32_t)wk.slot * kStageBytes + (uint32_t)(cb & (kStageChunks - 1)) * kBlockBytes, xrow + (uint32_t)cb * 64u, ce - cb);
+          fin_now = (ce == ch1);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(c.empty + (uint32_t)wk.slot * 8u);
+      wk.advance(1, c.n_stages);
+      if (fin_now) {
+        finish(acc[0] + acc2[0], acc[1] + acc2[1], gs, first);
+        first = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[i] = 0.f; acc2[i] = 0.f; }
+        if (wpg > 1) group_bar_sync(2 + wgrp, wpg * 32);  // the next round overwrites the partial words
       }
     }
   }
+  cur.advance(sb.n_stages, c.n_stages);
   if (PROF) prof_mark(p, pidx, 3);
 }
 
-// Producer side of one GEMV phase: stream this CTA's tiles through the ring, one contiguous bulk copy per 16 KB stage
-// (one k-block of the tile image).  The phase's norm weights travel in the same stream.  Returns false when the
+// Producer side of one GEMV phase: stream this CTA's groups through the ring, one contiguous bulk copy per stage (up to
+// 16 KB = 1024 columns of one group's image).  The phase's norm weights travel in the same stream.  Returns false when the
 // consumers asked to stop (frame loop finished early).
 template <bool PROF>
 __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph, const LaunchParams& p, int* ctl, RingCur& cur, RingCur& gcur, uint32_t& issued,
@@ -756,9 +800,9 @@ __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph
   const Slab sb = get_slab(ph, p);
   if (sb.g == 0) return true;
   const int K = (int)ph.K;
-  // the image keeps a CTA's groups contiguous: group r of the matrix starts at byte r * 8 * K * 2
+  const uint32_t gbytes = (uint32_t)K * 16u;  // one group: 8 rows
   const unsigned char* W = ((ph.flags & F_ABSPTR) ? reinterpret_cast<const unsigned char*>(p.lin_W) : p.tiled + (size_t)ph.w_off * 16) +
-                           (size_t)sb.grp0 * 16u * (size_t)K;
+                           (size_t)sb.grp0 * gbytes;
   const uint64_t pol = (ph.flags & F_L2_KEEP) ? pol_keep : pol_stream;
   if (PROF && (int)blockIdx.x == p.prof_cta && pidx < 512) p.prof[(size_t)pidx * 16 + 4] = clock64();
   if (ph.flags & F_PRENORM) {
@@ -777,12 +821,10 @@ __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph
     ++gissued;
   }
 #pragma unroll 1
-  for (int t = 0; t < sb.n_tiles; ++t) {
-    const int tg = min(sb.tile_groups, sb.g - t * sb.tile_groups);
-    const uint32_t bytes = (uint32_t)(tg << sb.s_log) * 1024u;  // (group, split) pairs x one 8-row swizzle atom
-    const unsigned char* src = W + (size_t)t * sb.tile_groups * 16u * (size_t)K;
+  for (int gi = 0; gi < sb.g; ++gi) {
 #pragma unroll 1
-    for (int kb = 0; kb < sb.kbs; ++kb) {
+    for (uint32_t off = 0; off < gbytes; off += kStageBytes) {
+      const uint32_t bytes = min((uint32_t)kStageBytes, gbytes - off);
       const uint32_t fullb = c.full + (uint32_t)cur.slot * 8u, emptyb = c.empty + (uint32_t)cur.slot * 8u;
       Spin spin;
       while (!mbar_try_wait_a(emptyb, cur.lap ^ 1u)) {
@@ -792,67 +834,12 @@ __device__ __forceinline__ bool gemv_phase_produce(const Ctx& c, const Phase& ph
       }
       if (ld_volatile_shared_i32(ctl) < 0) return false;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(bytes) : "memory");
-      bulk_g2s_a(c.ring + (uint32_t)cur.slot * kStageBytes, src + (size_t)kb * bytes, bytes, fullb, pol);
+      bulk_g2s_a(c.ring + (uint32_t)cur.slot * kStageBytes, W + (size_t)gi * gbytes + off, bytes, fullb, pol);
       cur.advance(1, c.n_stages);
       ++issued;
     }
   }
   if (PROF && (int)blockIdx.x == p.prof_cta && pidx < 512) p.prof[(size_t)pidx * 16 + 5] = clock64();
-  return true;
-}
-
-// MMA side of one GEMV phase (one thread).  A tile = kbs stages of the ring; every stage is one k-block [128 x 64] of the
-// A operand (K-major, 128-byte swizzle, 8-row atoms 1024 bytes apart), multiplied against the matching k-block of the B
-// operand with four tcgen05.mma (k = 16 each).  tcgen05.commit hands a stage back to the producer when its MMAs have read
-// it, and signals the consumers when the whole tile has been accumulated.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  // K-major, SWIZZLE_128B: start address >> 4 | LBO (unused for swizzled K-major) = 1 | SBO = 1024 B (8 rows) | version 1 | layout 2
-  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ bool gemv_phase_mma(const Ctx& c, const Phase& ph, const LaunchParams& p, int* ctl, RingCur& cur, uint32_t& par, int pidx) {
-  const Slab sb = get_slab(ph, p);
-  if (sb.g == 0) return true;
-  const int M = phase_m(ph, p);
-  const int nb = b_rows(M, sb.s_log);
-  // instruction descriptor: D = F32, A = B = BF16, both K-major, N = nb, M = 128
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-  const uint32_t btile = (uint32_t)nb * 128u;
-#pragma unroll 1
-  for (int t = 0; t < sb.n_tiles; ++t) {
-    {
-      Spin spin;
-      while (!mbar_try_wait_a(c.go, par)) {
-        if (ld_volatile_shared_i32(ctl) < 0) return false;
-        spin.tick(p, DE_GO_WAIT, pidx, t);
-      }
-    }
-    tc_fence_after();
-#pragma unroll 1
-    for (int kb = 0; kb < sb.kbs; ++kb) {
-      const uint32_t fullb = c.full + (uint32_t)cur.slot * 8u;
-      if (!mbar_try_wait_a(fullb, cur.lap)) {
-        Spin spin;
-        while (!mbar_try_wait_a(fullb, cur.lap)) spin.tick(p, DE_FULL_WAIT, pidx, cur.slot);
-      }
-      const uint32_t a0 = c.ring + (uint32_t)cur.slot * kStageBytes, b0 = c.bbuf + (uint32_t)kb * btile;
-#pragma unroll
-      for (int kk = 0; kk < kBlockK / 16; ++kk) {
-        const uint64_t da = umma_desc_sw128(a0 + kk * 32), db = umma_desc_sw128(b0 + kk * 32);
-        const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(c.tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc)
-            : "memory");
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.empty + (uint32_t)cur.slot * 8u) : "memory");
-      cur.advance(1, c.n_stages);
-    }
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c.done) : "memory");
-    par ^= 1u;
-  }
   return true;
 }
 
@@ -2052,45 +2039,29 @@ template <bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem sm = carve_smem(smem_raw, p);
-  Ctx c = make_ctx(smem_raw, p);
+  const Ctx c = make_ctx(smem_raw, p);
   const int tid = threadIdx.x;
-  const int warp_id = tid >> 5;
 
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 1);  // tcgen05.commit of the stage's MMAs
+      mbar_init(&sm.empty[s], kConsumerWarps);  // every consumer warp passes every stage
     }
     for (int s = 0; s < kGammaSlots; ++s) {
       mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGFullOffset) + s, 1);
       mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGEmptyOffset) + s, kConsumerWarps);
     }
-    mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGoOffset), kConsumerWarps);
-    mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kDoneOffset), 1);
     sm.ctl[0] = 0;
     fence_barrier_init();
   }
-  if (warp_id == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_raw + kTmemSlotOffset)), "n"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
   {
-    // The MMA always reads 128 rows of a stage and 16-row multiples of the B operand; rows that no copy / no thread wrote
-    // only reach accumulator entries nobody reads, but they must be finite — start from zeros.
-    uint4* r = reinterpret_cast<uint4*>(sm.bbuf);
-    const int n16 = (p.bbuf_bytes + p.n_stages * kStageBytes) / 16;  // the ring follows the B buffer
-    for (int i = tid; i < n16; i += kThreads) r[i] = make_uint4(0u, 0u, 0u, 0u);
-    fence_async_smem();  // generic-proxy zeros before async-proxy (TMA) writes
     const uint4* src = reinterpret_cast<const uint4*>(p.prog);
     uint4* dst = reinterpret_cast<uint4*>(sm.prog);
     for (int i = tid; i < p.n_phases * 2; i += kThreads) dst[i] = __ldg(src + i);
   }
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  c.tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + kTmemSlotOffset);
 
-  if (warp_id == kProducerWarp) {
+  if (tid >= kConsumerThreads) {
     // ------------------------------ producer warp (one thread) ------------------------------
     if ((tid & 31) == 0) {
       const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_keep_fraction();
@@ -2118,98 +2089,73 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
         mbar_wait(reinterpret_cast<uint64_t*>(smem_raw + kGFullOffset) + d.slot, d.lap, p, DE_FULL_WAIT, -4);
       }
     }
-  } else if (warp_id == kMmaWarp) {
-    // ------------------------------ MMA warp (one thread) ------------------------------
-    if ((tid & 31) == 0) {
-      RingCur cur{0, 0u};
-      uint32_t par = 0u;
-      bool ok = true;
-      for (int iter = 0; iter < p.n_iters && ok; ++iter) {
-        for (int i = 0; i < p.n_phases && ok; ++i) {
-          const Phase ph = load_phase(sm.prog, i);
-          if (ph.type == PH_GEMV) ok = gemv_phase_mma(c, ph, p, sm.ctl, cur, par, i);
-        }
-      }
-    }
-  } else {
-    // -------------------------------- consumer warps --------------------------------
-    RingCur gcur{0, 0u};
-    uint32_t par = 0u;
-    int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
-    int* frame_done = sm.ctl + 12;  // [4]
-    for (int iter = 0; iter < p.n_iters; ++iter) {
-      const uint32_t ep0 = p.epoch_base + (uint32_t)iter * (uint32_t)p.n_phases;
-      if (p.mode == MODE_FRAMES || p.mode == MODE_TALKER_STEP) {
-        // per-stream frame state: from the stream state at launch, afterwards from the sampler's control record
-        if (tid < p.n_rows) {
-          const StreamState* st = p.st + p.stream0 + tid;
-          int done, pos;
-          if (iter == 0) {
-            done = __ldcg(&st->done);
-            pos = __ldcg(&st->position);
-            int* sconst = reinterpret_cast<int*>(smem_raw + kStreamConstOffset);
-            sconst[tid] = __ldcg(&st->n_pad);
-            sconst[4 + tid] = __ldcg(&st->rope_delta);
-          } else {
-            done = (int)ll_wait(&st->ctl[0], ep0, p, -2);
-            pos = (int)ll_wait(&st->ctl[1], ep0, p, -2);
-          }
-          frame_pos[tid] = pos;
-          frame_done[tid] = done;
-        }
-        cbar_sync();
-        if (p.mode == MODE_FRAMES && iter > 0) {
-          int all_done = 1;
-          for (int b = 0; b < p.n_rows; ++b) all_done &= (frame_done[b] != 0);
-          if (all_done) {
-            if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], -1);  // tells the producer and the MMA warp (which wait ahead) to stop
-            break;
-          }
-        }
-      }
-      for (int i = 0; i < p.n_phases; ++i) {
-        const Phase ph = load_phase(sm.prog, i);
-        const uint32_t ep = ep0 + (uint32_t)i + 1u;
-        switch (ph.type) {
-          case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, gcur, par, i, ep); break;
-          case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
-          case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
-          default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
-        }
-      }
-    }
-    if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], -1);
+    return;
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp_id == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(kTmemCols) : "memory");
+
+  // -------------------------------- consumer warps --------------------------------
+  RingCur cur{0, 0u}, gcur{0, 0u};
+  int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
+  int* frame_done = sm.ctl + 12;  // [4]
+  for (int iter = 0; iter < p.n_iters; ++iter) {
+    const uint32_t ep0 = p.epoch_base + (uint32_t)iter * (uint32_t)p.n_phases;
+    if (p.mode == MODE_FRAMES || p.mode == MODE_TALKER_STEP) {
+      // per-stream frame state: from the stream state at launch, afterwards from the sampler's control record
+      if (tid < p.n_rows) {
+        const StreamState* st = p.st + p.stream0 + tid;
+        int done, pos;
+        if (iter == 0) {
+          done = __ldcg(&st->done);
+          pos = __ldcg(&st->position);
+          int* sconst = reinterpret_cast<int*>(smem_raw + kStreamConstOffset);
+          sconst[tid] = __ldcg(&st->n_pad);
+          sconst[4 + tid] = __ldcg(&st->rope_delta);
+        } else {
+          done = (int)ll_wait(&st->ctl[0], ep0, p, -2);
+          pos = (int)ll_wait(&st->ctl[1], ep0, p, -2);
+        }
+        frame_pos[tid] = pos;
+        frame_done[tid] = done;
+      }
+      cbar_sync();
+      if (p.mode == MODE_FRAMES && iter > 0) {
+        int all_done = 1;
+        for (int b = 0; b < p.n_rows; ++b) all_done &= (frame_done[b] != 0);
+        if (all_done) {
+          if (tid == 0) st_volatile_shared_i32(&sm.ctl[0], -1);  // tells the producer (which prefetches across frames) to stop
+          break;
+        }
+      }
+    }
+    for (int i = 0; i < p.n_phases; ++i) {
+      const Phase ph = load_phase(sm.prog, i);
+      const uint32_t ep = ep0 + (uint32_t)i + 1u;
+      switch (ph.type) {
+        case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, cur, gcur, i, ep); break;
+        case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
+        case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
+        default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
+      }
+    }
+  }
 }
 
-// Tiled image of one GEMV matrix (fq3_common.cuh: Plan).  W is row-major [N][K]; block c writes the slab of CTA c: its
-// 8-row groups, M-tile by M-tile, k-block by k-block, every (group, split) pair as one 1024-byte swizzle atom (row r8 is a
-// 128-byte line whose 16-byte chunk cc sits at position cc ^ r8).  Rows beyond N are zeros.
-__global__ void fq3_tile_weights_kernel(const bf16* __restrict__ W, uint4* __restrict__ out, int N, int K, Plan pl) {
-  const int cta = blockIdx.x;
-  const int g = pl.g_base + (cta < pl.g_rem ? 1 : 0);
-  const int grp0 = cta * pl.g_base + min(cta, pl.g_rem);
-  const int S = 1 << pl.s_log, Kh = K >> pl.s_log;
-  const long chunks = (long)g * K;  // 16-byte chunks of the slab (8 rows x K / 8 per group)
-  const long tile_chunks = (long)pl.tile_groups * K;
-  uint4* dst = out + (long)grp0 * K;
-  for (long idx = threadIdx.x; idx < chunks; idx += blockDim.x) {
-    const int t = (int)(idx / tile_chunks);
-    const long rem = idx - (long)t * tile_chunks;
-    const int tg = min(pl.tile_groups, g - t * pl.tile_groups);
-    const int per_kb = tg * S * 64;
-    const int kb = (int)(rem / per_kb);
-    const int r2 = (int)(rem - (long)kb * per_kb);
-    const int mgl = r2 >> 6, r3 = r2 & 63, r8 = r3 >> 3, pos = r3 & 7, cc = pos ^ r8;
-    const int rgl = mgl >> pl.s_log, h = mgl & (S - 1);
-    const int row = (grp0 + t * pl.tile_groups + rgl) * 8 + r8;
-    const int col = h * Kh + kb * kBlockK + cc * 8;
+// Fragment image of one GEMV matrix (fq3_common.cuh: Plan).  W is row-major [N][K]; the image keeps groups of 8 rows
+// contiguous (8 * K * 2 bytes each, in row order), a group being K / 32 blocks of 512 bytes: lane (r8, t) of a warp reads
+// bytes [(4 * r8 + t) * 16, +16) of a block = columns {2t, 2t+1 | 8+2t, 9+2t | 16+2t, 17+2t | 24+2t, 25+2t} of row r8 —
+// the B fragments (b0, b1) of two consecutive mma.m16n8k16 k-steps.  Rows beyond N are zeros.
+__global__ void fq3_tile_weights_kernel(const bf16* __restrict__ W, uint4* __restrict__ out, int N, int K) {
+  const long pieces = (long)((N + 7) / 8) * K;  // 16-byte pieces: K per group
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < pieces; idx += (long)gridDim.x * blockDim.x) {
+    const long grp = idx / K;
+    const int pc = (int)(idx - grp * K);
+    const int ch = pc >> 5, ln = pc & 31, r8 = ln >> 2, t = ln & 3;
+    const long row = grp * 8 + r8;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row < N) v = *reinterpret_cast<const uint4*>(W + (size_t)row * K + col);
-    dst[idx] = v;
+    if (row < N) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(W + (size_t)row * K + ch * kChunkK) + t;
+      v = make_uint4(__ldg(src), __ldg(src + 4), __ldg(src + 8), __ldg(src + 12));
+    }
+    out[idx] = v;
   }
 }
 
