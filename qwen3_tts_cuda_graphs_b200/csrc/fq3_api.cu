@@ -320,6 +320,19 @@ int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t 
   p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
   if (p.n_stages < 2) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
   const size_t smem = (size_t)fixed + (size_t)p.n_stages * kStageBytes;
+  // A round of a GEMV phase (gpr groups x spg stages) must fit in the ring (kernel: gemv_phase_consume).  Shapes that do not
+  // (1.7B gate/up: 12 groups x 2 stages per CTA) take fewer groups per round and more warps per group.
+  for (int i = 0; i < p.n_phases; ++i) {
+    const Phase& ph = prog_host[i];
+    if (ph.type != PH_GEMV) continue;
+    Plan& pl = p.plans[ph.plan];
+    if (pl.spg > p.n_stages) return fail(FQ3_E_UNSUPPORTED, "K too large for the weight ring");
+    const int g_max = pl.g_base + (pl.g_rem ? 1 : 0);
+    if (std::min(pl.gpr, g_max) * pl.spg > p.n_stages) {
+      pl.gpr = p.n_stages / pl.spg;
+      pl.wpg = std::max(1, std::min(kConsumerWarps / pl.gpr, pl.nch));
+    }
+  }
   const uint64_t span = (uint64_t)p.n_iters * (uint64_t)p.n_phases + 2;
   if ((uint64_t)e->epoch + span >= 0xFFFFFFF0ull) return fail(FQ3_E_INVALID, "LL epochs were not reserved for this launch");
   p.epoch_base = e->epoch;
@@ -642,7 +655,15 @@ int fq3_set_loop_state(fq3_engine* e, int idx, int token, const void* past_hidde
   return 0;
 }
 
-static int prefill_rows(const fq3_engine* e) { return kMaxRows; }
+// rows of a prompt one launch of the prefill program takes: bounded by the activation staging buffer next to a ring of at
+// least six stages
+static int prefill_rows(const fq3_engine* e) {
+  const long fixed = kHeaderBytes + kScratchBytes + (long)round_up((size_t)e->n_prefill_ph * sizeof(Phase), 1024) +
+                     (long)kGammaSlots * (long)round_up((size_t)e->tk.d.hidden * 2, 1024);
+  const long spg_max = ((long)e->tk.kmax() * 16 + kStageBytes - 1) / kStageBytes;
+  const long avail = (long)e->smem_max - fixed - std::max(6L, spg_max + 1) * kStageBytes;
+  return (int)std::max<long>(1, std::min<long>(avail / ((long)e->tk.kmax() * 2), kMaxRows));
+}
 
 // rows [start, T) of the prompt go through the persistent kernel; the K/V rows of [0, start) must already be in the cache
 static int prefill_impl(fq3_engine* e, int idx, const void* embeds_from_start, int T, int start, int n_left_pad, const fq3_policy* policy,

@@ -417,9 +417,14 @@ __device__ __forceinline__ uint32_t norm_pair(uint32_t x, float rs, uint32_t g) 
 // Shared-memory copy of an activation row, in the order the A fragments want it: a 32-column block is 64 bytes, lane t's
 // 16 bytes hold columns {2t, 2t+1 | 8+2t, 9+2t | 16+2t, 17+2t | 24+2t, 25+2t} (= a0, a2 of k-step 0, a0, a2 of k-step 1).
 // A quad q (columns 4q .. 4q+3, the two LL words a thread polls with one request) lands in two 4-byte slots 16 bytes apart.
+// (Every shared-memory load instruction costs a pass per quarter-warp whether its lanes are predicated off or read the same
+// address, so one 16-byte load per block is the cheapest way to fetch a stream's fragments; storing the row in both k-step
+// orders to save the register moves below was measured and is slower: profiles/r02b_gemv_variants.log.)
+constexpr uint32_t kXBlock = 64;
+__device__ __forceinline__ uint32_t xrow_bytes(int K) { return (uint32_t)K * 2u; }
 __device__ __forceinline__ uint32_t xquad_off(int q) {
   const int qq = q & 7;  // quad inside the block
-  return (uint32_t)(q >> 3) * 64u + (uint32_t)(qq & 1) * 32u + (uint32_t)((qq >> 2) * 2 + ((qq >> 1) & 1)) * 4u;
+  return (uint32_t)(q >> 3) * kXBlock + (uint32_t)(qq & 1) * 32u + (uint32_t)((qq >> 2) * 2 + ((qq >> 1) & 1)) * 4u;
 }
 __device__ __forceinline__ void xquad_store(uint32_t addr, uint32_t lo, uint32_t hi) {
   sts_u32(addr, lo);
@@ -437,7 +442,7 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
 #pragma unroll 1
   for (int m = 0; m < M; ++m) {
     const LLWord* src = in + (size_t)m * ld;
-    const uint32_t xrow = xs + (uint32_t)m * (uint32_t)K * 2u;
+    const uint32_t xrow = xs + (uint32_t)m * xrow_bytes(K);
     float ss = 0.f;
 #pragma unroll 1
     for (int q0 = 0; q0 < Kq; q0 += 2 * kConsumerThreads) {
@@ -485,7 +490,7 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
     for (int wi = 0; wi < kConsumerWarps; ++wi) tot += lds_f32(red + (uint32_t)(m * 16 + wi) * 4u);
     const float rs = rsqrtf(tot / (float)K + eps);
     const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
-    const uint32_t xrow = xs + (uint32_t)m * (uint32_t)K * 2u;
+    const uint32_t xrow = xs + (uint32_t)m * xrow_bytes(K);
 #pragma unroll 1
     for (int q = tid; q < Kq; q += kConsumerThreads) {
       const uint2 gg = lds_u32x2(gam + (uint32_t)q * 8u);
@@ -544,7 +549,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   float inv_k = pl.inv_k;
   uint32_t xdst0 = c.xs + xquad_off(tid), xdst1 = c.xs + xquad_off(tid + kConsumerThreads);
   // A rows: stream min(g8, M - 1) (rows beyond M repeat the last stream; their results are not read)
-  uint32_t xrow = c.xs + (uint32_t)min(g8, M - 1) * (uint32_t)K * 2u + (uint32_t)t * 16u;
+  uint32_t xrow = c.xs + (uint32_t)min(g8, M - 1) * xrow_bytes(K) + (uint32_t)t * 16u;
   const uint32_t lane_w = (uint32_t)lane * 16u;
   uint32_t pdst = c.scratch + (uint32_t)(warp * 32 + lane) * 8u;  // this lane's partial word (two fp32)
   LLWord* out = reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]);
@@ -568,14 +573,30 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   }
   // the first stage this warp reads: wait for it now (it landed long ago; a wait after the poll would sit on the critical path)
   RingCur my = cur;
-  if (g_ok0 && sb.n_stages <= c.n_stages && sb.g <= gpr) {
-    my.advance(gi * spg + (ch0 >> 5), c.n_stages);
+  const bool pre_ok = g_ok0;  // a round never takes more stages than the ring has slots (fq3_api.cu: launch), so the stage's
+                              // slot was handed back by an earlier phase and its copy needs nothing from this one
+  if (g_ok0) my.advance(gi * spg + (ch0 >> 5), c.n_stages);
+  if (pre_ok) {
     if (!mbar_try_wait_a(c.full + (uint32_t)my.slot * 8u, my.lap)) {
       Spin spin;
       while (!mbar_try_wait_a(c.full + (uint32_t)my.slot * 8u, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
     }
   }
-  pin(gsrc); pin(gfullb); pin(gemptyb); pin(eps); pin(inv_k); pin(xdst0); pin(xdst1); pin(xrow); pin(pdst); pin(f_word); pin(ch0); pin(ch1);
+  int n_rounds = small_div(sb.g + gpr - 1, gpr);  // 1 for every shape of the 0.6B model
+  uint32_t wa0 = c.ring + lane_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch0 & (kStageChunks - 1)) * kBlockBytes;
+  uint32_t xa0 = xrow + (uint32_t)ch0 * kXBlock;
+  // the norm weights were queued by the producer long ago as well
+  uint2 g0 = make_uint2(0u, 0u), g1 = g0;
+  if (fast && norm) {
+    if (!mbar_try_wait_a(gfullb, glap)) {
+      Spin spin;
+      while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
+    }
+    if (have0) g0 = lds_u32x2(gsrc);
+    if (have1) g1 = lds_u32x2(gsrc + kConsumerThreads * 8);
+  }
+  pin(gemptyb); pin(eps); pin(inv_k); pin(xdst0); pin(xdst1); pin(pdst); pin(f_word); pin(ch0); pin(ch1); pin(wa0); pin(xa0); pin(n_rounds);
+  pin(g0.x); pin(g0.y); pin(g1.x); pin(g1.y);
   // No barrier closes a GEMV phase, so a warp may arrive here while others still multiply the previous phase's activations
   // or read its partial words / the attention scratch.  Phases with a norm meet at the sum-of-squares barrier before they
   // write anything; the others meet here, in the shadow of the poll.
@@ -607,14 +628,6 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       }
       ss = warp_sum(ss);
       if (lane == 0) sts_f32(c.red + (uint32_t)warp * 4u, ss);
-      // the norm weights were queued by the producer long ago: read them while the barrier gathers the warps
-      if (!mbar_try_wait_a(gfullb, glap)) {
-        Spin spin;
-        while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
-      }
-      uint2 g0 = make_uint2(0u, 0u), g1 = g0;
-      if (have0) g0 = lds_u32x2(gsrc);
-      if (have1) g1 = lds_u32x2(gsrc + kConsumerThreads * 8);
       if (PROF) prof_mark(p, pidx, 15);
       cbar_sync();
       if (PROF) prof_mark(p, pidx, 14);
@@ -652,19 +665,42 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   }
   if (PROF) prof_mark(p, pidx, 1);
 
-  // ---- multiply, reduce the k-parts, publish
-  const bool one_pass = (sb.n_stages <= c.n_stages) && (sb.g <= gpr);  // every model shape: the phase fits in the ring, one round
-  const uint32_t lds_w = c.ring + lane_w;
+  // ---- multiply, reduce the k-parts, publish, hand the group's stages back
   // finish one unit: acc (stream g8, rows 2t, 2t+1 of group gi_) -> partial words -> epilogue -> publish
   auto finish = [&](float y0, float y1, int gi_, bool first_round) {
     if (wpg > 1) {
       if (kp != 0) sts_f32x2(pdst, y0, y1);
       group_bar_sync(2 + wgrp, wpg * 32);
       if (kp == 0) {
+        if (wpg <= 4) {
+          // few parts: every lane adds the partial words of its own (stream, word) in part order
+#pragma unroll
+          for (int k2 = 1; k2 < 4; ++k2) {
+            if (k2 < wpg) {
+              const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
+              y0 += v.x; y1 += v.y;
+            }
+          }
+        } else if (M == 1) {
+          // many parts, one stream: lane (g8, t) adds the parts g8, g8 + 8 of word t, three shuffles add the eight slices in
+          // a fixed order (the A rows of a single stream are copies: every lane's own accumulator equals lane t's)
+          float s0 = 0.f, s1 = 0.f;
+          const uint32_t q0 = c.scratch + (uint32_t)(warp * 32 + t) * 8u;
+          if (g8 != 0 && g8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)g8 * 256u); s0 = v.x; s1 = v.y; }
+          if (g8 + 8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)(g8 + 8) * 256u); s0 += v.x; s1 += v.y; }
+          if (g8 == 0) { s0 += y0; s1 += y1; }
+#pragma unroll
+          for (int o = 4; o <= 16; o <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          }
+          y0 = s0; y1 = s1;
+        } else {
 #pragma unroll 1
-        for (int k2 = 1; k2 < wpg; ++k2) {
-          const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
-          y0 += v.x; y1 += v.y;
+          for (int k2 = 1; k2 < wpg; ++k2) {
+            const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
+            y0 += v.x; y1 += v.y;
+          }
         }
       }
     }
@@ -696,96 +732,73 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       if (PROF) prof_cta_time(p, pidx, 1);
       if (f_lane && f_word < n_words) ll_st(out + (size_t)g8 * ldout + f_word, pack_bf16x2(lo, hi), ep);
       if (PROF && first_round) prof_mark(p, pidx, 11);
-    }
-  };
-  // blocks [ch, ce) of one stage against the matching columns of the A rows; two accumulator chains
-  auto mma_span = [&](float (&acc)[4], float (&acc2)[4], uint32_t wa, uint32_t xa, int n) {
-#pragma unroll 1
-    for (; n >= 2; n -= 2) {
-      const uint4 wv0 = lds128(wa), xv0 = lds128(xa);
-      const uint4 wv1 = lds128(wa + kBlockBytes), xv1 = lds128(xa + 64u);
-      mma_bf16(acc, xv0.x, xv0.x, xv0.y, xv0.y, wv0.x, wv0.y);
-      mma_bf16(acc2, xv1.x, xv1.x, xv1.y, xv1.y, wv1.x, wv1.y);
-      mma_bf16(acc, xv0.z, xv0.z, xv0.w, xv0.w, wv0.z, wv0.w);
-      mma_bf16(acc2, xv1.z, xv1.z, xv1.w, xv1.w, wv1.z, wv1.w);
-      wa += 2 * kBlockBytes;
-      xa += 128u;
-    }
-    if (n) {
-      const uint4 wv0 = lds128(wa), xv0 = lds128(xa);
-      mma_bf16(acc, xv0.x, xv0.x, xv0.y, xv0.y, wv0.x, wv0.y);
-      mma_bf16(acc, xv0.z, xv0.z, xv0.w, xv0.w, wv0.z, wv0.w);
-    }
-  };
-  if (one_pass) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
-    if (g_ok0) {
-      int ch = ch0;
-#pragma unroll 1
-      while (true) {
-        const int ce = min(ch1, (ch | (kStageChunks - 1)) + 1);  // end of this stage's blocks
-        if (PROF && ch == ch0) prof_mark(p, pidx, 8);
-        mma_span(acc, acc2, lds_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch & (kStageChunks - 1)) * kBlockBytes, xrow + (uint32_t)ch * 64u, ce - ch);
-        ch = ce;
-        if (ch >= ch1) break;
-        my.advance(1, c.n_stages);
-        const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
-        if (!mbar_try_wait_a(fb, my.lap)) {
-          Spin spin;
-          while (!mbar_try_wait_a(fb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+      // every warp of the group has finished reading the group's stages (its k loop lies in front of the group barrier):
+      // the group's first warp hands them back, one arrival per stage
+      __syncwarp();
+      if (lane == 0) {
+        RingCur rel = cur;
+        rel.advance(gi_ * spg, c.n_stages);
+        for (int s2 = 0; s2 < spg; ++s2) {
+          mbar_arrive_a(c.empty + (uint32_t)rel.slot * 8u);
+          rel.advance(1, c.n_stages);
         }
       }
-      if (PROF) prof_mark(p, pidx, 9);
-      finish(acc[0] + acc2[0], acc[1] + acc2[1], gi, true);
     }
-    // hand the stages back after the output is on its way: every warp passes every stage (waits for the copy — the slot's
-    // previous use is then closed — and releases it)
-    RingCur wk = cur;
+  };
 #pragma unroll 1
-    for (int si = 0; si < sb.n_stages; ++si) {
-      const uint32_t fb = c.full + (uint32_t)wk.slot * 8u;
-      if (!mbar_try_wait_a(fb, wk.lap)) {
-        Spin spin;
-        while (!mbar_try_wait_a(fb, wk.lap)) spin.tick(p, DE_FULL_WAIT, pidx, wk.slot);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(c.empty + (uint32_t)wk.slot * 8u);
-      wk.advance(1, c.n_stages);
+  for (int r = 0; r < n_rounds; ++r) {
+    // A round re-uses the ring slots of the round before.  mbarrier phases only tell adjacent uses of a slot apart, so
+    // nobody may wait for a slot's next use before all readers of the current one are through: rounds are separated by a
+    // block barrier (it also protects the partial words).
+    if (r != 0) cbar_sync();
+    gi = r * gpr + wgrp;
+    if (!(w_act && gi < sb.g)) continue;  // (all warps of a group skip together)
+    if (r != 0) {
+      my = cur;
+      my.advance(gi * spg + (ch0 >> 5), c.n_stages);
+      const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
+      Spin spin;
+      while (!mbar_try_wait_a(fb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+      wa0 = c.ring + lane_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch0 & (kStageChunks - 1)) * kBlockBytes;
     }
-  } else {
-    // generic shapes (more stages than the ring holds, or several rounds): every warp walks the stages in order, multiplies
-    // where a stage belongs to its unit, finishes a unit behind its last stage, and releases every stage as it passes
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
-    RingCur wk = cur;
-    bool first = true;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};  // two accumulator chains (k-step 0 / 1 of a block)
+    int ch = ch0;
+    uint32_t wa = wa0, xa = xa0;
+    if (PROF && r == 0) prof_mark(p, pidx, 8);
+    // Software-pipelined: the loads of block i + 1 are in flight while block i is multiplied.
+    uint4 wv = lds128(wa), xv = lds128(xa);
 #pragma unroll 1
-    for (int si = 0; si < sb.n_stages; ++si) {
-      const uint32_t fb = c.full + (uint32_t)wk.slot * 8u;
-      if (!mbar_try_wait_a(fb, wk.lap)) {
+    while (true) {
+      const int ce = min(ch1, (ch | (kStageChunks - 1)) + 1);  // end of this stage's blocks
+#pragma unroll 2
+      for (int n = ce - ch - 1; n > 0; --n) {
+        wa += kBlockBytes;
+        xa += kXBlock;
+        const uint4 wn = lds128(wa), xn = lds128(xa);
+        mma_bf16(acc, xv.x, xv.x, xv.y, xv.y, wv.x, wv.y);
+        mma_bf16(acc2, xv.z, xv.z, xv.w, xv.w, wv.z, wv.w);
+        wv = wn; xv = xn;
+      }
+      ch = ce;
+      if (ch >= ch1) break;
+      // the unit goes on in the next stage of the group
+      my.advance(1, c.n_stages);
+      const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
+      if (!mbar_try_wait_a(fb, my.lap)) {
         Spin spin;
-        while (!mbar_try_wait_a(fb, wk.lap)) spin.tick(p, DE_FULL_WAIT, pidx, wk.slot);
+        while (!mbar_try_wait_a(fb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
       }
-      const int gs = small_div(si, spg), sg = si - gs * spg;
-      const int rs_ = small_div(gs, gpr);
-      bool fin_now = false;
-      if (w_act && gs - rs_ * gpr == wgrp) {
-        const int cb = max(ch0, sg * kStageChunks), ce = min(ch1, (sg + 1) * kStageChunks);
-        if (cb < ce) {
-          mma_span(acc, acc2, lds_w + (uint32_t)wk.slot * kStageBytes + (uint32_t)(cb & (kStageChunks - 1)) * kBlockBytes, xrow + (uint32_t)cb * 64u, ce - cb);
-          fin_now = (ce == ch1);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(c.empty + (uint32_t)wk.slot * 8u);
-      wk.advance(1, c.n_stages);
-      if (fin_now) {
-        finish(acc[0] + acc2[0], acc[1] + acc2[1], gs, first);
-        first = false;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { acc[i] = 0.f; acc2[i] = 0.f; }
-        if (wpg > 1) group_bar_sync(2 + wgrp, wpg * 32);  // the next round overwrites the partial words
-      }
+      wa = c.ring + lane_w + (uint32_t)my.slot * kStageBytes;
+      xa += kXBlock;
+      const uint4 wn = lds128(wa), xn = lds128(xa);
+      mma_bf16(acc, xv.x, xv.x, xv.y, xv.y, wv.x, wv.y);
+      mma_bf16(acc2, xv.z, xv.z, xv.w, xv.w, wv.z, wv.w);
+      wv = wn; xv = xn;
     }
+    mma_bf16(acc, xv.x, xv.x, xv.y, xv.y, wv.x, wv.y);
+    mma_bf16(acc2, xv.z, xv.z, xv.w, xv.w, wv.z, wv.w);
+    if (PROF && r == 0) prof_mark(p, pidx, 9);
+    finish(acc[0] + acc2[0], acc[1] + acc2[1], gi, r == 0);
   }
   cur.advance(sb.n_stages, c.n_stages);
   if (PROF) prof_mark(p, pidx, 3);
@@ -2045,7 +2058,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
   if (tid == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], kConsumerWarps);  // every consumer warp passes every stage
+      mbar_init(&sm.empty[s], 1);  // the first warp of the stage's group, behind the group barrier
     }
     for (int s = 0; s < kGammaSlots; ++s) {
       mbar_init(reinterpret_cast<uint64_t*>(smem_raw + kGFullOffset) + s, 1);
