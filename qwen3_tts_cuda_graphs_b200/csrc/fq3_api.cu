@@ -186,7 +186,7 @@ void push_predictor(std::vector<Phase>& v, fq3_engine* e, bool only) {
     h.plan = plan_id(e, h.N, h.K, false);
     v.push_back(h);
     Phase s{};
-    s.type = PH_SAMPLE; s.stack = ST_PRED; s.aux = (uint8_t)i; s.kind = only ? SMP_PRED_ONLY : SMP_PRED;
+    s.type = PH_SAMPLE; s.stack = ST_PRED; s.aux = (uint8_t)i; s.skind = only ? SMP_PRED_ONLY : SMP_PRED;
     s.flags = r2 ? F_ROWS2 : 0;
     v.push_back(s);
   }
@@ -206,6 +206,17 @@ void push_talker(std::vector<Phase>& v, fq3_engine* e, bool last_row_head) {
 // Point every GEMV phase of a program at the fragment image of its matrix (built on first use), then upload the program.
 int upload(fq3_engine* e, std::vector<Phase>& v, Phase** d) {
   const uint8_t* arena = reinterpret_cast<const uint8_t*>(e->desc.arena);
+  // kinds: phases that agree in everything but their weights (the consumers' view), numbered in order of appearance
+  std::vector<std::array<uint32_t, 8>> kinds;
+  for (Phase& ph : v) {
+    if (ph.type != PH_GEMV) continue;
+    const std::array<uint32_t, 8> key{ph.flags, ph.in_buf, ph.out_buf, ph.res_buf, ph.N, ph.K, ph.plan, ph.b_off};
+    size_t k = 0;
+    while (k < kinds.size() && kinds[k] != key) ++k;
+    if (k == kinds.size()) kinds.push_back(key);
+    if (k >= (size_t)kMaxKinds) return -1;
+    ph.kind = (uint8_t)k;
+  }
   for (Phase& ph : v) {
     if (ph.type != PH_GEMV) continue;
     if (ph.N % 8) return -1;  // model matrices: whole 8-row groups (the image has the size of the matrix)
@@ -308,7 +319,18 @@ int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t 
     if (ph.flags & F_PRENORM) gamma_elems = std::max(gamma_elems, (size_t)ph.K);
   }
   p.xbuf_bytes = (int)round_up(xbytes, 1024);
-  p.prog_bytes = (int)round_up((size_t)p.n_phases * sizeof(Phase), 1024);
+  p.prog_bytes = (int)round_up((size_t)kKindBytes + kUnitBytes + (size_t)p.n_phases * sizeof(Phase), 1024);
+  // one representative phase per GEMV kind (the kernel resolves the kinds at start)
+  p.n_kinds = 0;
+  for (int i = 0; i < p.n_phases; ++i) {
+    const Phase& ph = prog_host[i];
+    if (ph.type != PH_GEMV) continue;
+    if (ph.kind >= kMaxKinds) return fail(FQ3_E_INVALID, "phase kind out of range");
+    if (ph.kind >= p.n_kinds) {
+      p.n_kinds = ph.kind + 1;
+      p.kind_phase[ph.kind] = (uint16_t)i;
+    }
+  }
   p.gam_bytes = (int)round_up(gamma_elems * 2, 1024);
   // Shared memory and L1 share 256 KB per SM: staying at or below the 196 KB carve-out leaves 60 KB of L1 for the table
   // reads of the attention and sampling phases.
@@ -543,7 +565,7 @@ static int create_impl(const fq3_model_desc* desc, fq3_engine* e) {
   push_talker(v, e, false);
   {
     Phase s{};
-    s.type = PH_SAMPLE; s.stack = ST_TALKER; s.kind = SMP_TALKER;
+    s.type = PH_SAMPLE; s.stack = ST_TALKER; s.skind = SMP_TALKER;
     v.push_back(s);
   }
   push_predictor(e->h_pred, e, true);
@@ -551,7 +573,7 @@ static int create_impl(const fq3_model_desc* desc, fq3_engine* e) {
   push_talker(e->h_prefill, e, true);
   {
     Phase s{};
-    s.type = PH_SAMPLE; s.stack = ST_TALKER; s.kind = SMP_PREFILL;
+    s.type = PH_SAMPLE; s.stack = ST_TALKER; s.skind = SMP_PREFILL;
     e->h_prefill.push_back(s);
   }
   if (g_plan_fail) { g_plan_fail = false; return fail(FQ3_E_UNSUPPORTED, "a GEMV shape of this model cannot be partitioned (odd N or K % 64)"); }
@@ -658,7 +680,7 @@ int fq3_set_loop_state(fq3_engine* e, int idx, int token, const void* past_hidde
 // rows of a prompt one launch of the prefill program takes: bounded by the activation staging buffer next to a ring of at
 // least six stages
 static int prefill_rows(const fq3_engine* e) {
-  const long fixed = kHeaderBytes + kScratchBytes + (long)round_up((size_t)e->n_prefill_ph * sizeof(Phase), 1024) +
+  const long fixed = kHeaderBytes + kScratchBytes + (long)round_up((size_t)kKindBytes + kUnitBytes + (size_t)e->n_prefill_ph * sizeof(Phase), 1024) +
                      (long)kGammaSlots * (long)round_up((size_t)e->tk.d.hidden * 2, 1024);
   const long spg_max = ((long)e->tk.kmax() * 16 + kStageBytes - 1) / kStageBytes;
   const long avail = (long)e->smem_max - fixed - std::max(6L, spg_max + 1) * kStageBytes;

@@ -89,9 +89,9 @@ struct __align__(16) Phase {
   uint32_t N;
   uint32_t K;
   uint8_t res_buf;
-  uint8_t kind;  // SAMPLE: SampleKind
+  uint8_t skind; // SAMPLE: SampleKind
   uint8_t plan;  // GEMV: index into LaunchParams::plans
-  uint8_t pad1;
+  uint8_t kind;  // GEMV: index into the launch's table of resolved phase kinds (KindDesc)
 };
 static_assert(sizeof(Phase) == 32, "Phase must stay 32 bytes");
 
@@ -113,6 +113,32 @@ struct Plan {
   int ro_shift;       // log2 of the weight rows behind one packed output word: 1 (plain) or 2 (SwiGLU: two (gate, up) pairs)
   float inv_k;        // 1 / K
 };
+// A GEMV phase "kind": everything a consumer needs that does not change from layer to layer (buffers, shape, this CTA's
+// share, the warps' units).  The kernel resolves each kind of a launch once, at start, into shared memory; a phase then
+// costs a few 16-byte loads instead of a page of address arithmetic on the critical path between two exchanges.
+constexpr int kMaxKinds = 32;
+struct __align__(16) KindDesc {
+  const LLWord* in;            // first input row (F_LAST_ROW applied)
+  int Kq, flags;               // 16-byte word pairs per row; Phase::flags
+  LLWord* out;
+  const LLWord* res;
+  const uint32_t* bias;
+  int ldout, ldres;
+  int g, grp0, wpg, gpr;       // this CTA's 8-row groups, first group; warps per group, groups per round
+  int spg, nch, ro_shift, n_stages;  // stages per group, blocks per group, log2 rows per word, stages of the phase on this CTA
+  float eps, inv_k;
+  int n_rounds, wpgrp;         // rounds; words per group
+  int M, n_words, K, fast;     // activation rows, packed output words of the matrix, columns, M == 1 && K <= 3072
+  int ldin, norm, pad0, pad1;
+};
+static_assert(sizeof(KindDesc) == 128, "KindDesc is eight 16-byte lines");
+struct __align__(16) UnitDesc {  // one consumer warp's unit of a kind
+  int wgrp, kp;    // group inside a round, k-part (wgrp >= gpr: the warp has no unit)
+  int ch0, ch1;    // blocks [ch0, ch1) of the group
+};
+constexpr int kKindBytes = kMaxKinds * (int)sizeof(KindDesc);                    // 4 KB
+constexpr int kUnitBytes = kMaxKinds * kConsumerWarps * (int)sizeof(UnitDesc);   // 6 KB
+
 // ---- run-time structures ----------------------------------------------------------------------
 struct StackRt {
   int hidden, inter, n_layers, nq, nkv, vocab;
@@ -160,6 +186,8 @@ enum Mode : int { MODE_FRAMES = 0, MODE_TALKER_STEP = 1, MODE_PREDICTOR = 2, MOD
 struct LaunchParams {
   const Phase* prog;
   int n_phases;
+  int n_kinds;                       // GEMV phase kinds of this launch
+  uint16_t kind_phase[kMaxKinds];    // a phase index of every kind (its representative)
   int n_iters;
   int mode;
   int n_rows;    // base row count M (streams for decode, chunk rows for prefill, M for linear)
@@ -187,7 +215,7 @@ struct LaunchParams {
   const void* lin_bias;
   float lin_eps;
   // smem carve-up
-  int n_stages, xbuf_bytes, prog_bytes, gam_bytes;  // ring stages of 16 KB; bytes of the activation staging buffer / of the program copy / of ONE norm-weight slot (1 KB multiples)
+  int n_stages, xbuf_bytes, prog_bytes, gam_bytes;  // ring stages of 16 KB; bytes of the activation staging buffer / of the kind tables + program copy / of ONE norm-weight slot (1 KB multiples)
   Plan plans[kMaxPlans];
   unsigned epoch_base;  // LL epoch of the phase before this launch's first phase
   unsigned long long watchdog_ns;

@@ -145,6 +145,8 @@ struct Smem {
   int* ctl;          // [0] producer go flag, [8..11] frame positions, [12..15] frame done flags
   float* red;        // [kMaxRows][16] RMSNorm partial sums
   unsigned char* scratch;
+  KindDesc* kinds;   // [kMaxKinds] resolved GEMV phase kinds
+  UnitDesc* units;   // [kMaxKinds][kConsumerWarps]
   Phase* prog;       // copy of the phase program (a global read per phase would sit on the critical path)
   unsigned char* gam;  // [kGammaSlots][gam_bytes] norm weights, streamed by the producer
   unsigned char* xbuf;  // activation rows of the current GEMV phase, in A-fragment order
@@ -158,7 +160,9 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* base, const LaunchPara
   s.ctl = reinterpret_cast<int*>(base + kCtlOffset);
   s.red = reinterpret_cast<float*>(base + kRedOffset);
   s.scratch = base + kHeaderBytes;
-  s.prog = reinterpret_cast<Phase*>(s.scratch + kScratchBytes);
+  s.kinds = reinterpret_cast<KindDesc*>(s.scratch + kScratchBytes);
+  s.units = reinterpret_cast<UnitDesc*>(s.scratch + kScratchBytes + kKindBytes);
+  s.prog = reinterpret_cast<Phase*>(s.scratch + kScratchBytes + kKindBytes + kUnitBytes);
   s.gam = s.scratch + kScratchBytes + p.prog_bytes;
   s.xbuf = s.gam + kGammaSlots * p.gam_bytes;
   s.ring = s.xbuf + p.xbuf_bytes;  // header, scratch, program, norm-weight slots and xbuf are 1 KB multiples
@@ -294,6 +298,7 @@ __device__ __forceinline__ Phase load_phase(const Phase* prog_smem, int i) {
 struct Ctx {  // per-thread constants (shared-memory addresses as 32-bit shared-window offsets)
   uint32_t full, empty, red, scratch, xs, ring, gfull, gempty, gam;
   int n_stages, gam_bytes;
+  uint32_t kinds, units;
   const Phase* prog;
 };
 __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchParams& p) {
@@ -310,6 +315,8 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchPa
   c.gempty = smem_u32(smem_base + kGEmptyOffset);
   c.gam = smem_u32(sm.gam);
   c.gam_bytes = p.gam_bytes;
+  c.kinds = smem_u32(sm.kinds);
+  c.units = smem_u32(sm.units);
   c.prog = sm.prog;
   return c;
 }
@@ -390,6 +397,43 @@ __device__ __forceinline__ Slab get_slab(const Phase& ph, const LaunchParams& p)
   s.grp0 = cta * pl.g_base + min(cta, pl.g_rem);
   s.n_stages = s.g * pl.spg;
   return s;
+}
+
+// Kernel start: resolve the GEMV phase kinds of this launch (thread k < n_kinds) and the warps' units (fq3_common.cuh: KindDesc).
+__device__ __forceinline__ void resolve_kind(const LaunchParams& p, const Phase& ph, KindDesc& kd) {
+  const Plan& pl = p.plans[ph.plan];
+  const Slab sb = get_slab(ph, p);
+  const uint32_t flags = ph.flags;
+  int M = (flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows, row_off = 0;
+  if (flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
+  const int K = (int)ph.K;
+  kd.ldin = p.ld[ph.in_buf];
+  kd.in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]) + (size_t)row_off * kd.ldin;
+  kd.Kq = K >> 2;
+  kd.flags = (int)flags;
+  kd.out = reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]);
+  kd.ldout = p.ld[ph.out_buf];
+  kd.res = (flags & F_RESID) ? reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) : nullptr;
+  kd.ldres = (flags & F_RESID) ? p.ld[ph.res_buf] : 0;
+  kd.bias = nullptr;
+  if (flags & F_BIAS)
+    kd.bias = reinterpret_cast<const uint32_t*>((flags & F_ABSPTR) ? p.lin_bias : static_cast<const void*>(p.arena + (size_t)ph.b_off * 16));
+  kd.g = sb.g; kd.grp0 = sb.grp0; kd.wpg = pl.wpg; kd.gpr = pl.gpr;
+  kd.spg = pl.spg; kd.nch = pl.nch; kd.ro_shift = pl.ro_shift; kd.n_stages = sb.n_stages;
+  kd.eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
+  kd.inv_k = pl.inv_k;
+  kd.n_rounds = sb.g ? (sb.g + pl.gpr - 1) / pl.gpr : 0;
+  kd.wpgrp = 8 >> pl.ro_shift;
+  kd.M = M; kd.n_words = (int)ph.N >> pl.ro_shift; kd.K = K;
+  kd.fast = (M == 1) && (kd.Kq <= 2 * kConsumerThreads);
+  kd.norm = (flags & F_PRENORM) ? 1 : 0;
+  kd.pad0 = 0; kd.pad1 = 0;
+}
+__device__ __forceinline__ void resolve_unit(const KindDesc& kd, int warp, UnitDesc& u) {
+  u.wgrp = warp / kd.wpg;
+  u.kp = warp - u.wgrp * kd.wpg;
+  u.ch0 = (u.kp * kd.nch) / kd.wpg;
+  u.ch1 = ((u.kp + 1) * kd.nch) / kd.wpg;
 }
 
 // Values computed before the poll must not be sunk behind it by the compiler: an empty asm pins them in a register.
@@ -506,26 +550,27 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
 template <bool PROF>
 __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, RingCur& gcur, int pidx,
                                                    uint32_t ep) {
-  const Slab sb = get_slab(ph, p);
-  if (sb.g == 0) return;  // more CTAs than row groups: nothing to do here (the producer skips the phase as well)
-  const uint32_t flags = ph.flags;
+  // the phase's kind and this warp's unit, resolved at kernel start (resolve_kind / resolve_unit): eight + one 16-byte loads
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int M = (flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows, row_off = 0;
-  if (flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
+  RingCur cur0 = cur, gcur0 = gcur;  // by value: the cursors stay in registers
+  const uint32_t kda = c.kinds + (uint32_t)ph.kind * (uint32_t)sizeof(KindDesc);
+  const uint4 k0 = lds128(kda);  // in | Kq | flags
+  const uint4 k3 = lds128(kda + 48u);  // g | grp0 | wpg | gpr
+  const uint4 ud = lds128(c.units + (uint32_t)(ph.kind * kConsumerWarps + warp) * (uint32_t)sizeof(UnitDesc));
+  if (k3.x == 0u) return;  // more CTAs than row groups: nothing to do here (the producer skips the phase as well)
+  const uint32_t flags = k0.w;
+  const int Kq = (int)k0.z;  // 16-byte word pairs ("quads": columns 4q .. 4q+3) per row; thread tid owns quads tid and tid + 384
+  const LLWord* in = reinterpret_cast<const LLWord*>(((unsigned long long)k0.y << 32) | k0.x);
   const uint32_t ep_in = (pidx == 0 && ep == p.epoch_base + 1) ? 0u : ep - 1;
-  const int K = (int)ph.K;
-  const int ldin = p.ld[ph.in_buf];
-  const LLWord* in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]) + (size_t)row_off * ldin;
   const bool norm = (flags & F_PRENORM) != 0;
-  const int Kq = K >> 2;  // 16-byte word pairs ("quads": columns 4q .. 4q+3) per row; thread tid owns quads tid and tid + 384
-  const bool fast = (M == 1) && (Kq <= 2 * kConsumerThreads);  // K <= 3072
   if (PROF) prof_mark(p, pidx, 0);
   if (PROF) prof_cta_time(p, pidx, 0);
-  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0 && M * K * 2 <= p.xbuf_bytes, pidx, 300000 + M);
 
   // ---- issue the first poll of this thread's input words
   const bool have0 = tid < Kq, have1 = tid + kConsumerThreads < Kq;
   const LLWord* src = in + 2 * tid;
+  const uint4 k6 = lds128(kda + 96u);  // M | n_words | K | fast
+  const bool fast = k6.w != 0u;
   uint4 w0 = make_uint4(0u, ep_in, 0u, ep_in), w1 = w0;
   if (fast) {
     if (have0) w0 = ll_ld_pair(src);
@@ -533,46 +578,50 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   }
 
   // ---- everything that does not depend on the input: overlaps the round trip of the poll
-  const Plan& pl = p.plans[ph.plan];
-  const int ro_shift = pl.ro_shift, wpg = pl.wpg, gpr = pl.gpr, spg = pl.spg, nch = pl.nch;
+  const uint4 k1 = lds128(kda + 16u);  // out | res
+  const uint4 k2 = lds128(kda + 32u);  // bias | ldout | ldres
+  const uint4 k4 = lds128(kda + 64u);  // spg | nch | ro_shift | n_stages
+  const uint4 k5 = lds128(kda + 80u);  // eps | inv_k | n_rounds | wpgrp
+  const int M = (int)k6.x, n_words = (int)k6.y, K = (int)k6.z;
+  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0 && M * K * 2 <= p.xbuf_bytes, pidx, 300000 + M);
+  struct { int g, grp0, n_stages; } sb = {(int)k3.x, (int)k3.y, (int)k4.w};
+  const int wpg = (int)k3.z, gpr = (int)k3.w, spg = (int)k4.x, ro_shift = (int)k4.z;
   const int g8 = lane >> 2, t = lane & 3;
   // this warp's unit: group (round * gpr + wgrp), k-part kp = blocks [ch0, ch1)
-  const int wgrp = small_div(warp, wpg), kp = warp - wgrp * wpg;
+  const int wgrp = (int)ud.x, kp = (int)ud.y;
   const bool w_act = wgrp < gpr;
-  int ch0 = small_div(kp * nch, wpg), ch1 = small_div((kp + 1) * nch, wpg);
+  int ch0 = (int)ud.z, ch1 = (int)ud.w;
   // norm weights arrive through the producer's stream (slot gcur of the small gamma ring)
-  uint32_t gsrc = c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes + (uint32_t)tid * 8u;
-  uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
-  const uint32_t glap = gcur.lap;
-  if (norm) gcur.advance(1, kGammaSlots);
-  float eps = (flags & F_ABSPTR) ? p.lin_eps : p.stacks[ph.stack].eps;
-  float inv_k = pl.inv_k;
+  uint32_t gsrc = c.gam + (uint32_t)gcur0.slot * (uint32_t)c.gam_bytes + (uint32_t)tid * 8u;
+  uint32_t gfullb = c.gfull + (uint32_t)gcur0.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur0.slot * 8u;
+  const uint32_t glap = gcur0.lap;
+  if (norm) gcur0.advance(1, kGammaSlots);
+  float eps = __uint_as_float(k5.x);
+  float inv_k = __uint_as_float(k5.y);
   uint32_t xdst0 = c.xs + xquad_off(tid), xdst1 = c.xs + xquad_off(tid + kConsumerThreads);
   // A rows: stream min(g8, M - 1) (rows beyond M repeat the last stream; their results are not read)
   uint32_t xrow = c.xs + (uint32_t)min(g8, M - 1) * xrow_bytes(K) + (uint32_t)t * 16u;
   const uint32_t lane_w = (uint32_t)lane * 16u;
   uint32_t pdst = c.scratch + (uint32_t)(warp * 32 + lane) * 8u;  // this lane's partial word (two fp32)
-  LLWord* out = reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]);
-  const int ldout = p.ld[ph.out_buf];
-  const int n_words = (int)ph.N >> ro_shift;  // packed output words of the whole matrix
+  LLWord* out = reinterpret_cast<LLWord*>(((unsigned long long)k1.y << 32) | k1.x);
+  const LLWord* resp = reinterpret_cast<const LLWord*>(((unsigned long long)k1.w << 32) | k1.z);
+  const uint32_t* biasp = reinterpret_cast<const uint32_t*>(((unsigned long long)k2.y << 32) | k2.x);
+  const int ldout = (int)k2.z, ldres = (int)k2.w;
   // finishing lane: stream g8, rows 2t, 2t+1 of the group -> plain: word 4 * group + t; SwiGLU: element 4 * group + t, the even lane
   // of a pair publishes word 2 * group + t / 2
   const bool f_lane = w_act && kp == 0 && g8 < M && (ro_shift == 1 || (t & 1) == 0);
   const int f_sub = (ro_shift == 1) ? t : (t >> 1);
-  const int wpgrp = 8 >> ro_shift;  // words per group
+  const int wpgrp = (int)k5.w;  // words per group
   int gi = wgrp;                     // group of round 0
   int f_word = (sb.grp0 + gi) * wpgrp + f_sub;
   uint32_t res0 = 0u, bias0 = 0u;
   const bool g_ok0 = w_act && gi < sb.g;
   if (f_lane && g_ok0 && f_word < n_words) {
-    if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)g8 * p.ld[ph.res_buf] + f_word).x;
-    if (flags & F_BIAS) {
-      const bf16* bias = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-      bias0 = __ldg(reinterpret_cast<const uint32_t*>(bias) + f_word);
-    }
+    if (flags & F_RESID) res0 = ll_ld(resp + (size_t)g8 * ldres + f_word).x;
+    if (flags & F_BIAS) bias0 = __ldg(biasp + f_word);
   }
   // the first stage this warp reads: wait for it now (it landed long ago; a wait after the poll would sit on the critical path)
-  RingCur my = cur;
+  RingCur my = cur0;
   const bool pre_ok = g_ok0;  // a round never takes more stages than the ring has slots (fq3_api.cu: launch), so the stage's
                               // slot was handed back by an earlier phase and its copy needs nothing from this one
   if (g_ok0) my.advance(gi * spg + (ch0 >> 5), c.n_stages);
@@ -582,7 +631,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       while (!mbar_try_wait_a(c.full + (uint32_t)my.slot * 8u, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
     }
   }
-  int n_rounds = small_div(sb.g + gpr - 1, gpr);  // 1 for every shape of the 0.6B model
+  int n_rounds = (int)k5.z;  // 1 for every shape of the 0.6B model
   uint32_t wa0 = c.ring + lane_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch0 & (kStageChunks - 1)) * kBlockBytes;
   uint32_t xa0 = xrow + (uint32_t)ch0 * kXBlock;
   // the norm weights were queued by the producer long ago as well
@@ -658,7 +707,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       Spin spin;
       while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
     }
-    load_x_general(p, flags, in, ldin, gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.xs, c.red);
+    load_x_general(p, flags, in, (int)lds_u32(kda + 112u), gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.xs, c.red);
     if (norm) {  // load_x_general ends with a barrier after the last read of the norm weights
       if (lane == 0) mbar_arrive_a(gemptyb);
     }
@@ -666,85 +715,6 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   if (PROF) prof_mark(p, pidx, 1);
 
   // ---- multiply, reduce the k-parts, publish, hand the group's stages back
-  // finish one unit: acc (stream g8, rows 2t, 2t+1 of group gi_) -> partial words -> epilogue -> publish
-  auto finish = [&](float y0, float y1, int gi_, bool first_round) {
-    if (wpg > 1) {
-      if (kp != 0) sts_f32x2(pdst, y0, y1);
-      group_bar_sync(2 + wgrp, wpg * 32);
-      if (kp == 0) {
-        if (wpg <= 4) {
-          // few parts: every lane adds the partial words of its own (stream, word) in part order
-#pragma unroll
-          for (int k2 = 1; k2 < 4; ++k2) {
-            if (k2 < wpg) {
-              const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
-              y0 += v.x; y1 += v.y;
-            }
-          }
-        } else if (M == 1) {
-          // many parts, one stream: lane (g8, t) adds the parts g8, g8 + 8 of word t, three shuffles add the eight slices in
-          // a fixed order (the A rows of a single stream are copies: every lane's own accumulator equals lane t's)
-          float s0 = 0.f, s1 = 0.f;
-          const uint32_t q0 = c.scratch + (uint32_t)(warp * 32 + t) * 8u;
-          if (g8 != 0 && g8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)g8 * 256u); s0 = v.x; s1 = v.y; }
-          if (g8 + 8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)(g8 + 8) * 256u); s0 += v.x; s1 += v.y; }
-          if (g8 == 0) { s0 += y0; s1 += y1; }
-#pragma unroll
-          for (int o = 4; o <= 16; o <<= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          }
-          y0 = s0; y1 = s1;
-        } else {
-#pragma unroll 1
-          for (int k2 = 1; k2 < wpg; ++k2) {
-            const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
-            y0 += v.x; y1 += v.y;
-          }
-        }
-      }
-    }
-    if (PROF && first_round) prof_mark(p, pidx, 10);
-    if (kp == 0) {
-      if (!first_round) {
-        f_word = (sb.grp0 + gi_) * wpgrp + f_sub;
-        if (f_lane && f_word < n_words) {
-          if (flags & F_RESID) res0 = ll_ld(reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)g8 * p.ld[ph.res_buf] + f_word).x;
-          if (flags & F_BIAS) {
-            const bf16* bp = (flags & F_ABSPTR) ? reinterpret_cast<const bf16*>(p.lin_bias) : reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16);
-            bias0 = __ldg(reinterpret_cast<const uint32_t*>(bp) + f_word);
-          }
-        }
-      }
-      float lo, hi;
-      if (flags & F_SWIGLU) {
-        // (y0, y1) = (gate, up) of element 4 * group + t; the odd lane of a pair hands its element to the even one
-        const float e = bf16r(bf16r(silu_f(bf16r(y0))) * bf16r(y1));
-        lo = e;
-        hi = __shfl_down_sync(0xffffffffu, e, 1);
-      } else {
-        lo = y0; hi = y1;
-        if (flags & F_BIAS) { lo += bf_lo(bias0); hi += bf_hi(bias0); }
-        lo = bf16r(lo); hi = bf16r(hi);
-        if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
-      }
-      if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
-      if (PROF) prof_cta_time(p, pidx, 1);
-      if (f_lane && f_word < n_words) ll_st(out + (size_t)g8 * ldout + f_word, pack_bf16x2(lo, hi), ep);
-      if (PROF && first_round) prof_mark(p, pidx, 11);
-      // every warp of the group has finished reading the group's stages (its k loop lies in front of the group barrier):
-      // the group's first warp hands them back, one arrival per stage
-      __syncwarp();
-      if (lane == 0) {
-        RingCur rel = cur;
-        rel.advance(gi_ * spg, c.n_stages);
-        for (int s2 = 0; s2 < spg; ++s2) {
-          mbar_arrive_a(c.empty + (uint32_t)rel.slot * 8u);
-          rel.advance(1, c.n_stages);
-        }
-      }
-    }
-  };
 #pragma unroll 1
   for (int r = 0; r < n_rounds; ++r) {
     // A round re-uses the ring slots of the round before.  mbarrier phases only tell adjacent uses of a slot apart, so
@@ -754,7 +724,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
     gi = r * gpr + wgrp;
     if (!(w_act && gi < sb.g)) continue;  // (all warps of a group skip together)
     if (r != 0) {
-      my = cur;
+      my = cur0;
       my.advance(gi * spg + (ch0 >> 5), c.n_stages);
       const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
       Spin spin;
@@ -798,11 +768,99 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
     mma_bf16(acc, xv.x, xv.x, xv.y, xv.y, wv.x, wv.y);
     mma_bf16(acc2, xv.z, xv.z, xv.w, xv.w, wv.z, wv.w);
     if (PROF && r == 0) prof_mark(p, pidx, 9);
-    finish(acc[0] + acc2[0], acc[1] + acc2[1], gi, r == 0);
+    // ---- finish the unit: stream g8, rows 2t, 2t+1 of group gi -> partial words -> epilogue -> publish
+    float y0 = acc[0] + acc2[0], y1 = acc[1] + acc2[1];
+    if (wpg > 1) {
+      if (kp != 0) sts_f32x2(pdst, y0, y1);
+      group_bar_sync(2 + wgrp, wpg * 32);
+      if (kp == 1) {
+        // every warp of the group has finished reading the group's stages (its k loop lies in front of the group barrier):
+        // the second warp hands them back, one arrival per stage — the first one is busy with the output
+        if (lane == 0) {
+          int rs = cur0.slot + gi * spg;
+          while (rs >= c.n_stages) rs -= c.n_stages;
+          for (int s2 = 0; s2 < spg; ++s2) {
+            mbar_arrive_a(c.empty + (uint32_t)rs * 8u);
+            if (++rs == c.n_stages) rs = 0;
+          }
+        }
+      } else if (kp == 0) {
+        if (wpg <= 4) {
+          // few parts: every lane adds the partial words of its own (stream, word) in part order
+#pragma unroll
+          for (int k2 = 1; k2 < 4; ++k2) {
+            if (k2 < wpg) {
+              const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
+              y0 += v.x; y1 += v.y;
+            }
+          }
+        } else if (M == 1) {
+          // many parts, one stream: lane (g8, t) adds the parts g8, g8 + 8 of word t, three shuffles add the eight slices in
+          // a fixed order (the A rows of a single stream are copies: every lane's own accumulator equals lane t's)
+          float s0 = 0.f, s1 = 0.f;
+          const uint32_t q0 = c.scratch + (uint32_t)(warp * 32 + t) * 8u;
+          if (g8 != 0 && g8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)g8 * 256u); s0 = v.x; s1 = v.y; }
+          if (g8 + 8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)(g8 + 8) * 256u); s0 += v.x; s1 += v.y; }
+          if (g8 == 0) { s0 += y0; s1 += y1; }
+#pragma unroll
+          for (int o = 4; o <= 16; o <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          }
+          y0 = s0; y1 = s1;
+        } else {
+#pragma unroll 1
+          for (int k2 = 1; k2 < wpg; ++k2) {
+            const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
+            y0 += v.x; y1 += v.y;
+          }
+        }
+      }
+    }
+    if (PROF && r == 0) prof_mark(p, pidx, 10);
+    if (kp == 0) {
+      if (r != 0) {
+        f_word = (sb.grp0 + gi) * wpgrp + f_sub;
+        if (f_lane && f_word < n_words) {
+          if (flags & F_RESID) res0 = ll_ld(resp + (size_t)g8 * ldres + f_word).x;
+          if (flags & F_BIAS) bias0 = __ldg(biasp + f_word);
+        }
+      }
+      float lo, hi;
+      if (flags & F_SWIGLU) {
+        // (y0, y1) = (gate, up) of element 4 * group + t; the odd lane of a pair hands its element to the even one
+        const float e = bf16r(bf16r(silu_f(bf16r(y0))) * bf16r(y1));
+        lo = e;
+        hi = __shfl_down_sync(0xffffffffu, e, 1);
+      } else {
+        lo = y0; hi = y1;
+        if (flags & F_BIAS) { lo += bf_lo(bias0); hi += bf_hi(bias0); }
+        lo = bf16r(lo); hi = bf16r(hi);
+        if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
+      }
+      if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
+      if (PROF) prof_cta_time(p, pidx, 1);
+      if (f_lane && f_word < n_words) ll_st(out + (size_t)g8 * ldout + f_word, pack_bf16x2(lo, hi), ep);
+      if (PROF && r == 0) prof_mark(p, pidx, 11);
+      if (wpg == 1) {  // a group of one warp hands its own stages back
+        __syncwarp();
+        if (lane == 0) {
+          int rs = cur0.slot + gi * spg;
+          while (rs >= c.n_stages) rs -= c.n_stages;
+          for (int s2 = 0; s2 < spg; ++s2) {
+            mbar_arrive_a(c.empty + (uint32_t)rs * 8u);
+            if (++rs == c.n_stages) rs = 0;
+          }
+        }
+      }
+    }
   }
-  cur.advance(sb.n_stages, c.n_stages);
+  cur0.advance(sb.n_stages, c.n_stages);
+  cur = cur0;
+  gcur = gcur0;
   if (PROF) prof_mark(p, pidx, 3);
 }
+
 
 // Producer side of one GEMV phase: stream this CTA's groups through the ring, one contiguous bulk copy per stage (up to
 // 16 KB = 1024 columns of one group's image).  The phase's norm weights travel in the same stream.  Returns false when the
@@ -1926,7 +1984,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
   const uint32_t ep_in = ep - 1;
   // CTAs without a stream idle through sampling phases: the once-per-step fence that makes this step's KV
   // rows visible to whichever CTA reads them in a later step goes here, off the critical path.
-  if ((int)blockIdx.x >= (p.mode == MODE_PREFILL ? 1 : p.n_rows) && threadIdx.x == 0 && ph.kind != SMP_PRED && ph.kind != SMP_PRED_ONLY)
+  if ((int)blockIdx.x >= (p.mode == MODE_PREFILL ? 1 : p.n_rows) && threadIdx.x == 0 && ph.skind != SMP_PRED && ph.skind != SMP_PRED_ONLY)
     __threadfence();  // cumulative: covers the K/V rows its CTA mates stored (ordered before by the consumer barriers)
   for (int b = blockIdx.x; b < (p.mode == MODE_PREFILL ? 1 : p.n_rows); b += gridDim.x) {
     prof_mark(p, pidx, 0);
@@ -1937,7 +1995,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
     LLWord* pin = reinterpret_cast<LLWord*>(p.bufs[p.has_s2m ? BUF_PIN : BUF_PX]);
     const int ldpin = p.ld[p.has_s2m ? BUF_PIN : BUF_PX];
     const LLWord* lgbuf = reinterpret_cast<const LLWord*>(p.bufs[BUF_LOGITS]);
-    if (ph.kind == SMP_PRED || ph.kind == SMP_PRED_ONLY) {
+    if (ph.skind == SMP_PRED || ph.skind == SMP_PRED_ONLY) {
       const int i = ph.aux;  // codebook step 0..ncb-1
       const int Vp = p.stacks[ST_PRED].vocab;
       const int lrow = (ph.flags & F_ROWS2) ? 2 * b + 1 : b;
@@ -1961,7 +2019,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
       if (i + 1 < ncb) {
         // next predictor input row: codec_embeds[i](tok)  (predictor_graph.py:144)
         publish_row(pin + (size_t)b * ldpin, p.pred_embeds[i] + (size_t)tok * Ht, Ht, ep);
-      } else if (ph.kind == SMP_PRED) {
+      } else if (ph.skind == SMP_PRED) {
         // frame complete: append [c0..c15], then build the next talker input (generate.py:159-171)
         const int nfr = __ldcg(&st->n_frames);
         const int c0 = __ldcg(&st->token);
@@ -2005,13 +2063,13 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
       const int Vt = p.stacks[ST_TALKER].vocab;
       const LLWord* lg = lgbuf + (size_t)b * p.ld[BUF_LOGITS];
       const int nfr = __ldcg(&st->n_frames);
-      const int done_now = (ph.kind == SMP_PREFILL) ? 0 : __ldcg(&st->done);  // includes this frame's cache-bound stop
+      const int done_now = (ph.skind == SMP_PREFILL) ? 0 : __ldcg(&st->done);  // includes this frame's cache-bound stop
       SampleArgs a;
       a.V = Vt; a.do_sample = p.pol.do_sample; a.top_k = p.pol.top_k; a.top_p = p.pol.top_p;
       a.temperature = p.pol.temperature; a.rep_pen = p.pol.rep_pen;
-      a.seen = (ph.kind == SMP_TALKER && nfr > 0) ? st->seen : nullptr;
+      a.seen = (ph.skind == SMP_TALKER && nfr > 0) ? st->seen : nullptr;
       a.suppress_start = max(0, Vt - p.pol.suppress_tail); a.eos = p.eos_id;
-      a.suppress_eos = (ph.kind == SMP_PREFILL) ? (p.pol.min_new_tokens > 0) : (nfr < p.pol.min_new_tokens);
+      a.suppress_eos = (ph.skind == SMP_PREFILL) ? (p.pol.min_new_tokens > 0) : (nfr < p.pol.min_new_tokens);
       a.round_bf16 = 1;
       a.seed = p.pol.seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(slot + 1));
       a.draw = __ldcg(&st->draws);
@@ -2020,7 +2078,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
       const bool live = !done_now;
       int new_done = done_now, new_pos = __ldcg(&st->position), new_gs = __ldcg(&st->gen_step);
       if (live) {
-        if (ph.kind == SMP_TALKER) { new_pos += 1; new_gs += 1; }
+        if (ph.skind == SMP_TALKER) { new_pos += 1; new_gs += 1; }
         if (tok == p.eos_id) new_done = 1;  // generate.py:150 — checked before the next frame is built
       } else {
         tok = __ldcg(&st->token);
@@ -2072,6 +2130,11 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
     uint4* dst = reinterpret_cast<uint4*>(sm.prog);
     for (int i = tid; i < p.n_phases * 2; i += kThreads) dst[i] = __ldg(src + i);
   }
+  __syncthreads();
+  // resolve the GEMV phase kinds of this launch, then every warp's unit of every kind
+  if (tid < p.n_kinds) resolve_kind(p, sm.prog[p.kind_phase[tid]], sm.kinds[tid]);
+  __syncthreads();
+  for (int i = tid; i < p.n_kinds * kConsumerWarps; i += kThreads) resolve_unit(sm.kinds[i / kConsumerWarps], i % kConsumerWarps, sm.units[i]);
   __syncthreads();
 
   if (tid >= kConsumerThreads) {
