@@ -242,7 +242,7 @@ def main():
     from qwen3_tts_cuda_graphs_b200.weights import param_bytes
 
     dev = f"cuda:{local}"
-    model = FasterQwen3TTS.from_pretrained(f"Qwen/Qwen3-TTS-12Hz-{args.model}", device=dev, dtype=torch.bfloat16,
+    model = FasterQwen3TTS.from_pretrained(f"synthetic://{args.model}", device=dev, dtype=torch.bfloat16,
                                            attn_implementation="eager", max_seq_len=2048, seed=0)
     eng = model.model.engine
     codec = model.model.model.speech_tokenizer.decoder
@@ -367,7 +367,7 @@ def main():
             # codec decode of every utterance included; wall clock between synchronisations
             from qwen3_tts_cuda_graphs_b200.generate import fast_generate_batch
             ns = args.batched_streams
-            model_b = FasterQwen3TTS.from_pretrained(f"Qwen/Qwen3-TTS-12Hz-{args.model}", device=dev, dtype=torch.bfloat16,
+            model_b = FasterQwen3TTS.from_pretrained(f"synthetic://{args.model}", device=dev, dtype=torch.bfloat16,
                                                      attn_implementation="eager", max_seq_len=2048, seed=0, max_streams=ns)
             mb, _, _, tie_b, tam_b, tth_b, tpe_b, _ = model_b._prepare_generation(TEXT, ref_wav, REF_TEXT, language="English",
                                                                                   non_streaming_mode=True)

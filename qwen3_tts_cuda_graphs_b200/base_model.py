@@ -15,6 +15,7 @@ ref-code prepending and proportional trimming) runs with the right shapes.
 from __future__ import annotations
 
 import hashlib
+import logging
 import os
 import types
 import wave
@@ -27,6 +28,8 @@ import torch
 from .config import TTSConfig, preset
 from .engine import Engine
 from .weights import Arena, init_synthetic, pack_arena
+
+logger = logging.getLogger(__name__)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -147,6 +150,8 @@ class _TextProjection:
         shape = x.shape
         rows = x.reshape(-1, shape[-1]).to(torch.bfloat16).contiguous()
         M = rows.shape[0]
+        if M == 0:  # a one-word text leaves no trailing rows (model.py:505-514 projects an empty slice)
+            return torch.empty(*shape[:-1], self.w2.shape[0], dtype=torch.bfloat16, device=rows.device)
         if self._gemm is not None and 0 < M <= 512:
             plan = self._plans.get(M)
             if plan is None:
@@ -177,6 +182,8 @@ class Talker:
     """Surface of `Qwen3TTSTalkerForConditionalGeneration` used by generate.py:99-124 and model.py:353-514."""
 
     def __init__(self, engine: Engine, arena: Arena, cfg: TTSConfig, stream_idx: int = 0):
+        if stream_idx != 0:
+            raise ValueError("the Talker operator surface addresses stream 0 only (the reference's seam is bs = 1)")
         self.engine, self.cfg, self.stream_idx = engine, cfg, stream_idx
         self.device = engine.device
         self.config = cfg.talker
@@ -204,7 +211,7 @@ class Talker:
         if trailing_text_hidden is not None and tts_pad_embed is not None:
             self.engine.set_text_conditioning(self.stream_idx, trailing_text_hidden[0], tts_pad_embed)
         logits = self.engine.prefill(self.stream_idx, inputs_embeds[0], n_pad, SamplingPolicy(do_sample=False), want_logits=True)
-        hidden = self.engine.last_hidden(self.stream_idx)
+        hidden = self.engine.last_hidden(0)  # fq3_prefill leaves the last row's hidden state in row 0 (include/fq3.h)
         self.rope_deltas = torch.tensor([[-n_pad]], dtype=torch.float32, device=self.device)
         T = inputs_embeds.shape[1]
         return types.SimpleNamespace(
@@ -284,15 +291,29 @@ class Qwen3TTSBaseModel:
     # ---- construction -------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, model_name: str, device_map="cuda", torch_dtype=torch.bfloat16, attn_implementation="sdpa",
-                        max_seq_len: int = 2048, max_streams: int = 1, seed: int = 0, weights=None, cfg: Optional[TTSConfig] = None):
-        """Named presets ("Qwen/Qwen3-TTS-12Hz-0.6B-Base", "synthetic://1.7B-CustomVoice", "tiny", ...) build
-        random-init weights of that architecture (BASELINE.json: no checkpoints offline)."""
+                        max_seq_len: int = 2048, max_streams: int = 1, seed: int = 0, weights=None, cfg: Optional[TTSConfig] = None,
+                        allow_synthetic: bool = False):
+        """Synthetic presets only: "synthetic://0.6B-Base", "synthetic://1.7B-CustomVoice", or the bare preset names
+        ("0.6B-Base", "tiny", ...) build seeded RANDOM-INIT weights of that architecture (BASELINE.json: no checkpoints
+        offline), a hashing tokenizer and pseudo speaker / reference-code encoders.
+
+        A Hugging Face id ("Qwen/Qwen3-TTS-12Hz-0.6B-Base") or a checkpoint directory is what a user of the reference passes
+        (model.py:107).  The safetensors loader, the BPE tokenizer and the speaker / codec encoders are SURVEY.md §8 row f3 and
+        are not built: such names raise instead of silently producing noise audio, unless `allow_synthetic=True` asks for the
+        random-init stand-in of the same architecture."""
         from .codec import SpeechTokenizer
 
-        if os.path.isdir(model_name):
+        looks_real = os.path.isdir(model_name) or model_name.lower().startswith("qwen/") or model_name.lower().endswith(".safetensors")
+        if looks_real and not allow_synthetic and weights is None:
             raise NotImplementedError(
-                "loading real safetensors checkpoints is SURVEY.md §8 row f3 (next); use a named preset"
+                f"{model_name!r} names a real checkpoint: loading safetensors weights, the tokenizer and the speaker / codec "
+                "encoders is not implemented (SURVEY.md §8 row f3).  Pass 'synthetic://<preset>' (or allow_synthetic=True) for "
+                "random-init weights of the same architecture — the audio is noise, only shapes and timing are meaningful."
             )
+        if os.path.isdir(model_name):
+            raise NotImplementedError("loading a checkpoint directory is SURVEY.md §8 row f3 (next); use a named preset")
+        if weights is None:
+            logger.warning("fq3: %r -> seeded random-init weights, hashing tokenizer, pseudo voice encoders (synthetic stand-in)", model_name)
         cfg = cfg or preset(model_name)
         dev = torch.device(device_map if isinstance(device_map, str) else "cuda")
         if dev.type != "cuda":

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
 
 LIBS = {
     "libfq3.so": (["fq3_api.cu"], ["fq3_kernel.cuh", "fq3_common.cuh", "../../include/fq3.h"], []),
-    "libfq3codec.so": (["fq3_codec.cu"], ["fq3_codec.cuh", "../../include/fq3_codec.h"], []),
+    "libfq3codec.so": (["fq3_codec.cu"], ["../../include/fq3_codec.h"], []),
 }
 
 

@@ -17,6 +17,8 @@ from .engine import Engine, SubPolicy
 class PredictorGraph:
     def __init__(self, engine: Engine, stream_idx: int = 0, do_sample: bool = True, top_k: int = 50, top_p: float = 1.0,
                  temperature: float = 0.9, seed: int = 0):
+        if stream_idx != 0:
+            raise ValueError("the PredictorGraph operator seam addresses stream 0 only (predictor_graph.py:70-71 is bs = 1 as well)")
         self.engine = engine
         self.stream_idx = stream_idx
         self.device = engine.device

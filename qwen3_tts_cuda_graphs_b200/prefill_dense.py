@@ -153,7 +153,7 @@ class DensePrefill:
             h = C.c_void_p()
             if self.lib.fq3c_graph_create(arr, len(self.ops), C.byref(h)) == 0:
                 if len(self.graphs) >= self.MAX_GRAPHS:
-                    _, old = self.graphs.popitem()
+                    old = self.graphs.pop(next(iter(self.graphs)))  # the oldest graph (dicts keep insertion order)
                     self.lib.fq3c_graph_destroy(old)
                 self.graphs[key] = g = h
             else:

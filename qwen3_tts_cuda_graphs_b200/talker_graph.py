@@ -16,6 +16,10 @@ from .engine import Engine
 
 class TalkerGraph:
     def __init__(self, engine: Engine, stream_idx: int = 0):
+        if stream_idx != 0:
+            # fq3_talker_step / fq3_prefill return hidden states through row 0 of the engine's buffers: the operator-at-a-time
+            # seam is single-stream like the reference's (talker_graph.py:46-47); batches go through fq3_decode_frames
+            raise ValueError("the TalkerGraph operator seam addresses stream 0 only; use fast_generate_batch for several streams")
         self.engine = engine
         self.stream_idx = stream_idx
         self.device = engine.device

@@ -5,7 +5,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from qwen3_tts_cuda_graphs_b200 import FasterQwen3TTS
-name = sys.argv[1] if len(sys.argv) > 1 else "Qwen/Qwen3-TTS-12Hz-1.7B-CustomVoice"
+name = sys.argv[1] if len(sys.argv) > 1 else "synthetic://1.7B-CustomVoice"
 m = FasterQwen3TTS.from_pretrained(name, device="cuda:0", dtype=torch.bfloat16, attn_implementation="eager", max_seq_len=2048, seed=0)
 kw = dict(text="Hello world! This is a streaming test of the custom voice model.", speaker="aiden", language="English", chunk_size=8,
           max_new_tokens=256, min_new_tokens=256)

@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from qwen3_tts_cuda_graphs_b200 import FasterQwen3TTS
 from qwen3_tts_cuda_graphs_b200.generate import fast_generate_batch
-name = "Qwen/Qwen3-TTS-12Hz-1.7B-VoiceDesign"
+name = "synthetic://1.7B-VoiceDesign"
 text = " ".join(["This is a long paragraph read by a designed voice, sentence number %d." % i for i in range(1, 13)])
 instruct = "A calm, low-pitched male narrator with a slow pace."
 frames = 750

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 from qwen3_tts_cuda_graphs_b200 import FasterQwen3TTS
-m = FasterQwen3TTS.from_pretrained("Qwen/Qwen3-TTS-12Hz-0.6B-Base", device="cuda:0", dtype=torch.bfloat16, attn_implementation="eager", max_seq_len=2048, seed=0)
+m = FasterQwen3TTS.from_pretrained("synthetic://0.6B-Base", device="cuda:0", dtype=torch.bfloat16, attn_implementation="eager", max_seq_len=2048, seed=0)
 ref = bench.make_ref_wav()
 f = lambda: m._prepare_generation(bench.TEXT, ref, bench.REF_TEXT, language="English", non_streaming_mode=True)
 for _ in range(5): f()

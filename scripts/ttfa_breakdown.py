@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import bench
 from qwen3_tts_cuda_graphs_b200 import FasterQwen3TTS
 from qwen3_tts_cuda_graphs_b200.streaming import fast_generate_streaming
-model = FasterQwen3TTS.from_pretrained("Qwen/Qwen3-TTS-12Hz-0.6B-Base", device="cuda:0", dtype=torch.bfloat16, attn_implementation="eager",
+model = FasterQwen3TTS.from_pretrained("synthetic://0.6B-Base", device="cuda:0", dtype=torch.bfloat16, attn_implementation="eager",
                                        max_seq_len=2048, seed=0)
 ref_wav = bench.make_ref_wav()
 kw = dict(text=bench.TEXT, language="English", ref_audio=ref_wav, ref_text=bench.REF_TEXT, chunk_size=8, max_new_tokens=64, min_new_tokens=64)

@@ -112,7 +112,7 @@ def pair(request):
     name, tl, pl = request.param
     cfg = make_cfg(name, tl, pl)
     w = make_weights(cfg, seed=11)
-    eng = make_engine(cfg, w, max_seq_len=128)
+    eng = make_engine(cfg, w, max_seq_len=272)
     orc = make_oracle(cfg, w)
     yield cfg, w, eng, orc
     eng.close()
@@ -206,7 +206,7 @@ def test_frame_loop_teacher_forced_against_oracle(pair):
     orc.sub.do_sample = False
     trace = {}
     frames = list(orc.generate_frames(tie, tam, tth, tpe, max_new_tokens=n, min_new_tokens=2, do_sample=False,
-                                      repetition_penalty=1.05, max_seq_len=128, trace=trace, forced=codes))
+                                      repetition_penalty=1.05, max_seq_len=272, trace=trace, forced=codes))
     assert len(frames) == n
     bad = []
     tscale = float(trace["prefill_logits"].abs().max())
@@ -389,7 +389,7 @@ def test_first_token_sampler_respects_suppression_and_top_k(tiny):
 # ------------------------------------------------------------------------------------------------
 # dense (tcgen05) prefill against the chunked decode-kernel prefill
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("T", [17, 40, 130])
+@pytest.mark.parametrize("T", [17, 40, 130, 240])
 def test_dense_prefill_matches_chunked_prefill(pair, T):
     """Rows [0, T-1) through the tensor-core GEMMs + the last row through the decode kernel must give the logits and the first
     token of the all-decode-kernel prefill, and the K/V it wrote must serve the next decode step (hidden state vs the oracle)."""
