@@ -44,7 +44,10 @@ def full(rep, dst, fpl):
                 def val(k):
                     v = float(d[k].replace(",", "")); un = u[k]
                     return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1.0, "us": 1e-3, "ns": 1e-6, "msecond": 1.0, "usecond": 1e-3, "nsecond": 1e-6}.get(un, 1.0)
-                tr = {"kernel": d.get("Kernel Name"), "frames_per_launch": fpl, "dram_bytes_read": val("dram__bytes_read.sum"),
+                sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+                from bench import kernel_source_hash
+                tr = {"kernel": d.get("Kernel Name"), "frames_per_launch": fpl, "kernel_hash": kernel_source_hash(),
+                      "dram_bytes_read": val("dram__bytes_read.sum"),
                       "dram_bytes_write": val("dram__bytes_write.sum"), "launch_ms_under_ncu": val("gpu__time_duration.sum"),
                       "source": f"{dst} (ncu --set full, one {fpl}-frame launch, 0.6B, prompt 39 rows)"}
                 json.dump(tr, open(os.path.join(os.path.dirname(dst) or ".", "ncu_traffic.json"), "w"), indent=1)

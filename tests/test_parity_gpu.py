@@ -485,3 +485,25 @@ def test_prefill_that_fills_the_cache_keeps_one_frame():
     assert st.error == 0 and st.done == 2
     assert st.n_frames == ref.shape[0] == 1
     eng.close()
+
+
+def test_set_loop_state_reseeds_a_stream(tiny_eng):
+    """fq3_set_loop_state (generate.py:120-134: the loop state the reference carries in Python locals — first token,
+    past_hidden, prefill length, generation step): re-seeding a prefilled stream with the very state the prefill left behind
+    must not change what the frame loop produces."""
+    eng = tiny_eng
+    cfg = eng.cfg
+    tie, tam, tth, tpe = synth_prompt(cfg, T=14, R=2, seed=5)
+    pol = _sp(do_sample=False, repetition_penalty=1.05)
+    sub = _sub(do_sample=False)
+    eng.set_text_conditioning(0, tth[0].cuda(), tpe.cuda())
+    eng.prefill(0, tie[0].cuda(), 0, pol)
+    eng.decode_frames(1, 6, pol, sub)
+    a = eng.read_codes(0, 0, eng.status(0).n_frames)
+    eng.prefill(0, tie[0].cuda(), 0, pol)
+    st = eng.status(0)
+    hid = eng.last_hidden(0).clone()
+    eng.set_loop_state(0, st.token, hid, st.position, st.gen_step)
+    eng.decode_frames(1, 6, pol, sub)
+    b = eng.read_codes(0, 0, eng.status(0).n_frames)
+    assert a.shape[0] == 6 and torch.equal(a, b)
