@@ -315,10 +315,10 @@ int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t 
     if (ph.type != PH_GEMV) continue;
     const int M = phase_rows_host(ph, p.n_rows);
     if (M > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "more activation rows than the GEMV stage takes");
-    xbytes = std::max(xbytes, (size_t)M * ph.K * 2);
+    xbytes = std::max(xbytes, (size_t)(M == 1 ? 2 : M) * ph.K * 2);  // single-stream rows alternate between two buffers
     if (ph.flags & F_PRENORM) gamma_elems = std::max(gamma_elems, (size_t)ph.K);
   }
-  p.xbuf_bytes = (int)round_up(xbytes, 1024);
+  p.xbuf_bytes = (int)round_up(xbytes, 2048);
   p.prog_bytes = (int)round_up((size_t)kKindBytes + kUnitBytes + (size_t)p.n_phases * sizeof(Phase), 1024);
   // one representative phase per GEMV kind (the kernel resolves the kinds at start)
   p.n_kinds = 0;

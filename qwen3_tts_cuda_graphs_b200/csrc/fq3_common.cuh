@@ -18,9 +18,15 @@ namespace fq3 {
 typedef __nv_bfloat16 bf16;
 
 // ---- geometry ---------------------------------------------------------------------------------
-constexpr int kConsumerWarps = 12;  // 12 consumers + 1 producer = 13 warps; registers are allotted per 4 warps -> 128 per thread
+constexpr int kConsumerWarps = 12;  // three warpgroups of consumers
 constexpr int kConsumerThreads = kConsumerWarps * 32;  // 384
-constexpr int kThreads = kConsumerThreads + 32;        // + one producer warp
+constexpr int kThreads = kConsumerThreads + 128;       // + the producer's warpgroup (warp 12 streams the weights, warps 13-15 only hand their
+                                                       // registers over: setmaxnreg moves 72 registers per thread of this warpgroup to the
+                                                       // consumers, 128 -> 152 per consumer thread)
+constexpr int kProducerRegs = 56;
+constexpr int kConsumerRegs = 152;
+constexpr int kPollWarps = 8;              // consumer warps 0-7 poll, normalise and stage a single-stream activation row; the
+constexpr int kPollThreads = kPollWarps * 32;  // group leaders sit on the other warps where they can (resolve_unit)
 constexpr int kMaxStages = 16;             // mbarrier pairs: ring stages in flight per SM
 constexpr int kGroupRows = 8;              // weight rows per group = the n dimension of mma.m16n8k16
 constexpr int kChunkK = 32;                // columns per fragment block (two k-steps of 16)
@@ -128,7 +134,7 @@ struct __align__(16) KindDesc {
   int spg, nch, ro_shift, n_stages;  // stages per group, blocks per group, log2 rows per word, stages of the phase on this CTA
   float eps, inv_k;
   int n_rounds, wpgrp;         // rounds; words per group
-  int M, n_words, K, fast;     // activation rows, packed output words of the matrix, columns, M == 1 && K <= 3072
+  int M, n_words, K, fast;     // activation rows, packed output words of the matrix, columns, M == 1 && K <= 3072 (three quads per polling thread)
   int ldin, norm, pad0, pad1;
 };
 static_assert(sizeof(KindDesc) == 128, "KindDesc is eight 16-byte lines");

@@ -250,9 +250,10 @@ __device__ __forceinline__ void prof_warp_time(const LaunchParams& p, int pidx, 
   if (p.prof && p.prof_cta == -3 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && pidx >= 0 && pidx < 512)
     p.prof[((size_t)pidx * 160 + 16 * (k >> 1) + (threadIdx.x >> 5)) * 2 + (k & 1)] = clock64();
 }
-__device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int slot) {
-  if (p.prof && threadIdx.x == 0 && (int)blockIdx.x == p.prof_cta && pidx >= 0 && pidx < 512) p.prof[(size_t)pidx * 16 + slot] = clock64();
+__device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int slot, int thread = 0) {
+  if (p.prof && (int)threadIdx.x == thread && (int)blockIdx.x == p.prof_cta && pidx >= 0 && pidx < 512) p.prof[(size_t)pidx * 16 + slot] = clock64();
 }
+constexpr int kProfLeader = (kConsumerWarps - 1) * 32;  // lane 0 of warp 11: the leader of group 0 (resolve_unit)
 
 // SiLU in fp32; the result is rounded to bf16 right away, so the fast exp / divide (a few ulp of fp32) do not show
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
@@ -298,7 +299,7 @@ __device__ __forceinline__ Phase load_phase(const Phase* prog_smem, int i) {
 struct Ctx {  // per-thread constants (shared-memory addresses as 32-bit shared-window offsets)
   uint32_t full, empty, red, scratch, xs, ring, gfull, gempty, gam;
   int n_stages, gam_bytes;
-  uint32_t kinds, units;
+  uint32_t kinds, units, xhalf;
   const Phase* prog;
 };
 __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchParams& p) {
@@ -315,6 +316,7 @@ __device__ __forceinline__ Ctx make_ctx(unsigned char* smem_base, const LaunchPa
   c.gempty = smem_u32(smem_base + kGEmptyOffset);
   c.gam = smem_u32(sm.gam);
   c.gam_bytes = p.gam_bytes;
+  c.xhalf = (uint32_t)p.xbuf_bytes / 2u;
   c.kinds = smem_u32(sm.kinds);
   c.units = smem_u32(sm.units);
   c.prog = sm.prog;
@@ -425,16 +427,30 @@ __device__ __forceinline__ void resolve_kind(const LaunchParams& p, const Phase&
   kd.n_rounds = sb.g ? (sb.g + pl.gpr - 1) / pl.gpr : 0;
   kd.wpgrp = 8 >> pl.ro_shift;
   kd.M = M; kd.n_words = (int)ph.N >> pl.ro_shift; kd.K = K;
-  kd.fast = (M == 1) && (kd.Kq <= 2 * kConsumerThreads);
+  kd.fast = (M == 1) && (kd.Kq <= 3 * kPollThreads);
   kd.norm = (flags & F_PRENORM) ? 1 : 0;
   kd.pad0 = 0; kd.pad1 = 0;
 }
+// Which unit a warp takes.  The first warp of a group ("leader", k-part 0) adds the parts, applies the epilogue and publishes:
+// it is the last warp of its CTA to leave a phase.  Leaders therefore sit on the highest warps — warps 8-11 do not poll the
+// next phase's input (kPollWarps), so a leader's way from its store to the next phase overlaps the pollers' wait, norm and
+// staging instead of delaying them.  The other k-parts fill the warps from 0 up.
 __device__ __forceinline__ void resolve_unit(const KindDesc& kd, int warp, UnitDesc& u) {
-  u.wgrp = warp / kd.wpg;
-  u.kp = warp - u.wgrp * kd.wpg;
-  u.ch0 = (u.kp * kd.nch) / kd.wpg;
-  u.ch1 = ((u.kp + 1) * kd.nch) / kd.wpg;
+  const int wpg = kd.wpg, gpr = kd.gpr;
+  if (warp >= kConsumerWarps - gpr) {
+    u.wgrp = kConsumerWarps - 1 - warp;
+    u.kp = 0;
+  } else if (wpg > 1 && warp < gpr * (wpg - 1)) {
+    u.wgrp = warp / (wpg - 1);
+    u.kp = 1 + warp - u.wgrp * (wpg - 1);
+  } else {
+    u.wgrp = gpr;  // no unit
+    u.kp = 0;
+  }
+  u.ch0 = (u.kp * kd.nch) / wpg;
+  u.ch1 = ((u.kp + 1) * kd.nch) / wpg;
 }
+__device__ __forceinline__ void poll_bar_sync() { asm volatile("bar.sync 14, %0;" ::"n"(kPollThreads) : "memory"); }
 
 // Values computed before the poll must not be sunk behind it by the compiler: an empty asm pins them in a register.
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
@@ -548,8 +564,8 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
 }
 
 template <bool PROF>
-__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, RingCur& gcur, int pidx,
-                                                   uint32_t ep) {
+__device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, RingCur& gcur, uint32_t& gst,
+                                                   int pidx, uint32_t ep) {
   // the phase's kind and this warp's unit, resolved at kernel start (resolve_kind / resolve_unit): eight + one 16-byte loads
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   RingCur cur0 = cur, gcur0 = gcur;  // by value: the cursors stay in registers
@@ -565,16 +581,19 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const bool norm = (flags & F_PRENORM) != 0;
   if (PROF) prof_mark(p, pidx, 0);
   if (PROF) prof_cta_time(p, pidx, 0);
+  if (PROF) prof_warp_time(p, pidx, 0);
 
-  // ---- issue the first poll of this thread's input words
-  const bool have0 = tid < Kq, have1 = tid + kConsumerThreads < Kq;
-  const LLWord* src = in + 2 * tid;
+  // ---- issue the first poll of this thread's input words (single-stream rows: warps 0-7, quads tid, tid + 256, tid + 512)
   const uint4 k6 = lds128(kda + 96u);  // M | n_words | K | fast
   const bool fast = k6.w != 0u;
-  uint4 w0 = make_uint4(0u, ep_in, 0u, ep_in), w1 = w0;
+  const bool poller = tid < kPollThreads;
+  const bool have0 = poller && tid < Kq, have1 = poller && tid + kPollThreads < Kq, have2 = poller && tid + 2 * kPollThreads < Kq;
+  const LLWord* src = in + 2 * tid;
+  uint4 w0 = make_uint4(0u, ep_in, 0u, ep_in), w1 = w0, w2 = w0;
   if (fast) {
     if (have0) w0 = ll_ld_pair(src);
-    if (have1) w1 = ll_ld_pair(src + 2 * kConsumerThreads);
+    if (have1) w1 = ll_ld_pair(src + 2 * kPollThreads);
+    if (have2) w2 = ll_ld_pair(src + 4 * kPollThreads);
   }
 
   // ---- everything that does not depend on the input: overlaps the round trip of the poll
@@ -598,11 +617,16 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   if (norm) gcur0.advance(1, kGammaSlots);
   float eps = __uint_as_float(k5.x);
   float inv_k = __uint_as_float(k5.y);
-  uint32_t xdst0 = c.xs + xquad_off(tid), xdst1 = c.xs + xquad_off(tid + kConsumerThreads);
+  // Single-stream rows and the partial words alternate between two buffers from one GEMV phase to the next: a warp that is
+  // already staging phase i + 1 cannot disturb a warp that still multiplies phase i, and no barrier has to open the phase.
+  const uint32_t par = gst & 1u;
+  const uint32_t xs = c.xs + (fast ? par * c.xhalf : 0u);
+  uint32_t xdst0 = xs + xquad_off(tid), xdst1 = xs + xquad_off(tid + kPollThreads), xdst2 = xs + xquad_off(tid + 2 * kPollThreads);
   // A rows: stream min(g8, M - 1) (rows beyond M repeat the last stream; their results are not read)
-  uint32_t xrow = c.xs + (uint32_t)min(g8, M - 1) * xrow_bytes(K) + (uint32_t)t * 16u;
+  uint32_t xrow = xs + (uint32_t)min(g8, M - 1) * xrow_bytes(K) + (uint32_t)t * 16u;
   const uint32_t lane_w = (uint32_t)lane * 16u;
-  uint32_t pdst = c.scratch + (uint32_t)(warp * 32 + lane) * 8u;  // this lane's partial word (two fp32)
+  const uint32_t pbase = c.scratch + par * (uint32_t)(kConsumerWarps * 32 * 8);
+  uint32_t pdst = pbase + (uint32_t)((wgrp * wpg + kp) * 32 + lane) * 8u;  // this lane's partial word (two fp32), by unit
   LLWord* out = reinterpret_cast<LLWord*>(((unsigned long long)k1.y << 32) | k1.x);
   const LLWord* resp = reinterpret_cast<const LLWord*>(((unsigned long long)k1.w << 32) | k1.z);
   const uint32_t* biasp = reinterpret_cast<const uint32_t*>(((unsigned long long)k2.y << 32) | k2.x);
@@ -634,74 +658,107 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   int n_rounds = (int)k5.z;  // 1 for every shape of the 0.6B model
   uint32_t wa0 = c.ring + lane_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch0 & (kStageChunks - 1)) * kBlockBytes;
   uint32_t xa0 = xrow + (uint32_t)ch0 * kXBlock;
-  // the norm weights were queued by the producer long ago as well
-  uint2 g0 = make_uint2(0u, 0u), g1 = g0;
-  if (fast && norm) {
-    if (!mbar_try_wait_a(gfullb, glap)) {
-      Spin spin;
-      while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
-    }
-    if (have0) g0 = lds_u32x2(gsrc);
-    if (have1) g1 = lds_u32x2(gsrc + kConsumerThreads * 8);
+  // Experiment (FQ3_PRE > 0, off): the stage is in shared memory long before the activations are, so the first FQ3_PRE weight
+  // blocks of this warp's unit could wait in registers and leave only the activation loads between "input visible" and
+  // "output stored".  Measured slower at 4 and 8 blocks even with 152 registers per thread (profiles/r02b_gemv_variants.log):
+  // the fragments are spilled around the poll loop.
+#ifndef FQ3_PRE
+#define FQ3_PRE 0
+#endif
+  constexpr int kPre = FQ3_PRE > 0 ? FQ3_PRE : 1;
+  uint4 wreg[kPre];
+  int npre = 0;
+  if (pre_ok && FQ3_PRE > 0) {
+    npre = min(min(ch1, (ch0 | (kStageChunks - 1)) + 1) - ch0, kPre);
+#pragma unroll
+    for (int i = 0; i < kPre; ++i)
+      if (i < npre) wreg[i] = lds128(wa0 + (uint32_t)i * kBlockBytes);
   }
-  pin(gemptyb); pin(eps); pin(inv_k); pin(xdst0); pin(xdst1); pin(pdst); pin(f_word); pin(ch0); pin(ch1); pin(wa0); pin(xa0); pin(n_rounds);
-  pin(g0.x); pin(g0.y); pin(g1.x); pin(g1.y);
-  // No barrier closes a GEMV phase, so a warp may arrive here while others still multiply the previous phase's activations
-  // or read its partial words / the attention scratch.  Phases with a norm meet at the sum-of-squares barrier before they
-  // write anything; the others meet here, in the shadow of the poll.
-  if (!(fast && norm)) cbar_sync();
+  // the norm weights were queued by the producer long ago as well
+  uint2 g0 = make_uint2(0u, 0u), g1 = g0, g2 = g0;
+  if (fast && norm) {
+    if (poller) {
+      if (!mbar_try_wait_a(gfullb, glap)) {
+        Spin spin;
+        while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
+      }
+      if (have0) g0 = lds_u32x2(gsrc);
+      if (have1) g1 = lds_u32x2(gsrc + kPollThreads * 8);
+      if (have2) g2 = lds_u32x2(gsrc + 2 * kPollThreads * 8);
+    } else if (lane == 0) {
+      mbar_arrive_a(gemptyb);  // the other warps do not read the norm weights
+    }
+  }
+  pin(gemptyb); pin(eps); pin(inv_k); pin(xdst0); pin(xdst1); pin(xdst2); pin(pdst); pin(f_word); pin(ch0); pin(ch1); pin(wa0); pin(xa0); pin(n_rounds);
+  pin(g0.x); pin(g0.y); pin(g1.x); pin(g1.y); pin(g2.x); pin(g2.y);
+  // No barrier closes a GEMV phase, so a warp may arrive here while others still multiply the previous phase's activations or
+  // read its partial words.  Single-stream phases are protected by the alternating buffers (above); multi-row phases use one
+  // buffer and meet here, in the shadow of the poll — and so does a single-stream phase that follows a multi-row one.
+  if (!fast || (gst & 2u)) cbar_sync();
 
   // ---- wait for the input, normalise, stage it in shared memory
   if (fast) {
-    if (ep_in != 0) {
-      unsigned tries = 0;
-      while ((w0.y != ep_in) | (w0.w != ep_in) | (w1.y != ep_in) | (w1.w != ep_in)) {
-        if (++tries > (unsigned)(p.debug >> 16)) __nanosleep((unsigned)(p.debug & 0xffff));
-        if (tries > (unsigned)(p.watchdog_ns >> 8)) device_fault(p, DE_LL_WAIT, pidx, (int)ep_in);
-        if (have0 && ((w0.y != ep_in) | (w0.w != ep_in))) w0 = ll_ld_pair(src);
-        if (have1 && ((w1.y != ep_in) | (w1.w != ep_in))) w1 = ll_ld_pair(src + 2 * kConsumerThreads);
+    if (poller) {
+      if (ep_in != 0) {
+        unsigned tries = 0;
+        while ((w0.y != ep_in) | (w0.w != ep_in) | (w1.y != ep_in) | (w1.w != ep_in) | (w2.y != ep_in) | (w2.w != ep_in)) {
+          if (++tries > (unsigned)(p.debug >> 16)) __nanosleep((unsigned)(p.debug & 0xffff));
+          if (tries > (unsigned)(p.watchdog_ns >> 8)) device_fault(p, DE_LL_WAIT, pidx, (int)ep_in);
+          if (have0 && ((w0.y != ep_in) | (w0.w != ep_in))) w0 = ll_ld_pair(src);
+          if (have1 && ((w1.y != ep_in) | (w1.w != ep_in))) w1 = ll_ld_pair(src + 2 * kPollThreads);
+          if (have2 && ((w2.y != ep_in) | (w2.w != ep_in))) w2 = ll_ld_pair(src + 4 * kPollThreads);
+        }
+      }
+      if (PROF) prof_mark(p, pidx, 7);
+      if (PROF) prof_warp_time(p, pidx, 5);
+      if (!norm) {
+        if (have0) xquad_store(xdst0, w0.x, w0.z);
+        if (have1) xquad_store(xdst1, w1.x, w1.z);
+        if (have2) xquad_store(xdst2, w2.x, w2.z);
+      } else {
+        float ss;
+        {  // absent pairs carry payload 0
+          const float a0 = bf_lo(w0.x), a1 = bf_hi(w0.x), a2 = bf_lo(w0.z), a3 = bf_hi(w0.z);
+          const float b0 = bf_lo(w1.x), b1 = bf_hi(w1.x), b2 = bf_lo(w1.z), b3 = bf_hi(w1.z);
+          const float c0 = bf_lo(w2.x), c1 = bf_hi(w2.x), c2 = bf_lo(w2.z), c3 = bf_hi(w2.z);
+          ss = (fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3)) + (fmaf(b0, b0, b1 * b1) + fmaf(b2, b2, b3 * b3)) +
+               (fmaf(c0, c0, c1 * c1) + fmaf(c2, c2, c3 * c3));
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) sts_f32(c.red + (uint32_t)warp * 4u, ss);
+        if (PROF) prof_mark(p, pidx, 15);
+        poll_bar_sync();  // the eight polling warps
+        if (PROF) prof_mark(p, pidx, 14);
+        float tot;
+        {
+          const float4 r0 = lds_f32x4(c.red), r1 = lds_f32x4(c.red + 16u);
+          static_assert(kPollWarps == 8, "the RMSNorm reduction reads eight per-warp sums");
+          tot = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w));
+        }
+        const float rs = rsqrtf(fmaf(tot, inv_k, eps));
+        const bool wr = (flags & F_WRITE_NORMED) && blockIdx.x == 0;
+        if (have0) {
+          const uint32_t y0 = norm_pair(w0.x, rs, g0.x), y1 = norm_pair(w0.z, rs, g0.y);
+          xquad_store(xdst0, y0, y1);
+          if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid] = make_uint2(y0, y1);
+        }
+        if (have1) {
+          const uint32_t y0 = norm_pair(w1.x, rs, g1.x), y1 = norm_pair(w1.z, rs, g1.y);
+          xquad_store(xdst1, y0, y1);
+          if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid + kPollThreads] = make_uint2(y0, y1);
+        }
+        if (have2) {
+          const uint32_t y0 = norm_pair(w2.x, rs, g2.x), y1 = norm_pair(w2.z, rs, g2.y);
+          xquad_store(xdst2, y0, y1);
+          if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid + 2 * kPollThreads] = make_uint2(y0, y1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(gemptyb);
       }
     }
-    if (PROF) prof_mark(p, pidx, 7);
-    if (PROF) prof_warp_time(p, pidx, 0);
-    if (!norm) {
-      if (have0) xquad_store(xdst0, w0.x, w0.z);
-      if (have1) xquad_store(xdst1, w1.x, w1.z);
-      cbar_sync();
-    } else {
-      float ss;
-      {  // absent pairs carry payload 0
-        const float a0 = bf_lo(w0.x), a1 = bf_hi(w0.x), a2 = bf_lo(w0.z), a3 = bf_hi(w0.z);
-        const float b0 = bf_lo(w1.x), b1 = bf_hi(w1.x), b2 = bf_lo(w1.z), b3 = bf_hi(w1.z);
-        ss = fmaf(a0, a0, a1 * a1) + fmaf(a2, a2, a3 * a3) + (fmaf(b0, b0, b1 * b1) + fmaf(b2, b2, b3 * b3));
-      }
-      ss = warp_sum(ss);
-      if (lane == 0) sts_f32(c.red + (uint32_t)warp * 4u, ss);
-      if (PROF) prof_mark(p, pidx, 15);
-      cbar_sync();
-      if (PROF) prof_mark(p, pidx, 14);
-      float tot;
-      {
-        const float4 r0 = lds_f32x4(c.red), r1 = lds_f32x4(c.red + 16u), r2 = lds_f32x4(c.red + 32u);
-        static_assert(kConsumerWarps == 12, "the RMSNorm reduction reads twelve per-warp sums");
-        tot = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w)) + ((r2.x + r2.y) + (r2.z + r2.w));
-      }
-      const float rs = rsqrtf(fmaf(tot, inv_k, eps));
-      const bool wr = (flags & F_WRITE_NORMED) && blockIdx.x == 0;
-      if (have0) {
-        const uint32_t y0 = norm_pair(w0.x, rs, g0.x), y1 = norm_pair(w0.z, rs, g0.y);
-        xquad_store(xdst0, y0, y1);
-        if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid] = make_uint2(y0, y1);
-      }
-      if (have1) {
-        const uint32_t y0 = norm_pair(w1.x, rs, g1.x), y1 = norm_pair(w1.z, rs, g1.y);
-        xquad_store(xdst1, y0, y1);
-        if (wr) reinterpret_cast<uint2*>(p.bufs[BUF_HID])[tid + kConsumerThreads] = make_uint2(y0, y1);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(gemptyb);
-      cbar_sync();  // xs complete; also protects red[] against the next phase
-    }
+    if (PROF) prof_warp_time(p, pidx, 6);
+    cbar_sync();  // all twelve warps: the activation row is staged (red[] is safe as well: the next norm phase lies behind this barrier)
+    if (PROF) prof_warp_time(p, pidx, 1);
   } else {
     if (norm && !mbar_try_wait_a(gfullb, glap)) {
       Spin spin;
@@ -735,11 +792,38 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
     int ch = ch0;
     uint32_t wa = wa0, xa = xa0;
     if (PROF && r == 0) prof_mark(p, pidx, 8);
-    // Software-pipelined: the loads of block i + 1 are in flight while block i is multiplied.
-    uint4 wv = lds128(wa), xv = lds128(xa);
+    if (PROF && r == 0) prof_warp_time(p, pidx, 2);
+    if (r == 0 && npre > 0) {
+      // blocks whose weights wait in registers: only the activation loads remain, one ahead of the MMAs
+      uint4 xv = lds128(xa);
+#pragma unroll
+      for (int i = 0; i < kPre; ++i) {
+        if (i < npre) {
+          uint4 xn = xv;
+          if (ch0 + i + 1 < ch1) xn = lds128(xa + (uint32_t)(i + 1) * kXBlock);
+          mma_bf16(acc, xv.x, xv.x, xv.y, xv.y, wreg[i].x, wreg[i].y);
+          mma_bf16(acc2, xv.z, xv.z, xv.w, xv.w, wreg[i].z, wreg[i].w);
+          xv = xn;
+        }
+      }
+      ch += npre;
+      wa += (uint32_t)npre * kBlockBytes;
+      xa += (uint32_t)npre * kXBlock;
+    }
 #pragma unroll 1
-    while (true) {
+    while (ch < ch1) {
+      if (ch != ch0 && (ch & (kStageChunks - 1)) == 0) {  // the unit goes on in the next stage of the group
+        my.advance(1, c.n_stages);
+        const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
+        if (!mbar_try_wait_a(fb, my.lap)) {
+          Spin spin;
+          while (!mbar_try_wait_a(fb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+        }
+        wa = c.ring + lane_w + (uint32_t)my.slot * kStageBytes;
+      }
       const int ce = min(ch1, (ch | (kStageChunks - 1)) + 1);  // end of this stage's blocks
+      // software-pipelined: the loads of block i + 1 are in flight while block i is multiplied
+      uint4 wv = lds128(wa), xv = lds128(xa);
 #pragma unroll 2
       for (int n = ce - ch - 1; n > 0; --n) {
         wa += kBlockBytes;
@@ -749,25 +833,14 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
         mma_bf16(acc2, xv.z, xv.z, xv.w, xv.w, wv.z, wv.w);
         wv = wn; xv = xn;
       }
-      ch = ce;
-      if (ch >= ch1) break;
-      // the unit goes on in the next stage of the group
-      my.advance(1, c.n_stages);
-      const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
-      if (!mbar_try_wait_a(fb, my.lap)) {
-        Spin spin;
-        while (!mbar_try_wait_a(fb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
-      }
-      wa = c.ring + lane_w + (uint32_t)my.slot * kStageBytes;
-      xa += kXBlock;
-      const uint4 wn = lds128(wa), xn = lds128(xa);
       mma_bf16(acc, xv.x, xv.x, xv.y, xv.y, wv.x, wv.y);
       mma_bf16(acc2, xv.z, xv.z, xv.w, xv.w, wv.z, wv.w);
-      wv = wn; xv = xn;
+      wa += kBlockBytes;
+      xa += kXBlock;
+      ch = ce;
     }
-    mma_bf16(acc, xv.x, xv.x, xv.y, xv.y, wv.x, wv.y);
-    mma_bf16(acc2, xv.z, xv.z, xv.w, xv.w, wv.z, wv.w);
     if (PROF && r == 0) prof_mark(p, pidx, 9);
+    if (PROF && r == 0) prof_warp_time(p, pidx, 3);
     // ---- finish the unit: stream g8, rows 2t, 2t+1 of group gi -> partial words -> epilogue -> publish
     float y0 = acc[0] + acc2[0], y1 = acc[1] + acc2[1];
     if (wpg > 1) {
@@ -798,7 +871,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
           // many parts, one stream: lane (g8, t) adds the parts g8, g8 + 8 of word t, three shuffles add the eight slices in
           // a fixed order (the A rows of a single stream are copies: every lane's own accumulator equals lane t's)
           float s0 = 0.f, s1 = 0.f;
-          const uint32_t q0 = c.scratch + (uint32_t)(warp * 32 + t) * 8u;
+          const uint32_t q0 = pbase + (uint32_t)(wgrp * wpg * 32 + t) * 8u;
           if (g8 != 0 && g8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)g8 * 256u); s0 = v.x; s1 = v.y; }
           if (g8 + 8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)(g8 + 8) * 256u); s0 += v.x; s1 += v.y; }
           if (g8 == 0) { s0 += y0; s1 += y1; }
@@ -817,7 +890,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
         }
       }
     }
-    if (PROF && r == 0) prof_mark(p, pidx, 10);
+    if (PROF && r == 0) prof_mark(p, pidx, 10, kProfLeader);
     if (kp == 0) {
       if (r != 0) {
         f_word = (sb.grp0 + gi) * wpgrp + f_sub;
@@ -841,7 +914,8 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
       if (PROF) prof_cta_time(p, pidx, 1);
       if (f_lane && f_word < n_words) ll_st(out + (size_t)g8 * ldout + f_word, pack_bf16x2(lo, hi), ep);
-      if (PROF && r == 0) prof_mark(p, pidx, 11);
+      if (PROF && r == 0) prof_mark(p, pidx, 11, kProfLeader);
+      if (PROF && r == 0) prof_warp_time(p, pidx, 7);
       if (wpg == 1) {  // a group of one warp hands its own stages back
         __syncwarp();
         if (lane == 0) {
@@ -858,7 +932,9 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   cur0.advance(sb.n_stages, c.n_stages);
   cur = cur0;
   gcur = gcur0;
-  if (PROF) prof_mark(p, pidx, 3);
+  gst = ((gst & 1u) ^ 1u) | (fast ? 0u : 2u);
+  if (PROF) prof_mark(p, pidx, 3, kProfLeader);
+  if (PROF) prof_warp_time(p, pidx, 4);
 }
 
 
@@ -2137,9 +2213,22 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
   for (int i = tid; i < p.n_kinds * kConsumerWarps; i += kThreads) resolve_unit(sm.kinds[i / kConsumerWarps], i % kConsumerWarps, sm.units[i]);
   __syncthreads();
 
+  // Register budget: the launch gives every thread 128 (64 K / 512); the producer's warpgroup keeps 56 and the three consumer
+  // warpgroups grow to 152 — room for the weight blocks a consumer prefetches into registers (gemv_phase_consume) without
+  // spilling.
+#ifndef FQ3_SETMAXNREG
+#define FQ3_SETMAXNREG 1
+#endif
+#if FQ3_SETMAXNREG
+  if (tid >= kConsumerThreads) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
+  }
+#endif
   if (tid >= kConsumerThreads) {
     // ------------------------------ producer warp (one thread) ------------------------------
-    if ((tid & 31) == 0) {
+    if (tid == kConsumerThreads) {
       const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_keep_fraction();
       const uint64_t pol_gamma = policy_evict_last();
       RingCur cur{0, 0u}, gcur{0, 0u};
@@ -2170,6 +2259,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
 
   // -------------------------------- consumer warps --------------------------------
   RingCur cur{0, 0u}, gcur{0, 0u};
+  uint32_t gst = 0u;              // GEMV phase state: bit 0 = activation / partial-word buffer, bit 1 = the last phase was multi-row
   int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
   int* frame_done = sm.ctl + 12;  // [4]
   for (int iter = 0; iter < p.n_iters; ++iter) {
@@ -2206,7 +2296,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
       const Phase ph = load_phase(sm.prog, i);
       const uint32_t ep = ep0 + (uint32_t)i + 1u;
       switch (ph.type) {
-        case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, cur, gcur, i, ep); break;
+        case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, cur, gcur, gst, i, ep); break;
         case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
         case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
         default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;

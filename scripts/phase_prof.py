@@ -25,7 +25,7 @@ names = {0: "qkv", 1: "attn", 2: "o", 3: "gu", 4: "down"}
 S = 16
 t0 = min(buf[i * S] for i in range(n) if buf[i * S])
 cols = ["poll", "n0", "n1", "n2", "pre", "mma", "red", "epi", "back"]
-print("GEMV (warp 0): poll = own input words visible; n0 = sum of squares + norm weights; n1 = barrier; n2 = rescale + stage x + barrier; pre = to the first MMA;")
+print("GEMV (thread 0 = a polling warp; red / epi / back = lane 0 of warp 11, the leader of group 0): poll = own input words visible; n0 = sum of squares + norm weights; n1 = barrier; n2 = rescale + stage x + barrier; pre = to the first MMA;")
 print("      mma = k loop of the warp's unit; red = k-parts through shared memory; epi = epilogue + publish; back = hand the stages back")
 print(f"{'ph':>4s} {'kind':5s} {'start':>9s} " + " ".join(f"{x:>6s}" for x in cols))
 agg = collections.defaultdict(lambda: [0] * 12)

@@ -21,14 +21,15 @@ eng.lib.fq3_debug_read_prof(eng.h, buf, N)
 eng.talker_step(0, x, 14, want_logits=False)
 eng.lib.fq3_debug_read_prof(eng.h, buf, N)
 names = {0: "qkv", 1: "attn", 2: "o", 3: "gu", 4: "down"}
+prev_end = None
 for ph in list(range(0, 15)) + list(range(135, 141)):
     kind = names[ph % 5] if ph < 140 else "head"
-    a = [buf[(ph * 160 + wp) * 2] for wp in range(12)]
-    b = [buf[(ph * 160 + wp) * 2 + 1] for wp in range(12)]
+    if kind == "attn": continue
+    def col(k): return [buf[(ph * 160 + 16 * (k >> 1) + wp) * 2 + (k & 1)] for wp in range(12)]
+    a = col(0)
     if not any(a): continue
     t0 = min(v for v in a if v)
-    print(f"ph {ph:3d} {kind:5s} poll-done per warp: " + " ".join(f"{(v - t0) if v else -1:5d}" for v in a))
-    if any(b): print(f"             at-barrier per warp: " + " ".join(f"{(v - t0) if v else -1:5d}" for v in b))
-    for k, nm in ((2, "mma-start"), (3, "mma-end"), (4, "phase-end")):
-        c = [buf[(ph * 160 + 16 * (k >> 1) + wp) * 2 + (k & 1)] for wp in range(12)]
-        if any(c): print(f"             {nm:>10s} per warp: " + " ".join(f"{(v - t0) if v else -1:5d}" for v in c))
+    print(f"ph {ph:3d} {kind:5s} (cycles from the first warp entering the phase; warps 0-7 poll, leaders sit on the high warps)")
+    for k, nm in ((0, "enter"), (5, "poll done"), (6, "at stage bar"), (1, "past stage bar"), (2, "mma start"), (3, "mma end"), (7, "published"), (4, "leave")):
+        c = col(k)
+        if any(c): print(f"    {nm:>14s}: " + " ".join(f"{(v - t0) if v else -1:5d}" for v in c))
