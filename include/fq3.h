@@ -158,6 +158,12 @@ int fq3_apply_repetition_penalty(fq3_engine* e, void* logits_f32, int V, const v
  * stream's codes buffer.  One launch, zero host synchronisations inside. */
 int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_policy* policy,
                       const fq3_subpolicy* sub, void* stream);
+/* Batched multi-request decode (no counterpart in the reference, which is hard-wired to bs = 1: talker_graph.py:46-47,
+ * predictor_graph.py:70-71).  fq3_decode_frames with n_streams <= 4 runs the reference-shaped frame program (two predictor
+ * rows per stream in pass 0).  Above four it runs the "wide" frame program in lock-step groups of up to
+ * fq3_lockstep_group(e) streams (16 where the model's rows fit the staging buffer), one launch per group and chunk: every
+ * stream of a group rides the same weight sweep, a stream's tokens are the ones its single-stream run produces. */
+int fq3_lockstep_group(const fq3_engine* e);
 
 /* The engine's grid may be smaller than the device (128 of 148 SMs by default: every model shape partitions evenly over
  * 128 CTAs) so that other work — the codec decode of the previous streaming chunk — runs beside the frame loop on the

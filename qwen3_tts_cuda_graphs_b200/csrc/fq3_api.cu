@@ -59,9 +59,12 @@ struct fq3_engine {
   int* err_dev = nullptr;
   float* pred_logits_all = nullptr;
   uint8_t* seen_scratch = nullptr;
-  Phase *d_frames = nullptr, *d_pred = nullptr, *d_talker = nullptr, *d_prefill = nullptr, *d_linear = nullptr;
-  std::vector<Phase> h_frames, h_pred, h_talker, h_prefill;  // host copies (shared-memory sizing)
-  int n_frames_ph = 0, n_pred_ph = 0, n_talker_ph = 0, n_prefill_ph = 0;
+  Phase *d_frames = nullptr, *d_pred = nullptr, *d_talker = nullptr, *d_prefill = nullptr, *d_linear = nullptr, *d_wide = nullptr;
+  std::vector<Phase> h_frames, h_pred, h_talker, h_prefill, h_wide;  // host copies (shared-memory sizing)
+  int n_frames_ph = 0, n_pred_ph = 0, n_talker_ph = 0, n_prefill_ph = 0, n_wide_ph = 0;
+  int ref_stages = 0;     // ring stages of a single-stream launch of the frame program (the wide program copies its k-splits)
+  int wide_rows = 0;      // streams per lock-step group of the wide frame program (0: not available for this model)
+  std::vector<uint8_t> in_wpin;  // per stream: the predictor's pass-0 input rows live in BUF_WPIN (1) or in the pair layout (0)
   uint8_t* tiled = nullptr;               // fragment images of every GEMV matrix (fq3_tile_weights_kernel); Phase::w_off indexes it
   size_t tiled_bytes = 0;
   std::vector<std::pair<uint64_t, uint64_t>> tiled_map;  // arena byte offset -> image byte offset
@@ -192,6 +195,61 @@ void push_predictor(std::vector<Phase>& v, fq3_engine* e, bool only) {
   }
 }
 
+// Predictor of the wide frame program (more than four lock-step streams).  Pass 0 of the reference feeds two rows per stream,
+// [past_hidden ; codec_embed(token)] (predictor_graph.py:125-139); here it runs as two single-row passes — 0a: past_hidden at
+// position 0 (it only has to leave its K/V rows behind: no head, no sampler, and the last layer stops after attention), 0b:
+// codec_embed(token) at position 1 — so every GEMV phase stages one row per stream.  Causal attention makes that the same
+// arithmetic.  Input rows come from BUF_WPIN (by stream slot).
+void push_predictor_wide(std::vector<Phase>& v, fq3_engine* e) {
+  const int L = e->pr.d.n_layers;
+  for (int half = 0; half < 2; ++half) {
+    const uint16_t fb = half ? F_WPIN_B : 0;
+    const size_t first = v.size();
+    if (e->desc.has_s2m) {
+      Phase p{};
+      p.type = PH_GEMV; p.stack = ST_PRED; p.aux = 0; p.flags = F_BIAS | F_L2_KEEP | F_IN_PREV | fb;
+      p.in_buf = BUF_WPIN; p.out_buf = BUF_PX; p.w_off = off16(e->desc.s2m_w_off); p.b_off = off16(e->desc.s2m_b_off);
+      p.N = e->pr.d.hidden; p.K = e->tk.d.hidden;
+      p.plan = plan_id(e, p.N, p.K, false);
+      v.push_back(p);
+    }
+    for (int l = 0; l < L; ++l) {
+      const size_t at = v.size();
+      push_layer(e, v, e->pr, ST_PRED, l, false, 0, true);
+      if (l == 0 && !e->desc.has_s2m) {  // layer 0 reads its input and residual rows straight from BUF_WPIN
+        v[at].in_buf = BUF_WPIN; v[at].flags |= F_IN_PREV | fb;
+        v[at + 2].res_buf = BUF_WPIN; v[at + 2].flags |= fb;
+      }
+      if (half == 0) v[at + 1].flags |= F_PASS0A;
+      if (half == 0 && l == L - 1) v.resize(at + 2);
+    }
+    (void)first;
+  }
+  for (int i = 0; i < e->ncb; ++i) {
+    if (i > 0) {
+      if (e->desc.has_s2m) {
+        Phase p{};
+        p.type = PH_GEMV; p.stack = ST_PRED; p.aux = (uint8_t)i; p.flags = F_BIAS | F_L2_KEEP;
+        p.in_buf = BUF_PIN; p.out_buf = BUF_PX; p.w_off = off16(e->desc.s2m_w_off); p.b_off = off16(e->desc.s2m_b_off);
+        p.N = e->pr.d.hidden; p.K = e->tk.d.hidden;
+        p.plan = plan_id(e, p.N, p.K, false);
+        v.push_back(p);
+      }
+      for (int l = 0; l < L; ++l) push_layer(e, v, e->pr, ST_PRED, l, false, (uint8_t)i, true);
+    }
+    Phase h{};
+    h.type = PH_GEMV; h.stack = ST_PRED; h.aux = (uint8_t)i;
+    h.flags = F_PRENORM | F_OUT_F32 | F_L2_KEEP;
+    h.in_buf = BUF_PX; h.out_buf = BUF_LOGITS; h.w_off = off16(e->lm_head_offs[i]);
+    h.g_off = off16(e->pr.d.final_norm_off); h.N = e->pr.d.vocab; h.K = e->pr.d.hidden;
+    h.plan = plan_id(e, h.N, h.K, false);
+    v.push_back(h);
+    Phase sm{};
+    sm.type = PH_SAMPLE; sm.stack = ST_PRED; sm.aux = (uint8_t)i; sm.skind = SMP_PRED;
+    v.push_back(sm);
+  }
+}
+
 void push_talker(std::vector<Phase>& v, fq3_engine* e, bool last_row_head) {
   for (int l = 0; l < e->tk.d.n_layers; ++l) push_layer(e, v, e->tk, ST_TALKER, l, false, 0, false);
   Phase h{};
@@ -268,6 +326,8 @@ void fill_common(fq3_engine* e, LaunchParams& p) {
   if (const char* d = getenv("FQ3_DEBUG")) p.debug = atoi(d);
   p.n_iters = 1;
   p.stream0 = 0;
+  p.wide = 0;
+  p.max_streams = e->desc.max_streams;
 }
 
 int check_device_fault(fq3_engine* e) {
@@ -307,19 +367,37 @@ int reserve_epochs(fq3_engine* e, uint64_t span, cudaStream_t s) {
 
 // Launch the persistent kernel: one CTA per SM, cooperative (all CTAs must be co-resident: they poll each other's words).
 // smem: header | scratch | program | norm-weight slots | activation rows | weight ring (16 KB stages, everything that is left).
-int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t s) {
-  const int grid = e->G;
+// shared-memory carve-up of a launch: fills p.xbuf_bytes / prog_bytes / gam_bytes / n_stages; returns the fixed bytes or < 0
+long carve(fq3_engine* e, LaunchParams& p, const Phase* prog_host) {
   size_t xbytes = 0, gamma_elems = 0;
   for (int i = 0; i < p.n_phases; ++i) {
     const Phase& ph = prog_host[i];
     if (ph.type != PH_GEMV) continue;
     const int M = phase_rows_host(ph, p.n_rows);
-    if (M > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "more activation rows than the GEMV stage takes");
-    xbytes = std::max(xbytes, (size_t)(M == 1 ? 2 : M) * ph.K * 2);  // single-stream rows alternate between two buffers
+    if (M > (p.wide ? kMaxWide : kMaxRows)) return fail(FQ3_E_UNSUPPORTED, "more activation rows than the GEMV stage takes");
+    // single-stream rows alternate between two buffers; the rows of a multi-row phase are padded (kernel: xrow_stride)
+    xbytes = std::max(xbytes, (M == 1 && !p.wide) ? (size_t)4 * ph.K : (size_t)M * ((size_t)ph.K * 2 + 64));
     if (ph.flags & F_PRENORM) gamma_elems = std::max(gamma_elems, (size_t)ph.K);
   }
   p.xbuf_bytes = (int)round_up(xbytes, 2048);
   p.prog_bytes = (int)round_up((size_t)kKindBytes + kUnitBytes + (size_t)p.n_phases * sizeof(Phase), 1024);
+  p.gam_bytes = (int)round_up(gamma_elems * 2, 1024);
+  // Shared memory and L1 share 256 KB per SM: staying at or below the 196 KB carve-out leaves 60 KB of L1 for the table
+  // reads of the attention and sampling phases.
+  const long fixed = kHeaderBytes + kScratchBytes + (long)p.xbuf_bytes + (long)p.prog_bytes + (long)kGammaSlots * p.gam_bytes;
+  const long budget = e->ring_cap > 0 ? (long)e->smem_max : std::min<long>((long)e->smem_max, 196L * 1024);
+  long avail = budget - fixed;
+  if (avail < 6L * kStageBytes) avail = (long)e->smem_max - fixed;
+  if (e->ring_cap > 0) avail = std::min(avail, e->ring_cap);
+  p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
+  if (p.n_stages < 2) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
+  return fixed;
+}
+
+int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t s) {
+  const int grid = e->G;
+  const long fixed = carve(e, p, prog_host);
+  if (fixed < 0) return (int)fixed;
   // one representative phase per GEMV kind (the kernel resolves the kinds at start)
   p.n_kinds = 0;
   for (int i = 0; i < p.n_phases; ++i) {
@@ -331,16 +409,6 @@ int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t 
       p.kind_phase[ph.kind] = (uint16_t)i;
     }
   }
-  p.gam_bytes = (int)round_up(gamma_elems * 2, 1024);
-  // Shared memory and L1 share 256 KB per SM: staying at or below the 196 KB carve-out leaves 60 KB of L1 for the table
-  // reads of the attention and sampling phases.
-  const long fixed = kHeaderBytes + kScratchBytes + (long)p.xbuf_bytes + (long)p.prog_bytes + (long)kGammaSlots * p.gam_bytes;
-  const long budget = e->ring_cap > 0 ? (long)e->smem_max : std::min<long>((long)e->smem_max, 196L * 1024);
-  long avail = budget - fixed;
-  if (avail < 6L * kStageBytes) avail = (long)e->smem_max - fixed;
-  if (e->ring_cap > 0) avail = std::min(avail, e->ring_cap);
-  p.n_stages = (int)std::min<long>(kMaxStages, avail / kStageBytes);
-  if (p.n_stages < 2) return fail(FQ3_E_INVALID, "not enough shared memory for the weight ring");
   const size_t smem = (size_t)fixed + (size_t)p.n_stages * kStageBytes;
   // A round of a GEMV phase (gpr groups x spg stages) must fit in the ring (kernel: gemv_phase_consume).  Shapes that do not
   // (1.7B gate/up: 12 groups x 2 stages per CTA) take fewer groups per round and more warps per group.
@@ -350,17 +418,26 @@ int launch(fq3_engine* e, LaunchParams& p, const Phase* prog_host, cudaStream_t 
     Plan& pl = p.plans[ph.plan];
     if (pl.spg > p.n_stages) return fail(FQ3_E_UNSUPPORTED, "K too large for the weight ring");
     const int g_max = pl.g_base + (pl.g_rem ? 1 : 0);
-    if (std::min(pl.gpr, g_max) * pl.spg > p.n_stages) {
-      pl.gpr = p.n_stages / pl.spg;
+    const bool follow_ref = p.mode == MODE_FRAMES && (p.wide || p.n_rows > 1) && e->ref_stages > 0;
+    if (follow_ref && std::min(pl.gpr, g_max) * pl.spg > e->ref_stages) {
+      // the k-split (warps per group) a single-stream launch of the frame program uses for this shape: a batched launch must
+      // add a row's products in the same order, whatever its own (smaller) ring allows
+      pl.gpr = e->ref_stages / pl.spg;
       pl.wpg = std::max(1, std::min(kConsumerWarps / pl.gpr, pl.nch));
     }
+    if (std::min(pl.gpr, g_max) * pl.spg > p.n_stages) {
+      pl.gpr = p.n_stages / pl.spg;
+      if (!follow_ref) pl.wpg = std::max(1, std::min(kConsumerWarps / pl.gpr, pl.nch));  // batched frame loops: same k-split, more rounds
+    }
   }
+
   const uint64_t span = (uint64_t)p.n_iters * (uint64_t)p.n_phases + 2;
   if ((uint64_t)e->epoch + span >= 0xFFFFFFF0ull) return fail(FQ3_E_INVALID, "LL epochs were not reserved for this launch");
   p.epoch_base = e->epoch;
   e->epoch += (uint32_t)span;
   void* args[] = {&p};
-  CK(cudaLaunchCooperativeKernel(p.prof ? (void*)fq3_stream_kernel<true> : (void*)fq3_stream_kernel<false>, dim3(grid), dim3(kThreads), args, smem, s));
+  void* fn = p.wide ? (void*)fq3_stream_kernel<false, true> : (p.prof ? (void*)fq3_stream_kernel<true, false> : (void*)fq3_stream_kernel<false, false>);
+  CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, s));
   e->launches += 1;
   return 0;
 }
@@ -405,6 +482,22 @@ SubPolicy to_sub(const fq3_subpolicy* q) {
   SubPolicy p{};
   p.do_sample = q->do_sample; p.top_k = q->top_k; p.top_p = q->top_p; p.temperature = q->temperature;
   return p;
+}
+
+// The rows that cross launches — [past_hidden ; codec_embed(token)] of every stream — live in the pair layout (rows 2s, 2s+1 of
+// BUF_PIN / BUF_PX: prefill, set_loop_state and the frame program of up to four streams) or in BUF_WPIN (the wide program).
+// Bring streams [s0, s0 + n) into the layout the next launch reads.
+int sync_pin_layout(fq3_engine* e, int s0, int n, bool to_wpin, cudaStream_t s) {
+  const int pb = e->desc.has_s2m ? BUF_PIN : BUF_PX;
+  for (int i = s0; i < s0 + n; ++i) {
+    if ((e->in_wpin[i] != 0) == to_wpin) continue;
+    fq3_wpin_from_pairs_kernel<<<1, 256, 0, s>>>(reinterpret_cast<LLWord*>(e->bufs[BUF_WPIN]), e->ld[BUF_WPIN], reinterpret_cast<LLWord*>(e->bufs[pb]),
+                                                 e->ld[pb], i, e->desc.max_streams, to_wpin ? 0 : 1);
+    e->launches += 1;
+    CK(cudaGetLastError());
+    e->in_wpin[i] = to_wpin ? 1 : 0;
+  }
+  return 0;
 }
 
 int check_stack(const fq3_stack_desc& d, const char* name) {
@@ -469,10 +562,11 @@ static int create_impl(const fq3_model_desc* desc, fq3_engine* e) {
   }
   if (const char* w = getenv("FQ3_WATCHDOG_MS")) e->watchdog_ns = (unsigned long long)atoll(w) * 1000000ull;
   e->smem_max = (size_t)smem_optin;
-  CK(cudaFuncSetAttribute(fq3_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
-  CK(cudaFuncSetAttribute(fq3_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  CK(cudaFuncSetAttribute(fq3_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  CK(cudaFuncSetAttribute(fq3_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+  CK(cudaFuncSetAttribute(fq3_stream_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fq3_stream_kernel<false>, kThreads, smem_optin));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fq3_stream_kernel<false, false>, kThreads, smem_optin));
   if (occ < 1) return fail(FQ3_E_UNSUPPORTED, "stream kernel does not fit on an SM");
 
   e->ncb = desc->n_code_groups - 1;
@@ -486,7 +580,7 @@ static int create_impl(const fq3_model_desc* desc, fq3_engine* e) {
   e->pr.d.layer_offs = nullptr;
 
   const int B = desc->max_streams;
-  const int R = std::max(2 * B, kMaxRows);
+  const int R = std::max(2 * B, 2 * kMaxRows);
   e->max_rows = R;
   const uint8_t* arena = reinterpret_cast<const uint8_t*>(desc->arena);
   // --- static KV caches (StaticCache of talker_graph.py:43 / predictor_graph.py:61) ---
@@ -525,6 +619,7 @@ static int create_impl(const fq3_model_desc* desc, fq3_engine* e) {
     e->bufs[BUF_PIN] = e->bufs[BUF_PX];
     e->ld[BUF_PIN] = e->ld[BUF_PX];
   }
+  if (mk(BUF_WPIN, Ht / 2, LL, 2 * B)) return -FQ3_E_CUDA;
   e->lin_words = 32768;
   if (mk(BUF_LIN_IN, e->lin_words, LL, kMaxRows) || mk(BUF_LIN_OUT, e->lin_words, LL, kMaxRows) ||
       mk(BUF_LIN_RES, e->lin_words, LL, kMaxRows))
@@ -539,6 +634,7 @@ static int create_impl(const fq3_model_desc* desc, fq3_engine* e) {
   CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->err_dev), e->err_host, 0));
   // --- per-stream state ---
   e->h_st.resize(B);
+  e->in_wpin.assign(B, 0);
   if (dalloc(e, &e->d_st, B)) return -FQ3_E_CUDA;
   for (int b = 0; b < B; ++b) {
     StreamState& s = e->h_st[b];
@@ -576,11 +672,36 @@ static int create_impl(const fq3_model_desc* desc, fq3_engine* e) {
     s.type = PH_SAMPLE; s.stack = ST_TALKER; s.skind = SMP_PREFILL;
     e->h_prefill.push_back(s);
   }
+  push_predictor_wide(e->h_wide, e);
+  push_talker(e->h_wide, e, false);
+  {
+    Phase s{};
+    s.type = PH_SAMPLE; s.stack = ST_TALKER; s.skind = SMP_TALKER;
+    e->h_wide.push_back(s);
+  }
   if (g_plan_fail) { g_plan_fail = false; return fail(FQ3_E_UNSUPPORTED, "a GEMV shape of this model cannot be partitioned (odd N or K % 64)"); }
   e->n_frames_ph = (int)e->h_frames.size();
   e->n_pred_ph = (int)e->h_pred.size();
   e->n_talker_ph = (int)e->h_talker.size();
   e->n_prefill_ph = (int)e->h_prefill.size();
+  e->n_wide_ph = (int)e->h_wide.size();
+  if (upload(e, e->h_wide, &e->d_wide)) return fail(FQ3_E_CUDA, "wide program upload");
+  {
+    // streams per lock-step group of the wide program: the padded activation rows of the longest K next to a ring that holds
+    // one group of that K plus one more stage (at least four stages)
+    const int kmax = std::max(e->tk.kmax(), e->pr.kmax());
+    const long fixed = kHeaderBytes + kScratchBytes + (long)round_up((size_t)kKindBytes + kUnitBytes + (size_t)e->n_wide_ph * sizeof(Phase), 1024) +
+                       (long)kGammaSlots * (long)round_up((size_t)std::max(e->tk.d.hidden, e->pr.d.hidden) * 2, 1024);
+    const long spg_max = ((long)kmax * 16 + kStageBytes - 1) / kStageBytes;
+    const long avail = (long)e->smem_max - fixed - std::max(4L, spg_max + 1) * kStageBytes - 2048;
+    e->wide_rows = (int)std::max<long>(0, std::min<long>(avail / ((long)kmax * 2 + 64), kMaxWide));
+  }
+  {
+    LaunchParams q{};
+    q.n_phases = e->n_frames_ph; q.n_rows = 1;
+    if (carve(e, q, e->h_frames.data()) < 0) return -FQ3_E_INVALID;
+    e->ref_stages = q.n_stages;
+  }
   if (upload(e, e->h_frames, &e->d_frames) || upload(e, e->h_pred, &e->d_pred) || upload(e, e->h_talker, &e->d_talker) ||
       upload(e, e->h_prefill, &e->d_prefill))
     return fail(FQ3_E_CUDA, "program upload / weight tiling (matrix rows must be a multiple of 8)");
@@ -672,6 +793,7 @@ int fq3_set_loop_state(fq3_engine* e, int idx, int token, const void* past_hidde
   const bf16* emb = reinterpret_cast<const bf16*>(reinterpret_cast<const uint8_t*>(e->desc.arena) + e->desc.codec_embed_off) +
                     (size_t)token * Ht;
   CK(cudaMemcpyAsync(hid, past_hidden, (size_t)Ht * 2, cudaMemcpyDeviceToDevice, s));
+  e->in_wpin[idx] = 0;
   if (int r = pack_ll(e, BUF_PIN, 2 * idx, past_hidden, Ht, 1, Ht, s)) return r;
   if (int r = pack_ll(e, BUF_PIN, 2 * idx + 1, emb, Ht, 1, Ht, s)) return r;
   return 0;
@@ -684,7 +806,7 @@ static int prefill_rows(const fq3_engine* e) {
                      (long)kGammaSlots * (long)round_up((size_t)e->tk.d.hidden * 2, 1024);
   const long spg_max = ((long)e->tk.kmax() * 16 + kStageBytes - 1) / kStageBytes;
   const long avail = (long)e->smem_max - fixed - std::max(6L, spg_max + 1) * kStageBytes;
-  return (int)std::max<long>(1, std::min<long>(avail / ((long)e->tk.kmax() * 2), kMaxRows));
+  return (int)std::max<long>(1, std::min<long>(avail / ((long)e->tk.kmax() * 2 + 64), kMaxRows));
 }
 
 // rows [start, T) of the prompt go through the persistent kernel; the K/V rows of [0, start) must already be in the cache
@@ -721,6 +843,7 @@ static int prefill_impl(fq3_engine* e, int idx, const void* embeds_from_start, i
     if (int r = launch(e, p, e->h_prefill.data(), s)) return r;
   }
   fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, T, 0, 8, 0, 0, 0);
+  e->in_wpin[idx] = 0;  // SMP_PREFILL published the stream's predictor rows in the pair layout
   e->launches += 1;
   CK(cudaGetLastError());
   if (out_logits)
@@ -834,9 +957,35 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
                       void* stream) {
   if (!e || !policy || !sub) return fail(FQ3_E_INVALID, "bad decode arguments");
   if (n_streams < 1 || n_streams > e->desc.max_streams) return fail(FQ3_E_INVALID, "n_streams out of range");
-  if (2 * n_streams > kMaxRows) return fail(FQ3_E_UNSUPPORTED, "batched decode above 4 streams is not built");
   if (n_frames <= 0) return 0;
+  if (2 * n_streams > kMaxRows) {
+    // more than four streams: the wide frame program, in lock-step groups of up to wide_rows streams, one launch per group
+    // (a group streams the weights once for all its streams; groups follow each other on the stream)
+    if (e->wide_rows < 1) return fail(FQ3_E_UNSUPPORTED, "this model's rows do not fit the wide frame program's staging buffer");
+    const int n_groups = (n_streams + e->wide_rows - 1) / e->wide_rows;
+    const int per = (n_streams + n_groups - 1) / n_groups;  // even groups
+    // all streams first: a group's working rows overwrite pair-layout rows of other groups' streams
+    if (int r = sync_pin_layout(e, 0, n_streams, true, (cudaStream_t)stream)) return r;
+    for (int s0 = 0; s0 < n_streams; s0 += per) {
+      const int n = std::min(per, n_streams - s0);
+      if (int r = reserve_epochs(e, (uint64_t)n_frames * (uint64_t)e->n_wide_ph + 2, (cudaStream_t)stream)) return r;
+      LaunchParams p{};
+      fill_common(e, p);
+      p.prog = e->d_wide;
+      p.n_phases = e->n_wide_ph;
+      p.mode = MODE_FRAMES;
+      p.wide = 1;
+      p.n_rows = n;
+      p.stream0 = s0;
+      p.n_iters = n_frames;
+      p.pol = to_policy(policy);
+      p.sub = to_sub(sub);
+      if (int r = launch(e, p, e->h_wide.data(), (cudaStream_t)stream)) return r;
+    }
+    return 0;
+  }
   if (int r = reserve_epochs(e, (uint64_t)n_frames * (uint64_t)e->n_frames_ph + 2, (cudaStream_t)stream)) return r;
+  if (int r = sync_pin_layout(e, 0, n_streams, false, (cudaStream_t)stream)) return r;
   LaunchParams p{};
   fill_common(e, p);
   p.prog = e->d_frames;
@@ -856,6 +1005,7 @@ int fq3_set_decode_grid(fq3_engine* e, int n_ctas) {
   if (n_ctas <= 0 || n_ctas == e->G || n_ctas == e->n_sms) return 0;
   return fail(FQ3_E_UNSUPPORTED, "the decode grid is fixed at engine creation (FQ3_GRID)");
 }
+int fq3_lockstep_group(const fq3_engine* e) { return e ? std::max(e->wide_rows, kMaxRows / 2) : 0; }
 int fq3_reduced_grid(const fq3_engine* e) { return (e && e->G < e->n_sms) ? e->G : 0; }
 
 int fq3_clear_fault(fq3_engine* e, void* stream) {

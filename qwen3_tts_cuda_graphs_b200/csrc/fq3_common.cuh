@@ -35,6 +35,7 @@ constexpr int kStageBytes = 16 * 1024;     // ring stage: up to 32 blocks (1024 
 constexpr int kStageChunks = kStageBytes / kBlockBytes;  // 32
 constexpr int kHeadDim = 128;              // talker and predictor heads (asserted on the host)
 constexpr int kMaxRows = 8;                // activation rows (tokens) per launch, GEMV register tile
+constexpr int kMaxWide = 16;               // streams of one lock-step group of the wide frame program: the 16 A rows of mma.m16n8k16
 constexpr int kMaxSplits = 16;             // split-KV partitions per (sequence, kv head)
 constexpr int kSplitLen = 4 * kConsumerWarps;              // positions one CTA sweeps per (row, kv head) before the context is split over CTAs
 constexpr int kPartStride = 132;           // floats per attention partial: m, l, pad, pad, o[128]
@@ -44,14 +45,17 @@ constexpr int kMaxVocab = 5120;            // sampling scratch holds V fp32 logi
 //          attention q rows fp32 [2][128] | fresh K/V rows bf16 [8][2][128] | warp partials [12][2][132] = 17.4 KB;
 //          sampling 20 KB logits + histogram + reductions = 21.5 KB
 constexpr int kScratchBytes = 24 * 1024;
-// smem header: full[16] | empty[16] | ctl[16] | red[8][16] | gfull[4] | gempty[4] | stream consts
+// smem header: full[16] | empty[16] | ctl: go flag, [8..23] frame positions, [24..39] frame done flags | red[16][8] | gfull[4] | gempty[4] |
+// stream consts
 constexpr int kEmptyOffset = 128;
 constexpr int kCtlOffset = 256;
-constexpr int kRedOffset = 320;
-constexpr int kGFullOffset = 832;
-constexpr int kGEmptyOffset = 864;
-constexpr int kStreamConstOffset = 896;  // int [4] n_pad | [4] rope_delta of the streams of this launch
-constexpr int kHeaderBytes = 1024;
+constexpr int kFramePosIdx = 8;          // ints from the start of ctl
+constexpr int kFrameDoneIdx = 8 + kMaxWide;
+constexpr int kRedOffset = 512;          // float [kMaxWide][8]: RMSNorm partial sums per (row, eighth of the row)
+constexpr int kGFullOffset = 1024;
+constexpr int kGEmptyOffset = 1056;
+constexpr int kStreamConstOffset = 1088;  // int [16] n_pad | [16] rope_delta of the streams of this launch
+constexpr int kHeaderBytes = 2048;
 constexpr int kGammaSlots = 4;             // norm-weight vectors in flight (streamed by the producer like the weights)
 constexpr int kMaxPlans = 24;
 
@@ -79,7 +83,12 @@ enum PhaseFlags : uint16_t {
   F_WRITE_NORMED = 128, // CTA 0 also stores the normalised input rows (past_hidden)
   F_L2_KEEP = 256,      // weights are re-read soon (predictor): L2 evict_last hint
   F_ABSPTR = 512,       // fq3_linear: absolute pointers taken from LaunchParams
-  F_SILU = 1024         // out = silu(out) after bias (text_projection fc1, model.py:395-403)
+  F_SILU = 1024,        // out = silu(out) after bias (text_projection fc1, model.py:395-403)
+  // wide frame program (more than four lock-step streams): predictor pass 0 runs as two single-row passes (0a: past_hidden at
+  // position 0, 0b: codec_embed(token) at position 1) whose input rows live in BUF_WPIN, addressed by stream slot
+  F_PASS0A = 2048,      // ATTN: position 0
+  F_WPIN_B = 4096,      // GEMV: BUF_WPIN rows [max_streams + slot] (0b) instead of [slot] (0a)
+  F_IN_PREV = 8192      // GEMV: the input was published by the last phase of the previous iteration (or before the launch)
 };
 
 struct __align__(16) Phase {
@@ -103,7 +112,7 @@ static_assert(sizeof(Phase) == 32, "Phase must stay 32 bytes");
 
 enum BufId : uint8_t {
   BUF_TX = 0, BUF_TQKV, BUF_TATT, BUF_TACT, BUF_PX, BUF_PQKV, BUF_PATT, BUF_PACT, BUF_PIN,
-  BUF_LOGITS, BUF_HID, BUF_LIN_IN, BUF_LIN_OUT, BUF_LIN_RES, BUF_COUNT
+  BUF_LOGITS, BUF_HID, BUF_LIN_IN, BUF_LIN_OUT, BUF_LIN_RES, BUF_WPIN, BUF_COUNT
 };
 
 // Host-computed partition of one GEMV shape (N, K, SwiGLU) over the grid, in groups of 8 consecutive weight rows.
@@ -197,6 +206,8 @@ struct LaunchParams {
   int n_iters;
   int mode;
   int n_rows;    // base row count M (streams for decode, chunk rows for prefill, M for linear)
+  int wide;      // wide frame program: up to kMaxWide streams, pass 0 split, BUF_WPIN
+  int max_streams;
   int stream0;   // first stream index (single-stream entry points)
   int pos_override;  // >=0: talker position for MODE_TALKER_STEP
   int pf_pos0, pf_n_pad, pf_rope_delta, pf_final;

@@ -142,8 +142,8 @@ __device__ __forceinline__ float warp_max(float v) {
 struct Smem {
   uint64_t* full;    // [kMaxStages]
   uint64_t* empty;   // [kMaxStages]
-  int* ctl;          // [0] producer go flag, [8..11] frame positions, [12..15] frame done flags
-  float* red;        // [kMaxRows][16] RMSNorm partial sums
+  int* ctl;          // [0] producer go flag, [kFramePosIdx ..] frame positions, [kFrameDoneIdx ..] frame done flags
+  float* red;        // [kMaxWide][8] RMSNorm partial sums
   unsigned char* scratch;
   KindDesc* kinds;   // [kMaxKinds] resolved GEMV phase kinds
   UnitDesc* units;   // [kMaxKinds][kConsumerWarps]
@@ -409,14 +409,17 @@ __device__ __forceinline__ void resolve_kind(const LaunchParams& p, const Phase&
   int M = (flags & F_ROWS2) ? 2 * p.n_rows : p.n_rows, row_off = 0;
   if (flags & F_LAST_ROW) { row_off = M - 1; M = 1; }
   const int K = (int)ph.K;
+  // rows of BUF_WPIN are addressed by stream slot (they cross launches): [slot] = past_hidden, [max_streams + slot] = codec_embed(token)
+  const int wpin_row = p.stream0 + ((flags & F_WPIN_B) ? p.max_streams : 0);
+  if (ph.in_buf == BUF_WPIN) row_off += wpin_row;
   kd.ldin = p.ld[ph.in_buf];
   kd.in = reinterpret_cast<const LLWord*>(p.bufs[ph.in_buf]) + (size_t)row_off * kd.ldin;
   kd.Kq = K >> 2;
   kd.flags = (int)flags;
   kd.out = reinterpret_cast<LLWord*>(p.bufs[ph.out_buf]);
   kd.ldout = p.ld[ph.out_buf];
-  kd.res = (flags & F_RESID) ? reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) : nullptr;
   kd.ldres = (flags & F_RESID) ? p.ld[ph.res_buf] : 0;
+  kd.res = (flags & F_RESID) ? reinterpret_cast<const LLWord*>(p.bufs[ph.res_buf]) + (size_t)(ph.res_buf == BUF_WPIN ? wpin_row : 0) * kd.ldres : nullptr;
   kd.bias = nullptr;
   if (flags & F_BIAS)
     kd.bias = reinterpret_cast<const uint32_t*>((flags & F_ABSPTR) ? p.lin_bias : static_cast<const void*>(p.arena + (size_t)ph.b_off * 16));
@@ -491,33 +494,54 @@ __device__ __forceinline__ void xquad_store(uint32_t addr, uint32_t lo, uint32_t
   sts_u32(addr + 16u, hi);
 }
 
-// General activation load (several rows, or rows too long for the register path): raw payloads go through shared
-// memory, each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square,
-// x*rsqrt -> bf16, * weight -> bf16.
-__device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
-                                            int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red) {
+// Shared-memory stride of the activation rows of a multi-row phase: 64 bytes of padding put rows g and g + 1 in different
+// banks, so the 16-byte A-fragment loads of a quarter-warp (two rows x four lanes) do not collide.
+__device__ __forceinline__ uint32_t xrow_stride(int K) { return (uint32_t)K * 2u + 64u; }
+
+// Multi-row activation load (several rows, or rows too long for the register path): raw payloads go through shared memory,
+// each thread re-reads exactly what it wrote.  HF rounding points (Qwen3RMSNorm): fp32 mean-square, x*rsqrt -> bf16,
+// * weight -> bf16.  The sum of squares of a row is built exactly as the single-stream register path builds it — eight
+// "virtual warps" per row, lane l of virtual warp v owns quads 32v + l + 256j and adds them in j order, a shuffle tree per
+// virtual warp, the eight sums in a fixed tree — so a stream's arithmetic does not depend on how many streams (or prompt rows)
+// share the launch.  A unit = (row, virtual warp); a warp keeps UNITS units (up to UNITS * kMaxJ 16-byte requests per lane) in flight.
+constexpr int kMaxJ = 6;  // quads per lane of a unit: K <= 6144
+template <int UNITS, int JC>
+__device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
+                                         int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red) {
   const int Kq = K >> 2;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool norm = (flags & F_PRENORM) != 0;
+  const int n_units = M * 8;
+  const uint32_t rstride = xrow_stride(K);
+  const float inv_k = __frcp_rn((float)K);  // = the host's 1.0f / K (Plan::inv_k)
+  FQ3_ASSERT(Kq <= 256 * kMaxJ && M <= kMaxWide, pidx, 310000 + M);
 #pragma unroll 1
-  for (int m = 0; m < M; ++m) {
-    const LLWord* src = in + (size_t)m * ld;
-    const uint32_t xrow = xs + (uint32_t)m * xrow_bytes(K);
-    float ss = 0.f;
+  for (int u0 = warp; u0 < n_units; u0 += UNITS * kConsumerWarps) {
+    float ss[UNITS];
+#pragma unroll
+    for (int h = 0; h < UNITS; ++h) ss[h] = 0.f;
 #pragma unroll 1
-    for (int q0 = 0; q0 < Kq; q0 += 2 * kConsumerThreads) {
-      uint4 w[2];
+    for (int j0 = 0; j0 * 256 < Kq; j0 += JC) {  // JC quads per lane and unit at a time
+      uint4 w[UNITS][JC];
       Spin spin;
       bool bad;
       unsigned tries = 0;
       do {
         bad = false;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int q = q0 + tid + i * kConsumerThreads;
-          if (q < Kq) {
-            w[i] = ll_ld_pair(src + 2 * q);
-            bad |= (w[i].y != ep_in) | (w[i].w != ep_in);
+        for (int h = 0; h < UNITS; ++h) {
+          const int u = u0 + h * kConsumerWarps;
+          if (u < n_units) {
+            const LLWord* src = in + (size_t)(u >> 3) * ld;
+            const int qb = (u & 7) * 32 + lane + 256 * j0;
+#pragma unroll
+            for (int j = 0; j < JC; ++j) {
+              const int q = qb + 256 * j;
+              if (q < Kq) {
+                w[h][j] = ll_ld_pair(src + 2 * q);
+                bad |= (w[h][j].y != ep_in) | (w[h][j].w != ep_in);
+              }
+            }
           }
         }
         if (ep_in == 0) break;
@@ -527,32 +551,46 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
         }
       } while (bad);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int q = q0 + tid + i * kConsumerThreads;
-        if (q < Kq) {
-          xquad_store(xrow + xquad_off(q), w[i].x, w[i].z);
-          const float x0 = bf_lo(w[i].x), x1 = bf_hi(w[i].x), x2 = bf_lo(w[i].z), x3 = bf_hi(w[i].z);
-          ss += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
+      for (int h = 0; h < UNITS; ++h) {
+        const int u = u0 + h * kConsumerWarps;
+        if (u < n_units) {
+          const int qb = (u & 7) * 32 + lane + 256 * j0;
+          const uint32_t xrow = xs + (uint32_t)(u >> 3) * rstride;
+#pragma unroll
+          for (int j = 0; j < JC; ++j) {
+            const int q = qb + 256 * j;
+            if (q < Kq) {
+              xquad_store(xrow + xquad_off(q), w[h][j].x, w[h][j].z);
+              const float x0 = bf_lo(w[h][j].x), x1 = bf_hi(w[h][j].x), x2 = bf_lo(w[h][j].z), x3 = bf_hi(w[h][j].z);
+              ss[h] += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);  // first quad: 0 + sq = sq exactly
+            }
+          }
         }
       }
     }
     if (norm) {
-      ss = warp_sum(ss);
-      if (lane == 0) sts_f32(red + (uint32_t)(m * 16 + warp) * 4u, ss);
+#pragma unroll
+      for (int h = 0; h < UNITS; ++h) {
+        const int u = u0 + h * kConsumerWarps;
+        if (u < n_units) {
+          const float t = warp_sum(ss[h]);
+          if (lane == 0) sts_f32(red + (uint32_t)u * 4u, t);
+        }
+      }
     }
   }
   cbar_sync();
   if (!norm) return;
 #pragma unroll 1
-  for (int m = 0; m < M; ++m) {
-    float tot = 0.f;
-#pragma unroll
-    for (int wi = 0; wi < kConsumerWarps; ++wi) tot += lds_f32(red + (uint32_t)(m * 16 + wi) * 4u);
-    const float rs = rsqrtf(tot / (float)K + eps);
+  for (int u = warp; u < n_units; u += kConsumerWarps) {
+    const int m = u >> 3, qb = (u & 7) * 32 + lane;
+    const float4 r0 = lds_f32x4(red + (uint32_t)m * 32u), r1 = lds_f32x4(red + (uint32_t)m * 32u + 16u);
+    const float tot = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w));
+    const float rs = rsqrtf(fmaf(tot, inv_k, eps));
     const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
-    const uint32_t xrow = xs + (uint32_t)m * xrow_bytes(K);
+    const uint32_t xrow = xs + (uint32_t)m * rstride;
 #pragma unroll 1
-    for (int q = tid; q < Kq; q += kConsumerThreads) {
+    for (int q = qb; q < Kq; q += 256) {
       const uint2 gg = lds_u32x2(gam + (uint32_t)q * 8u);
       const uint32_t a = xrow + xquad_off(q);
       const uint32_t y0 = norm_pair(lds_u32(a), rs, gg.x), y1 = norm_pair(lds_u32(a + 16u), rs, gg.y);
@@ -561,6 +599,23 @@ __device__ __noinline__ void load_x_general(const LaunchParams& p, uint32_t flag
     }
   }
   cbar_sync();
+}
+
+// Sum of the k-parts of one (stream, output word) in the order the single-stream path adds them (its shuffle tree): part g is
+// paired with part g + 8, the eight pairs are added as ((0+1)+(2+3))+((4+5)+(6+7)).  pa = this lane's word of part 0; parts
+// lie `stride` bytes apart; y0 / y1 enter as the lane's own part-0 sums.
+__device__ __noinline__ float2 tree_parts(float y0, float y1, uint32_t pa, uint32_t stride, int wpg) {
+  float P0[8], P1[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float s0 = 0.f, s1 = 0.f;
+    if (g != 0 && g < wpg) { const float2 v = lds_f32x2(pa + (uint32_t)g * stride); s0 = v.x; s1 = v.y; }
+    if (g + 8 < wpg) { const float2 v = lds_f32x2(pa + (uint32_t)(g + 8) * stride); s0 += v.x; s1 += v.y; }
+    if (g == 0) { s0 += y0; s1 += y1; }
+    P0[g] = s0; P1[g] = s1;
+  }
+  return make_float2(((P0[0] + P0[1]) + (P0[2] + P0[3])) + ((P0[4] + P0[5]) + (P0[6] + P0[7])),
+                     ((P1[0] + P1[1]) + (P1[2] + P1[3])) + ((P1[4] + P1[5]) + (P1[6] + P1[7])));
 }
 
 template <bool PROF>
@@ -602,7 +657,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const uint4 k4 = lds128(kda + 64u);  // spg | nch | ro_shift | n_stages
   const uint4 k5 = lds128(kda + 80u);  // eps | inv_k | n_rounds | wpgrp
   const int M = (int)k6.x, n_words = (int)k6.y, K = (int)k6.z;
-  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0 && M * K * 2 <= p.xbuf_bytes, pidx, 300000 + M);
+  FQ3_ASSERT(M >= 1 && M <= kMaxRows && (K & 63) == 0 && (M == 1 ? 2 * K * 2 : M * (int)xrow_stride(K)) <= p.xbuf_bytes, pidx, 300000 + M);
   struct { int g, grp0, n_stages; } sb = {(int)k3.x, (int)k3.y, (int)k4.w};
   const int wpg = (int)k3.z, gpr = (int)k3.w, spg = (int)k4.x, ro_shift = (int)k4.z;
   const int g8 = lane >> 2, t = lane & 3;
@@ -623,7 +678,7 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   const uint32_t xs = c.xs + (fast ? par * c.xhalf : 0u);
   uint32_t xdst0 = xs + xquad_off(tid), xdst1 = xs + xquad_off(tid + kPollThreads), xdst2 = xs + xquad_off(tid + 2 * kPollThreads);
   // A rows: stream min(g8, M - 1) (rows beyond M repeat the last stream; their results are not read)
-  uint32_t xrow = xs + (uint32_t)min(g8, M - 1) * xrow_bytes(K) + (uint32_t)t * 16u;
+  uint32_t xrow = xs + (uint32_t)min(g8, M - 1) * xrow_stride(K) + (uint32_t)t * 16u;
   const uint32_t lane_w = (uint32_t)lane * 16u;
   const uint32_t pbase = c.scratch + par * (uint32_t)(kConsumerWarps * 32 * 8);
   uint32_t pdst = pbase + (uint32_t)((wgrp * wpg + kp) * 32 + lane) * 8u;  // this lane's partial word (two fp32), by unit
@@ -764,8 +819,8 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
       Spin spin;
       while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
     }
-    load_x_general(p, flags, in, (int)lds_u32(kda + 112u), gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.xs, c.red);
-    if (norm) {  // load_x_general ends with a barrier after the last read of the norm weights
+    load_x_rows<1, 3>(p, flags, in, (int)lds_u32(kda + 112u), gsrc - (uint32_t)tid * 8u, eps, K, M, ep_in, pidx, c.xs, c.red);
+    if (norm) {  // load_x_rows ends with a barrier after the last read of the norm weights
       if (lane == 0) mbar_arrive_a(gemptyb);
     }
   }
@@ -882,11 +937,25 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
           }
           y0 = s0; y1 = s1;
         } else {
+          // many parts, several streams: the single-stream tree once per stream (stream m's own sums sit in lanes (m, t));
+          // lane (m, t) keeps the result
+          float r0 = y0, r1 = y1;
 #pragma unroll 1
-          for (int k2 = 1; k2 < wpg; ++k2) {
-            const float2 v = lds_f32x2(pdst + (uint32_t)k2 * 256u);
-            y0 += v.x; y1 += v.y;
+          for (int m = 0; m < M; ++m) {
+            float s0 = 0.f, s1 = 0.f;
+            const uint32_t q0 = pbase + (uint32_t)(wgrp * wpg * 32 + m * 4 + t) * 8u;
+            if (g8 != 0 && g8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)g8 * 256u); s0 = v.x; s1 = v.y; }
+            if (g8 + 8 < wpg) { const float2 v = lds_f32x2(q0 + (uint32_t)(g8 + 8) * 256u); s0 += v.x; s1 += v.y; }
+            const float o0 = __shfl_sync(0xffffffffu, y0, m * 4 + t), o1 = __shfl_sync(0xffffffffu, y1, m * 4 + t);
+            if (g8 == 0) { s0 += o0; s1 += o1; }
+#pragma unroll
+            for (int o = 4; o <= 16; o <<= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            }
+            if (g8 == m) { r0 = s0; r1 = s1; }
           }
+          y0 = r0; y1 = r1;
         }
       }
     }
@@ -937,6 +1006,165 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
   if (PROF) prof_warp_time(p, pidx, 4);
 }
 
+
+// GEMV phase of the wide frame program: up to kMaxWide = 16 lock-step streams, all 16 A rows of the MMA in use (rows g8 and
+// g8 + 8 of a lane's fragments are different streams; a lane ends up with two output words).  Same arithmetic per stream as the
+// single-stream path (load_x_rows, tree_parts, the same accumulator chains), so a stream's tokens do not depend on its
+// neighbours.  What grows with the batch is the staging: every CTA polls M * K / 2 LL words per phase.
+__device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& ph, const LaunchParams& p, const KindDesc* kdp, const UnitDesc* udp,
+                                                     RingCur& cur, RingCur& gcur, uint32_t& gst, int pidx, uint32_t ep) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const KindDesc kd = *kdp;
+  const UnitDesc ud = *udp;
+  if (kd.g == 0) return;
+  const uint32_t flags = (uint32_t)kd.flags;
+  const int M = kd.M, K = kd.K, n_words = kd.n_words;
+  const bool norm = (flags & F_PRENORM) != 0;
+  uint32_t ep_in = (pidx == 0 && ep == p.epoch_base + 1) ? 0u : ep - 1;
+  if (flags & F_IN_PREV) {  // rows published by the talker sampler of the previous iteration (epoch = this iteration's base)
+    const uint32_t ep0 = ep - (uint32_t)pidx - 1u;
+    ep_in = (ep0 == p.epoch_base) ? 0u : ep0;
+  }
+  FQ3_ASSERT(M >= 1 && M <= kMaxWide && (K & 63) == 0 && M * (int)xrow_stride(K) <= p.xbuf_bytes, pidx, 320000 + M);
+  const uint32_t gsrc = c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes;
+  const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
+  const uint32_t glap = gcur.lap;
+  if (norm) gcur.advance(1, kGammaSlots);
+  cbar_sync();  // the previous phase's readers of the activation rows / partial words are through
+  if (norm && !mbar_try_wait_a(gfullb, glap)) {
+    Spin spin;
+    while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
+  }
+  load_x_rows<2, 3>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red);
+  if (norm && lane == 0) mbar_arrive_a(gemptyb);
+
+  const int g8 = lane >> 2, t = lane & 3;
+  const int wgrp = ud.wgrp, kp = ud.kp, ch0 = ud.ch0, ch1 = ud.ch1;
+  const int wpg = kd.wpg, gpr = kd.gpr, spg = kd.spg, ro_shift = kd.ro_shift, wpgrp = kd.wpgrp;
+  const bool w_act = wgrp < gpr;
+  const uint32_t rstride = xrow_stride(K);
+  const uint32_t xlo = c.xs + (uint32_t)min(g8, M - 1) * rstride + (uint32_t)t * 16u;
+  const uint32_t xhi = c.xs + (uint32_t)min(g8 + 8, M - 1) * rstride + (uint32_t)t * 16u;
+  const uint32_t lane_w = (uint32_t)lane * 16u;
+  // partial words: [unit][half: streams g8 / g8 + 8][lane] two fp32
+  const uint32_t pdst = c.scratch + (uint32_t)((wgrp * wpg + kp) * 64 + lane) * 8u;
+  const int f_sub = (ro_shift == 1) ? t : (t >> 1);
+  const bool t_ok = (ro_shift == 1) || ((t & 1) == 0);
+#pragma unroll 1
+  for (int r = 0; r < kd.n_rounds; ++r) {
+    if (r != 0) cbar_sync();  // rounds re-use ring slots and partial words (gemv_phase_consume)
+    const int gi = r * gpr + wgrp;
+    if (!(w_act && gi < kd.g)) continue;
+    RingCur my = cur;
+    my.advance(gi * spg + (ch0 >> 5), c.n_stages);
+    {
+      const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
+      Spin spin;
+      while (!mbar_try_wait_a(fb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+    }
+    uint32_t wa = c.ring + lane_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch0 & (kStageChunks - 1)) * kBlockBytes;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    int ch = ch0;
+#pragma unroll 1
+    while (ch < ch1) {
+      if (ch != ch0 && (ch & (kStageChunks - 1)) == 0) {
+        my.advance(1, c.n_stages);
+        const uint32_t fb = c.full + (uint32_t)my.slot * 8u;
+        Spin spin;
+        while (!mbar_try_wait_a(fb, my.lap)) spin.tick(p, DE_FULL_WAIT, pidx, my.slot);
+        wa = c.ring + lane_w + (uint32_t)my.slot * kStageBytes;
+      }
+      const int ce = min(ch1, (ch | (kStageChunks - 1)) + 1);
+      uint32_t xa = (uint32_t)ch * kXBlock;
+      uint4 wv = lds128(wa), xl = lds128(xlo + xa), xh = lds128(xhi + xa);
+#pragma unroll 2
+      for (int n = ce - ch - 1; n > 0; --n) {
+        wa += kBlockBytes;
+        xa += kXBlock;
+        const uint4 wn = lds128(wa), xln = lds128(xlo + xa), xhn = lds128(xhi + xa);
+        mma_bf16(acc, xl.x, xh.x, xl.y, xh.y, wv.x, wv.y);
+        mma_bf16(acc2, xl.z, xh.z, xl.w, xh.w, wv.z, wv.w);
+        wv = wn; xl = xln; xh = xhn;
+      }
+      mma_bf16(acc, xl.x, xh.x, xl.y, xh.y, wv.x, wv.y);
+      mma_bf16(acc2, xl.z, xh.z, xl.w, xh.w, wv.z, wv.w);
+      wa += kBlockBytes;
+      ch = ce;
+    }
+    // lane (g8, t): streams g8 (y[0], y[1]) and g8 + 8 (y[2], y[3]), rows 2t, 2t+1 of group gi
+    float y[4] = {acc[0] + acc2[0], acc[1] + acc2[1], acc[2] + acc2[2], acc[3] + acc2[3]};
+    if (wpg > 1) {
+      if (kp != 0) {
+        sts_f32x2(pdst, y[0], y[1]);
+        sts_f32x2(pdst + 256u, y[2], y[3]);
+      }
+      group_bar_sync(2 + wgrp, wpg * 32);
+      if (kp == 1) {
+        if (lane == 0) {  // every warp of the group is through with the group's stages: hand them back
+          int rs = cur.slot + gi * spg;
+          while (rs >= c.n_stages) rs -= c.n_stages;
+          for (int s2 = 0; s2 < spg; ++s2) {
+            mbar_arrive_a(c.empty + (uint32_t)rs * 8u);
+            if (++rs == c.n_stages) rs = 0;
+          }
+        }
+      } else if (kp == 0) {
+        if (wpg <= 4) {
+#pragma unroll
+          for (int k2 = 1; k2 < 4; ++k2) {
+            if (k2 < wpg) {
+              const float2 v0 = lds_f32x2(pdst + (uint32_t)k2 * 512u), v1 = lds_f32x2(pdst + (uint32_t)k2 * 512u + 256u);
+              y[0] += v0.x; y[1] += v0.y; y[2] += v1.x; y[3] += v1.y;
+            }
+          }
+        } else {
+          const float2 v0 = tree_parts(y[0], y[1], pdst, 512u, wpg), v1 = tree_parts(y[2], y[3], pdst + 256u, 512u, wpg);
+          y[0] = v0.x; y[1] = v0.y; y[2] = v1.x; y[3] = v1.y;
+        }
+      }
+    }
+    if (kp == 0) {
+      const int f_word = (kd.grp0 + gi) * wpgrp + f_sub;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = g8 + 8 * h;
+        const bool f_lane = row < M && t_ok && f_word < n_words;
+        const float y0 = y[2 * h], y1 = y[2 * h + 1];
+        uint32_t res0 = 0u, bias0 = 0u;
+        if (f_lane) {
+          if (flags & F_RESID) res0 = ll_ld(kd.res + (size_t)row * kd.ldres + f_word).x;
+          if (flags & F_BIAS) bias0 = __ldg(kd.bias + f_word);
+        }
+        float lo, hi;
+        if (flags & F_SWIGLU) {
+          const float e = bf16r(bf16r(silu_f(bf16r(y0))) * bf16r(y1));
+          lo = e;
+          hi = __shfl_down_sync(0xffffffffu, e, 1);
+        } else {
+          lo = y0; hi = y1;
+          if (flags & F_BIAS) { lo += bf_lo(bias0); hi += bf_hi(bias0); }
+          lo = bf16r(lo); hi = bf16r(hi);
+          if (flags & F_SILU) { lo = bf16r(silu_f(lo)); hi = bf16r(silu_f(hi)); }
+        }
+        if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
+        if (f_lane) ll_st(kd.out + (size_t)row * kd.ldout + f_word, pack_bf16x2(lo, hi), ep);
+      }
+      if (wpg == 1) {
+        __syncwarp();
+        if (lane == 0) {
+          int rs = cur.slot + gi * spg;
+          while (rs >= c.n_stages) rs -= c.n_stages;
+          for (int s2 = 0; s2 < spg; ++s2) {
+            mbar_arrive_a(c.empty + (uint32_t)rs * 8u);
+            if (++rs == c.n_stages) rs = 0;
+          }
+        }
+      }
+    }
+  }
+  cur.advance(kd.n_stages, c.n_stages);
+  gst = ((gst & 1u) ^ 1u) | 2u;
+}
 
 // Producer side of one GEMV phase: stream this CTA's groups through the ring, one contiguous bulk copy per stage (up to
 // 16 KB = 1024 columns of one group's image).  The phase's norm weights travel in the same stream.  Returns false when the
@@ -1015,11 +1243,11 @@ __device__ __forceinline__ Group get_group(const Phase& ph, const LaunchParams& 
     // result is discarded (done = 2), so any in-range row will do (generate.py:174-177 returns one frame and breaks)
     r.pos0 = min((p.pos_override >= 0) ? p.pos_override : frame_pos[g], p.stacks[ST_TALKER].max_pos - 1);
     // launch constants of the stream, parked in shared memory by the frame loop (two L2 round trips per attention phase otherwise)
-    const int* sconst = frame_pos + (kStreamConstOffset - kCtlOffset) / 4 - 8;
+    const int* sconst = frame_pos + (kStreamConstOffset - kCtlOffset) / 4 - kFramePosIdx;
     r.n_pad = sconst[g];
-    r.rope_delta = sconst[4 + g];
+    r.rope_delta = sconst[kMaxWide + g];
   } else {
-    r.pos0 = (ph.flags & F_ROWS2) ? 0 : (int)ph.aux + 1;
+    r.pos0 = (ph.flags & (F_ROWS2 | F_PASS0A)) ? 0 : (int)ph.aux + 1;
     r.n_pad = 0;
     r.rope_delta = 0;
   }
@@ -1462,9 +1690,10 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& 
     }
     return;
   }
-  int nrows_tot = 0;
-  for (int g = 0; g < ng; ++g) nrows_tot += get_group(ph, p, g, frame_pos).nrows;
-  const int cap = max(1, min(small_div(G, max(1, nrows_tot * S.nkv)), kMaxSplits));
+  // The split structure of a row depends on its context length alone (the same cap as the single-stream case above), so a
+  // stream's attention arithmetic does not change with the number of streams in the launch; with more items than CTAs a
+  // CTA takes several, and every CTA publishes all its partials before it waits for anybody else's (two passes).
+  const int cap = max(1, min(small_div(G, S.nkv), kMaxSplits));
   int total = 0;
   for (int g = 0; g < ng; ++g) {
     const Group gr = get_group(ph, p, g, frame_pos);
@@ -1481,23 +1710,27 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& 
     first = cta;
     step = G;
   }
-  for (int item = first; item < total; item += step) {
-    int base = 0;
-    bool found = false;
-    for (int g = 0; g < ng && !found; ++g) {
-      const Group gr = get_group(ph, p, g, frame_pos);
-      for (int r = 0; r < gr.nrows; ++r) {
-        const int nsplit = num_splits(gr.pos0 + r + 1 - gr.n_pad, cap);
-        const int nitems = S.nkv * nsplit;
-        if (item < base + nitems) {
-          const int it = item - base;
-          const int kvh = small_div(it, nsplit), sp = it - kvh * nsplit;
-          attn_row<PROF>(ph, p, smem_base, gr, r, kvh, sp, nsplit, ep, pidx);
-          if (nsplit > 1 && sp == 0) attn_combine(ph, p, gr, r, kvh, nsplit, ep, pidx);
-          found = true;
-          break;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+    for (int item = first; item < total; item += step) {
+      int base = 0;
+      bool found = false;
+      for (int g = 0; g < ng && !found; ++g) {
+        const Group gr = get_group(ph, p, g, frame_pos);
+        for (int r = 0; r < gr.nrows; ++r) {
+          const int nsplit = num_splits(gr.pos0 + r + 1 - gr.n_pad, cap);
+          const int nitems = S.nkv * nsplit;
+          if (item < base + nitems) {
+            const int it = item - base;
+            const int kvh = small_div(it, nsplit), sp = it - kvh * nsplit;
+            if (pass == 0) attn_row<PROF>(ph, p, smem_base, gr, r, kvh, sp, nsplit, ep, pidx);
+            else if (nsplit > 1 && sp == 0) attn_combine(ph, p, gr, r, kvh, nsplit, ep, pidx);
+            found = true;
+            break;
+          }
+          base += nitems;
         }
-        base += nitems;
       }
     }
   }
@@ -2051,6 +2284,7 @@ __device__ __forceinline__ void publish_row(LLWord* dst, const bf16* src, int n,
   for (int c = threadIdx.x; c < (n >> 1); c += kConsumerThreads) ll_st(dst + c, __ldg(reinterpret_cast<const uint32_t*>(src) + c), ep);
 }
 
+template <bool WIDE>
 __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
                              const int* frame_done) {
   const Smem sm = carve_smem(smem_base, p);
@@ -2169,8 +2403,14 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
       // predictor pass-0 input rows [past_hidden ; codec_embed(token)] (generate.py:154-155), addressed by
       // stream slot; always re-published so every reader sees this phase's epoch
       const bf16* hid = reinterpret_cast<const bf16*>(p.bufs[BUF_HID]) + (size_t)b * p.ld[BUF_HID];
-      publish_row(pin + (size_t)(2 * slot) * ldpin, hid, Ht, ep);
-      publish_row(pin + (size_t)(2 * slot + 1) * ldpin, p.codec_embed + (size_t)tok * Ht, Ht, ep);
+      if constexpr (WIDE) {  // the wide program keeps them in BUF_WPIN (the host converts between the two layouts: fq3_api.cu, sync_pin_layout)
+        LLWord* wp = reinterpret_cast<LLWord*>(p.bufs[BUF_WPIN]);
+        publish_row(wp + (size_t)slot * p.ld[BUF_WPIN], hid, Ht, ep);
+        publish_row(wp + (size_t)(p.max_streams + slot) * p.ld[BUF_WPIN], p.codec_embed + (size_t)tok * Ht, Ht, ep);
+      } else {
+        publish_row(pin + (size_t)(2 * slot) * ldpin, hid, Ht, ep);
+        publish_row(pin + (size_t)(2 * slot + 1) * ldpin, p.codec_embed + (size_t)tok * Ht, Ht, ep);
+      }
       if (threadIdx.x == 0) __threadfence();  // once per step: K/V rows stored by this CTA (see above)
     }
     prof_mark(p, pidx, 6);
@@ -2182,7 +2422,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const LaunchParams
 // =================================================================================================
 // Kernel
 // =================================================================================================
-template <bool PROF>
+template <bool PROF, bool WIDE>
 __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const Smem sm = carve_smem(smem_raw, p);
@@ -2260,8 +2500,8 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
   // -------------------------------- consumer warps --------------------------------
   RingCur cur{0, 0u}, gcur{0, 0u};
   uint32_t gst = 0u;              // GEMV phase state: bit 0 = activation / partial-word buffer, bit 1 = the last phase was multi-row
-  int* frame_pos = sm.ctl + 8;    // [4] talker positions of this iteration
-  int* frame_done = sm.ctl + 12;  // [4]
+  int* frame_pos = sm.ctl + kFramePosIdx;    // [kMaxWide] talker positions of this iteration
+  int* frame_done = sm.ctl + kFrameDoneIdx;  // [kMaxWide]
   for (int iter = 0; iter < p.n_iters; ++iter) {
     const uint32_t ep0 = p.epoch_base + (uint32_t)iter * (uint32_t)p.n_phases;
     if (p.mode == MODE_FRAMES || p.mode == MODE_TALKER_STEP) {
@@ -2274,7 +2514,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
           pos = __ldcg(&st->position);
           int* sconst = reinterpret_cast<int*>(smem_raw + kStreamConstOffset);
           sconst[tid] = __ldcg(&st->n_pad);
-          sconst[4 + tid] = __ldcg(&st->rope_delta);
+          sconst[kMaxWide + tid] = __ldcg(&st->rope_delta);
         } else {
           done = (int)ll_wait(&st->ctl[0], ep0, p, -2);
           pos = (int)ll_wait(&st->ctl[1], ep0, p, -2);
@@ -2296,9 +2536,12 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
       const Phase ph = load_phase(sm.prog, i);
       const uint32_t ep = ep0 + (uint32_t)i + 1u;
       switch (ph.type) {
-        case PH_GEMV: gemv_phase_consume<PROF>(c, ph, p, cur, gcur, gst, i, ep); break;
+        case PH_GEMV:
+          if constexpr (WIDE) gemv_phase_consume_wide(c, ph, p, sm.kinds + ph.kind, sm.units + (int)ph.kind * kConsumerWarps + (tid >> 5), cur, gcur, gst, i, ep);
+          else gemv_phase_consume<PROF>(c, ph, p, cur, gcur, gst, i, ep);
+          break;
         case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
-        case PH_SAMPLE: sample_phase(ph, p, smem_raw, ep, i, frame_done); break;
+        case PH_SAMPLE: sample_phase<WIDE>(ph, p, smem_raw, ep, i, frame_done); break;
         default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
       }
     }
@@ -2365,6 +2608,19 @@ fq3_rep_penalty_kernel(float* logits, int V, const long long* history, int n_his
       x = (x > 0.f) ? x / penalty : x * penalty;
       logits[i] = round_bf16 ? bf16r(x) : x;
     }
+  }
+}
+
+// Wide frame program entry: rows [2 * slot], [2 * slot + 1] of the pair layout -> BUF_WPIN rows [slot], [max_streams + slot]
+// (epoch 0: "written before the launch"), or back.  One block, one stream.
+__global__ void fq3_wpin_from_pairs_kernel(LLWord* wpin, int ldw, LLWord* pairs, int ldp, int slot, int max_streams, int reverse) {
+  for (int c = threadIdx.x; c < ldw; c += blockDim.x) {
+    LLWord* a0 = wpin + (size_t)slot * ldw + c;
+    LLWord* a1 = wpin + (size_t)(max_streams + slot) * ldw + c;
+    LLWord* b0 = pairs + (size_t)(2 * slot) * ldp + c;
+    LLWord* b1 = pairs + (size_t)(2 * slot + 1) * ldp + c;
+    if (reverse) { *b0 = make_uint2(a0->x, 0u); *b1 = make_uint2(a1->x, 0u); }
+    else { *a0 = make_uint2(b0->x, 0u); *a1 = make_uint2(b1->x, 0u); }
   }
 }
 

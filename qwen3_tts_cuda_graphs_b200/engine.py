@@ -233,6 +233,11 @@ class Engine:
         logits.reshape(-1, V)[0].copy_(work)
         return logits
 
+    @property
+    def lockstep_group(self) -> int:
+        """Streams that share one weight sweep of the frame loop (fq3.h: fq3_lockstep_group); more streams run in groups."""
+        return int(self.lib.fq3_lockstep_group(self.h))
+
     def decode_frames(self, n_streams: int, n_frames: int, policy: SamplingPolicy, sub: SubPolicy):
         pol, s = policy.c(), sub.c()
         _lib.check(self.lib.fq3_decode_frames(self.h, int(n_streams), int(n_frames), C.byref(pol), C.byref(s), _stream()))

@@ -1,4 +1,4 @@
-"""Device timing of batched lock-step decode (n_streams = 1, 2, 4) on synthetic weights."""
+"""Device timing of batched lock-step decode (n_streams = 1 .. 64) on synthetic weights."""
 import os, sys, time, json
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,11 +9,13 @@ name = sys.argv[1] if len(sys.argv) > 1 else "0.6B-Base"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 cfg = make_cfg(name)
 w = make_weights(cfg, seed=0, norm_jitter=0.0)
-eng = make_engine(cfg, w, max_seq_len=2048, max_streams=4, max_frames=2048)
+counts = [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else "1,2,4,8,16,32,64".split(","))]
+eng = make_engine(cfg, w, max_seq_len=int(os.environ.get("MAX_SEQ", "1024")), max_streams=max(counts), max_frames=2048)
+print("lockstep group", eng.lockstep_group)
 pol = SamplingPolicy(do_sample=True, temperature=0.9, top_k=50, repetition_penalty=1.05, min_new_tokens=10000)
 sub = SubPolicy(do_sample=True, top_k=50, temperature=0.9)
 ev = lambda: torch.cuda.Event(enable_timing=True)
-for ns in (1, 2, 4):
+for ns in counts:
     for s in range(ns):
         tie, tam, tth, tpe = synth_prompt(cfg, T=14, seed=1 + s)
         eng.set_text_conditioning(s, tth[0].cuda(), tpe.cuda())

@@ -325,6 +325,83 @@ def test_two_streams_match_single_stream(tiny):
     eng.close()
 
 
+def _batch_vs_single(cfg, w, n_streams, n_frames, lens, max_seq_len=256):
+    """Every stream of a lock-step batch must produce exactly the ids of its own single-stream run (greedy + repetition
+    penalty): the wide frame program splits predictor pass 0 in two and stages up to 16 rows, none of which may change a
+    stream's arithmetic."""
+    eng = make_engine(cfg, w, max_streams=n_streams, max_seq_len=max_seq_len)
+    pol = _sp(do_sample=False, repetition_penalty=1.05)
+    sub = _sub(do_sample=False)
+    prompts = [synth_prompt(cfg, T=lens[i % len(lens)], seed=10 + i) for i in range(n_streams)]
+    singles = []
+    for tie, tam, tth, tpe in prompts:
+        eng.set_text_conditioning(0, tth[0].cuda(), tpe.cuda())
+        eng.prefill(0, tie[0].cuda(), 0, pol)
+        eng.decode_frames(1, n_frames, pol, sub)
+        singles.append(eng.read_codes(0, 0, eng.status(0).n_frames))
+    for i, (tie, tam, tth, tpe) in enumerate(prompts):
+        eng.set_text_conditioning(i, tth[0].cuda(), tpe.cuda())
+        eng.prefill(i, tie[0].cuda(), 0, pol)
+    # two launches: the second one starts from the state the first one left on the device
+    eng.decode_frames(n_streams, n_frames // 2, pol, sub)
+    eng.decode_frames(n_streams, n_frames - n_frames // 2, pol, sub)
+    bad = []
+    for i in range(n_streams):
+        st = eng.status(i)
+        assert st.error == 0
+        got = eng.read_codes(i, 0, st.n_frames)
+        if st.n_frames != singles[i].shape[0] or not torch.equal(got, singles[i]):
+            bad.append(i)
+    group = eng.lockstep_group
+    eng.close()
+    assert not bad, (bad, group)
+
+
+@pytest.mark.parametrize("n_streams", [5, 8, 16])
+def test_wide_streams_match_single_stream_tiny(tiny, n_streams):
+    cfg, w, _ = tiny
+    _batch_vs_single(cfg, w, n_streams, 10, lens=[14, 9, 21, 5])
+
+
+def test_wide_groups_match_single_stream_tiny(tiny):
+    """More streams than one lock-step group holds: groups of 16 follow each other (40 streams -> 14 + 13 + 13)."""
+    cfg, w, _ = tiny
+    _batch_vs_single(cfg, w, 40, 6, lens=[14, 9, 21, 5, 30])
+
+
+def test_wide_streams_match_single_stream_real_dims():
+    """0.6B dims (k-parts in shared memory, 3072-column rows, split attention off), two layers each, 16 streams, contexts on both
+    sides of the 48-position short-range attention path."""
+    cfg = make_cfg("0.6B-Base", 2, 2)
+    w = make_weights(cfg, seed=0)
+    _batch_vs_single(cfg, w, 16, 8, lens=[14, 60, 37, 101])
+
+
+def test_normal_program_after_wide_program(tiny):
+    """The two frame programs keep the predictor's cross-launch rows in different layouts; the host converts between them."""
+    cfg, w, _ = tiny
+    eng = make_engine(cfg, w, max_streams=6)
+    pol = _sp(do_sample=False, repetition_penalty=1.05)
+    sub = _sub(do_sample=False)
+    prompts = [synth_prompt(cfg, T=8 + i, seed=30 + i) for i in range(6)]
+    ref = []
+    for tie, tam, tth, tpe in prompts[:2]:
+        eng.set_text_conditioning(0, tth[0].cuda(), tpe.cuda())
+        eng.prefill(0, tie[0].cuda(), 0, pol)
+        eng.decode_frames(1, 9, pol, sub)
+        ref.append(eng.read_codes(0, 0, 9))
+    for i, (tie, tam, tth, tpe) in enumerate(prompts):
+        eng.set_text_conditioning(i, tth[0].cuda(), tpe.cuda())
+        eng.prefill(i, tie[0].cuda(), 0, pol)
+    eng.decode_frames(6, 3, pol, sub)   # wide
+    eng.decode_frames(2, 3, pol, sub)   # reference-shaped program on streams 0, 1
+    eng.decode_frames(6, 3, pol, sub)   # wide again (streams 2-5 are three frames behind)
+    for i in range(2):
+        assert eng.status(i).n_frames == 9
+        assert torch.equal(eng.read_codes(i, 0, 9), ref[i]), i
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # in-kernel samplers (sampling.py:32-66 semantics inside the persistent kernel)
 # ------------------------------------------------------------------------------------------------
