@@ -262,8 +262,9 @@ def main():
     ap.add_argument("--anchor-frames", type=int, default=48, dest="anchor_frames",
                     help="frames timed by the same-box GPU anchor (oracle restated as CUDA-graph replays); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batched-streams", type=int, default=4, dest="batched_streams",
-                    help="extra (reported, not the headline) leg at N=1: this many utterances decoded in lock-step; 0 = skip")
+    ap.add_argument("--batched-streams", type=str, default="4,16,64", dest="batched_streams",
+                    help="extra (reported, not the headline) leg at N=1: this many utterances decoded request-parallel on one GPU "
+                         "(comma list; lock-step groups of up to 16 share a weight sweep); 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -407,33 +408,42 @@ def main():
             },
             "decode_ms_per_frame": avg_ms / args.chunk,
         }
-        if world == 1 and args.batched_streams > 1:
-            # request-parallel decode inside one GPU (BASELINE configs[4]): the same prompt on every stream, non-streaming,
+        batch_sizes = [int(x) for x in str(args.batched_streams).split(",") if x.strip() and int(x) > 1]
+        if world == 1 and batch_sizes:
+            # request-parallel decode inside one GPU (BASELINE configs[3] / [4]): the same prompt on every stream, non-streaming,
             # codec decode of every utterance included; wall clock between synchronisations
             from qwen3_tts_cuda_graphs_b200.generate import fast_generate_batch
-            ns = args.batched_streams
             model_b = FasterQwen3TTS.from_pretrained(f"synthetic://{args.model}", device=dev, dtype=torch.bfloat16,
-                                                     attn_implementation="eager", max_seq_len=2048, seed=0, max_streams=ns)
+                                                     attn_implementation="eager", max_seq_len=1024, seed=0, max_streams=max(batch_sizes))
             mb, _, _, tie_b, tam_b, tth_b, tpe_b, _ = model_b._prepare_generation(TEXT, ref_wav, REF_TEXT, language="English",
                                                                                   non_streaming_mode=True)
-            reqs = [(tie_b, tam_b, tth_b, tpe_b)] * ns
+            by = {}
+            for ns in batch_sizes:
+                reqs = [(tie_b, tam_b, tth_b, tpe_b)] * ns
 
-            def batched_step():
-                codes, _ = fast_generate_batch(model_b.talker_graph, model_b.predictor_graph, reqs, **gen_kw)
-                n = 0
-                for c in codes:
-                    a, sr_b = model_b._decode_full(mb, c)
-                    n += len(a[0])
-                return n / sr_b
+                def batched_step():
+                    codes, _ = fast_generate_batch(model_b.talker_graph, model_b.predictor_graph, reqs, **gen_kw)
+                    n = 0
+                    for c in codes:
+                        a, sr_b = model_b._decode_full(mb, c)
+                        n += len(a[0])
+                    return n / sr_b
 
-            batched_step()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            a_s = sum(batched_step() for _ in range(max(1, args.steps - 1)))
-            torch.cuda.synchronize()
-            line["batched"] = {"streams": ns, "value": a_s / (time.perf_counter() - t0), "unit": UNIT,
-                               "what": "lock-step request-parallel decode of identical prompts on one GPU, non-streaming, codec included"}
+                batched_step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                reps = max(1, args.steps - 1) if ns <= 16 else 1
+                a_s = sum(batched_step() for _ in range(reps))
+                torch.cuda.synchronize()
+                by[str(ns)] = a_s / (time.perf_counter() - t0)
+            line["batched"] = {"by_streams": by, "unit": UNIT, "lockstep_group": model_b.model.engine.lockstep_group,
+                               "streams": max(batch_sizes), "value": by[str(max(batch_sizes))],
+                               "what": "request-parallel decode of identical prompts on one GPU (groups of up to lockstep_group streams share "
+                                       "every weight sweep; more streams run group after group), non-streaming, max_seq_len 1024, prefill and "
+                                       "codec decode of every utterance included"}
             model_b.model.engine.close()
+            del model_b
+            torch.cuda.empty_cache()
         if world == 1 and args.anchor_frames > 0:
             # same-box GPU anchor: the reference's execution style — static caches, attention over all slots
             # with a mask, CUDA-graph replays of the talker step and the predictor loop — restated on the same weights

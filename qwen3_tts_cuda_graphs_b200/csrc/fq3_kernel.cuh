@@ -253,6 +253,14 @@ __device__ __forceinline__ void prof_warp_time(const LaunchParams& p, int pidx, 
 __device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int slot, int thread = 0) {
   if (p.prof && (int)threadIdx.x == thread && (int)blockIdx.x == p.prof_cta && pidx >= 0 && pidx < 512) p.prof[(size_t)pidx * 16 + slot] = clock64();
 }
+// FQ3_PROF=<cta> with the wide program: thread 0 of that CTA adds cycles per category (scripts/wide_prof.py)
+__device__ __forceinline__ void prof_acc(const LaunchParams& p, int cat, long long& t, int thread = 0) {
+  if (p.prof && (int)threadIdx.x == thread && (int)blockIdx.x == p.prof_cta) {
+    const long long now = clock64();
+    p.prof[cat] += now - t;
+    t = now;
+  }
+}
 constexpr int kProfLeader = (kConsumerWarps - 1) * 32;  // lane 0 of warp 11: the leader of group 0 (resolve_unit)
 
 // SiLU in fp32; the result is rounded to bf16 right away, so the fast exp / divide (a few ulp of fp32) do not show
@@ -507,7 +515,7 @@ __device__ __forceinline__ uint32_t xrow_stride(int K) { return (uint32_t)K * 2u
 constexpr int kMaxJ = 6;  // quads per lane of a unit: K <= 6144
 template <int UNITS, int JC>
 __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
-                                         int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red) {
+                                         int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red, long long* tprof = nullptr) {
   const int Kq = K >> 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool norm = (flags & F_PRENORM) != 0;
@@ -523,48 +531,52 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
 #pragma unroll 1
     for (int j0 = 0; j0 * 256 < Kq; j0 += JC) {  // JC quads per lane and unit at a time
       uint4 w[UNITS][JC];
-      Spin spin;
-      bool bad;
-      unsigned tries = 0;
-      do {
-        bad = false;
-#pragma unroll
-        for (int h = 0; h < UNITS; ++h) {
-          const int u = u0 + h * kConsumerWarps;
-          if (u < n_units) {
-            const LLWord* src = in + (size_t)(u >> 3) * ld;
-            const int qb = (u & 7) * 32 + lane + 256 * j0;
-#pragma unroll
-            for (int j = 0; j < JC; ++j) {
-              const int q = qb + 256 * j;
-              if (q < Kq) {
-                w[h][j] = ll_ld_pair(src + 2 * q);
-                bad |= (w[h][j].y != ep_in) | (w[h][j].w != ep_in);
-              }
-            }
-          }
-        }
-        if (ep_in == 0) break;
-        if (bad) {
-          if (++tries > 4) __nanosleep(40);
-          spin.tick(p, DE_LL_WAIT, pidx, (int)ep_in);
-        }
-      } while (bad);
 #pragma unroll
       for (int h = 0; h < UNITS; ++h) {
         const int u = u0 + h * kConsumerWarps;
-        if (u < n_units) {
-          const int qb = (u & 7) * 32 + lane + 256 * j0;
-          const uint32_t xrow = xs + (uint32_t)(u >> 3) * rstride;
+        const LLWord* src = in + (size_t)(u >> 3) * ld;
+        const int qb = (u & 7) * 32 + lane + 256 * j0;
 #pragma unroll
-          for (int j = 0; j < JC; ++j) {
-            const int q = qb + 256 * j;
-            if (q < Kq) {
-              xquad_store(xrow + xquad_off(q), w[h][j].x, w[h][j].z);
-              const float x0 = bf_lo(w[h][j].x), x1 = bf_hi(w[h][j].x), x2 = bf_lo(w[h][j].z), x3 = bf_hi(w[h][j].z);
-              ss[h] += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);  // first quad: 0 + sq = sq exactly
-            }
+        for (int j = 0; j < JC; ++j) {
+          w[h][j] = make_uint4(0u, ep_in, 0u, ep_in);  // absent quads: payload 0, never waited for
+          if (u < n_units && qb + 256 * j < Kq) w[h][j] = ll_ld_pair(src + 2 * (qb + 256 * j));
+        }
+      }
+      if (ep_in != 0) {
+        Spin spin;
+        unsigned tries = 0;
+        while (true) {
+          bool bad = false;
+#pragma unroll
+          for (int h = 0; h < UNITS; ++h) {
+#pragma unroll
+            for (int j = 0; j < JC; ++j) bad |= (w[h][j].y != ep_in) | (w[h][j].w != ep_in);
           }
+          if (!bad) break;
+          if (++tries > 4) __nanosleep(40);
+          spin.tick(p, DE_LL_WAIT, pidx, (int)ep_in);
+#pragma unroll
+          for (int h = 0; h < UNITS; ++h) {  // only the quads that are still missing are requested again
+            const int u = u0 + h * kConsumerWarps;
+            const LLWord* src = in + (size_t)(u >> 3) * ld;
+            const int qb = (u & 7) * 32 + lane + 256 * j0;
+#pragma unroll
+            for (int j = 0; j < JC; ++j)
+              if ((w[h][j].y != ep_in) | (w[h][j].w != ep_in)) w[h][j] = ll_ld_pair(src + 2 * (qb + 256 * j));
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < UNITS; ++h) {
+        const int u = u0 + h * kConsumerWarps;
+        const int qb = (u & 7) * 32 + lane + 256 * j0;
+        const uint32_t xrow = xs + (uint32_t)(u >> 3) * rstride;
+#pragma unroll
+        for (int j = 0; j < JC; ++j) {
+          const int q = qb + 256 * j;
+          if (u < n_units && q < Kq) xquad_store(xrow + xquad_off(q), w[h][j].x, w[h][j].z);
+          const float x0 = bf_lo(w[h][j].x), x1 = bf_hi(w[h][j].x), x2 = bf_lo(w[h][j].z), x3 = bf_hi(w[h][j].z);
+          ss[h] += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);  // first quad: 0 + sq = sq exactly; absent quads add 0
         }
       }
     }
@@ -572,33 +584,40 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
 #pragma unroll
       for (int h = 0; h < UNITS; ++h) {
         const int u = u0 + h * kConsumerWarps;
-        if (u < n_units) {
-          const float t = warp_sum(ss[h]);
-          if (lane == 0) sts_f32(red + (uint32_t)u * 4u, t);
+        const float t = warp_sum(ss[h]);
+        if (u < n_units && lane == 0) sts_f32(red + (uint32_t)u * 4u, t);
+      }
+    }
+  }
+  cbar_sync();
+  if (tprof) prof_acc(p, 1, *tprof);
+  if (!norm) return;
+  // rescale: UNITS units of a warp side by side (independent chains); the norm phases have K <= 2048, two quads per lane
+#pragma unroll 1
+  for (int u0 = warp; u0 < n_units; u0 += UNITS * kConsumerWarps) {
+#pragma unroll
+    for (int h = 0; h < UNITS; ++h) {
+      const int u = u0 + h * kConsumerWarps;
+      if (u < n_units) {
+        const int m = u >> 3, qb = (u & 7) * 32 + lane;
+        const float4 r0 = lds_f32x4(red + (uint32_t)m * 32u), r1 = lds_f32x4(red + (uint32_t)m * 32u + 16u);
+        const float tot = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w));
+        const float rs = rsqrtf(fmaf(tot, inv_k, eps));
+        const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
+        const uint32_t xrow = xs + (uint32_t)m * rstride;
+#pragma unroll 2
+        for (int q = qb; q < Kq; q += 256) {
+          const uint2 gg = lds_u32x2(gam + (uint32_t)q * 8u);
+          const uint32_t a = xrow + xquad_off(q);
+          const uint32_t y0 = norm_pair(lds_u32(a), rs, gg.x), y1 = norm_pair(lds_u32(a + 16u), rs, gg.y);
+          xquad_store(a, y0, y1);
+          if (wr) reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID])[q] = make_uint2(y0, y1);
         }
       }
     }
   }
   cbar_sync();
-  if (!norm) return;
-#pragma unroll 1
-  for (int u = warp; u < n_units; u += kConsumerWarps) {
-    const int m = u >> 3, qb = (u & 7) * 32 + lane;
-    const float4 r0 = lds_f32x4(red + (uint32_t)m * 32u), r1 = lds_f32x4(red + (uint32_t)m * 32u + 16u);
-    const float tot = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w));
-    const float rs = rsqrtf(fmaf(tot, inv_k, eps));
-    const bool wr = (flags & F_WRITE_NORMED) && (int)blockIdx.x == (m % (int)gridDim.x);
-    const uint32_t xrow = xs + (uint32_t)m * rstride;
-#pragma unroll 1
-    for (int q = qb; q < Kq; q += 256) {
-      const uint2 gg = lds_u32x2(gam + (uint32_t)q * 8u);
-      const uint32_t a = xrow + xquad_off(q);
-      const uint32_t y0 = norm_pair(lds_u32(a), rs, gg.x), y1 = norm_pair(lds_u32(a + 16u), rs, gg.y);
-      xquad_store(a, y0, y1);
-      if (wr) reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.bufs[BUF_HID]) + (size_t)m * p.ld[BUF_HID])[q] = make_uint2(y0, y1);
-    }
-  }
-  cbar_sync();
+  if (tprof) prof_acc(p, 2, *tprof);
 }
 
 // Sum of the k-parts of one (stream, output word) in the order the single-stream path adds them (its shuffle tree): part g is
@@ -1030,17 +1049,38 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
   const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
   const uint32_t glap = gcur.lap;
   if (norm) gcur.advance(1, kGammaSlots);
+  long long tp = p.prof ? clock64() : 0ll;
   cbar_sync();  // the previous phase's readers of the activation rows / partial words are through
+  prof_acc(p, 0, tp);
   if (norm && !mbar_try_wait_a(gfullb, glap)) {
     Spin spin;
     while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
   }
-  load_x_rows<2, 3>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red);
+  // the output lanes' residual / bias words are older than this phase's input: request them now, under the poll
+  const int g8 = lane >> 2, t = lane & 3;
+  const int f_sub = (kd.ro_shift == 1) ? t : (t >> 1);
+  const bool t_ok = (kd.ro_shift == 1) || ((t & 1) == 0);
+  uint32_t res_pre[2] = {0u, 0u}, bias_pre = 0u;
+  {
+    const int f_word = (kd.grp0 + ud.wgrp) * kd.wpgrp + f_sub;
+    if (ud.wgrp < kd.gpr && ud.kp == 0 && ud.wgrp < kd.g && t_ok && f_word < n_words) {
+      if (flags & F_RESID) {
+        if (g8 < M) res_pre[0] = ll_ld(kd.res + (size_t)g8 * kd.ldres + f_word).x;
+        if (g8 + 8 < M) res_pre[1] = ll_ld(kd.res + (size_t)(g8 + 8) * kd.ldres + f_word).x;
+      }
+      if (flags & F_BIAS) bias_pre = __ldg(kd.bias + f_word);
+    }
+  }
+  {
+    long long* tpp = p.prof ? &tp : nullptr;
+    if (K <= 1024) load_x_rows<6, 1>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+    else if (K <= 2048) load_x_rows<3, 2>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+    else load_x_rows<2, 3>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+  }
   if (norm && lane == 0) mbar_arrive_a(gemptyb);
 
-  const int g8 = lane >> 2, t = lane & 3;
   const int wgrp = ud.wgrp, kp = ud.kp, ch0 = ud.ch0, ch1 = ud.ch1;
-  const int wpg = kd.wpg, gpr = kd.gpr, spg = kd.spg, ro_shift = kd.ro_shift, wpgrp = kd.wpgrp;
+  const int wpg = kd.wpg, gpr = kd.gpr, spg = kd.spg, wpgrp = kd.wpgrp;
   const bool w_act = wgrp < gpr;
   const uint32_t rstride = xrow_stride(K);
   const uint32_t xlo = c.xs + (uint32_t)min(g8, M - 1) * rstride + (uint32_t)t * 16u;
@@ -1048,8 +1088,6 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
   const uint32_t lane_w = (uint32_t)lane * 16u;
   // partial words: [unit][half: streams g8 / g8 + 8][lane] two fp32
   const uint32_t pdst = c.scratch + (uint32_t)((wgrp * wpg + kp) * 64 + lane) * 8u;
-  const int f_sub = (ro_shift == 1) ? t : (t >> 1);
-  const bool t_ok = (ro_shift == 1) || ((t & 1) == 0);
 #pragma unroll 1
   for (int r = 0; r < kd.n_rounds; ++r) {
     if (r != 0) cbar_sync();  // rounds re-use ring slots and partial words (gemv_phase_consume)
@@ -1065,6 +1103,8 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
     uint32_t wa = c.ring + lane_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch0 & (kStageChunks - 1)) * kBlockBytes;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
     int ch = ch0;
+    long long tq = p.prof ? clock64() : 0ll;
+    if (p.prof) { tq = tp; prof_acc(p, 8, tq, kProfLeader); }  // 8: from the staging barrier to the weights being there
 #pragma unroll 1
     while (ch < ch1) {
       if (ch != ch0 && (ch & (kStageChunks - 1)) == 0) {
@@ -1093,6 +1133,7 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
     }
     // lane (g8, t): streams g8 (y[0], y[1]) and g8 + 8 (y[2], y[3]), rows 2t, 2t+1 of group gi
     float y[4] = {acc[0] + acc2[0], acc[1] + acc2[1], acc[2] + acc2[2], acc[3] + acc2[3]};
+    prof_acc(p, 9, tq, kProfLeader);  // 9: k loop
     if (wpg > 1) {
       if (kp != 0) {
         sts_f32x2(pdst, y[0], y[1]);
@@ -1123,6 +1164,7 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
         }
       }
     }
+    prof_acc(p, 10, tq, kProfLeader);  // 10: k-parts through shared memory
     if (kp == 0) {
       const int f_word = (kd.grp0 + gi) * wpgrp + f_sub;
 #pragma unroll
@@ -1130,8 +1172,8 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
         const int row = g8 + 8 * h;
         const bool f_lane = row < M && t_ok && f_word < n_words;
         const float y0 = y[2 * h], y1 = y[2 * h + 1];
-        uint32_t res0 = 0u, bias0 = 0u;
-        if (f_lane) {
+        uint32_t res0 = res_pre[h], bias0 = bias_pre;
+        if (f_lane && r != 0) {
           if (flags & F_RESID) res0 = ll_ld(kd.res + (size_t)row * kd.ldres + f_word).x;
           if (flags & F_BIAS) bias0 = __ldg(kd.bias + f_word);
         }
@@ -1149,6 +1191,7 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
         if (flags & F_RESID) { lo = bf16r(bf_lo(res0) + lo); hi = bf16r(bf_hi(res0) + hi); }
         if (f_lane) ll_st(kd.out + (size_t)row * kd.ldout + f_word, pack_bf16x2(lo, hi), ep);
       }
+      prof_acc(p, 11, tq, kProfLeader);  // 11: epilogue + publish
       if (wpg == 1) {
         __syncwarp();
         if (lane == 0) {
@@ -1164,6 +1207,8 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
   }
   cur.advance(kd.n_stages, c.n_stages);
   gst = ((gst & 1u) ^ 1u) | 2u;
+  prof_acc(p, 3, tp);
+  if (p.prof && tid == 0 && (int)blockIdx.x == p.prof_cta) p.prof[6] += 1;
 }
 
 // Producer side of one GEMV phase: stream this CTA's groups through the ring, one contiguous bulk copy per stage (up to
@@ -1462,30 +1507,39 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
     }
     if (PROF) prof_mark(p, pidx, 2);
     cbar_sync();
-    if (threadIdx.x < gq * HW) {  // a thread owns one packed output word
-      const int j = threadIdx.x / HW, wd = threadIdx.x - j * HW;
-      const int qh = kvh * gq + j;
-      const int row = gr.first_row + r;
-      const int n = b - a;
-      const float* sj = sc + j * kAttnShort;
-      // the scores beyond n are -inf (cleared at the top of the phase): four at a time
-      const float4* s4 = reinterpret_cast<const float4*>(sj);
-      const int n4 = (n + 3) >> 2;
+    // probabilities once per (head, position) — not once per output word: thread (j, i) finds the head's maximum and stores
+    // exp(s_i - max); the scores beyond n are -inf (cleared at the top of the phase) and give 0
+    float* pr = reinterpret_cast<float*>(vst + kAttnShort * 16);  // [kGq][kAttnShort] | maxima [kGq]
+    const int n = b - a;
+    const int n4 = (n + 3) >> 2;
+    if (threadIdx.x < kGq * kAttnShort) {
+      const int j = threadIdx.x / kAttnShort, i = threadIdx.x - j * kAttnShort;
+      const float4* s4 = reinterpret_cast<const float4*>(sc + j * kAttnShort);
       float Mx = -INFINITY;
       for (int g4 = 0; g4 < n4; ++g4) {
         const float4 v = s4[g4];
         Mx = fmaxf(Mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
       }
+      pr[threadIdx.x] = expf(sc[threadIdx.x] - Mx);
+      if (i == 0) pr[kGq * kAttnShort + j] = Mx;
+    }
+    cbar_sync();
+    if (threadIdx.x < gq * HW) {  // a thread owns one packed output word
+      const int j = threadIdx.x / HW, wd = threadIdx.x - j * HW;
+      const int qh = kvh * gq + j;
+      const int row = gr.first_row + r;
+      const float4* p4 = reinterpret_cast<const float4*>(pr + j * kAttnShort);
+      const float Mx = pr[kGq * kAttnShort + j];
       const uint32_t* vw = reinterpret_cast<const uint32_t*>(vst) + wd;
       float Lsum = 0.f, O0 = 0.f, O1 = 0.f;
 #pragma unroll 2
       for (int g4 = 0; g4 < n4; ++g4) {
-        const float4 v = s4[g4];
-        const float sx[4] = {v.x, v.y, v.z, v.w};
+        const float4 v = p4[g4];
+        const float px[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = 4 * g4 + e;
-          const float pe = expf(sx[e] - Mx);  // 0 beyond n
+          const float pe = px[e];  // 0 beyond n
           const uint32_t v2 = (i < n) ? vw[i * HW] : 0u;
           Lsum += pe;
           O0 = fmaf(pe, bf_lo(v2), O0);
@@ -2540,8 +2594,24 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
           if constexpr (WIDE) gemv_phase_consume_wide(c, ph, p, sm.kinds + ph.kind, sm.units + (int)ph.kind * kConsumerWarps + (tid >> 5), cur, gcur, gst, i, ep);
           else gemv_phase_consume<PROF>(c, ph, p, cur, gcur, gst, i, ep);
           break;
-        case PH_ATTN: attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos); break;
-        case PH_SAMPLE: sample_phase<WIDE>(ph, p, smem_raw, ep, i, frame_done); break;
+        case PH_ATTN:
+          if constexpr (WIDE) {
+            long long tp = p.prof ? clock64() : 0ll;
+            attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos);
+            prof_acc(p, 4, tp);
+          } else {
+            attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos);
+          }
+          break;
+        case PH_SAMPLE:
+          if constexpr (WIDE) {
+            long long tp = p.prof ? clock64() : 0ll;
+            sample_phase<WIDE>(ph, p, smem_raw, ep, i, frame_done);
+            prof_acc(p, 5, tp);
+          } else {
+            sample_phase<WIDE>(ph, p, smem_raw, ep, i, frame_done);
+          }
+          break;
         default: if (tid == 0) device_fault(p, DE_BAD_PHASE, i, ph.type); break;
       }
     }

@@ -122,9 +122,10 @@ def fast_generate(
 def fast_generate_batch(talker_graph, predictor_graph, requests, max_new_tokens: int = 2048, min_new_tokens: int = 2,
                         temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0, do_sample: bool = True,
                         repetition_penalty: float = 1.05, seed: Optional[int] = None):
-    """Request-parallel generation (BASELINE configs[4]; no counterpart in the reference, which is bs = 1): up to
-    `engine.max_streams` independent utterances share every weight sweep of the persistent kernel (lock-step frames; a
-    stream that hit EOS idles until the group is done).  `requests` = list of (talker_input_embeds, attention_mask,
+    """Request-parallel generation (BASELINE configs[3] / [4]; no counterpart in the reference, which is bs = 1): up to
+    `engine.max_streams` independent utterances per call; lock-step groups of up to `engine.lockstep_group` (16) of them share
+    every weight sweep of the persistent kernel (a stream that hit EOS idles until its group is done; more streams than one
+    group run group after group).  `requests` = list of (talker_input_embeds, attention_mask,
     trailing_text_hiddens, tts_pad_embed) as built for fast_generate.  Returns ([codec_ids | None per request], timing).
     Each stream draws from its own Philox stream (seed ^ slot), so a request's tokens do not depend on its neighbours."""
     eng = talker_graph.engine
