@@ -24,12 +24,16 @@ def causal_conv1d(x, w, b, dilation=1):
     return F.conv1d(F.pad(x, (pad, 0)), w, b, dilation=dilation)
 
 
-def causal_trans_conv1d(x, w, b, stride):
-    """Qwen3OmniMoeCausalTransConvNet: ConvTranspose1d then trim (k - stride) on BOTH sides."""
+def causal_trans_conv1d(x, w, b, stride, trim="both"):
+    """ConvTranspose1d, then trim (k - stride).  "both": on BOTH sides, as Qwen3OmniMoeCausalTransConvNet does (the sibling this
+    file is pinned to); "right": at the end only — the causal variant whose length law (stride * T, no lookahead) is the one the
+    reference's own sample WAVs show (every file is k x 1920 samples)."""
     k = w.shape[-1]
     y = F.conv_transpose1d(x, w, b, stride=stride)
     pad = k - stride
-    return y[..., pad: y.shape[-1] - pad] if pad > 0 else y
+    if pad <= 0:
+        return y
+    return y[..., : y.shape[-1] - pad] if trim == "right" else y[..., pad: y.shape[-1] - pad]
 
 
 def snake_beta(x, alpha, beta):
@@ -136,7 +140,7 @@ class CodecOracle:
         for i, r in enumerate(c.upsample_rates):
             p = f"decoder.{i + 1}.block"
             x = snake_beta(x, w[f"{p}.0.alpha"], w[f"{p}.0.beta"])
-            x = causal_trans_conv1d(x, w[f"{p}.1.conv.weight"], w[f"{p}.1.conv.bias"], r)
+            x = causal_trans_conv1d(x, w[f"{p}.1.conv.weight"], w[f"{p}.1.conv.bias"], r, getattr(c, "trans_conv_trim", "both"))
             for j, dil in enumerate((1, 3, 9)):
                 x = self.res_unit(x, f"{p}.{j + 2}", dil)
         n = len(c.upsample_rates) + 1

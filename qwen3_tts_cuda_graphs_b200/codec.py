@@ -10,7 +10,8 @@ bf16 activations (include/fq3_codec.h) and hands the list to ONE C call, `fq3c_r
 same tensor-core implicit-GEMM kernel:
   * causal conv k, dilation d  -> taps k, row offsets -(k-1-j)*d, weights [C_out, k*C_in]
   * transposed conv k=s (ConvNeXt stage) -> one tap, N = s*C_out, output rows [T, s*C_out] == [T*s, C_out]
-  * transposed conv k=2s, stride s, trimmed s on both sides (vocoder) -> two taps (+1, 0), N = s*C_out, M = T-1
+  * transposed conv k=2s, stride s (vocoder) -> two taps, N = s*C_out: trimmed s on the right only (causal; config
+    trans_conv_trim = "right", T*s rows, taps (0, -1)) or s on both sides like the sibling ("both", (T-1)*s rows, taps (+1, 0))
 SnakeBeta is fused into the epilogue of the GEMM that produces its input; bias, GELU, layer-scale and residual adds
 are epilogue flags as well.  Plans (op list + activation buffers) are cached per T, so steady-state streaming
 decode issues no allocation.
@@ -51,16 +52,18 @@ SPLITK_WS_CAP = 64 << 20       # bytes of fp32 workspace one plan may pin
 VOCODER_DILATIONS = (1, 3, 9)  # the three residual units of a decoder block (7-tap causal convs)
 
 
-def vocoder_tail_starts(rows0: int, upsample_rates, skip: int):
+def vocoder_tail_starts(rows0: int, upsample_rates, skip: int, trim: str = "both"):
     """First output row every vocoder op must produce so that waveform samples [skip, n) come out exactly as in a full
-    decode.  Layers, in order: dec0 (7-tap causal conv over `rows0` rows); per block i: transposed conv (kernel 2r, stride r,
-    right-trimmed: output row m*r + k reads input rows m and m+1; (rows-1)*r output rows), then three residual units
-    (7-tap causal conv with dilation d -> reads back 6*d rows; 1x1 conv + residual -> same row); final 7-tap causal conv.
+    decode.  Layers, in order: dec0 (7-tap causal conv over `rows0` rows); per block i: transposed conv (kernel 2r, stride r;
+    trim "both": output row m*r + k reads input rows m and m+1, (rows-1)*r output rows; trim "right": it reads rows m-1 and m,
+    rows*r output rows), then three residual units (7-tap causal conv with dilation d -> reads back 6*d rows; 1x1 conv +
+    residual -> same row); final 7-tap causal conv.
     Returns (dec0_begin, tconv_begin[i] in the transposed conv's own (input) rows, unit_begin[i][j], final_begin)."""
     nblk = len(upsample_rates)
+    right = trim == "right"
     lvl_rows = [rows0]
     for r in upsample_rates:
-        lvl_rows.append((lvl_rows[-1] - 1) * r)
+        lvl_rows.append(lvl_rows[-1] * r if right else (lvl_rows[-1] - 1) * r)
     s_need = max(0, min(int(skip), max(lvl_rows[-1] - 1, 0)))
     fin_begin = s_need
     s_need -= 6
@@ -71,7 +74,7 @@ def vocoder_tail_starts(rows0: int, upsample_rates, skip: int):
             unit_begin[i][j] = max(0, s_need)
             s_need -= 6 * VOCODER_DILATIONS[j]
         tconv_begin[i] = max(0, s_need) // upsample_rates[i]
-        s_need = tconv_begin[i]
+        s_need = tconv_begin[i] - (1 if right else 0)
     return max(0, s_need), tconv_begin, unit_begin, fin_begin
 
 
@@ -416,14 +419,17 @@ class CodecDecoder:
         D = c.decoder_dim
         nblk = len(c.upsample_rates)
         dils = VOCODER_DILATIONS
-        dec0_begin, tconv_begin, unit_begin, fin_begin = vocoder_tail_starts(rows, c.upsample_rates, skip)
+        right = c.trans_conv_trim == "right"
+        dec0_begin, tconv_begin, unit_begin, fin_begin = vocoder_tail_starts(rows, c.upsample_rates, skip, c.trans_conv_trim)
         _, xs = self._gemm(plan, x, g["dec0.w"], rows, D, H, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["dec0.b"],
                            snake="decoder.1.block.0", m_begin=dec0_begin)
         for i, r in enumerate(c.upsample_rates):
             cin, cout = D // 2 ** i, D // 2 ** (i + 1)
             p = f"decoder.{i + 1}.block"
-            m_out = rows - 1
-            y, ys = self._gemm(plan, xs, g[f"{p}.1.w"], m_out, r * cout, cin, taps=2, tap_off=[1, 0], bias=g[f"{p}.1.b"],
+            # weights [W[:, :, :r] | W[:, :, r:]]: trimmed on both sides, output block m = x[m+1] W_lo + x[m] W_hi (m < rows - 1);
+            # trimmed on the right only (causal), block m = x[m] W_lo + x[m-1] W_hi with x[-1] = 0 (m < rows)
+            m_out = rows if right else rows - 1
+            y, ys = self._gemm(plan, xs, g[f"{p}.1.w"], m_out, r * cout, cin, taps=2, tap_off=[0, -1] if right else [1, 0], bias=g[f"{p}.1.b"],
                                col_mod=cout, snake=f"{p}.2.act1", m_begin=tconv_begin[i])
             rows = m_out * r
             x, xs = y.view(-1, cout)[:max(rows, 1)], ys.view(-1, cout)[:max(rows, 1)]
@@ -465,12 +471,7 @@ class CodecDecoder:
             raise CodecError(self.lib.fq3c_last_error().decode())
 
     def n_samples(self, T: int) -> int:
-        rows = T
-        for f in self.cfg.upsampling_ratios:
-            rows *= f
-        for r in self.cfg.upsample_rates:
-            rows = (rows - 1) * r
-        return max(rows, 0)
+        return self.cfg.n_samples(T)
 
     # ---- run ------------------------------------------------------------------------------------
     @torch.inference_mode()

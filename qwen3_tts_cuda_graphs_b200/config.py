@@ -105,6 +105,20 @@ class CodecDecoderConfig:
     upsample_rates: Tuple[int, ...] = (8, 5, 4, 3)
     decoder_dim: int = 1536
     sample_rate: int = 24000
+    # How the vocoder's transposed convolutions (kernel 2r, stride r) are trimmed.
+    #   "right": causal — drop the last r samples only: T frames give exactly total_upsample * T samples (every sample WAV the
+    #            reference ships is k x 1920 samples long) and sample n depends on frames <= n // 1920 alone;
+    #   "both":  r on each side, as the in-container sibling (transformers Qwen3OmniMoeCausalTransConvNet) does:
+    #            1920 * T - 555 samples for the full-size rates, and a block looks one input row ahead.
+    trans_conv_trim: str = "right"
+
+    def n_samples(self, frames: int) -> int:
+        rows = frames
+        for f in self.upsampling_ratios:
+            rows *= f
+        for r in self.upsample_rates:
+            rows = rows * r if self.trans_conv_trim == "right" else (rows - 1) * r
+        return max(rows, 0)
 
     @property
     def total_upsample(self) -> int:

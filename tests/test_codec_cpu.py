@@ -57,7 +57,8 @@ def _oracle_from_sibling(cfg, m):
 
 @pytest.fixture(scope="module")
 def pair():
-    cfg = preset("tiny").codec
+    from dataclasses import replace
+    cfg = replace(preset("tiny").codec, trans_conv_trim="both")  # the sibling trims its transposed convs on both sides
     m = _sibling(cfg)
     return cfg, m, _oracle_from_sibling(cfg, m)
 
@@ -99,6 +100,36 @@ def test_upsample_and_vocoder_equal_sibling(pair, T):
     for r in cfg.upsample_rates:
         n = (n - 1) * r
     assert got.numel() == n
+
+
+def test_causal_trim_length_law_and_causality():
+    """trans_conv_trim = "right" (the default): exactly total_upsample * T samples (1920 * T at the full-size rates, the length
+    of every sample WAV the reference ships) and a strictly causal decoder — appending frames never changes earlier samples,
+    and the variant is the sibling-trimmed decode shifted by one block per transposed conv (same weights, same taps)."""
+    from dataclasses import replace
+    from oracle.codec_oracle import CodecOracle, causal_trans_conv1d
+    from qwen3_tts_cuda_graphs_b200.codec import init_codec_synthetic
+    from qwen3_tts_cuda_graphs_b200.config import CodecDecoderConfig
+    assert CodecDecoderConfig().trans_conv_trim == "right" and CodecDecoderConfig().n_samples(7) == 1920 * 7
+    assert replace(CodecDecoderConfig(), trans_conv_trim="both").n_samples(7) == 1920 * 7 - 555
+    cfg = preset("tiny").codec
+    assert cfg.trans_conv_trim == "right"
+    orc = CodecOracle(cfg, init_codec_synthetic(cfg, seed=3))
+    g = torch.Generator().manual_seed(5)
+    codes = torch.randint(0, cfg.codebook_size, (7, cfg.num_quantizers), generator=g)
+    full = orc.decode(codes)
+    assert full.numel() == cfg.total_upsample * 7 == cfg.n_samples(7)
+    for t in (1, 3, 6):
+        part = orc.decode(codes[:t])
+        assert part.numel() == cfg.total_upsample * t
+        err = float((part - full[: part.numel()]).abs().max())
+        assert err <= 2e-4, (t, err)  # fp32 matmuls of different shapes
+    # one transposed conv: "right" = "both" with one more block in front
+    x = torch.randn(1, 6, 9, generator=g)
+    w = torch.randn(6, 4, 10, generator=g)
+    b = torch.randn(4, generator=g)
+    yr, yb = causal_trans_conv1d(x, w, b, 5, "right"), causal_trans_conv1d(x, w, b, 5, "both")
+    assert yr.shape[-1] == 45 and yb.shape[-1] == 40 and torch.equal(yr[..., 5:], yb)
 
 
 def test_dequantiser_restatement(pair):

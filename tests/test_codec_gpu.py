@@ -23,11 +23,14 @@ def snr_db(got, ref):
     return float(10 * torch.log10(ref.pow(2).sum() / noise.clamp_min(1e-30)))
 
 
-def make(name, seed=1):
+def make(name, seed=1, trim=None):
+    from dataclasses import replace
     from oracle.codec_oracle import CodecOracle
     from qwen3_tts_cuda_graphs_b200.codec import CodecDecoder, init_codec_synthetic
 
     cfg = preset(name).codec
+    if trim is not None:
+        cfg = replace(cfg, trans_conv_trim=trim)
     w = init_codec_synthetic(cfg, seed=seed)
     orc = CodecOracle(cfg, w)
     orc.bf16 = CodecOracle(cfg, {k: v.to(torch.bfloat16) for k, v in w.items()})
@@ -99,15 +102,29 @@ def test_tail_only_decode_full_size():
     assert torch.equal(part[skip:], full[skip:])
 
 
-def test_full_size_decoder_matches_oracle():
-    """Real dims (hidden 1024, 8 layers, window 72, decoder_dim 1536): one streaming chunk of 8 frames."""
-    cfg, dec, orc = make("0.6B-Base", seed=2)
+@pytest.mark.parametrize("trim", ["right", "both"])
+def test_full_size_decoder_matches_oracle(trim):
+    """Real dims (hidden 1024, 8 layers, window 72, decoder_dim 1536): one streaming chunk of 8 frames.  "right" (default):
+    exactly 1920 samples per frame, the reference's length law; "both": the sibling's trim the oracle is pinned with."""
+    cfg, dec, orc = make("0.6B-Base", seed=2, trim=trim)
     T = 8
     codes = torch.randint(0, cfg.codebook_size, (T, cfg.num_quantizers), generator=torch.Generator().manual_seed(1))
     ref = orc.decode(codes)
     got = dec.decode(codes.cuda())
-    assert got.numel() == ref.numel() == 1920 * T - 555
+    assert got.numel() == ref.numel() == (1920 * T if trim == "right" else 1920 * T - 555)
     check_waveform(got, ref, orc.bf16.decode(codes))
+
+
+@pytest.mark.parametrize("T", [2, 8, 33])
+def test_tiny_waveform_matches_oracle_sibling_trim(T):
+    cfg, dec, orc = make("tiny", trim="both")
+    codes = torch.randint(0, cfg.codebook_size, (T, cfg.num_quantizers), generator=torch.Generator().manual_seed(T))
+    ref = orc.decode(codes)
+    got = dec.decode(codes.cuda())
+    assert got.numel() == ref.numel() == dec.n_samples(T)
+    check_waveform(got, ref, orc.bf16.decode(codes))
+    skip = int(round(0.6 * got.numel()))
+    assert torch.equal(dec.decode(codes.cuda(), skip_samples=skip)[skip:], got[skip:])
 
 
 def test_speech_tokenizer_surface(tiny):

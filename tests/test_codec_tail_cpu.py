@@ -6,11 +6,12 @@ import pytest
 from qwen3_tts_cuda_graphs_b200.codec import VOCODER_DILATIONS, vocoder_tail_starts
 
 
-def brute_force(rows0, rates, skip):
+def brute_force(rows0, rates, skip, trim="both"):
     """Needed-row sets, walking the layers backwards with explicit per-row dependencies."""
+    right = trim == "right"
     lvl = [rows0]
     for r in rates:
-        lvl.append((lvl[-1] - 1) * r)
+        lvl.append(lvl[-1] * r if right else (lvl[-1] - 1) * r)
     n = lvl[-1]
     need = set(range(skip, n))                      # final conv output rows
     fin = min(need)
@@ -23,22 +24,23 @@ def brute_force(rows0, rates, skip):
             d = VOCODER_DILATIONS[j]
             need = need | {r - t * d for r in need for t in range(7) if r - t * d >= 0}   # conv1 input (and the residual: same rows)
         r_ = rates[i]
-        rows_in = {q // r_ for q in need} | {q // r_ + 1 for q in need}
+        rows_in = {q // r_ for q in need} | {q // r_ + (-1 if right else 1) for q in need}
         tconv[i] = min(q // r_ for q in need)       # transposed-conv op row m produces output rows m*r .. m*r + r - 1
         need = {m for m in rows_in if 0 <= m < lvl[i]}
     dec0 = min(need)
     return dec0, tconv, units, fin
 
 
+@pytest.mark.parametrize("trim", ["both", "right"])
 @pytest.mark.parametrize("rows0,rates", [(132, (8, 5, 4, 3)), (32, (8, 5, 4, 3)), (36, (2, 2)), (64, (3,)), (9, (4, 3))])
-def test_tail_starts_match_dependency_closure(rows0, rates):
+def test_tail_starts_match_dependency_closure(rows0, rates, trim):
     lvl = [rows0]
     for r in rates:
-        lvl.append((lvl[-1] - 1) * r)
+        lvl.append(lvl[-1] * r if trim == "right" else (lvl[-1] - 1) * r)
     n = lvl[-1]
     for skip in sorted({0, 1, 7, n // 3, n // 2, (3 * n) // 4, n - 1}):
-        got = vocoder_tail_starts(rows0, rates, skip)
-        ref = brute_force(rows0, rates, skip)
+        got = vocoder_tail_starts(rows0, rates, skip, trim)
+        ref = brute_force(rows0, rates, skip, trim)
         assert got[3] == ref[3] == skip
         for i in range(len(rates)):
             for j in range(3):
