@@ -22,11 +22,17 @@ enum fq3c_kind {
   FQ3C_GEMM = 0,      /* C[M,N] = epi(sum_t A[m + tap_off[t], :cin] . B[n, t*cin:(t+1)*cin])            */
   FQ3C_RVQ = 1,       /* A=codes i64 [M,Q]; B=codebooks bf16 [Q,cb,dim]; C[M, 2*dim] = [sum first | sum rest] */
   FQ3C_RMSNORM = 2,   /* C[M,N] = rmsnorm(A[M,N]) * scale(f32 [N]), eps=f0                                  */
-  FQ3C_ROPE = 3,      /* in place on A[M, lda]: i0 heads of dim i1 starting at column i2, theta=f0          */
-  FQ3C_ATTN = 4,      /* A=qkv [M, lda] (q | k | v), i0 heads, i1 kv heads, i2 head_dim, window K; C[M, i0*i2] */
-  FQ3C_DWCONV = 5,    /* depthwise causal conv k=taps: C[m,c] = bias[c] + sum_j B(f32)[c,j] A[m-(taps-1)+j, c]  */
+  FQ3C_ROPE = 3,      /* in place on A[M, lda]: i0 heads of dim i1 starting at column i2, theta=f0; row m is position
+                         m + *p0 when p0 (device int32) is given (stateful decode), else m                       */
+  FQ3C_ATTN = 4,      /* A=qkv [M, lda] (q | k | v), i0 heads, i1 kv heads, i2 head_dim, window K; C[M, i0*i2].  Stateful
+                         decode: A holds `taps` history rows in front of the M query rows (query m = row taps + m), of
+                         which the last min(*p0, taps) are valid (p0 = device int32: positions decoded so far)       */
+  FQ3C_DWCONV = 5,    /* depthwise causal conv k=taps: C[m,c] = bias[c] + sum_j B(f32)[c,j] A[m-(taps-1)+j, c]; rows down
+                         to -i0 in front of A are history rows (stateful decode), further back reads as zero        */
   FQ3C_LAYERNORM = 6, /* C = layernorm(A) * scale + bias (f32), eps=f0                                      */
   FQ3C_SNAKE = 7,     /* C = A + p1[c] * sin(A * p0[c])^2   (p0 = exp(alpha), p1 = 1/(exp(beta)+1e-9))      */
+  FQ3C_COPY = 9,      /* C[M, N] = A[M, N] (bf16 rows; lda / ldc): history roll of the stateful decode               */
+  FQ3C_ADVANCE = 10,  /* *(int32*)C += i0 (one thread): the stateful decode's position counter                        */
   FQ3C_QKNORM_ROPE_KV = 8 /* dense talker prefill: A = fused qkv rows [M, lda], i0 q heads, i1 kv heads of dim 128; q/k heads get the
                              per-head RMSNorm (bf16 gamma p0 / p1, eps f0) and the rotary embedding from the bf16 tables B (cos) /
                              bias (sin) at position row + i2, in place; finished k / v rows also go to the static KV cache

@@ -30,6 +30,7 @@ from . import build as _build
 from .config import CodecDecoderConfig
 
 K_GEMM, K_RVQ, K_RMSNORM, K_ROPE, K_ATTN, K_DWCONV, K_LAYERNORM, K_SNAKE = range(8)
+K_COPY, K_ADVANCE = 9, 10
 F_BIAS, F_GELU, F_RESID, F_SCALE, F_SWIGLU, F_CLAMP, F_OUT_F32, F_SNAKE2, F_SILU = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
@@ -122,7 +123,7 @@ def load_lib():
     lib.fq3c_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
     lib.fq3c_graph_destroy.restype = C.c_int
     lib.fq3c_graph_destroy.argtypes = [C.c_void_p]
-    if lib.fq3c_abi_version() != 3:
+    if lib.fq3c_abi_version() != 4:
         raise CodecError("libfq3codec.so ABI version mismatch")
     _lib = lib
     return lib
@@ -497,9 +498,189 @@ class CodecDecoder:
         self.run_plan(plan)
         return plan.wav.view(-1)[: plan.n_samples].clone()
 
+    def open_stream(self, max_chunk_frames: int = 8) -> "CodecStream":
+        """Stateful incremental decode of one utterance (CodecStream): every chunk costs its own frames only."""
+        return CodecStream(self, max_chunk_frames)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.fq3c_launch_count())
+
+
+class CodecStream:
+    """Stateful incremental decode of one utterance (replaces the re-decoding policy of
+    faster_qwen3_tts/model.py:737-826: 25 context frames with every chunk of 8).
+
+    With the causal transposed convolutions (config trans_conv_trim = "right") every layer of the decoder looks backwards only,
+    so a chunk needs nothing but the rows earlier chunks left behind: the last k-1 (dilated: 6*d) input rows of every causal
+    convolution, one row per vocoder transposed conv, and the rotated K / V rows of the last window-1 positions of every
+    transformer layer.  Each such layer input is a buffer [history rows | new rows]: the implicit GEMM reads its taps at
+    (offset + history) >= 0, so rows of earlier chunks take the place of the causal zero padding, and the last ops of a
+    chunk's list roll every buffer's tail into its history rows.  A chunk of n frames costs n frames and returns exactly
+    n * total_upsample samples; the concatenation over chunks equals the full, non-streaming decode of all frames bit for
+    bit when neither side splits its GEMMs over K (the stateful lists never do; FQ3C_SPLITK=0 turns it off for the full
+    decode), because every output element then accumulates the same products in the same order.
+    """
+
+    def __init__(self, dec: "CodecDecoder", max_chunk_frames: int = 8):
+        if dec.cfg.trans_conv_trim != "right":
+            raise ValueError('stateful decode needs causal transposed convolutions (trans_conv_trim = "right"): the sibling trim '
+                             '("both") makes every vocoder block look one input row ahead')
+        self.dec, self.cfg, self.device = dec, dec.cfg, dec.device
+        self.max_frames = int(max_chunk_frames)
+        self.hist: List[tuple] = []          # (buffer [hist + rows_max, cols], hist rows, name)
+        self.rows_of: Dict[str, int] = {}    # new rows per frame of every history buffer
+        self._plans: Dict[int, _Plan] = {}
+        self.pos = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.codes = torch.zeros(self.max_frames, self.cfg.num_quantizers, dtype=torch.int64, device=self.device)
+        self.n_frames = 0
+        c = self.cfg
+        H, W = c.hidden_size, c.sliding_window
+        qkv_dim = (c.num_attention_heads + 2 * c.num_key_value_heads) * c.head_dim
+        self.k_pre = dec.g["pre_conv.w"].shape[1] // c.latent_dim
+        self.b: Dict[str, torch.Tensor] = {}
+        self._mk("pre_in", self.k_pre - 1, 1, c.latent_dim)
+        for l in range(c.num_hidden_layers):
+            self._mk(f"qkv{l}", W - 1, 1, qkv_dim)
+        per = 1
+        for i, f in enumerate(c.upsampling_ratios):
+            per *= f
+            self._mk(f"cnx{i}", 6, per, H)
+        self._mk("dec0_in", 6, per, H)
+        D = c.decoder_dim
+        for i, r in enumerate(c.upsample_rates):
+            cin, cout = D // 2 ** i, D // 2 ** (i + 1)
+            self._mk(f"tc{i}", 1, per, cin)
+            per *= r
+            for j, dil in enumerate(VOCODER_DILATIONS):
+                self._mk(f"u{i}.{j}", 6 * dil, per, cout)
+        self._mk("fin_in", 6, per, D // 2 ** len(c.upsample_rates))
+        self.tmp = torch.zeros(max(h * t.shape[1] for t, h, _ in self.hist), dtype=torch.bfloat16, device=self.device)
+
+    def _mk(self, name, hist, rows_per_frame, cols):
+        t = torch.zeros(hist + rows_per_frame * self.max_frames, cols, dtype=torch.bfloat16, device=self.device)
+        self.b[name] = t
+        self.hist.append((t, hist, name))
+        self.rows_of[name] = rows_per_frame
+
+    def reset(self):
+        """Start a new utterance: history rows back to the causal zero padding, position 0."""
+        for t, h, _ in self.hist:
+            t[:h].zero_()
+        self.pos.zero_()
+        self.n_frames = 0
+
+    def _build(self, T: int) -> _Plan:
+        d_, c, g, b = self.dec, self.cfg, self.dec.g, self.b
+        plan = _Plan()
+        H, d, nh, nkv, W = c.hidden_size, c.head_dim, c.num_attention_heads, c.num_key_value_heads, c.sliding_window
+        plan.codes = self.codes
+        q = d_._simple(plan, K_RVQ, self.codes[:T], T, 2 * c.codebook_dim, B=g["cb"], K=c.codebook_size,
+                       i0=c.num_semantic_quantizers, i1=c.num_quantizers, i2=c.codebook_dim)
+        plan.ops[-1].lda = c.num_quantizers
+        k = self.k_pre
+        d_._gemm(plan, q, g["rvq_proj"], T, c.latent_dim, 2 * c.codebook_dim, out=b["pre_in"][k - 1:k - 1 + T])
+        x, _ = d_._gemm(plan, b["pre_in"][:k - 1 + T], g["pre_conv.w"], T, H, c.latent_dim, taps=k, tap_off=list(range(k)),
+                        bias=g["pre_conv.b"])
+        qkv_dim = (nh + 2 * nkv) * d
+        for l in range(c.num_hidden_layers):
+            p = f"pre_transformer.layers.{l}"
+            buf = b[f"qkv{l}"]
+            new = buf[W - 1:W - 1 + T]
+            h = d_._simple(plan, K_RMSNORM, x, T, H, scale=g[f"{p}.ln1"], f0=c.rms_norm_eps)
+            d_._gemm(plan, h, g[f"{p}.wqkv"], T, qkv_dim, H, out=new)
+            d_._simple(plan, K_ROPE, new, T, qkv_dim, out=new, i0=nh + nkv, i1=d, i2=0, f0=c.rope_theta, p0=self.pos)
+            a = d_._simple(plan, K_ATTN, buf[:W - 1 + T], T, nh * d, i0=nh, i1=nkv, i2=d, K=W, taps=W - 1, p0=self.pos)
+            x, _ = d_._gemm(plan, a, g[f"{p}.wo"], T, H, nh * d, scale=g[f"{p}.ls1"], res=x)
+            h = d_._simple(plan, K_RMSNORM, x, T, H, scale=g[f"{p}.ln2"], f0=c.rms_norm_eps)
+            m, _ = d_._gemm(plan, h, g[f"{p}.wgu"], T, 2 * c.intermediate_size, H, flags=F_SWIGLU)
+            x, _ = d_._gemm(plan, m, g[f"{p}.wdown"], T, H, c.intermediate_size, scale=g[f"{p}.ls2"], res=x)
+        x = d_._simple(plan, K_RMSNORM, x, T, H, scale=g["norm"], f0=c.rms_norm_eps)
+        rows = T
+        n_up = len(c.upsampling_ratios)
+        for i, f in enumerate(c.upsampling_ratios):
+            p = f"upsample.{i}"
+            cb = b[f"cnx{i}"]
+            xin = cb[6:6 + rows * f]
+            d_._gemm(plan, x, g[f"{p}.t.w"], rows, f * H, H, bias=g[f"{p}.t.b"], col_mod=H, out=xin.view(rows, f * H))
+            rows *= f
+            h = d_._simple(plan, K_DWCONV, xin, rows, H, B=g[f"{p}.dw.w"], bias=g[f"{p}.dw.b"], taps=7, i0=6)
+            h = d_._simple(plan, K_LAYERNORM, h, rows, H, scale=g[f"{p}.ln.w"], bias=g[f"{p}.ln.b"], f0=1e-6)
+            h, _ = d_._gemm(plan, h, g[f"{p}.pw1.w"], rows, 4 * H, H, bias=g[f"{p}.pw1.b"], flags=F_GELU)
+            out = b["dec0_in"][6:6 + rows] if i == n_up - 1 else None
+            x, _ = d_._gemm(plan, h, g[f"{p}.pw2.w"], rows, H, 4 * H, bias=g[f"{p}.pw2.b"], scale=g[f"{p}.gamma"], res=xin, out=out)
+        if n_up == 0:
+            d_._simple(plan, K_COPY, x, rows, H, out=b["dec0_in"][6:6 + rows])
+        D = c.decoder_dim
+        nblk = len(c.upsample_rates)
+        d_._gemm(plan, b["dec0_in"][:6 + rows], g["dec0.w"], rows, D, H, taps=7, tap_off=list(range(7)), bias=g["dec0.b"],
+                 snake="decoder.1.block.0", out2=b["tc0"][1:1 + rows])
+        for i, r in enumerate(c.upsample_rates):
+            cin, cout = D // 2 ** i, D // 2 ** (i + 1)
+            p = f"decoder.{i + 1}.block"
+            u0 = b[f"u{i}.0"]
+            y, _ = d_._gemm(plan, b[f"tc{i}"][:1 + rows], g[f"{p}.1.w"], rows, r * cout, cin, taps=2, tap_off=[1, 0], bias=g[f"{p}.1.b"],
+                            col_mod=cout, snake=f"{p}.2.act1", out2=u0[6:6 + rows * r].view(rows, r * cout))
+            rows *= r
+            x = y.view(rows, cout)
+            for j, dil in enumerate(VOCODER_DILATIONS):
+                q_ = f"{p}.{j + 2}"
+                uin = b[f"u{i}.{j}"]
+                _, hs = d_._gemm(plan, uin[:6 * dil + rows], g[f"{q_}.c1.w"], rows, cout, cout, taps=7, tap_off=[t * dil for t in range(7)],
+                                 bias=g[f"{q_}.c1.b"], snake=f"{q_}.act2")
+                if j < 2:
+                    nxt, dn = f"{p}.{j + 3}.act1", 6 * VOCODER_DILATIONS[j + 1]
+                    o2 = b[f"u{i}.{j + 1}"][dn:dn + rows]
+                elif i + 1 < nblk:
+                    nxt, o2 = f"decoder.{i + 2}.block.0", b[f"tc{i + 1}"][1:1 + rows]
+                else:
+                    nxt, o2 = "final", b["fin_in"][6:6 + rows]
+                x, _ = d_._gemm(plan, hs, g[f"{q_}.c2.w"], rows, cout, cout, bias=g[f"{q_}.c2.b"], res=x, snake=nxt, out2=o2)
+        out_dim = D // 2 ** nblk
+        plan.wav = torch.zeros(max(rows, 1), 1, dtype=torch.float32, device=self.device)
+        d_._gemm(plan, b["fin_in"][:6 + rows], g["final.w"], rows, 1, out_dim, taps=7, tap_off=list(range(7)), bias=g["final.b"],
+                 flags=F_CLAMP, out=plan.wav, out_f32=True)
+        plan.n_samples = rows
+        # roll: the last `hist` rows of [history | new] become the history of the next chunk (through a scratch buffer when
+        # the two ranges overlap), then the position counter moves on
+        for t, hist, name in self.hist:
+            n_new = self.rows_of[name] * T
+            cols = t.shape[1]
+            src = t[n_new:n_new + hist]
+            if n_new >= hist:
+                d_._simple(plan, K_COPY, src, hist, cols, out=t[:hist])
+            else:
+                tmp = self.tmp[:hist * cols].view(hist, cols)
+                d_._simple(plan, K_COPY, src, hist, cols, out=tmp)
+                d_._simple(plan, K_COPY, tmp, hist, cols, out=t[:hist])
+        adv = Op()
+        adv.kind, adv.M, adv.N, adv.i0, adv.C = K_ADVANCE, 1, 1, T, self.pos.data_ptr()
+        plan.ops.append(adv)
+        plan.arr = (Op * len(plan.ops))(*plan.ops)
+        return plan
+
+    @torch.inference_mode()
+    def decode(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes int64 [n, Q], the next n <= max_chunk_frames frames of the utterance -> float32 [n * total_upsample] on the device."""
+        T = int(codes.shape[0])
+        if T == 0:
+            return torch.zeros(0, dtype=torch.float32, device=self.device)
+        if T > self.max_frames:
+            return torch.cat([self.decode(codes[i:i + self.max_frames]) for i in range(0, T, self.max_frames)])
+        plan = self._plans.get(T)
+        if plan is None:
+            plan = self._plans[T] = self._build(T)
+        self.codes[:T].copy_(codes.to(torch.int64), non_blocking=True)
+        self.dec.run_plan(plan)
+        self.n_frames += T
+        return plan.wav.view(-1)[: plan.n_samples].clone()
+
+    def close(self):
+        for plan in self._plans.values():
+            if plan.graph is not None:
+                self.dec.lib.fq3c_graph_destroy(plan.graph)
+                plan.graph = None
+        self._plans.clear()
 
 
 class SpeechTokenizer:

@@ -537,11 +537,12 @@ __global__ void fq3c_layernorm_kernel(const fq3c_op o) {
 // RoPE in place on q and k inside the fused qkv buffer (HF rotate_half convention, bf16 rounding per product).
 __global__ void fq3c_rope_kernel(const fq3c_op o) {
   const int t = blockIdx.x, nheads = o.i0, d = o.i1, col0 = o.i2, half = d / 2;
+  const int pos = t + (o.p0 ? *reinterpret_cast<const int*>(o.p0) : 0);
   bf16* row = reinterpret_cast<bf16*>(const_cast<void*>(o.A)) + (size_t)t * o.lda + col0;
   for (int idx = threadIdx.x; idx < nheads * half; idx += blockDim.x) {
     const int h = idx / half, i = idx - h * half;
     const float inv = powf(o.f0, -2.0f * i / d);
-    const float ang = (float)t * inv;
+    const float ang = (float)pos * inv;
     const float c = bf16r(cosf(ang)), s = bf16r(sinf(ang));
     bf16* p = row + h * d;
     const float a = __bfloat162float(p[i]), b = __bfloat162float(p[i + half]);
@@ -567,16 +568,18 @@ __device__ __forceinline__ void attn_load(const bf16* p, float (&v)[4]) {
   }
 }
 template <int PER>
-__device__ __forceinline__ void attn_warp(const fq3c_op& o, int t, int h, int lane) {
+__device__ __forceinline__ void attn_warp(const fq3c_op& o, int t_out, int h, int lane) {
   const int nh = o.i0, nkv = o.i1, d = o.i2, win = o.K;
   const int kvh = h / (nh / nkv);
   const bf16* base = reinterpret_cast<const bf16*>(o.A);
   const int qoff = h * d + lane * PER, koff = nh * d + kvh * d + lane * PER, voff = nh * d + nkv * d + kvh * d + lane * PER;
   float q[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int hist = o.taps, t = t_out + hist;  // stateful decode: `hist` rows of earlier chunks sit in front of the query rows
+  const int first = o.p0 ? hist - min(*reinterpret_cast<const int*>(o.p0), hist) : 0;
   attn_load<PER>(base + (size_t)t * o.lda + qoff, q);
   const float scale = rsqrtf((float)d);
   float m = -INFINITY, l = 0.f;
-  const int j0 = max(0, t - win + 1);
+  const int j0 = max(first, t - win + 1);
   for (int jb = j0; jb <= t; jb += 4) {
     float s[4], v[4][4];
 #pragma unroll
@@ -604,16 +607,18 @@ __device__ __forceinline__ void attn_warp(const fq3c_op& o, int t, int h, int la
       }
     }
   }
-  bf16* out = reinterpret_cast<bf16*>(o.C) + (size_t)t * o.ldc + h * d + lane * PER;
+  bf16* out = reinterpret_cast<bf16*>(o.C) + (size_t)t_out * o.ldc + h * d + lane * PER;
 #pragma unroll
   for (int i = 0; i < PER; ++i) out[i] = __float2bfloat16_rn(acc[i] / l);
 }
 // any head_dim <= 128 (lane owns dims lane, lane + 32, ...): the small test configurations
-__device__ __forceinline__ void attn_warp_generic(const fq3c_op& o, int t, int h, int lane) {
+__device__ __forceinline__ void attn_warp_generic(const fq3c_op& o, int t_out, int h, int lane) {
   const int nh = o.i0, nkv = o.i1, d = o.i2, win = o.K;
   const int kvh = h / (nh / nkv);
   const bf16* base = reinterpret_cast<const bf16*>(o.A);
   const int qoff = h * d, koff = nh * d + kvh * d, voff = nh * d + nkv * d + kvh * d;
+  const int hist = o.taps, t = t_out + hist;
+  const int first = o.p0 ? hist - min(*reinterpret_cast<const int*>(o.p0), hist) : 0;
   const int per = (d + 31) / 32;  // <= 4
   float q[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = 0; i < per; ++i) {
@@ -622,7 +627,7 @@ __device__ __forceinline__ void attn_warp_generic(const fq3c_op& o, int t, int h
   }
   const float scale = rsqrtf((float)d);
   float m = -INFINITY, l = 0.f;
-  const int j0 = max(0, t - win + 1);
+  const int j0 = max(first, t - win + 1);
   for (int j = j0; j <= t; ++j) {
     float s = 0.f;
     for (int i = 0; i < per; ++i) {
@@ -640,7 +645,7 @@ __device__ __forceinline__ void attn_warp_generic(const fq3c_op& o, int t, int h
     }
     m = mn;
   }
-  bf16* out = reinterpret_cast<bf16*>(o.C) + (size_t)t * o.ldc + h * d;
+  bf16* out = reinterpret_cast<bf16*>(o.C) + (size_t)t_out * o.ldc + h * d;
   for (int i = 0; i < per; ++i) {
     const int c = lane + i * 32;
     if (c < d) out[c] = __float2bfloat16_rn(acc[i] / l);
@@ -712,12 +717,24 @@ __global__ void fq3c_dwconv_kernel(const fq3c_op o) {
     const int t = (int)(i / o.N), c = (int)(i - (size_t)t * o.N);
     float a = b[c];
     for (int j = 0; j < o.taps; ++j) {
-      const int r = t - (o.taps - 1) + j;
-      if (r >= 0) a += w[c * o.taps + j] * __bfloat162float(x[(size_t)r * o.lda + c]);
+      const int r = t - (o.taps - 1) + j;  // rows [-i0, 0) are the history rows of a stateful decode
+      if (r >= -o.i0) a += w[c * o.taps + j] * __bfloat162float(x[(long)r * o.lda + c]);
     }
     y[(size_t)t * o.ldc + c] = __float2bfloat16_rn(a);
   }
 }
+
+__global__ void fq3c_copy_kernel(const fq3c_op o) {
+  const int nv = o.N >> 3;  // 16-byte pieces per row (N, lda, ldc are multiples of 8)
+  const size_t n = (size_t)o.M * nv;
+  const bf16* x = reinterpret_cast<const bf16*>(o.A);
+  bf16* y = reinterpret_cast<bf16*>(o.C);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i / nv, c = (i - t * nv) * 8;
+    *reinterpret_cast<uint4*>(y + t * o.ldc + c) = *reinterpret_cast<const uint4*>(x + t * o.lda + c);
+  }
+}
+__global__ void fq3c_advance_kernel(int* counter, int by) { *counter += by; }
 
 __global__ void fq3c_snake_kernel(const fq3c_op o) {
   const size_t n = (size_t)o.M * o.N;
@@ -739,7 +756,7 @@ int fail(const std::string& m) { g_err = m; return -1; }
 
 extern "C" {
 
-int fq3c_abi_version(void) { return 3; }
+int fq3c_abi_version(void) { return 4; }
 const char* fq3c_last_error(void) { return g_err.c_str(); }
 int64_t fq3c_launch_count(void) { return g_launches; }
 
@@ -839,6 +856,17 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
       case FQ3C_SNAKE: {
         const size_t n = (size_t)o.M * o.N;
         fq3c_snake_kernel<<<(unsigned)std::min<size_t>(4096, (n + 255) / 256), 256, 0, s>>>(o);
+        break;
+      }
+      case FQ3C_COPY: {
+        if ((o.N % 8) || (o.lda % 8) || (o.ldc % 8) || !o.A || !o.C) return fail("copy: N, lda, ldc must be multiples of 8");
+        const size_t n = (size_t)o.M * (o.N >> 3);
+        fq3c_copy_kernel<<<(unsigned)std::min<size_t>(1024, (n + 255) / 256), 256, 0, s>>>(o);
+        break;
+      }
+      case FQ3C_ADVANCE: {
+        if (!o.C) return fail("advance: null counter");
+        fq3c_advance_kernel<<<1, 1, 0, s>>>(reinterpret_cast<int*>(o.C), o.i0);
         break;
       }
       default: return fail("unknown op kind");

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import contextlib
 import logging
+import os
 import wave
 from pathlib import Path
 from typing import Generator, List, Optional, Tuple, Union
@@ -37,6 +38,7 @@ class FasterQwen3TTS:
         self.sample_rate = self._infer_sample_rate(base_model)
         self._warmed_up = False
         self._codec_stream = None  # side stream of the overlapped streaming decode (FQ3_OVERLAP_CODEC)
+        self._codec_streams = {}   # chunk_size -> codec.CodecStream (FQ3_STATEFUL_CODEC)
         self._voice_prompt_cache = {}
 
     @staticmethod
@@ -269,6 +271,15 @@ class FasterQwen3TTS:
         min_cal = max(context_frames, chunk_size)
         all_codes, prev_len, spf = [], 0, None
         tok = m.speech_tokenizer
+        # Opt-in (FQ3_STATEFUL_CODEC=1): stateful incremental decode instead of the windowed re-decode — every chunk costs its own
+        # frames only and the audio equals the full non-streaming decode (codec.CodecStream).  The windowed policy below stays
+        # the default because it is the reference's.
+        cstream = None
+        if os.environ.get("FQ3_STATEFUL_CODEC", "0") == "1" and getattr(tok.decoder.cfg, "trans_conv_trim", "") == "right":
+            cstream = self._codec_streams.get(chunk_size)
+            if cstream is None:
+                cstream = self._codec_streams[chunk_size] = tok.decoder.open_stream(max(chunk_size, 8))
+        first = True
         for chunk, timing in stream:
             # FQ3_OVERLAP_CODEC (streaming.py): the next chunk is already running on the main stream, so everything below — the
             # window gather and the codec decode — goes to a side stream that only waits for THIS chunk's codes
@@ -278,29 +289,37 @@ class FasterQwen3TTS:
                     self._codec_stream = torch.cuda.Stream(device=chunk.device)
                 self._codec_stream.wait_event(ready)
             with (torch.cuda.stream(self._codec_stream) if ready is not None else contextlib.nullcontext()):
-                all_codes.append(chunk)
-                n_new = chunk.shape[0]
-                flat = torch.cat(all_codes, dim=0)
-                n_total = flat.shape[0]
-                if spf is None:
-                    codes_in = flat if ref_codes is None else torch.cat([ref_codes.to(flat.device), flat], dim=0)
-                    audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0)})
-                    audio = audio_list[0].flatten()
-                    if ref_codes is not None:
-                        audio = audio[int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * len(audio)):]
-                    new_audio = audio[prev_len:]
-                    prev_len = len(audio)
-                    if n_total >= min_cal:
-                        spf = len(audio) / n_total
+                if cstream is not None:
+                    if first:
+                        cstream.reset()
+                        if ref_codes is not None:  # ICL: the reference audio's codes are acoustic context, decoded for their state only
+                            cstream.decode(ref_codes.to(chunk.device))
+                        first = False
+                    new_audio, sr = cstream.decode(chunk), tok.sample_rate
                 else:
-                    start = max(0, n_total - n_new - context_frames)
-                    window = flat[start:]
-                    n_ctx = window.shape[0] - n_new
-                    cut = int(round(n_ctx * spf)) if n_ctx > 0 else 0
-                    # the context frames are decoded for their state only: tell the decoder which samples will be thrown away
-                    audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0), "skip_samples": cut})
-                    audio = audio_list[0].flatten()
-                    new_audio = audio[cut:] if n_ctx > 0 else audio
+                    all_codes.append(chunk)
+                    n_new = chunk.shape[0]
+                    flat = torch.cat(all_codes, dim=0)
+                    n_total = flat.shape[0]
+                    if spf is None:
+                        codes_in = flat if ref_codes is None else torch.cat([ref_codes.to(flat.device), flat], dim=0)
+                        audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0)})
+                        audio = audio_list[0].flatten()
+                        if ref_codes is not None:
+                            audio = audio[int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * len(audio)):]
+                        new_audio = audio[prev_len:]
+                        prev_len = len(audio)
+                        if n_total >= min_cal:
+                            spf = len(audio) / n_total
+                    else:
+                        start = max(0, n_total - n_new - context_frames)
+                        window = flat[start:]
+                        n_ctx = window.shape[0] - n_new
+                        cut = int(round(n_ctx * spf)) if n_ctx > 0 else 0
+                        # the context frames are decoded for their state only: tell the decoder which samples will be thrown away
+                        audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0), "skip_samples": cut})
+                        audio = audio_list[0].flatten()
+                        new_audio = audio[cut:] if n_ctx > 0 else audio
             if ready is not None:
                 self._codec_stream.synchronize()
             yield (self._to_numpy(new_audio) if to_host else new_audio), sr, timing

@@ -270,3 +270,53 @@ def test_transformer_block_on_device_matches_oracle(tiny):
     src = plan.ops[-1].C
     got = next(t for t in plan.keep if t.data_ptr() == src)
     assert _rel(got, ref) <= 0.03
+
+
+# ---- stateful incremental decode ---------------------------------------------------
+def _stream_decode(dec, codes, sizes, max_chunk=8):
+    st = dec.open_stream(max_chunk)
+    parts, i, k = [], 0, 0
+    while i < codes.shape[0]:
+        n = sizes[k % len(sizes)]
+        parts.append(st.decode(codes[i:i + n].cuda()))
+        i += n
+        k += 1
+    return st, torch.cat(parts)
+
+
+@pytest.mark.parametrize("name,T,sizes", [("tiny", 29, [8]), ("tiny", 23, [3, 8, 1, 5]), ("0.6B-Base", 90, [8]), ("0.6B-Base", 19, [8, 2])])
+def test_stateful_stream_equals_full_decode_bit_for_bit(monkeypatch, name, T, sizes):
+    """The decoder is causal (trans_conv_trim = "right"), so chunk-by-chunk decoding with carried conv tails / K-V rows must
+    give the FULL non-streaming decode of all frames, bit for bit, when neither side splits a GEMM over K (the stateful op
+    lists never do; FQ3C_SPLITK=0 turns it off for the full decode: every output element then sums the same products in the
+    same order).  T = 90 > the 72-position window at full size: the window cut-off is crossed; ragged chunk sizes."""
+    monkeypatch.setenv("FQ3C_SPLITK", "0")
+    cfg, dec, orc = make(name, seed=4)
+    codes = torch.randint(0, cfg.codebook_size, (T, cfg.num_quantizers), generator=torch.Generator().manual_seed(T))
+    full = dec.decode(codes.cuda())
+    st, got = _stream_decode(dec, codes, sizes)
+    assert got.numel() == full.numel() == cfg.total_upsample * T
+    assert torch.equal(got, full), float((got - full).abs().max())
+    # a second utterance on the same stream object after reset()
+    st.reset()
+    codes2 = torch.randint(0, cfg.codebook_size, (11, cfg.num_quantizers), generator=torch.Generator().manual_seed(99))
+    got2 = torch.cat([st.decode(codes2[:8].cuda()), st.decode(codes2[8:].cuda())])
+    assert torch.equal(got2, dec.decode(codes2.cuda()))
+    st.close()
+
+
+def test_stateful_stream_matches_oracle_and_default_decode():
+    """Against the fp32 oracle (waveform SNR) and against the default full decode (split-K on: same values up to fp32
+    summation order)."""
+    cfg, dec, orc = make("tiny", seed=5)
+    T = 21
+    codes = torch.randint(0, cfg.codebook_size, (T, cfg.num_quantizers), generator=torch.Generator().manual_seed(7))
+    _, got = _stream_decode(dec, codes, [8])
+    check_waveform(got, orc.decode(codes), orc.bf16.decode(codes))
+    assert snr_db(got, dec.decode(codes.cuda())) >= 35.0
+
+
+def test_stateful_stream_needs_causal_trim():
+    cfg, dec, _ = make("tiny", trim="both")
+    with pytest.raises(ValueError):
+        dec.open_stream(8)

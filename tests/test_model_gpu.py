@@ -179,3 +179,19 @@ def test_voice_clone_batch_matches_single_requests(ref_wav):
             assert a.shape == b.shape and np.array_equal(a, b)
     finally:
         m.model.engine.close()
+
+
+def test_streaming_with_stateful_codec_equals_non_streaming_audio(base, ref_wav, monkeypatch):
+    """FQ3_STATEFUL_CODEC=1: the chunks of generate_voice_clone_streaming concatenate to EXACTLY the audio of the non-streaming
+    call (same codes: greedy) — the stateful codec stream reproduces the full decode bit for bit (split-K off on both sides),
+    where the reference's windowed policy only approximates it."""
+    monkeypatch.setenv("FQ3C_SPLITK", "0")
+    base.predictor_graph.do_sample = False
+    kw = dict(max_new_tokens=27, min_new_tokens=27, do_sample=False)   # 27 frames: a plan no other test has cached
+    full, sr = base.generate_voice_clone(TEXT, "English", ref_wav, "", **kw)
+    monkeypatch.setenv("FQ3_STATEFUL_CODEC", "1")
+    chunks = [a for a, _, _ in base.generate_voice_clone_streaming(TEXT, "English", ref_wav, "", chunk_size=8, **kw)]
+    assert [len(c) for c in chunks] == [8 * 1920, 8 * 1920, 8 * 1920, 3 * 1920]
+    got = np.concatenate(chunks)
+    assert got.shape == full[0].shape
+    assert np.array_equal(got, full[0])
