@@ -498,9 +498,9 @@ class CodecDecoder:
         self.run_plan(plan)
         return plan.wav.view(-1)[: plan.n_samples].clone()
 
-    def open_stream(self, max_chunk_frames: int = 8) -> "CodecStream":
+    def open_stream(self, max_chunk_frames: int = 8, split_k: Optional[bool] = None) -> "CodecStream":
         """Stateful incremental decode of one utterance (CodecStream): every chunk costs its own frames only."""
-        return CodecStream(self, max_chunk_frames)
+        return CodecStream(self, max_chunk_frames, split_k)
 
     @property
     def launch_count(self) -> int:
@@ -518,16 +518,19 @@ class CodecStream:
     (offset + history) >= 0, so rows of earlier chunks take the place of the causal zero padding, and the last ops of a
     chunk's list roll every buffer's tail into its history rows.  A chunk of n frames costs n frames and returns exactly
     n * total_upsample samples; the concatenation over chunks equals the full, non-streaming decode of all frames bit for
-    bit when neither side splits its GEMMs over K (the stateful lists never do; FQ3C_SPLITK=0 turns it off for the full
-    decode), because every output element then accumulates the same products in the same order.
+    bit when neither side splits its GEMMs over K (FQ3C_SPLITK=0, or split_k=False here), because every output element then
+    accumulates the same products in the same order; with split-K (the default, faster) the two agree up to fp32 summation order.
     """
 
-    def __init__(self, dec: "CodecDecoder", max_chunk_frames: int = 8):
+    def __init__(self, dec: "CodecDecoder", max_chunk_frames: int = 8, split_k: Optional[bool] = None):
         if dec.cfg.trans_conv_trim != "right":
             raise ValueError('stateful decode needs causal transposed convolutions (trans_conv_trim = "right"): the sibling trim '
                              '("both") makes every vocoder block look one input row ahead')
         self.dec, self.cfg, self.device = dec, dec.cfg, dec.device
         self.max_frames = int(max_chunk_frames)
+        # short GEMMs with a long reduction may be split over K like the full decode's (faster: 8 rows cover few tiles); the chunks
+        # then equal the full decode up to fp32 summation order instead of bit for bit.  FQ3C_SPLITK=0 / split_k=False: exact.
+        self.split_k = (os.environ.get("FQ3C_SPLITK", "1") != "0") if split_k is None else bool(split_k)
         self.hist: List[tuple] = []          # (buffer [hist + rows_max, cols], hist rows, name)
         self.rows_of: Dict[str, int] = {}    # new rows per frame of every history buffer
         self._plans: Dict[int, _Plan] = {}
@@ -656,6 +659,8 @@ class CodecStream:
         adv = Op()
         adv.kind, adv.M, adv.N, adv.i0, adv.C = K_ADVANCE, 1, 1, T, self.pos.data_ptr()
         plan.ops.append(adv)
+        if self.split_k:
+            attach_splitk_workspace(plan.ops, self.device, plan.keep)
         plan.arr = (Op * len(plan.ops))(*plan.ops)
         return plan
 

@@ -287,8 +287,8 @@ def _stream_decode(dec, codes, sizes, max_chunk=8):
 @pytest.mark.parametrize("name,T,sizes", [("tiny", 29, [8]), ("tiny", 23, [3, 8, 1, 5]), ("0.6B-Base", 90, [8]), ("0.6B-Base", 19, [8, 2])])
 def test_stateful_stream_equals_full_decode_bit_for_bit(monkeypatch, name, T, sizes):
     """The decoder is causal (trans_conv_trim = "right"), so chunk-by-chunk decoding with carried conv tails / K-V rows must
-    give the FULL non-streaming decode of all frames, bit for bit, when neither side splits a GEMM over K (the stateful op
-    lists never do; FQ3C_SPLITK=0 turns it off for the full decode: every output element then sums the same products in the
+    give the FULL non-streaming decode of all frames, bit for bit, when neither side splits a GEMM over K (FQ3C_SPLITK=0 turns it
+    off for both: every output element then sums the same products in the
     same order).  T = 90 > the 72-position window at full size: the window cut-off is crossed; ragged chunk sizes."""
     monkeypatch.setenv("FQ3C_SPLITK", "0")
     cfg, dec, orc = make(name, seed=4)
