@@ -158,6 +158,14 @@ int fq3_apply_repetition_penalty(fq3_engine* e, void* logits_f32, int V, const v
  * stream's codes buffer.  One launch, zero host synchronisations inside. */
 int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_policy* policy,
                       const fq3_subpolicy* sub, void* stream);
+/* Prompt assembly on the device (replaces the ~60 eager tensor ops of `_build_talker_inputs_local`, model.py:331-553, behind
+ * the same Python method).  Every prompt row is text part + codec part, described by one int32[4] record:
+ *   [0] index into tp_rows (bf16 [n, H_t] = text_projection(text_embedding(ids)) of every text token the prompt needs), -1 = none
+ *   [1] codec part: 0 none | 1 talker codec embedding row [2] | 2 row [2] of spk_rows (bf16 [n_spk, H_t]) | 3 the 16-codebook
+ *       embedding sum of reference frame [2] of ref_codes_i32 (int32 [n_ref, 16]; generate_icl_prompt's running bf16 sum)
+ * Rows with neither part are zeros (left padding).  out: bf16 [n_rows, H_t].  All pointers are device addresses. */
+int fq3_assemble_prompt(fq3_engine* e, const void* tp_rows, const void* desc_i32x4, int n_rows, const void* spk_rows,
+                        const void* ref_codes_i32, void* out_bf16, void* stream);
 /* Batched multi-request decode (no counterpart in the reference, which is hard-wired to bs = 1: talker_graph.py:46-47,
  * predictor_graph.py:70-71).  fq3_decode_frames with n_streams <= 4 runs the reference-shaped frame program (two predictor
  * rows per stream in pass 0).  Above four it runs the "wide" frame program in lock-step groups of up to

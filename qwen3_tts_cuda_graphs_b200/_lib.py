@@ -73,6 +73,7 @@ SYMBOLS = {
     "fq3_decode_frames": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(Policy), C.POINTER(SubPolicy), _P]),
     "fq3_reduced_grid": (C.c_int, [_P]),
     "fq3_lockstep_group": (C.c_int, [_P]),
+    "fq3_assemble_prompt": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P]),
     "fq3_set_decode_grid": (C.c_int, [_P, C.c_int]),
     "fq3_clear_fault": (C.c_int, [_P, _P]),
     "fq3_debug_set_epoch": (C.c_int, [_P, C.c_uint32]),

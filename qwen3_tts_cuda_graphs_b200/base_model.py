@@ -345,7 +345,9 @@ class Qwen3TTSBaseModel:
                 ids = self.tokenizer.instruct(t[10:])
             else:
                 ids = self.tokenizer.assistant(t)
-            out.append(torch.tensor([ids], dtype=torch.long, device=self.device))
+            t_ = torch.tensor([ids], dtype=torch.long, device=self.device)
+            t_._host_ids = list(ids)  # the prompt builder lays the prompt out on the host: spare it a device read-back
+            out.append(t_)
         return out
 
     # ---- validation (model.py:846-847) ---------------------------------------------------------

@@ -1005,6 +1005,24 @@ int fq3_set_decode_grid(fq3_engine* e, int n_ctas) {
   if (n_ctas <= 0 || n_ctas == e->G || n_ctas == e->n_sms) return 0;
   return fail(FQ3_E_UNSUPPORTED, "the decode grid is fixed at engine creation (FQ3_GRID)");
 }
+int fq3_assemble_prompt(fq3_engine* e, const void* tp_rows, const void* desc_i32x4, int n_rows, const void* spk_rows,
+                        const void* ref_codes_i32, void* out_bf16, void* stream) {
+  if (!e || !desc_i32x4 || !out_bf16 || n_rows < 0) return fail(FQ3_E_INVALID, "bad assemble_prompt arguments");
+  if (n_rows == 0) return 0;
+  PromptTables tb{};
+  const uint8_t* arena = reinterpret_cast<const uint8_t*>(e->desc.arena);
+  tb.codec_embed = reinterpret_cast<const bf16*>(arena + e->desc.codec_embed_off);
+  for (int i = 0; i < e->ncb; ++i) tb.pred_embeds[i] = reinterpret_cast<const bf16*>(arena + e->pred_embed_offs[i]);
+  tb.ncb = e->ncb;
+  fq3_assemble_prompt_kernel<<<n_rows, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(tp_rows), reinterpret_cast<const int4*>(desc_i32x4), e->tk.d.hidden, tb,
+      reinterpret_cast<const bf16*>(spk_rows), reinterpret_cast<const int*>(ref_codes_i32), e->desc.n_code_groups,
+      reinterpret_cast<bf16*>(out_bf16));
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int fq3_lockstep_group(const fq3_engine* e) { return e ? std::max(e->wide_rows, kMaxRows / 2) : 0; }
 int fq3_reduced_grid(const fq3_engine* e) { return (e && e->G < e->n_sms) ? e->G : 0; }
 

@@ -2694,6 +2694,53 @@ __global__ void fq3_wpin_from_pairs_kernel(LLWord* wpin, int ldw, LLWord* pairs,
   }
 }
 
+// Prompt assembly (model.py:331-553): one block per prompt row.  A row is text part + codec part:
+//   desc.x  index into the projected text rows tp [n_tp, H] (text_projection(text_embedding(id))), -1 = none
+//   desc.y  codec part: 0 none | 1 talker codec embedding row desc.z | 2 speaker row desc.z | 3 the 16-codebook embedding sum of
+//           reference frame desc.z (generate_icl_prompt: CE(c0), then + emb_g(c_g) one codebook at a time, each add rounded to
+//           bf16 like the reference's bf16 tensor adds)
+// and the two parts meet in one more bf16 add.  Rows with neither part are the left padding: zeros.
+struct PromptTables {
+  const bf16* codec_embed;
+  const bf16* pred_embeds[32];
+  int ncb;
+};
+__global__ void fq3_assemble_prompt_kernel(const bf16* __restrict__ tp, const int4* __restrict__ desc, int H, PromptTables tb,
+                                           const bf16* __restrict__ spk, const int* __restrict__ ref_codes, int n_groups, bf16* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int4 d = desc[r];
+  const int Hw = H >> 1;
+  uint32_t* o = reinterpret_cast<uint32_t*>(out + (size_t)r * H);
+  const uint32_t* t = d.x >= 0 ? reinterpret_cast<const uint32_t*>(tp + (size_t)d.x * H) : nullptr;
+  for (int c = threadIdx.x; c < Hw; c += blockDim.x) {
+    float c0 = 0.f, c1 = 0.f;
+    bool have_c = d.y != 0;
+    if (d.y == 1) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(tb.codec_embed + (size_t)d.z * H) + c);
+      c0 = bf_lo(v); c1 = bf_hi(v);
+    } else if (d.y == 2) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(spk + (size_t)d.z * H) + c);
+      c0 = bf_lo(v); c1 = bf_hi(v);
+    } else if (d.y == 3) {
+      const int* codes = ref_codes + (size_t)d.z * n_groups;
+      uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(tb.codec_embed + (size_t)codes[0] * H) + c);
+      c0 = bf_lo(v); c1 = bf_hi(v);
+      for (int g = 0; g < tb.ncb; ++g) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(tb.pred_embeds[g] + (size_t)codes[g + 1] * H) + c);
+        c0 = bf16r(c0 + bf_lo(v)); c1 = bf16r(c1 + bf_hi(v));
+      }
+    }
+    uint32_t res = 0u;
+    if (t) {
+      const uint32_t v = __ldg(t + c);
+      res = have_c ? pack_bf16x2(bf_lo(v) + c0, bf_hi(v) + c1) : v;
+    } else if (have_c) {
+      res = pack_bf16x2(c0, c1);
+    }
+    o[c] = res;
+  }
+}
+
 // LL-epoch wrap (fq3_api.cu: reserve_epochs): keep the payloads, mark every word "written before the launch"
 __global__ void fq3_ll_clear_epochs_kernel(LLWord* w, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) w[i].y = 0u;

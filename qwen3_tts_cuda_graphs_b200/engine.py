@@ -233,6 +233,13 @@ class Engine:
         logits.reshape(-1, V)[0].copy_(work)
         return logits
 
+    def assemble_prompt(self, tp_rows: torch.Tensor, desc: torch.Tensor, spk_rows: Optional[torch.Tensor], ref_codes: Optional[torch.Tensor],
+                        out: torch.Tensor) -> None:
+        """fq3.h: fq3_assemble_prompt.  desc int32 [n, 4] on the device; out bf16 [n, H_t]."""
+        assert desc.dtype == torch.int32 and desc.is_cuda and desc.is_contiguous() and out.is_contiguous() and tp_rows.is_contiguous()
+        _lib.check(self.lib.fq3_assemble_prompt(self.h, tp_rows.data_ptr(), desc.data_ptr(), int(desc.shape[0]), _ptr(spk_rows),
+                                                _ptr(ref_codes), out.data_ptr(), _stream()))
+
     @property
     def lockstep_group(self) -> int:
         """Streams that share one weight sweep of the frame loop (fq3.h: fq3_lockstep_group); more streams run in groups."""

@@ -156,7 +156,129 @@ class FasterQwen3TTS:
 
     def _build_talker_inputs_local(self, m, input_ids, ref_ids, voice_clone_prompt, languages, speakers,
                                    non_streaming_mode: bool, instruct_ids=None):
-        """Prompt layout of model.py:331-553.  TP = text_projection(text_embedding(ids)),
+        """Prompt layout of model.py:331-553.  Default: the layout is worked out on the host as one descriptor per row and the rows
+        are produced by ONE text_projection call over every text token of the prompt plus one assembly kernel
+        (fq3_assemble_prompt); FQ3_PROMPT_FUSED=0 keeps the op-by-op mirror of the reference (`_build_talker_inputs_eager`,
+        about sixty small launches), which the parity tests hold the fused path against."""
+        eng = getattr(self.talker_graph, "engine", None) or getattr(m.talker, "engine", None)
+        if os.environ.get("FQ3_PROMPT_FUSED", "1") == "0" or eng is None:
+            return self._build_talker_inputs_eager(m, input_ids, ref_ids, voice_clone_prompt, languages, speakers,
+                                                   non_streaming_mode, instruct_ids)
+        t, tc, cfg = m.talker, m.config.talker_config, m.config
+        dev = t.device
+        H = tc.hidden_size
+        tok: List[int] = [cfg.tts_bos_token_id, cfg.tts_eos_token_id, cfg.tts_pad_token_id]  # every text token whose projection is needed
+        BOS, EOS, PAD = 0, 1, 2
+
+        def host(ids) -> List[int]:
+            h = getattr(ids, "_host_ids", None)
+            return list(h) if h is not None else [int(x) for x in ids.reshape(-1).tolist()]
+
+        def tp(ids) -> List[int]:  # indices of the projected rows of these token ids
+            ids = host(ids) if hasattr(ids, "reshape") else [int(x) for x in ids]
+            base = len(tok)
+            tok.extend(ids)
+            return list(range(base, base + len(ids)))
+
+        spk_rows = m.generate_speaker_prompt(voice_clone_prompt) if voice_clone_prompt is not None else None
+        speakers = speakers if speakers is not None else [None] * len(input_ids)
+        spk_table: List[torch.Tensor] = []
+        ref_tables: List[torch.Tensor] = []
+        n_ref = 0
+        NONE, CE, SPK, ICL = 0, 1, 2, 3
+        seqs, trailing = [], []
+        for i, (ids, language, speaker) in enumerate(zip(input_ids, languages, speakers)):
+            rows: List[tuple] = []  # (text row index | -1, codec kind, codec index)
+            if instruct_ids is not None and instruct_ids[i] is not None:
+                rows += [(k, NONE, 0) for k in tp(instruct_ids[i])]
+            if spk_rows is None:
+                if speaker in ("", None):
+                    spk = None
+                else:
+                    if speaker.lower() not in tc.spk_id:
+                        raise NotImplementedError(f"Speaker {speaker} not implemented")
+                    spk = (CE, tc.spk_id[speaker.lower()])
+            else:
+                use = voice_clone_prompt["x_vector_only_mode"][i] or voice_clone_prompt["icl_mode"][i]
+                spk = None
+                if use:
+                    spk = (SPK, len(spk_table))
+                    spk_table.append(spk_rows[i].reshape(1, -1))
+            assert language is not None
+            if language.lower() == "auto":
+                lang_id = None
+            else:
+                if language.lower() not in tc.codec_language_id:
+                    raise NotImplementedError(f"Language {language} not implemented")
+                lang_id = tc.codec_language_id[language.lower()]
+            if language.lower() in ("chinese", "auto") and speaker not in ("", None) and tc.spk_is_dialect.get(speaker.lower()):
+                lang_id = tc.codec_language_id[tc.spk_is_dialect[speaker.lower()]]
+            prefix = ([tc.codec_nothink_id, tc.codec_think_bos_id, tc.codec_think_eos_id] if lang_id is None else
+                      [tc.codec_think_id, tc.codec_think_bos_id, lang_id, tc.codec_think_eos_id])
+            codec = [(CE, c) for c in prefix] + ([spk] if spk is not None else []) + [(CE, tc.codec_pad_id), (CE, tc.codec_bos_id)]
+            n = len(codec)
+            ids_l = host(ids)
+            rows += [(k, NONE, 0) for k in tp(ids_l[:3])]  # role tokens
+            rows += [(PAD if k < n - 2 else BOS, codec[k][0], codec[k][1]) for k in range(n - 1)]
+            icl = (voice_clone_prompt is not None and voice_clone_prompt.get("ref_code") is not None
+                   and voice_clone_prompt["icl_mode"][i])
+            if icl:
+                # generate_icl_prompt (base_model.py): text = TP(ref ++ text) ++ eos, codec = CE(bos) ++ 16-codebook sums of the ref frames
+                ref_code = voice_clone_prompt["ref_code"][i]
+                text = tp(host(ref_ids[i])[3:-2] + ids_l[3:-5]) + [EOS]
+                cod = [(CE, tc.codec_bos_id)] + [(ICL, n_ref + f) for f in range(ref_code.shape[0])]
+                ref_tables.append(ref_code.to(torch.int32))
+                n_ref += ref_code.shape[0]
+                Lt, Lc = len(text), len(cod)
+                if non_streaming_mode:
+                    rows += [(k, CE, tc.codec_pad_id) for k in text] + [(PAD, ck, ci) for ck, ci in cod]
+                    trail = [PAD]
+                elif Lt >= Lc:
+                    rows += [(text[k], cod[k][0], cod[k][1]) for k in range(Lc)]
+                    trail = text[Lc:] if Lt > Lc else [PAD]
+                else:
+                    rows += [(text[k] if k < Lt else PAD, cod[k][0], cod[k][1]) for k in range(Lc)]
+                    trail = [PAD]
+            elif non_streaming_mode:
+                rows += [(k, CE, tc.codec_pad_id) for k in tp(ids_l[3:-5]) + [EOS]]
+                rows.append((PAD, CE, tc.codec_bos_id))
+                trail = [PAD]
+            else:
+                rows.append((tp(ids_l[3:4])[0], codec[-1][0], codec[-1][1]))
+                trail = tp(ids_l[4:-5]) + [EOS]
+            seqs.append(rows)
+            trailing.append(trail)
+        # left-pad the batch, right-pad the trailing rows with the tts_pad vector (model.py:519-551); one more row: pad_e itself
+        B = len(seqs)
+        lens = [len(r) for r in seqs]
+        T = max(lens)
+        R = max(len(x) for x in trailing)
+        desc = torch.zeros(B * T + B * R + 1, 4, dtype=torch.int32)
+        desc[:, 0] = -1
+        tam = torch.zeros(B, T, dtype=torch.long)
+        for b_, rows in enumerate(seqs):
+            if rows:
+                desc[b_ * T + T - lens[b_]:(b_ + 1) * T, :3] = torch.tensor(rows, dtype=torch.int32)
+            tam[b_, T - lens[b_]:] = 1
+        for b_, tr in enumerate(trailing):
+            base = B * T + b_ * R
+            desc[base:base + R, 0] = PAD
+            desc[base:base + len(tr), 0] = torch.tensor(tr, dtype=torch.int32)
+        desc[-1, 0] = PAD
+        tok_dev = torch.tensor(tok, dtype=torch.long).to(dev, non_blocking=True)
+        tp_rows = t.text_projection(t.get_text_embeddings()(tok_dev)).contiguous()
+        spk_dev = torch.cat(spk_table, 0).to(dev, torch.bfloat16).contiguous() if spk_table else None
+        ref_dev = torch.cat(ref_tables, 0).to(dev).contiguous() if ref_tables else None
+        out = torch.empty(desc.shape[0], H, dtype=torch.bfloat16, device=dev)
+        eng.assemble_prompt(tp_rows, desc.to(dev, non_blocking=True), spk_dev, ref_dev, out)
+        tie = out[:B * T].view(B, T, H)
+        tth = out[B * T:B * T + B * R].view(B, R, H)
+        pad_e = out[-1].view(1, 1, H)
+        return tie, tam.to(dev), tth, pad_e
+
+    def _build_talker_inputs_eager(self, m, input_ids, ref_ids, voice_clone_prompt, languages, speakers,
+                                   non_streaming_mode: bool, instruct_ids=None):
+        """Op-by-op mirror of model.py:331-553.  TP = text_projection(text_embedding(ids)),
         CE = talker codec embedding."""
         t, tc, cfg = m.talker, m.config.talker_config, m.config
         dev = t.device

@@ -404,6 +404,12 @@ def test_prompt_builder_matches_oracle(tts_pair, mode, nsm):
                                         x_vector_only_mode=[True, True], icl_mode=[False, False])
         kw["languages"], kw["instruct_ids"], kw["ref_ids"] = ["English", "German"], [None, None], [None, None]
     got = tts._build_talker_inputs_local(m=m, input_ids=ids, non_streaming_mode=nsm, **kw)
+    # the default path is the fused one (one text_projection call + fq3_assemble_prompt); the op-by-op mirror of the reference
+    # must give the very same bits (same rounding points: one bf16 add per row, the ICL codebook sum one add at a time)
+    eager = tts._build_talker_inputs_eager(m, ids, kw["ref_ids"], kw["voice_clone_prompt"], kw["languages"], kw["speakers"], nsm,
+                                           kw["instruct_ids"])
+    for a_, b_ in zip(got, eager):
+        assert a_.shape == b_.shape and torch.equal(a_.cpu(), b_.cpu())
     cpu = lambda x: None if x is None else x.cpu()
     okw = dict(kw)
     okw["ref_ids"] = [cpu(r) for r in kw["ref_ids"]]
