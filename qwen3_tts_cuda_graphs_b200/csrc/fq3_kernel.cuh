@@ -1500,10 +1500,9 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      if (idx[u] >= 0) {
-        vst[idx[u] * 16 + dl] = vv[u];
-        if (dl < kGq) sc[dl * kAttnShort + idx[u]] = (dl == 0) ? sv[u][0] : sv[u][1];
-      }
+      // every slot of the V staging area is written (zeros beyond the range): the output loop below reads whole groups of four
+      vst[(warp * 2 + hw + u * 2 * kConsumerWarps) * 16 + dl] = vv[u];
+      if (idx[u] >= 0 && dl < kGq) sc[dl * kAttnShort + idx[u]] = (dl == 0) ? sv[u][0] : sv[u][1];
     }
     if (PROF) prof_mark(p, pidx, 2);
     cbar_sync();
@@ -1532,19 +1531,15 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
       const float Mx = pr[kGq * kAttnShort + j];
       const uint32_t* vw = reinterpret_cast<const uint32_t*>(vst) + wd;
       float Lsum = 0.f, O0 = 0.f, O1 = 0.f;
-#pragma unroll 2
+      // four positions per step, loads first (the slots beyond n hold probability 0 and a zero V row: they add nothing)
+#pragma unroll 3
       for (int g4 = 0; g4 < n4; ++g4) {
         const float4 v = p4[g4];
-        const float px[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = 4 * g4 + e;
-          const float pe = px[e];  // 0 beyond n
-          const uint32_t v2 = (i < n) ? vw[i * HW] : 0u;
-          Lsum += pe;
-          O0 = fmaf(pe, bf_lo(v2), O0);
-          O1 = fmaf(pe, bf_hi(v2), O1);
-        }
+        const uint32_t w0 = vw[(4 * g4) * HW], w1 = vw[(4 * g4 + 1) * HW], w2 = vw[(4 * g4 + 2) * HW], w3 = vw[(4 * g4 + 3) * HW];
+        Lsum += v.x; O0 = fmaf(v.x, bf_lo(w0), O0); O1 = fmaf(v.x, bf_hi(w0), O1);
+        Lsum += v.y; O0 = fmaf(v.y, bf_lo(w1), O0); O1 = fmaf(v.y, bf_hi(w1), O1);
+        Lsum += v.z; O0 = fmaf(v.z, bf_lo(w2), O0); O1 = fmaf(v.z, bf_hi(w2), O1);
+        Lsum += v.w; O0 = fmaf(v.w, bf_lo(w3), O0); O1 = fmaf(v.w, bf_hi(w3), O1);
       }
       if (nsplit == 1) {
         const float y0 = bf16r(Lsum > 0.f ? O0 / Lsum : 0.f), y1 = bf16r(Lsum > 0.f ? O1 / Lsum : 0.f);
@@ -1670,6 +1665,21 @@ __device__ __forceinline__ void attn_row(const Phase& ph, const LaunchParams& p,
   if (PROF) prof_mark(p, pidx, 3);
 }
 
+// One step of the split-KV merge: fold the partial state (ms, ls, a0, a1) of the next split into the running one.  Shared by the
+// cross-CTA combine and by the single-CTA multi-split item of the wide program, so both add in the same order with the same
+// expressions (the batch must not change a stream's arithmetic).
+__device__ __forceinline__ void combine_step(float& Mx, float& Lsum, float& O0, float& O1, float ms, float ls, float a0, float a1) {
+  if (ms != -INFINITY) {
+    const float m_new = fmaxf(Mx, ms);
+    const float c_old = (Mx == -INFINITY) ? 0.f : expf(Mx - m_new);
+    const float c_new = expf(ms - m_new);
+    Lsum = Lsum * c_old + ls * c_new;
+    O0 = O0 * c_old + a0 * c_new;
+    O1 = O1 * c_old + a1 * c_new;
+    Mx = m_new;
+  }
+}
+
 // Split-KV combine (contexts beyond kSplitLen): the CTA of split 0 polls the partials of all splits (its own included)
 // and merges them in split order.
 __device__ __forceinline__ void attn_combine(const Phase& ph, const LaunchParams& p, const Group& gr, int r, int kvh, int nsplit, uint32_t ep,
@@ -1705,15 +1715,7 @@ __device__ __forceinline__ void attn_combine(const Phase& ph, const LaunchParams
           const float ls = __uint_as_float(ll_check(wl[u], q + 1, ep, p, pidx));
           const float a0 = __uint_as_float(ll_check(wa[u], q + 4 + 2 * wd, ep, p, pidx));
           const float a1 = __uint_as_float(ll_check(wb[u], q + 5 + 2 * wd, ep, p, pidx));
-          if (ms != -INFINITY) {
-            const float m_new = fmaxf(Mx, ms);
-            const float c_old = (Mx == -INFINITY) ? 0.f : expf(Mx - m_new);
-            const float c_new = expf(ms - m_new);
-            Lsum = Lsum * c_old + ls * c_new;
-            O0 = O0 * c_old + a0 * c_new;
-            O1 = O1 * c_old + a1 * c_new;
-            Mx = m_new;
-          }
+          combine_step(Mx, Lsum, O0, O1, ms, ls, a0, a1);
         }
       }
     }
@@ -1722,8 +1724,180 @@ __device__ __forceinline__ void attn_combine(const Phase& ph, const LaunchParams
   }
 }
 
+// Wide program, contexts beyond one split: ONE CTA takes all splits of a (stream, kv head) in turn — same split boundaries, same
+// per-split two-pass softmax, same merge order as the cross-CTA scheme (attn_row + attn_combine), so the result is bit-identical
+// to the single-stream run; but q is normalised once, nothing travels through global memory between the splits, and the K/V rows
+// of split s + 1 are requested while split s is being reduced.  Decode rows only (one row per stream), splits of <= kAttnShort.
+__device__ __forceinline__ void attn_item_multi(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, const Group& gr, int kvh, int nsplit,
+                                                uint32_t ep, int pidx) {
+  const Smem sm = carve_smem(smem_base, p);
+  const StackRt& S = p.stacks[ph.stack];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = S.nq / S.nkv;
+  const int qb = ph.stack == ST_TALKER ? BUF_TQKV : BUF_PQKV, ab = ph.stack == ST_TALKER ? BUF_TATT : BUF_PATT;
+  const LLWord* qkv = reinterpret_cast<const LLWord*>(p.bufs[qb]) + (size_t)gr.first_row * p.ld[qb];
+  constexpr int HW = kHeadDim / 2;
+  const size_t head_base = (((size_t)ph.layer * S.n_slots + gr.slot) * S.nkv + kvh) * (size_t)S.max_pos * kHeadDim;
+  bf16* Kc = S.kcache + head_base;
+  bf16* Vc = S.vcache + head_base;
+  const int pos = gr.pos0;
+  const int L = pos + 1 - gr.n_pad;
+  const int per = (L + nsplit - 1) / nsplit;
+  FQ3_ASSERT(pos >= 0 && pos < S.max_pos && per <= kAttnShort && nsplit <= kMaxSplits, pidx, 220000 + pos);
+  float* qs = reinterpret_cast<float*>(sm.scratch);
+  uint4* fresh = reinterpret_cast<uint4*>(sm.scratch + 1024);
+  float* wp = reinterpret_cast<float*>(sm.scratch + 1024 + 4096);
+  float* sc = wp;                                                  // [kGq][kAttnShort]
+  uint4* vst = reinterpret_cast<uint4*>(wp + kGq * kAttnShort);    // [kAttnShort][16 pieces]
+  float* pr = reinterpret_cast<float*>(vst + kAttnShort * 16);     // [kGq][kAttnShort] | maxima [kGq]
+  const uint32_t ep_in = ep - 1;
+  const int hw = lane >> 4, dl = lane & 15;
+  uint4 kpre[kAttnPre], vpre[kAttnPre];
+  auto request = [&](int sp) {  // the cached K/V rows of split sp that this half-warp scores
+    const int a = gr.n_pad + sp * per, b = min(a + per, pos + 1);
+#pragma unroll
+    for (int u = 0; u < kAttnPre; ++u) {
+      const int i = a + warp * 2 + hw + u * 2 * kConsumerWarps;
+      kpre[u] = make_uint4(0u, 0u, 0u, 0u);
+      vpre[u] = kpre[u];
+      if (i < b && i < pos) {
+        kpre[u] = __ldcg(reinterpret_cast<const uint4*>(Kc + (size_t)i * kHeadDim) + dl);
+        vpre[u] = __ldcg(reinterpret_cast<const uint4*>(Vc + (size_t)i * kHeadDim) + dl);
+      }
+    }
+  };
+  long long tq = p.prof ? clock64() : 0ll;
+  request(0);
+  cbar_sync();  // the scratch may still be read by the previous phase's finishing threads
+  prof_acc(p, 12, tq);
+  // q heads (norm + rope, pre-scaled) and the fresh K / V row of this position: same code as attn_row, one warp each
+  for (int it = warp; it < gq + 2; it += kConsumerWarps) {
+    if (it < gq) {
+      const int rp = min(max(pos + gr.rope_delta, 0), S.rope_len - 1);
+      const LLWord* src = qkv + (kvh * gq + it) * HW + lane * 2;
+      const RopeRegs rr = rope_load(reinterpret_cast<const bf16*>(p.arena + (size_t)ph.g_off * 16), S.rope_cos + (size_t)rp * kHeadDim,
+                                    S.rope_sin + (size_t)rp * kHeadDim, lane);
+      LLWord w0, w1;
+      ll_head_wait(src, ep_in, w0, w1, p, pidx);
+      float x[4] = {bf_lo(w0.x), bf_hi(w0.x), bf_lo(w1.x), bf_hi(w1.x)};
+      head_norm_rope(x, rr, S.eps, lane);
+      const float scale = rsqrtf((float)kHeadDim);
+      *reinterpret_cast<float4*>(qs + it * kHeadDim + lane * 4) = make_float4(x[0] * scale, x[1] * scale, x[2] * scale, x[3] * scale);
+    } else {
+      const bool is_v = (it - gq) != 0;
+      uint2* f = reinterpret_cast<uint2*>(fresh);
+      if (is_v) {
+        const LLWord* vsrc = qkv + (S.nq + S.nkv + kvh) * HW + lane * 2;
+        LLWord v0, v1;
+        ll_head_wait(vsrc, ep_in, v0, v1, p, pidx);
+        const uint2 vv = make_uint2(v0.x, v1.x);
+        *reinterpret_cast<uint2*>(Vc + (size_t)pos * kHeadDim + lane * 4) = vv;
+        f[32 + lane] = vv;
+      } else {
+        const int rp = min(max(pos + gr.rope_delta, 0), S.rope_len - 1);
+        const LLWord* ksrc = qkv + (S.nq + kvh) * HW + lane * 2;
+        const RopeRegs rr = rope_load(reinterpret_cast<const bf16*>(p.arena + (size_t)ph.b_off * 16), S.rope_cos + (size_t)rp * kHeadDim,
+                                      S.rope_sin + (size_t)rp * kHeadDim, lane);
+        LLWord k0, k1;
+        ll_head_wait(ksrc, ep_in, k0, k1, p, pidx);
+        float x[4] = {bf_lo(k0.x), bf_hi(k0.x), bf_lo(k1.x), bf_hi(k1.x)};
+        head_norm_rope(x, rr, S.eps, lane);
+        const uint2 kk = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+        *reinterpret_cast<uint2*>(Kc + (size_t)pos * kHeadDim + lane * 4) = kk;
+        f[lane] = kk;
+      }
+    }
+  }
+  cbar_sync();
+  float qr[kGq][8];
+#pragma unroll
+  for (int j = 0; j < kGq; ++j) {
+    const float4 q0 = *reinterpret_cast<const float4*>(qs + j * kHeadDim + dl * 8);
+    const float4 q1 = *reinterpret_cast<const float4*>(qs + j * kHeadDim + dl * 8 + 4);
+    qr[j][0] = q0.x; qr[j][1] = q0.y; qr[j][2] = q0.z; qr[j][3] = q0.w;
+    qr[j][4] = q1.x; qr[j][5] = q1.y; qr[j][6] = q1.z; qr[j][7] = q1.w;
+  }
+  float Mx = -INFINITY, Lsum = 0.f, O0 = 0.f, O1 = 0.f;  // running state of an output thread (one packed output word)
+  const int oj = threadIdx.x / HW, owd = threadIdx.x - oj * HW;
+  prof_acc(p, 13, tq);
+#pragma unroll 1
+  for (int sp = 0; sp < nsplit; ++sp) {
+    const int a = gr.n_pad + sp * per, b = min(a + per, pos + 1);
+    const int n = b - a, n4 = (n + 3) >> 2;
+    // every half-warp scores its (<= 2) positions of this split and parks their V rows; slots beyond n get -inf
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = warp * 2 + hw + u * 2 * kConsumerWarps;
+      const int i = a + idx;
+      uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
+      if (i < b) {
+        if (i >= pos) { kk = fresh[dl]; vv = fresh[16 + dl]; }
+        else { kk = kpre[u]; vv = vpre[u]; }
+      }
+      const float k[8] = {bf_lo(kk.x), bf_hi(kk.x), bf_lo(kk.y), bf_hi(kk.y), bf_lo(kk.z), bf_hi(kk.z), bf_lo(kk.w), bf_hi(kk.w)};
+      float sv[kGq];
+#pragma unroll
+      for (int j = 0; j < kGq; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) t = fmaf(qr[j][d], k[d], t);
+        sv[j] = t;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < kGq; ++j) sv[j] += __shfl_xor_sync(0xffffffffu, sv[j], o);
+      }
+      vst[idx * 16 + dl] = vv;  // zeros beyond the range
+      if (dl < kGq) sc[dl * kAttnShort + idx] = (i < b) ? ((dl == 0) ? sv[0] : sv[1]) : -INFINITY;
+    }
+    if (sp + 1 < nsplit) request(sp + 1);
+    prof_acc(p, 14, tq);
+    cbar_sync();
+    prof_acc(p, 15, tq);
+    if (threadIdx.x < kGq * kAttnShort) {
+      const int j = threadIdx.x / kAttnShort, i = threadIdx.x - j * kAttnShort;
+      const float4* s4 = reinterpret_cast<const float4*>(sc + j * kAttnShort);
+      float m = -INFINITY;
+      for (int g4 = 0; g4 < n4; ++g4) {
+        const float4 v = s4[g4];
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      }
+      pr[threadIdx.x] = expf(sc[threadIdx.x] - m);
+      if (i == 0) pr[kGq * kAttnShort + j] = m;
+    }
+    prof_acc(p, 18, tq);
+    cbar_sync();
+    prof_acc(p, 19, tq);
+    if (threadIdx.x < gq * HW) {
+      const float4* p4 = reinterpret_cast<const float4*>(pr + oj * kAttnShort);
+      const float ms = pr[kGq * kAttnShort + oj];
+      const uint32_t* vw = reinterpret_cast<const uint32_t*>(vst) + owd;
+      float ls = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll 3
+      for (int g4 = 0; g4 < n4; ++g4) {
+        const float4 v = p4[g4];
+        const uint32_t w0 = vw[(4 * g4) * HW], w1 = vw[(4 * g4 + 1) * HW], w2 = vw[(4 * g4 + 2) * HW], w3 = vw[(4 * g4 + 3) * HW];
+        ls += v.x; a0 = fmaf(v.x, bf_lo(w0), a0); a1 = fmaf(v.x, bf_hi(w0), a1);
+        ls += v.y; a0 = fmaf(v.y, bf_lo(w1), a0); a1 = fmaf(v.y, bf_hi(w1), a1);
+        ls += v.z; a0 = fmaf(v.z, bf_lo(w2), a0); a1 = fmaf(v.z, bf_hi(w2), a1);
+        ls += v.w; a0 = fmaf(v.w, bf_lo(w3), a0); a1 = fmaf(v.w, bf_hi(w3), a1);
+      }
+      combine_step(Mx, Lsum, O0, O1, ms, ls, a0, a1);
+    }
+    prof_acc(p, 16, tq);
+    cbar_sync();  // the next split overwrites the scores, the parked V rows and the probabilities
+    prof_acc(p, 17, tq);
+  }
+  if (threadIdx.x < gq * HW) {
+    const int qh = kvh * gq + oj;
+    const float y0 = bf16r(Lsum > 0.f ? O0 / Lsum : 0.f), y1 = bf16r(Lsum > 0.f ? O1 / Lsum : 0.f);
+    ll_st(reinterpret_cast<LLWord*>(p.bufs[ab]) + (size_t)gr.first_row * p.ld[ab] + qh * HW + owd, pack_bf16x2(y0, y1), ep);
+  }
+}
 
-template <bool PROF>
+
+template <bool PROF, bool WIDE>
 __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& p, unsigned char* smem_base, uint32_t ep, int pidx,
                                            const int* frame_pos) {
   const StackRt& S = p.stacks[ph.stack];
@@ -1748,10 +1922,20 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& 
   // stream's attention arithmetic does not change with the number of streams in the launch; with more items than CTAs a
   // CTA takes several, and every CTA publishes all its partials before it waits for anybody else's (two passes).
   const int cap = max(1, min(small_div(G, S.nkv), kMaxSplits));
+  // wide program: a row whose splits fit the two-pass path is ONE item per kv head (attn_item_multi walks its splits)
+  auto row_items = [&](const Group& gr, int r, int& nsplit, bool& multi) {
+    const int L = gr.pos0 + r + 1 - gr.n_pad;
+    nsplit = num_splits(L, cap);
+    multi = WIDE && p.mode != MODE_PREFILL && nsplit > 1 && (L + nsplit - 1) / nsplit <= kAttnShort;
+    return S.nkv * (multi ? 1 : nsplit);
+  };
   int total = 0;
   for (int g = 0; g < ng; ++g) {
     const Group gr = get_group(ph, p, g, frame_pos);
-    for (int r = 0; r < gr.nrows; ++r) total += S.nkv * num_splits(gr.pos0 + r + 1 - gr.n_pad, cap);
+    for (int r = 0; r < gr.nrows; ++r) {
+      int ns; bool mu;
+      total += row_items(gr, r, ns, mu);
+    }
   }
   // item -> CTA: spread the items over the whole grid (stride) so concurrent items sit on distant SMs
   const int stride = (total <= G) ? small_div(G, total) : 1;
@@ -1773,13 +1957,19 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& 
       for (int g = 0; g < ng && !found; ++g) {
         const Group gr = get_group(ph, p, g, frame_pos);
         for (int r = 0; r < gr.nrows; ++r) {
-          const int nsplit = num_splits(gr.pos0 + r + 1 - gr.n_pad, cap);
-          const int nitems = S.nkv * nsplit;
+          int nsplit; bool multi;
+          const int nitems = row_items(gr, r, nsplit, multi);
           if (item < base + nitems) {
             const int it = item - base;
-            const int kvh = small_div(it, nsplit), sp = it - kvh * nsplit;
-            if (pass == 0) attn_row<PROF>(ph, p, smem_base, gr, r, kvh, sp, nsplit, ep, pidx);
-            else if (nsplit > 1 && sp == 0) attn_combine(ph, p, gr, r, kvh, nsplit, ep, pidx);
+            if (multi) {
+              if constexpr (WIDE) {
+                if (pass == 0) attn_item_multi(ph, p, smem_base, gr, it, nsplit, ep, pidx);
+              }
+            } else {
+              const int kvh = small_div(it, nsplit), sp = it - kvh * nsplit;
+              if (pass == 0) attn_row<PROF>(ph, p, smem_base, gr, r, kvh, sp, nsplit, ep, pidx);
+              else if (nsplit > 1 && sp == 0) attn_combine(ph, p, gr, r, kvh, nsplit, ep, pidx);
+            }
             found = true;
             break;
           }
@@ -2597,10 +2787,10 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
         case PH_ATTN:
           if constexpr (WIDE) {
             long long tp = p.prof ? clock64() : 0ll;
-            attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos);
+            attn_phase<PROF, true>(ph, p, smem_raw, ep, i, frame_pos);
             prof_acc(p, 4, tp);
           } else {
-            attn_phase<PROF>(ph, p, smem_raw, ep, i, frame_pos);
+            attn_phase<PROF, false>(ph, p, smem_raw, ep, i, frame_pos);
           }
           break;
         case PH_SAMPLE:

@@ -29,6 +29,7 @@ tot = sum(buf[i] for i in range(6))
 print(f"{ns} streams, context {T}: {a.elapsed_time(b) / frames:.3f} ms per frame-step; CTA {os.environ.get('FQ3_PROF')} thread 0, {buf[6] // frames} GEMV phases per frame")
 for i, n in enumerate(names):
     print(f"  {n:26s} {buf[i] / frames:10.0f} cycles/frame  {100 * buf[i] / tot:5.1f} %")
-for i, n in ((8, "leader: wait for weights"), (9, "leader: k loop"), (10, "leader: k-parts"), (11, "leader: epilogue + publish")):
+for i, n in ((12, "multi-attn: entry barrier"), (13, "multi-attn: q / fresh K,V"), (14, "multi-attn: scores + request"), (15, "multi-attn: barrier 1"),
+             (18, "multi-attn: probabilities"), (19, "multi-attn: barrier 2"), (16, "multi-attn: output + merge"), (17, "multi-attn: barrier 3"), (8, "leader: wait for weights"), (9, "leader: k loop"), (10, "leader: k-parts"), (11, "leader: epilogue + publish")):
     print(f"  {n:26s} {buf[i] / frames:10.0f} cycles/frame")
 print(f"  {'sum':26s} {tot / frames:10.0f} cycles/frame = {tot / frames / 1.965e3:.0f} us at 1.965 GHz")
