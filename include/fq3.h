@@ -170,7 +170,10 @@ int fq3_assemble_prompt(fq3_engine* e, const void* tp_rows, const void* desc_i32
  * predictor_graph.py:70-71).  fq3_decode_frames with n_streams <= 4 runs the reference-shaped frame program (two predictor
  * rows per stream in pass 0).  Above four it runs the "wide" frame program in lock-step groups of up to
  * fq3_lockstep_group(e) streams (16 where the model's rows fit the staging buffer), one launch per group and chunk: every
- * stream of a group rides the same weight sweep, a stream's tokens are the ones its single-stream run produces. */
+ * stream of a group rides the same weight sweep, a stream's tokens are the ones its single-stream run produces.
+ * fq3_lockstep_group returns 4 when the wide program is not available for the model (1.7B dims: a row of the 6144-wide
+ * down-projection input is 12 KB, three fit next to the weight ring); fq3_decode_frames then refuses more than four streams
+ * with -FQ3_E_UNSUPPORTED and the host decodes in groups of four. */
 int fq3_lockstep_group(const fq3_engine* e);
 
 /* The engine's grid may be smaller than the device (128 of 148 SMs by default: every model shape partitions evenly over

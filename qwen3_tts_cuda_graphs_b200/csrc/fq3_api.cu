@@ -961,7 +961,10 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
   if (2 * n_streams > kMaxRows) {
     // more than four streams: the wide frame program, in lock-step groups of up to wide_rows streams, one launch per group
     // (a group streams the weights once for all its streams; groups follow each other on the stream)
-    if (e->wide_rows < 1) return fail(FQ3_E_UNSUPPORTED, "this model's rows do not fit the wide frame program's staging buffer");
+    // (1.7B dims: a 6144-column row is 12 KB and the ring must hold a six-stage group: three rows fit — not worth it next to the
+    // four streams of the reference-shaped program; the host then runs groups of four through that one)
+    if (e->wide_rows <= kMaxRows / 2)
+      return fail(FQ3_E_UNSUPPORTED, "more than four lock-step streams do not fit this model's staging buffer: decode in groups of fq3_lockstep_group()");
     const int n_groups = (n_streams + e->wide_rows - 1) / e->wide_rows;
     const int per = (n_streams + n_groups - 1) / n_groups;  // even groups
     // all streams first: a group's working rows overwrite pair-layout rows of other groups' streams
@@ -1023,7 +1026,7 @@ int fq3_assemble_prompt(fq3_engine* e, const void* tp_rows, const void* desc_i32
   return 0;
 }
 
-int fq3_lockstep_group(const fq3_engine* e) { return e ? std::max(e->wide_rows, kMaxRows / 2) : 0; }
+int fq3_lockstep_group(const fq3_engine* e) { return e ? std::max(e->wide_rows, kMaxRows / 2) : 0; }  /* 4 = no wide program */
 int fq3_reduced_grid(const fq3_engine* e) { return (e && e->G < e->n_sms) ? e->G : 0; }
 
 int fq3_clear_fault(fq3_engine* e, void* stream) {

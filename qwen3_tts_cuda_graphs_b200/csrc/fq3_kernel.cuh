@@ -522,6 +522,10 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
   const int n_units = M * 8;
   const uint32_t rstride = xrow_stride(K);
   const float inv_k = __frcp_rn((float)K);  // = the host's 1.0f / K (Plan::inv_k)
+  // (every CTA reads the same rows in the same order.  Starting each CTA at a different unit — so that they do not all ask L2 for
+  // the same lines at once — was measured and is 9 % slower at 16 streams, and so are twelve requests per lane instead of six:
+  // L2 serves the common lines well, the staging is bound by the bytes, M * K * 8 per CTA and phase.)
+  auto unit_of = [&](int u) { return u; };
   FQ3_ASSERT(Kq <= 256 * kMaxJ && M <= kMaxWide, pidx, 310000 + M);
 #pragma unroll 1
   for (int u0 = warp; u0 < n_units; u0 += UNITS * kConsumerWarps) {
@@ -533,13 +537,14 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
       uint4 w[UNITS][JC];
 #pragma unroll
       for (int h = 0; h < UNITS; ++h) {
-        const int u = u0 + h * kConsumerWarps;
+        const bool uok = u0 + h * kConsumerWarps < n_units;
+        const int u = unit_of(u0 + h * kConsumerWarps);
         const LLWord* src = in + (size_t)(u >> 3) * ld;
         const int qb = (u & 7) * 32 + lane + 256 * j0;
 #pragma unroll
         for (int j = 0; j < JC; ++j) {
           w[h][j] = make_uint4(0u, ep_in, 0u, ep_in);  // absent quads: payload 0, never waited for
-          if (u < n_units && qb + 256 * j < Kq) w[h][j] = ll_ld_pair(src + 2 * (qb + 256 * j));
+          if (uok && qb + 256 * j < Kq) w[h][j] = ll_ld_pair(src + 2 * (qb + 256 * j));
         }
       }
       if (ep_in != 0) {
@@ -557,7 +562,7 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
           spin.tick(p, DE_LL_WAIT, pidx, (int)ep_in);
 #pragma unroll
           for (int h = 0; h < UNITS; ++h) {  // only the quads that are still missing are requested again
-            const int u = u0 + h * kConsumerWarps;
+            const int u = unit_of(u0 + h * kConsumerWarps);
             const LLWord* src = in + (size_t)(u >> 3) * ld;
             const int qb = (u & 7) * 32 + lane + 256 * j0;
 #pragma unroll
@@ -568,13 +573,14 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
       }
 #pragma unroll
       for (int h = 0; h < UNITS; ++h) {
-        const int u = u0 + h * kConsumerWarps;
+        const bool uok = u0 + h * kConsumerWarps < n_units;
+        const int u = unit_of(u0 + h * kConsumerWarps);
         const int qb = (u & 7) * 32 + lane + 256 * j0;
         const uint32_t xrow = xs + (uint32_t)(u >> 3) * rstride;
 #pragma unroll
         for (int j = 0; j < JC; ++j) {
           const int q = qb + 256 * j;
-          if (u < n_units && q < Kq) xquad_store(xrow + xquad_off(q), w[h][j].x, w[h][j].z);
+          if (uok && q < Kq) xquad_store(xrow + xquad_off(q), w[h][j].x, w[h][j].z);
           const float x0 = bf_lo(w[h][j].x), x1 = bf_hi(w[h][j].x), x2 = bf_lo(w[h][j].z), x3 = bf_hi(w[h][j].z);
           ss[h] += fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);  // first quad: 0 + sq = sq exactly; absent quads add 0
         }
@@ -583,9 +589,10 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
     if (norm) {
 #pragma unroll
       for (int h = 0; h < UNITS; ++h) {
-        const int u = u0 + h * kConsumerWarps;
+        const bool uok = u0 + h * kConsumerWarps < n_units;
+        const int u = unit_of(u0 + h * kConsumerWarps);
         const float t = warp_sum(ss[h]);
-        if (u < n_units && lane == 0) sts_f32(red + (uint32_t)u * 4u, t);
+        if (uok && lane == 0) sts_f32(red + (uint32_t)u * 4u, t);
       }
     }
   }
@@ -597,8 +604,8 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
   for (int u0 = warp; u0 < n_units; u0 += UNITS * kConsumerWarps) {
 #pragma unroll
     for (int h = 0; h < UNITS; ++h) {
-      const int u = u0 + h * kConsumerWarps;
-      if (u < n_units) {
+      if (u0 + h * kConsumerWarps < n_units) {
+        const int u = unit_of(u0 + h * kConsumerWarps);
         const int m = u >> 3, qb = (u & 7) * 32 + lane;
         const float4 r0 = lds_f32x4(red + (uint32_t)m * 32u), r1 = lds_f32x4(red + (uint32_t)m * 32u + 16u);
         const float tot = ((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w));
@@ -1073,6 +1080,7 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
   }
   {
     long long* tpp = p.prof ? &tp : nullptr;
+    // six 16-byte requests per lane in flight (twelve was measured: slower — every CTA asks L2 for the same lines)
     if (K <= 1024) load_x_rows<6, 1>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
     else if (K <= 2048) load_x_rows<3, 2>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
     else load_x_rows<2, 3>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);

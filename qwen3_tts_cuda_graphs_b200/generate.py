@@ -138,8 +138,11 @@ def fast_generate_batch(talker_graph, predictor_graph, requests, max_new_tokens:
     frames = 0
     torch.cuda.synchronize()
     t0 = time.time()
-    for g0 in range(0, len(requests), eng.max_streams):
-        group = requests[g0:g0 + eng.max_streams]
+    # one call per engine-full of requests when the wide frame program is available (it forms its own lock-step groups of up to
+    # 16); otherwise (1.7B dims) groups of four through the reference-shaped program
+    per_call = eng.max_streams if eng.lockstep_group > 4 else min(eng.max_streams, 4)
+    for g0 in range(0, len(requests), per_call):
+        group = requests[g0:g0 + per_call]
         for s, (tie, tam, tth, tpe) in enumerate(group):
             if tie.shape[1] > eng.max_seq_len:
                 raise RuntimeError(
