@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Summaries for profiles/: (1) launch list csv -> markdown table, (2) one --set full report -> metric list + ncu_traffic.json.
 usage: summarize_ncu.py launches <launches.csv> <out.md>
-       summarize_ncu.py full <report.ncu-rep> <out.txt> [frames_per_launch]"""
+       summarize_ncu.py full <report.ncu-rep> <out.txt> [frames_per_launch]
+       summarize_ncu.py gemm <report.ncu-rep> <out.txt>      (tensor-pipe utilisation of the captured GEMM launches)"""
 import csv, io, json, subprocess, sys, collections, os
 
 def launches(src, dst):
@@ -54,5 +55,21 @@ def full(rep, dst, fpl):
                 print(tr)
     print(open(dst).read()[:2500])
 
+def gemm(rep, dst):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    want = [k for k in hdr if k in KEEP or k.startswith("sm__pipe_tensor") or k.startswith("sm__inst_executed_pipe_tensor")
+            or k in ("launch__grid_size", "sm__cycles_elapsed.avg", "smsp__inst_executed_pipe_uniform.sum")]
+    with open(dst, "w") as f:
+        f.write(f"# {rep}: tensor-pipe view of the captured launches (ncu --set full)\n")
+        for li, r in enumerate(rows[2:]):
+            d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
+            f.write(f"## launch {li}: {d.get('Kernel Name')}  grid {d.get('launch__grid_size')}\n")
+            for k in want:
+                f.write(f"{k:90s} {d[k]:>18s} {u[k]}\n")
+    print(open(dst).read()[:3000])
+
 if sys.argv[1] == "launches": launches(sys.argv[2], sys.argv[3])
+elif sys.argv[1] == "gemm": gemm(sys.argv[2], sys.argv[3])
 else: full(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 8)
