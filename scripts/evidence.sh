@@ -15,9 +15,11 @@ if [ "$2" != "nonu" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_${tag}.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fq3_stream -s 3 -c 1 -o gpurun_out/prof_frames_${tag} python scripts/prof_frames.py > gpurun_out/ncu_full_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_full_${tag}.log
-# tensor-pipe utilisation of the tcgen05 GEMM (codec decode of a 33-frame window): the largest launches of one decode
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fq3c_gemm_tc5 -s 150 -c 60 -o gpurun_out/prof_gemm_${tag} python scripts/codec_time.py > gpurun_out/ncu_gemm_${tag}.log 2>&1
+# tensor-pipe utilisation of the tcgen05 GEMM (codec decode of a 33-frame window): a dozen launches of one decode; the report is
+# summarised here and deleted (gpurun_out/ must stay under 64 MiB)
+timeout 600 ncu --set full --clock-control none -k regex:fq3c_gemm_tc5 -s 150 -c 14 -o /tmp/prof_gemm_${tag} python scripts/codec_time.py > gpurun_out/ncu_gemm_${tag}.log 2>&1
 tail -2 gpurun_out/ncu_gemm_${tag}.log
+python scripts/summarize_ncu.py gemm /tmp/prof_gemm_${tag}.ncu-rep gpurun_out/ncu_gemm_summary_${tag}.txt > /dev/null 2>&1
 fi
 FQ3_PROF=0 timeout 300 python scripts/wide_prof.py 16 14 > gpurun_out/wide_profile_${tag}.log 2>&1
 FQ3_PROF=77 timeout 300 python scripts/wide_prof.py 16 300 >> gpurun_out/wide_profile_${tag}.log 2>&1

@@ -228,6 +228,41 @@ def test_frame_loop_teacher_forced_against_oracle(pair):
     assert (codes[:, 1:] < cfg.predictor.vocab_size).all()
 
 
+def test_left_padded_prompt_and_frames_against_oracle(pair):
+    """Left-padded prompt (the batched layout of model.py:519-551: zero rows in front, attention mask 0 there, rope positions
+    shifted by -n_pad: talker_graph.py:172-196) through prefill AND the frame loop, against the oracle run on the same padded
+    input with the same mask — the padding path checked against the reference's semantics, not only against the unpadded run."""
+    cfg, w, eng, orc = pair
+    tie, tam, tth, tpe = synth_prompt(cfg, T=12, R=2, seed=6)
+    n_pad, n = 4, 6
+    H = cfg.talker.hidden_size
+    tie_p = torch.cat([torch.zeros(1, n_pad, H, dtype=torch.bfloat16), tie], dim=1)
+    tam_p = torch.cat([torch.zeros(1, n_pad, dtype=torch.long), tam], dim=1)
+    pol = _sp(do_sample=False, repetition_penalty=1.05, min_new_tokens=2)
+    eng.set_text_conditioning(0, tth[0].cuda(), tpe.cuda())
+    logits = eng.prefill(0, tie_p[0].cuda(), n_pad, pol, want_logits=True).clone()
+    ref_logits, _, plen = orc.talker_prefill(tie_p, tam_p)
+    assert plen == 12 + n_pad
+    assert rel_err(logits, ref_logits[0]) <= TOL, rel_err(logits, ref_logits[0])
+    eng.decode_frames(1, n, pol, _sub(do_sample=False))
+    st = eng.status(0)
+    assert st.error == 0 and st.n_frames == n and st.position == 12 + n_pad + n
+    codes = eng.read_codes(0, 0, n)
+    orc.sub.do_sample = False
+    trace = {}
+    frames = list(orc.generate_frames(tie_p, tam_p, tth, tpe, max_new_tokens=n, min_new_tokens=2, do_sample=False,
+                                      repetition_penalty=1.05, max_seq_len=272, trace=trace, forced=codes))
+    assert len(frames) == n
+    tscale = float(trace["prefill_logits"].abs().max())
+    bad = []
+    for i in range(n):
+        nxt = int(codes[i + 1, 0]) if i + 1 < n else st.token
+        fin = trace["talker_final"][i]
+        if float(fin.max() - fin[nxt]) > TOL * tscale:
+            bad.append(("talker", i, nxt, int(fin.argmax())))
+    assert not bad, bad
+
+
 # ------------------------------------------------------------------------------------------------
 # loop control: determinism, chunking, EOS / min_new_tokens, cache bound
 # ------------------------------------------------------------------------------------------------
