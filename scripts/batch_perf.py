@@ -3,6 +3,7 @@ import os, sys, time, json
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+if os.environ.get("FQ3_VARIANT"): sys.path.insert(0, os.path.join(ROOT, "variants", os.environ["FQ3_VARIANT"]))
 from helpers import make_cfg, make_weights, make_engine, synth_prompt
 from qwen3_tts_cuda_graphs_b200.engine import SamplingPolicy, SubPolicy
 name = sys.argv[1] if len(sys.argv) > 1 else "0.6B-Base"
