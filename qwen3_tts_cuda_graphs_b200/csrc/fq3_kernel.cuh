@@ -254,8 +254,11 @@ __device__ __forceinline__ void prof_mark(const LaunchParams& p, int pidx, int s
   if (p.prof && (int)threadIdx.x == thread && (int)blockIdx.x == p.prof_cta && pidx >= 0 && pidx < 512) p.prof[(size_t)pidx * 16 + slot] = clock64();
 }
 // FQ3_PROF=<cta> with the wide program: thread 0 of that CTA adds cycles per category (scripts/wide_prof.py)
+#ifndef FQ3_WIDE_PROF
+#define FQ3_WIDE_PROF 0  // build with -DFQ3_WIDE_PROF=1 for scripts/wide_prof.py (the marks cost ~700 cycles each and a few per cent when idle)
+#endif
 __device__ __forceinline__ void prof_acc(const LaunchParams& p, int cat, long long& t, int thread = 0) {
-  if (p.prof && (int)threadIdx.x == thread && (int)blockIdx.x == p.prof_cta) {
+  if (FQ3_WIDE_PROF && p.prof && (int)threadIdx.x == thread && (int)blockIdx.x == p.prof_cta) {
     const long long now = clock64();
     p.prof[cat] += now - t;
     t = now;
@@ -513,7 +516,7 @@ __device__ __forceinline__ uint32_t xrow_stride(int K) { return (uint32_t)K * 2u
 // virtual warp, the eight sums in a fixed tree — so a stream's arithmetic does not depend on how many streams (or prompt rows)
 // share the launch.  A unit = (row, virtual warp); a warp keeps UNITS units (up to UNITS * kMaxJ 16-byte requests per lane) in flight.
 constexpr int kMaxJ = 6;  // quads per lane of a unit: K <= 6144
-template <int UNITS, int JC>
+template <int UNITS, int JC, bool ENTRY_BARRIER = false>
 __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
                                          int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red, long long* tprof = nullptr) {
   const int Kq = K >> 2;
@@ -527,6 +530,7 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
   // L2 serves the common lines well, the staging is bound by the bytes, M * K * 8 per CTA and phase.)
   auto unit_of = [&](int u) { return u; };
   FQ3_ASSERT(Kq <= 256 * kMaxJ && M <= kMaxWide, pidx, 310000 + M);
+  if (ENTRY_BARRIER && warp >= n_units) cbar_sync();  // a warp without a unit still meets the others (below: behind the first requests)
 #pragma unroll 1
   for (int u0 = warp; u0 < n_units; u0 += UNITS * kConsumerWarps) {
     float ss[UNITS];
@@ -547,6 +551,8 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
           if (uok && qb + 256 * j < Kq) w[h][j] = ll_ld_pair(src + 2 * (qb + 256 * j));
         }
       }
+      // the block barrier that lets go of the previous phase's rows and partial words waits in the shadow of the first requests
+      if (ENTRY_BARRIER && u0 == warp && j0 == 0) cbar_sync();
       if (ep_in != 0) {
         Spin spin;
         unsigned tries = 0;
@@ -1056,9 +1062,9 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
   const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
   const uint32_t glap = gcur.lap;
   if (norm) gcur.advance(1, kGammaSlots);
-  long long tp = p.prof ? clock64() : 0ll;
-  cbar_sync();  // the previous phase's readers of the activation rows / partial words are through
-  prof_acc(p, 0, tp);
+  long long tp = (FQ3_WIDE_PROF && p.prof) ? clock64() : 0ll;
+  // (the block barrier behind which the previous phase's activation rows and partial words may be overwritten sits inside
+  // load_x_rows, behind the first poll requests: ENTRY_BARRIER)
   if (norm && !mbar_try_wait_a(gfullb, glap)) {
     Spin spin;
     while (!mbar_try_wait_a(gfullb, glap)) spin.tick(p, DE_FULL_WAIT, pidx, 100);
@@ -1079,11 +1085,11 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
     }
   }
   {
-    long long* tpp = p.prof ? &tp : nullptr;
+    long long* tpp = (FQ3_WIDE_PROF && p.prof) ? &tp : nullptr;
     // six 16-byte requests per lane in flight (twelve was measured: slower — every CTA asks L2 for the same lines)
-    if (K <= 1024) load_x_rows<6, 1>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
-    else if (K <= 2048) load_x_rows<3, 2>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
-    else load_x_rows<2, 3>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+    if (K <= 1024) load_x_rows<6, 1, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+    else if (K <= 2048) load_x_rows<3, 2, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+    else load_x_rows<2, 3, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
   }
   if (norm && lane == 0) mbar_arrive_a(gemptyb);
 
@@ -1111,8 +1117,8 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
     uint32_t wa = c.ring + lane_w + (uint32_t)my.slot * kStageBytes + (uint32_t)(ch0 & (kStageChunks - 1)) * kBlockBytes;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
     int ch = ch0;
-    long long tq = p.prof ? clock64() : 0ll;
-    if (p.prof) { tq = tp; prof_acc(p, 8, tq, kProfLeader); }  // 8: from the staging barrier to the weights being there
+    long long tq = (FQ3_WIDE_PROF && p.prof) ? clock64() : 0ll;
+    if (FQ3_WIDE_PROF && p.prof) { tq = tp; prof_acc(p, 8, tq, kProfLeader); }  // 8: from the staging barrier to the weights being there
 #pragma unroll 1
     while (ch < ch1) {
       if (ch != ch0 && (ch & (kStageChunks - 1)) == 0) {
@@ -1216,7 +1222,7 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
   cur.advance(kd.n_stages, c.n_stages);
   gst = ((gst & 1u) ^ 1u) | 2u;
   prof_acc(p, 3, tp);
-  if (p.prof && tid == 0 && (int)blockIdx.x == p.prof_cta) p.prof[6] += 1;
+  if (FQ3_WIDE_PROF && p.prof && tid == 0 && (int)blockIdx.x == p.prof_cta) p.prof[6] += 1;
 }
 
 // Producer side of one GEMV phase: stream this CTA's groups through the ring, one contiguous bulk copy per stage (up to
@@ -1774,7 +1780,7 @@ __device__ __forceinline__ void attn_item_multi(const Phase& ph, const LaunchPar
       }
     }
   };
-  long long tq = p.prof ? clock64() : 0ll;
+  long long tq = (FQ3_WIDE_PROF && p.prof) ? clock64() : 0ll;
   request(0);
   cbar_sync();  // the scratch may still be read by the previous phase's finishing threads
   prof_acc(p, 12, tq);
@@ -1930,6 +1936,36 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, const LaunchParams& 
   // stream's attention arithmetic does not change with the number of streams in the launch; with more items than CTAs a
   // CTA takes several, and every CTA publishes all its partials before it waits for anybody else's (two passes).
   const int cap = max(1, min(small_div(G, S.nkv), kMaxSplits));
+  if constexpr (WIDE) {
+    if (p.mode != MODE_PREFILL && !(ph.flags & F_ROWS2)) {
+      // decode rows of the wide program: exactly one item per (stream, kv head) as long as every context fits the two-pass path
+      // (nsplit = ceil(L / 48) <= cap) — item -> (stream, kv head) is a division, not a walk over the streams
+      int Lmax = 0;
+      for (int g = 0; g < ng; ++g) {
+        const Group gr = get_group(ph, p, g, frame_pos);
+        Lmax = max(Lmax, gr.pos0 + 1 - gr.n_pad);
+      }
+      if (Lmax <= kAttnShort * cap) {
+        const int total = ng * S.nkv;
+        const int stride = (total <= G) ? small_div(G, total) : 1;
+        int first = cta, step = G;
+        if (stride > 1) {
+          const int q = small_div(cta, stride);
+          first = (cta - q * stride == 0 && q < total) ? q : total;
+          step = total;
+        }
+#pragma unroll 1
+        for (int item = first; item < total; item += step) {
+          const int g = small_div(item, S.nkv), kvh = item - g * S.nkv;
+          const Group gr = get_group(ph, p, g, frame_pos);
+          const int nsplit = num_splits(gr.pos0 + 1 - gr.n_pad, cap);
+          if (nsplit == 1) attn_row<PROF>(ph, p, smem_base, gr, 0, kvh, 0, 1, ep, pidx);
+          else attn_item_multi(ph, p, smem_base, gr, kvh, nsplit, ep, pidx);
+        }
+        return;
+      }
+    }
+  }
   // wide program: a row whose splits fit the two-pass path is ONE item per kv head (attn_item_multi walks its splits)
   auto row_items = [&](const Group& gr, int r, int& nsplit, bool& multi) {
     const int L = gr.pos0 + r + 1 - gr.n_pad;
@@ -2794,7 +2830,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
           break;
         case PH_ATTN:
           if constexpr (WIDE) {
-            long long tp = p.prof ? clock64() : 0ll;
+            long long tp = (FQ3_WIDE_PROF && p.prof) ? clock64() : 0ll;
             attn_phase<PROF, true>(ph, p, smem_raw, ep, i, frame_pos);
             prof_acc(p, 4, tp);
           } else {
@@ -2803,7 +2839,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
           break;
         case PH_SAMPLE:
           if constexpr (WIDE) {
-            long long tp = p.prof ? clock64() : 0ll;
+            long long tp = (FQ3_WIDE_PROF && p.prof) ? clock64() : 0ll;
             sample_phase<WIDE>(ph, p, smem_raw, ep, i, frame_done);
             prof_acc(p, 5, tp);
           } else {

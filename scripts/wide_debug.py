@@ -3,6 +3,7 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+if os.environ.get("FQ3_VARIANT"): sys.path.insert(0, os.path.join(ROOT, "variants", os.environ["FQ3_VARIANT"]))  # A/B builds (scripts/build_variant.sh)
 from helpers import make_cfg, make_weights, make_engine, synth_prompt
 from qwen3_tts_cuda_graphs_b200.engine import SamplingPolicy, SubPolicy
 name, tl, pl = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])

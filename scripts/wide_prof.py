@@ -1,8 +1,9 @@
-"""Where a frame of the wide program goes (FQ3_PROF=<cta>): cycles per category of one CTA's thread 0, per frame."""
+"""Where a frame of the wide program goes (build with scripts/build_variant.sh wprof -DFQ3_WIDE_PROF=1; FQ3_VARIANT=wprof FQ3_PROF=<cta>): cycles per category of one CTA's thread 0, per frame."""
 import os, sys, ctypes as C
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+if os.environ.get("FQ3_VARIANT"): sys.path.insert(0, os.path.join(ROOT, "variants", os.environ["FQ3_VARIANT"]))  # A/B builds (scripts/build_variant.sh)
 from helpers import make_cfg, make_weights, make_engine, synth_prompt
 from qwen3_tts_cuda_graphs_b200.engine import SamplingPolicy, SubPolicy
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 16
