@@ -517,7 +517,7 @@ __device__ __forceinline__ uint32_t xrow_stride(int K) { return (uint32_t)K * 2u
 // share the launch.  A unit = (row, virtual warp); a warp keeps UNITS units (up to UNITS * kMaxJ 16-byte requests per lane) in flight.
 constexpr int kMaxJ = 6;  // quads per lane of a unit: K <= 6144
 template <int UNITS, int JC, bool ENTRY_BARRIER = false>
-__device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
+__device__ __forceinline__ void load_x_rows_impl(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
                                          int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red, long long* tprof = nullptr) {
   const int Kq = K >> 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -633,10 +633,17 @@ __device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, 
   if (tprof) prof_acc(p, 2, *tprof);
 }
 
+// out of line for the tuned single-stream kernel (a cold path there: predictor pass 0, prefill chunks); the wide kernel inlines it
+template <int UNITS, int JC>
+__device__ __noinline__ void load_x_rows(const LaunchParams& p, uint32_t flags, const LLWord* in, int ld, uint32_t gam, float eps,
+                                         int K, int M, uint32_t ep_in, int pidx, uint32_t xs, uint32_t red) {
+  load_x_rows_impl<UNITS, JC, false>(p, flags, in, ld, gam, eps, K, M, ep_in, pidx, xs, red, nullptr);
+}
+
 // Sum of the k-parts of one (stream, output word) in the order the single-stream path adds them (its shuffle tree): part g is
 // paired with part g + 8, the eight pairs are added as ((0+1)+(2+3))+((4+5)+(6+7)).  pa = this lane's word of part 0; parts
 // lie `stride` bytes apart; y0 / y1 enter as the lane's own part-0 sums.
-__device__ __noinline__ float2 tree_parts(float y0, float y1, uint32_t pa, uint32_t stride, int wpg) {
+__device__ __forceinline__ float2 tree_parts(float y0, float y1, uint32_t pa, uint32_t stride, int wpg) {
   float P0[8], P1[8];
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
@@ -1043,11 +1050,37 @@ __device__ __forceinline__ void gemv_phase_consume(const Ctx& c, const Phase& ph
 // g8 + 8 of a lane's fragments are different streams; a lane ends up with two output words).  Same arithmetic per stream as the
 // single-stream path (load_x_rows, tree_parts, the same accumulator chains), so a stream's tokens do not depend on its
 // neighbours.  What grows with the batch is the staging: every CTA polls M * K / 2 LL words per phase.
-__device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& ph, const LaunchParams& p, const KindDesc* kdp, const UnitDesc* udp,
-                                                     RingCur& cur, RingCur& gcur, uint32_t& gst, int pidx, uint32_t ep) {
+// (Inlined into the wide kernel: as a separate function its cursors lived in local memory, and with 227 KB of shared memory the
+// 28 KB of L1 that are left do not hold 384 threads' stack frames — every access to them was an L2 round trip, 14 % of the
+// samples of an ncu capture.  The kind / unit descriptors are read from shared memory field by field for the same reason.)
+struct KindRegs {  // the fields of a KindDesc, loaded with eight 16-byte shared-memory reads
+  const LLWord* in; int Kq, flags; LLWord* out; const LLWord* res; const uint32_t* bias; int ldout, ldres;
+  int g, grp0, wpg, gpr, spg, nch, ro_shift, n_stages; float eps, inv_k; int n_rounds, wpgrp, M, n_words, K, fast, ldin, norm;
+};
+__device__ __forceinline__ KindRegs load_kind(uint32_t kda) {
+  const uint4 k0 = lds128(kda), k1 = lds128(kda + 16u), k2 = lds128(kda + 32u), k3 = lds128(kda + 48u), k4 = lds128(kda + 64u),
+              k5 = lds128(kda + 80u), k6 = lds128(kda + 96u), k7 = lds128(kda + 112u);
+  KindRegs r;
+  r.in = reinterpret_cast<const LLWord*>(((unsigned long long)k0.y << 32) | k0.x); r.Kq = (int)k0.z; r.flags = (int)k0.w;
+  r.out = reinterpret_cast<LLWord*>(((unsigned long long)k1.y << 32) | k1.x);
+  r.res = reinterpret_cast<const LLWord*>(((unsigned long long)k1.w << 32) | k1.z);
+  r.bias = reinterpret_cast<const uint32_t*>(((unsigned long long)k2.y << 32) | k2.x); r.ldout = (int)k2.z; r.ldres = (int)k2.w;
+  r.g = (int)k3.x; r.grp0 = (int)k3.y; r.wpg = (int)k3.z; r.gpr = (int)k3.w;
+  r.spg = (int)k4.x; r.nch = (int)k4.y; r.ro_shift = (int)k4.z; r.n_stages = (int)k4.w;
+  r.eps = __uint_as_float(k5.x); r.inv_k = __uint_as_float(k5.y); r.n_rounds = (int)k5.z; r.wpgrp = (int)k5.w;
+  r.M = (int)k6.x; r.n_words = (int)k6.y; r.K = (int)k6.z; r.fast = (int)k6.w;
+  r.ldin = (int)k7.x; r.norm = (int)k7.y;
+  return r;
+}
+__device__ __forceinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& ph, const LaunchParams& p, RingCur& cur, RingCur& gcur, uint32_t& gst,
+                                                        int pidx, uint32_t ep) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const KindDesc kd = *kdp;
-  const UnitDesc ud = *udp;
+  const KindRegs kd = load_kind(c.kinds + (uint32_t)ph.kind * (uint32_t)sizeof(KindDesc));
+  struct { int wgrp, kp, ch0, ch1; } ud;
+  {
+    const uint4 u4 = lds128(c.units + (uint32_t)(ph.kind * kConsumerWarps + warp) * (uint32_t)sizeof(UnitDesc));
+    ud.wgrp = (int)u4.x; ud.kp = (int)u4.y; ud.ch0 = (int)u4.z; ud.ch1 = (int)u4.w;
+  }
   if (kd.g == 0) return;
   const uint32_t flags = (uint32_t)kd.flags;
   const int M = kd.M, K = kd.K, n_words = kd.n_words;
@@ -1087,9 +1120,9 @@ __device__ __noinline__ void gemv_phase_consume_wide(const Ctx& c, const Phase& 
   {
     long long* tpp = (FQ3_WIDE_PROF && p.prof) ? &tp : nullptr;
     // six 16-byte requests per lane in flight (twelve was measured: slower — every CTA asks L2 for the same lines)
-    if (K <= 1024) load_x_rows<6, 1, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
-    else if (K <= 2048) load_x_rows<3, 2, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
-    else load_x_rows<2, 3, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+    if (K <= 1024) load_x_rows_impl<6, 1, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+    else if (K <= 2048) load_x_rows_impl<3, 2, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
+    else load_x_rows_impl<2, 3, true>(p, flags, kd.in, kd.ldin, gsrc, kd.eps, K, M, ep_in, pidx, c.xs, c.red, tpp);
   }
   if (norm && lane == 0) mbar_arrive_a(gemptyb);
 
@@ -2825,7 +2858,7 @@ __global__ void __launch_bounds__(kThreads, 1) fq3_stream_kernel(const __grid_co
       const uint32_t ep = ep0 + (uint32_t)i + 1u;
       switch (ph.type) {
         case PH_GEMV:
-          if constexpr (WIDE) gemv_phase_consume_wide(c, ph, p, sm.kinds + ph.kind, sm.units + (int)ph.kind * kConsumerWarps + (tid >> 5), cur, gcur, gst, i, ep);
+          if constexpr (WIDE) gemv_phase_consume_wide(c, ph, p, cur, gcur, gst, i, ep);
           else gemv_phase_consume<PROF>(c, ph, p, cur, gcur, gst, i, ep);
           break;
         case PH_ATTN:
