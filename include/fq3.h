@@ -167,8 +167,8 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
 int fq3_assemble_prompt(fq3_engine* e, const void* tp_rows, const void* desc_i32x4, int n_rows, const void* spk_rows,
                         const void* ref_codes_i32, void* out_bf16, void* stream);
 /* Batched multi-request decode (no counterpart in the reference, which is hard-wired to bs = 1: talker_graph.py:46-47,
- * predictor_graph.py:70-71).  fq3_decode_frames with n_streams <= 4 runs the reference-shaped frame program (two predictor
- * rows per stream in pass 0).  Above four it runs the "wide" frame program in lock-step groups of up to
+ * predictor_graph.py:70-71).  fq3_decode_frames with one or two streams runs the reference-shaped frame program (two predictor
+ * rows per stream in pass 0; it can take four).  From three streams on it runs the "wide" frame program in lock-step groups of up to
  * fq3_lockstep_group(e) streams (16 where the model's rows fit the staging buffer), one launch per group and chunk: every
  * stream of a group rides the same weight sweep, a stream's tokens are the ones its single-stream run produces.
  * fq3_lockstep_group returns 4 when the wide program is not available for the model (1.7B dims: a row of the 6144-wide

@@ -958,7 +958,11 @@ int fq3_decode_frames(fq3_engine* e, int n_streams, int n_frames, const fq3_poli
   if (!e || !policy || !sub) return fail(FQ3_E_INVALID, "bad decode arguments");
   if (n_streams < 1 || n_streams > e->desc.max_streams) return fail(FQ3_E_INVALID, "n_streams out of range");
   if (n_frames <= 0) return 0;
-  if (2 * n_streams > kMaxRows) {
+  // The wide program takes over from three streams on where the model has one (measured at 0.6B dims, ms per frame-step,
+  // reference-shaped / wide: 2 streams 2.18 / 2.17, 3: 2.39 / 2.25, 4: 2.77 / 2.35; one stream 1.55 / 2.01).  FQ3_WIDE_FROM overrides.
+  int wide_from = 3;
+  if (const char* wf = getenv("FQ3_WIDE_FROM")) wide_from = std::max(1, atoi(wf));
+  if ((n_streams >= wide_from && e->wide_rows > kMaxRows / 2) || 2 * n_streams > kMaxRows) {
     // more than four streams: the wide frame program, in lock-step groups of up to wide_rows streams, one launch per group
     // (a group streams the weights once for all its streams; groups follow each other on the stream)
     // (1.7B dims: a 6144-column row is 12 KB and the ring must hold a six-stage group: three rows fit — not worth it next to the
