@@ -392,7 +392,7 @@ def _batch_vs_single(cfg, w, n_streams, n_frames, lens, max_seq_len=256):
     assert not bad, (bad, group)
 
 
-@pytest.mark.parametrize("n_streams", [5, 8, 16])
+@pytest.mark.parametrize("n_streams", [3, 4, 5, 8, 16])
 def test_wide_streams_match_single_stream_tiny(tiny, n_streams):
     cfg, w, _ = tiny
     _batch_vs_single(cfg, w, n_streams, 10, lens=[14, 9, 21, 5])
@@ -410,6 +410,14 @@ def test_wide_streams_match_single_stream_real_dims():
     cfg = make_cfg("0.6B-Base", 2, 2)
     w = make_weights(cfg, seed=0)
     _batch_vs_single(cfg, w, 16, 8, lens=[14, 60, 37, 101])
+
+
+def test_wide_streams_match_single_stream_full_depth():
+    """The real 0.6B stack at full depth (28 + 5 layers), 16 streams with contexts from 14 to 201 positions (one to five KV
+    splits): 8 frames of every stream equal its single-stream run."""
+    cfg = make_cfg("0.6B-Base")
+    w = make_weights(cfg, seed=0)
+    _batch_vs_single(cfg, w, 16, 8, lens=[14, 60, 137, 201])
 
 
 def test_normal_program_after_wide_program(tiny):
