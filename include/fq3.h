@@ -130,6 +130,12 @@ int fq3_prefill(fq3_engine* e, int stream_idx, const void* embeds, int T, int n_
  * sample exactly as fq3_prefill.  embeds_tail: bf16 [n_tail, H_t].  No left padding on this path. */
 int fq3_prefill_tail(fq3_engine* e, int stream_idx, const void* embeds_tail, int T, int n_tail, const fq3_policy* policy,
                      void* out_logits, void* stream);
+/* Prefill whose T rows were ALL computed elsewhere (dense tensor-core prefill: K/V of every layer already in the static cache):
+ * last_hidden = the last row's residual stream after the last layer (bf16 [H_t], before the final norm).  Runs the final
+ * RMSNorm + codec_head and the first-token sample (generate.py:119-134) and leaves the stream ready for fq3_decode_frames,
+ * exactly as fq3_prefill does. */
+int fq3_prefill_head(fq3_engine* e, int stream_idx, const void* last_hidden, int T, const fq3_policy* policy, void* out_logits,
+                     void* stream);
 /* Device address of one layer's static talker cache of one stream: bf16 [n_kv_heads][max_seq_len][head_dim];
  * which = 0 keys, 1 values (the StaticCache of talker_graph.py:43). */
 void* fq3_kv_cache_ptr(fq3_engine* e, int stream_idx, int layer, int which);

@@ -65,6 +65,7 @@ SYMBOLS = {
     "fq3_set_loop_state": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),
     "fq3_prefill": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.POINTER(Policy), _P, _P]),
     "fq3_prefill_tail": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.POINTER(Policy), _P, _P]),
+    "fq3_prefill_head": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(Policy), _P, _P]),
     "fq3_kv_cache_ptr": (_P, [_P, C.c_int, C.c_int, C.c_int]),
     "fq3_talker_step": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P]),
     "fq3_predictor_run": (C.c_int, [_P, C.c_int, _P, C.POINTER(SubPolicy), C.c_uint64, _P, _P, _P]),

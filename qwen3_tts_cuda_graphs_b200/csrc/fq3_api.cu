@@ -862,6 +862,42 @@ int fq3_prefill_tail(fq3_engine* e, int idx, const void* embeds_tail, int T, int
   return prefill_impl(e, idx, embeds_tail, T, T - n_tail, 0, policy, out_logits, stream);
 }
 
+int fq3_prefill_head(fq3_engine* e, int idx, const void* last_hidden, int T, const fq3_policy* policy, void* out_logits, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  if (!last_hidden || !policy || T <= 0) return fail(FQ3_E_INVALID, "bad prefill_head arguments");
+  if (T > e->tk.d.max_pos) {
+    char b[200];
+    snprintf(b, sizeof b, "Input is too long: prefill has %d tokens but max_seq_len=%d. Use shorter text or shorter "
+                          "reference audio.", T, e->tk.d.max_pos);
+    return fail(FQ3_E_TOO_LONG, b);
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ht = e->tk.d.hidden;
+  if (int r = reserve_epochs(e, 4, s)) return r;
+  fq3_reset_stream_kernel<<<1, 256, 0, s>>>(e->d_st + idx, e->tk.d.vocab);
+  fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, 0, 0, 2, 0, 0, 0);
+  e->launches += 2;
+  if (int r = pack_ll(e, BUF_TX, 0, last_hidden, Ht, 1, Ht, s)) return r;
+  LaunchParams p{};
+  fill_common(e, p);
+  // the last two phases of the prefill program: final norm + codec_head on the row, then the first-token sampler
+  p.prog = e->d_prefill + (e->n_prefill_ph - 2);
+  p.n_phases = 2;
+  p.mode = MODE_PREFILL;
+  p.n_rows = 1;
+  p.stream0 = idx;
+  p.pf_pos0 = T - 1; p.pf_n_pad = 0; p.pf_rope_delta = 0; p.pf_final = 1;
+  p.pol = to_policy(policy);
+  if (int r = launch(e, p, e->h_prefill.data() + (e->n_prefill_ph - 2), s)) return r;
+  fq3_set_state_kernel<<<1, 32, 0, s>>>(e->d_st + idx, 0, T, 0, 8, 0, 0, 0);
+  e->in_wpin[idx] = 0;
+  e->launches += 1;
+  CK(cudaGetLastError());
+  if (out_logits)
+    if (int r = unpack_f32(e, out_logits, e->tk.d.vocab, BUF_LOGITS, 0, 1, e->tk.d.vocab, s)) return r;
+  return 0;
+}
+
 void* fq3_kv_cache_ptr(fq3_engine* e, int idx, int layer, int which) {
   if (!e || idx < 0 || idx >= e->desc.max_streams || layer < 0 || layer >= e->rt[0].n_layers) return nullptr;
   const StackRt& S = e->rt[0];

@@ -180,8 +180,13 @@ class Engine:
                 from . import prefill_dense
                 self._dense = prefill_dense.make(self)
             if self._dense is not None and T - 1 >= self._dense.MIN_ROWS:
-                self._dense.run(idx, e, T - 1)
-                _lib.check(self.lib.fq3_prefill_tail(self.h, idx, e[T - 1:].data_ptr(), T, 1, C.byref(pol), _ptr(logits), _stream()))
+                if self._dense.full:
+                    self._dense.run(idx, e, T)
+                    last = self._dense.x_last[T - 1]
+                    _lib.check(self.lib.fq3_prefill_head(self.h, idx, last.data_ptr(), T, C.byref(pol), _ptr(logits), _stream()))
+                else:
+                    self._dense.run(idx, e, T - 1)
+                    _lib.check(self.lib.fq3_prefill_tail(self.h, idx, e[T - 1:].data_ptr(), T, 1, C.byref(pol), _ptr(logits), _stream()))
                 return logits
         _lib.check(self.lib.fq3_prefill(self.h, idx, e.data_ptr(), T, int(n_left_pad), C.byref(pol), _ptr(logits), _stream()))
         return logits

@@ -43,6 +43,10 @@ class DensePrefill:
         self.seen = {}
         self.graph_failed = set()
         self.use_graphs = os.environ.get("FQ3C_GRAPH", "1") != "0"
+        # full mode (default): ALL T rows go through ALL layers here and only the final norm + codec_head + first-token sample
+        # run in the decode kernel (fq3_prefill_head); FQ3_DENSE_FULL=0: rows [0, T-1) here, the last row through the decode
+        # kernel's 141 phases (fq3_prefill_tail)
+        self.full = os.environ.get("FQ3_DENSE_FULL", "1") != "0"
         a, t = engine.arena, self.cfg
         dev = engine.device
         L = t.num_hidden_layers
@@ -101,7 +105,7 @@ class DensePrefill:
             o.C2 = eng.lib.fq3_kv_cache_ptr(eng.h, 0, l, 1)
             o.ldc, o.col_mod = eng.max_seq_len, Q
             ops.append(o)
-            if l == L - 1:
+            if l == L - 1 and not self.full:
                 break  # the last row (decode-kernel path) only needs this layer's K/V of the earlier rows
             o = Op()
             o.kind, o.M, o.N = K_ATTN, cap, nq * d
@@ -120,6 +124,7 @@ class DensePrefill:
         self.graphs, self.seen = {}, {}
         if os.environ.get("FQ3C_SPLITK", "1") != "0":
             _codec.attach_splitk_workspace(ops, dev, self.keep)
+        self.x_last = x[cur]  # full mode: the residual stream after the last layer
         self.ops = ops
         self.kv_ops = [(i, o) for i, o in enumerate(ops) if o.kind == K_QKNORM_ROPE_KV]
         self.arr = (Op * len(ops))(*ops)

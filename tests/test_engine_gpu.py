@@ -510,9 +510,10 @@ def test_first_token_sampler_respects_suppression_and_top_k(tiny):
 # dense (tcgen05) prefill against the chunked decode-kernel prefill
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("T", [17, 40, 130, 240])
-def test_dense_prefill_matches_chunked_prefill(pair, T):
-    """Rows [0, T-1) through the tensor-core GEMMs + the last row through the decode kernel must give the logits and the first
-    token of the all-decode-kernel prefill, and the K/V it wrote must serve the next decode step (hidden state vs the oracle)."""
+def test_dense_prefill_matches_chunked_prefill(pair, T, monkeypatch):
+    """The tensor-core prefill must give the logits and the first token of the all-decode-kernel prefill, and the K/V it wrote
+    must serve the next decode step (hidden state vs the oracle) — in both of its forms: all T rows through all layers +
+    fq3_prefill_head (default), and rows [0, T-1) + the last row through the decode kernel (fq3_prefill_tail, FQ3_DENSE_FULL=0)."""
     cfg, w, eng, orc = pair
     if T >= eng.max_seq_len:
         pytest.skip("prompt longer than this fixture's cache")
@@ -520,22 +521,33 @@ def test_dense_prefill_matches_chunked_prefill(pair, T):
     pol = _sp(do_sample=False, repetition_penalty=1.0, min_new_tokens=2)
     xg = (0.05 * torch.randn(1, 1, cfg.talker.hidden_size, generator=torch.Generator().manual_seed(9))).to(torch.bfloat16)
     out = {}
-    for dense in (False, True):
+    for mode in ("chunked", "full", "tail"):
+        if mode != "chunked":
+            monkeypatch.setenv("FQ3_DENSE_FULL", "1" if mode == "full" else "0")
+            if eng._dense is not None:
+                eng._dense.close()
+            eng._dense, eng._dense_tried = None, False  # rebuilt under the new setting
         eng.set_text_conditioning(0, tth[0].cuda(), tpe.cuda())
-        lg = eng.prefill(0, tie[0].cuda(), 0, pol, want_logits=True, dense=dense)
+        lg = eng.prefill(0, tie[0].cuda(), 0, pol, want_logits=True, dense=(mode != "chunked"))
         st = eng.status(0)
         assert st.position == T and st.error == 0
+        if mode != "chunked":
+            assert eng._dense is not None and eng._dense.full == (mode == "full")
         h, _ = eng.talker_step(0, xg.cuda(), T)
         torch.cuda.synchronize()
-        out[dense] = (lg.cpu(), st.token, h.cpu())
+        out[mode] = (lg.cpu(), st.token, h.cpu())
     ref_logits, _, _ = orc.talker_prefill(tie, tam)
     ref_h = orc.talker_step(xg, T)
     scale = float(ref_logits.float().abs().max())
-    assert rel_err(out[True][0], out[False][0]) <= TOL
-    assert rel_err(out[True][0], ref_logits[0]) <= TOL
-    assert margin_argmax_agree(out[True][0], out[False][0], TOL * scale)
-    assert rel_err(out[True][2], ref_h) <= TOL, rel_err(out[True][2], ref_h)
-    assert rel_err(out[True][2], out[False][2]) <= TOL
+    for mode in ("full", "tail"):
+        assert rel_err(out[mode][0], out["chunked"][0]) <= TOL, mode
+        assert rel_err(out[mode][0], ref_logits[0]) <= TOL, mode
+        assert margin_argmax_agree(out[mode][0], out["chunked"][0], TOL * scale), mode
+        assert rel_err(out[mode][2], ref_h) <= TOL, (mode, rel_err(out[mode][2], ref_h))
+        assert rel_err(out[mode][2], out["chunked"][2]) <= TOL, mode
+    monkeypatch.delenv("FQ3_DENSE_FULL")
+    eng._dense.close()
+    eng._dense, eng._dense_tried = None, False
 
 
 # ------------------------------------------------------------------------------------------------
