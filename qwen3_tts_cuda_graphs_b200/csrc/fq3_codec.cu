@@ -2,12 +2,14 @@
 //
 // Activations are channels-last bf16 [time, channels]; every convolution is an implicit GEMM over (tap, c_in)
 // whose A rows are time-shifted views of the same buffer (no im2col), so causal padding is a bounds check.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, nothing links against libcuda)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "../../include/fq3_codec.h"
@@ -304,8 +306,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Split-K (splits > 1, short-and-wide problems that would leave most SMs idle): blockIdx.z takes a contiguous range of
 // k-blocks and stores its raw fp32 tile into the workspace [split][M][Nw]; fq3c_splitk_reduce_kernel adds the splits in
 // order and applies the fused epilogue.
-template <int MINB>  // CTAs per SM the register budget is planned for: 2 with three stages, 1 with six
-__global__ void __launch_bounds__(TTHREADS, MINB) fq3c_gemm_tc5_kernel(const fq3c_op o, const int BN, const int splits, const int Nw, const int NST) {
+// TMA = true: the operand tiles arrive by cp.async.bulk.tensor (SASS UTMALDG) — one elected thread asks for the A box (128 rows x 64
+// columns at row m0 + tap offset: rows outside the tensor, i.e. the causal padding, come back as zeros) and the B box (BN x 64) of a
+// k-block and both count their bytes on the stage's `full` mbarrier; SWIZZLE_128B writes exactly the layout described above.  Used
+// whenever a k-block cannot straddle two taps (one tap, or c_in a multiple of 64); the cp.async loaders stay for the rest.
+template <int MINB, bool TMA>  // MINB: CTAs per SM the register budget is planned for: 2 with three stages, 1 with six
+__global__ void __launch_bounds__(TTHREADS, MINB) fq3c_gemm_tc5_kernel(const fq3c_op o, const int BN, const int splits, const int Nw, const int NST,
+                                                                        const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ unsigned char tsmem_raw[];
   const uint32_t raw = smem_u32(tsmem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(TTHREADS, MINB) fq3c_gemm_tc5_kernel(const fq3
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
-      mbar_init(full + 8u * s, TLOADERS);
+      mbar_init(full + 8u * s, TMA ? 1 : TLOADERS);
       mbar_init(empty + 8u * s, 1);
     }
     mbar_init(done, 1);
@@ -347,7 +354,7 @@ __global__ void __launch_bounds__(TTHREADS, MINB) fq3c_gemm_tc5_kernel(const fq3
       for (int kt = 0; kt < KT; ++kt) {
         const int st = kt % NST;
         mbar_wait(full + 8u * st, (uint32_t)((kt / NST) & 1));
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) writes -> tensor core (async proxy) reads
+        if (!TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) writes -> tensor core (async proxy) reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a0 = a_smem + (uint32_t)st * T_A_BYTES, b0 = b_smem + (uint32_t)st * T_B_BYTES;
 #pragma unroll
@@ -371,6 +378,28 @@ __global__ void __launch_bounds__(TTHREADS, MINB) fq3c_gemm_tc5_kernel(const fq3
     // warps 0-3: A rows r0 + 16 i (i < 8), chunk c; warps 4-7: B rows likewise.  Eight lanes cover one 128-byte line of a row.
     const int lt = tid & 127, c = lt & 7, r0 = lt >> 3;
     const bool is_a = warp < 4;
+    if (TMA) {
+      if (tid == 0) {
+        const uint32_t tx = (uint32_t)(T_A_BYTES + BN * TK * 2);
+        for (int kt = 0; kt < KT; ++kt) {
+          const int st = kt % NST;
+          if (kt >= NST) mbar_wait(empty + 8u * st, (uint32_t)(((kt / NST) - 1) & 1));
+          const int k0 = (kt_begin + kt) * TK;
+          const int tap = k0 / o.cin, ci = k0 - tap * o.cin;
+          const int toff = (tap < 8) ? o.tap_off[tap] : 0;
+          const uint32_t fb = full + 8u * st;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tx) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                           a_smem + (uint32_t)st * T_A_BYTES),
+                       "l"(&tmA), "r"(ci), "r"(m0 + toff), "r"(fb)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                           b_smem + (uint32_t)st * T_B_BYTES),
+                       "l"(&tmB), "r"(k0), "r"(n0), "r"(fb)
+                       : "memory");
+        }
+      }
+    } else
     for (int kt = 0; kt < KT; ++kt) {
       const int st = kt % NST;
       if (kt >= NST) {  // one lane per warp polls: 256 spinning threads would swamp the shared-memory pipe the copies need
@@ -752,6 +781,35 @@ __global__ void fq3c_snake_kernel(const fq3c_op o) {
 
 int fail(const std::string& m) { g_err = m; return -1; }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+// bf16 matrix [rows, inner] with a row pitch of ld elements, boxes of box_rows x 64 columns, 128-byte swizzle, zeros outside
+bool make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn || !base || inner == 0 || rows == 0) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) return false;
+  const cuuint64_t dims[2] = {inner, rows};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 extern "C" {
@@ -773,8 +831,10 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
         if (use_tc5 < 0) {
           const char* e = getenv("FQ3C_TCGEN05");
           use_tc5 = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-          if (use_tc5 && (cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess ||
-                          cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(3)) != cudaSuccess))
+          if (use_tc5 && (cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess ||
+                          cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(3)) != cudaSuccess ||
+                          cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess ||
+                          cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(3)) != cudaSuccess))
             return fail("cannot reserve shared memory for the tcgen05 GEMM");
         }
         static int tc5_min_k = -1;
@@ -817,10 +877,22 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
           static int two_ctas = -1;
           if (two_ctas < 0) { const char* e2 = getenv("FQ3C_TWO_CTAS"); two_ctas = (e2 == nullptr || atoi(e2) != 0) ? 1 : 0; }
           const long n_ctas = (long)grid.x * grid.y * grid.z;
-          if (two_ctas && n_ctas >= 2 * 148 && KT <= 24)
-            fq3c_gemm_tc5_kernel<2><<<grid, TTHREADS, t_smem(3), s>>>(o, bn, splits, Nw, 3);
-          else
-            fq3c_gemm_tc5_kernel<1><<<grid, TTHREADS, T_SMEM, s>>>(o, bn, splits, Nw, TSTAGES);
+          // operand tiles by TMA tensor loads where a 64-column k-block stays inside one tap (FQ3C_TMA=0: cp.async loaders everywhere)
+          static int use_tma = -1;
+          if (use_tma < 0) { const char* e4 = getenv("FQ3C_TMA"); use_tma = (e4 == nullptr || atoi(e4) != 0) ? 1 : 0; }
+          CUtensorMap tmA, tmB;
+          memset(&tmA, 0, sizeof tmA); memset(&tmB, 0, sizeof tmB);
+          const bool tma = use_tma && (o.taps == 1 || o.cin % TK == 0) &&
+                           make_map(&tmA, o.A, (uint64_t)o.cin, (uint64_t)o.a_rows, (uint64_t)o.lda, TM) &&
+                           make_map(&tmB, o.B, (uint64_t)o.K, (uint64_t)o.N, (uint64_t)o.K, (uint32_t)bn);
+          const bool two = two_ctas && n_ctas >= 2 * 148 && KT <= 24;
+          if (tma) {
+            if (two) fq3c_gemm_tc5_kernel<2, true><<<grid, TTHREADS, t_smem(3), s>>>(o, bn, splits, Nw, 3, tmA, tmB);
+            else fq3c_gemm_tc5_kernel<1, true><<<grid, TTHREADS, T_SMEM, s>>>(o, bn, splits, Nw, TSTAGES, tmA, tmB);
+          } else {
+            if (two) fq3c_gemm_tc5_kernel<2, false><<<grid, TTHREADS, t_smem(3), s>>>(o, bn, splits, Nw, 3, tmA, tmB);
+            else fq3c_gemm_tc5_kernel<1, false><<<grid, TTHREADS, T_SMEM, s>>>(o, bn, splits, Nw, TSTAGES, tmA, tmB);
+          }
           if (splits > 1) {
             const long n = (long)(o.M - o.m_begin) * (Nw >> 3);
             fq3c_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o, splits, Nw);
