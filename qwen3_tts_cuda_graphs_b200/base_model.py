@@ -6,11 +6,14 @@ The reference dereferences a fixed set of attributes and helpers on that object 
 provides exactly that surface on top of the fq3 engine, so `FasterQwen3TTS` can keep the reference's call
 structure.  Everything dimension- or id-dependent comes from `TTSConfig`.
 
-What is NOT here ("next"): the ECAPA speaker encoder and the codec *encoder* that turn a
-reference wav into an x-vector / ref codes, the real BPE tokenizer and the safetensors loader.  Without weights
-or network they cannot be exercised; `create_voice_clone_prompt` derives a deterministic pseudo x-vector and
-pseudo ref codes from the audio bytes so that every code path downstream (prompt layout, ICL prefill length,
-ref-code prepending and proportional trimming) runs with the right shapes.
+Two ways in:
+* a checkpoint directory (`from_pretrained("/path/to/Qwen3-TTS-12Hz-0.6B-Base")`): `checkpoint.py` reads config + safetensors
+  into the arena and the codec decoder, `HFTokenizer` wraps the directory's BPE tokenizer files, `frontend.py` turns a
+  reference wav into an x-vector (ECAPA speaker encoder) and reference codes (Mimi-style codec encoder);
+* `synthetic://<preset>`: seeded random-init weights (BASELINE.json: no checkpoints offline), a hashing tokenizer, and
+  `create_voice_clone_prompt` derives a deterministic pseudo x-vector and pseudo ref codes from the audio bytes so that every
+  code path downstream (prompt layout, ICL prefill length, ref-code prepending and proportional trimming) runs with the
+  right shapes.
 """
 from __future__ import annotations
 
@@ -71,6 +74,43 @@ class SyntheticTokenizer:
     def instruct(self, text: str) -> List[int]:
         c = self.cfg
         return self.role("user") + self.encode(text) + [c.im_end_token_id, c.newline_token_id]
+
+
+class HFTokenizer:
+    """The checkpoint's own BPE tokenizer (`tokenizer.json`, or `vocab.json` + `merges.txt` through transformers).  The chat
+    templates are the strings whose token layout the reference's slicing assumes (`model.py:435,454,466,480,509`; SURVEY.md
+    §8c): the ids come out as 3 role ids + text + 5 (assistant) / 2 (ref, instruct) trailer ids."""
+
+    ASSISTANT = "<|im_start|>assistant\n{}<|im_end|>\n<|im_start|>assistant\n"
+    REF = "<|im_start|>assistant\n{}<|im_end|>\n"
+    INSTRUCT = "<|im_start|>user\n{}<|im_end|>\n"
+
+    def __init__(self, path: str):
+        tj = os.path.join(path, "tokenizer.json")
+        if os.path.exists(tj):
+            from tokenizers import Tokenizer
+
+            self._tok = Tokenizer.from_file(tj)
+            self._encode = lambda t: self._tok.encode(t, add_special_tokens=False).ids
+        elif os.path.exists(os.path.join(path, "vocab.json")):
+            from transformers import AutoTokenizer
+
+            self._tok = AutoTokenizer.from_pretrained(path)
+            self._encode = lambda t: self._tok(t, add_special_tokens=False)["input_ids"]
+        else:
+            raise FileNotFoundError(f"{path}: neither tokenizer.json nor vocab.json + merges.txt")
+
+    def encode(self, text: str) -> List[int]:
+        return list(self._encode(text))
+
+    def assistant(self, text: str) -> List[int]:
+        return self.encode(self.ASSISTANT.format(text))
+
+    def ref(self, text: str) -> List[int]:
+        return self.encode(self.REF.format(text))
+
+    def instruct(self, text: str) -> List[int]:
+        return self.encode(self.INSTRUCT.format(text))
 
 
 @dataclass
@@ -280,11 +320,12 @@ class InnerModel:
 class Qwen3TTSBaseModel:
     """`base_model` of the reference (qwen_tts.Qwen3TTSModel surface)."""
 
-    def __init__(self, cfg: TTSConfig, engine: Engine, arena: Arena, speech_tokenizer):
+    def __init__(self, cfg: TTSConfig, engine: Engine, arena: Arena, speech_tokenizer, tokenizer=None, frontend=None):
         self.cfg = cfg
         self.engine = engine
         self.arena = arena
-        self.tokenizer = SyntheticTokenizer(cfg)
+        self.tokenizer = tokenizer if tokenizer is not None else SyntheticTokenizer(cfg)
+        self.frontend = frontend  # frontend.VoiceFrontEnd of a real checkpoint; None = pseudo voice encoders (synthetic presets)
         self.device = engine.device
         self.model = InnerModel(cfg, Talker(engine, arena, cfg), speech_tokenizer)
 
@@ -293,38 +334,82 @@ class Qwen3TTSBaseModel:
     def from_pretrained(cls, model_name: str, device_map="cuda", torch_dtype=torch.bfloat16, attn_implementation="sdpa",
                         max_seq_len: int = 2048, max_streams: int = 1, seed: int = 0, weights=None, cfg: Optional[TTSConfig] = None,
                         allow_synthetic: bool = False):
-        """Synthetic presets only: "synthetic://0.6B-Base", "synthetic://1.7B-CustomVoice", or the bare preset names
-        ("0.6B-Base", "tiny", ...) build seeded RANDOM-INIT weights of that architecture (BASELINE.json: no checkpoints
-        offline), a hashing tokenizer and pseudo speaker / reference-code encoders.
+        """A checkpoint DIRECTORY (what a user of the reference passes, model.py:107) is loaded for real: config.json +
+        safetensors -> arena / codec decoder (`checkpoint.py`), the directory's BPE tokenizer, and — when the files carry them —
+        the speaker encoder and the codec encoder for reference audio (`frontend.py`).  A hub id ("Qwen/Qwen3-TTS-12Hz-0.6B-Base")
+        is resolved through the local Hugging Face cache only (no network here) and raises when it is not cached.
 
-        A Hugging Face id ("Qwen/Qwen3-TTS-12Hz-0.6B-Base") or a checkpoint directory is what a user of the reference passes
-        (model.py:107).  The safetensors loader, the BPE tokenizer and the speaker / codec encoders are SURVEY.md §8 row f3 and
-        are not built: such names raise instead of silently producing noise audio, unless `allow_synthetic=True` asks for the
-        random-init stand-in of the same architecture."""
+        "synthetic://0.6B-Base", "synthetic://1.7B-CustomVoice", or the bare preset names ("0.6B-Base", "tiny", ...) build
+        seeded RANDOM-INIT weights of that architecture (BASELINE.json: no checkpoints offline), a hashing tokenizer and pseudo
+        speaker / reference-code encoders; `allow_synthetic=True` asks for that stand-in under a real name instead of an
+        error.  The audio is noise then: only shapes and timing are meaningful."""
         from .codec import SpeechTokenizer
 
-        looks_real = os.path.isdir(model_name) or model_name.lower().startswith("qwen/") or model_name.lower().endswith(".safetensors")
-        if looks_real and not allow_synthetic and weights is None:
-            raise NotImplementedError(
-                f"{model_name!r} names a real checkpoint: loading safetensors weights, the tokenizer and the speaker / codec "
-                "encoders is not implemented (SURVEY.md §8 row f3).  Pass 'synthetic://<preset>' (or allow_synthetic=True) for "
-                "random-init weights of the same architecture — the audio is noise, only shapes and timing are meaningful."
-            )
-        if os.path.isdir(model_name):
-            raise NotImplementedError("loading a checkpoint directory is SURVEY.md §8 row f3 (next); use a named preset")
-        if weights is None:
-            logger.warning("fq3: %r -> seeded random-init weights, hashing tokenizer, pseudo voice encoders (synthetic stand-in)", model_name)
-        cfg = cfg or preset(model_name)
         dev = torch.device(device_map if isinstance(device_map, str) else "cuda")
         if dev.type != "cuda":
             raise ValueError("the fq3 engine needs a CUDA device")
         if torch_dtype not in (torch.bfloat16, "bfloat16"):
             raise ValueError("the fq3 engine computes in bf16 (fp32 accumulate); other dtypes are not implemented")
+        looks_real = os.path.isdir(model_name) or model_name.lower().startswith("qwen/") or model_name.lower().endswith(".safetensors")
+        if looks_real and not allow_synthetic and weights is None:
+            path = model_name if os.path.isdir(model_name) else cls._resolve_hub_id(model_name)
+            return cls._from_checkpoint(path, dev, max_seq_len, max_streams)
+        if weights is None:
+            logger.warning("fq3: %r -> seeded random-init weights, hashing tokenizer, pseudo voice encoders (synthetic stand-in)", model_name)
+        cfg = cfg or preset(os.path.basename(os.path.normpath(model_name)) if os.path.isdir(model_name) else model_name)
         w = weights if weights is not None else init_synthetic(cfg, seed=seed)
         arena = pack_arena(cfg, w, max_seq_len, dev)
         engine = Engine(cfg, arena, max_seq_len=max_seq_len, max_streams=max_streams, max_frames=max(4096, max_seq_len))
         tok = SpeechTokenizer.synthetic(cfg.codec, dev, seed=seed + 1)
         return cls(cfg, engine, arena, tok)
+
+    @staticmethod
+    def _resolve_hub_id(model_name: str) -> str:
+        try:
+            from huggingface_hub import snapshot_download
+
+            return snapshot_download(model_name, local_files_only=True)
+        except Exception as e:  # not cached / hub library absent: there is no network to fall back to
+            raise FileNotFoundError(
+                f"{model_name!r} is not in the local Hugging Face cache and this build never downloads: pass the checkpoint "
+                "directory, or 'synthetic://<preset>' for random-init weights of the same architecture"
+            ) from e
+
+    @classmethod
+    def _from_checkpoint(cls, path: str, dev, max_seq_len: int, max_streams: int):
+        """model.py:107-119 for a directory in the layout of checkpoint.py's docstring."""
+        import json
+
+        from . import checkpoint as ck
+        from . import frontend as fe
+        from .codec import CodecDecoder, SpeechTokenizer
+
+        cfg = ck.read_config(path)
+        w = ck.load_lm_weights(path, cfg)
+        arena = pack_arena(cfg, w, max_seq_len, dev)
+        del w
+        engine = Engine(cfg, arena, max_seq_len=max_seq_len, max_streams=max_streams, max_frames=max(4096, max_seq_len))
+        sdir = os.path.join(path, "speech_tokenizer")
+        if not os.path.isdir(sdir):
+            raise ck.CheckpointError(f"{path}: no speech_tokenizer/ directory (the 12 Hz codec decoder lives there)")
+        tok = SpeechTokenizer(CodecDecoder(cfg.codec, ck.load_codec_weights(sdir, cfg.codec), dev))
+        with open(os.path.join(path, "config.json")) as f:
+            raw = json.load(f)
+        frontend = None
+        spk_w = ck.load_prefixed(path, ("speaker_encoder.", "model.speaker_encoder."))
+        if spk_w:
+            scfg = dict(raw.get("speaker_encoder_config") or {})
+            scfg.setdefault("enc_dim", cfg.speaker_embed_dim or cfg.talker.hidden_size)
+            codec_enc = None
+            enc_w = ck.load_prefixed(sdir, ("encoder.", "model.encoder."))
+            if enc_w:
+                with open(os.path.join(sdir, "config.json")) as f:
+                    craw = json.load(f)
+                codec_enc = fe.CodecEncoder(craw.get("encoder_config") or {}, enc_w, cfg.talker.num_code_groups, dev)
+            frontend = fe.VoiceFrontEnd(fe.SpeakerEncoder(scfg, spk_w, dev), codec_enc)
+        elif cfg.tts_model_type == "base":
+            logger.warning("fq3: %s carries no speaker_encoder.* tensors; voice cloning falls back to pseudo voice encoders", path)
+        return cls(cfg, engine, arena, tok, tokenizer=HFTokenizer(path), frontend=frontend)
 
     # ---- text helpers (model.py:223-261) ---------------------------------------------------------
     def _build_assistant_text(self, text: str) -> str:
@@ -386,6 +471,10 @@ class Qwen3TTSBaseModel:
         return int.from_bytes(h, "little"), secs
 
     def create_voice_clone_prompt(self, ref_audio, ref_text: str = "", x_vector_only_mode: bool = False):
+        if self.frontend is not None:  # real checkpoint: speaker encoder + codec encoder (frontend.py)
+            spk = self.frontend.x_vector(ref_audio).to(torch.bfloat16).to(self.device)
+            code = None if x_vector_only_mode else self.frontend.ref_codes(ref_audio).to(self.device)
+            return [VoiceClonePromptItem(code, spk, x_vector_only_mode, not x_vector_only_mode, ref_text or None)]
         seed, secs = self._audio_fingerprint(ref_audio)
         g = torch.Generator().manual_seed(seed % (2**63 - 1))
         H = self.cfg.talker.hidden_size

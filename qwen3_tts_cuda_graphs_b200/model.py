@@ -88,13 +88,10 @@ class FasterQwen3TTS:
 
     # ---- prompt preparation ----------------------------------------------------------------------
     def _load_ref_audio_with_silence(self, ref_audio, silence_secs: float = 0.5) -> Tuple[np.ndarray, int]:
-        """model.py:185-200 (PCM16 wav via the stdlib; soundfile is not in this image)."""
-        with wave.open(str(ref_audio), "rb") as wf:
-            sr, nch, n = wf.getframerate(), wf.getnchannels(), wf.getnframes()
-            raw = wf.readframes(n)
-        audio = np.frombuffer(raw, dtype=np.int16).astype(np.float32) / 32768.0
-        if nch > 1:
-            audio = audio.reshape(-1, nch).mean(axis=1)
+        """model.py:185-200 (`sf.read` + mono mix-down; soundfile is not in this image: frontend.load_audio)."""
+        from .frontend import load_audio
+
+        audio, sr = load_audio(str(ref_audio))
         if silence_secs > 0:
             audio = np.concatenate([audio, np.zeros(int(silence_secs * sr), dtype=np.float32)])
         return audio, sr
@@ -117,8 +114,10 @@ class FasterQwen3TTS:
         else:
             try:
                 audio_in = self._load_ref_audio_with_silence(ref_audio, silence_secs=0.5 if append_silence else 0.0)
-            except (FileNotFoundError, wave.Error, EOFError):
-                audio_in = str(ref_audio)
+            except (FileNotFoundError, wave.Error, EOFError, ValueError):
+                if self.model.frontend is not None:
+                    raise
+                audio_in = str(ref_audio)  # synthetic presets fingerprint the path instead
             items = self.model.create_voice_clone_prompt(ref_audio=audio_in, ref_text=ref_text)
             vcp = self.model._prompt_items_to_voice_clone_prompt(items)
             rt = items[0].ref_text

@@ -54,3 +54,71 @@ def margin_argmax_agree(a: torch.Tensor, b: torch.Tensor, tol: float):
     if float(top2[0] - top2[1]) <= tol:
         return True
     return int(a.argmax()) == int(b.argmax())
+
+
+# ---- a checkpoint directory of the tiny preset in the layout qwen3_tts_cuda_graphs_b200/checkpoint.py reads ----
+TINY_WORDS = ["<unk>", "assistant", "user", "hello", "world", "short", "parity", "test", "the", "quick", "brown", "fox", "jumps",
+              "over", "lazy", "dog", "speak", "slowly", "calm", "voice", "reference", "clip", "says", "this", ".", ",", "!", "?"]
+
+TINY_SPEAKER_CFG = dict(mel_dim=128, enc_dim=256, enc_channels=(32, 32, 32, 32, 96), enc_kernel_sizes=(5, 3, 3, 3, 1),
+                        enc_dilations=(1, 2, 3, 4, 1), enc_attention_channels=16, enc_res2net_scale=4, enc_se_channels=16,
+                        sample_rate=24000)
+
+
+def tiny_mimi_config():
+    from transformers import MimiConfig
+
+    return MimiConfig(hidden_size=32, num_filters=8, num_hidden_layers=2, intermediate_size=64, num_attention_heads=4,
+                      num_key_value_heads=4, codebook_size=2048, codebook_dim=16, vector_quantization_hidden_dimension=16,
+                      num_quantizers=16, upsample_groups=32, sliding_window=16)
+
+
+def write_tiny_tokenizer(path, cfg):
+    """tokenizer.json whose chat-template pieces map to the tiny preset's special ids (config.preset("tiny"))."""
+    import os
+
+    from tokenizers import Regex, Tokenizer, models, normalizers, pre_tokenizers
+
+    vocab = {w: 16 + i for i, w in enumerate(TINY_WORDS)}
+    vocab["<unk>"] = 15
+    vocab.update({"<|im_start|>": cfg.im_start_token_id, "<|im_end|>": cfg.im_end_token_id, "assistant": cfg.assistant_token_id,
+                  "user": cfg.user_token_id, "\n": cfg.newline_token_id})
+    used = set(vocab.values())
+    vocab.update({f"<reserved_{i}>": i for i in range(max(used) + 1) if i not in used})  # a dense id range, like a real vocab.json
+    tok = Tokenizer(models.WordLevel(vocab, unk_token="<unk>"))
+    tok.normalizer = normalizers.Lowercase()
+    tok.pre_tokenizer = pre_tokenizers.Sequence([
+        pre_tokenizers.Split(Regex(r"<\|im_start\|>|<\|im_end\|>|\n|[.,!?]"), behavior="isolated"),
+        pre_tokenizers.Split(Regex(r" +"), behavior="removed"),
+    ])
+    os.makedirs(path, exist_ok=True)
+    tok.save(os.path.join(path, "tokenizer.json"))
+
+
+def write_tiny_checkpoint(path, cfg=None, seed=0, shards=1, mimi_codebooks=False, with_frontend=True):
+    """Returns (cfg, lm weights, codec weights, speaker-encoder weights | None, MimiModel | None)."""
+    from qwen3_tts_cuda_graphs_b200 import checkpoint as ck
+    from qwen3_tts_cuda_graphs_b200 import frontend as fe
+    from qwen3_tts_cuda_graphs_b200.codec import init_codec_synthetic
+
+    cfg = cfg or preset("tiny-Base")
+    lm = init_synthetic(cfg, seed=seed, norm_jitter=0.1)
+    codec = init_codec_synthetic(cfg.codec, seed=seed + 1)
+    extra = codec_extra = spk = mimi = None
+    extra_cfg, codec_extra_cfg = {}, {}
+    if with_frontend:
+        spk = fe.init_speaker_encoder_synthetic(TINY_SPEAKER_CFG, seed=seed + 2)
+        extra = {"speaker_encoder." + k: v for k, v in spk.items()}
+        extra_cfg["speaker_encoder_config"] = {k: (list(v) if isinstance(v, tuple) else v) for k, v in TINY_SPEAKER_CFG.items()}
+        from transformers import MimiModel
+
+        torch.manual_seed(seed + 3)
+        mc = tiny_mimi_config()
+        mimi = MimiModel(mc).eval()
+        keep = ("encoder.", "encoder_transformer.", "downsample.", "quantizer.")
+        codec_extra = {"encoder." + k: v.detach().clone() for k, v in mimi.state_dict().items() if k.startswith(keep)}
+        codec_extra_cfg["encoder_config"] = mc.to_dict()
+    ck.export_checkpoint(path, cfg, lm, codec, extra=extra, codec_extra=codec_extra, shards=shards, mimi_codebooks=mimi_codebooks,
+                         extra_config=extra_cfg, codec_extra_config=codec_extra_cfg)
+    write_tiny_tokenizer(path, cfg)
+    return cfg, lm, codec, spk, mimi
