@@ -80,7 +80,7 @@ typedef struct fq3_subpolicy {
 /* Host-visible per-stream status after fq3_decode_frames (streaming.py:157-188 needs steps + is_final). */
 typedef struct fq3_status {
   int32_t n_frames;  /* frames appended so far for this utterance */
-  int32_t done;      /* 0 running, 1 EOS sampled (generate.py:150), 2 static cache full (generate.py:175-177) */
+  int32_t done;      /* 0 running, 1 EOS sampled (generate.py:150), 2 static cache full (generate.py:175-177), 3 retired by the host */
   int32_t position;  /* next KV position */
   int32_t gen_step;  /* generate.py:199 */
   int32_t token;     /* first-codebook id that will open the next frame */
@@ -103,6 +103,11 @@ int64_t fq3_launch_count(const fq3_engine* e);
 /* ---- per-utterance set-up ------------------------------------------------------------------ */
 /* TalkerGraph.reset (talker_graph.py:149-151): forget KV, history, frame count of one stream. */
 int fq3_reset_stream(fq3_engine* e, int stream_idx, void* stream);
+/* Serving (no counterpart in the reference, whose servers hold one lock around a bs = 1 model: examples/openai_server.py:71,181):
+ * take one stream out of the lock-step frame loop — it idles (status.done = 3) in every later fq3_decode_frames until it is
+ * reset and prefilled again.  A scheduler retires the slot of a finished / cancelled / length-capped request so that the
+ * other streams of the group keep decoding, and parks never-used slots the same way. */
+int fq3_retire_stream(fq3_engine* e, int stream_idx, void* stream);
 /* TalkerGraph.set_generation_state (talker_graph.py:172-196): left pads and rope delta of one stream. */
 int fq3_set_generation_state(fq3_engine* e, int stream_idx, int n_left_pad, int rope_delta, void* stream);
 /* trailing_text_hiddens / tts_pad_embed of generate.py:168-171; copied into engine-owned buffers.

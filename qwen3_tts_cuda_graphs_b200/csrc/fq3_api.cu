@@ -736,6 +736,14 @@ int fq3_reset_stream(fq3_engine* e, int idx, void* stream) {
   return 0;
 }
 
+int fq3_retire_stream(fq3_engine* e, int idx, void* stream) {
+  if (int r = check_stream(e, idx)) return r;
+  fq3_set_state_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e->d_st + idx, 0, 0, 0, 32, 0, 0, 0);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int fq3_set_generation_state(fq3_engine* e, int idx, int n_left_pad, int rope_delta, void* stream) {
   if (int r = check_stream(e, idx)) return r;
   fq3_set_state_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e->d_st + idx, 0, 0, 0, 2, n_left_pad, rope_delta, 0);

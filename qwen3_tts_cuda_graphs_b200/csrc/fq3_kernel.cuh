@@ -3033,6 +3033,7 @@ __global__ void fq3_set_state_kernel(StreamState* st, int token, int position, i
     if (set_mask & 4) st->n_trailing = n_trailing;
     if (set_mask & 8) { st->position = position; st->gen_step = gen_step; }
     if (set_mask & 16) st->done = 0;
+    if (set_mask & 32) st->done = 3;  // retired by the host (fq3_retire_stream): idles in lock-step launches until reset
   }
 }
 

@@ -143,6 +143,10 @@ class Engine:
     def reset_stream(self, idx: int = 0):
         _lib.check(self.lib.fq3_reset_stream(self.h, idx, _stream()))
 
+    def retire_stream(self, idx: int):
+        """Take a slot out of the lock-step frame loop until its next reset + prefill (fq3.h: fq3_retire_stream)."""
+        _lib.check(self.lib.fq3_retire_stream(self.h, idx, _stream()))
+
     def set_generation_state(self, idx: int, n_left_pad: int, rope_delta: int):
         _lib.check(self.lib.fq3_set_generation_state(self.h, idx, int(n_left_pad), int(rope_delta), _stream()))
 

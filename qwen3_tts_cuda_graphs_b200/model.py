@@ -26,6 +26,45 @@ from .talker_graph import TalkerGraph
 logger = logging.getLogger(__name__)
 
 
+class WindowedDecode:
+    """The hybrid streaming decode policy of model.py:737-826 for ONE utterance: accumulate and re-decode everything until 25
+    frames exist (that first decode also calibrates samples per frame), then decode a sliding window of 25 context frames +
+    the new chunk and keep the new chunk's samples.  `push(chunk)` returns the new samples; the context part of a window is
+    decoded tail-only (`skip_samples`, codec.CodecDecoder.decode).  Used by `_stream_audio` and by serving.BatchScheduler."""
+
+    def __init__(self, tok, ref_codes, chunk_size: int, context_frames: int = 25):
+        self.tok, self.ref_codes = tok, ref_codes
+        self.context_frames = context_frames
+        self.min_cal = max(context_frames, chunk_size)
+        self.all_codes, self.prev_len, self.spf = [], 0, None
+
+    def push(self, chunk: torch.Tensor):
+        tok, ref_codes = self.tok, self.ref_codes
+        self.all_codes.append(chunk)
+        n_new = chunk.shape[0]
+        flat = torch.cat(self.all_codes, dim=0)
+        n_total = flat.shape[0]
+        if self.spf is None:
+            codes_in = flat if ref_codes is None else torch.cat([ref_codes.to(flat.device), flat], dim=0)
+            audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0)})
+            audio = audio_list[0].flatten()
+            if ref_codes is not None:
+                audio = audio[int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * len(audio)):]
+            new_audio = audio[self.prev_len:]
+            self.prev_len = len(audio)
+            if n_total >= self.min_cal:
+                self.spf = len(audio) / n_total
+            return new_audio, sr
+        start = max(0, n_total - n_new - self.context_frames)
+        window = flat[start:]
+        n_ctx = window.shape[0] - n_new
+        cut = int(round(n_ctx * self.spf)) if n_ctx > 0 else 0
+        # the context frames are decoded for their state only: tell the decoder which samples will be thrown away
+        audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0), "skip_samples": cut})
+        audio = audio_list[0].flatten()
+        return (audio[cut:] if n_ctx > 0 else audio), sr
+
+
 class FasterQwen3TTS:
     def __init__(self, base_model, predictor_graph, talker_graph, device: str = "cuda",
                  dtype: torch.dtype = torch.bfloat16, max_seq_len: int = 2048):
@@ -388,10 +427,8 @@ class FasterQwen3TTS:
         """Hybrid streaming decode policy of model.py:737-826 (accumulate until 25 frames, then a 25-frame
         left-context sliding window).  to_host=False keeps each chunk as a device tensor (bench.py's
         device-resident leg); the public generators always yield host numpy like the reference."""
-        context_frames = 25
-        min_cal = max(context_frames, chunk_size)
-        all_codes, prev_len, spf = [], 0, None
         tok = m.speech_tokenizer
+        window = WindowedDecode(tok, ref_codes, chunk_size)
         # Opt-in (FQ3_STATEFUL_CODEC=1): stateful incremental decode instead of the windowed re-decode — every chunk costs its own
         # frames only and the audio equals the full non-streaming decode (codec.CodecStream).  The windowed policy below stays
         # the default because it is the reference's.
@@ -418,29 +455,7 @@ class FasterQwen3TTS:
                         first = False
                     new_audio, sr = cstream.decode(chunk), tok.sample_rate
                 else:
-                    all_codes.append(chunk)
-                    n_new = chunk.shape[0]
-                    flat = torch.cat(all_codes, dim=0)
-                    n_total = flat.shape[0]
-                    if spf is None:
-                        codes_in = flat if ref_codes is None else torch.cat([ref_codes.to(flat.device), flat], dim=0)
-                        audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0)})
-                        audio = audio_list[0].flatten()
-                        if ref_codes is not None:
-                            audio = audio[int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * len(audio)):]
-                        new_audio = audio[prev_len:]
-                        prev_len = len(audio)
-                        if n_total >= min_cal:
-                            spf = len(audio) / n_total
-                    else:
-                        start = max(0, n_total - n_new - context_frames)
-                        window = flat[start:]
-                        n_ctx = window.shape[0] - n_new
-                        cut = int(round(n_ctx * spf)) if n_ctx > 0 else 0
-                        # the context frames are decoded for their state only: tell the decoder which samples will be thrown away
-                        audio_list, sr = tok.decode({"audio_codes": window.unsqueeze(0), "skip_samples": cut})
-                        audio = audio_list[0].flatten()
-                        new_audio = audio[cut:] if n_ctx > 0 else audio
+                    new_audio, sr = window.push(chunk)
             if ready is not None:
                 self._codec_stream.synchronize()
             yield (self._to_numpy(new_audio) if to_host else new_audio), sr, timing

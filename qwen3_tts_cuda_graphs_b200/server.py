@@ -1,0 +1,283 @@
+"""HTTP front of the serving layer: the reference's OpenAI-compatible endpoint
+(`examples/openai_server.py:219-265`: POST /v1/audio/speech, GET /health; wav / pcm streamed chunk by chunk with an
+unknown-length WAV header) and the demo's server-sent-events protocol (`demo/server.py:332-541`: POST /generate/stream ->
+`data: {"type": "queued" | "chunk" | "done" | "error", ...}`), on top of `serving.BatchScheduler` instead of a global lock:
+concurrent requests decode in lock-step on the same weight sweep, one scheduler per GPU, requests go to the least-loaded one
+(replicas only — DESIGN.md §7).
+
+    python -m qwen3_tts_cuda_graphs_b200.server --model <dir | synthetic://0.6B-Base> --ref-audio voice.wav --ref-text "..." \
+        [--voices voices.json] [--gpus 8] [--max-concurrent 16] [--port 8000]
+
+`create_app(backends, voices, default_voice)` takes anything with the scheduler's `submit(TTSRequest) -> handle` surface, so the
+HTTP layer is tested on CPU with a stand-in backend (`tests/test_server_cpu.py`).
+"""
+from __future__ import annotations
+
+import argparse
+import asyncio
+import base64
+import io
+import json
+import logging
+import os
+import struct
+import sys
+import threading
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+from pydantic import BaseModel
+
+from .serving import TTSRequest
+
+logger = logging.getLogger(__name__)
+
+CONTENT_TYPES = {"wav": "audio/wav", "pcm": "audio/pcm"}
+
+
+# ---- audio helpers (examples/openai_server.py:88-118) ------------------------------------------
+def to_pcm16(pcm: np.ndarray) -> bytes:
+    return np.clip(np.asarray(pcm, dtype=np.float32) * 32768.0, -32768, 32767).astype("<i2").tobytes()
+
+
+def wav_header(sample_rate: int, data_len: int = 0xFFFFFFFF) -> bytes:
+    """16-bit mono WAV header; data_len 0xFFFFFFFF = streamed, length unknown."""
+    riff = 0xFFFFFFFF if data_len == 0xFFFFFFFF else 36 + data_len
+    return (b"RIFF" + struct.pack("<I", riff) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, sample_rate, sample_rate * 2, 2, 16)
+            + b"data" + struct.pack("<I", data_len))
+
+
+def to_wav_bytes(pcm: np.ndarray, sample_rate: int) -> bytes:
+    raw = to_pcm16(pcm)
+    return wav_header(sample_rate, len(raw)) + raw
+
+
+class SpeechRequest(BaseModel):  # examples/openai_server.py:78-83
+    model: str = "tts-1"
+    input: str
+    voice: str = "alloy"
+    response_format: str = "wav"
+    speed: float = 1.0  # accepted, not applied (as in the reference)
+
+
+class Dispatcher:
+    """Least-loaded choice among per-GPU backends (request-parallel replicas; no exchange between them)."""
+
+    def __init__(self, backends: List[object]):
+        if not backends:
+            raise ValueError("no backend")
+        self.backends = list(backends)
+        self.in_flight = [0] * len(self.backends)
+        self._lock = threading.Lock()
+
+    def submit(self, req: TTSRequest):
+        with self._lock:
+            i = min(range(len(self.backends)), key=lambda j: self.in_flight[j])
+            self.in_flight[i] += 1
+        try:
+            h = self.backends[i].submit(req)
+        except Exception:
+            self.release(i)
+            raise
+        h._backend_index = i
+        return h
+
+    def release(self, i: int):
+        with self._lock:
+            self.in_flight[i] = max(0, self.in_flight[i] - 1)
+
+
+def _request_for(voice_cfg: dict, text: str, overrides: Optional[dict] = None) -> TTSRequest:
+    """A voices.json entry -> request.  Entries: {"ref_audio", "ref_text", "language"} (voice clone, as in the reference),
+    {"speaker", "language", "instruct"} (custom voice) or {"instruct", "language"} (voice design)."""
+    kw = dict(text=text, language=voice_cfg.get("language", "Auto"))
+    if voice_cfg.get("speaker"):
+        kw.update(kind="custom_voice", speaker=voice_cfg["speaker"], instruct=voice_cfg.get("instruct") or None)
+    elif voice_cfg.get("ref_audio"):
+        kw.update(kind="voice_clone", ref_audio=voice_cfg["ref_audio"], ref_text=voice_cfg.get("ref_text", ""),
+                  xvec_only=bool(voice_cfg.get("xvec_only", True)), non_streaming_mode=False)
+    elif voice_cfg.get("instruct"):
+        kw.update(kind="voice_design", instruct=voice_cfg["instruct"])
+    else:
+        raise ValueError("a voice needs ref_audio, speaker or instruct")
+    for k in ("max_new_tokens", "temperature", "top_k", "top_p", "repetition_penalty", "do_sample"):
+        if k in voice_cfg:
+            kw[k] = voice_cfg[k]
+    kw.update(overrides or {})
+    return TTSRequest(**kw)
+
+
+def create_app(backends: List[object], voices: Dict[str, dict], default_voice: Optional[str] = None, sample_rate: int = 24000):
+    from fastapi import FastAPI, Form, HTTPException
+    from fastapi.responses import StreamingResponse
+
+    app = FastAPI(title="qwen3-tts B200 engine: OpenAI-compatible API")
+    disp = Dispatcher(backends)
+    app.state.dispatcher = disp
+
+    def resolve_voice(name: str) -> dict:  # examples/openai_server.py:146-165
+        if name in voices:
+            return voices[name]
+        if default_voice and default_voice in voices:
+            logger.warning("Voice %r not configured; falling back to default voice %r", name, default_voice)
+            return voices[default_voice]
+        raise HTTPException(status_code=400, detail=f"Voice {name!r} is not configured. Available voices: {list(voices.keys())}")
+
+    async def chunks_of(handle):
+        """Pull a handle's chunks without blocking the event loop; releases the backend slot when the stream ends."""
+        loop = asyncio.get_event_loop()
+        it = iter(handle)
+        try:
+            while True:
+                item = await loop.run_in_executor(None, lambda: next(it, None))
+                if item is None:
+                    return
+                yield item
+        finally:
+            if getattr(handle, "finish_reason", None) is None and hasattr(handle, "cancel"):
+                handle.cancel()  # client went away mid-stream: free the slot at the next chunk boundary
+            disp.release(getattr(handle, "_backend_index", 0))
+
+    @app.get("/health")
+    async def health():
+        return {"status": "ok", "model_loaded": True, "backends": len(disp.backends), "in_flight": list(disp.in_flight)}
+
+    @app.get("/v1/voices")
+    async def list_voices():
+        return {"voices": sorted(voices), "default": default_voice}
+
+    @app.post("/v1/audio/speech")
+    async def create_speech(req: SpeechRequest):
+        if not req.input.strip():
+            raise HTTPException(status_code=400, detail="'input' text is empty")
+        voice_cfg = resolve_voice(req.voice)
+        fmt = req.response_format.lower()
+        if fmt == "mp3":
+            raise HTTPException(status_code=400, detail="response_format='mp3' needs pydub + ffmpeg, which this build does not ship. Use: wav, pcm")
+        if fmt not in CONTENT_TYPES:
+            raise HTTPException(status_code=400, detail=f"response_format {fmt!r} not supported. Use: wav, pcm")
+        try:
+            handle = disp.submit(_request_for(voice_cfg, req.input))
+        except ValueError as e:
+            raise HTTPException(status_code=400, detail=str(e))
+
+        async def audio_stream():
+            if fmt == "wav":
+                yield wav_header(sample_rate)
+            async for audio, _sr, _info in chunks_of(handle):
+                yield to_pcm16(audio)
+
+        return StreamingResponse(audio_stream(), media_type=CONTENT_TYPES[fmt])
+
+    @app.post("/generate/stream")
+    async def generate_stream(text: str = Form(...), language: str = Form("English"), mode: str = Form("voice_clone"),
+                              ref_text: str = Form(""), speaker: str = Form(""), instruct: str = Form(""),
+                              xvec_only: bool = Form(True), temperature: float = Form(0.9), top_k: int = Form(50),
+                              repetition_penalty: float = Form(1.05), voice: str = Form("")):
+        """The demo's SSE protocol (demo/server.py:332-541); reference audio comes from a configured voice instead of an upload."""
+        if not text.strip():
+            raise HTTPException(status_code=400, detail="text is empty")
+        over = dict(language=language, temperature=temperature, top_k=top_k, repetition_penalty=repetition_penalty)
+        try:
+            if mode == "voice_clone":
+                cfg = dict(resolve_voice(voice or (default_voice or "")))
+                if ref_text:
+                    cfg["ref_text"] = ref_text
+                cfg["xvec_only"] = xvec_only
+                req = _request_for(cfg, text, over)
+            elif mode == "custom":
+                req = _request_for({"speaker": speaker, "instruct": instruct}, text, over)
+            elif mode == "voice_design":
+                req = _request_for({"instruct": instruct}, text, over)
+            else:
+                raise ValueError(f"unknown mode {mode!r}")
+        except ValueError as e:
+            raise HTTPException(status_code=400, detail=str(e))
+        ahead = sum(disp.in_flight)
+        handle = disp.submit(req)
+        t0 = time.perf_counter()
+
+        async def sse():
+            yield f"data: {json.dumps({'type': 'queued', 'position': ahead})}\n\n"
+            total_audio_s, ttfa_ms = 0.0, None
+            try:
+                async for audio, sr, _info in chunks_of(handle):
+                    now_ms = (time.perf_counter() - t0) * 1000
+                    ttfa_ms = now_ms if ttfa_ms is None else ttfa_ms
+                    total_audio_s += len(audio) / sr
+                    payload = {"type": "chunk", "audio_b64": base64.b64encode(to_wav_bytes(audio, sr)).decode(), "sample_rate": sr,
+                               "ttfa_ms": round(ttfa_ms), "rtf": round(total_audio_s / (now_ms / 1000), 3) if now_ms > 0 else 0.0,
+                               "total_audio_s": round(total_audio_s, 3), "elapsed_ms": round(now_ms)}
+                    yield f"data: {json.dumps(payload)}\n\n"
+                total_ms = (time.perf_counter() - t0) * 1000
+                done = {"type": "done", "ttfa_ms": round(ttfa_ms or 0), "total_audio_s": round(total_audio_s, 3),
+                        "rtf": round(total_audio_s / (total_ms / 1000), 3) if total_ms > 0 else 0.0, "total_ms": round(total_ms)}
+                yield f"data: {json.dumps(done)}\n\n"
+            except Exception as e:  # generation errors travel in-band, like the demo's
+                yield f"data: {json.dumps({'type': 'error', 'message': str(e)})}\n\n"
+
+        return StreamingResponse(sse(), media_type="text/event-stream")
+
+    return app
+
+
+# ---- entry point (examples/openai_server.py:273-356) -------------------------------------------
+def load_voices(args) -> (Dict[str, dict], str):
+    if args.voices:
+        with open(args.voices) as f:
+            voices = json.load(f)
+        return voices, next(iter(voices))
+    if args.ref_audio:
+        return {"default": {"ref_audio": args.ref_audio, "ref_text": args.ref_text, "language": args.language}}, "default"
+    if args.speaker:
+        return {"default": {"speaker": args.speaker, "language": args.language}}, "default"
+    print("ERROR: provide --ref-audio <file>, --speaker <id> or --voices <config.json>", file=sys.stderr)
+    sys.exit(1)
+
+
+def build_backends(model: str, gpus: int, max_concurrent: int, chunk_frames: int, max_seq_len: int = 2048):
+    """One model replica + scheduler per GPU."""
+    import torch
+
+    from .model import FasterQwen3TTS
+    from .serving import BatchScheduler
+
+    out = []
+    for g in range(gpus):
+        tts = FasterQwen3TTS.from_pretrained(model, device=f"cuda:{g}", dtype=torch.bfloat16, max_seq_len=max_seq_len,
+                                             max_streams=max_concurrent)
+        out.append(BatchScheduler(tts, chunk_frames=chunk_frames, max_concurrent=max_concurrent).start())
+    return out
+
+
+def main(argv=None):
+    p = argparse.ArgumentParser(description="OpenAI-compatible TTS server on the fq3 engine", formatter_class=argparse.RawDescriptionHelpFormatter)
+    p.add_argument("--model", default=os.environ.get("QWEN_TTS_MODEL", "synthetic://0.6B-Base"), help="checkpoint directory, cached hub id, or synthetic://<preset>")
+    p.add_argument("--voices", default=os.environ.get("QWEN_TTS_VOICES"), metavar="FILE")
+    p.add_argument("--ref-audio", default=os.environ.get("QWEN_TTS_REF_AUDIO"), metavar="FILE")
+    p.add_argument("--ref-text", default=os.environ.get("QWEN_TTS_REF_TEXT", ""))
+    p.add_argument("--speaker", default=None, help="CustomVoice speaker id when --voices is not used")
+    p.add_argument("--language", default=os.environ.get("QWEN_TTS_LANGUAGE", "Auto"))
+    p.add_argument("--host", default="0.0.0.0")
+    p.add_argument("--port", type=int, default=8000)
+    p.add_argument("--gpus", type=int, default=1, help="replicas, one per GPU")
+    p.add_argument("--max-concurrent", type=int, default=16, help="lock-step streams per GPU")
+    p.add_argument("--chunk-frames", type=int, default=8, help="frames per launch = streaming granularity (8 frames = 0.64 s)")
+    args = p.parse_args(argv)
+    logging.basicConfig(level=logging.INFO)
+    voices, default_voice = load_voices(args)
+    import uvicorn
+
+    backends = build_backends(args.model, args.gpus, args.max_concurrent, args.chunk_frames)
+    app = create_app(backends, voices, default_voice, sample_rate=backends[0].tts.sample_rate)
+    logger.info("Server listening on http://%s:%d (%d GPU(s), %d streams each)", args.host, args.port, args.gpus, args.max_concurrent)
+    try:
+        uvicorn.run(app, host=args.host, port=args.port)
+    finally:
+        for b in backends:
+            b.stop()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,324 @@
+"""Continuous-batching scheduler over the lock-step frame loop ("serving layer ... on top of a
+continuous-batching scheduler").
+
+The reference's servers hold ONE lock around a bs = 1 model (`examples/openai_server.py:71,181`, `demo/server.py:167,517`):
+requests queue behind each other and a 10-second utterance blocks everyone for 2–3 seconds.  This engine decodes up to
+`fq3_lockstep_group` (16) utterances per weight sweep and more in groups, so the serving loop is:
+
+    admit   waiting requests take free stream slots: prompt build -> reset -> prefill (one slot at a time, between two chunks)
+    launch  ONE `fq3_decode_frames(high-water slot count, chunk_frames)` for every running utterance
+    emit    while that launch runs, the previous chunk's codes go through the codec on a side stream (the decode grid leaves
+            20 SMs free) and out to each request's queue
+    retire  a slot whose utterance hit EOS / its length cap / the cache bound / was cancelled is parked with
+            `fq3_retire_stream` so the others keep going, and is free for the next admit
+
+A request joins at the next chunk boundary (≤ chunk_frames frame-steps away) and leaves without stopping anyone.  A stream's
+tokens do not depend on its neighbours (batch-invariant arithmetic): under greedy decoding every request's
+codes equal its single-stream run (`tests/test_serving_gpu.py`).  The sampling policy is a launch argument, so requests are
+batched with requests of the same policy; a request with another policy waits for the running cohort to drain.
+
+All engine calls happen on the scheduler's own thread (the engine, like the reference's model, is not thread-safe).
+"""
+from __future__ import annotations
+
+import logging
+import queue
+import threading
+import time
+from dataclasses import dataclass, field
+from typing import Dict, Iterator, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .engine import SamplingPolicy
+
+logger = logging.getLogger(__name__)
+
+_DONE = object()
+
+
+@dataclass
+class TTSRequest:
+    """One utterance.  `kind`: "voice_clone" (ref_audio / ref_text / xvec_only), "custom_voice" (speaker), "voice_design"
+    (instruct) — the three generate_* families of the reference API (model.py:556, :829, :1004)."""
+
+    text: str
+    kind: str = "voice_clone"
+    language: str = "Auto"
+    ref_audio: Optional[object] = None
+    ref_text: str = ""
+    speaker: Optional[str] = None
+    instruct: Optional[str] = None
+    xvec_only: bool = True
+    non_streaming_mode: bool = True
+    append_silence: bool = True
+    max_new_tokens: int = 2048
+    min_new_tokens: int = 2
+    temperature: float = 0.9
+    top_k: int = 50
+    top_p: float = 1.0
+    do_sample: bool = True
+    repetition_penalty: float = 1.05
+
+    def policy_key(self) -> tuple:
+        return (self.do_sample, self.top_k, self.top_p, self.temperature, self.repetition_penalty, self.min_new_tokens)
+
+
+class RequestHandle:
+    """What `submit` returns: iterate for (audio float32, sample_rate, info) chunks as they are decoded, or `result()` for the
+    whole utterance.  `codes` collects the int64 [n, 16] codec ids chunk by chunk."""
+
+    def __init__(self, req: TTSRequest, rid: int):
+        self.request, self.id = req, rid
+        self.q: "queue.Queue" = queue.Queue()
+        self.codes: List[torch.Tensor] = []
+        self.t_submit = time.time()
+        self.t_first: Optional[float] = None
+        self.t_done: Optional[float] = None
+        self.finish_reason: Optional[str] = None
+        self.cancelled = False
+        self._sr = 24000
+
+    def cancel(self):
+        self.cancelled = True
+
+    def __iter__(self) -> Iterator[Tuple[np.ndarray, int, dict]]:
+        while True:
+            item = self.q.get()
+            if item is _DONE:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+
+    def result(self, timeout: Optional[float] = None) -> Tuple[np.ndarray, int]:
+        parts = [a for a, _, _ in self]
+        if not parts:
+            return np.zeros(1, dtype=np.float32), self._sr  # model.py:630-632: empty generation -> one zero sample
+        return np.concatenate(parts), self._sr
+
+    @property
+    def ttfa_s(self) -> Optional[float]:
+        return None if self.t_first is None else self.t_first - self.t_submit
+
+
+@dataclass
+class _Active:
+    handle: RequestHandle
+    slot: int
+    window: object
+    emitted: int = 0
+    budget: int = 0
+    chunk_index: int = 0
+
+
+class BatchScheduler:
+    """Continuous batching for one engine (= one GPU).  `tts` must have been loaded with `max_streams` >= the wanted
+    concurrency (`FasterQwen3TTS.from_pretrained(..., max_streams=16)`)."""
+
+    def __init__(self, tts, chunk_frames: int = 8, max_concurrent: Optional[int] = None, seed: int = 0):
+        self.tts = tts
+        self.eng = tts.model.engine
+        self.chunk_frames = int(chunk_frames)
+        cap = self.eng.max_streams
+        if self.eng.lockstep_group <= 4:  # 1.7B dims: no wide program, the frame loop takes four streams per launch
+            cap = min(cap, 4)
+        self.max_concurrent = min(cap, max_concurrent or cap)
+        self.seed = seed
+        self._pending: "queue.Queue[RequestHandle]" = queue.Queue()
+        self._deferred: List[RequestHandle] = []   # waiting for the running cohort's policy to drain
+        self._active: Dict[int, _Active] = {}
+        self._cohort: Optional[tuple] = None
+        self._thread: Optional[threading.Thread] = None
+        self._stop = threading.Event()
+        self._wake = threading.Event()
+        self._next_id = 0
+        self._side: Optional[torch.cuda.Stream] = None
+        self.stats = {"launches": 0, "frames": 0, "requests": 0, "max_batch": 0}
+
+    # ---- public ----
+    def start(self):
+        if self._thread is None:
+            self._thread = threading.Thread(target=self._run, name="fq3-scheduler", daemon=True)
+            self._thread.start()
+        return self
+
+    def stop(self, timeout: float = 30.0):
+        self._stop.set()
+        self._wake.set()
+        if self._thread is not None:
+            self._thread.join(timeout)
+            self._thread = None
+
+    def __enter__(self):
+        return self.start()
+
+    def __exit__(self, *exc):
+        self.stop()
+
+    def submit(self, req: TTSRequest) -> RequestHandle:
+        if req.kind not in ("voice_clone", "custom_voice", "voice_design"):
+            raise ValueError(f"unknown request kind {req.kind!r}")
+        h = RequestHandle(req, self._next_id)
+        self._next_id += 1
+        h._sr = self.tts.sample_rate
+        self._pending.put(h)
+        self._wake.set()
+        return h
+
+    # ---- scheduler thread ----
+    def _prepare(self, r: TTSRequest):
+        """Prompt embeddings exactly as the matching generate_* method builds them (model.py:202-330)."""
+        t = self.tts
+        if r.kind == "voice_clone":
+            m, _, _, tie, tam, tth, tpe, ref_codes = t._prepare_generation(
+                r.text, r.ref_audio, r.ref_text, language=r.language, xvec_only=r.xvec_only,
+                non_streaming_mode=r.non_streaming_mode, append_silence=r.append_silence, instruct=r.instruct)
+            return m, tie, tam, tth, tpe, ref_codes
+        if r.kind == "custom_voice":
+            t._check_custom(r.language, r.speaker)
+            instruct = None if t.model.model.tts_model_size in "0b6" else r.instruct  # model.py:849-850
+            m, _, _, tie, tam, tth, tpe = t._prepare_generation_custom(r.text, r.language, r.speaker, instruct)
+        else:
+            t._check_design(r.language)
+            m, _, _, tie, tam, tth, tpe = t._prepare_generation_custom(r.text, r.language, None, r.instruct)
+        return m, tie, tam, tth, tpe, None
+
+    def _policy(self, key: tuple) -> SamplingPolicy:
+        do_sample, top_k, top_p, temperature, rep, min_new = key
+        return SamplingPolicy(do_sample=do_sample, top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=rep,
+                              min_new_tokens=min_new, suppress_tail=1024, seed=self.seed)
+
+    def _admit(self):
+        """Move waiting requests into free slots (prefill runs here, between two chunk launches)."""
+        from .generate import _left_pads
+        from .model import WindowedDecode
+
+        waiting = self._deferred
+        self._deferred = []
+        while True:
+            try:
+                waiting.append(self._pending.get_nowait())
+            except queue.Empty:
+                break
+        for h in waiting:
+            if h.cancelled:
+                self._finish(h, "cancelled")
+                continue
+            key = h.request.policy_key()
+            if self._cohort is None and not self._active:
+                self._cohort = key
+            free = [s for s in range(self.max_concurrent) if s not in self._active]
+            if key != self._cohort or not free:
+                self._deferred.append(h)
+                continue
+            slot = free[0]
+            try:
+                m, tie, tam, tth, tpe, ref_codes = self._prepare(h.request)
+                if tie.shape[1] > self.eng.max_seq_len:
+                    raise RuntimeError(  # talker_graph.py:163-167
+                        f"Input is too long: prefill has {tie.shape[1]} tokens but max_seq_len={self.eng.max_seq_len}. "
+                        "Use shorter text or shorter reference audio.")
+                self.eng.set_text_conditioning(slot, tth[0], tpe)
+                self.eng.prefill(slot, tie[0], _left_pads(tam), self._policy(key))
+            except Exception as e:  # a bad request must not take the loop down
+                h.q.put(e)
+                self._finish(h, "error")
+                continue
+            window = WindowedDecode(m.speech_tokenizer, ref_codes, self.chunk_frames)
+            self._active[slot] = _Active(h, slot, window, budget=min(h.request.max_new_tokens, self.eng.max_frames))
+            self.stats["requests"] += 1
+
+    def _finish(self, h: RequestHandle, reason: str):
+        h.finish_reason = reason
+        h.t_done = time.time()
+        h.q.put(_DONE)
+
+    def _emit(self, work: List[tuple]):
+        """Codec decode + hand-out of one chunk's codes, on the side stream (the next chunk is already running)."""
+        if not work:
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.eng.device)
+        with torch.cuda.stream(self._side):
+            for a, chunk, final, reason in work:
+                audio, sr = a.window.push(chunk.to(self.eng.device))
+                wav = self.tts._to_numpy(audio)  # D2H on the side stream, synchronises it
+                h = a.handle
+                if h.t_first is None:
+                    h.t_first = time.time()
+                h.codes.append(chunk)
+                info = {"chunk_index": a.chunk_index, "chunk_steps": int(chunk.shape[0]), "total_steps_so_far": a.emitted,
+                        "is_final": final, "slot": a.slot}
+                a.chunk_index += 1
+                h.q.put((wav, sr, info))
+                if final:
+                    self._finish(h, reason)
+
+    def _run(self):
+        eng = self.eng
+        try:
+            torch.cuda.set_device(eng.device)
+            with torch.inference_mode():
+                for s in range(self.eng.max_streams):
+                    eng.retire_stream(s)  # never-used slots idle inside a launch
+                backlog: List[tuple] = []  # (active, codes chunk, final?, reason) of the chunk that just finished
+                while not self._stop.is_set():
+                    self._admit()
+                    if not self._active:
+                        self._emit(backlog)
+                        backlog = []
+                        self._cohort = None
+                        if self._deferred:
+                            continue
+                        self._wake.wait(timeout=0.05)
+                        self._wake.clear()
+                        continue
+                    hi = max(self._active) + 1
+                    eng.decode_frames(hi, self.chunk_frames, self._policy(self._cohort), self.tts.predictor_graph.policy())
+                    self.stats["launches"] += 1
+                    self.stats["max_batch"] = max(self.stats["max_batch"], len(self._active))
+                    self._emit(backlog)  # previous chunk's audio while this one decodes
+                    backlog = []
+                    for slot in sorted(self._active):
+                        a = self._active[slot]
+                        st = eng.status(slot)  # synchronises the launch (first call) and reads the slot's counters
+                        if st.error:
+                            raise RuntimeError(f"device fault {st.error} in slot {slot}")
+                        n_new = min(st.n_frames, a.budget) - a.emitted
+                        reason = None
+                        if a.handle.cancelled:
+                            reason = "cancelled"
+                        elif st.done == 1:
+                            reason = "stop"          # EOS (generate.py:150)
+                        elif st.done == 2:
+                            reason = "cache_full"    # generate.py:175-177
+                        elif st.n_frames >= a.budget:
+                            reason = "length"
+                        if n_new > 0 and reason != "cancelled":
+                            chunk = eng.read_codes(slot, a.emitted, n_new)
+                            a.emitted += n_new
+                            self.stats["frames"] += n_new
+                            backlog.append((a, chunk, reason is not None, reason))
+                        elif reason is not None:
+                            self._finish(a.handle, reason)
+                        if reason is not None:
+                            eng.retire_stream(slot)
+                            del self._active[slot]
+                self._emit(backlog)
+        except BaseException as e:  # surface a scheduler failure to every waiter instead of hanging them
+            logger.exception("fq3 scheduler stopped")
+            for a in list(self._active.values()):
+                a.handle.q.put(e)
+                a.handle.q.put(_DONE)
+            for h in self._deferred:
+                h.q.put(e)
+                h.q.put(_DONE)
+            while True:
+                try:
+                    h = self._pending.get_nowait()
+                except queue.Empty:
+                    break
+                h.q.put(e)
+                h.q.put(_DONE)

@@ -1,0 +1,130 @@
+"""HTTP layer of the serving row against a stand-in backend: the OpenAI endpoint's contract
+(examples/openai_server.py:219-265 — streamed WAV with an unknown-length header, pcm, 400s for empty input / unknown voice /
+unsupported format, default-voice fallback) and the demo's SSE protocol (demo/server.py:332-541: queued / chunk / done)."""
+import base64
+import json
+import struct
+
+import numpy as np
+import pytest
+from starlette.testclient import TestClient
+
+from qwen3_tts_cuda_graphs_b200 import server
+from qwen3_tts_cuda_graphs_b200.serving import RequestHandle, TTSRequest, _DONE
+
+
+class StubBackend:
+    """submit() -> a handle that already holds three 0.1 s chunks (a ramp, so order is checkable)."""
+
+    def __init__(self, fail=False):
+        self.requests = []
+        self.fail = fail
+
+    def submit(self, req: TTSRequest):
+        h = RequestHandle(req, len(self.requests))
+        self.requests.append(req)
+        if self.fail:
+            h.q.put(RuntimeError("boom"))
+        else:
+            for i in range(3):
+                h.q.put((np.full(2400, 0.1 * (i + 1), dtype=np.float32), 24000, {"chunk_index": i, "is_final": i == 2}))
+            h.finish_reason = "stop"
+        h.q.put(_DONE)
+        return h
+
+
+VOICES = {"alloy": {"ref_audio": "alloy.wav", "ref_text": "hi", "language": "English"},
+          "aiden": {"speaker": "aiden", "language": "English"}}
+
+
+@pytest.fixture()
+def client():
+    b0, b1 = StubBackend(), StubBackend()
+    app = server.create_app([b0, b1], VOICES, "alloy")
+    return TestClient(app), b0, b1
+
+
+def test_health_and_voices(client):
+    c, *_ = client
+    assert c.get("/health").json()["status"] == "ok"
+    assert c.get("/v1/voices").json() == {"voices": ["aiden", "alloy"], "default": "alloy"}
+
+
+def test_speech_streams_a_wav_with_unknown_length_header(client):
+    c, b0, b1 = client
+    r = c.post("/v1/audio/speech", json={"model": "tts-1", "input": "Hello!", "voice": "alloy", "response_format": "wav"})
+    assert r.status_code == 200 and r.headers["content-type"] == "audio/wav"
+    body = r.content
+    assert body[:4] == b"RIFF" and body[8:16] == b"WAVEfmt " and struct.unpack("<I", body[40:44])[0] == 0xFFFFFFFF
+    assert struct.unpack("<IHHIIHH", body[16:36]) == (16, 1, 1, 24000, 48000, 2, 16)
+    pcm = np.frombuffer(body[44:], dtype="<i2")
+    assert pcm.size == 7200 and abs(pcm[0] - 3276) <= 1 and abs(pcm[-1] - 9830) <= 1
+    req = (b0.requests + b1.requests)[0]
+    assert req.kind == "voice_clone" and req.ref_audio == "alloy.wav" and req.ref_text == "hi" and req.language == "English"
+    assert req.non_streaming_mode is False  # examples/openai_server.py:190
+    assert c.app.state.dispatcher.in_flight == [0, 0]  # released when the stream ended
+
+
+def test_pcm_custom_voice_and_least_loaded_dispatch(client):
+    c, b0, b1 = client
+    r = c.post("/v1/audio/speech", json={"input": "Hi", "voice": "aiden", "response_format": "pcm"})
+    assert r.status_code == 200 and r.headers["content-type"] == "audio/pcm" and len(r.content) == 7200 * 2
+    c.post("/v1/audio/speech", json={"input": "Hi again", "voice": "aiden", "response_format": "pcm"})
+    reqs = b0.requests + b1.requests
+    assert len(reqs) == 2 and all(q.kind == "custom_voice" and q.speaker == "aiden" for q in reqs)
+    d = server.Dispatcher([b0, b1])
+    h0, h1 = d.submit(TTSRequest("a")), d.submit(TTSRequest("b"))
+    assert {h0._backend_index, h1._backend_index} == {0, 1}  # the second goes to the idle replica
+
+
+def test_errors_mirror_the_reference(client):
+    c, *_ = client
+    assert c.post("/v1/audio/speech", json={"input": "   ", "voice": "alloy"}).status_code == 400
+    assert c.post("/v1/audio/speech", json={"input": "x", "voice": "alloy", "response_format": "flac"}).status_code == 400
+    assert c.post("/v1/audio/speech", json={"input": "x", "voice": "alloy", "response_format": "mp3"}).status_code == 400
+    # unknown voice falls back to the default one (examples/openai_server.py:150-157) ...
+    assert c.post("/v1/audio/speech", json={"input": "x", "voice": "nobody"}).status_code == 200
+    # ... and is a 400 when there is no default
+    app = server.create_app([StubBackend()], VOICES, None)
+    assert TestClient(app).post("/v1/audio/speech", json={"input": "x", "voice": "nobody"}).status_code == 400
+
+
+def test_sse_protocol(client):
+    c, *_ = client
+    r = c.post("/generate/stream", data={"text": "Hello there", "mode": "custom", "speaker": "aiden", "language": "English"})
+    assert r.status_code == 200 and r.headers["content-type"].startswith("text/event-stream")
+    msgs = [json.loads(line[6:]) for line in r.text.splitlines() if line.startswith("data: ")]
+    assert [m["type"] for m in msgs] == ["queued", "chunk", "chunk", "chunk", "done"]
+    wav = base64.b64decode(msgs[1]["audio_b64"])
+    assert wav[:4] == b"RIFF" and struct.unpack("<I", wav[40:44])[0] == 4800 and msgs[1]["sample_rate"] == 24000
+    assert msgs[-1]["total_audio_s"] == pytest.approx(0.3, abs=1e-3)
+    r = c.post("/generate/stream", data={"text": "x", "mode": "nonsense"})
+    assert r.status_code == 400
+
+
+def test_sse_reports_generation_errors_in_band():
+    app = server.create_app([StubBackend(fail=True)], VOICES, "alloy")
+    r = TestClient(app).post("/generate/stream", data={"text": "x", "mode": "voice_clone"})
+    msgs = [json.loads(line[6:]) for line in r.text.splitlines() if line.startswith("data: ")]
+    assert msgs[-1] == {"type": "error", "message": "boom"}
+
+
+def test_cli_parser_has_the_reference_subcommands_and_writes_wav(tmp_path):
+    import wave
+
+    from qwen3_tts_cuda_graphs_b200 import cli
+
+    p = cli.build_parser()
+    a = p.parse_args(["clone", "--model", "m", "--text", "t", "--output", "o.wav", "--ref-audio", "a.wav", "--ref-text", "r", "--greedy",
+                      "--streaming", "--no-non-streaming-mode"])
+    assert (a.greedy, a.streaming, a.non_streaming_mode, a.chunk_size, a.max_new_tokens) == (True, True, False, 8, 2048)
+    stem, kw = cli._call(None, "clone", "t", a)
+    assert stem == "generate_voice_clone" and kw["do_sample"] is False and kw["ref_audio"] == "a.wav" and kw["non_streaming_mode"] is False
+    a = p.parse_args(["serve", "--mode", "design", "--model", "m", "--instruct", "calm", "--concurrency", "8"])
+    assert a.concurrency == 8 and cli._call(None, "design", "t", a)[0] == "generate_voice_design"
+    a = p.parse_args(["custom", "--model", "m", "--text", "t", "--output", "o.wav", "--list-speakers"])
+    assert a.list_speakers
+    out = str(tmp_path / "d" / "x.wav")
+    cli.write_audio(out, np.linspace(-1, 1, 480, dtype=np.float32), 24000)
+    with wave.open(out) as wf:
+        assert (wf.getframerate(), wf.getnchannels(), wf.getsampwidth(), wf.getnframes()) == (24000, 1, 2, 480)
