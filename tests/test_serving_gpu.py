@@ -40,6 +40,7 @@ def tts():
     from qwen3_tts_cuda_graphs_b200 import FasterQwen3TTS
 
     m = FasterQwen3TTS.from_pretrained("tiny-Base", device="cuda", dtype=torch.bfloat16, max_seq_len=256, max_streams=6)
+    m.predictor_graph.do_sample = False  # greedy predictor too (the reference's tests set it the same way, test_e2e_parity.py:208-215)
     yield m
     m.model.engine.close()
 
