@@ -113,12 +113,43 @@ class _Active:
     chunk_index: int = 0
 
 
+class _StatefulAudio:
+    """push(chunk) -> the chunk's samples through the slot's codec.CodecStream (same surface as model.WindowedDecode)."""
+
+    def __init__(self, cstream, sample_rate: int):
+        self.cs, self.sr = cstream, sample_rate
+
+    def push(self, chunk: torch.Tensor):
+        return self.cs.decode(chunk), self.sr
+
+
 class BatchScheduler:
     """Continuous batching for one engine (= one GPU).  `tts` must have been loaded with `max_streams` >= the wanted
     concurrency (`FasterQwen3TTS.from_pretrained(..., max_streams=16)`)."""
 
-    def __init__(self, tts, chunk_frames: int = 8, max_concurrent: Optional[int] = None, seed: int = 0):
+    def __init__(self, tts, chunk_frames: int = 8, max_concurrent: Optional[int] = None, seed: int = 0, codec_lanes: int = 4,
+                 codec_mode: str = "auto", codec_split_k: Optional[bool] = None, overlap_codec: bool = False):
+        """codec_mode: "windowed" (default, = "auto") — the reference's 25-frame left-context re-decode (model.py:737-826): the
+        audio is bit for bit what the single-stream streaming API returns for the same codes; "stateful" — one
+        codec.CodecStream per slot: a chunk costs its own frames and the audio is the full non-streaming decode of the
+        utterance's codes (bit for bit with codec_split_k=False, up to fp32 summation order otherwise).
+        codec_lanes: CUDA streams the utterances' codec decodes of one chunk are spread over (16 windowed decodes: 23 ms on one
+        stream, 11 ms on four, profiles/r02k_codec_lanes_probe.log).
+        overlap_codec: decode the previous chunk's audio WHILE the next chunk's frame loop runs (on the 20 SMs its grid leaves
+        free) instead of before it.  Measured faster (197 vs 173 audio-s/s at 16 streams) but off by default: one of nine
+        overlapped runs ended in a device watchdog fault of the wide frame program (an exchange word that never arrived,
+        profiles/r02k_serving_overlap_fault.log) that the serialised order never showed — an open issue, see DESIGN.md §8."""
         self.tts = tts
+        self.codec_lanes = max(1, int(codec_lanes))
+        self.overlap_codec = bool(overlap_codec)
+        causal = getattr(tts.model.model.speech_tokenizer.decoder.cfg, "trans_conv_trim", "") == "right"
+        if codec_mode == "auto":
+            codec_mode = "windowed"
+        if codec_mode not in ("stateful", "windowed") or (codec_mode == "stateful" and not causal):
+            raise ValueError(f"codec_mode {codec_mode!r} is not available for this decoder")
+        self.codec_mode, self.codec_split_k = codec_mode, codec_split_k
+        self._cstreams: Dict[int, object] = {}  # slot -> codec.CodecStream (stateful mode)
+        self._draining: set = set()  # slots whose last chunk still waits for the codec: their codec state is not reusable yet
         self.eng = tts.model.engine
         self.chunk_frames = int(chunk_frames)
         cap = self.eng.max_streams
@@ -134,8 +165,10 @@ class BatchScheduler:
         self._stop = threading.Event()
         self._wake = threading.Event()
         self._next_id = 0
-        self._side: Optional[torch.cuda.Stream] = None
-        self.stats = {"launches": 0, "frames": 0, "requests": 0, "max_batch": 0}
+        self._lanes: List[tuple] = []  # (CUDA stream, speech tokenizer with its own launch plans) per codec lane
+        # seconds per part of the loop: admit (prompt build + prefill), launch (host side of fq3_decode_frames), emit (codec lanes +
+        # D2H + hand-out of the previous chunk), wait (blocked on the running launch)
+        self.stats = {"launches": 0, "frames": 0, "requests": 0, "max_batch": 0, "t_admit": 0.0, "t_launch": 0.0, "t_emit": 0.0, "t_wait": 0.0}
 
     # ---- public ----
     def start(self):
@@ -209,7 +242,7 @@ class BatchScheduler:
             key = h.request.policy_key()
             if self._cohort is None and not self._active:
                 self._cohort = key
-            free = [s for s in range(self.max_concurrent) if s not in self._active]
+            free = [s for s in range(self.max_concurrent) if s not in self._active and s not in self._draining]
             if key != self._cohort or not free:
                 self._deferred.append(h)
                 continue
@@ -226,7 +259,18 @@ class BatchScheduler:
                 h.q.put(e)
                 self._finish(h, "error")
                 continue
-            window = WindowedDecode(m.speech_tokenizer, ref_codes, self.chunk_frames)
+            lane_stream, lane_tok = self._lane(slot, m.speech_tokenizer)
+            if self.codec_mode == "stateful":
+                cs = self._cstreams.get(slot)
+                if cs is None:
+                    cs = self._cstreams[slot] = lane_tok.decoder.open_stream(max(self.chunk_frames, 8), self.codec_split_k)
+                with torch.cuda.stream(lane_stream):  # ordered behind the slot's previous utterance on the same lane
+                    cs.reset()
+                    if ref_codes is not None:  # ICL: the reference clip's codes are acoustic context, decoded for their state only
+                        cs.decode(ref_codes.to(self.eng.device))
+                window = _StatefulAudio(cs, lane_tok.sample_rate)
+            else:
+                window = WindowedDecode(lane_tok, ref_codes, self.chunk_frames)
             self._active[slot] = _Active(h, slot, window, budget=min(h.request.max_new_tokens, self.eng.max_frames))
             self.stats["requests"] += 1
 
@@ -235,26 +279,45 @@ class BatchScheduler:
         h.t_done = time.time()
         h.q.put(_DONE)
 
+    def _lane(self, slot: int, tok):
+        """Codec lane of a slot.  A windowed decode of one utterance is a chain of ~150 small launches (1.4 ms, latency-bound),
+        so the utterances of a chunk are spread over a few CUDA streams, each with its own copy of the decoder's launch plans
+        (the packed weights are shared); together they fill the SMs the frame loop leaves free."""
+        import copy
+
+        from .codec import SpeechTokenizer
+
+        if not self._lanes:
+            for i in range(self.codec_lanes):
+                dec = copy.copy(tok.decoder)
+                dec._plans = {}
+                self._lanes.append((torch.cuda.Stream(device=self.eng.device), SpeechTokenizer(dec)))
+        return self._lanes[slot % len(self._lanes)]
+
     def _emit(self, work: List[tuple]):
-        """Codec decode + hand-out of one chunk's codes, on the side stream (the next chunk is already running)."""
+        """Codec decode + hand-out of one chunk's codes on the codec lanes (the next chunk is already running)."""
         if not work:
             return
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.eng.device)
-        with torch.cuda.stream(self._side):
-            for a, chunk, final, reason in work:
-                audio, sr = a.window.push(chunk.to(self.eng.device))
-                wav = self.tts._to_numpy(audio)  # D2H on the side stream, synchronises it
-                h = a.handle
-                if h.t_first is None:
-                    h.t_first = time.time()
-                h.codes.append(chunk)
-                info = {"chunk_index": a.chunk_index, "chunk_steps": int(chunk.shape[0]), "total_steps_so_far": a.emitted,
-                        "is_final": final, "slot": a.slot}
-                a.chunk_index += 1
-                h.q.put((wav, sr, info))
-                if final:
-                    self._finish(h, reason)
+        staged = []
+        for a, chunk, final, reason in work:  # enqueue every utterance's decode first ...
+            stream = self._lanes[a.slot % len(self._lanes)][0]
+            with torch.cuda.stream(stream):
+                audio, sr = a.window.push(chunk.to(self.eng.device, non_blocking=True))
+            staged.append((stream, audio, sr))
+        for (a, chunk, final, reason), (stream, audio, sr) in zip(work, staged):  # ... then collect
+            with torch.cuda.stream(stream):
+                wav = self.tts._to_numpy(audio)  # D2H on the lane's stream, synchronises it
+            h = a.handle
+            if h.t_first is None:
+                h.t_first = time.time()
+            h.codes.append(chunk)
+            info = {"chunk_index": a.chunk_index, "chunk_steps": int(chunk.shape[0]), "total_steps_so_far": a.emitted,
+                    "is_final": final, "slot": a.slot}
+            a.chunk_index += 1
+            h.q.put((wav, sr, info))
+            if final:
+                self._draining.discard(a.slot)
+                self._finish(h, reason)
 
     def _run(self):
         eng = self.eng
@@ -265,7 +328,10 @@ class BatchScheduler:
                     eng.retire_stream(s)  # never-used slots idle inside a launch
                 backlog: List[tuple] = []  # (active, codes chunk, final?, reason) of the chunk that just finished
                 while not self._stop.is_set():
+                    t0 = time.perf_counter()
                     self._admit()
+                    t1 = time.perf_counter()
+                    self.stats["t_admit"] += t1 - t0
                     if not self._active:
                         self._emit(backlog)
                         backlog = []
@@ -275,12 +341,19 @@ class BatchScheduler:
                         self._wake.wait(timeout=0.05)
                         self._wake.clear()
                         continue
+                    if not self.overlap_codec:  # codec of the previous chunk on the idle GPU, before the next launch
+                        self._emit(backlog)
+                        backlog = []
                     hi = max(self._active) + 1
                     eng.decode_frames(hi, self.chunk_frames, self._policy(self._cohort), self.tts.predictor_graph.policy())
+                    t2 = time.perf_counter()
                     self.stats["launches"] += 1
                     self.stats["max_batch"] = max(self.stats["max_batch"], len(self._active))
                     self._emit(backlog)  # previous chunk's audio while this one decodes
                     backlog = []
+                    t3 = time.perf_counter()
+                    self.stats["t_launch"] += t2 - t1
+                    self.stats["t_emit"] += t3 - t2
                     for slot in sorted(self._active):
                         a = self._active[slot]
                         st = eng.status(slot)  # synchronises the launch (first call) and reads the slot's counters
@@ -301,12 +374,18 @@ class BatchScheduler:
                             a.emitted += n_new
                             self.stats["frames"] += n_new
                             backlog.append((a, chunk, reason is not None, reason))
+                            if reason is not None:
+                                self._draining.add(slot)
                         elif reason is not None:
                             self._finish(a.handle, reason)
                         if reason is not None:
                             eng.retire_stream(slot)
                             del self._active[slot]
+                    self.stats["t_wait"] += time.perf_counter() - t3
                 self._emit(backlog)
+                for cs in self._cstreams.values():
+                    cs.close()
+                self._cstreams.clear()
         except BaseException as e:  # surface a scheduler failure to every waiter instead of hanging them
             logger.exception("fq3 scheduler stopped")
             for a in list(self._active.values()):

@@ -57,7 +57,7 @@ def test_requests_joining_and_leaving_match_their_single_stream_runs(tts, ref_wa
     from qwen3_tts_cuda_graphs_b200.serving import BatchScheduler, TTSRequest
 
     want = [_single_stream(tts, ref_wav, t, n) for t, n in zip(TEXTS, LENGTHS)]
-    sched = BatchScheduler(tts, chunk_frames=8).start()
+    sched = BatchScheduler(tts, chunk_frames=8, codec_mode="windowed").start()
     try:
         def req(i):
             return TTSRequest(TEXTS[i], ref_audio=ref_wav, language="English", max_new_tokens=LENGTHS[i], do_sample=False)
@@ -90,7 +90,7 @@ def test_requests_joining_and_leaving_match_their_single_stream_runs(tts, ref_wa
 def test_cancel_bad_request_and_policy_cohorts(tts, ref_wav):
     from qwen3_tts_cuda_graphs_b200.serving import BatchScheduler, TTSRequest
 
-    with BatchScheduler(tts, chunk_frames=8) as sched:
+    with BatchScheduler(tts, chunk_frames=8, codec_mode="windowed") as sched:
         long_one = sched.submit(TTSRequest(TEXTS[1], ref_audio=ref_wav, language="English", max_new_tokens=120, do_sample=False))
         bad = sched.submit(TTSRequest("x", ref_audio=ref_wav, language="Klingon", max_new_tokens=8, do_sample=False))
         victim = sched.submit(TTSRequest(TEXTS[2], ref_audio=ref_wav, language="English", max_new_tokens=200, do_sample=False))
@@ -108,3 +108,30 @@ def test_cancel_bad_request_and_policy_cohorts(tts, ref_wav):
         assert sampled.finish_reason in ("length", "stop") and b.size >= 1920 and np.isfinite(b).all()
     want, _ = _single_stream(tts, ref_wav, TEXTS[1], 120)
     assert torch.equal(torch.cat(long_one.codes), want)
+
+
+def test_stateful_codec_mode_gives_the_full_decode_of_every_request(tts, ref_wav, monkeypatch):
+    """codec_mode="stateful": one CodecStream per slot.  Without split-K on either side the audio of every request is the full
+    non-streaming decode of its codes bit for bit — also for a slot that is reused by a later request and for an ICL request
+    whose reference codes are decoded for their state first."""
+    from qwen3_tts_cuda_graphs_b200.serving import BatchScheduler, TTSRequest
+
+    monkeypatch.setenv("FQ3C_SPLITK", "0")
+    m = tts.model.model
+    n_req = 9  # more than the six slots: slots are reused
+    with BatchScheduler(tts, chunk_frames=8, codec_mode="stateful", codec_split_k=False) as sched:
+        hs = [sched.submit(TTSRequest(TEXTS[i % 6], ref_audio=ref_wav, ref_text="reference clip says this." if i == 4 else "",
+                                      xvec_only=i != 4, language="English", max_new_tokens=LENGTHS[i % 6] + i, do_sample=False))
+              for i in range(n_req)]
+        audio = [h.result()[0] for h in hs]
+    for i, h in enumerate(hs):
+        codes = torch.cat(h.codes).cuda()
+        assert codes.shape[0] == LENGTHS[i % 6] + i
+        if i == 4:
+            (vcp, _), = [v for k, v in tts._voice_prompt_cache.items() if k[0] == ref_wav and not k[2]]
+            ref = vcp["ref_code"][0].cuda()
+            full = m.speech_tokenizer.decoder.decode(torch.cat([ref, codes]))[ref.shape[0] * 1920:]
+        else:
+            full = m.speech_tokenizer.decoder.decode(codes)
+        assert audio[i].shape == (codes.shape[0] * 1920,)
+        assert np.array_equal(audio[i], full.cpu().numpy()), f"request {i}: max diff {np.abs(audio[i] - full.cpu().numpy()).max()}"
