@@ -61,9 +61,8 @@ def config_from_hf(raw: dict, codec_raw: Optional[dict] = None) -> TTSConfig:
     pc = dict(tc.pop("code_predictor_config", None) or raw.get("code_predictor_config") or {})
     size = str(raw.get("tts_model_size") or ("1b7" if tc.get("hidden_size", 1024) >= 2048 else "0b6")).lower()
     kind = str(raw.get("tts_model_type") or "base").lower()
-    name = {"0b6": "0.6B", "1b7": "1.7B"}.get(size)
-    if name is None:
-        raise CheckpointError(f"config.json: unknown tts_model_size {size!r}")
+    # defaults for absent keys come from the preset of the nearest named size; the size tag itself is kept as written
+    name = {"0b6": "0.6B", "1b7": "1.7B"}.get(size) or ("1.7B" if tc.get("hidden_size", 1024) >= 2048 else "0.6B")
     kinds = {"base": "Base", "custom_voice": "CustomVoice", "voice_design": "VoiceDesign"}
     base = preset(f"{name}-{kinds.get(kind, 'Base')}")
     for k in ("codec_language_id", "spk_id"):
