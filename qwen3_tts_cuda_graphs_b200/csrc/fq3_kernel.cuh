@@ -1091,6 +1091,22 @@ __device__ __forceinline__ void gemv_phase_consume_wide(const Ctx& c, const Phas
     ep_in = (ep0 == p.epoch_base) ? 0u : ep0;
   }
   FQ3_ASSERT(M >= 1 && M <= kMaxWide && (K & 63) == 0 && M * (int)xrow_stride(K) <= p.xbuf_bytes, pidx, 320000 + M);
+  if ((flags & (F_IN_PREV | F_WPIN_B)) == (F_IN_PREV | F_WPIN_B) && pidx > 0) {
+    // First phase of pass 0b.  Its input (BUF_WPIN) is older than the iteration, so unlike every other phase it does not depend
+    // on the phase before it — pass 0a's last attention — and a CTA without an attention item there (fewer than 16 streams) is
+    // already here while others still poll that attention's q / k / v words in the buffer THIS phase publishes into: a word of
+    // this phase landing first makes their exact-epoch poll spin for good (seen once as a watchdog fault, with the codec of a
+    // serving loop running beside the kernel).  An attention item reads all its inputs before it computes any output, so one
+    // output word per (stream, kv head) with the previous phase's epoch proves the buffer is free; the block barrier inside
+    // load_x_rows keeps every warp's publish behind this wait.
+    const StackRt& Sp = p.stacks[ST_PRED];
+    const int n_items = M * Sp.nkv;
+    const int words_per_item = (Sp.nq / Sp.nkv) * (kHeadDim / 2);
+    for (int it = tid; it < n_items; it += kConsumerWarps * 32) {
+      const int g = it / Sp.nkv, kvh = it - g * Sp.nkv;
+      (void)ll_wait(reinterpret_cast<const LLWord*>(p.bufs[BUF_PATT]) + (size_t)g * p.ld[BUF_PATT] + (size_t)kvh * words_per_item, ep - 1u, p, pidx);
+    }
+  }
   const uint32_t gsrc = c.gam + (uint32_t)gcur.slot * (uint32_t)c.gam_bytes;
   const uint32_t gfullb = c.gfull + (uint32_t)gcur.slot * 8u, gemptyb = c.gempty + (uint32_t)gcur.slot * 8u;
   const uint32_t glap = gcur.lap;

@@ -128,17 +128,17 @@ class BatchScheduler:
     concurrency (`FasterQwen3TTS.from_pretrained(..., max_streams=16)`)."""
 
     def __init__(self, tts, chunk_frames: int = 8, max_concurrent: Optional[int] = None, seed: int = 0, codec_lanes: int = 4,
-                 codec_mode: str = "auto", codec_split_k: Optional[bool] = None, overlap_codec: bool = False):
+                 codec_mode: str = "auto", codec_split_k: Optional[bool] = None, overlap_codec: bool = True):
         """codec_mode: "windowed" (default, = "auto") — the reference's 25-frame left-context re-decode (model.py:737-826): the
         audio is bit for bit what the single-stream streaming API returns for the same codes; "stateful" — one
         codec.CodecStream per slot: a chunk costs its own frames and the audio is the full non-streaming decode of the
         utterance's codes (bit for bit with codec_split_k=False, up to fp32 summation order otherwise).
         codec_lanes: CUDA streams the utterances' codec decodes of one chunk are spread over (16 windowed decodes: 23 ms on one
         stream, 11 ms on four, profiles/r02k_codec_lanes_probe.log).
-        overlap_codec: decode the previous chunk's audio WHILE the next chunk's frame loop runs (on the 20 SMs its grid leaves
-        free) instead of before it.  Measured faster (197 vs 173 audio-s/s at 16 streams) but off by default: one of nine
-        overlapped runs ended in a device watchdog fault of the wide frame program (an exchange word that never arrived,
-        profiles/r02k_serving_overlap_fault.log) that the serialised order never showed — an open issue, see DESIGN.md §8."""
+        overlap_codec (default): decode the previous chunk's audio WHILE the next chunk's frame loop runs (on the 20 SMs its grid
+        leaves free) instead of before it: 192 vs 173 audio-s/s at 16 streams.  (The first overlapped runs exposed a missing
+        dependency in the wide frame program — fixed, DESIGN.md §3.5 "pass 0a -> 0b"; profiles/r02k_serving_overlap_fault.log,
+        r02k_overlap_stress_after_fix.log.)"""
         self.tts = tts
         self.codec_lanes = max(1, int(codec_lanes))
         self.overlap_codec = bool(overlap_codec)

@@ -22,7 +22,7 @@ ap.add_argument("--rate", type=float, default=0.0)
 ap.add_argument("--chunk", type=int, default=8)
 ap.add_argument("--lanes", type=int, default=4)
 ap.add_argument("--codec", default="auto")
-ap.add_argument("--overlap", type=int, default=0)
+ap.add_argument("--overlap", type=int, default=1)
 args = ap.parse_args()
 
 model = FasterQwen3TTS.from_pretrained(args.model, device="cuda", dtype=torch.bfloat16, max_seq_len=1024, seed=0, max_streams=args.concurrent)
