@@ -265,6 +265,8 @@ def main():
     ap.add_argument("--batched-streams", type=str, default="4,16,64", dest="batched_streams",
                     help="extra (reported, not the headline) leg at N=1: this many utterances decoded request-parallel on one GPU "
                          "(comma list; lock-step groups of up to 16 share a weight sweep); 0 = skip")
+    ap.add_argument("--serving-requests", type=int, default=32, dest="serving_requests",
+                    help="extra leg at N=1: this many requests through serving.BatchScheduler (16 concurrent); 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -441,6 +443,35 @@ def main():
                                "what": "request-parallel decode of identical prompts on one GPU (groups of up to lockstep_group streams share "
                                        "every weight sweep; more streams run group after group), non-streaming, max_seq_len 1024, prefill and "
                                        "codec decode of every utterance included"}
+            if args.serving_requests > 0:
+                # the same GPU through the serving layer: requests submitted at once to the continuous-batching
+                # scheduler, audio streamed back chunk by chunk; wall clock incl. prompt build, prefill, codec, D2H
+                try:
+                    import threading
+                    from qwen3_tts_cuda_graphs_b200.serving import BatchScheduler, TTSRequest
+                    conc = min(16, max(batch_sizes))
+
+                    def serve(n_req):
+                        got = []
+                        with BatchScheduler(model_b, chunk_frames=args.chunk, max_concurrent=conc) as sched:
+                            t0 = time.perf_counter()
+                            hs = [sched.submit(TTSRequest(TEXT + f" Request {i}.", ref_audio=ref_wav, ref_text=REF_TEXT, language="English", **gen_kw))
+                                  for i in range(n_req)]
+                            ths = [threading.Thread(target=lambda h=h: got.append(len(h.result()[0]) / model_b.sample_rate)) for h in hs]
+                            for th in ths:
+                                th.start()
+                            for th in ths:
+                                th.join()
+                            dt = time.perf_counter() - t0
+                        return sum(got) / dt, [h.ttfa_s for h in hs if h.ttfa_s is not None]
+                    serve(4)
+                    v, ttfas = serve(args.serving_requests)
+                    line["serving"] = {"value": v, "unit": UNIT, "requests": args.serving_requests, "concurrent": conc, "chunk_frames": args.chunk,
+                                       "ttfa_ms_first_wave_mean": 1000.0 * float(np.mean(sorted(ttfas)[:conc])) if ttfas else None,
+                                       "what": "serving.BatchScheduler (continuous batching, windowed streaming codec per utterance, codec lanes "
+                                               "beside the next launch): all requests submitted at once, audio streamed back per chunk"}
+                except Exception as ex:  # a reported extra: never fail the bench on it
+                    line["serving"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
             model_b.model.engine.close()
             del model_b
             torch.cuda.empty_cache()

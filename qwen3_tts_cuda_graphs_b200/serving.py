@@ -128,18 +128,24 @@ class BatchScheduler:
     concurrency (`FasterQwen3TTS.from_pretrained(..., max_streams=16)`)."""
 
     def __init__(self, tts, chunk_frames: int = 8, max_concurrent: Optional[int] = None, seed: int = 0, codec_lanes: int = 4,
-                 codec_mode: str = "auto", codec_split_k: Optional[bool] = None, overlap_codec: bool = True):
+                 codec_mode: str = "auto", codec_split_k: Optional[bool] = None, overlap_codec: bool = True,
+                 emit_every: int = 1):
         """codec_mode: "windowed" (default, = "auto") — the reference's 25-frame left-context re-decode (model.py:737-826): the
         audio is bit for bit what the single-stream streaming API returns for the same codes; "stateful" — one
         codec.CodecStream per slot: a chunk costs its own frames and the audio is the full non-streaming decode of the
         utterance's codes (bit for bit with codec_split_k=False, up to fp32 summation order otherwise).
         codec_lanes: CUDA streams the utterances' codec decodes of one chunk are spread over (16 windowed decodes: 23 ms on one
         stream, 11 ms on four, profiles/r02k_codec_lanes_probe.log).
+        emit_every: after an utterance's first chunk (time to first audio is not touched) hand audio out every `emit_every`
+        chunks: a 41-frame window per 16 new frames instead of two 33-frame windows — less codec work per second of audio, at
+        the price of coarser streaming; the audio then differs from the chunk-by-chunk streaming run by the windowed policy's
+        own approximation (not at all in stateful mode).
         overlap_codec (default): decode the previous chunk's audio WHILE the next chunk's frame loop runs (on the 20 SMs its grid
         leaves free) instead of before it: 192 vs 173 audio-s/s at 16 streams.  (The first overlapped runs exposed a missing
         dependency in the wide frame program — fixed, DESIGN.md §3.5 "pass 0a -> 0b"; profiles/r02k_serving_overlap_fault.log,
         r02k_overlap_stress_after_fix.log.)"""
         self.tts = tts
+        self.emit_every = max(1, int(emit_every))
         self.codec_lanes = max(1, int(codec_lanes))
         self.overlap_codec = bool(overlap_codec)
         causal = getattr(tts.model.model.speech_tokenizer.decoder.cfg, "trans_conv_trim", "") == "right"
@@ -369,6 +375,9 @@ class BatchScheduler:
                             reason = "cache_full"    # generate.py:175-177
                         elif st.n_frames >= a.budget:
                             reason = "length"
+                        if n_new > 0 and reason is None and a.emitted > 0 and n_new < self.emit_every * self.chunk_frames:
+                            # emit_every > 1: after an utterance's first chunk, hand audio out every few chunks
+                            continue
                         if n_new > 0 and reason != "cancelled":
                             chunk = eng.read_codes(slot, a.emitted, n_new)
                             a.emitted += n_new
