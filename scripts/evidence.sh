@@ -27,3 +27,5 @@ timeout 600 python scripts/batch_perf.py 0.6B-Base 16 1,2,4,8,16,32,64 > gpurun_
 timeout 300 python scripts/codec_stream_time.py > gpurun_out/codec_stream_${tag}.log 2>&1
 timeout 300 python scripts/ttfa_breakdown.py > gpurun_out/ttfa_${tag}.log 2>&1
 timeout 300 python scripts/quick_perf.py 0.6B-Base 64 14 > gpurun_out/quick_perf_${tag}.log 2>&1
+timeout 300 python scripts/serving_bench.py --concurrent 16 --requests 48 --frames 250 2>&1 | grep "^{" > gpurun_out/serving_${tag}.log
+timeout 100 python scripts/serving_bench.py --concurrent 16 --requests 1 --frames 250 2>&1 | grep "^{" >> gpurun_out/serving_${tag}.log

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: per-test limit in seconds (pytest-timeout; a no-op marker where the plugin is absent)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]  # a dead scheduler thread must fail the test, not hang the suite
 
 TEXTS = [
     "Short parity test.",
