@@ -270,7 +270,7 @@ class BatchScheduler:
                 cs = self._cstreams.get(slot)
                 if cs is None:
                     cs = self._cstreams[slot] = lane_tok.decoder.open_stream(max(self.chunk_frames, 8), self.codec_split_k)
-                with torch.cuda.stream(lane_stream):  # ordered behind the slot's previous utterance on the same lane
+                with self._on(lane_stream):  # ordered behind the slot's previous utterance on the same lane
                     cs.reset()
                     if ref_codes is not None:  # ICL: the reference clip's codes are acoustic context, decoded for their state only
                         cs.decode(ref_codes.to(self.eng.device))
@@ -285,6 +285,13 @@ class BatchScheduler:
         h.t_done = time.time()
         h.q.put(_DONE)
 
+    @staticmethod
+    def _on(stream):
+        """Context of a codec lane's CUDA stream (a no-op for the host-only doubles of tests/test_serving_cpu.py)."""
+        import contextlib
+
+        return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
     def _lane(self, slot: int, tok):
         """Codec lane of a slot.  A windowed decode of one utterance is a chain of ~150 small launches (1.4 ms, latency-bound),
         so the utterances of a chunk are spread over a few CUDA streams, each with its own copy of the decoder's launch plans
@@ -297,7 +304,8 @@ class BatchScheduler:
             for i in range(self.codec_lanes):
                 dec = copy.copy(tok.decoder)
                 dec._plans = {}
-                self._lanes.append((torch.cuda.Stream(device=self.eng.device), SpeechTokenizer(dec)))
+                stream = torch.cuda.Stream(device=self.eng.device) if torch.device(self.eng.device).type == "cuda" else None
+                self._lanes.append((stream, SpeechTokenizer(dec)))
         return self._lanes[slot % len(self._lanes)]
 
     def _emit(self, work: List[tuple]):
@@ -307,11 +315,11 @@ class BatchScheduler:
         staged = []
         for a, chunk, final, reason in work:  # enqueue every utterance's decode first ...
             stream = self._lanes[a.slot % len(self._lanes)][0]
-            with torch.cuda.stream(stream):
+            with self._on(stream):
                 audio, sr = a.window.push(chunk.to(self.eng.device, non_blocking=True))
             staged.append((stream, audio, sr))
         for (a, chunk, final, reason), (stream, audio, sr) in zip(work, staged):  # ... then collect
-            with torch.cuda.stream(stream):
+            with self._on(stream):
                 wav = self.tts._to_numpy(audio)  # D2H on the lane's stream, synchronises it
             h = a.handle
             if h.t_first is None:
@@ -328,7 +336,8 @@ class BatchScheduler:
     def _run(self):
         eng = self.eng
         try:
-            torch.cuda.set_device(eng.device)
+            if torch.device(eng.device).type == "cuda":
+                torch.cuda.set_device(eng.device)
             with torch.inference_mode():
                 for s in range(self.eng.max_streams):
                     eng.retire_stream(s)  # never-used slots idle inside a launch
