@@ -128,7 +128,7 @@ class BatchScheduler:
     concurrency (`FasterQwen3TTS.from_pretrained(..., max_streams=16)`)."""
 
     def __init__(self, tts, chunk_frames: int = 8, max_concurrent: Optional[int] = None, seed: int = 0, codec_lanes: int = 4,
-                 codec_mode: str = "auto", codec_split_k: Optional[bool] = None, overlap_codec: bool = True,
+                 codec_mode: str = "auto", codec_split_k: Optional[bool] = None, overlap_codec="auto",
                  emit_every: int = 1):
         """codec_mode: "windowed" (default, = "auto") — the reference's 25-frame left-context re-decode (model.py:737-826): the
         audio is bit for bit what the single-stream streaming API returns for the same codes; "stateful" — one
@@ -140,14 +140,21 @@ class BatchScheduler:
         chunks: a 41-frame window per 16 new frames instead of two 33-frame windows — less codec work per second of audio, at
         the price of coarser streaming; the audio then differs from the chunk-by-chunk streaming run by the windowed policy's
         own approximation (not at all in stateful mode).
-        overlap_codec (default): decode the previous chunk's audio WHILE the next chunk's frame loop runs (on the 20 SMs its grid
-        leaves free) instead of before it: 192 vs 173 audio-s/s at 16 streams.  (The first overlapped runs exposed a missing
-        dependency in the wide frame program — fixed, DESIGN.md §3.5 "pass 0a -> 0b"; profiles/r02k_serving_overlap_fault.log,
-        r02k_overlap_stress_after_fix.log.)"""
+        overlap_codec: where the previous chunk's codec runs relative to the next frame-loop launch.  "host": on the GPU the
+        codec lanes run first and the launch waits for them (stream events), on the host the audio is collected and handed out
+        while the frame loop runs — no contention on the GPU, nothing idle on the host (16 streams: 202 audio-s/s, stable).
+        "gpu": the codec runs WHILE the frame loop runs, on the 20 SMs its grid leaves free — best for one or two utterances
+        (a lone request: 44 vs 41 audio-s/s), but with many the two slow each other through L2 and throughput spreads
+        134–209 audio-s/s run to run.  "auto" (default): "gpu" for up to two utterances in the chunk, "host" beyond.
+        "none": codec, host collection, then launch.
+        (The first "gpu" runs exposed a missing dependency in the wide frame program — fixed, DESIGN.md §3.5 "pass 0a -> 0b";
+        profiles/r02k_serving_overlap_fault.log, r02k_overlap_stress_after_fix.log.)"""
         self.tts = tts
         self.emit_every = max(1, int(emit_every))
         self.codec_lanes = max(1, int(codec_lanes))
-        self.overlap_codec = bool(overlap_codec)
+        self.overlap_codec = {True: "gpu", False: "none"}.get(overlap_codec, overlap_codec)
+        if self.overlap_codec not in ("auto", "host", "gpu", "none"):
+            raise ValueError(f"overlap_codec {overlap_codec!r}: auto | host | gpu | none")
         causal = getattr(tts.model.model.speech_tokenizer.decoder.cfg, "trans_conv_trim", "") == "right"
         if codec_mode == "auto":
             codec_mode = "windowed"
@@ -301,6 +308,10 @@ class BatchScheduler:
         from .codec import SpeechTokenizer
 
         if not self._lanes:
+            # the lanes (and the launch plans / CUDA graphs they have built) belong to the model, not to one scheduler object
+            cache = self.tts.__dict__.setdefault("_serving_lanes", {})
+            self._lanes = cache.setdefault(self.codec_lanes, [])
+        if not self._lanes:
             for i in range(self.codec_lanes):
                 dec = copy.copy(tok.decoder)
                 dec._plans = {}
@@ -308,17 +319,35 @@ class BatchScheduler:
                 self._lanes.append((stream, SpeechTokenizer(dec)))
         return self._lanes[slot % len(self._lanes)]
 
-    def _emit(self, work: List[tuple]):
-        """Codec decode + hand-out of one chunk's codes on the codec lanes (the next chunk is already running)."""
-        if not work:
-            return
+    def _emit_enqueue(self, work: List[tuple]) -> list:
+        """Enqueue the codec decode of one chunk's codes on the codec lanes (asynchronous)."""
+        import os
+        if os.environ.get("FQ3_SERVE_PROFILE") and not getattr(self, "_prof", None):
+            import cProfile
+            self._prof = cProfile.Profile()
+        if getattr(self, "_prof", None):
+            self._prof.enable()
+            try:
+                return self._emit_enqueue_impl(work)
+            finally:
+                self._prof.disable()
+        return self._emit_enqueue_impl(work)
+
+    def _emit_enqueue_impl(self, work: List[tuple]) -> list:
         staged = []
-        for a, chunk, final, reason in work:  # enqueue every utterance's decode first ...
+        for a, chunk, final, reason in work:
             stream = self._lanes[a.slot % len(self._lanes)][0]
+            # pinned staging: a copy from pageable memory first synchronises the lane's stream, i.e. waits for the decode of the
+            # utterance enqueued on that lane just before
+            src = chunk.pin_memory() if stream is not None else chunk
             with self._on(stream):
-                audio, sr = a.window.push(chunk.to(self.eng.device, non_blocking=True))
+                audio, sr = a.window.push(src.to(self.eng.device, non_blocking=True))
             staged.append((stream, audio, sr))
-        for (a, chunk, final, reason), (stream, audio, sr) in zip(work, staged):  # ... then collect
+        return staged
+
+    def _emit_collect(self, work: List[tuple], staged: list):
+        """Audio to the host and out to each request's queue."""
+        for (a, chunk, final, reason), (stream, audio, sr) in zip(work, staged):
             with self._on(stream):
                 wav = self.tts._to_numpy(audio)  # D2H on the lane's stream, synchronises it
             h = a.handle
@@ -332,6 +361,22 @@ class BatchScheduler:
             if final:
                 self._draining.discard(a.slot)
                 self._finish(h, reason)
+
+    def _emit(self, work: List[tuple]):
+        if work:
+            self._emit_collect(work, self._emit_enqueue(work))
+
+    def _lanes_before_main(self):
+        """Make the engine's stream wait for everything enqueued on the codec lanes: the next frame-loop launch then starts when
+        the codec is done (no contention on the GPU) while the host is already free to collect the audio."""
+        if torch.device(self.eng.device).type != "cuda":
+            return
+        main = torch.cuda.current_stream(self.eng.device)
+        for stream, _ in self._lanes:
+            if stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                main.wait_event(ev)
 
     def _run(self):
         eng = self.eng
@@ -356,15 +401,28 @@ class BatchScheduler:
                         self._wake.wait(timeout=0.05)
                         self._wake.clear()
                         continue
-                    if not self.overlap_codec:  # codec of the previous chunk on the idle GPU, before the next launch
+                    staged = None
+                    mode = self.overlap_codec
+                    if mode == "auto":
+                        mode = "gpu" if len(backlog) <= 2 else "host"
+                    if mode == "none":  # codec of the previous chunk before the next launch, host waits for it
                         self._emit(backlog)
                         backlog = []
+                    elif mode == "host" and backlog:  # GPU: codec, then frame loop; host: collects beside the frame loop
+                        staged = self._emit_enqueue(backlog)
+                        tq = time.perf_counter()
+                        self._lanes_before_main()
+                        self.stats["t_enqueue"] = self.stats.get("t_enqueue", 0.0) + tq - t1
+                        self.stats["t_fence"] = self.stats.get("t_fence", 0.0) + time.perf_counter() - tq
                     hi = max(self._active) + 1
                     eng.decode_frames(hi, self.chunk_frames, self._policy(self._cohort), self.tts.predictor_graph.policy())
                     t2 = time.perf_counter()
                     self.stats["launches"] += 1
                     self.stats["max_batch"] = max(self.stats["max_batch"], len(self._active))
-                    self._emit(backlog)  # previous chunk's audio while this one decodes
+                    if staged is not None:
+                        self._emit_collect(backlog, staged)
+                    else:
+                        self._emit(backlog)  # "gpu": previous chunk's codec on the SMs the running launch leaves free
                     backlog = []
                     t3 = time.perf_counter()
                     self.stats["t_launch"] += t2 - t1
@@ -404,6 +462,9 @@ class BatchScheduler:
                 for cs in self._cstreams.values():
                     cs.close()
                 self._cstreams.clear()
+                if getattr(self, "_prof", None):
+                    import pstats
+                    pstats.Stats(self._prof).sort_stats("cumulative").print_stats(18)
         except BaseException as e:  # surface a scheduler failure to every waiter instead of hanging them
             logger.exception("fq3 scheduler stopped")
             for a in list(self._active.values()):

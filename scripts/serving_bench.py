@@ -22,7 +22,7 @@ ap.add_argument("--rate", type=float, default=0.0)
 ap.add_argument("--chunk", type=int, default=8)
 ap.add_argument("--lanes", type=int, default=4)
 ap.add_argument("--codec", default="auto")
-ap.add_argument("--overlap", type=int, default=1)
+ap.add_argument("--overlap", default="auto", help="auto | host | gpu | none")
 ap.add_argument("--emit-every", type=int, default=1, dest="emit_every")
 args = ap.parse_args()
 
@@ -33,7 +33,7 @@ texts = [bench.TEXT + f" Request number {i}." for i in range(max(args.requests, 
 
 def run(n_req, rate):
     handles, done = [], []
-    with BatchScheduler(model, chunk_frames=args.chunk, max_concurrent=args.concurrent, codec_lanes=args.lanes, codec_mode=args.codec, overlap_codec=bool(args.overlap), emit_every=args.emit_every) as sched:
+    with BatchScheduler(model, chunk_frames=args.chunk, max_concurrent=args.concurrent, codec_lanes=args.lanes, codec_mode=args.codec, overlap_codec=args.overlap, emit_every=args.emit_every) as sched:
         def consume(h):
             a, sr = h.result()
             done.append((h, len(a) / sr))
@@ -55,7 +55,7 @@ def run(n_req, rate):
     ttfa = np.array([h.ttfa_s for h, _ in done]) * 1000
     lat = np.array([h.t_done - h.t_submit for h, _ in done]) * 1000
     audio = sum(s for _, s in done)
-    return {"requests": n_req, "rate_per_s": rate, "concurrent": args.concurrent, "frames": args.frames, "chunk_frames": args.chunk, "codec_lanes": args.lanes, "codec_mode": sched.codec_mode, "overlap_codec": bool(args.overlap), "emit_every": args.emit_every,
+    return {"requests": n_req, "rate_per_s": rate, "concurrent": args.concurrent, "frames": args.frames, "chunk_frames": args.chunk, "codec_lanes": args.lanes, "codec_mode": sched.codec_mode, "overlap_codec": args.overlap, "emit_every": args.emit_every,
             "audio_s_per_s": round(audio / dt, 1), "seconds": round(dt, 3),
             "ttfa_ms": {"mean": round(float(ttfa.mean()), 1), "p50": round(float(np.percentile(ttfa, 50)), 1), "p95": round(float(np.percentile(ttfa, 95)), 1)},
             "latency_ms": {"mean": round(float(lat.mean()), 1), "p95": round(float(np.percentile(lat, 95)), 1)},

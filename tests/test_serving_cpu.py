@@ -127,7 +127,7 @@ def _audio_ok(h, n):
     assert codes.shape == (n, 16) and torch.equal(codes[:, 1], torch.arange(n)) and int(codes[0, 0]) == h.id_key
 
 
-@pytest.mark.parametrize("mode,overlap", [("windowed", True), ("windowed", False), ("stateful", True)])
+@pytest.mark.parametrize("mode,overlap", [("windowed", "auto"), ("windowed", "host"), ("windowed", "gpu"), ("windowed", "none"), ("stateful", "host")])
 def test_more_requests_than_slots_all_complete_in_shared_launches(mode, overlap):
     eng = FakeEngine(max_streams=4)
     tts = FakeTTS(eng)
