@@ -459,17 +459,21 @@ def main():
                                   for i in range(n_req)]
                             ths = [threading.Thread(target=lambda h=h: got.append(len(h.result()[0]) / model_b.sample_rate)) for h in hs]
                             for th in ths:
+                                th.daemon = True
                                 th.start()
+                            deadline = time.perf_counter() + 180.0
                             for th in ths:
-                                th.join()
+                                th.join(max(0.0, deadline - time.perf_counter()))
+                            if any(th.is_alive() for th in ths):
+                                raise TimeoutError("serving leg did not finish within 180 s")
                             dt = time.perf_counter() - t0
                         return sum(got) / dt, [h.ttfa_s for h in hs if h.ttfa_s is not None]
                     serve(4)
                     v, ttfas = serve(args.serving_requests)
                     line["serving"] = {"value": v, "unit": UNIT, "requests": args.serving_requests, "concurrent": conc, "chunk_frames": args.chunk,
                                        "ttfa_ms_first_wave_mean": 1000.0 * float(np.mean(sorted(ttfas)[:conc])) if ttfas else None,
-                                       "what": "serving.BatchScheduler (continuous batching, windowed streaming codec per utterance, codec lanes "
-                                               "beside the next launch): all requests submitted at once, audio streamed back per chunk"}
+                                       "what": "serving.BatchScheduler (continuous batching, windowed streaming codec per utterance on four codec lanes, "
+                                               "host work beside the next launch): all requests submitted at once, audio streamed back per chunk"}
                 except Exception as ex:  # a reported extra: never fail the bench on it
                     line["serving"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
             model_b.model.engine.close()
