@@ -321,19 +321,6 @@ class BatchScheduler:
 
     def _emit_enqueue(self, work: List[tuple]) -> list:
         """Enqueue the codec decode of one chunk's codes on the codec lanes (asynchronous)."""
-        import os
-        if os.environ.get("FQ3_SERVE_PROFILE") and not getattr(self, "_prof", None):
-            import cProfile
-            self._prof = cProfile.Profile()
-        if getattr(self, "_prof", None):
-            self._prof.enable()
-            try:
-                return self._emit_enqueue_impl(work)
-            finally:
-                self._prof.disable()
-        return self._emit_enqueue_impl(work)
-
-    def _emit_enqueue_impl(self, work: List[tuple]) -> list:
         staged = []
         for a, chunk, final, reason in work:
             stream = self._lanes[a.slot % len(self._lanes)][0]
@@ -462,9 +449,7 @@ class BatchScheduler:
                 for cs in self._cstreams.values():
                     cs.close()
                 self._cstreams.clear()
-                if getattr(self, "_prof", None):
-                    import pstats
-                    pstats.Stats(self._prof).sort_stats("cumulative").print_stats(18)
+
         except BaseException as e:  # surface a scheduler failure to every waiter instead of hanging them
             logger.exception("fq3 scheduler stopped")
             for a in list(self._active.values()):
