@@ -248,6 +248,7 @@ class BatchScheduler:
                 waiting.append(self._pending.get_nowait())
             except queue.Empty:
                 break
+        blocked = False  # FIFO: once a request waits for another policy's cohort to drain, nothing behind it overtakes it
         for h in waiting:
             if h.cancelled:
                 self._finish(h, "cancelled")
@@ -256,7 +257,8 @@ class BatchScheduler:
             if self._cohort is None and not self._active:
                 self._cohort = key
             free = [s for s in range(self.max_concurrent) if s not in self._active and s not in self._draining]
-            if key != self._cohort or not free:
+            if blocked or key != self._cohort or not free:
+                blocked = blocked or key != self._cohort
                 self._deferred.append(h)
                 continue
             slot = free[0]
@@ -269,6 +271,10 @@ class BatchScheduler:
                 self.eng.set_text_conditioning(slot, tth[0], tpe)
                 self.eng.prefill(slot, tie[0], _left_pads(tam), self._policy(key))
             except Exception as e:  # a bad request must not take the loop down
+                try:
+                    self.eng.retire_stream(slot)  # whatever the failed prefill left in the slot must not decode
+                except Exception:
+                    pass
                 h.q.put(e)
                 self._finish(h, "error")
                 continue
@@ -446,6 +452,20 @@ class BatchScheduler:
                             del self._active[slot]
                     self.stats["t_wait"] += time.perf_counter() - t3
                 self._emit(backlog)
+                for a in list(self._active.values()):  # stop() in mid-utterance: nobody may wait for ever
+                    if a.handle.finish_reason is None:
+                        self._finish(a.handle, "shutdown")
+                    eng.retire_stream(a.slot)
+                self._active.clear()
+                leftover = list(self._deferred)
+                self._deferred = []
+                while True:
+                    try:
+                        leftover.append(self._pending.get_nowait())
+                    except queue.Empty:
+                        break
+                for h in leftover:
+                    self._finish(h, "shutdown")
                 for cs in self._cstreams.values():
                     cs.close()
                 self._cstreams.clear()

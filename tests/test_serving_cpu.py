@@ -220,3 +220,25 @@ def test_emit_every_hands_out_the_first_chunk_at_once_then_pairs():
         h.id_key = 7
         sizes = [len(a) // SPF for a, _, _ in h]
     assert sizes[0] == 8 and sum(sizes) == 45 and all(s in (16, 13, 5) or s == 8 for s in sizes[1:]) and len(sizes) <= 4
+
+
+def test_a_waiting_policy_is_not_starved_and_stop_releases_everyone():
+    eng = FakeEngine(max_streams=2, frame_sleep=0.001)
+    tts = FakeTTS(eng)
+    sched = BatchScheduler(tts, chunk_frames=8).start()
+    first = sched.submit(_req(1, 64))
+    other = sched.submit(TTSRequest(f"2,{10 ** 9}", ref_audio="v.wav", language="English", max_new_tokens=16, temperature=0.5))
+    behind = [sched.submit(_req(10 + i, 16)) for i in range(3)]  # same policy as `first`, but they arrived after `other`
+    other.id_key = 2
+    _audio_ok(other, 16)
+    first_other = [pol for pol, _, _ in eng.launches].index((True, 50, 0.5))
+    # the cohort of `first` drained before `other` ran, and none of the later same-policy requests was admitted before it
+    assert all(len(live) <= 1 for pol, live, _ in eng.launches[:first_other])
+    endless = sched.submit(_req(99, 10 ** 6))
+    it = iter(endless)
+    next(it)
+    sched.stop()
+    list(it)  # returns: the scheduler released the request on shutdown
+    assert endless.finish_reason in ("shutdown", "length")
+    for i, h in enumerate(behind):
+        assert h.finish_reason in ("length", "shutdown")
