@@ -67,6 +67,14 @@ typedef struct fq3c_op {
   int64_t ws_bytes;      /* NULL / 0 = never split.  Ops of one stream-ordered list may share it.                                  */
   int32_t m_begin;       /* GEMM: only output rows [m_begin, M) are computed (tail-only streaming decode); pointers stay at row 0 */
   int32_t reserved;
+  /* GEMM, optional (ABI 5): the RMSNorm that reads the finished output rows, fused behind the epilogue — a decoder layer's norm
+   * reads exactly the residual stream its o / down projection just wrote.  norm_out bf16 [M, norm_ld] = FQ3C_RMSNORM(C rows)
+   * with weights norm_w (f32 [N]) and eps norm_eps, same arithmetic and summation order as the stand-alone op.  With split-K it
+   * runs inside the reduction kernel (one CTA per row), otherwise as one more launch.  Not with FQ3C_SWIGLU / FQ3C_OUT_F32. */
+  void* norm_out;
+  const void* norm_w;
+  int32_t norm_ld;
+  float norm_eps;
 } fq3c_op;
 
 int fq3c_abi_version(void);

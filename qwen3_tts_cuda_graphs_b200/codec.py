@@ -43,6 +43,7 @@ class Op(C.Structure):
         ("A", C.c_void_p), ("B", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("scale", C.c_void_p),
         ("p0", C.c_void_p), ("p1", C.c_void_p), ("C", C.c_void_p), ("C2", C.c_void_p),
         ("ws", C.c_void_p), ("ws_bytes", C.c_int64), ("m_begin", C.c_int32), ("reserved", C.c_int32),
+        ("norm_out", C.c_void_p), ("norm_w", C.c_void_p), ("norm_ld", C.c_int32), ("norm_eps", C.c_float),
     ]
 
 
@@ -77,6 +78,23 @@ def vocoder_tail_starts(rows0: int, upsample_rates, skip: int, trim: str = "both
         tconv_begin[i] = max(0, s_need) // upsample_rates[i]
         s_need = tconv_begin[i] - (1 if right else 0)
     return max(0, s_need), tconv_begin, unit_begin, fin_begin
+
+
+def fuse_row_norms(ops: list) -> list:
+    """An RMSNORM op that reads exactly the rows the GEMM before it wrote becomes that GEMM's fused norm (fq3c_op.norm_out):
+    inside the split-K reduction when the GEMM is split, one small launch otherwise — same arithmetic, fewer launches (two per
+    transformer layer of the prompt prefill and of the codec).  FQ3C_FUSE_NORM=0 keeps the ops apart."""
+    if os.environ.get("FQ3C_FUSE_NORM", "1") == "0":
+        return ops
+    out = []
+    for o in ops:
+        g = out[-1] if out else None
+        if (o.kind == K_RMSNORM and g is not None and g.kind == K_GEMM and not (g.flags & (F_SWIGLU | F_OUT_F32)) and not g.norm_out
+                and g.m_begin == 0 and o.A == g.C and o.lda == g.ldc and o.N == g.N and o.M == g.M and o.a_rows == g.M):
+            g.norm_out, g.norm_w, g.norm_ld, g.norm_eps = o.C, o.scale, o.ldc, o.f0
+            continue
+        out.append(o)
+    return out
 
 
 def attach_splitk_workspace(ops, device, keep) -> None:
@@ -123,7 +141,7 @@ def load_lib():
     lib.fq3c_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
     lib.fq3c_graph_destroy.restype = C.c_int
     lib.fq3c_graph_destroy.argtypes = [C.c_void_p]
-    if lib.fq3c_abi_version() != 4:
+    if lib.fq3c_abi_version() != 5:
         raise CodecError("libfq3codec.so ABI version mismatch")
     _lib = lib
     return lib
@@ -446,6 +464,7 @@ class CodecDecoder:
         self._gemm(plan, xs, g["final.w"], rows, 1, out_dim, taps=7, tap_off=[j - 6 for j in range(7)], bias=g["final.b"],
                    flags=F_CLAMP, out=plan.wav, out_f32=True, m_begin=fin_begin)
         plan.n_samples = rows
+        plan.ops = fuse_row_norms(plan.ops)
         if os.environ.get("FQ3C_SPLITK", "1") != "0":
             attach_splitk_workspace(plan.ops, self.device, plan.keep)
         plan.arr = (Op * len(plan.ops))(*plan.ops)
@@ -659,6 +678,7 @@ class CodecStream:
         adv = Op()
         adv.kind, adv.M, adv.N, adv.i0, adv.C = K_ADVANCE, 1, 1, T, self.pos.data_ptr()
         plan.ops.append(adv)
+        plan.ops = fuse_row_norms(plan.ops)
         if self.split_k:
             attach_splitk_workspace(plan.ops, self.device, plan.keep)
         plan.arr = (Op * len(plan.ops))(*plan.ops)

@@ -547,6 +547,43 @@ __global__ void fq3c_rmsnorm_kernel(const fq3c_op o) {
     y[c] = __float2bfloat16_rn(bf16r(bf16r(__bfloat162float(x[c]) * rs) * w[c]));
 }
 
+// RMSNorm of the rows a GEMM just finished (fq3c_op.norm_out), with the arithmetic of fq3c_rmsnorm_kernel: same column-strided
+// partial sums, same block tree, same rounding points — the fused form changes the launch count, not a bit of the result.
+__device__ __forceinline__ void row_rmsnorm(const fq3c_op& o, int row, float* red) {
+  const bf16* x = reinterpret_cast<const bf16*>(o.C) + (size_t)row * o.ldc;
+  bf16* y = reinterpret_cast<bf16*>(o.norm_out) + (size_t)row * o.norm_ld;
+  const float* w = reinterpret_cast<const float*>(o.norm_w);
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < o.N; c += blockDim.x) { const float v = __bfloat162float(x[c]); ss += v * v; }
+  ss = block_sum(ss, red);
+  const float rs = rsqrtf(ss / o.N + o.norm_eps);
+  for (int c = threadIdx.x; c < o.N; c += blockDim.x)
+    y[c] = __float2bfloat16_rn(bf16r(bf16r(__bfloat162float(x[c]) * rs) * w[c]));
+}
+__global__ void __launch_bounds__(256) fq3c_rownorm_kernel(const fq3c_op o) {
+  __shared__ float red[32];
+  row_rmsnorm(o, o.m_begin + blockIdx.x, red);
+}
+// split-K reduction + epilogue + RMSNorm, one CTA per output row: the row's eight-column groups are reduced and written by
+// their threads, then the whole CTA reads the finished row back (it is in L1 / L2) for the norm
+__global__ void __launch_bounds__(256) fq3c_splitk_reduce_norm_kernel(const fq3c_op o, const int splits, const int Nw) {
+  __shared__ float red[32];
+  const int row = o.m_begin + blockIdx.x;
+  const float* ws = reinterpret_cast<const float*>(o.ws);
+  for (int col = threadIdx.x * 8; col < Nw; col += blockDim.x * 8) {
+    float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int z = 0; z < splits; ++z) {
+      const float4* src = reinterpret_cast<const float4*>(ws + ((size_t)z * o.M + row) * Nw + col);
+      const float4 v0 = src[0], v1 = src[1];
+      a8[0] += v0.x; a8[1] += v0.y; a8[2] += v0.z; a8[3] += v0.w;
+      a8[4] += v1.x; a8[5] += v1.y; a8[6] += v1.z; a8[7] += v1.w;
+    }
+    epilogue_row8(o, row, col, a8);
+  }
+  __syncthreads();  // the row's global writes are visible to the whole block behind the barrier
+  row_rmsnorm(o, row, red);
+}
+
 __global__ void fq3c_layernorm_kernel(const fq3c_op o) {
   __shared__ float red[32];
   const bf16* x = reinterpret_cast<const bf16*>(o.A) + (size_t)blockIdx.x * o.lda;
@@ -814,7 +851,7 @@ bool make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, u
 
 extern "C" {
 
-int fq3c_abi_version(void) { return 4; }
+int fq3c_abi_version(void) { return 5; }
 const char* fq3c_last_error(void) { return g_err.c_str(); }
 int64_t fq3c_launch_count(void) { return g_launches; }
 
@@ -827,6 +864,8 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
       case FQ3C_GEMM: {
         if (o.K % 8 || o.cin % 8 || o.taps > 8 || o.col_mod <= 0) return fail("gemm: K and cin must be multiples of 8, taps <= 8");
         if (o.m_begin < 0 || o.m_begin >= o.M) return fail("gemm: m_begin outside [0, M)");
+        if (o.norm_out && ((o.flags & (FQ3C_SWIGLU | FQ3C_OUT_F32)) || !o.norm_w || o.norm_ld < o.N))
+          return fail("gemm: a fused RMSNorm needs a bf16 [M, N] output, weights and norm_ld >= N");
         static int use_tc5 = -1;
         if (use_tc5 < 0) {
           const char* e = getenv("FQ3C_TCGEN05");
@@ -894,14 +933,25 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
             else fq3c_gemm_tc5_kernel<1, false><<<grid, TTHREADS, T_SMEM, s>>>(o, bn, splits, Nw, TSTAGES, tmA, tmB);
           }
           if (splits > 1) {
-            const long n = (long)(o.M - o.m_begin) * (Nw >> 3);
-            fq3c_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o, splits, Nw);
+            if (o.norm_out) {
+              fq3c_splitk_reduce_norm_kernel<<<(unsigned)(o.M - o.m_begin), 256, 0, s>>>(o, splits, Nw);
+            } else {
+              const long n = (long)(o.M - o.m_begin) * (Nw >> 3);
+              fq3c_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o, splits, Nw);
+            }
+            g_launches += 1;
+          } else if (o.norm_out) {
+            fq3c_rownorm_kernel<<<(unsigned)(o.M - o.m_begin), 256, 0, s>>>(o);
             g_launches += 1;
           }
           break;
         }
         dim3 grid((o.N + BN - 1) / BN, (o.M - o.m_begin + BM - 1) / BM);
         fq3c_gemm_kernel<<<grid, 128, 0, s>>>(o);
+        if (o.norm_out) {
+          fq3c_rownorm_kernel<<<(unsigned)(o.M - o.m_begin), 256, 0, s>>>(o);
+          g_launches += 1;
+        }
         break;
       }
       case FQ3C_RVQ: fq3c_rvq_kernel<<<o.M, 128, 0, s>>>(o); break;

@@ -122,6 +122,7 @@ class DensePrefill:
         for h in self.graphs.values():
             self.lib.fq3c_graph_destroy(h)
         self.graphs, self.seen = {}, {}
+        ops = _codec.fuse_row_norms(ops)
         if os.environ.get("FQ3C_SPLITK", "1") != "0":
             _codec.attach_splitk_workspace(ops, dev, self.keep)
         self.x_last = x[cur]  # full mode: the residual stream after the last layer

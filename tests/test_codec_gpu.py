@@ -260,14 +260,15 @@ def test_transformer_block_on_device_matches_oracle(tiny):
     ref = orc.transformer(x.permute(0, 2, 1))[0]
     plan = dec._build(T)
     plan.codes.copy_(codes)
-    n_prefix = 3 + 8 * cfg.num_hidden_layers + 1
     from qwen3_tts_cuda_graphs_b200.codec import Op
+    fused = [i for i, o in enumerate(plan.ops) if o.norm_out]  # RMSNorms ride on the GEMM before them (codec.fuse_row_norms)
+    n_prefix = fused[-1] + 1 if fused else 3 + 8 * cfg.num_hidden_layers + 1
+    if fused:
+        assert len(fused) == 2 * cfg.num_hidden_layers + 1 and n_prefix == 3 + 6 * cfg.num_hidden_layers
     plan.arr = (Op * n_prefix)(*plan.ops[:n_prefix])
     plan.ops = plan.ops[:n_prefix]
     dec.run_plan(plan)
-    got = torch.empty(T, cfg.hidden_size, dtype=torch.bfloat16, device="cuda")
-    import ctypes
-    src = plan.ops[-1].C
+    src = plan.ops[-1].norm_out if fused else plan.ops[-1].C  # the final norm's output
     got = next(t for t in plan.keep if t.data_ptr() == src)
     assert _rel(got, ref) <= 0.03
 
@@ -320,3 +321,19 @@ def test_stateful_stream_needs_causal_trim():
     cfg, dec, _ = make("tiny", trim="both")
     with pytest.raises(ValueError):
         dec.open_stream(8)
+
+
+@pytest.mark.parametrize("name,T", [("tiny", 21), ("0.6B-Base", 33)])
+def test_fused_row_norm_decode_is_bit_identical(monkeypatch, name, T):
+    """codec.fuse_row_norms: the transformer's RMSNorms as the fused norm of the GEMM before them (inside the split-K reduction
+    where the GEMM is split): two launches fewer per layer + the final norm, the waveform identical bit for bit."""
+    codes = torch.randint(0, 2048, (T, 16), generator=torch.Generator().manual_seed(T)).cuda()
+    cfg, dec, _ = make(name, seed=8)
+    a = dec.decode(codes)
+    n_fused = len(dec._plans[T].ops)
+    assert sum(1 for o in dec._plans[T].ops if o.norm_out) == 2 * cfg.num_hidden_layers + 1
+    monkeypatch.setenv("FQ3C_FUSE_NORM", "0")
+    _, dec2, _ = make(name, seed=8)
+    b = dec2.decode(codes)
+    assert len(dec2._plans[T].ops) == n_fused + 2 * cfg.num_hidden_layers + 1
+    assert torch.equal(a, b)

@@ -550,6 +550,36 @@ def test_dense_prefill_matches_chunked_prefill(pair, T, monkeypatch):
     eng._dense, eng._dense_tried = None, False
 
 
+@pytest.mark.parametrize("T", [40, 240])
+def test_dense_prefill_fused_row_norm_is_bit_identical(pair, T, monkeypatch):
+    """fq3c_op.norm_out: the RMSNorm behind an o / down projection runs inside the split-K reduction (or as one small launch)
+    with the arithmetic of the stand-alone op — logits, first token and the next step's hidden state do not change by a bit,
+    the op list loses two launches per layer."""
+    cfg, w, eng, orc = pair
+    if T >= eng.max_seq_len:
+        pytest.skip("prompt longer than this fixture's cache")
+    tie, tam, tth, tpe = synth_prompt(cfg, T=T, seed=6)
+    pol = _sp(do_sample=False, repetition_penalty=1.0, min_new_tokens=2)
+    xg = (0.05 * torch.randn(1, 1, cfg.talker.hidden_size, generator=torch.Generator().manual_seed(10))).to(torch.bfloat16)
+    out, n_ops = {}, {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("FQ3C_FUSE_NORM", fuse)
+        if eng._dense is not None:
+            eng._dense.close()
+        eng._dense, eng._dense_tried = None, False
+        eng.set_text_conditioning(0, tth[0].cuda(), tpe.cuda())
+        lg = eng.prefill(0, tie[0].cuda(), 0, pol, want_logits=True, dense=True)
+        tok = eng.status(0).token
+        h, _ = eng.talker_step(0, xg.cuda(), T)
+        torch.cuda.synchronize()
+        out[fuse], n_ops[fuse] = (lg.cpu(), tok, h.cpu()), len(eng._dense.ops)
+    assert n_ops["0"] - n_ops["1"] == 2 * cfg.talker.num_hidden_layers - 1  # every norm but the first rides on a GEMM
+    assert torch.equal(out["1"][0], out["0"][0]) and out["1"][1] == out["0"][1] and torch.equal(out["1"][2], out["0"][2])
+    monkeypatch.delenv("FQ3C_FUSE_NORM")
+    eng._dense.close()
+    eng._dense, eng._dense_tried = None, False
+
+
 # ------------------------------------------------------------------------------------------------
 # long contexts: split-KV attention (48 positions per CTA) with the combine step, up to ten splits
 # ------------------------------------------------------------------------------------------------
