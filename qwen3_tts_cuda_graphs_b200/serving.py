@@ -178,6 +178,7 @@ class BatchScheduler:
         self._stop = threading.Event()
         self._wake = threading.Event()
         self._next_id = 0
+        self._submit_lock = threading.Lock()  # submit() is the one method other threads call
         self._lanes: List[tuple] = []  # (CUDA stream, speech tokenizer with its own launch plans) per codec lane
         # seconds per part of the loop: admit (prompt build + prefill), launch (host side of fq3_decode_frames), emit (codec lanes +
         # D2H + hand-out of the previous chunk), wait (blocked on the running launch)
@@ -206,8 +207,9 @@ class BatchScheduler:
     def submit(self, req: TTSRequest) -> RequestHandle:
         if req.kind not in ("voice_clone", "custom_voice", "voice_design"):
             raise ValueError(f"unknown request kind {req.kind!r}")
-        h = RequestHandle(req, self._next_id)
-        self._next_id += 1
+        with self._submit_lock:
+            h = RequestHandle(req, self._next_id)
+            self._next_id += 1
         h._sr = self.tts.sample_rate
         self._pending.put(h)
         self._wake.set()
