@@ -26,7 +26,10 @@ enum fq3c_kind {
                          m + *p0 when p0 (device int32) is given (stateful decode), else m                       */
   FQ3C_ATTN = 4,      /* A=qkv [M, lda] (q | k | v), i0 heads, i1 kv heads, i2 head_dim, window K; C[M, i0*i2].  Stateful
                          decode: A holds `taps` history rows in front of the M query rows (query m = row taps + m), of
-                         which the last min(*p0, taps) are valid (p0 = device int32: positions decoded so far)       */
+                         which the last min(*p0, taps) are valid (p0 = device int32: positions decoded so far).
+                         flags bit 0 (ABI 5): prompt-prefill form — head_dim 128, no history rows, M <= 2048: a two-phase
+                         kernel (lanes over keys for the scores, lanes over dims for the output) with the same rounding
+                         points; fp32 sums in another order                                                           */
   FQ3C_DWCONV = 5,    /* depthwise causal conv k=taps: C[m,c] = bias[c] + sum_j B(f32)[c,j] A[m-(taps-1)+j, c]; rows down
                          to -i0 in front of A are history rows (stateful decode), further back reads as zero        */
   FQ3C_LAYERNORM = 6, /* C = layernorm(A) * scale + bias (f32), eps=f0                                      */

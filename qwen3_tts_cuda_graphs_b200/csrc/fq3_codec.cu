@@ -729,6 +729,115 @@ __global__ void fq3c_attn_kernel(const fq3c_op o) {
   else attn_warp_generic(o, t, h, lane);
 }
 
+// Causal attention of the dense prompt prefill (FQ3C_ATTN with flags bit 0: head_dim 128, no history rows, window >= M, M <= 2048):
+// one warp per (query, head), two phases with different lane roles instead of the key-by-key online softmax above —
+//   1. four lanes per KEY, eight keys per step: a lane multiplies 32 dims of its key (q from shared memory, four 16-byte loads of the
+//      key row), two shuffles finish the dot product (against five per key in the kernel above); the score, rounded to bf16 exactly
+//      where the kernel above rounds it, goes to shared memory, and after the warp's max is known the same lane replaces it by
+//      p = exp(score - max) — once per key, not once per key and lane;
+//   2. lanes take DIMS (four each): every lane walks the keys in order, p straight from shared memory, and accumulates l and its
+//      four output dims — no rescaling, no shuffles.
+// Same rounding points as attn_warp (score -> bf16 -> x scale -> bf16; fp32 softmax and accumulation; bf16 output); the fp32 sums run in
+// another order, which the prefill tests bound against the oracle and the chunked prefill.  M = 240 (ICL prompt): 78 -> ~12 us per layer.
+constexpr int APF_WARPS = 8;
+__global__ void __launch_bounds__(APF_WARPS * 32) fq3c_attn_prefill_kernel(const fq3c_op o, const int tpad) {
+  extern __shared__ unsigned char apf_smem[];
+  const int nh = o.i0, nkv = o.i1, T = o.M, win = o.K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // heavy queries (many keys) first: the grid's tail then consists of the short ones.  (Warps of a CTA = the heads of one query;
+  // consecutive queries of one head per CTA was measured: slower, 99 vs 66 us at M = 240.)
+  const int gw = blockIdx.x * APF_WARPS + warp;
+  if (gw >= T * nh) return;
+  const int t = T - 1 - gw / nh, h = gw - (gw / nh) * nh;
+  const int kvh = h / (nh / nkv);
+  float* qs = reinterpret_cast<float*>(apf_smem) + warp * 128;
+  float* sc = reinterpret_cast<float*>(apf_smem + APF_WARPS * 128 * 4) + (size_t)warp * tpad;
+  const bf16* base = reinterpret_cast<const bf16*>(o.A);
+  const size_t lda = (size_t)o.lda;
+  const int koff = nh * 128 + kvh * 128, voff = (nh + nkv) * 128 + kvh * 128;
+  {
+    const uint2 r = *reinterpret_cast<const uint2*>(base + (size_t)t * lda + h * 128 + lane * 4);
+    *reinterpret_cast<float4*>(qs + lane * 4) = make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u),
+                                                            __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+  }
+  __syncwarp();
+  const float scale = rsqrtf(128.f);
+  const int j0 = max(0, t - win + 1);
+  float mx = -INFINITY;
+  // four lanes per key, eight keys per step: the four lanes of a key read 64 contiguous bytes per load instruction (a warp-wide
+  // load touches 8 lines; one lane per key would touch 32 and the L1 tag stage, one line per cycle, becomes the bound: measured)
+  const int sub = lane & 3, kq = lane >> 2;
+  for (int jb = j0; jb <= t; jb += 16) {  // two groups of eight keys per step: sixteen rows in flight per L2 round trip
+    uint4 kk[2][4];
+    bool ok[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int j = jb + g * 8 + kq;
+      ok[g] = j <= t;
+      const uint4* kr = reinterpret_cast<const uint4*>(base + (size_t)(ok[g] ? j : t) * lda + koff) + sub;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) kk[g][c] = kr[c * 4];
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float* qp = qs + (c * 4 + sub) * 8;
+        const float4 qa = *reinterpret_cast<const float4*>(qp), qb = *reinterpret_cast<const float4*>(qp + 4);
+        d0 += qa.x * __uint_as_float(kk[g][c].x << 16) + qa.y * __uint_as_float(kk[g][c].x & 0xffff0000u) +
+              qa.z * __uint_as_float(kk[g][c].y << 16) + qa.w * __uint_as_float(kk[g][c].y & 0xffff0000u);
+        d1 += qb.x * __uint_as_float(kk[g][c].z << 16) + qb.y * __uint_as_float(kk[g][c].z & 0xffff0000u) +
+              qb.z * __uint_as_float(kk[g][c].w << 16) + qb.w * __uint_as_float(kk[g][c].w & 0xffff0000u);
+      }
+      float dsum = d0 + d1;
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+      const float su = bf16r(bf16r(dsum) * scale);
+      if (ok[g]) {
+        if (sub == 0) sc[jb + g * 8 + kq - j0] = su;
+        mx = fmaxf(mx, su);
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  // the exponentials once per key (the lane that scored it), not once per key and lane: expf is ~20 instructions
+  for (int j = j0 + lane; j <= t; j += 32) sc[j - j0] = expf(sc[j - j0] - mx);
+  __syncwarp();
+  float l = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bf16* vp = base + voff + lane * 4;
+  int j = j0;
+  // sixteen keys per step: the step is one L2 round trip (the V rows of a prompt are not in L1), so all sixteen loads go out before
+  // the first one is used; the accumulation itself stays in key order
+  for (; j + 15 <= t; j += 16) {
+    uint2 r[16];
+    float pr[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) r[u] = *reinterpret_cast<const uint2*>(vp + (size_t)(j + u) * lda);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) pr[u] = sc[j + u - j0];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      l += pr[u];
+      acc[0] += pr[u] * __uint_as_float(r[u].x << 16); acc[1] += pr[u] * __uint_as_float(r[u].x & 0xffff0000u);
+      acc[2] += pr[u] * __uint_as_float(r[u].y << 16); acc[3] += pr[u] * __uint_as_float(r[u].y & 0xffff0000u);
+    }
+  }
+  for (; j <= t; ++j) {
+    const uint2 r0 = *reinterpret_cast<const uint2*>(vp + (size_t)j * lda);
+    const float p0 = sc[j - j0];
+    l += p0;
+    acc[0] += p0 * __uint_as_float(r0.x << 16); acc[1] += p0 * __uint_as_float(r0.x & 0xffff0000u);
+    acc[2] += p0 * __uint_as_float(r0.y << 16); acc[3] += p0 * __uint_as_float(r0.y & 0xffff0000u);
+  }
+  bf16* out = reinterpret_cast<bf16*>(o.C) + (size_t)t * o.ldc + h * 128 + lane * 4;
+  const float inv = 1.f / l;
+  uint2 w;
+  w.x = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[0] * inv)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[1] * inv)) << 16);
+  w.y = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[2] * inv)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(acc[3] * inv)) << 16);
+  *reinterpret_cast<uint2*>(out) = w;
+}
+
 // Dense prefill helper (talker): one warp per (row, head) of the fused qkv rows A [M, lda] = (q heads | k heads | v heads).
 //   q / k heads: per-head RMSNorm with bf16 gamma (q: p0, k: p1), HF rounding points, then rotary embedding from the bf16
 //                tables B (cos) / bias (sin) at position row + i2 (rotate-half), in place;
@@ -960,6 +1069,22 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
       case FQ3C_ROPE: fq3c_rope_kernel<<<o.M, 256, 0, s>>>(o); break;
       case FQ3C_ATTN: {
         if (o.i2 > 128) return fail("attn: head_dim > 128");
+        static int use_apf = -1;
+        if (use_apf < 0) { const char* e5 = getenv("FQ3C_ATTN_PREFILL"); use_apf = (e5 == nullptr || atoi(e5) != 0) ? 1 : 0; }
+        if (use_apf && (o.flags & 1) && o.i2 == 128 && o.taps == 0 && !o.p0 && o.M <= 2048 && (o.lda % 8) == 0 && (o.ldc % 4) == 0 &&
+            (o.i0 % o.i1) == 0) {
+          const int tpad = (o.M + 7) & ~7;
+          const size_t smem = (size_t)APF_WARPS * 128 * 4 + (size_t)APF_WARPS * tpad * 4;
+          static bool apf_attr = false;
+          if (!apf_attr) {
+            if (cudaFuncSetAttribute(fq3c_attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APF_WARPS * (128 + 2048) * 4) != cudaSuccess)
+              return fail("cannot reserve shared memory for the prefill attention");
+            apf_attr = true;
+          }
+          const int warps = o.M * o.i0;
+          fq3c_attn_prefill_kernel<<<(warps + APF_WARPS - 1) / APF_WARPS, APF_WARPS * 32, smem, s>>>(o, tpad);
+          break;
+        }
         const int warps = o.M * o.i0;
         fq3c_attn_kernel<<<(warps + 7) / 8, 256, 0, s>>>(o);
         break;

@@ -109,6 +109,7 @@ class DensePrefill:
                 break  # the last row (decode-kernel path) only needs this layer's K/V of the earlier rows
             o = Op()
             o.kind, o.M, o.N = K_ATTN, cap, nq * d
+            o.flags = 1  # fq3_codec.h: the prompt-prefill form of FQ3C_ATTN (two-phase kernel; no history rows, head_dim 128)
             o.A, o.lda, o.a_rows = qkv.data_ptr(), Q, cap
             o.C, o.ldc, o.col_mod = att.data_ptr(), nq * d, nq * d
             o.i0, o.i1, o.i2, o.K = nq, nkv, d, eng.max_seq_len  # window >= T: plain causal attention
