@@ -252,6 +252,8 @@ class _Plan:
 class CodecDecoder:
     """Weights repacked for the implicit-GEMM kernels + per-T launch plans."""
 
+    MAX_LONG_PLANS = 6
+
     def __init__(self, cfg: CodecDecoderConfig, weights: Dict[str, torch.Tensor], device):
         self.cfg = cfg
         self.device = torch.device(device)
@@ -506,13 +508,25 @@ class CodecDecoder:
         key = T if skip == 0 else (T, skip)
         plan = self._plans.get(key)
         if plan is None:
-            # streaming revisits a handful of sizes (chunk multiples, then chunk+25); long one-shot decodes are
-            # not worth pinning gigabytes of activation buffers for
-            for k in [k for k in self._plans if (k[0] if isinstance(k, tuple) else k) > 96 or len(self._plans) >= 24]:
-                old = self._plans.pop(k)
+            # streaming revisits a handful of sizes (chunk multiples, then chunk+25; with an ICL voice also reference + 8 / 16 / 24
+            # frames, the same for every request of that voice).  Plans are kept least-recently-used: at most MAX_LONG_PLANS of more
+            # than 96 frames (a long plan pins ~1 MB of activations per frame), 24 in all.
+            def frames(k):
+                return k[0] if isinstance(k, tuple) else k
+            while True:
+                long_keys = [k for k in self._plans if frames(k) > 96]
+                if len(long_keys) >= self.MAX_LONG_PLANS and T > 96:
+                    victim = long_keys[0]
+                elif len(self._plans) >= 24:
+                    victim = next(iter(self._plans))
+                else:
+                    break
+                old = self._plans.pop(victim)
                 if old.graph is not None:
                     self.lib.fq3c_graph_destroy(old.graph)
             plan = self._plans[key] = self._build(T, skip)
+        else:
+            self._plans[key] = self._plans.pop(key)  # most recently used goes last
         plan.codes.copy_(codes.to(torch.int64), non_blocking=True)
         self.run_plan(plan)
         return plan.wav.view(-1)[: plan.n_samples].clone()

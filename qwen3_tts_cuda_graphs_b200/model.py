@@ -46,7 +46,15 @@ class WindowedDecode:
         n_total = flat.shape[0]
         if self.spf is None:
             codes_in = flat if ref_codes is None else torch.cat([ref_codes.to(flat.device), flat], dim=0)
-            audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0)})
+            skip = 0
+            if ref_codes is not None:
+                # the reference clip's part is cut off proportionally (model.py:788-795); where the decoder's length law is exact
+                # (causal trim: total_upsample samples per frame) the cut is known before the decode, and the vocoder skips what
+                # only those samples can see (CodecDecoder.decode: the kept samples are bit-identical to a full decode)
+                dec = getattr(tok, "decoder", None)
+                if dec is not None and getattr(getattr(dec, "cfg", None), "trans_conv_trim", "") == "right":
+                    skip = int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * dec.n_samples(int(codes_in.shape[0])))
+            audio_list, sr = tok.decode({"audio_codes": codes_in.unsqueeze(0), "skip_samples": skip} if skip else {"audio_codes": codes_in.unsqueeze(0)})
             audio = audio_list[0].flatten()
             if ref_codes is not None:
                 audio = audio[int(ref_codes.shape[0] / max(codes_in.shape[0], 1) * len(audio)):]

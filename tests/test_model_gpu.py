@@ -116,6 +116,26 @@ def test_icl_mode_prepends_ref_codes_and_trims(base, ref_wav):
     assert len(audio[0]) == total - int(n_ref / (n_ref + 10) * total)
 
 
+def test_icl_streaming_skips_the_reference_part_without_changing_a_sample(base, ref_wav, monkeypatch):
+    """While the window policy still accumulates (model.py:737-826) an ICL stream decodes reference + generated frames and throws
+    the reference part away; with the causal length law that cut is known up front and the vocoder only computes what the kept
+    samples can see.  Same samples as with the skip turned off (FQ3C_TAIL_ONLY=0), chunk by chunk."""
+    kw = dict(max_new_tokens=40, do_sample=False, xvec_only=False, chunk_size=8)
+    base.predictor_graph.do_sample = False
+    try:
+        fast = [a for a, _, _ in base.generate_voice_clone_streaming(TEXT, "English", ref_wav, "reference words", **kw)]
+        dec = base.model.model.speech_tokenizer.decoder
+        n_ref = int(round((1.2 + 0.5) * 12.5))
+        assert any(isinstance(k, tuple) and k[0] == n_ref + 8 and k[1] > 0 for k in dec._plans), "the first ICL decode did not skip the reference part"
+        monkeypatch.setenv("FQ3C_TAIL_ONLY", "0")
+        full = [a for a, _, _ in base.generate_voice_clone_streaming(TEXT, "English", ref_wav, "reference words", **kw)]
+    finally:
+        base.predictor_graph.do_sample = True
+    assert [len(a) for a in fast] == [len(a) for a in full] == [8 * 1920] * 5
+    for a, b in zip(fast, full):
+        assert np.array_equal(a, b)
+
+
 def test_prefill_longer_than_cache_raises(base, ref_wav):
     with pytest.raises(RuntimeError, match="Input is too long"):
         base.generate_voice_clone(" ".join(["word"] * 300), "English", ref_wav, "", max_new_tokens=4)
