@@ -414,8 +414,13 @@ class FasterQwen3TTS:
     def _decode_full(self, m, codec_ids, ref_codes=None) -> Tuple[List[np.ndarray], int]:
         """model.py:634-656: prepend ICL ref codes, decode, cut the reference part proportionally."""
         codes = codec_ids if ref_codes is None else torch.cat([ref_codes.to(codec_ids.device), codec_ids], dim=0)
-        audio_list, sr = m.speech_tokenizer.decode({"audio_codes": codes.unsqueeze(0)})
         ref_len = 0 if ref_codes is None else ref_codes.shape[0]
+        inputs = {"audio_codes": codes.unsqueeze(0)}
+        dec = getattr(m.speech_tokenizer, "decoder", None)
+        if ref_len > 0 and dec is not None and getattr(getattr(dec, "cfg", None), "trans_conv_trim", "") == "right":
+            # the samples of the reference part are thrown away below: the vocoder need not compute them (WindowedDecode.push)
+            inputs["skip_samples"] = int(ref_len / max(codes.shape[0], 1) * dec.n_samples(int(codes.shape[0])))
+        audio_list, sr = m.speech_tokenizer.decode(inputs)
         out = []
         for a in audio_list:
             a = self._to_numpy(a)

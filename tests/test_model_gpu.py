@@ -116,6 +116,20 @@ def test_icl_mode_prepends_ref_codes_and_trims(base, ref_wav):
     assert len(audio[0]) == total - int(n_ref / (n_ref + 10) * total)
 
 
+def test_icl_non_streaming_decode_skips_the_reference_part_bit_exactly(base, ref_wav, monkeypatch):
+    """_decode_full (model.py:634-656) cuts the reference clip's samples off; the vocoder does not compute them (skip_samples) and the
+    kept ones do not change by a bit."""
+    base.predictor_graph.do_sample = False
+    try:
+        kw = dict(max_new_tokens=14, do_sample=False, xvec_only=False)
+        fast, _ = base.generate_voice_clone(TEXT, "English", ref_wav, "reference words", **kw)
+        monkeypatch.setenv("FQ3C_TAIL_ONLY", "0")
+        full, _ = base.generate_voice_clone(TEXT, "English", ref_wav, "reference words", **kw)
+    finally:
+        base.predictor_graph.do_sample = True
+    assert fast[0].shape == full[0].shape == (14 * 1920,) and np.array_equal(fast[0], full[0])
+
+
 def test_icl_streaming_skips_the_reference_part_without_changing_a_sample(base, ref_wav, monkeypatch):
     """While the window policy still accumulates (model.py:737-826) an ICL stream decodes reference + generated frames and throws
     the reference part away; with the causal length law that cut is known up front and the vocoder only computes what the kept
