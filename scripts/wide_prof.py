@@ -28,6 +28,9 @@ eng.lib.fq3_debug_read_prof(eng.h, buf, 64)
 names = ["entry barrier", "poll + stage", "norm", "mma + reduce + epilogue", "attention", "sample"]
 tot = sum(buf[i] for i in range(6))
 print(f"{ns} streams, context {T}: {a.elapsed_time(b) / frames:.3f} ms per frame-step; CTA {os.environ.get('FQ3_PROF')} thread 0, {buf[6] // frames} GEMV phases per frame")
+if tot == 0:
+    print("  (the per-category cycle marks of the wide kernel are compiled out by default: build with -DFQ3_WIDE_PROF=1 for the split)")
+    sys.exit(0)
 for i, n in enumerate(names):
     print(f"  {n:26s} {buf[i] / frames:10.0f} cycles/frame  {100 * buf[i] / tot:5.1f} %")
 for i, n in ((12, "multi-attn: entry barrier"), (13, "multi-attn: q / fresh K,V"), (14, "multi-attn: scores + request"), (15, "multi-attn: barrier 1"),
