@@ -36,6 +36,10 @@ enum fq3c_kind {
   FQ3C_SNAKE = 7,     /* C = A + p1[c] * sin(A * p0[c])^2   (p0 = exp(alpha), p1 = 1/(exp(beta)+1e-9))      */
   FQ3C_COPY = 9,      /* C[M, N] = A[M, N] (bf16 rows; lda / ldc): history roll of the stateful decode               */
   FQ3C_ADVANCE = 10,  /* *(int32*)C += i0 (one thread): the stateful decode's position counter                        */
+  FQ3C_ROLL = 11,     /* every history roll of a stateful chunk + the counter in ONE launch (ABI 5): A = device int64 [M, 5]
+                         rows (buffer address, hist rows, new rows, cols, ld): rows [new, new + hist) of each bf16 buffer
+                         move to [0, hist) (overlapping ranges in batches of `new` rows, a block barrier between them);
+                         then *(int32*)C += i0.  Replaces 2 x FQ3C_COPY per buffer (through scratch) + FQ3C_ADVANCE    */
   FQ3C_QKNORM_ROPE_KV = 8 /* dense talker prefill: A = fused qkv rows [M, lda], i0 q heads, i1 kv heads of dim 128; q/k heads get the
                              per-head RMSNorm (bf16 gamma p0 / p1, eps f0) and the rotary embedding from the bf16 tables B (cos) /
                              bias (sin) at position row + i2, in place; finished k / v rows also go to the static KV cache

@@ -30,7 +30,7 @@ from . import build as _build
 from .config import CodecDecoderConfig
 
 K_GEMM, K_RVQ, K_RMSNORM, K_ROPE, K_ATTN, K_DWCONV, K_LAYERNORM, K_SNAKE = range(8)
-K_COPY, K_ADVANCE = 9, 10
+K_COPY, K_ADVANCE, K_ROLL = 9, 10, 11
 F_BIAS, F_GELU, F_RESID, F_SCALE, F_SWIGLU, F_CLAMP, F_OUT_F32, F_SNAKE2, F_SILU = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
@@ -679,19 +679,32 @@ class CodecStream:
         plan.n_samples = rows
         # roll: the last `hist` rows of [history | new] become the history of the next chunk (through a scratch buffer when
         # the two ranges overlap), then the position counter moves on
-        for t, hist, name in self.hist:
-            n_new = self.rows_of[name] * T
-            cols = t.shape[1]
-            src = t[n_new:n_new + hist]
-            if n_new >= hist:
-                d_._simple(plan, K_COPY, src, hist, cols, out=t[:hist])
-            else:
-                tmp = self.tmp[:hist * cols].view(hist, cols)
-                d_._simple(plan, K_COPY, src, hist, cols, out=tmp)
-                d_._simple(plan, K_COPY, tmp, hist, cols, out=t[:hist])
-        adv = Op()
-        adv.kind, adv.M, adv.N, adv.i0, adv.C = K_ADVANCE, 1, 1, T, self.pos.data_ptr()
-        plan.ops.append(adv)
+        if os.environ.get("FQ3C_ROLL", "1") != "0":
+            # one launch for all of it (FQ3C_ROLL): 37 copies + the counter were 38 of a chunk's 129 launches
+            rows = []
+            for t, hist, name in self.hist:
+                assert t.is_contiguous() and t.shape[1] % 8 == 0
+                rows.append([t.data_ptr(), hist, self.rows_of[name] * T, t.shape[1], t.shape[1]])
+            desc = torch.tensor(rows, dtype=torch.int64, device=self.device)
+            plan.keep.append(desc)
+            roll = Op()
+            roll.kind, roll.M, roll.N, roll.i0 = K_ROLL, len(rows), 1, T
+            roll.A, roll.C = desc.data_ptr(), self.pos.data_ptr()
+            plan.ops.append(roll)
+        else:
+            for t, hist, name in self.hist:
+                n_new = self.rows_of[name] * T
+                cols = t.shape[1]
+                src = t[n_new:n_new + hist]
+                if n_new >= hist:
+                    d_._simple(plan, K_COPY, src, hist, cols, out=t[:hist])
+                else:
+                    tmp = self.tmp[:hist * cols].view(hist, cols)
+                    d_._simple(plan, K_COPY, src, hist, cols, out=tmp)
+                    d_._simple(plan, K_COPY, tmp, hist, cols, out=t[:hist])
+            adv = Op()
+            adv.kind, adv.M, adv.N, adv.i0, adv.C = K_ADVANCE, 1, 1, T, self.pos.data_ptr()
+            plan.ops.append(adv)
         plan.ops = fuse_row_norms(plan.ops)
         if self.split_k:
             attach_splitk_workspace(plan.ops, self.device, plan.keep)

@@ -910,6 +910,28 @@ __global__ void fq3c_copy_kernel(const fq3c_op o) {
   }
 }
 __global__ void fq3c_advance_kernel(int* counter, int by) { *counter += by; }
+// FQ3C_ROLL: blockIdx.x = history buffer, blockIdx.y = column slice (slices are independent).  dst row r <- src row r + new; when the
+// ranges overlap (new < hist) the rows go in batches of `new`: a batch's sources are the next batch's destinations, so a block
+// barrier separates them; within a batch sources and destinations are disjoint.
+constexpr int ROLL_SLICES = 8;
+__global__ void __launch_bounds__(256) fq3c_roll_kernel(const long long* desc, int* counter, int by) {
+  const long long* d = desc + (size_t)blockIdx.x * 5;
+  bf16* base = reinterpret_cast<bf16*>(d[0]);
+  const int hist = (int)d[1], n_new = (int)d[2], cols = (int)d[3], ld = (int)d[4];
+  const int nv = cols >> 3;
+  const int p0 = (int)(((long)blockIdx.y * nv) / ROLL_SLICES), p1 = (int)(((long)(blockIdx.y + 1) * nv) / ROLL_SLICES);
+  const int np = p1 - p0;
+  const int batch = n_new >= hist ? hist : n_new;
+  for (int r0 = 0; r0 < hist && np > 0; r0 += batch) {
+    const int rows = min(batch, hist - r0);
+    for (int i = threadIdx.x; i < rows * np; i += blockDim.x) {
+      const int r = r0 + i / np, p = p0 + i % np;
+      *reinterpret_cast<uint4*>(base + (size_t)r * ld + p * 8) = *reinterpret_cast<const uint4*>(base + (size_t)(r + n_new) * ld + p * 8);
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && counter) *counter += by;
+}
 
 __global__ void fq3c_snake_kernel(const fq3c_op o) {
   const size_t n = (size_t)o.M * o.N;
@@ -1109,6 +1131,11 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
         if ((o.N % 8) || (o.lda % 8) || (o.ldc % 8) || !o.A || !o.C) return fail("copy: N, lda, ldc must be multiples of 8");
         const size_t n = (size_t)o.M * (o.N >> 3);
         fq3c_copy_kernel<<<(unsigned)std::min<size_t>(1024, (n + 255) / 256), 256, 0, s>>>(o);
+        break;
+      }
+      case FQ3C_ROLL: {
+        if (!o.A || o.M <= 0) return fail("roll: no descriptors");
+        fq3c_roll_kernel<<<dim3((unsigned)o.M, ROLL_SLICES), 256, 0, s>>>(reinterpret_cast<const long long*>(o.A), reinterpret_cast<int*>(o.C), o.i0);
         break;
       }
       case FQ3C_ADVANCE: {
