@@ -986,6 +986,23 @@ int fq3c_abi_version(void) { return 5; }
 const char* fq3c_last_error(void) { return g_err.c_str(); }
 int64_t fq3c_launch_count(void) { return g_launches; }
 
+// Opt-in shared-memory sizes are a per-DEVICE function attribute: a process that serves several GPUs (server.py --gpus N: one scheduler
+// thread per device) must set them on each device it launches on, not once per process.
+static bool device_attrs_ready() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (done[dev]) return true;
+  if (cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(3)) != cudaSuccess ||
+      cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(3)) != cudaSuccess ||
+      cudaFuncSetAttribute(fq3c_attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APF_WARPS * (128 + 2048) * 4) != cudaSuccess)
+    return false;
+  done[dev] = true;
+  return true;
+}
+
 int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   for (int i = 0; i < n_ops; ++i) {
@@ -1001,12 +1018,8 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
         if (use_tc5 < 0) {
           const char* e = getenv("FQ3C_TCGEN05");
           use_tc5 = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-          if (use_tc5 && (cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess ||
-                          cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(3)) != cudaSuccess ||
-                          cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) != cudaSuccess ||
-                          cudaFuncSetAttribute(fq3c_gemm_tc5_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(3)) != cudaSuccess))
-            return fail("cannot reserve shared memory for the tcgen05 GEMM");
         }
+        if (use_tc5 && !device_attrs_ready()) return fail("cannot reserve shared memory for the tcgen05 GEMM / prefill attention");
         static int tc5_min_k = -1;
         if (tc5_min_k < 0) { const char* e3 = getenv("FQ3C_TC5_MINK"); tc5_min_k = e3 ? atoi(e3) : TK; }  // one k-block is enough: the vectorised epilogue beats the mma.sync kernel even at K = 96
         if (use_tc5 && o.N >= 16 && o.K >= tc5_min_k) {
@@ -1097,12 +1110,7 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
             (o.i0 % o.i1) == 0) {
           const int tpad = (o.M + 7) & ~7;
           const size_t smem = (size_t)APF_WARPS * 128 * 4 + (size_t)APF_WARPS * tpad * 4;
-          static bool apf_attr = false;
-          if (!apf_attr) {
-            if (cudaFuncSetAttribute(fq3c_attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APF_WARPS * (128 + 2048) * 4) != cudaSuccess)
-              return fail("cannot reserve shared memory for the prefill attention");
-            apf_attr = true;
-          }
+          if (!device_attrs_ready()) return fail("cannot reserve shared memory for the prefill attention");
           const int warps = o.M * o.i0;
           fq3c_attn_prefill_kernel<<<(warps + APF_WARPS - 1) / APF_WARPS, APF_WARPS * 32, smem, s>>>(o, tpad);
           break;
