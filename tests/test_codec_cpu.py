@@ -155,3 +155,43 @@ def test_full_decode_is_causal_and_bounded(pair):
     b = orc.decode(codes)
     assert float(b.abs().max()) <= 1.0
     assert torch.allclose(a, b[: a.numel()], atol=1e-5)
+
+
+def test_fuse_row_norms_rewrites_only_the_safe_pattern(monkeypatch):
+    """codec.fuse_row_norms (host logic): an RMSNORM that reads exactly the rows the GEMM before it wrote becomes that GEMM's
+    norm_out; anything else stays a separate op (different buffer / shape, SwiGLU or fp32 output, a tail-only GEMM, a GEMM that
+    already carries a norm), and FQ3C_FUSE_NORM=0 turns the rewrite off."""
+    from qwen3_tts_cuda_graphs_b200.codec import F_OUT_F32, F_RESID, F_SWIGLU, K_ATTN, K_GEMM, K_RMSNORM, Op, fuse_row_norms
+
+    def gemm(C, M=8, N=64, flags=0, ldc=64, m_begin=0):
+        o = Op()
+        o.kind, o.M, o.N, o.K, o.flags, o.C, o.ldc, o.m_begin = K_GEMM, M, N, 64, flags, C, ldc, m_begin
+        return o
+
+    def norm(A, out, M=8, N=64, lda=64, rows=None):
+        o = Op()
+        o.kind, o.M, o.N, o.A, o.lda, o.a_rows, o.C, o.ldc, o.scale, o.f0 = K_RMSNORM, M, N, A, lda, M if rows is None else rows, out, 64, 0x9000, 1e-6
+        return o
+
+    ops = fuse_row_norms([gemm(0x1000, flags=F_RESID), norm(0x1000, 0x2000)])
+    assert len(ops) == 1 and ops[0].norm_out == 0x2000 and ops[0].norm_w == 0x9000 and ops[0].norm_ld == 64 and abs(ops[0].norm_eps - 1e-6) < 1e-12
+    keep = [
+        [gemm(0x1000), norm(0x1100, 0x2000)],                    # reads another buffer
+        [gemm(0x1000), norm(0x1000, 0x2000, N=32)],              # another width
+        [gemm(0x1000), norm(0x1000, 0x2000, M=4)],               # another row count
+        [gemm(0x1000, flags=F_SWIGLU), norm(0x1000, 0x2000)],    # the GEMM's output is not [M, N] bf16
+        [gemm(0x1000, flags=F_OUT_F32), norm(0x1000, 0x2000)],
+        [gemm(0x1000, m_begin=3), norm(0x1000, 0x2000)],         # tail-only GEMM: rows below m_begin are not written
+        [norm(0x1000, 0x2000)],                                  # nothing in front
+    ]
+    for lst in keep:
+        out = fuse_row_norms(list(lst))
+        assert len(out) == len(lst) and not any(o.norm_out for o in out if o.kind == K_GEMM)
+    a = Op()
+    a.kind = K_ATTN
+    ops = fuse_row_norms([gemm(0x1000), a, norm(0x1000, 0x2000)])  # not adjacent
+    assert len(ops) == 3
+    ops = fuse_row_norms([gemm(0x1000), norm(0x1000, 0x2000), norm(0x1000, 0x3000)])  # one norm per GEMM
+    assert len(ops) == 2 and ops[0].norm_out == 0x2000 and ops[1].kind == K_RMSNORM
+    monkeypatch.setenv("FQ3C_FUSE_NORM", "0")
+    assert len(fuse_row_norms([gemm(0x1000), norm(0x1000, 0x2000)])) == 2
