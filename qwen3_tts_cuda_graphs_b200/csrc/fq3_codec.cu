@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -19,7 +20,10 @@ typedef __nv_bfloat16 bf16;
 namespace {
 
 thread_local std::string g_err;
-int64_t g_launches = 0;
+// launches of the whole process (several scheduler threads may run op lists at once: one per GPU) and of the calling thread alone
+std::atomic<int64_t> g_launches{0};
+thread_local int64_t t_launches = 0;
+inline void count_launches(int64_t n) { g_launches += n; t_launches += n; }
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -984,7 +988,7 @@ extern "C" {
 
 int fq3c_abi_version(void) { return 5; }
 const char* fq3c_last_error(void) { return g_err.c_str(); }
-int64_t fq3c_launch_count(void) { return g_launches; }
+int64_t fq3c_launch_count(void) { return g_launches.load(); }
 
 // Opt-in shared-memory sizes are a per-DEVICE function attribute: a process that serves several GPUs (server.py --gpus N: one scheduler
 // thread per device) must set them on each device it launches on, not once per process.
@@ -1083,10 +1087,10 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
               const long n = (long)(o.M - o.m_begin) * (Nw >> 3);
               fq3c_splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(o, splits, Nw);
             }
-            g_launches += 1;
+            count_launches(1);
           } else if (o.norm_out) {
             fq3c_rownorm_kernel<<<(unsigned)(o.M - o.m_begin), 256, 0, s>>>(o);
-            g_launches += 1;
+            count_launches(1);
           }
           break;
         }
@@ -1094,7 +1098,7 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
         fq3c_gemm_kernel<<<grid, 128, 0, s>>>(o);
         if (o.norm_out) {
           fq3c_rownorm_kernel<<<(unsigned)(o.M - o.m_begin), 256, 0, s>>>(o);
-          g_launches += 1;
+          count_launches(1);
         }
         break;
       }
@@ -1153,7 +1157,7 @@ int fq3c_run(const fq3c_op* ops, int n_ops, void* stream) {
       }
       default: return fail("unknown op kind");
     }
-    g_launches += 1;
+    count_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(std::string("launch failed at op ") + std::to_string(i) + ": " + cudaGetErrorString(e));
   }
@@ -1171,7 +1175,7 @@ int fq3c_graph_create(const fq3c_op* ops, int n_ops, void** out) {
   if (!ops || !out || n_ops <= 0) return fail("graph: bad arguments");
   cudaStream_t cs;
   if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) return fail("graph: stream create failed");
-  const int64_t before = g_launches;
+  const int64_t before = t_launches;
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
   int rc = 0;
@@ -1179,8 +1183,8 @@ int fq3c_graph_create(const fq3c_op* ops, int n_ops, void** out) {
     rc = fq3c_run(ops, n_ops, cs);
     e = cudaStreamEndCapture(cs, &g);
   }
-  const int n_kernels = (int)(g_launches - before);
-  g_launches = before;  // nothing ran yet
+  const int n_kernels = (int)(t_launches - before);
+  count_launches(-(int64_t)n_kernels);  // nothing ran yet
   cudaStreamDestroy(cs);
   if (rc != 0 || e != cudaSuccess || !g) {
     if (g) cudaGraphDestroy(g);
@@ -1198,7 +1202,7 @@ int fq3c_graph_launch(void* graph, void* stream) {
   if (!g) return fail("graph: null handle");
   const cudaError_t e = cudaGraphLaunch(g->exec, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(std::string("graph: launch failed: ") + cudaGetErrorString(e));
-  g_launches += g->n_kernels;
+  count_launches(g->n_kernels);
   return 0;
 }
 int fq3c_graph_destroy(void* graph) {
