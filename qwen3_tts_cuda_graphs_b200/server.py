@@ -251,6 +251,25 @@ def build_backends(model: str, gpus: int, max_concurrent: int, chunk_frames: int
     return out
 
 
+def warm_up(backends: List[object], voices: Dict[str, dict], rounds: int = 2, frames: int = 40) -> float:
+    """Run a short utterance of every configured voice through every replica before the port opens (the reference's servers call
+    `_warmup` for the same reason: `demo/server.py:317,688`): the voice prompts are encoded and cached, the dense-prefill graph, the
+    codec lanes' launch plans and their CUDA graphs are built — all of which would otherwise land in the first requests' latency.
+    Returns the seconds it took."""
+    t0 = time.perf_counter()
+    for _ in range(rounds):  # a plan becomes a CUDA graph on its second use
+        handles = []
+        for b in backends:
+            for cfg in voices.values():
+                handles.append(b.submit(_request_for(cfg, "Warm up.", {"max_new_tokens": frames, "min_new_tokens": min(frames, 2)})))
+        for h in handles:
+            try:
+                h.result()
+            except Exception as e:  # a broken voice must not keep the server from starting; it will fail per request
+                logger.warning("warm-up of a voice failed: %s", e)
+    return time.perf_counter() - t0
+
+
 def main(argv=None):
     p = argparse.ArgumentParser(description="OpenAI-compatible TTS server on the fq3 engine", formatter_class=argparse.RawDescriptionHelpFormatter)
     p.add_argument("--model", default=os.environ.get("QWEN_TTS_MODEL", "synthetic://0.6B-Base"), help="checkpoint directory, cached hub id, or synthetic://<preset>")
@@ -264,12 +283,15 @@ def main(argv=None):
     p.add_argument("--gpus", type=int, default=1, help="replicas, one per GPU")
     p.add_argument("--max-concurrent", type=int, default=16, help="lock-step streams per GPU")
     p.add_argument("--chunk-frames", type=int, default=8, help="frames per launch = streaming granularity (8 frames = 0.64 s)")
+    p.add_argument("--no-warmup", action="store_true", help="open the port at once; the first requests then pay for plan building")
     args = p.parse_args(argv)
     logging.basicConfig(level=logging.INFO)
     voices, default_voice = load_voices(args)
     import uvicorn
 
     backends = build_backends(args.model, args.gpus, args.max_concurrent, args.chunk_frames)
+    if not args.no_warmup:
+        logger.info("Warm-up: %.1f s", warm_up(backends, voices))
     app = create_app(backends, voices, default_voice, sample_rate=backends[0].tts.sample_rate)
     logger.info("Server listening on http://%s:%d (%d GPU(s), %d streams each)", args.host, args.port, args.gpus, args.max_concurrent)
     try:

@@ -128,3 +128,12 @@ def test_cli_parser_has_the_reference_subcommands_and_writes_wav(tmp_path):
     cli.write_audio(out, np.linspace(-1, 1, 480, dtype=np.float32), 24000)
     with wave.open(out) as wf:
         assert (wf.getframerate(), wf.getnchannels(), wf.getsampwidth(), wf.getnframes()) == (24000, 1, 2, 480)
+
+
+def test_warm_up_runs_every_voice_on_every_replica_and_survives_a_broken_voice():
+    b0, b1 = StubBackend(), StubBackend(fail=True)
+    dt = server.warm_up([b0, b1], VOICES, rounds=2, frames=12)
+    assert dt >= 0
+    for b in (b0, b1):
+        assert len(b.requests) == 2 * len(VOICES)
+        assert {r.kind for r in b.requests} == {"voice_clone", "custom_voice"} and all(r.max_new_tokens == 12 for r in b.requests)
