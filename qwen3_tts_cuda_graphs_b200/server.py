@@ -61,6 +61,10 @@ class SpeechRequest(BaseModel):  # examples/openai_server.py:78-83
     speed: float = 1.0  # accepted, not applied (as in the reference)
 
 
+class BackendUnavailable(RuntimeError):
+    """Every replica's scheduler has stopped (HTTP 503)."""
+
+
 class Dispatcher:
     """Least-loaded choice among per-GPU backends (request-parallel replicas; no exchange between them)."""
 
@@ -71,9 +75,15 @@ class Dispatcher:
         self.in_flight = [0] * len(self.backends)
         self._lock = threading.Lock()
 
+    def healthy(self) -> List[bool]:
+        return [bool(getattr(b, "healthy", True)) for b in self.backends]
+
     def submit(self, req: TTSRequest):
         with self._lock:
-            i = min(range(len(self.backends)), key=lambda j: self.in_flight[j])
+            live = [j for j, ok in enumerate(self.healthy()) if ok]  # a replica whose loop died (device fault) is routed around
+            if not live:
+                raise BackendUnavailable("no healthy backend: every replica's scheduler has stopped")
+            i = min(live, key=lambda j: self.in_flight[j])
             self.in_flight[i] += 1
         try:
             h = self.backends[i].submit(req)
@@ -141,7 +151,9 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
 
     @app.get("/health")
     async def health():
-        return {"status": "ok", "model_loaded": True, "backends": len(disp.backends), "in_flight": list(disp.in_flight)}
+        ok = disp.healthy()
+        status = "ok" if all(ok) else ("degraded" if any(ok) else "down")
+        return {"status": status, "model_loaded": True, "backends": len(disp.backends), "healthy": ok, "in_flight": list(disp.in_flight)}
 
     @app.get("/v1/voices")
     async def list_voices():
@@ -161,6 +173,8 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
             handle = disp.submit(_request_for(voice_cfg, req.input))
         except ValueError as e:
             raise HTTPException(status_code=400, detail=str(e))
+        except RuntimeError as e:  # BackendUnavailable, or the chosen replica failed between the check and the submit
+            raise HTTPException(status_code=503, detail=str(e))
 
         async def audio_stream():
             if fmt == "wav":
@@ -195,7 +209,10 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
         except ValueError as e:
             raise HTTPException(status_code=400, detail=str(e))
         ahead = sum(disp.in_flight)
-        handle = disp.submit(req)
+        try:
+            handle = disp.submit(req)
+        except RuntimeError as e:
+            raise HTTPException(status_code=503, detail=str(e))
         t0 = time.perf_counter()
 
         async def sse():

@@ -180,6 +180,8 @@ class BatchScheduler:
         self._next_id = 0
         self._submit_lock = threading.Lock()  # submit() is the one method other threads call
         self._lanes: List[tuple] = []  # (CUDA stream, speech tokenizer with its own launch plans) per codec lane
+        self._backlog: List[tuple] = []  # (active, codes chunk, final?, reason) of the chunk that just finished
+        self._failure: Optional[BaseException] = None  # what stopped the loop (device fault, ...): submit() refuses from then on
         # seconds per part of the loop: admit (prompt build + prefill), launch (host side of fq3_decode_frames), emit (codec lanes +
         # D2H + hand-out of the previous chunk), wait (blocked on the running launch)
         self.stats = {"launches": 0, "frames": 0, "requests": 0, "max_batch": 0, "t_admit": 0.0, "t_launch": 0.0, "t_emit": 0.0, "t_wait": 0.0}
@@ -196,7 +198,17 @@ class BatchScheduler:
         self._wake.set()
         if self._thread is not None:
             self._thread.join(timeout)
+            if self._thread.is_alive():  # still inside a launch: keep the handle, a second start() must not run beside it
+                logger.warning("fq3 scheduler thread did not stop within %.0f s", timeout)
+                return
             self._thread = None
+        self._stop.clear()
+
+    @property
+    def healthy(self) -> bool:
+        """False once the loop has died of an exception (a device fault is sticky: the engine has to be rebuilt or
+        `fq3_clear_fault`-ed): the HTTP front then routes around this replica (server.Dispatcher) and /health says so."""
+        return self._failure is None
 
     def __enter__(self):
         return self.start()
@@ -207,6 +219,8 @@ class BatchScheduler:
     def submit(self, req: TTSRequest) -> RequestHandle:
         if req.kind not in ("voice_clone", "custom_voice", "voice_design"):
             raise ValueError(f"unknown request kind {req.kind!r}")
+        if self._failure is not None:  # nobody would ever answer: say so now instead of letting the caller wait for ever
+            raise RuntimeError(f"scheduler stopped after a failure: {self._failure!r}")
         with self._submit_lock:
             h = RequestHandle(req, self._next_id)
             self._next_id += 1
@@ -381,15 +395,15 @@ class BatchScheduler:
             with torch.inference_mode():
                 for s in range(self.eng.max_streams):
                     eng.retire_stream(s)  # never-used slots idle inside a launch
-                backlog: List[tuple] = []  # (active, codes chunk, final?, reason) of the chunk that just finished
+                self._backlog = []
                 while not self._stop.is_set():
                     t0 = time.perf_counter()
                     self._admit()
                     t1 = time.perf_counter()
                     self.stats["t_admit"] += t1 - t0
                     if not self._active:
-                        self._emit(backlog)
-                        backlog = []
+                        self._emit(self._backlog)
+                        self._backlog = []
                         self._cohort = None
                         if self._deferred:
                             continue
@@ -399,12 +413,12 @@ class BatchScheduler:
                     staged = None
                     mode = self.overlap_codec
                     if mode == "auto":
-                        mode = "gpu" if len(backlog) <= 2 else "host"
+                        mode = "gpu" if len(self._backlog) <= 2 else "host"
                     if mode == "none":  # codec of the previous chunk before the next launch, host waits for it
-                        self._emit(backlog)
-                        backlog = []
-                    elif mode == "host" and backlog:  # GPU: codec, then frame loop; host: collects beside the frame loop
-                        staged = self._emit_enqueue(backlog)
+                        self._emit(self._backlog)
+                        self._backlog = []
+                    elif mode == "host" and self._backlog:  # GPU: codec, then frame loop; host: collects beside the frame loop
+                        staged = self._emit_enqueue(self._backlog)
                         tq = time.perf_counter()
                         self._lanes_before_main()
                         self.stats["t_enqueue"] = self.stats.get("t_enqueue", 0.0) + tq - t1
@@ -415,10 +429,10 @@ class BatchScheduler:
                     self.stats["launches"] += 1
                     self.stats["max_batch"] = max(self.stats["max_batch"], len(self._active))
                     if staged is not None:
-                        self._emit_collect(backlog, staged)
+                        self._emit_collect(self._backlog, staged)
                     else:
-                        self._emit(backlog)  # "gpu": previous chunk's codec on the SMs the running launch leaves free
-                    backlog = []
+                        self._emit(self._backlog)  # "gpu": previous chunk's codec on the SMs the running launch leaves free
+                    self._backlog = []
                     t3 = time.perf_counter()
                     self.stats["t_launch"] += t2 - t1
                     self.stats["t_emit"] += t3 - t2
@@ -444,7 +458,7 @@ class BatchScheduler:
                             chunk = eng.read_codes(slot, a.emitted, n_new)
                             a.emitted += n_new
                             self.stats["frames"] += n_new
-                            backlog.append((a, chunk, reason is not None, reason))
+                            self._backlog.append((a, chunk, reason is not None, reason))
                             if reason is not None:
                                 self._draining.add(slot)
                         elif reason is not None:
@@ -453,7 +467,7 @@ class BatchScheduler:
                             eng.retire_stream(slot)
                             del self._active[slot]
                     self.stats["t_wait"] += time.perf_counter() - t3
-                self._emit(backlog)
+                self._emit(self._backlog)
                 for a in list(self._active.values()):  # stop() in mid-utterance: nobody may wait for ever
                     if a.handle.finish_reason is None:
                         self._finish(a.handle, "shutdown")
@@ -474,16 +488,27 @@ class BatchScheduler:
 
         except BaseException as e:  # surface a scheduler failure to every waiter instead of hanging them
             logger.exception("fq3 scheduler stopped")
-            for a in list(self._active.values()):
-                a.handle.q.put(e)
-                a.handle.q.put(_DONE)
-            for h in self._deferred:
+            self._failure = e
+            waiters = {id(a.handle): a.handle for a in self._active.values()}
+            for a, _chunk, _final, _reason in self._backlog:  # a retired slot's last chunk was still waiting for the codec
+                if a.handle.finish_reason is None:
+                    waiters.setdefault(id(a.handle), a.handle)
+            self._active.clear()
+            self._backlog = []
+            for h in waiters.values():
+                h.finish_reason = "error"
                 h.q.put(e)
                 h.q.put(_DONE)
+            for h in self._deferred:
+                h.finish_reason = "error"
+                h.q.put(e)
+                h.q.put(_DONE)
+            self._deferred = []
             while True:
                 try:
                     h = self._pending.get_nowait()
                 except queue.Empty:
                     break
+                h.finish_reason = "error"
                 h.q.put(e)
                 h.q.put(_DONE)

@@ -137,3 +137,20 @@ def test_warm_up_runs_every_voice_on_every_replica_and_survives_a_broken_voice()
     for b in (b0, b1):
         assert len(b.requests) == 2 * len(VOICES)
         assert {r.kind for r in b.requests} == {"voice_clone", "custom_voice"} and all(r.max_new_tokens == 12 for r in b.requests)
+
+
+def test_dead_replicas_are_routed_around_and_all_dead_is_a_503():
+    b0, b1 = StubBackend(), StubBackend()
+    b0.healthy = False  # serving.BatchScheduler.healthy after its loop died (device fault)
+    c = TestClient(server.create_app([b0, b1], VOICES, "alloy"))
+    assert c.get("/health").json()["status"] == "degraded" and c.get("/health").json()["healthy"] == [False, True]
+    for _ in range(3):
+        assert c.post("/v1/audio/speech", json={"input": "Hi", "voice": "alloy"}).status_code == 200
+    assert len(b0.requests) == 0 and len(b1.requests) == 3
+    b1.healthy = False
+    assert c.get("/health").json()["status"] == "down"
+    r = c.post("/v1/audio/speech", json={"input": "Hi", "voice": "alloy"})
+    assert r.status_code == 503 and "no healthy backend" in r.json()["detail"]
+    r = c.post("/generate/stream", data={"text": "Hi", "voice": "alloy"})
+    assert r.status_code == 503
+    assert c.app.state.dispatcher.in_flight == [0, 0]

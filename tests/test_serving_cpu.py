@@ -242,3 +242,59 @@ def test_a_waiting_policy_is_not_starved_and_stop_releases_everyone():
     assert endless.finish_reason in ("shutdown", "length")
     for i, h in enumerate(behind):
         assert h.finish_reason in ("length", "shutdown")
+
+
+@pytest.mark.parametrize("where", ["status", "launch"])
+def test_a_device_fault_reaches_every_waiter_and_later_submits_are_refused(where):
+    """The loop dies of a device fault (engine.status().error != 0): running requests, the request whose last chunk was still
+    waiting for the codec, requests waiting for a slot or for another policy's cohort — all get the exception, none hangs;
+    submit() refuses afterwards and `healthy` turns False (server.Dispatcher routes around the replica)."""
+
+    class FaultyEngine(FakeEngine):
+        fault_after = 3
+
+        def status(self, s):
+            st = super().status(s)
+            if where == "status" and len(self.launches) >= self.fault_after:
+                st.error = 7
+            return st
+
+        def decode_frames(self, hi, n, policy, sub):
+            if where == "launch" and len(self.launches) + 1 >= self.fault_after:  # fq3_decode_frames -> FQ3_E_DEVICE_FAULT
+                raise RuntimeError("device fault 7 at launch")
+            super().decode_frames(hi, n, policy, sub)
+
+    eng = FaultyEngine(max_streams=2, frame_sleep=0.001)
+    tts = FakeTTS(eng)
+    sched = BatchScheduler(tts, chunk_frames=8, overlap_codec="host").start()
+    running = sched.submit(_req(1, 10 ** 4))
+    ending = sched.submit(_req(2, 16))            # retired after launch 2; its final chunk waits for the codec beside launch 3
+    queued = sched.submit(_req(3, 16))            # no free slot yet
+    other = sched.submit(TTSRequest(f"4,{10 ** 9}", ref_audio="v.wav", language="English", max_new_tokens=16, temperature=0.5))
+    for h in (running, ending, queued, other):
+        if where == "status" and h is ending:  # its last chunk went out beside launch 3, before the fault was read
+            assert len(h.result()[0]) == 16 * SPF and h.finish_reason == "length"
+            continue
+        with pytest.raises(RuntimeError, match="device fault 7"):
+            h.result()
+        assert h.finish_reason == "error"
+    assert sched.healthy is False
+    with pytest.raises(RuntimeError, match="scheduler stopped"):
+        sched.submit(_req(5, 8))
+    sched.stop()
+
+
+def test_stop_then_start_serves_again():
+    eng = FakeEngine(max_streams=2)
+    tts = FakeTTS(eng)
+    sched = BatchScheduler(tts, chunk_frames=8).start()
+    a = sched.submit(_req(1, 12))
+    a.id_key = 1
+    _audio_ok(a, 12)
+    sched.stop()
+    sched.start()
+    b = sched.submit(_req(2, 9))
+    b.id_key = 2
+    _audio_ok(b, 9)
+    sched.stop()
+    assert sched.healthy
