@@ -125,7 +125,11 @@ def cmd_serve(args):
     def drain(block_all: bool):
         while waiting and (block_all or len(waiting) >= 4 * args.concurrency):
             out_path, h, start = waiting.pop(0)
-            audio, sr = h.result()
+            try:
+                audio, sr = h.result()
+            except Exception as e:  # one bad line must not lose the utterances decoding beside it
+                print(f"ERROR: {out_path}: {e}", file=sys.stderr)
+                continue
             write_audio(out_path, audio, sr)
             _report(out_path, audio, sr, start)
 
