@@ -1,7 +1,9 @@
 """HTTP front of the serving layer: the reference's OpenAI-compatible endpoint
 (`examples/openai_server.py:219-265`: POST /v1/audio/speech, GET /health; wav / pcm streamed chunk by chunk with an
 unknown-length WAV header) and the demo's server-sent-events protocol (`demo/server.py:332-541`: POST /generate/stream ->
-`data: {"type": "queued" | "chunk" | "done" | "error", ...}`), on top of `serving.BatchScheduler` instead of a global lock:
+`data: {"type": "queued" | "chunk" | "done" | "error", ...}`; POST /generate -> one base64 WAV + metrics, `:546-662`; GET /status;
+reference audio as an upload, a preset or a configured voice; the demo's text / upload size limits), on top of
+`serving.BatchScheduler` instead of a global lock:
 concurrent requests decode in lock-step on the same weight sweep, one scheduler per GPU, requests go to the least-loaded one
 (replicas only — DESIGN.md §7).
 
@@ -16,17 +18,21 @@ from __future__ import annotations
 import argparse
 import asyncio
 import base64
+import hashlib
 import io
 import json
 import logging
 import os
 import struct
 import sys
+import tempfile
 import threading
 import time
 from typing import Dict, List, Optional
 
 import numpy as np
+from fastapi import FastAPI, File, Form, HTTPException, UploadFile  # module level: the endpoints' annotations are resolved by name
+from fastapi.responses import JSONResponse, StreamingResponse
 from pydantic import BaseModel
 
 from .serving import TTSRequest
@@ -34,6 +40,28 @@ from .serving import TTSRequest
 logger = logging.getLogger(__name__)
 
 CONTENT_TYPES = {"wav": "audio/wav", "pcm": "audio/pcm"}
+MAX_TEXT_CHARS = 1000                 # demo/server.py:173
+MAX_AUDIO_BYTES = 10 * 1024 * 1024    # demo/server.py:175 (about one minute of 44.1 kHz stereo 16-bit WAV)
+AUDIO_TOO_LARGE = ("Audio file too large ({size_mb:.1f} MB). Voice cloning works best with short clips under 1 minute — "
+                   "please upload a shorter recording.")
+_ref_paths: Dict[str, str] = {}
+_ref_paths_lock = threading.Lock()
+
+
+def cached_ref_path(content: bytes) -> str:
+    """An uploaded reference clip -> a file named after its content hash (demo/server.py:201-212), so the same clip uploaded again
+    is the same `ref_audio` path and hits the model's voice-prompt cache (x-vector / reference codes are encoded once per voice)."""
+    digest = hashlib.sha1(content).hexdigest()
+    with _ref_paths_lock:
+        path = _ref_paths.get(digest)
+        if path and os.path.exists(path):
+            return path
+        path = os.path.join(tempfile.gettempdir(), f"fq3_tts_ref_{digest}.wav")
+        if not os.path.exists(path):
+            with open(path, "wb") as f:
+                f.write(content)
+        _ref_paths[digest] = path
+        return path
 
 
 # ---- audio helpers (examples/openai_server.py:88-118) ------------------------------------------
@@ -119,9 +147,6 @@ def _request_for(voice_cfg: dict, text: str, overrides: Optional[dict] = None) -
 
 
 def create_app(backends: List[object], voices: Dict[str, dict], default_voice: Optional[str] = None, sample_rate: int = 24000):
-    from fastapi import FastAPI, Form, HTTPException
-    from fastapi.responses import StreamingResponse
-
     app = FastAPI(title="qwen3-tts B200 engine: OpenAI-compatible API")
     disp = Dispatcher(backends)
     app.state.dispatcher = disp
@@ -184,39 +209,76 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
 
         return StreamingResponse(audio_stream(), media_type=CONTENT_TYPES[fmt])
 
-    @app.post("/generate/stream")
-    async def generate_stream(text: str = Form(...), language: str = Form("English"), mode: str = Form("voice_clone"),
-                              ref_text: str = Form(""), speaker: str = Form(""), instruct: str = Form(""),
-                              xvec_only: bool = Form(True), temperature: float = Form(0.9), top_k: int = Form(50),
-                              repetition_penalty: float = Form(1.05), voice: str = Form("")):
-        """The demo's SSE protocol (demo/server.py:332-541); reference audio comes from a configured voice instead of an upload."""
+    async def demo_request(text, language, mode, ref_text, speaker, instruct, xvec_only, temperature, top_k, repetition_penalty,
+                           voice, ref_preset, ref_audio) -> TTSRequest:
+        """The demo's form (demo/server.py:332-372, :546-587) -> a request.  Reference audio: an upload, else a configured voice
+        (`ref_preset` / `voice`, the demo's presets), else the default voice."""
         if not text.strip():
             raise HTTPException(status_code=400, detail="text is empty")
+        if len(text) > MAX_TEXT_CHARS:
+            raise HTTPException(status_code=400, detail=f"Text too long ({len(text)} chars). Maximum is {MAX_TEXT_CHARS} characters.")
         over = dict(language=language, temperature=temperature, top_k=top_k, repetition_penalty=repetition_penalty)
         try:
             if mode == "voice_clone":
-                cfg = dict(resolve_voice(voice or (default_voice or "")))
-                if ref_text:
-                    cfg["ref_text"] = ref_text
+                if ref_audio is not None and getattr(ref_audio, "filename", None):
+                    content = await ref_audio.read()
+                    if len(content) > MAX_AUDIO_BYTES:
+                        raise HTTPException(status_code=400, detail=AUDIO_TOO_LARGE.format(size_mb=len(content) / 1024 / 1024))
+                    cfg = {"ref_audio": cached_ref_path(content), "ref_text": ref_text}
+                else:
+                    cfg = dict(resolve_voice(ref_preset or voice or (default_voice or "")))
+                    if ref_text:
+                        cfg["ref_text"] = ref_text
                 cfg["xvec_only"] = xvec_only
-                req = _request_for(cfg, text, over)
-            elif mode == "custom":
-                req = _request_for({"speaker": speaker, "instruct": instruct}, text, over)
-            elif mode == "voice_design":
-                req = _request_for({"instruct": instruct}, text, over)
-            else:
-                raise ValueError(f"unknown mode {mode!r}")
+                return _request_for(cfg, text, over)
+            if mode == "custom":
+                return _request_for({"speaker": speaker, "instruct": instruct}, text, over)
+            if mode == "voice_design":
+                return _request_for({"instruct": instruct}, text, over)
+            raise ValueError(f"unknown mode {mode!r}")
         except ValueError as e:
             raise HTTPException(status_code=400, detail=str(e))
-        ahead = sum(disp.in_flight)
+
+    def submit_or_503(req: TTSRequest):
         try:
-            handle = disp.submit(req)
+            return disp.submit(req)
         except RuntimeError as e:
             raise HTTPException(status_code=503, detail=str(e))
+
+    @app.get("/status")
+    async def status():
+        """demo/server.py:251-277, for the model(s) this server was started with (no load / unload at run time)."""
+        tts = getattr(disp.backends[0], "tts", None)
+        model_type, speakers, name = None, [], None
+        if tts is not None:
+            try:
+                model_type = tts.model.model.tts_model_type
+                speakers = list(tts.model.get_supported_speakers() or [])
+                name = getattr(tts.model, "name", None)
+            except Exception:
+                speakers = []
+        return {"loaded": True, "model": name, "loading": False, "model_type": model_type, "speakers": speakers,
+                "transcription_available": False,
+                "preset_refs": [{"id": k, "label": k, "ref_text": v.get("ref_text", "")} for k, v in voices.items() if v.get("ref_audio")],
+                "queue_depth": sum(disp.in_flight), "backends": len(disp.backends), "healthy": disp.healthy()}
+
+    @app.post("/generate/stream")
+    async def generate_stream(text: str = Form(...), language: str = Form("English"), mode: str = Form("voice_clone"),
+                              ref_text: str = Form(""), speaker: str = Form(""), instruct: str = Form(""),
+                              xvec_only: bool = Form(True), chunk_size: int = Form(8), temperature: float = Form(0.9),
+                              top_k: int = Form(50), repetition_penalty: float = Form(1.05), voice: str = Form(""),
+                              ref_preset: str = Form(""), ref_audio: UploadFile = File(None)):
+        """The demo's SSE protocol (demo/server.py:332-541).  `chunk_size` is accepted for compatibility: the streaming granularity
+        is the scheduler's `chunk_frames` (one launch for all running utterances), set when the server starts."""
+        req = await demo_request(text, language, mode, ref_text, speaker, instruct, xvec_only, temperature, top_k, repetition_penalty,
+                                 voice, ref_preset, ref_audio)
+        ahead = sum(disp.in_flight)
+        handle = submit_or_503(req)
         t0 = time.perf_counter()
 
         async def sse():
-            yield f"data: {json.dumps({'type': 'queued', 'position': ahead})}\n\n"
+            if ahead > 0:  # demo/server.py:513-514: only said when somebody is ahead
+                yield f"data: {json.dumps({'type': 'queued', 'position': ahead})}\n\n"
             total_audio_s, ttfa_ms = 0.0, None
             try:
                 async for audio, sr, _info in chunks_of(handle):
@@ -234,7 +296,33 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
             except Exception as e:  # generation errors travel in-band, like the demo's
                 yield f"data: {json.dumps({'type': 'error', 'message': str(e)})}\n\n"
 
-        return StreamingResponse(sse(), media_type="text/event-stream")
+        return StreamingResponse(sse(), media_type="text/event-stream", headers={"Cache-Control": "no-cache", "X-Accel-Buffering": "no"})
+
+    @app.post("/generate")
+    async def generate_non_streaming(text: str = Form(...), language: str = Form("English"), mode: str = Form("voice_clone"),
+                                     ref_text: str = Form(""), speaker: str = Form(""), instruct: str = Form(""),
+                                     xvec_only: bool = Form(True), temperature: float = Form(0.9), top_k: int = Form(50),
+                                     repetition_penalty: float = Form(1.05), voice: str = Form(""), ref_preset: str = Form(""),
+                                     ref_audio: UploadFile = File(None)):
+        """The demo's one-shot endpoint (demo/server.py:546-662): the whole utterance as one base64 WAV plus metrics."""
+        req = await demo_request(text, language, mode, ref_text, speaker, instruct, xvec_only, temperature, top_k, repetition_penalty,
+                                 voice, ref_preset, ref_audio)
+        handle = submit_or_503(req)
+        t0 = time.perf_counter()
+        parts, sr = [], sample_rate
+        try:
+            async for audio, sr, _info in chunks_of(handle):
+                parts.append(audio)
+        except HTTPException:
+            raise
+        except Exception as e:
+            raise HTTPException(status_code=500, detail=str(e))
+        elapsed = time.perf_counter() - t0
+        audio = np.concatenate(parts) if parts else np.zeros(1, dtype=np.float32)
+        dur = len(audio) / sr
+        return JSONResponse({"audio_b64": base64.b64encode(to_wav_bytes(audio, sr)).decode(), "sample_rate": sr,
+                             "metrics": {"total_ms": round(elapsed * 1000), "audio_duration_s": round(dur, 3),
+                                         "rtf": round(dur / elapsed, 3) if elapsed > 0 else 0.0}})
 
     return app
 

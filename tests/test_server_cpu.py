@@ -94,9 +94,9 @@ def test_sse_protocol(client):
     r = c.post("/generate/stream", data={"text": "Hello there", "mode": "custom", "speaker": "aiden", "language": "English"})
     assert r.status_code == 200 and r.headers["content-type"].startswith("text/event-stream")
     msgs = [json.loads(line[6:]) for line in r.text.splitlines() if line.startswith("data: ")]
-    assert [m["type"] for m in msgs] == ["queued", "chunk", "chunk", "chunk", "done"]
-    wav = base64.b64decode(msgs[1]["audio_b64"])
-    assert wav[:4] == b"RIFF" and struct.unpack("<I", wav[40:44])[0] == 4800 and msgs[1]["sample_rate"] == 24000
+    assert [m["type"] for m in msgs] == ["chunk", "chunk", "chunk", "done"]  # "queued" only when somebody is ahead (demo/server.py:513)
+    wav = base64.b64decode(msgs[0]["audio_b64"])
+    assert wav[:4] == b"RIFF" and struct.unpack("<I", wav[40:44])[0] == 4800 and msgs[0]["sample_rate"] == 24000
     assert msgs[-1]["total_audio_s"] == pytest.approx(0.3, abs=1e-3)
     r = c.post("/generate/stream", data={"text": "x", "mode": "nonsense"})
     assert r.status_code == 400
@@ -154,3 +154,61 @@ def test_dead_replicas_are_routed_around_and_all_dead_is_a_503():
     r = c.post("/generate/stream", data={"text": "Hi", "voice": "alloy"})
     assert r.status_code == 503
     assert c.app.state.dispatcher.in_flight == [0, 0]
+
+
+def test_sse_says_queued_when_requests_are_ahead(client):
+    c, *_ = client
+    c.app.state.dispatcher.in_flight[0] = 3  # three utterances already running on replica 0
+    r = c.post("/generate/stream", data={"text": "Hi", "mode": "voice_design", "instruct": "a calm voice"})
+    msgs = [json.loads(line[6:]) for line in r.text.splitlines() if line.startswith("data: ")]
+    assert msgs[0] == {"type": "queued", "position": 3} and msgs[-1]["type"] == "done"
+
+
+def test_uploaded_reference_audio_becomes_a_content_addressed_file(client, tmp_path):
+    """demo/server.py:366-373: an uploaded clip is written once under its content hash, so a repeated upload is the same
+    `ref_audio` path (the model's voice-prompt cache key)."""
+    import os
+
+    c, b0, b1 = client
+    clip = b"RIFF" + bytes(range(256)) * 4
+    paths = []
+    for _ in range(2):
+        r = c.post("/generate/stream", data={"text": "Hello", "mode": "voice_clone", "ref_text": "what the clip says", "xvec_only": "false"},
+                   files={"ref_audio": ("my voice.wav", clip, "audio/wav")})
+        assert r.status_code == 200
+    reqs = b0.requests + b1.requests
+    assert len(reqs) == 2 and reqs[0].ref_audio == reqs[1].ref_audio and reqs[0].kind == "voice_clone"
+    assert reqs[0].ref_text == "what the clip says" and reqs[0].xvec_only is False
+    with open(reqs[0].ref_audio, "rb") as f:
+        assert f.read() == clip
+    os.unlink(reqs[0].ref_audio)
+    # without an upload: the named preset / voice, else the default voice
+    c.post("/generate/stream", data={"text": "Hello", "ref_preset": "alloy"})
+    assert (b0.requests + b1.requests)[-1].ref_audio == "alloy.wav" or b1.requests[-1].ref_audio == "alloy.wav"
+
+
+def test_demo_limits_and_one_shot_endpoint(client, monkeypatch):
+    c, b0, b1 = client
+    r = c.post("/generate/stream", data={"text": "x" * (server.MAX_TEXT_CHARS + 1)})
+    assert r.status_code == 400 and "Text too long" in r.json()["detail"]
+    monkeypatch.setattr(server, "MAX_AUDIO_BYTES", 64)
+    r = c.post("/generate", data={"text": "Hi"}, files={"ref_audio": ("big.wav", b"0" * 65, "audio/wav")})
+    assert r.status_code == 400 and "Audio file too large" in r.json()["detail"]
+    r = c.post("/generate", data={"text": "Hi", "mode": "custom", "speaker": "aiden", "temperature": "0.5", "top_k": "20"})
+    assert r.status_code == 200
+    body = r.json()
+    wav = base64.b64decode(body["audio_b64"])
+    assert wav[:4] == b"RIFF" and struct.unpack("<I", wav[40:44])[0] == 7200 * 2 and body["sample_rate"] == 24000
+    assert body["metrics"]["audio_duration_s"] == pytest.approx(0.3, abs=1e-3) and set(body["metrics"]) == {"total_ms", "audio_duration_s", "rtf"}
+    req = (b0.requests + b1.requests)[-1]
+    assert req.kind == "custom_voice" and req.temperature == 0.5 and req.top_k == 20
+    assert c.app.state.dispatcher.in_flight == [0, 0]
+    failing = TestClient(server.create_app([StubBackend(fail=True)], VOICES, "alloy"))
+    assert failing.post("/generate", data={"text": "Hi"}).status_code == 500
+
+
+def test_status_lists_preset_voices(client):
+    c, *_ = client
+    st = c.get("/status").json()
+    assert st["loaded"] is True and st["queue_depth"] == 0 and st["healthy"] == [True, True]
+    assert st["preset_refs"] == [{"id": "alloy", "label": "alloy", "ref_text": "hi"}]
