@@ -736,8 +736,8 @@ class CodecStream:
 
 
 class SpeechTokenizer:
-    """`model.speech_tokenizer` surface the reference uses: `.decode({"audio_codes": [B,T,Q]}) -> ([wav], sr)` and
-    `.sample_rate` (model.py:56-58, :642)."""
+    """`model.speech_tokenizer` surface the reference uses: `.decode({"audio_codes": [B,T,Q]}) -> ([wav], sr)` (model.py:642), the
+    list form `.decode([{"audio_codes": [T,Q]}, ...])` of its examples, and `.sample_rate` (model.py:56-58)."""
 
     def __init__(self, decoder: CodecDecoder):
         self.decoder = decoder
@@ -748,6 +748,11 @@ class SpeechTokenizer:
         return cls(CodecDecoder(cfg, init_codec_synthetic(cfg, seed=seed), device))
 
     def decode(self, inputs) -> Tuple[List[torch.Tensor], int]:
+        if isinstance(inputs, (list, tuple)):  # [{"audio_codes": [T, Q]}, ...]: the form of examples/generate_with_embedding.py:104
+            out: List[torch.Tensor] = []
+            for item in inputs:
+                out.extend(self.decode(item)[0])
+            return out, self.sample_rate
         codes = inputs["audio_codes"] if isinstance(inputs, dict) else inputs
         skip = int(inputs.get("skip_samples", 0)) if isinstance(inputs, dict) else 0  # extension: see CodecDecoder.decode
         if codes.dim() == 2:

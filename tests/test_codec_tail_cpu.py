@@ -64,3 +64,30 @@ def test_tail_starts_save_most_of_a_streaming_window():
     dec0, tconv, units, fin = vocoder_tail_starts(rows0, rates, skip)
     assert fin == skip and dec0 >= 80          # of 132 rows (row 100 = first kept frame; the reach is ~3.5 frames)
     assert units[-1][0] > 0.7 * n              # last block (the most expensive one) starts near the kept samples
+
+
+def test_speech_tokenizer_accepts_the_dict_batch_and_list_forms():
+    """`speech_tokenizer.decode` is called with {"audio_codes": [B, T, Q]} by the reference's model (model.py:642) and with a list of
+    {"audio_codes": [T, Q]} by its examples (examples/generate_with_embedding.py:98): both give one waveform per item."""
+    import types
+
+    import torch
+
+    from qwen3_tts_cuda_graphs_b200.codec import SpeechTokenizer
+
+    class Dec:
+        cfg = types.SimpleNamespace(sample_rate=24000)
+
+        def decode(self, codes, skip_samples=0):
+            assert codes.dim() == 2
+            return codes[:, 0].float().repeat_interleave(4)[skip_samples:]
+
+    tok = SpeechTokenizer(Dec())
+    a, b = torch.arange(6).reshape(3, 2), torch.arange(10, 14).reshape(2, 2)
+    wavs, sr = tok.decode({"audio_codes": a.unsqueeze(0)})
+    assert sr == 24000 and len(wavs) == 1 and wavs[0].shape == (12,)
+    wavs, sr = tok.decode([{"audio_codes": a}, {"audio_codes": b}])
+    assert sr == 24000 and [w.shape[0] for w in wavs] == [12, 8] and wavs[1][0] == 10
+    wavs, _ = tok.decode({"audio_codes": a, "skip_samples": 4})
+    assert wavs[0].shape == (8,)
+    assert tok.decode(a)[0][0].shape == (12,)
