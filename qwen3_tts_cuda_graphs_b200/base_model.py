@@ -329,6 +329,12 @@ class Qwen3TTSBaseModel:
         self.device = engine.device
         self.model = InnerModel(cfg, Talker(engine, arena, cfg), speech_tokenizer)
 
+    @property
+    def speech_tokenizer(self):
+        """The wrapper level also hands out the codec (`model.model.speech_tokenizer.decode(...)` in
+        examples/generate_with_embedding.py:98); the reference's own code reaches it one level down (model.py:56-58, :642)."""
+        return self.model.speech_tokenizer
+
     # ---- construction -------------------------------------------------------------------------
     @classmethod
     def from_pretrained(cls, model_name: str, device_map="cuda", torch_dtype=torch.bfloat16, attn_implementation="sdpa",

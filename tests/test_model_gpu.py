@@ -229,3 +229,35 @@ def test_streaming_with_stateful_codec_equals_non_streaming_audio(base, ref_wav,
     got = np.concatenate(chunks)
     assert got.shape == full[0].shape
     assert np.array_equal(got, full[0])
+
+
+def test_reference_example_flow_with_a_saved_speaker_embedding(base, ref_wav, tmp_path):
+    """examples/extract_speaker.py + examples/generate_with_embedding.py line by line: x-vector saved to a .pt file, loaded back
+    into a voice_clone_prompt dict, prompt built with `_build_talker_inputs_local`, `fast_generate` called positionally,
+    `speech_tokenizer.decode` with the list form — same codes and audio as `generate_voice_clone(xvec_only=True)`."""
+    from qwen3_tts_cuda_graphs_b200.generate import fast_generate
+
+    items = base.model.create_voice_clone_prompt(ref_audio=ref_wav, ref_text="", x_vector_only_mode=True)  # extract_speaker.py:32-38
+    path = str(tmp_path / "speaker.pt")
+    torch.save(items[0].ref_spk_embedding.cpu(), path)
+    spk_emb = torch.load(path, weights_only=True).to("cuda:0")                                              # generate_with_embedding.py:29
+    vcp = dict(ref_code=[None], ref_spk_embedding=[spk_emb], x_vector_only_mode=[True], icl_mode=[False])
+    input_ids = base.model._tokenize_texts([base.model._build_assistant_text(TEXT)])
+    tie, tam, tth, tpe = base._build_talker_inputs_local(
+        m=base.model.model, input_ids=input_ids, ref_ids=[None], voice_clone_prompt=vcp, languages=["English"], speakers=None,
+        non_streaming_mode=False)
+    base._warmup(tie.shape[1])
+    talker, config = base.model.model.talker, base.model.model.config.talker_config
+    base.predictor_graph.do_sample = False
+    try:
+        talker.rope_deltas = None
+        codec_ids, timing = fast_generate(talker, tie, tam, tth, tpe, config, base.predictor_graph, base.talker_graph,
+                                          temperature=0.9, top_k=50, do_sample=False, max_new_tokens=20)
+        assert codec_ids.shape == (20, 16) and timing["steps"] == 20 and timing["ms_per_step"] > 0
+        wavs, sr = base.model.speech_tokenizer.decode([{"audio_codes": codec_ids.to(base.device)}])
+        assert sr == 24000 and len(wavs) == 1
+        audio, _ = base.generate_voice_clone(TEXT, "English", ref_wav, "", xvec_only=True, non_streaming_mode=False,
+                                             do_sample=False, max_new_tokens=20)
+        assert np.array_equal(wavs[0].flatten().float().cpu().numpy(), audio[0])
+    finally:
+        base.predictor_graph.do_sample = True
