@@ -341,7 +341,14 @@ def load_voices(args) -> (Dict[str, dict], str):
     sys.exit(1)
 
 
-def build_backends(model: str, gpus: int, max_concurrent: int, chunk_frames: int, max_seq_len: int = 2048):
+def replica_devices(gpus: int, device: str = "cuda") -> List[str]:
+    """--gpus N -> cuda:0 .. cuda:N-1; one replica may be placed with the reference's --device flag ("cuda" = cuda:0, "cuda:3")."""
+    if gpus <= 1:
+        return [device if ":" in device else "cuda:0"]
+    return [f"cuda:{g}" for g in range(gpus)]
+
+
+def build_backends(model: str, gpus: int, max_concurrent: int, chunk_frames: int, max_seq_len: int = 2048, device: str = "cuda"):
     """One model replica + scheduler per GPU."""
     import torch
 
@@ -349,8 +356,8 @@ def build_backends(model: str, gpus: int, max_concurrent: int, chunk_frames: int
     from .serving import BatchScheduler
 
     out = []
-    for g in range(gpus):
-        tts = FasterQwen3TTS.from_pretrained(model, device=f"cuda:{g}", dtype=torch.bfloat16, max_seq_len=max_seq_len,
+    for dev in replica_devices(gpus, device):
+        tts = FasterQwen3TTS.from_pretrained(model, device=dev, dtype=torch.bfloat16, max_seq_len=max_seq_len,
                                              max_streams=max_concurrent)
         out.append(BatchScheduler(tts, chunk_frames=chunk_frames, max_concurrent=max_concurrent).start())
     return out
@@ -385,7 +392,8 @@ def main(argv=None):
     p.add_argument("--language", default=os.environ.get("QWEN_TTS_LANGUAGE", "Auto"))
     p.add_argument("--host", default="0.0.0.0")
     p.add_argument("--port", type=int, default=8000)
-    p.add_argument("--gpus", type=int, default=1, help="replicas, one per GPU")
+    p.add_argument("--device", default="cuda", help="Torch device of a single replica (default: cuda)")
+    p.add_argument("--gpus", type=int, default=1, help="replicas, one per GPU (cuda:0 .. cuda:N-1)")
     p.add_argument("--max-concurrent", type=int, default=16, help="lock-step streams per GPU")
     p.add_argument("--chunk-frames", type=int, default=8, help="frames per launch = streaming granularity (8 frames = 0.64 s)")
     p.add_argument("--no-warmup", action="store_true", help="open the port at once; the first requests then pay for plan building")
@@ -394,7 +402,7 @@ def main(argv=None):
     voices, default_voice = load_voices(args)
     import uvicorn
 
-    backends = build_backends(args.model, args.gpus, args.max_concurrent, args.chunk_frames)
+    backends = build_backends(args.model, args.gpus, args.max_concurrent, args.chunk_frames, device=args.device)
     if not args.no_warmup:
         logger.info("Warm-up: %.1f s", warm_up(backends, voices))
     app = create_app(backends, voices, default_voice, sample_rate=backends[0].tts.sample_rate)

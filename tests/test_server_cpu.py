@@ -212,3 +212,8 @@ def test_status_lists_preset_voices(client):
     st = c.get("/status").json()
     assert st["loaded"] is True and st["queue_depth"] == 0 and st["healthy"] == [True, True]
     assert st["preset_refs"] == [{"id": "alloy", "label": "alloy", "ref_text": "hi"}]
+
+
+def test_replica_placement():
+    assert server.replica_devices(1) == ["cuda:0"] and server.replica_devices(1, "cuda:3") == ["cuda:3"]
+    assert server.replica_devices(4, "cuda:3") == ["cuda:0", "cuda:1", "cuda:2", "cuda:3"]
