@@ -83,17 +83,27 @@ class RequestHandle:
     def cancel(self):
         self.cancelled = True
 
-    def __iter__(self) -> Iterator[Tuple[np.ndarray, int, dict]]:
+    def chunks(self, timeout: Optional[float] = None) -> Iterator[Tuple[np.ndarray, int, dict]]:
+        """The utterance's chunks as they arrive; `timeout` (seconds, for the whole utterance) raises TimeoutError and cancels
+        the request, so its slot is freed at the next chunk boundary."""
+        deadline = None if timeout is None else time.monotonic() + timeout
         while True:
-            item = self.q.get()
+            try:
+                item = self.q.get(timeout=None if deadline is None else max(0.0, deadline - time.monotonic()))
+            except queue.Empty:
+                self.cancel()
+                raise TimeoutError(f"request {self.id}: no result within {timeout} s") from None
             if item is _DONE:
                 return
             if isinstance(item, BaseException):
                 raise item
             yield item
 
+    def __iter__(self) -> Iterator[Tuple[np.ndarray, int, dict]]:
+        return self.chunks()
+
     def result(self, timeout: Optional[float] = None) -> Tuple[np.ndarray, int]:
-        parts = [a for a, _, _ in self]
+        parts = [a for a, _, _ in self.chunks(timeout)]
         if not parts:
             return np.zeros(1, dtype=np.float32), self._sr  # model.py:630-632: empty generation -> one zero sample
         return np.concatenate(parts), self._sr

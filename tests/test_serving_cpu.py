@@ -298,3 +298,16 @@ def test_stop_then_start_serves_again():
     _audio_ok(b, 9)
     sched.stop()
     assert sched.healthy
+
+
+def test_result_timeout_raises_and_cancels():
+    eng = FakeEngine(max_streams=1, frame_sleep=0.002)
+    tts = FakeTTS(eng)
+    with BatchScheduler(tts, chunk_frames=8) as sched:
+        slow = sched.submit(_req(1, 10 ** 5))
+        with pytest.raises(TimeoutError):
+            slow.result(timeout=0.2)
+        assert slow.cancelled
+        nxt = sched.submit(_req(2, 8))  # the only slot is free again at the next chunk boundary
+        nxt.id_key = 2
+        _audio_ok(nxt, 8)
