@@ -32,14 +32,14 @@ from typing import Dict, List, Optional
 
 import numpy as np
 from fastapi import FastAPI, File, Form, HTTPException, UploadFile  # module level: the endpoints' annotations are resolved by name
-from fastapi.responses import JSONResponse, StreamingResponse
+from fastapi.responses import JSONResponse, Response, StreamingResponse
 from pydantic import BaseModel
 
 from .serving import TTSRequest
 
 logger = logging.getLogger(__name__)
 
-CONTENT_TYPES = {"wav": "audio/wav", "pcm": "audio/pcm"}
+CONTENT_TYPES = {"wav": "audio/wav", "pcm": "audio/pcm", "mp3": "audio/mpeg"}
 MAX_TEXT_CHARS = 1000                 # demo/server.py:173
 MAX_AUDIO_BYTES = 10 * 1024 * 1024    # demo/server.py:175 (about one minute of 44.1 kHz stereo 16-bit WAV)
 AUDIO_TOO_LARGE = ("Audio file too large ({size_mb:.1f} MB). Voice cloning works best with short clips under 1 minute — "
@@ -79,6 +79,23 @@ def wav_header(sample_rate: int, data_len: int = 0xFFFFFFFF) -> bytes:
 def to_wav_bytes(pcm: np.ndarray, sample_rate: int) -> bytes:
     raw = to_pcm16(pcm)
     return wav_header(sample_rate, len(raw)) + raw
+
+
+def mp3_encoder():
+    """pydub's AudioSegment (needs ffmpeg) or the reference's 400 (examples/openai_server.py:121-130).  Asked for BEFORE the utterance
+    is generated, so a server without pydub refuses at once instead of after the decode."""
+    try:
+        from pydub import AudioSegment
+    except ImportError:
+        raise HTTPException(status_code=400, detail="response_format='mp3' requires pydub: pip install pydub")
+    return AudioSegment
+
+
+def to_mp3_bytes(pcm: np.ndarray, sample_rate: int, segment_cls=None) -> bytes:
+    segment = (segment_cls or mp3_encoder())(to_pcm16(pcm), frame_rate=sample_rate, sample_width=2, channels=1)
+    buf = io.BytesIO()
+    segment.export(buf, format="mp3")
+    return buf.getvalue()
 
 
 class SpeechRequest(BaseModel):  # examples/openai_server.py:78-83
@@ -190,16 +207,25 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
             raise HTTPException(status_code=400, detail="'input' text is empty")
         voice_cfg = resolve_voice(req.voice)
         fmt = req.response_format.lower()
-        if fmt == "mp3":
-            raise HTTPException(status_code=400, detail="response_format='mp3' needs pydub + ffmpeg, which this build does not ship. Use: wav, pcm")
         if fmt not in CONTENT_TYPES:
-            raise HTTPException(status_code=400, detail=f"response_format {fmt!r} not supported. Use: wav, pcm")
+            raise HTTPException(status_code=400, detail=f"response_format {fmt!r} not supported. Use: wav, pcm, mp3")
+        segment_cls = mp3_encoder() if fmt == "mp3" else None
         try:
             handle = disp.submit(_request_for(voice_cfg, req.input))
         except ValueError as e:
             raise HTTPException(status_code=400, detail=str(e))
         except RuntimeError as e:  # BackendUnavailable, or the chosen replica failed between the check and the submit
             raise HTTPException(status_code=503, detail=str(e))
+
+        if fmt == "mp3":  # the whole utterance, then one encode (examples/openai_server.py:242-259)
+            parts, sr = [], sample_rate
+            try:
+                async for audio, sr, _info in chunks_of(handle):
+                    parts.append(audio)
+            except Exception as e:
+                raise HTTPException(status_code=500, detail=str(e))
+            audio = np.concatenate(parts) if parts else np.zeros(1, dtype=np.float32)
+            return Response(content=to_mp3_bytes(audio, sr, segment_cls), media_type=CONTENT_TYPES[fmt])
 
         async def audio_stream():
             if fmt == "wav":

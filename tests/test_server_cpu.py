@@ -81,7 +81,8 @@ def test_errors_mirror_the_reference(client):
     c, *_ = client
     assert c.post("/v1/audio/speech", json={"input": "   ", "voice": "alloy"}).status_code == 400
     assert c.post("/v1/audio/speech", json={"input": "x", "voice": "alloy", "response_format": "flac"}).status_code == 400
-    assert c.post("/v1/audio/speech", json={"input": "x", "voice": "alloy", "response_format": "mp3"}).status_code == 400
+    r = c.post("/v1/audio/speech", json={"input": "x", "voice": "alloy", "response_format": "mp3"})
+    assert r.status_code == 400 and "requires pydub" in r.json()["detail"]  # examples/openai_server.py:126-129 (pydub is not in this image)
     # unknown voice falls back to the default one (examples/openai_server.py:150-157) ...
     assert c.post("/v1/audio/speech", json={"input": "x", "voice": "nobody"}).status_code == 200
     # ... and is a 400 when there is no default
@@ -217,3 +218,25 @@ def test_status_lists_preset_voices(client):
 def test_replica_placement():
     assert server.replica_devices(1) == ["cuda:0"] and server.replica_devices(1, "cuda:3") == ["cuda:3"]
     assert server.replica_devices(4, "cuda:3") == ["cuda:0", "cuda:1", "cuda:2", "cuda:3"]
+
+
+def test_mp3_is_one_encode_of_the_whole_utterance_when_pydub_exists(client, monkeypatch):
+    """examples/openai_server.py:242-259 with a stand-in for pydub.AudioSegment (pydub + ffmpeg are not in this image)."""
+    import sys
+    import types
+
+    seen = {}
+
+    class Segment:
+        def __init__(self, raw, frame_rate, sample_width, channels):
+            seen.update(n=len(raw), frame_rate=frame_rate, sample_width=sample_width, channels=channels)
+
+        def export(self, buf, format):
+            buf.write(b"ID3" + format.encode())
+
+    monkeypatch.setitem(sys.modules, "pydub", types.SimpleNamespace(AudioSegment=Segment))
+    c, b0, b1 = client
+    r = c.post("/v1/audio/speech", json={"input": "Hello", "voice": "alloy", "response_format": "mp3"})
+    assert r.status_code == 200 and r.headers["content-type"] == "audio/mpeg" and r.content == b"ID3mp3"
+    assert seen == dict(n=7200 * 2, frame_rate=24000, sample_width=2, channels=1)
+    assert c.app.state.dispatcher.in_flight == [0, 0]
