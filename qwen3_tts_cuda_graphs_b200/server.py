@@ -163,7 +163,8 @@ def _request_for(voice_cfg: dict, text: str, overrides: Optional[dict] = None) -
     return TTSRequest(**kw)
 
 
-def create_app(backends: List[object], voices: Dict[str, dict], default_voice: Optional[str] = None, sample_rate: int = 24000):
+def create_app(backends: List[object], voices: Dict[str, dict], default_voice: Optional[str] = None, sample_rate: int = 24000,
+               model_name: Optional[str] = None):
     app = FastAPI(title="qwen3-tts B200 engine: OpenAI-compatible API")
     disp = Dispatcher(backends)
     app.state.dispatcher = disp
@@ -275,18 +276,44 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
     async def status():
         """demo/server.py:251-277, for the model(s) this server was started with (no load / unload at run time)."""
         tts = getattr(disp.backends[0], "tts", None)
-        model_type, speakers, name = None, [], None
+        model_type, speakers, name = None, [], model_name
         if tts is not None:
             try:
                 model_type = tts.model.model.tts_model_type
                 speakers = list(tts.model.get_supported_speakers() or [])
-                name = getattr(tts.model, "name", None)
             except Exception:
                 speakers = []
         return {"loaded": True, "model": name, "loading": False, "model_type": model_type, "speakers": speakers,
                 "transcription_available": False,
                 "preset_refs": [{"id": k, "label": k, "ref_text": v.get("ref_text", "")} for k, v in voices.items() if v.get("ref_audio")],
                 "queue_depth": sum(disp.in_flight), "backends": len(disp.backends), "healthy": disp.healthy()}
+
+    @app.get("/preset_ref/{preset_id}")
+    async def preset_ref(preset_id: str):
+        """demo/server.py:279-290: a configured voice's reference clip, for the page's player."""
+        cfg = voices.get(preset_id)
+        if not cfg or not cfg.get("ref_audio"):
+            raise HTTPException(status_code=404, detail="Preset not found")
+        try:
+            with open(cfg["ref_audio"], "rb") as f:
+                audio_b64 = base64.b64encode(f.read()).decode()
+        except OSError:
+            raise HTTPException(status_code=404, detail="Preset audio not found")
+        return {"id": preset_id, "label": preset_id, "filename": os.path.basename(str(cfg["ref_audio"])),
+                "ref_text": cfg.get("ref_text", ""), "audio_b64": audio_b64}
+
+    @app.post("/load")
+    async def load_model(model_id: str = Form(...)):
+        """demo/server.py:293-329 switches models at run time; here the replicas are built once at start-up (weights packed into
+        per-GPU arenas, launch plans warmed), so asking for the served model succeeds and anything else says how to get it."""
+        if model_name is None or model_id == model_name:
+            return {"status": "already_loaded", "model": model_name or model_id}
+        raise HTTPException(status_code=400, detail=f"This server serves {model_name!r}; restart it with --model {model_id} to switch.")
+
+    @app.post("/transcribe")
+    async def transcribe_audio(audio: UploadFile = File(...)):
+        """demo/server.py:225-248 needs the optional nano-parakeet model; without it the reference answers 503 too."""
+        raise HTTPException(status_code=503, detail="Transcription model not loaded")
 
     @app.post("/generate/stream")
     async def generate_stream(text: str = Form(...), language: str = Form("English"), mode: str = Form("voice_clone"),
@@ -431,7 +458,7 @@ def main(argv=None):
     backends = build_backends(args.model, args.gpus, args.max_concurrent, args.chunk_frames, device=args.device)
     if not args.no_warmup:
         logger.info("Warm-up: %.1f s", warm_up(backends, voices))
-    app = create_app(backends, voices, default_voice, sample_rate=backends[0].tts.sample_rate)
+    app = create_app(backends, voices, default_voice, sample_rate=backends[0].tts.sample_rate, model_name=args.model)
     logger.info("Server listening on http://%s:%d (%d GPU(s), %d streams each)", args.host, args.port, args.gpus, args.max_concurrent)
     try:
         uvicorn.run(app, host=args.host, port=args.port)

@@ -240,3 +240,18 @@ def test_mp3_is_one_encode_of_the_whole_utterance_when_pydub_exists(client, monk
     assert r.status_code == 200 and r.headers["content-type"] == "audio/mpeg" and r.content == b"ID3mp3"
     assert seen == dict(n=7200 * 2, frame_rate=24000, sample_width=2, channels=1)
     assert c.app.state.dispatcher.in_flight == [0, 0]
+
+
+def test_demo_side_endpoints(tmp_path):
+    clip = tmp_path / "alloy.wav"
+    clip.write_bytes(b"RIFFxxxxWAVE")
+    voices = {"alloy": {"ref_audio": str(clip), "ref_text": "hi"}, "aiden": {"speaker": "aiden"}}
+    c = TestClient(server.create_app([StubBackend()], voices, "alloy", model_name="synthetic://0.6B-Base"))
+    r = c.get("/preset_ref/alloy").json()
+    assert r["filename"] == "alloy.wav" and r["ref_text"] == "hi" and base64.b64decode(r["audio_b64"]) == b"RIFFxxxxWAVE"
+    assert c.get("/preset_ref/aiden").status_code == 404 and c.get("/preset_ref/nobody").status_code == 404
+    assert c.post("/load", data={"model_id": "synthetic://0.6B-Base"}).json()["model"] == "synthetic://0.6B-Base"
+    r = c.post("/load", data={"model_id": "Qwen/Qwen3-TTS-12Hz-1.7B-Base"})
+    assert r.status_code == 400 and "--model" in r.json()["detail"]
+    assert c.post("/transcribe", files={"audio": ("a.wav", b"x", "audio/wav")}).status_code == 503
+    assert c.get("/status").json()["model"] == "synthetic://0.6B-Base"
