@@ -10,5 +10,6 @@ from qwen3_tts_cuda_graphs_b200.generate import fast_generate  # noqa: F401
 from qwen3_tts_cuda_graphs_b200.streaming import fast_generate_streaming  # noqa: F401
 from qwen3_tts_cuda_graphs_b200.sampling import apply_repetition_penalty, sample_logits  # noqa: F401
 
+__version__ = "0.2.4"  # the reference release whose API surface this package mirrors (faster_qwen3_tts/__init__.py:6)
 __all__ = ["FasterQwen3TTS", "PredictorGraph", "TalkerGraph", "fast_generate", "fast_generate_streaming",
            "sample_logits", "apply_repetition_penalty"]
