@@ -34,6 +34,7 @@ import numpy as np
 from fastapi import FastAPI, File, Form, HTTPException, UploadFile  # module level: the endpoints' annotations are resolved by name
 from fastapi.responses import JSONResponse, Response, StreamingResponse
 from pydantic import BaseModel
+from starlette.background import BackgroundTask
 
 from .serving import TTSRequest
 
@@ -177,8 +178,19 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
             return voices[default_voice]
         raise HTTPException(status_code=400, detail=f"Voice {name!r} is not configured. Available voices: {list(voices.keys())}")
 
+    def settle(handle):
+        """Once per request, whichever comes first — the end of its stream, or the end of the response (a client that went away
+        before the first byte never starts the stream): cancel what is still decoding (the slot is freed at the next chunk
+        boundary) and give the replica's in-flight count back."""
+        if getattr(handle, "_settled", False):
+            return
+        handle._settled = True
+        if getattr(handle, "finish_reason", None) is None and hasattr(handle, "cancel"):
+            handle.cancel()
+        disp.release(getattr(handle, "_backend_index", 0))
+
     async def chunks_of(handle):
-        """Pull a handle's chunks without blocking the event loop; releases the backend slot when the stream ends."""
+        """Pull a handle's chunks without blocking the event loop."""
         loop = asyncio.get_event_loop()
         it = iter(handle)
         try:
@@ -188,9 +200,7 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
                     return
                 yield item
         finally:
-            if getattr(handle, "finish_reason", None) is None and hasattr(handle, "cancel"):
-                handle.cancel()  # client went away mid-stream: free the slot at the next chunk boundary
-            disp.release(getattr(handle, "_backend_index", 0))
+            settle(handle)
 
     @app.get("/health")
     async def health():
@@ -234,7 +244,7 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
             async for audio, _sr, _info in chunks_of(handle):
                 yield to_pcm16(audio)
 
-        return StreamingResponse(audio_stream(), media_type=CONTENT_TYPES[fmt])
+        return StreamingResponse(audio_stream(), media_type=CONTENT_TYPES[fmt], background=BackgroundTask(settle, handle))
 
     async def demo_request(text, language, mode, ref_text, speaker, instruct, xvec_only, temperature, top_k, repetition_penalty,
                            voice, ref_preset, ref_audio) -> TTSRequest:
@@ -349,7 +359,8 @@ def create_app(backends: List[object], voices: Dict[str, dict], default_voice: O
             except Exception as e:  # generation errors travel in-band, like the demo's
                 yield f"data: {json.dumps({'type': 'error', 'message': str(e)})}\n\n"
 
-        return StreamingResponse(sse(), media_type="text/event-stream", headers={"Cache-Control": "no-cache", "X-Accel-Buffering": "no"})
+        return StreamingResponse(sse(), media_type="text/event-stream", headers={"Cache-Control": "no-cache", "X-Accel-Buffering": "no"},
+                                 background=BackgroundTask(settle, handle))
 
     @app.post("/generate")
     async def generate_non_streaming(text: str = Form(...), language: str = Form("English"), mode: str = Form("voice_clone"),

@@ -255,3 +255,28 @@ def test_demo_side_endpoints(tmp_path):
     assert r.status_code == 400 and "--model" in r.json()["detail"]
     assert c.post("/transcribe", files={"audio": ("a.wav", b"x", "audio/wav")}).status_code == 503
     assert c.get("/status").json()["model"] == "synthetic://0.6B-Base"
+
+
+def test_a_response_that_never_streams_still_gives_the_slot_back():
+    """A client that goes away before the first byte never starts the body generator; the response's background task settles
+    the request (cancel + in-flight count) all the same."""
+    import asyncio
+
+    class NeverEnding:
+        def __init__(self):
+            self.handles = []
+
+        def submit(self, req):
+            h = RequestHandle(req, len(self.handles))  # nothing is ever put on its queue
+            self.handles.append(h)
+            return h
+
+    b = NeverEnding()
+    app = server.create_app([b], VOICES, "alloy")
+    route = next(r for r in app.routes if getattr(r, "path", "") == "/v1/audio/speech")
+    resp = asyncio.run(route.endpoint(server.SpeechRequest(input="Hello", voice="alloy")))
+    assert app.state.dispatcher.in_flight == [1]
+    asyncio.run(resp.background())  # what Starlette runs when the response ends, streamed or not
+    assert app.state.dispatcher.in_flight == [0] and b.handles[0].cancelled
+    asyncio.run(resp.background())  # idempotent
+    assert app.state.dispatcher.in_flight == [0]
