@@ -280,3 +280,36 @@ def test_a_response_that_never_streams_still_gives_the_slot_back():
     assert app.state.dispatcher.in_flight == [0] and b.handles[0].cancelled
     asyncio.run(resp.background())  # idempotent
     assert app.state.dispatcher.in_flight == [0]
+
+
+def test_http_front_on_the_real_scheduler_with_engine_doubles():
+    """server.create_app over serving.BatchScheduler itself (engine / model doubles of test_serving_cpu.py): two concurrent HTTP
+    requests share launches, the WAV body holds every frame once and in order, the slots and in-flight counts come back."""
+    import threading
+
+    from test_serving_cpu import SPF, FakeEngine, FakeTTS
+
+    from qwen3_tts_cuda_graphs_b200.serving import BatchScheduler
+
+    eng = FakeEngine(max_streams=4, frame_sleep=0.001)
+    voices = {"alloy": {"ref_audio": "v.wav", "language": "English", "max_new_tokens": 240, "do_sample": False}}
+    with BatchScheduler(FakeTTS(eng), chunk_frames=8) as sched:
+        c = TestClient(server.create_app([sched], voices, "alloy"))
+        out = {}
+
+        def post(key):
+            out[key] = c.post("/v1/audio/speech", json={"input": f"{key},1000000000", "voice": "alloy", "response_format": "pcm"})
+
+        ts = [threading.Thread(target=post, args=(k,)) for k in (5, 6)]
+        [t.start() for t in ts]
+        [t.join(60) for t in ts]
+        for k in (5, 6):
+            assert out[k].status_code == 200
+            pcm = np.frombuffer(out[k].content, dtype="<i2")
+            assert pcm.size == 240 * SPF  # 30 launches of 8 ms each: the two requests overlap whatever the threads' start skew
+            # FakeDecoder: frame i -> 1920 samples of value i (clipped to int16 full scale by the PCM conversion)
+            assert np.array_equal(pcm[::SPF], np.clip(np.arange(240) * 32768.0, -32768, 32767).astype(np.int16))
+        assert c.get("/health").json() == {"status": "ok", "model_loaded": True, "backends": 1, "healthy": [True], "in_flight": [0]}
+        r = c.post("/generate", data={"text": "9,5", "voice": "alloy"})  # EOS after five frames
+        assert r.status_code == 200 and r.json()["metrics"]["audio_duration_s"] == pytest.approx(5 * 0.08)
+    assert any(len(live) == 2 for _, live, _ in eng.launches)
