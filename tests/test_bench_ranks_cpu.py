@@ -42,3 +42,32 @@ def test_single_rank_is_identity():
 
     times, totals = bench.aggregate_over_ranks([12.5], [3.0], "cpu", 1)
     assert times == [12.5] and totals == [3.0]
+
+
+def test_reference_arm_prints_the_contract_line_on_rank_0_only():
+    """`bench.py --impl reference` (the CPU arm): rank 0 prints ONE JSON line with the contract's keys, the same metric / unit /
+    config keys as the B200 arm, a cpu_baseline describing this run and an e2e equal to the line's value; other ranks exit 0
+    without work.  Tiny preset, one 8-frame step: the arm's code path, not its number."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "tiny-Base", "--steps", "1", "--warmup", "0",
+           "--cpu-frames", "8", "--gpus", "2"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r0 = subprocess.run(cmd, env=dict(env, RANK="0", WORLD_SIZE="2"), capture_output=True, text=True, timeout=300)
+    assert r0.returncode == 0, r0.stderr[-2000:]
+    lines = [l for l in r0.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "audio_seconds_per_second" and d["unit"] == "audio-s/s" and d["n_gpus"] == 2
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"] and "model" not in d["config"] and d["config"]["reference_sample"]["frames_per_step"] == 8
+    r1 = subprocess.run(cmd, env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
