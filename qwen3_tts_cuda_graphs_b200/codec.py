@@ -748,7 +748,7 @@ class SpeechTokenizer:
         return cls(CodecDecoder(cfg, init_codec_synthetic(cfg, seed=seed), device))
 
     def decode(self, inputs) -> Tuple[List[torch.Tensor], int]:
-        if isinstance(inputs, (list, tuple)):  # [{"audio_codes": [T, Q]}, ...]: the form of examples/generate_with_embedding.py:104
+        if isinstance(inputs, (list, tuple)):  # [{"audio_codes": [T, Q]}, ...]: the form of the reference's examples/generate_with_embedding.py:98
             out: List[torch.Tensor] = []
             for item in inputs:
                 out.extend(self.decode(item)[0])
