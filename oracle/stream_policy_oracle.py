@@ -48,3 +48,13 @@ def stream_decode_policy(chunks: Iterable[np.ndarray], decode: Callable[[np.ndar
             context = (total - first) - fresh
             out = wav[int(round(context * per_frame)):] if context > 0 else wav
         yield out
+
+
+def full_decode_policy(codes: np.ndarray, decode: Callable[[np.ndarray], np.ndarray], ref_codes: Optional[np.ndarray]) -> np.ndarray:
+    """Non-streaming decode, `model.py:634-656`: ICL reference codes go in front of the generated ones (`:636-641`), one decode
+    (`:642`), and the reference's share of the waveform — `int(ref_len / total_len * len(audio))` samples — is cut off (`:645-655`)."""
+    if ref_codes is None:
+        return np.asarray(decode(np.asarray(codes))).reshape(-1)
+    both = np.concatenate([np.asarray(ref_codes), np.asarray(codes)], axis=0)
+    wav = np.asarray(decode(both)).reshape(-1)
+    return wav[int(ref_codes.shape[0] / max(both.shape[0], 1) * len(wav)):]

@@ -112,3 +112,25 @@ def test_the_comparison_notices_a_different_window_or_cut():
         if wd.spf is not None:
             wd.spf = SPF + 1.0 / 25  # one sample too many per 25 context frames
     assert any(a.shape != b.shape for a, b in zip(got, want))
+
+
+@pytest.mark.parametrize("trim_mode", ["right", "both"])
+@pytest.mark.parametrize("ref_frames", [0, 37])
+def test_non_streaming_decode_cuts_the_reference_part_like_the_reference(trim_mode, ref_frames):
+    """`FasterQwen3TTS._decode_full` against the oracle's restatement of model.py:634-656 (tail-only decode of the ICL reference part
+    included: no skipped sample may come out)."""
+    from oracle.stream_policy_oracle import full_decode_policy
+
+    from qwen3_tts_cuda_graphs_b200.model import FasterQwen3TTS
+
+    codes = np.random.default_rng(3).integers(0, 2048, size=(41, 16))
+    ref = np.random.default_rng(4).integers(0, 2048, size=(ref_frames, 16)) if ref_frames else None
+    dec = ToyDecoder(trim_mode)
+    want = full_decode_policy(codes, lambda c: toy_wave(np.asarray(c), dec.trim), ref)
+    self_ = types.SimpleNamespace(_to_numpy=FasterQwen3TTS._to_numpy)
+    inner = types.SimpleNamespace(speech_tokenizer=SpeechTokenizer(dec))
+    got, sr = FasterQwen3TTS._decode_full(self_, inner, torch.from_numpy(codes), None if ref is None else torch.from_numpy(ref))
+    assert sr == 24000 and len(got) == 1 and got[0].dtype == np.float32
+    assert not np.isnan(got[0]).any() and np.array_equal(got[0], want)
+    if trim_mode == "right":
+        assert len(got[0]) == 41 * SPF
