@@ -101,3 +101,46 @@ def test_the_operator_seam_is_single_stream_like_the_reference():
         TalkerGraph(eng, stream_idx=1)                                         # talker_graph.py:46-47: bs = 1 buffers
     with pytest.raises(ValueError):
         PredictorGraph(eng, stream_idx=2)                                      # predictor_graph.py:70-71
+
+
+def test_sampling_wrappers_have_no_cpu_fallback_and_pass_the_reference_arguments_on():
+    """`sampling.py:10-66` signatures: without an engine both entry points refuse (no CPU arithmetic behind them); with one,
+    suppression is applied before the engine call (mask and id list, sampling.py:41-47), the policy carries temperature / top-k /
+    top-p / do_sample, the penalty is a no-op for 1.0 or an empty history (sampling.py:17-18)."""
+    from qwen3_tts_cuda_graphs_b200 import sampling
+
+    sampling.set_default_engine(None)
+    logits = torch.tensor([[0.5, 2.0, -1.0, 3.0]])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sampling.sample_logits(logits, temperature=0.9, top_k=50, top_p=1.0, do_sample=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sampling.apply_repetition_penalty(logits.clone().unsqueeze(0), torch.tensor([1]), 1.1)
+    same = logits.clone()
+    assert sampling.apply_repetition_penalty(same, torch.tensor([1]), 1.0) is same          # penalty 1.0: untouched, no engine needed
+    assert sampling.apply_repetition_penalty(same, torch.tensor([], dtype=torch.long), 1.3) is same
+
+    seen = {}
+
+    class Eng:
+        def sample(self, x, history, pol, eos_id, suppress_eos, draw_index):
+            seen.update(x=x.clone(), history=history, pol=pol, eos_id=eos_id, suppress_eos=suppress_eos, draw_index=draw_index)
+            return torch.tensor([int(torch.argmax(x))])
+
+        def apply_repetition_penalty(self, lg, hist, p):
+            seen.update(rep=(tuple(lg.shape), hist.tolist(), p))
+            return lg
+
+    mask = torch.tensor([False, False, False, True])
+    tok = sampling.sample_logits(logits, temperature=0.7, top_k=5, top_p=0.9, do_sample=False, suppress_mask=mask, suppress_tokens=[1],
+                                 engine=Eng(), seed=11, draw_index=4)
+    assert tok.tolist() == [0]                                                               # ids 3 (mask) and 1 (list) were suppressed
+    assert seen["x"].tolist() == [0.5, float("-inf"), -1.0, float("-inf")] and logits[0, 1] == 2.0   # on a clone (sampling.py:40)
+    p = seen["pol"]
+    assert (p.do_sample, p.top_k, p.top_p, p.temperature, p.seed, p.repetition_penalty) == (False, 5, 0.9, 0.7, 11, 1.0)
+    assert seen["draw_index"] == 4 and seen["history"] is None and seen["suppress_eos"] is False
+    sampling.set_default_engine(Eng())
+    try:
+        sampling.apply_repetition_penalty(logits.clone().unsqueeze(0), torch.tensor([1, 1, 3]), 1.1)
+        assert seen["rep"] == ((1, 1, 4), [1, 1, 3], 1.1)
+    finally:
+        sampling.set_default_engine(None)
