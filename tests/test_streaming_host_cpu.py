@@ -135,3 +135,81 @@ def test_overlapped_mode_launches_ahead_and_restores_the_grid(no_cuda, monkeypat
     eng = EngineDouble(reduced=128)
     out = list(_gen(eng, max_new_tokens=24, chunk_size=8))
     assert all("codes_ready" not in i for _, i in out) and all(g == 0 for _, _, g in [e for e in eng.log if e[0] == "launch"])
+
+
+def test_non_streaming_generate_returns_codes_and_the_reference_timing_keys(no_cuda):
+    """generate.py:205-215: (int64 [T, 16] | None, {prefill_ms, decode_s, steps, ms_per_step, steps_per_s}); one launch for the
+    whole utterance, one status read."""
+    from qwen3_tts_cuda_graphs_b200.generate import fast_generate
+
+    def run(eng, **kw):
+        tg, pg = TalkerGraph(eng), PredictorGraph(eng)
+        H = eng.cfg.talker.hidden_size
+        return fast_generate(types.SimpleNamespace(engine=eng), torch.zeros(1, 14, H), torch.ones(1, 14, dtype=torch.long),
+                             torch.zeros(1, 1, H), torch.zeros(1, 1, H), eng.cfg.talker, pg, tg, seed=3, **kw)
+
+    eng = EngineDouble(eos_at=37)
+    codes, timing = run(eng, max_new_tokens=2048)
+    assert codes.shape == (37, 16) and codes.dtype == torch.int64 and torch.equal(codes[:, 0], torch.arange(37))
+    assert set(timing) == {"prefill_ms", "decode_s", "steps", "ms_per_step", "steps_per_s"} and timing["steps"] == 37
+    assert [e for e in eng.log if e[0] == "launch"] == [("launch", 2048, 0)] and len([e for e in eng.log if e[0] == "status"]) == 1
+    codes, timing = run(EngineDouble(eos_at=0), max_new_tokens=64)
+    assert codes is None and timing["steps"] == 0 and timing["ms_per_step"] == 0                # generate.py:213-215
+    eng = EngineDouble()
+    eng.max_frames = 100
+    codes, _ = run(eng, max_new_tokens=2048)
+    assert codes.shape[0] == 100                                                                 # the engine's frame store bounds the launch
+    with pytest.raises(NotImplementedError):
+        run(EngineDouble(), parity_mode=True)
+
+
+def test_batch_generate_groups_requests_by_what_one_launch_takes(no_cuda):
+    """fast_generate_batch: one launch per engine-full of requests with the wide program (lock-step groups of 16 formed on the
+    device), groups of four otherwise (1.7B dims); every request gets its own codes back, a request that produced nothing None."""
+    from qwen3_tts_cuda_graphs_b200.generate import fast_generate_batch
+
+    class Batched(EngineDouble):
+        def __init__(self, max_streams, lockstep_group):
+            super().__init__()
+            self.max_streams, self.lockstep_group = max_streams, lockstep_group
+            self.frames = {}
+
+        def prefill(self, idx, embeds, n_pad, policy):
+            self.frames[idx] = -int(embeds[0, 0])       # the request's length rides in its first embedding value
+            self.log.append(("prefill", idx, n_pad))
+
+        def decode_frames(self, n_streams, n_frames, policy, sub):
+            self.log.append(("launch", n_streams, n_frames))
+            for s in range(n_streams):
+                self.frames[s] = min(-self.frames[s], n_frames)
+
+        def status(self, idx=0):
+            return types.SimpleNamespace(n_frames=self.frames[idx], done=0, error=0)
+
+        def read_codes(self, idx, first, n):
+            return torch.full((n, 16), idx, dtype=torch.int64)
+
+    def reqs(lengths, pads=0):
+        H = 8
+        out = []
+        for n in lengths:
+            tie = torch.zeros(1, 6, H)
+            tie[0, 0, 0] = n
+            tam = torch.ones(1, 6, dtype=torch.long)
+            tam[0, :pads] = 0
+            out.append((tie, tam, torch.zeros(1, 1, H), torch.zeros(1, 1, H)))
+        return out
+
+    lengths = [5, 0, 9, 3, 7, 2]
+    for max_streams, group, want_launches in ((16, 16, [6]), (4, 16, [4, 2]), (16, 4, [4, 2])):
+        eng = Batched(max_streams, group)
+        tg, pg = TalkerGraph(eng), PredictorGraph(eng)
+        codes, timing = fast_generate_batch(tg, pg, reqs(lengths, pads=2), max_new_tokens=50, seed=5)
+        assert [e[1] for e in eng.log if e[0] == "launch"] == want_launches
+        assert [None if c is None else c.shape[0] for c in codes] == [5, None, 9, 3, 7, 2]
+        assert timing["frames"] == sum(lengths) and {"total_s", "frames", "audio_s_per_s"} <= set(timing)
+        assert all(e[2] == 2 for e in eng.log if e[0] == "prefill")                             # left pads counted from the mask
+    with pytest.raises(RuntimeError, match="Input is too long"):
+        eng = Batched(4, 16)
+        eng.max_seq_len = 5
+        fast_generate_batch(TalkerGraph(eng), PredictorGraph(eng), reqs([3]))
